@@ -1,0 +1,107 @@
+"""ctypes view of include/ebcadrl.h — the C ABI of the B200 hot path.
+
+The product library is eb-cadrl_b200/lib/libebcadrl.so (CUDA, sm_100a).  There is no CPU
+fallback: `load()` raises if the library is missing.  (tests/ load the CPU oracle through
+tests/oracle_backend.py with the same struct definitions; nothing in this package does.)
+"""
+import ctypes
+import os
+
+ABI_VERSION = 1
+
+EVENT_NAMES = ["Nothing", "Danger", "ReachGoal", "CollisionAdult", "CollisionBicycle",
+               "CollisionChild", "CollisionObstacle", "Timeout"]
+EV_NOTHING, EV_DANGER, EV_REACH_GOAL, EV_COLLISION_ADULT, EV_COLLISION_BICYCLE, \
+    EV_COLLISION_CHILD, EV_COLLISION_OBSTACLE, EV_TIMEOUT = range(8)
+
+KIN_HOLONOMIC, KIN_UNICYCLE = 0, 1
+POLICY_ORCA, POLICY_LINEAR = 0, 1
+
+c_i32, c_f64, c_f32 = ctypes.c_int32, ctypes.c_double, ctypes.c_float
+vp = ctypes.c_void_p
+
+
+class EbcConfig(ctypes.Structure):
+    _fields_ = [
+        ("abi_version", c_i32), ("n_episodes", c_i32), ("max_humans", c_i32), ("max_statics", c_i32),
+        ("max_rects", c_i32), ("n_actions", c_i32), ("robot_kinematics", c_i32), ("rotate_theta", c_i32),
+        ("with_agent_type", c_i32), ("robot_visible", c_i32), ("human_policy", c_i32 * 3),
+        ("new_reward", c_i32), ("has_max_goal_distance", c_i32), ("orca_max_neighbors", c_i32),
+        ("time_step", c_f64), ("time_limit", c_f64), ("time_max", c_f64), ("time_good", c_f64),
+        ("max_goal_distance", c_f64), ("success_reward", c_f64),
+        ("collision_penalty_adult", c_f64), ("collision_penalty_bicycle", c_f64),
+        ("collision_penalty_obstacle", c_f64), ("collision_penalty_child", c_f64),
+        ("discomfort_dist_adult", c_f64), ("discomfort_dist_bicycle", c_f64), ("discomfort_dist_child", c_f64),
+        ("discomfort_penalty_factor_adult", c_f64), ("discomfort_penalty_factor_bicycle", c_f64),
+        ("discomfort_penalty_factor_child", c_f64), ("rotation_penalty_factor", c_f64),
+        ("map_size_m", c_f64), ("map_resolution", c_f64), ("gamma", c_f64), ("orca_safety_space", c_f64),
+        ("orca_neighbor_dist", c_f32), ("orca_time_horizon", c_f32),
+    ]
+
+
+class EbcState(ctypes.Structure):
+    _fields_ = [(n, vp) for n in (
+        "hum_pv", "hum_gr", "hum_type", "hum_count", "hum_nv", "stat", "stat_count", "rect", "rect_count",
+        "rob_pv", "rob_gr", "rob_theta", "time")]
+
+
+class EbcLinear(ctypes.Structure):
+    _fields_ = [("weight", vp), ("bias", vp), ("in_dim", c_i32), ("out_dim", c_i32)]
+
+
+class EbcWeights(ctypes.Structure):
+    _fields_ = [("input_dim", c_i32), ("self_state_dim", c_i32), ("with_global_state", c_i32),
+                ("mlp1", EbcLinear * 2), ("mlp2", EbcLinear * 2), ("attention", EbcLinear * 3),
+                ("mlp3", EbcLinear * 4)]
+
+
+# name -> (restype, argtypes) for every entry point include/ebcadrl.h declares for libebcadrl.so
+SIM = vp
+PROTOTYPES = {
+    "ebc_create": (c_i32, [ctypes.POINTER(EbcConfig), c_i32, ctypes.POINTER(SIM)]),
+    "ebc_destroy": (None, [SIM]),
+    "ebc_last_error": (ctypes.c_char_p, [SIM]),
+    "ebc_abi_version": (c_i32, []),
+    "ebc_bind": (c_i32, [SIM, ctypes.POINTER(EbcState)]),
+    "ebc_set_actions": (c_i32, [SIM, vp, c_i32]),
+    "ebc_set_weights": (c_i32, [SIM, ctypes.POINTER(EbcWeights)]),
+    "ebc_orca": (c_i32, [SIM, vp]),
+    "ebc_robot_orca": (c_i32, [SIM, c_f64, vp, vp]),
+    "ebc_lookahead": (c_i32, [SIM, vp, vp, vp, vp, vp]),
+    "ebc_value": (c_i32, [SIM, vp, ctypes.c_int64, vp, vp, vp]),
+    "ebc_select": (c_i32, [SIM, vp, vp, vp, vp, vp, vp]),
+    "ebc_step": (c_i32, [SIM, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "ebc_orca_step": (c_i32, [SIM, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "ebc_transform": (c_i32, [SIM, vp, vp]),
+    "ebc_launch_count": (ctypes.c_int64, [SIM]),
+}
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib", "libebcadrl.so")
+
+
+class EbcError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load(path=None):
+    """dlopen libebcadrl.so and type every symbol.  Fails loudly when it is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise EbcError("CUDA extension %s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback)" % p)
+    lib = ctypes.CDLL(p)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)   # AttributeError if the library does not export the header's symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ebc_abi_version() != ABI_VERSION:
+        raise EbcError("libebcadrl.so ABI %d != %d" % (lib.ebc_abi_version(), ABI_VERSION))
+    if path is None:
+        _lib = lib
+    return lib

@@ -1,0 +1,245 @@
+"""BatchedSim — N independent EB-CADRL episodes advanced at once on one B200.
+
+Host-side owner of the structure-of-arrays episode state (torch tensors on the device,
+borrowed by the C ABI through raw pointers).  All compute is in libebcadrl.so
+(eb-cadrl_b200/csrc); torch is used for device memory and streams only.
+
+The methods map 1:1 onto the reference's hot path:
+    orca()       env.step's per-human policy loop    simulator/env.py:392-405, policy/orca.py:85-157
+    lookahead()  env.onestep_lookahead x A actions    simulator/env.py:207-209, rl/policy/multi_human_rl.py:38-61
+    value()      SARL value network                   rl/policy/sarl.py:38-82
+    select()     reward + gamma^(dt v_pref) V, argmax rl/policy/multi_human_rl.py:72-80
+    step()       env.step(action, update=True)        simulator/env.py:388-466
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import abi
+
+_WEIGHT_KEYS = (["mlp1.0", "mlp1.2"], ["mlp2.0", "mlp2.2"], ["attention.0", "attention.2", "attention.4"],
+                ["mlp3.0", "mlp3.2", "mlp3.4", "mlp3.6"])
+
+
+class CudaBackend(object):
+    """Thin adapter over libebcadrl.so (the only backend this package ships)."""
+    name = "cuda"
+
+    def __init__(self, lib=None):
+        self.lib = lib or abi.load()
+
+    def create(self, cfg, device_index):
+        h = abi.SIM()
+        rc = self.lib.ebc_create(ctypes.byref(cfg), device_index, ctypes.byref(h))
+        if rc != 0:
+            raise abi.EbcError("ebc_create: %s" % self.lib.ebc_last_error(None).decode())
+        return h
+
+    def destroy(self, h):
+        self.lib.ebc_destroy(h)
+
+    def last_error(self, h):
+        return self.lib.ebc_last_error(h).decode()
+
+    def call(self, name, h, *args, stream=None):
+        fn = getattr(self.lib, "ebc_" + name)
+        if name in ("bind", "set_actions", "set_weights"):
+            rc = fn(h, *args)
+        else:
+            rc = fn(h, *args, stream)
+        if rc != 0:
+            raise abi.EbcError("ebc_%s failed (%d): %s" % (name, rc, self.last_error(h)))
+
+    def launch_count(self, h):
+        return int(self.lib.ebc_launch_count(h))
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class BatchedSim(object):
+    def __init__(self, cfg, n_episodes, max_humans, max_statics=0, max_rects=0, n_actions=81,
+                 device="cuda:0", backend=None):
+        self.cfg = cfg
+        self.N, self.Hmax, self.Smax, self.Rmax, self.A = n_episodes, max_humans, max_statics, max_rects, n_actions
+        self.n = max_humans + max_statics
+        self.D = cfg.D
+        self.device = torch.device(device)
+        if backend is None:
+            if self.device.type != "cuda":
+                raise abi.EbcError("BatchedSim needs a CUDA device: the hot path has no CPU fallback")
+            backend = CudaBackend()
+        self.be = backend
+        self._abi_cfg = cfg.to_abi(n_episodes, max_humans, max_statics, max_rects, n_actions)
+        dev_index = self.device.index if self.device.type == "cuda" and self.device.index is not None else 0
+        if self.device.type == "cuda":
+            torch.cuda.set_device(self.device)
+        self.h = self.be.create(self._abi_cfg, dev_index)
+        N, H, S, R, A = self.N, self.Hmax, max(self.Smax, 1), max(self.Rmax, 1), self.A
+        z = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype, device=self.device)  # noqa: E731
+        self.hum_pv = z(N, H, 4)
+        self.hum_gr = z(N, H, 4)
+        self.hum_type = z(N, H, dtype=torch.uint8)
+        self.hum_count = z(N, dtype=torch.int32)
+        self.hum_nv = z(N, H, 2)
+        self.stat = z(N, S, 4)
+        self.stat_count = z(N, dtype=torch.int32)
+        self.rect = z(N, R, 4, dtype=torch.int16)
+        self.rect_count = z(N, dtype=torch.int32)
+        self.rob_pv = z(N, 4)
+        self.rob_gr = z(N, 4)
+        self.rob_theta = z(N)
+        self.time = z(N, dtype=torch.float64)
+        # per-decision buffers
+        self.vin = None
+        self.la_reward = z(N, A, dtype=torch.float64)
+        self.la_done = z(N, A, dtype=torch.uint8)
+        self.la_event = z(N, A, dtype=torch.uint8)
+        self.values = z(N, A)
+        self.action_values = z(N, A, dtype=torch.float64)
+        self.argmax = z(N, dtype=torch.int32)
+        self.nan_flag = z(N, dtype=torch.uint8)
+        # per-step outputs
+        self.reward = z(N, dtype=torch.float64)
+        self.done = z(N, dtype=torch.uint8)
+        self.event = z(N, dtype=torch.uint8)
+        self.dmin = z(N, 3, dtype=torch.float64)
+        self.dist_to_goal = z(N, dtype=torch.float64)
+        self.actions = None
+        st = abi.EbcState()
+        for name in ("hum_pv", "hum_gr", "hum_type", "hum_count", "hum_nv", "stat", "stat_count", "rect",
+                     "rect_count", "rob_pv", "rob_gr", "rob_theta", "time"):
+            setattr(st, name, getattr(self, name).data_ptr())
+        self._state = st
+        self.be.call("bind", self.h, ctypes.byref(st))
+
+    def close(self):
+        if getattr(self, "h", None) is not None:
+            self.be.destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- configuration ------------------------------------------------------------
+    def _stream(self):
+        if self.device.type == "cuda":
+            return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return None
+
+    def set_actions(self, table):
+        table = np.ascontiguousarray(table, dtype=np.float64)
+        assert table.shape == (self.A, 2), table.shape
+        self.actions = table
+        self.be.call("set_actions", self.h, table.ctypes.data_as(ctypes.c_void_p), self.A)
+
+    def set_weights(self, state_dict, with_global_state=True, self_state_dim=6):
+        """state_dict: the reference's ValueNetwork.state_dict() (rl/policy/sarl.py:9-36), tensors or arrays."""
+        keep = []
+
+        def lin(key):
+            w = np.ascontiguousarray(np.asarray(state_dict[key + ".weight"], dtype=np.float32))
+            b = np.ascontiguousarray(np.asarray(state_dict[key + ".bias"], dtype=np.float32))
+            keep.extend([w, b])
+            l = abi.EbcLinear()
+            l.weight, l.bias = w.ctypes.data, b.ctypes.data
+            l.out_dim, l.in_dim = w.shape
+            return l
+
+        w = abi.EbcWeights()
+        w.input_dim, w.self_state_dim, w.with_global_state = self.D, self_state_dim, int(with_global_state)
+        for field, keys in zip(("mlp1", "mlp2", "attention", "mlp3"), _WEIGHT_KEYS):
+            arr = getattr(w, field)
+            for i, k in enumerate(keys):
+                arr[i] = lin(k)
+        self.be.call("set_weights", self.h, ctypes.byref(w))
+        self._have_weights = True
+
+    # ---- scene upload -------------------------------------------------------------
+    def load_episodes(self, first, hum_pv, hum_gr, hum_type, hum_count, stat=None, stat_count=None,
+                      rect=None, rect_count=None, rob_pv=None, rob_gr=None, rob_theta=None, time=None):
+        """Copy host arrays (numpy, already padded to Hmax/Smax/Rmax) into episodes [first, first+k)."""
+        k = len(hum_count)
+        sl = slice(first, first + k)
+
+        def put(dst, src, dtype):
+            if src is None:
+                return
+            t = torch.as_tensor(np.ascontiguousarray(src), dtype=dtype)
+            dst[sl].copy_(t.reshape(dst[sl].shape), non_blocking=False)
+
+        put(self.hum_pv, hum_pv, torch.float32)
+        put(self.hum_gr, hum_gr, torch.float32)
+        put(self.hum_type, hum_type, torch.uint8)
+        put(self.hum_count, hum_count, torch.int32)
+        if self.Smax:
+            put(self.stat, stat, torch.float32)
+        put(self.stat_count, stat_count, torch.int32)
+        if self.Rmax:
+            put(self.rect, rect, torch.int16)
+        put(self.rect_count, rect_count, torch.int32)
+        put(self.rob_pv, rob_pv, torch.float32)
+        put(self.rob_gr, rob_gr, torch.float32)
+        put(self.rob_theta, rob_theta, torch.float32)
+        put(self.time, time, torch.float64)
+
+    # ---- hot path -----------------------------------------------------------------
+    def orca(self):
+        self.be.call("orca", self.h, stream=self._stream())
+
+    def robot_orca(self, safety_space, out=None):
+        if out is None:
+            out = torch.zeros(self.N, 2, dtype=torch.float64, device=self.device)
+        self.be.call("robot_orca", self.h, ctypes.c_double(safety_space), _ptr(out), stream=self._stream())
+        return out
+
+    def lookahead(self, build_inputs=True):
+        if build_inputs and self.vin is None:
+            self.vin = torch.zeros(self.N, self.A, self.n, self.D, dtype=torch.float32, device=self.device)
+        self.be.call("lookahead", self.h, _ptr(self.vin if build_inputs else None), _ptr(self.la_reward),
+                     _ptr(self.la_done), _ptr(self.la_event), stream=self._stream())
+
+    def value(self, vin=None, row_count=None, out=None):
+        if vin is None:
+            vin, out, n_states = self.vin, self.values, self.N * self.A
+        else:
+            n_states = vin.shape[0]
+            if out is None:
+                out = torch.zeros(n_states, dtype=torch.float32, device=self.device)
+        self.be.call("value", self.h, _ptr(vin), ctypes.c_int64(n_states), _ptr(row_count), _ptr(out),
+                     stream=self._stream())
+        return out
+
+    def select(self):
+        self.be.call("select", self.h, _ptr(self.la_reward), _ptr(self.values), _ptr(self.action_values),
+                     _ptr(self.argmax), _ptr(self.nan_flag), stream=self._stream())
+        return self.argmax
+
+    def decide(self):
+        """One robot decision for every episode (rl/policy/multi_human_rl.py:12-87, test phase)."""
+        self.orca()
+        self.lookahead()
+        self.value()
+        return self.select()
+
+    def step(self, action_idx=None, action=None, active=None, fused_orca=False):
+        """env.step(update=True).  `fused_orca`: run the human policies in the same launch
+        (policy-free path); otherwise hum_nv from the preceding orca() is used."""
+        name = "orca_step" if fused_orca else "step"
+        self.be.call(name, self.h, _ptr(action_idx), _ptr(action), _ptr(active), _ptr(self.reward),
+                     _ptr(self.done), _ptr(self.event), _ptr(self.dmin), _ptr(self.dist_to_goal),
+                     stream=self._stream())
+
+    def transform(self, out=None):
+        if out is None:
+            out = torch.zeros(self.N, self.n, self.D, dtype=torch.float32, device=self.device)
+        self.be.call("transform", self.h, _ptr(out), stream=self._stream())
+        return out
+
+    def launch_count(self):
+        return self.be.launch_count(self.h)

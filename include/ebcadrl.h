@@ -1,0 +1,252 @@
+/*
+ * ebcadrl.h — C ABI of the B200-native batched crowd-navigation hot path.
+ *
+ * This is the drop-in boundary for ONE path of kolomeytsev/EB-CADRL: the
+ * `simulator/env.py` reset/step/onestep_lookahead loop with ORCA humans and the
+ * SARL / EB-CADRL one-step lookahead + value network.  Plain pointers and sizes
+ * only: no C++ types, no torch types, no exceptions cross this line.
+ *
+ * Two implementations export (almost) the same entry points:
+ *   - libebcadrl.so  (eb-cadrl_b200/csrc, CUDA sm_100a): `ebc_*`, DEVICE pointers.
+ *   - libebc_oracle.so (oracle/, plain C, TEST INFRASTRUCTURE ONLY): `ebc_ref_*`,
+ *     HOST pointers, same structs, same semantics.  The product never loads it.
+ *
+ * Every entry point cites the reference code it replaces (paths relative to the
+ * reference repository root).
+ *
+ * Conventions
+ *   N      episodes advanced at once (this rank's shard)
+ *   Hmax   human slots per episode; humans are stored adults, then bicycles,
+ *          then children (the reference's list order, simulator/env.py:392)
+ *   Smax   static-disc slots (walls seen by the robot as ADULT_STATIC discs,
+ *          simulator/scene/scene_generator.py:380-422)
+ *   Rmax   zero-cell rectangles of the occupancy grid (simulator/env.py:227-261
+ *          tests a window of scene.map; the grid is a union of rectangles written
+ *          by scene_generator.py:888-922)
+ *   A      discrete robot actions (rl/policy/cadrl.py:91-116), index 0 = stop
+ *   n      entity rows per lookahead state = Hmax + Smax (rows past an episode's
+ *          own count are zero-filled and masked)
+ *   D      rotated row width: 13, or 17 with the 4-class entity-type one-hot
+ *          (rl/policy/cadrl.py:236-337)
+ * All calls are asynchronous on the given stream; no hidden synchronisation.
+ * Return value: 0 on success, negative `ebc_status` otherwise; the message is in
+ * `ebc_last_error`.
+ */
+#ifndef EBCADRL_H
+#define EBCADRL_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EBC_ABI_VERSION 1
+
+/* simulator/utils/utils.py:9-14 (AgentType IntEnum) */
+enum { EBC_ADULT = 0, EBC_BICYCLE = 1, EBC_CHILD = 2, EBC_ADULT_STATIC = 3, EBC_ROBOT = 4 };
+
+/* Event codes = the Info subclass returned by Reward.compute
+ * (simulator/utils/reward.py:103-179, simulator/utils/info.py). */
+enum {
+  EBC_EV_NOTHING = 0,
+  EBC_EV_DANGER = 1,
+  EBC_EV_REACH_GOAL = 2,
+  EBC_EV_COLLISION_ADULT = 3,
+  EBC_EV_COLLISION_BICYCLE = 4,
+  EBC_EV_COLLISION_CHILD = 5,
+  EBC_EV_COLLISION_OBSTACLE = 6,
+  EBC_EV_TIMEOUT = 7
+};
+
+enum { EBC_KIN_HOLONOMIC = 0, EBC_KIN_UNICYCLE = 1 };   /* agent.py:164-188: any non-"holonomic" string */
+enum { EBC_POLICY_ORCA = 0, EBC_POLICY_LINEAR = 1 };    /* simulator/policy/policy_factory.py:10-14 */
+
+typedef enum ebc_status {
+  EBC_OK = 0,
+  EBC_ERR_INVALID = -1,   /* bad argument / config */
+  EBC_ERR_UNBOUND = -2,   /* ebc_bind / ebc_set_actions / ebc_set_weights not called */
+  EBC_ERR_CUDA = -3,      /* CUDA runtime error (message has the cudaError string) */
+  EBC_ERR_NOMEM = -4
+} ebc_status;
+
+/* Per-simulator constants: the env INI ([env] [reward] [map] [robot]) and the
+ * policy INI ([rl] [action_space] [sarl]) boiled down to a POD.
+ * simulator/env.py:58-87, simulator/utils/reward.py:18-75, rl/policy/cadrl.py:73-82,
+ * rl/policy/sarl.py:90-128, simulator/policy/orca.py:57-69. */
+typedef struct ebc_config {
+  int32_t abi_version;       /* EBC_ABI_VERSION */
+  int32_t n_episodes;        /* N */
+  int32_t max_humans;        /* Hmax (1..64) */
+  int32_t max_statics;       /* Smax (0..64); Hmax + Smax <= 64 */
+  int32_t max_rects;         /* Rmax (>=0) */
+  int32_t n_actions;         /* A (1..256) */
+  int32_t robot_kinematics;  /* EBC_KIN_*: how env/agent code moves the robot */
+  int32_t rotate_theta;      /* 1 iff policy kinematics == "unicycle" exactly (cadrl.py:261-265) */
+  int32_t with_agent_type;   /* 1: D = 17 (sarl.py:100-108), 0: D = 13 */
+  int32_t robot_visible;     /* [robot] visible: humans' ORCA sees the robot (env.py:401-402) */
+  int32_t human_policy[3];   /* EBC_POLICY_* for adults, bicycles, children */
+  int32_t new_reward;        /* reward.py:19 */
+  int32_t has_max_goal_distance; /* reward.py:21-23 (None when absent) */
+  int32_t orca_max_neighbors;    /* orca.py:65 (10) */
+  double time_step;          /* [env] time_step */
+  double time_limit;         /* [env] time_limit (getint in the reference) */
+  double time_max, time_good, max_goal_distance, success_reward;
+  double collision_penalty_adult, collision_penalty_bicycle;
+  double collision_penalty_obstacle, collision_penalty_child;
+  double discomfort_dist_adult, discomfort_dist_bicycle, discomfort_dist_child;
+  double discomfort_penalty_factor_adult, discomfort_penalty_factor_bicycle;
+  double discomfort_penalty_factor_child;
+  double rotation_penalty_factor;
+  double map_size_m, map_resolution; /* [map] */
+  double gamma;                      /* [rl] gamma */
+  double orca_safety_space;          /* orca.py:63 (0; IL robot uses 0.15, train.py:126-132) */
+  float orca_neighbor_dist;          /* orca.py:64 (10) */
+  float orca_time_horizon;           /* orca.py:66 (5) */
+} ebc_config;
+
+/* Structure-of-arrays episode state.  The library BORROWS these arrays (owned by
+ * the caller, e.g. torch tensors); it never frees them.  fp32 state, float4-packed
+ * per agent so that one warp lane loads one agent with one 16-byte load.
+ * Layout follows simulator/utils/state.py:1-92 (FullState / ObservableState). */
+typedef struct ebc_state {
+  float *hum_pv;        /* [N*Hmax*4]  px, py, vx, vy */
+  float *hum_gr;        /* [N*Hmax*4]  gx, gy, v_pref, radius */
+  uint8_t *hum_type;    /* [N*Hmax]    EBC_ADULT / EBC_BICYCLE / EBC_CHILD, sorted ascending */
+  int32_t *hum_count;   /* [N]         humans in the episode (<= Hmax) */
+  float *hum_nv;        /* [N*Hmax*2]  human action of the current step (ORCA output), written by ebc_orca */
+  float *stat;          /* [N*Smax*4]  px, py, radius, 0  (static discs, robot-only observation) */
+  int32_t *stat_count;  /* [N] */
+  int16_t *rect;        /* [N*Rmax*4]  x0, y0, x1, y1: half-open zero-cell rectangle of scene.map */
+  int32_t *rect_count;  /* [N] */
+  float *rob_pv;        /* [N*4]       px, py, vx, vy */
+  float *rob_gr;        /* [N*4]       gx, gy, v_pref, radius */
+  float *rob_theta;     /* [N] */
+  double *time;         /* [N]         env.global_time */
+} ebc_state;
+
+/* SARL / EB-CADRL value network (rl/policy/sarl.py:9-82).  HOST pointers to the
+ * state_dict tensors, PyTorch nn.Linear layout: weight [out][in] row-major, bias [out].
+ * Keys: mlp1.{0,2}, mlp2.{0,2}, attention.{0,2,4}, mlp3.{0,2,4,6}.
+ * The library copies (and re-lays-out) them; the caller may free them afterwards. */
+typedef struct ebc_linear {
+  const float *weight;
+  const float *bias;
+  int32_t in_dim, out_dim;
+} ebc_linear;
+
+typedef struct ebc_weights {
+  int32_t input_dim;        /* D */
+  int32_t self_state_dim;   /* 6 (cadrl.py:55) */
+  int32_t with_global_state;/* sarl.py:28-32 */
+  ebc_linear mlp1[2];
+  ebc_linear mlp2[2];
+  ebc_linear attention[3];
+  ebc_linear mlp3[4];
+} ebc_weights;
+
+typedef struct ebc_sim ebc_sim;   /* opaque */
+
+/* ---- lifetime -------------------------------------------------------------------- */
+int ebc_create(const ebc_config *cfg, int device, ebc_sim **out);
+void ebc_destroy(ebc_sim *sim);
+const char *ebc_last_error(const ebc_sim *sim);   /* sim may be NULL: last create error */
+int ebc_abi_version(void);
+
+/* Borrow the caller's device arrays. */
+int ebc_bind(ebc_sim *sim, const ebc_state *state);
+
+/* Action table, HOST pointer, A x 2 doubles: (vx, vy) for a holonomic robot, (v, r)
+ * otherwise; built on the host exactly like rl/policy/cadrl.py:91-116. */
+int ebc_set_actions(ebc_sim *sim, const double *actions, int32_t n_actions);
+
+int ebc_set_weights(ebc_sim *sim, const ebc_weights *w);
+
+/* ---- the hot path ---------------------------------------------------------------- */
+
+/* K1. Human policy step: state.hum_nv[e,h] <- policy_h(current state).
+ * Replaces the per-human loop of simulator/env.py:392-405 -> agents.py:13-30 ->
+ * simulator/policy/orca.py:85-157 -> rvo2 PyRVOSimulator.doStep (agent 0 only), and
+ * simulator/policy/linear.py:17-23 for `linear` humans. */
+int ebc_orca(ebc_sim *sim, void *stream);
+
+/* Robot driven by ORCA (imitation learning, rl/train.py:99-143; reset() returns
+ * obstacle_vertices for it, env.py:201-204): robot = agent 0, neighbours = humans then
+ * static discs.  out_action: [N*2] doubles (vx, vy). */
+int ebc_robot_orca(ebc_sim *sim, double safety_space, double *out_action, void *stream);
+
+/* K3. One-step lookahead for every (episode, action): env.onestep_lookahead
+ * (simulator/env.py:207-209 -> step(update=False) :388-466), i.e. collisions
+ * (env.py:303-338, utils/collisions.py:4-57, obstacle grid env.py:227-261), reward /
+ * done / event (utils/reward.py:80-181), next human states (agent.py:80-93), robot
+ * propagate (rl/policy/cadrl.py:118-165) and the rotated joint state
+ * (rl/policy/multi_human_rl.py:52-61 + cadrl.py:236-337).  Requires ebc_orca first.
+ *   vin    [N*A*n*D] fp32 value-network input (NULL: skip the joint-state build)
+ *   reward [N*A] f64, done [N*A] u8, event [N*A] u8  (any may be NULL) */
+int ebc_lookahead(ebc_sim *sim, float *vin, double *reward, uint8_t *done, uint8_t *event,
+                  void *stream);
+
+/* K4. Value network forward (rl/policy/sarl.py:38-82) over `n_states` states of n rows
+ * each; row_count[s] (<= n) rows are real, the rest are padding (excluded from the
+ * mean and the softmax).  vin [n_states*n*D] -> values [n_states].
+ * row_count may be NULL (all n rows real).  Used with n_states = N*A for the lookahead,
+ * in which case pass row_count = NULL and the per-episode counts bound to the sim are used. */
+int ebc_value(ebc_sim *sim, const float *vin, int64_t n_states, const int32_t *row_count,
+              float *values, void *stream);
+
+/* K5. Action selection (rl/policy/multi_human_rl.py:25-26,72-80):
+ * action_values[e,a] = reward[e,a] + gamma^(time_step*v_pref) * values[e,a] (float64),
+ * argmax[e] = first maximum (strict '>'), or 0 (the stop action) when the robot is
+ * already within `radius` of its goal (policy.py:43-54).  nan_flag[e] = 1 when no action
+ * compares greater than -inf ("Value network is not well trained.", :81-82). */
+int ebc_select(ebc_sim *sim, const double *reward, const float *values, double *action_values,
+               int32_t *argmax, uint8_t *nan_flag, void *stream);
+
+/* K2. Committed step: env.step(action, update=True) (simulator/env.py:388-466 with
+ * compute_step_update :340-386 and agent.py:202-228).  Uses state.hum_nv from ebc_orca.
+ * Exactly one of action_idx [N] (index into the action table) / action [N*2] f64 is given.
+ * Episodes with active[e] == 0 are left untouched (active may be NULL = all).
+ * Outputs (any may be NULL): reward [N] f64, done [N] u8, event [N] u8,
+ * dmin [N*3] f64 (adult, bicycle, child; +inf when none), dist_to_goal [N] f64. */
+int ebc_step(ebc_sim *sim, const int32_t *action_idx, const double *action, const uint8_t *active,
+             double *reward, uint8_t *done, uint8_t *event, double *dmin, double *dist_to_goal,
+             void *stream);
+
+/* Fused convenience for the policy-free path (robot action given, e.g. the `linear`
+ * robot of tests/test_collisions_simulation.py): ebc_orca + ebc_step in one launch. */
+int ebc_orca_step(ebc_sim *sim, const int32_t *action_idx, const double *action,
+                  const uint8_t *active, double *reward, uint8_t *done, uint8_t *event,
+                  double *dmin, double *dist_to_goal, void *stream);
+
+/* Rotated CURRENT joint state for the replay memory
+ * (rl/policy/multi_human_rl.py:128-149): out [N*n*D]. */
+int ebc_transform(ebc_sim *sim, float *out, void *stream);
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t ebc_launch_count(const ebc_sim *sim);
+
+/* ---- CPU twins (oracle/libebc_oracle.so only; HOST pointers; test infrastructure) -- */
+int ebc_ref_create(const ebc_config *cfg, ebc_sim **out);
+void ebc_ref_destroy(ebc_sim *sim);
+const char *ebc_ref_last_error(const ebc_sim *sim);
+int ebc_ref_bind(ebc_sim *sim, const ebc_state *state);
+int ebc_ref_set_actions(ebc_sim *sim, const double *actions, int32_t n_actions);
+int ebc_ref_set_weights(ebc_sim *sim, const ebc_weights *w);
+int ebc_ref_orca(ebc_sim *sim);
+int ebc_ref_robot_orca(ebc_sim *sim, double safety_space, double *out_action);
+int ebc_ref_lookahead(ebc_sim *sim, float *vin, double *reward, uint8_t *done, uint8_t *event);
+int ebc_ref_value(ebc_sim *sim, const float *vin, int64_t n_states, const int32_t *row_count,
+                  float *values);
+int ebc_ref_select(ebc_sim *sim, const double *reward, const float *values, double *action_values,
+                   int32_t *argmax, uint8_t *nan_flag);
+int ebc_ref_step(ebc_sim *sim, const int32_t *action_idx, const double *action,
+                 const uint8_t *active, double *reward, uint8_t *done, uint8_t *event,
+                 double *dmin, double *dist_to_goal);
+int ebc_ref_transform(ebc_sim *sim, float *out);
+void ebc_ref_set_threads(int n);   /* OpenMP threads over episodes (cpu_baseline leg) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EBCADRL_H */

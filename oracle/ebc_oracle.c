@@ -1,0 +1,937 @@
+/*
+ * ebc_oracle.c — CPU restatement of the EB-CADRL hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under eb-cadrl_b200/ may import, link or execute
+ * this file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * `--impl reference` legs use it, and only as the checker / reported CPU baseline.
+ *
+ * Parity status
+ *   - In-tree reference code (env step, collisions, reward, lookahead, rotate, value
+ *     net): PINNED.  tests/golden/ holds vectors produced by importing the unmodified
+ *     reference (/root/reference) with oracle/shims on PYTHONPATH; tests/test_oracle_golden.py
+ *     replays them through this file.
+ *   - rvo2 (Python-RVO2 over RVO2 Library v2.0.x, un-vendored and un-pinned by the
+ *     reference, absent from this image): restated below from the published RVO2
+ *     algorithm (Agent::computeNeighbors / insertAgentNeighbor / computeNewVelocity,
+ *     linearProgram1/2/3, RVO_EPSILON = 1e-5f).  Numerically "parity unpinned" (the
+ *     reference holds no float golden for it); pinned at event level by the reference's
+ *     own episode-outcome tests (tests/test_collisions_simulation.py,
+ *     tests/test_basic_simulation.py), which pass with this restatement plugged in as
+ *     `rvo2` (oracle/run_reference_tests.py).
+ *
+ * Arithmetic: rvo2 part in IEEE fp32, everything the reference does in Python floats in
+ * fp64 (promoted from the fp32 state), the rotate / value-net part in fp32 (the reference
+ * casts to torch.float32 at rl/policy/multi_human_rl.py:52-60).  Build with
+ * -ffp-contract=off so that no multiply-add is fused (RVO2 on baseline x86-64 has none).
+ *
+ * Every function cites the reference file:line it follows.
+ */
+#include "../include/ebcadrl.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define RVO_EPSILON 0.00001f
+#define MAX_LINES 80 /* >= max neighbours considered (cap = orca_max_neighbors <= 64) */
+
+typedef struct { float px, py, dx, dy; } line_t; /* RVO2 Line: point, direction */
+
+static inline float det2(float ax, float ay, float bx, float by) { return ax * by - ay * bx; }
+static inline float dot2(float ax, float ay, float bx, float by) { return ax * bx + ay * by; }
+
+/* RVO2 Agent.cpp linearProgram1. */
+static int lp1(const line_t *L, int i, float radius, float ox, float oy, int dir_opt, float *rx,
+               float *ry) {
+  const float dp = dot2(L[i].px, L[i].py, L[i].dx, L[i].dy);
+  const float disc = dp * dp + radius * radius - dot2(L[i].px, L[i].py, L[i].px, L[i].py);
+  if (disc < 0.0f) return 0;
+  const float s = sqrtf(disc);
+  float tl = -dp - s;
+  float tr = -dp + s;
+  for (int j = 0; j < i; ++j) {
+    const float den = det2(L[i].dx, L[i].dy, L[j].dx, L[j].dy);
+    const float num = det2(L[j].dx, L[j].dy, L[i].px - L[j].px, L[i].py - L[j].py);
+    if (fabsf(den) <= RVO_EPSILON) {
+      if (num < 0.0f) return 0;
+      continue;
+    }
+    const float t = num / den;
+    if (den >= 0.0f) {
+      tr = fminf(tr, t);
+    } else {
+      tl = fmaxf(tl, t);
+    }
+    if (tl > tr) return 0;
+  }
+  float t;
+  if (dir_opt) {
+    t = (dot2(ox, oy, L[i].dx, L[i].dy) > 0.0f) ? tr : tl;
+  } else {
+    t = dot2(L[i].dx, L[i].dy, ox - L[i].px, oy - L[i].py);
+    if (t < tl) t = tl;
+    else if (t > tr) t = tr;
+  }
+  *rx = L[i].px + t * L[i].dx;
+  *ry = L[i].py + t * L[i].dy;
+  return 1;
+}
+
+/* RVO2 Agent.cpp linearProgram2. */
+static int lp2(const line_t *L, int n, float radius, float ox, float oy, int dir_opt, float *rx,
+               float *ry) {
+  if (dir_opt) {
+    *rx = ox * radius;
+    *ry = oy * radius;
+  } else if (dot2(ox, oy, ox, oy) > radius * radius) {
+    const float inv = 1.0f / sqrtf(dot2(ox, oy, ox, oy)); /* normalize(v) = v / abs(v) */
+    *rx = (ox * inv) * radius;
+    *ry = (oy * inv) * radius;
+  } else {
+    *rx = ox;
+    *ry = oy;
+  }
+  for (int i = 0; i < n; ++i) {
+    if (det2(L[i].dx, L[i].dy, L[i].px - *rx, L[i].py - *ry) > 0.0f) {
+      const float tx = *rx, ty = *ry;
+      if (!lp1(L, i, radius, ox, oy, dir_opt, rx, ry)) {
+        *rx = tx;
+        *ry = ty;
+        return i;
+      }
+    }
+  }
+  return n;
+}
+
+/* RVO2 Agent.cpp linearProgram3 (numObstLines = 0 on the reference's live path). */
+static void lp3(const line_t *L, int n, int num_obst, int begin, float radius, float *rx,
+                float *ry) {
+  float distance = 0.0f;
+  line_t proj[MAX_LINES];
+  for (int i = begin; i < n; ++i) {
+    if (det2(L[i].dx, L[i].dy, L[i].px - *rx, L[i].py - *ry) > distance) {
+      int m = 0;
+      for (int j = 0; j < num_obst; ++j) proj[m++] = L[j];
+      for (int j = num_obst; j < i; ++j) {
+        line_t ln;
+        const float d = det2(L[i].dx, L[i].dy, L[j].dx, L[j].dy);
+        if (fabsf(d) <= RVO_EPSILON) {
+          if (dot2(L[i].dx, L[i].dy, L[j].dx, L[j].dy) > 0.0f) continue;
+          ln.px = 0.5f * (L[i].px + L[j].px);
+          ln.py = 0.5f * (L[i].py + L[j].py);
+        } else {
+          const float t = det2(L[j].dx, L[j].dy, L[i].px - L[j].px, L[i].py - L[j].py) / d;
+          ln.px = L[i].px + t * L[i].dx;
+          ln.py = L[i].py + t * L[i].dy;
+        }
+        const float ddx = L[j].dx - L[i].dx, ddy = L[j].dy - L[i].dy;
+        const float inv = 1.0f / sqrtf(dot2(ddx, ddy, ddx, ddy));
+        ln.dx = ddx * inv;
+        ln.dy = ddy * inv;
+        proj[m++] = ln;
+      }
+      const float tx = *rx, ty = *ry;
+      if (lp2(proj, m, radius, -L[i].dy, L[i].dx, 1, rx, ry) < m) {
+        *rx = tx;
+        *ry = ty;
+      }
+      distance = det2(L[i].dx, L[i].dy, L[i].px - *rx, L[i].py - *ry);
+    }
+  }
+}
+
+/* One agent's RVO2 step: computeNeighbors + computeNewVelocity (agent-agent part).
+ * SURVEY Appendix A.1-A.4.  `others` are visited in index order (RVO2's kd-tree leaf
+ * order for <= 10 agents; for more agents the order only matters for exact distance
+ * ties). */
+void ebc_ref_orca_agent(float px, float py, float vx, float vy, float radius, float max_speed,
+                        float pref_x, float pref_y, int n_other, const float *opx,
+                        const float *opy, const float *ovx, const float *ovy, const float *orad,
+                        float neighbor_dist, int max_neighbors, float time_horizon,
+                        float time_step, float *out_vx, float *out_vy) {
+  int nb[MAX_LINES];
+  float nbd[MAX_LINES];
+  int cnt = 0;
+  if (max_neighbors > MAX_LINES) max_neighbors = MAX_LINES;
+  float range_sq = neighbor_dist * neighbor_dist;
+  if (max_neighbors > 0) {
+    for (int j = 0; j < n_other; ++j) { /* Agent::insertAgentNeighbor */
+      const float ddx = px - opx[j], ddy = py - opy[j];
+      const float d = dot2(ddx, ddy, ddx, ddy);
+      if (d < range_sq) {
+        if (cnt < max_neighbors) ++cnt;
+        int i = cnt - 1;
+        while (i != 0 && d < nbd[i - 1]) {
+          nbd[i] = nbd[i - 1];
+          nb[i] = nb[i - 1];
+          --i;
+        }
+        nbd[i] = d;
+        nb[i] = j;
+        if (cnt == max_neighbors) range_sq = nbd[cnt - 1];
+      }
+    }
+  }
+  line_t L[MAX_LINES];
+  const float inv_th = 1.0f / time_horizon;
+  for (int k = 0; k < cnt; ++k) {
+    const int j = nb[k];
+    const float rpx = opx[j] - px, rpy = opy[j] - py;
+    const float rvx = vx - ovx[j], rvy = vy - ovy[j];
+    const float dist_sq = dot2(rpx, rpy, rpx, rpy);
+    const float R = radius + orad[j];
+    const float R_sq = R * R;
+    float ux, uy;
+    line_t ln;
+    if (dist_sq > R_sq) {
+      const float wx = rvx - inv_th * rpx, wy = rvy - inv_th * rpy;
+      const float wlen_sq = dot2(wx, wy, wx, wy);
+      const float dp1 = dot2(wx, wy, rpx, rpy);
+      if (dp1 < 0.0f && dp1 * dp1 > R_sq * wlen_sq) {
+        const float wlen = sqrtf(wlen_sq);
+        const float inv = 1.0f / wlen;
+        const float uwx = wx * inv, uwy = wy * inv;
+        ln.dx = uwy;
+        ln.dy = -uwx;
+        const float s = R * inv_th - wlen;
+        ux = s * uwx;
+        uy = s * uwy;
+      } else {
+        const float leg = sqrtf(dist_sq - R_sq);
+        const float inv = 1.0f / dist_sq;
+        if (det2(rpx, rpy, wx, wy) > 0.0f) {
+          ln.dx = (rpx * leg - rpy * R) * inv;
+          ln.dy = (rpx * R + rpy * leg) * inv;
+        } else {
+          ln.dx = (-(rpx * leg + rpy * R)) * inv;
+          ln.dy = (-(-rpx * R + rpy * leg)) * inv;
+        }
+        const float dp2 = dot2(rvx, rvy, ln.dx, ln.dy);
+        ux = dp2 * ln.dx - rvx;
+        uy = dp2 * ln.dy - rvy;
+      }
+    } else {
+      const float inv_ts = 1.0f / time_step;
+      const float wx = rvx - inv_ts * rpx, wy = rvy - inv_ts * rpy;
+      const float wlen = sqrtf(dot2(wx, wy, wx, wy));
+      const float inv = 1.0f / wlen;
+      const float uwx = wx * inv, uwy = wy * inv;
+      ln.dx = uwy;
+      ln.dy = -uwx;
+      const float s = R * inv_ts - wlen;
+      ux = s * uwx;
+      uy = s * uwy;
+    }
+    ln.px = vx + 0.5f * ux;
+    ln.py = vy + 0.5f * uy;
+    L[k] = ln;
+  }
+  float rx, ry;
+  const int fail = lp2(L, cnt, max_speed, pref_x, pref_y, 0, &rx, &ry);
+  if (fail < cnt) lp3(L, cnt, 0, fail, max_speed, &rx, &ry);
+  *out_vx = rx;
+  *out_vy = ry;
+}
+
+/* ------------------------------------------------------------------------------------
+ * Minimal stand-in for rvo2.PyRVOSimulator (Python-RVO2 src/rvo2.pyx), used through
+ * oracle/shims/rvo2.py so that the unmodified reference can run here.
+ * Call sites: simulator/policy/orca.py:105-154.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  float ts;
+  int n, cap;
+  float *px, *py, *vx, *vy, *prx, *pry, *rad, *maxs, *nd, *th;
+  int *maxn;
+} rvo_sim;
+
+void *ebc_rvo_create(float time_step) {
+  rvo_sim *s = (rvo_sim *)calloc(1, sizeof(rvo_sim));
+  s->ts = time_step;
+  return s;
+}
+void ebc_rvo_destroy(void *h) {
+  rvo_sim *s = (rvo_sim *)h;
+  if (!s) return;
+  free(s->px); free(s->py); free(s->vx); free(s->vy); free(s->prx); free(s->pry);
+  free(s->rad); free(s->maxs); free(s->nd); free(s->th); free(s->maxn);
+  free(s);
+}
+int ebc_rvo_add_agent(void *h, float px, float py, float nd, int maxn, float th, float rad,
+                      float maxs, float vx, float vy) {
+  rvo_sim *s = (rvo_sim *)h;
+  if (s->n == s->cap) {
+    s->cap = s->cap ? 2 * s->cap : 16;
+#define GROW(p, T) s->p = (T *)realloc(s->p, sizeof(T) * (size_t)s->cap)
+    GROW(px, float); GROW(py, float); GROW(vx, float); GROW(vy, float); GROW(prx, float);
+    GROW(pry, float); GROW(rad, float); GROW(maxs, float); GROW(nd, float); GROW(th, float);
+    GROW(maxn, int);
+#undef GROW
+  }
+  const int i = s->n++;
+  s->px[i] = px; s->py[i] = py; s->vx[i] = vx; s->vy[i] = vy; s->prx[i] = 0; s->pry[i] = 0;
+  s->rad[i] = rad; s->maxs[i] = maxs; s->nd[i] = nd; s->th[i] = th; s->maxn[i] = maxn;
+  return i;
+}
+int ebc_rvo_num_agents(void *h) { return ((rvo_sim *)h)->n; }
+void ebc_rvo_set_pos(void *h, int i, float x, float y) { rvo_sim *s = h; s->px[i] = x; s->py[i] = y; }
+void ebc_rvo_set_vel(void *h, int i, float x, float y) { rvo_sim *s = h; s->vx[i] = x; s->vy[i] = y; }
+void ebc_rvo_set_pref(void *h, int i, float x, float y) { rvo_sim *s = h; s->prx[i] = x; s->pry[i] = y; }
+void ebc_rvo_get_vel(void *h, int i, float *x, float *y) { rvo_sim *s = h; *x = s->vx[i]; *y = s->vy[i]; }
+void ebc_rvo_get_pos(void *h, int i, float *x, float *y) { rvo_sim *s = h; *x = s->px[i]; *y = s->py[i]; }
+/* RVOSimulator::doStep: new velocity for every agent, then update(). */
+void ebc_rvo_do_step(void *h) {
+  rvo_sim *s = (rvo_sim *)h;
+  const int n = s->n;
+  float *nvx = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1) * 7);
+  float *nvy = nvx + n, *ox = nvy + n, *oy = ox + n, *ovx = oy + n, *ovy = ovx + n,
+        *orad = ovy + n;
+  for (int i = 0; i < n; ++i) {
+    int m = 0;
+    for (int j = 0; j < n; ++j) {
+      if (j == i) continue;
+      ox[m] = s->px[j]; oy[m] = s->py[j]; ovx[m] = s->vx[j]; ovy[m] = s->vy[j];
+      orad[m] = s->rad[j];
+      ++m;
+    }
+    ebc_ref_orca_agent(s->px[i], s->py[i], s->vx[i], s->vy[i], s->rad[i], s->maxs[i], s->prx[i],
+                       s->pry[i], m, ox, oy, ovx, ovy, orad, s->nd[i], s->maxn[i], s->th[i],
+                       s->ts, &nvx[i], &nvy[i]);
+  }
+  for (int i = 0; i < n; ++i) {
+    s->vx[i] = nvx[i];
+    s->vy[i] = nvy[i];
+    s->px[i] += s->vx[i] * s->ts;
+    s->py[i] += s->vy[i] * s->ts;
+  }
+  free(nvx);
+}
+
+/* ------------------------------------------------------------------------------------
+ * Batched CPU twin of the C ABI.
+ * ---------------------------------------------------------------------------------- */
+struct ebc_sim {
+  ebc_config cfg;
+  ebc_state st;
+  int bound;
+  double *actions; /* A*2 */
+  int have_actions;
+  /* value net (copied) */
+  int have_weights;
+  int D, self_dim, with_global;
+  struct { float *w, *b; int in, out; } lin[11]; /* mlp1[2] mlp2[2] att[3] mlp3[4] */
+  char err[256];
+};
+
+static char g_create_err[256];
+static int g_threads = 1;
+
+void ebc_ref_set_threads(int n) { g_threads = n > 0 ? n : 1; }
+
+static int fail(ebc_sim *s, int code, const char *msg) {
+  snprintf(s ? s->err : g_create_err, 256, "%s", msg);
+  return code;
+}
+
+int ebc_ref_create(const ebc_config *cfg, ebc_sim **out) {
+  if (!cfg || !out) return fail(NULL, EBC_ERR_INVALID, "null argument");
+  if (cfg->abi_version != EBC_ABI_VERSION) return fail(NULL, EBC_ERR_INVALID, "abi_version mismatch");
+  if (cfg->n_episodes < 1 || cfg->max_humans < 1 || cfg->max_humans > 64 || cfg->max_statics < 0 ||
+      cfg->max_humans + cfg->max_statics > 64 || cfg->max_rects < 0 || cfg->n_actions < 1 ||
+      cfg->n_actions > 256 || cfg->orca_max_neighbors < 0 || cfg->orca_max_neighbors > 64)
+    return fail(NULL, EBC_ERR_INVALID, "config out of range");
+  ebc_sim *s = (ebc_sim *)calloc(1, sizeof(ebc_sim));
+  if (!s) return fail(NULL, EBC_ERR_NOMEM, "calloc failed");
+  s->cfg = *cfg;
+  *out = s;
+  return EBC_OK;
+}
+
+void ebc_ref_destroy(ebc_sim *s) {
+  if (!s) return;
+  free(s->actions);
+  for (int i = 0; i < 11; ++i) { free(s->lin[i].w); free(s->lin[i].b); }
+  free(s);
+}
+
+const char *ebc_ref_last_error(const ebc_sim *s) { return s ? s->err : g_create_err; }
+
+int ebc_ref_bind(ebc_sim *s, const ebc_state *st) {
+  if (!s || !st) return EBC_ERR_INVALID;
+  if (!st->hum_pv || !st->hum_gr || !st->hum_type || !st->hum_count || !st->hum_nv ||
+      !st->stat_count || !st->rect_count || !st->rob_pv || !st->rob_gr || !st->rob_theta ||
+      !st->time)
+    return fail(s, EBC_ERR_INVALID, "ebc_bind: null state array");
+  s->st = *st;
+  s->bound = 1;
+  return EBC_OK;
+}
+
+int ebc_ref_set_actions(ebc_sim *s, const double *a, int32_t n) {
+  if (!s || !a || n != s->cfg.n_actions) return fail(s, EBC_ERR_INVALID, "ebc_set_actions: bad table");
+  free(s->actions);
+  s->actions = (double *)malloc(sizeof(double) * 2 * (size_t)n);
+  memcpy(s->actions, a, sizeof(double) * 2 * (size_t)n);
+  s->have_actions = 1;
+  return EBC_OK;
+}
+
+int ebc_ref_set_weights(ebc_sim *s, const ebc_weights *w) {
+  if (!s || !w) return EBC_ERR_INVALID;
+  const int D = s->cfg.with_agent_type ? 17 : 13;
+  if (w->input_dim != D) return fail(s, EBC_ERR_INVALID, "ebc_set_weights: input_dim != D");
+  const ebc_linear *src[11] = {&w->mlp1[0], &w->mlp1[1], &w->mlp2[0], &w->mlp2[1],
+                               &w->attention[0], &w->attention[1], &w->attention[2],
+                               &w->mlp3[0], &w->mlp3[1], &w->mlp3[2], &w->mlp3[3]};
+  for (int i = 0; i < 11; ++i) {
+    free(s->lin[i].w); free(s->lin[i].b);
+    const size_t nw = (size_t)src[i]->in_dim * (size_t)src[i]->out_dim;
+    s->lin[i].w = (float *)malloc(sizeof(float) * nw);
+    s->lin[i].b = (float *)malloc(sizeof(float) * (size_t)src[i]->out_dim);
+    memcpy(s->lin[i].w, src[i]->weight, sizeof(float) * nw);
+    memcpy(s->lin[i].b, src[i]->bias, sizeof(float) * (size_t)src[i]->out_dim);
+    s->lin[i].in = src[i]->in_dim;
+    s->lin[i].out = src[i]->out_dim;
+  }
+  s->D = D;
+  s->self_dim = w->self_state_dim;
+  s->with_global = w->with_global_state;
+  /* shape chain (sarl.py:23-36) */
+  const int h1 = s->lin[1].out;
+  if (s->lin[0].in != D || s->lin[1].in != s->lin[0].out || s->lin[2].in != h1 ||
+      s->lin[3].in != s->lin[2].out || s->lin[4].in != (s->with_global ? 2 * h1 : h1) ||
+      s->lin[5].in != s->lin[4].out || s->lin[6].in != s->lin[5].out || s->lin[6].out != 1 ||
+      s->lin[7].in != s->lin[3].out + s->self_dim || s->lin[8].in != s->lin[7].out ||
+      s->lin[9].in != s->lin[8].out || s->lin[10].in != s->lin[9].out || s->lin[10].out != 1)
+    return fail(s, EBC_ERR_INVALID, "ebc_set_weights: inconsistent layer shapes");
+  s->have_weights = 1;
+  return EBC_OK;
+}
+
+/* simulator/policy/orca.py:113-119,136-140: self radius / max speed / preferred velocity.
+ * Python computes these in float64 and rvo2 narrows to float at the Cython boundary. */
+static inline void orca_self_params(float px, float py, float gx, float gy, float radius,
+                                    double safety, float *r_out, float *prefx, float *prefy) {
+  *r_out = (float)((double)radius + 0.01 + safety);
+  const double vx = (double)gx - (double)px, vy = (double)gy - (double)py;
+  const double speed = sqrt(vx * vx + vy * vy);
+  if (speed > 1.0) {
+    *prefx = (float)(vx / speed);
+    *prefy = (float)(vy / speed);
+  } else {
+    *prefx = (float)vx;
+    *prefy = (float)vy;
+  }
+}
+
+/* K1: simulator/env.py:392-405 + simulator/policy/orca.py:85-157 (+ linear.py:17-23). */
+int ebc_ref_orca(ebc_sim *s) {
+  if (!s || !s->bound) return fail(s, EBC_ERR_UNBOUND, "ebc_orca: state not bound");
+  const ebc_config *c = &s->cfg;
+  const int Hm = c->max_humans;
+#pragma omp parallel for schedule(static) num_threads(g_threads)
+  for (int e = 0; e < c->n_episodes; ++e) {
+    const int H = s->st.hum_count[e];
+    const float *pv = s->st.hum_pv + (size_t)e * Hm * 4;
+    const float *gr = s->st.hum_gr + (size_t)e * Hm * 4;
+    const uint8_t *ty = s->st.hum_type + (size_t)e * Hm;
+    float *nv = s->st.hum_nv + (size_t)e * Hm * 2;
+    float ox[65], oy[65], ovx[65], ovy[65], orad[65];
+    for (int h = 0; h < H; ++h) {
+      const float px = pv[h * 4], py = pv[h * 4 + 1], vx = pv[h * 4 + 2], vy = pv[h * 4 + 3];
+      const float gx = gr[h * 4], gy = gr[h * 4 + 1], vpref = gr[h * 4 + 2], rad = gr[h * 4 + 3];
+      if (c->human_policy[ty[h] < 3 ? ty[h] : 0] == EBC_POLICY_LINEAR) {
+        /* linear.py:17-23, float64 then stored as fp32 state */
+        const double th = atan2((double)gy - (double)py, (double)gx - (double)px);
+        nv[h * 2] = (float)(cos(th) * (double)vpref);
+        nv[h * 2 + 1] = (float)(sin(th) * (double)vpref);
+        continue;
+      }
+      int m = 0;
+      for (int j = 0; j < H; ++j) {
+        if (j == h) continue;
+        ox[m] = pv[j * 4]; oy[m] = pv[j * 4 + 1]; ovx[m] = pv[j * 4 + 2]; ovy[m] = pv[j * 4 + 3];
+        orad[m] = (float)((double)gr[j * 4 + 3] + 0.01 + c->orca_safety_space);
+        ++m;
+      }
+      if (c->robot_visible) { /* env.py:401-402: robot appended last */
+        const float *rp = s->st.rob_pv + (size_t)e * 4;
+        ox[m] = rp[0]; oy[m] = rp[1]; ovx[m] = rp[2]; ovy[m] = rp[3];
+        orad[m] = (float)((double)s->st.rob_gr[(size_t)e * 4 + 3] + 0.01 + c->orca_safety_space);
+        ++m;
+      }
+      float r_self, prefx, prefy;
+      orca_self_params(px, py, gx, gy, rad, c->orca_safety_space, &r_self, &prefx, &prefy);
+      ebc_ref_orca_agent(px, py, vx, vy, r_self, vpref, prefx, prefy, m, ox, oy, ovx, ovy, orad,
+                         c->orca_neighbor_dist, c->orca_max_neighbors, c->orca_time_horizon,
+                         (float)c->time_step, &nv[h * 2], &nv[h * 2 + 1]);
+    }
+  }
+  return EBC_OK;
+}
+
+/* Robot as ORCA agent 0 (imitation learning): rl/train.py:99-143 + orca.py:85-157 with
+ * ob = humans + static discs (env.py:188-193). */
+int ebc_ref_robot_orca(ebc_sim *s, double safety, double *out) {
+  if (!s || !s->bound) return fail(s, EBC_ERR_UNBOUND, "ebc_robot_orca: state not bound");
+  const ebc_config *c = &s->cfg;
+  const int Hm = c->max_humans, Sm = c->max_statics;
+#pragma omp parallel for schedule(static) num_threads(g_threads)
+  for (int e = 0; e < c->n_episodes; ++e) {
+    const int H = s->st.hum_count[e], S = s->st.stat_count[e];
+    const float *pv = s->st.hum_pv + (size_t)e * Hm * 4;
+    const float *gr = s->st.hum_gr + (size_t)e * Hm * 4;
+    float ox[65], oy[65], ovx[65], ovy[65], orad[65];
+    int m = 0;
+    for (int j = 0; j < H; ++j) {
+      ox[m] = pv[j * 4]; oy[m] = pv[j * 4 + 1]; ovx[m] = pv[j * 4 + 2]; ovy[m] = pv[j * 4 + 3];
+      orad[m] = (float)((double)gr[j * 4 + 3] + 0.01 + safety);
+      ++m;
+    }
+    for (int k = 0; k < S; ++k) {
+      const float *sd = s->st.stat + ((size_t)e * Sm + k) * 4;
+      ox[m] = sd[0]; oy[m] = sd[1]; ovx[m] = 0.0f; ovy[m] = 0.0f;
+      orad[m] = (float)((double)sd[2] + 0.01 + safety);
+      ++m;
+    }
+    const float *rp = s->st.rob_pv + (size_t)e * 4;
+    const float *rg = s->st.rob_gr + (size_t)e * 4;
+    float r_self, prefx, prefy, vx, vy;
+    orca_self_params(rp[0], rp[1], rg[0], rg[1], rg[3], safety, &r_self, &prefx, &prefy);
+    ebc_ref_orca_agent(rp[0], rp[1], rp[2], rp[3], r_self, rg[2], prefx, prefy, m, ox, oy, ovx, ovy,
+                       orad, c->orca_neighbor_dist, c->orca_max_neighbors, c->orca_time_horizon,
+                       (float)c->time_step, &vx, &vy);
+    out[(size_t)e * 2] = (double)vx;
+    out[(size_t)e * 2 + 1] = (double)vy;
+  }
+  return EBC_OK;
+}
+
+/* simulator/utils/collisions.py:4-26 with (x3, y3) = (0, 0). */
+static inline double point_to_segment_dist0(double x1, double y1, double x2, double y2) {
+  const double px = x2 - x1, py = y2 - y1;
+  if (px == 0.0 && py == 0.0) return sqrt((0.0 - x1) * (0.0 - x1) + (0.0 - y1) * (0.0 - y1));
+  double u = ((0.0 - x1) * px + (0.0 - y1) * py) / (px * px + py * py);
+  if (u > 1.0) u = 1.0;
+  else if (u < 0.0) u = 0.0;
+  const double x = x1 + u * px, y = y1 + u * py;
+  return sqrt((x - 0.0) * (x - 0.0) + (y - 0.0) * (y - 0.0));
+}
+
+typedef struct {
+  double dmin[3];
+  int coll[3];
+  int coll_obst;
+  double end_x, end_y; /* robot next position (agent.py:164-188) */
+  double dist_to_goal;
+  double reward;
+  int done, event;
+} outcome_t;
+
+/* env.py:424-444: compute_collisions + Reward.compute for one (episode, action).
+ * a0, a1 = (vx, vy) holonomic or (v, r) otherwise. */
+static void evaluate_action(const ebc_sim *s, int e, double a0, double a1, outcome_t *o) {
+  const ebc_config *c = &s->cfg;
+  const int Hm = c->max_humans;
+  const int H = s->st.hum_count[e];
+  const float *pv = s->st.hum_pv + (size_t)e * Hm * 4;
+  const float *gr = s->st.hum_gr + (size_t)e * Hm * 4;
+  const uint8_t *ty = s->st.hum_type + (size_t)e * Hm;
+  const float *rp = s->st.rob_pv + (size_t)e * 4;
+  const float *rg = s->st.rob_gr + (size_t)e * 4;
+  const double rpx = rp[0], rpy = rp[1], rrad = rg[3], theta = s->st.rob_theta[e];
+  const double dt = c->time_step;
+  /* robot velocity implied by the action (collisions.py:37-42) and next position
+   * (agent.py:164-176) */
+  double avx, avy;
+  if (c->robot_kinematics == EBC_KIN_HOLONOMIC) {
+    avx = a0;
+    avy = a1;
+    o->end_x = rpx + a0 * dt;
+    o->end_y = rpy + a1 * dt;
+  } else {
+    const double th = theta + a1;
+    avx = a0 * cos(a1 + theta);
+    avy = a0 * sin(a1 + theta);
+    o->end_x = rpx + cos(th) * a0 * dt;
+    o->end_y = rpy + sin(th) * a0 * dt;
+  }
+  /* env.py:303-338: per type, list order, stop at the first collision */
+  for (int t = 0; t < 3; ++t) { o->dmin[t] = INFINITY; o->coll[t] = 0; }
+  for (int h = 0; h < H; ++h) {
+    const int t = ty[h];
+    if (t > 2 || o->coll[t]) continue;
+    const double px = (double)pv[h * 4] - rpx, py = (double)pv[h * 4 + 1] - rpy;
+    const double vx = (double)pv[h * 4 + 2] - avx, vy = (double)pv[h * 4 + 3] - avy;
+    const double ex = px + vx * dt, ey = py + vy * dt;
+    const double closest = point_to_segment_dist0(px, py, ex, ey) - (double)gr[h * 4 + 3] - rrad;
+    if (closest < 0.0) o->coll[t] = 1;
+    else if (closest < o->dmin[t]) o->dmin[t] = closest;
+  }
+  /* env.py:227-261: occupancy-grid window test == integer AABB overlap against the
+   * zero-cell rectangles of scene.map */
+  o->coll_obst = 0;
+  {
+    const int ix = (int)rint((o->end_x + c->map_size_m / 2.0) / c->map_resolution);
+    const int iy = (int)rint((o->end_y + c->map_size_m / 2.0) / c->map_resolution);
+    const int sz = (int)ceil(rrad / sqrt(2.0) / c->map_resolution);
+    const int G = (int)rint(c->map_size_m / c->map_resolution);
+    int sx = ix - sz, ex = sx + sz * 2, sy = iy - sz, ey = sy + sz * 2;
+    if (sx < 0) sx = 0;
+    if (ex > G) ex = G;
+    if (sy < 0) sy = 0;
+    if (ey > G) ey = G;
+    if (ex > sx && ey > sy) {
+      const int R = s->st.rect_count[e];
+      const int16_t *rc = s->st.rect + (size_t)e * c->max_rects * 4;
+      for (int j = 0; j < R; ++j)
+        if (sx < rc[j * 4 + 2] && rc[j * 4] < ex && sy < rc[j * 4 + 3] && rc[j * 4 + 1] < ey) {
+          o->coll_obst = 1;
+          break;
+        }
+    }
+  }
+  /* reward.py:80-181 */
+  const double gdx = o->end_x - (double)rg[0], gdy = o->end_y - (double)rg[1];
+  const double dist = sqrt(gdx * gdx + gdy * gdy);
+  o->dist_to_goal = dist;
+  const int reaching = dist < rrad;
+  const double goal_reward = c->has_max_goal_distance ? 1.0 - dist / c->max_goal_distance : 0.0;
+  double reward = c->new_reward ? goal_reward : 0.0;
+  const double gt = s->st.time[e];
+  int done, ev;
+  if (gt >= c->time_limit) { done = 1; ev = EBC_EV_TIMEOUT; }
+  else if (o->coll[EBC_CHILD]) { reward += c->collision_penalty_child; done = 1; ev = EBC_EV_COLLISION_CHILD; }
+  else if (o->coll[EBC_BICYCLE]) { reward += c->collision_penalty_bicycle; done = 1; ev = EBC_EV_COLLISION_BICYCLE; }
+  else if (o->coll[EBC_ADULT]) { reward += c->collision_penalty_adult; done = 1; ev = EBC_EV_COLLISION_ADULT; }
+  else if (o->coll_obst) { reward += c->collision_penalty_obstacle; done = 1; ev = EBC_EV_COLLISION_OBSTACLE; }
+  else if (reaching) {
+    if (c->new_reward) {
+      double tr; /* reward.py:8-14 */
+      if (gt < c->time_good) tr = 1.0;
+      else if (gt <= c->time_max) tr = (c->time_max - gt) / (c->time_max - c->time_good);
+      else tr = 0.0;
+      reward += tr;
+    } else {
+      reward += c->success_reward;
+    }
+    done = 1; ev = EBC_EV_REACH_GOAL;
+  } else if (o->dmin[EBC_CHILD] < c->discomfort_dist_child) {
+    reward = (o->dmin[EBC_CHILD] - c->discomfort_dist_child) * c->discomfort_penalty_factor_child * dt;
+    done = 0; ev = EBC_EV_DANGER;
+  } else if (o->dmin[EBC_BICYCLE] < c->discomfort_dist_bicycle) {
+    reward = (o->dmin[EBC_BICYCLE] - c->discomfort_dist_bicycle) * c->discomfort_penalty_factor_bicycle * dt;
+    done = 0; ev = EBC_EV_DANGER;
+  } else if (o->dmin[EBC_ADULT] < c->discomfort_dist_adult) {
+    reward = (o->dmin[EBC_ADULT] - c->discomfort_dist_adult) * c->discomfort_penalty_factor_adult * dt;
+    done = 0; ev = EBC_EV_DANGER;
+  } else if (c->robot_kinematics != EBC_KIN_HOLONOMIC && fabs(a1) > 0.0 && c->rotation_penalty_factor != 0.0) {
+    reward = fabs(a1) * c->rotation_penalty_factor;
+    done = 0; ev = EBC_EV_NOTHING;
+  } else { reward = 0.0; done = 0; ev = EBC_EV_NOTHING; }
+  o->reward = reward; o->done = done; o->event = ev;
+}
+
+/* rl/policy/cadrl.py:236-337 in fp32, one row.  js = the 15-tuple of state.py:19-30,65-66
+ * already narrowed to fp32 (torch.Tensor([...]) at multi_human_rl.py:52-60). */
+static void rotate_row(const float *js, int rotate_theta, int with_type, float *out) {
+  const float dx = js[5] - js[0], dy = js[6] - js[1];
+  const float rot = atan2f(js[6] - js[1], js[5] - js[0]);
+  const float cr = cosf(rot), sr = sinf(rot);
+  out[0] = sqrtf(dx * dx + dy * dy);                 /* dg */
+  out[1] = js[7];                                    /* v_pref */
+  out[2] = rotate_theta ? js[8] - rot : 0.0f;        /* theta */
+  out[3] = js[4];                                    /* radius */
+  out[4] = js[2] * cr + js[3] * sr;                  /* vx */
+  out[5] = js[3] * cr - js[2] * sr;                  /* vy */
+  out[6] = (js[9] - js[0]) * cr + (js[10] - js[1]) * sr;  /* px1 */
+  out[7] = (js[10] - js[1]) * cr - (js[9] - js[0]) * sr;  /* py1 */
+  out[8] = js[11] * cr + js[12] * sr;                /* vx1 */
+  out[9] = js[12] * cr - js[11] * sr;                /* vy1 */
+  out[10] = js[13];                                  /* radius1 */
+  const float ax = js[0] - js[9], ay = js[1] - js[10];
+  out[11] = sqrtf(ax * ax + ay * ay);                /* da */
+  out[12] = js[4] + js[13];                          /* radius sum */
+  if (with_type) {
+    const int t = (int)js[14];
+    for (int k = 0; k < 4; ++k) out[13 + k] = (k == t) ? 1.0f : 0.0f;
+  }
+}
+
+/* K3: rl/policy/multi_human_rl.py:38-61 + env.onestep_lookahead (env.py:207-209). */
+int ebc_ref_lookahead(ebc_sim *s, float *vin, double *reward, uint8_t *done, uint8_t *event) {
+  if (!s || !s->bound) return fail(s, EBC_ERR_UNBOUND, "ebc_lookahead: state not bound");
+  if (!s->have_actions) return fail(s, EBC_ERR_UNBOUND, "ebc_lookahead: action table not set");
+  const ebc_config *c = &s->cfg;
+  const int Hm = c->max_humans, Sm = c->max_statics, A = c->n_actions;
+  const int n = Hm + Sm, D = c->with_agent_type ? 17 : 13;
+  const double dt = c->time_step;
+#pragma omp parallel for schedule(static) num_threads(g_threads)
+  for (int e = 0; e < c->n_episodes; ++e) {
+    const int H = s->st.hum_count[e], S = s->st.stat_count[e];
+    const float *pv = s->st.hum_pv + (size_t)e * Hm * 4;
+    const float *gr = s->st.hum_gr + (size_t)e * Hm * 4;
+    const float *nv = s->st.hum_nv + (size_t)e * Hm * 2;
+    const uint8_t *ty = s->st.hum_type + (size_t)e * Hm;
+    const float *rp = s->st.rob_pv + (size_t)e * 4;
+    const float *rg = s->st.rob_gr + (size_t)e * 4;
+    const double theta = s->st.rob_theta[e];
+    for (int a = 0; a < A; ++a) {
+      const double a0 = s->actions[a * 2], a1 = s->actions[a * 2 + 1];
+      outcome_t o;
+      evaluate_action(s, e, a0, a1, &o);
+      const size_t ea = (size_t)e * A + a;
+      if (reward) reward[ea] = o.reward;
+      if (done) done[ea] = (uint8_t)o.done;
+      if (event) event[ea] = (uint8_t)o.event;
+      if (!vin) continue;
+      /* cadrl.py:118-165 propagate(robot FullState) in float64, narrowed by torch.Tensor */
+      float js[15];
+      if (c->robot_kinematics == EBC_KIN_HOLONOMIC) {
+        js[0] = (float)((double)rp[0] + a0 * dt);
+        js[1] = (float)((double)rp[1] + a1 * dt);
+        js[2] = (float)a0;
+        js[3] = (float)a1;
+        js[8] = (float)theta;
+      } else {
+        const double nth = theta + a1;
+        const double nvx = a0 * cos(nth), nvy = a0 * sin(nth);
+        js[0] = (float)((double)rp[0] + nvx * dt);
+        js[1] = (float)((double)rp[1] + nvy * dt);
+        js[2] = (float)nvx;
+        js[3] = (float)nvy;
+        js[8] = (float)nth;
+      }
+      js[4] = rg[3]; js[5] = rg[0]; js[6] = rg[1]; js[7] = rg[2];
+      float *rows = vin + ea * (size_t)n * D;
+      memset(rows, 0, sizeof(float) * (size_t)n * D);
+      for (int h = 0; h < H; ++h) { /* agent.py:80-93 get_next_observable_state(orca action) */
+        js[9] = (float)((double)pv[h * 4] + (double)nv[h * 2] * dt);
+        js[10] = (float)((double)pv[h * 4 + 1] + (double)nv[h * 2 + 1] * dt);
+        js[11] = nv[h * 2];
+        js[12] = nv[h * 2 + 1];
+        js[13] = gr[h * 4 + 3];
+        js[14] = (float)ty[h];
+        rotate_row(js, c->rotate_theta, c->with_agent_type, rows + (size_t)h * D);
+      }
+      for (int k = 0; k < S; ++k) { /* env.py:457-458 static discs, type 3 */
+        const float *sd = s->st.stat + ((size_t)e * Sm + k) * 4;
+        js[9] = sd[0]; js[10] = sd[1]; js[11] = 0.0f; js[12] = 0.0f; js[13] = sd[2];
+        js[14] = (float)EBC_ADULT_STATIC;
+        rotate_row(js, c->rotate_theta, c->with_agent_type, rows + (size_t)(H + k) * D);
+      }
+    }
+  }
+  return EBC_OK;
+}
+
+/* rl/policy/multi_human_rl.py:128-149: rotate(current joint state). */
+int ebc_ref_transform(ebc_sim *s, float *out) {
+  if (!s || !s->bound) return fail(s, EBC_ERR_UNBOUND, "ebc_transform: state not bound");
+  const ebc_config *c = &s->cfg;
+  const int Hm = c->max_humans, Sm = c->max_statics;
+  const int n = Hm + Sm, D = c->with_agent_type ? 17 : 13;
+#pragma omp parallel for schedule(static) num_threads(g_threads)
+  for (int e = 0; e < c->n_episodes; ++e) {
+    const int H = s->st.hum_count[e], S = s->st.stat_count[e];
+    const float *pv = s->st.hum_pv + (size_t)e * Hm * 4;
+    const float *gr = s->st.hum_gr + (size_t)e * Hm * 4;
+    const uint8_t *ty = s->st.hum_type + (size_t)e * Hm;
+    const float *rp = s->st.rob_pv + (size_t)e * 4;
+    const float *rg = s->st.rob_gr + (size_t)e * 4;
+    float js[15];
+    js[0] = rp[0]; js[1] = rp[1]; js[2] = rp[2]; js[3] = rp[3];
+    js[4] = rg[3]; js[5] = rg[0]; js[6] = rg[1]; js[7] = rg[2]; js[8] = s->st.rob_theta[e];
+    float *rows = out + (size_t)e * n * D;
+    memset(rows, 0, sizeof(float) * (size_t)n * D);
+    for (int h = 0; h < H; ++h) {
+      js[9] = pv[h * 4]; js[10] = pv[h * 4 + 1]; js[11] = pv[h * 4 + 2]; js[12] = pv[h * 4 + 3];
+      js[13] = gr[h * 4 + 3]; js[14] = (float)ty[h];
+      rotate_row(js, c->rotate_theta, c->with_agent_type, rows + (size_t)h * D);
+    }
+    for (int k = 0; k < S; ++k) {
+      const float *sd = s->st.stat + ((size_t)e * Sm + k) * 4;
+      js[9] = sd[0]; js[10] = sd[1]; js[11] = 0.0f; js[12] = 0.0f; js[13] = sd[2];
+      js[14] = (float)EBC_ADULT_STATIC;
+      rotate_row(js, c->rotate_theta, c->with_agent_type, rows + (size_t)(H + k) * D);
+    }
+  }
+  return EBC_OK;
+}
+
+/* nn.Linear: y = W x + b, fp32 in / fp32 out, accumulated in fp64 and rounded once (the
+ * correctly-rounded result the reference's MKL sgemm approximates). */
+static void linear_f(const float *w, const float *b, int in, int out, const float *x, float *y,
+                     int relu) {
+  for (int o = 0; o < out; ++o) {
+    double acc = (double)b[o];
+    const float *wr = w + (size_t)o * in;
+    for (int k = 0; k < in; ++k) acc += (double)wr[k] * (double)x[k];
+    float v = (float)acc;
+    y[o] = (relu && v < 0.0f) ? 0.0f : v;
+  }
+}
+
+/* rl/policy/sarl.py:38-82, one state of `rows` real rows. */
+static float value_forward(const ebc_sim *s, const float *x, int rows, int stride) {
+  const int D = s->D;
+  const int d1a = s->lin[0].out, h1d = s->lin[1].out, d2a = s->lin[2].out, h2d = s->lin[3].out;
+  const int a1d = s->lin[4].out, a2d = s->lin[5].out;
+  float *h1 = (float *)malloc(sizeof(float) * (size_t)rows * (h1d + h2d + 1) + sizeof(float) * 4096);
+  float *h2 = h1 + (size_t)rows * h1d;
+  float *sc = h2 + (size_t)rows * h2d;
+  float *tmp = sc + rows; /* scratch >= 4096 floats */
+  float *tmp2 = tmp + 1024, *att_in = tmp + 2048;
+  for (int r = 0; r < rows; ++r) {
+    linear_f(s->lin[0].w, s->lin[0].b, D, d1a, x + (size_t)r * stride, tmp, 1);
+    linear_f(s->lin[1].w, s->lin[1].b, d1a, h1d, tmp, h1 + (size_t)r * h1d, 1); /* last_relu */
+    linear_f(s->lin[2].w, s->lin[2].b, h1d, d2a, h1 + (size_t)r * h1d, tmp, 1);
+    linear_f(s->lin[3].w, s->lin[3].b, d2a, h2d, tmp, h2 + (size_t)r * h2d, 0);
+  }
+  float *g = tmp2 + 512;
+  if (s->with_global) { /* sarl.py:51-60 torch.mean over the entity dimension */
+    for (int k = 0; k < h1d; ++k) {
+      double acc = 0.0;
+      for (int r = 0; r < rows; ++r) acc += (double)h1[(size_t)r * h1d + k];
+      g[k] = (float)(acc / (double)rows);
+    }
+  }
+  for (int r = 0; r < rows; ++r) {
+    memcpy(att_in, h1 + (size_t)r * h1d, sizeof(float) * h1d);
+    if (s->with_global) memcpy(att_in + h1d, g, sizeof(float) * h1d);
+    linear_f(s->lin[4].w, s->lin[4].b, s->lin[4].in, a1d, att_in, tmp, 1);
+    linear_f(s->lin[5].w, s->lin[5].b, a1d, a2d, tmp, tmp2, 1);
+    linear_f(s->lin[6].w, s->lin[6].b, a2d, 1, tmp2, &sc[r], 0);
+  }
+  /* sarl.py:69-70 masked softmax without max subtraction */
+  double sum = 0.0;
+  for (int r = 0; r < rows; ++r) {
+    const float e = (sc[r] != 0.0f) ? expf(sc[r]) : 0.0f;
+    sc[r] = e;
+    sum += (double)e;
+  }
+  const float fsum = (float)sum;
+  float *joint = tmp; /* [self_dim + h2d] */
+  for (int k = 0; k < s->self_dim; ++k) joint[k] = x[k];
+  for (int k = 0; k < h2d; ++k) {
+    double acc = 0.0;
+    for (int r = 0; r < rows; ++r) acc += (double)(sc[r] / fsum) * (double)h2[(size_t)r * h2d + k];
+    joint[s->self_dim + k] = (float)acc;
+  }
+  float *m1 = tmp2, *m2 = att_in, *m3 = tmp2 + 512;
+  float v;
+  linear_f(s->lin[7].w, s->lin[7].b, s->lin[7].in, s->lin[7].out, joint, m1, 1);
+  linear_f(s->lin[8].w, s->lin[8].b, s->lin[8].in, s->lin[8].out, m1, m2, 1);
+  linear_f(s->lin[9].w, s->lin[9].b, s->lin[9].in, s->lin[9].out, m2, m3, 1);
+  linear_f(s->lin[10].w, s->lin[10].b, s->lin[10].in, 1, m3, &v, 0);
+  free(h1);
+  return v;
+}
+
+/* K4 */
+int ebc_ref_value(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row_count,
+                  float *values) {
+  if (!s || !s->have_weights) return fail(s, EBC_ERR_UNBOUND, "ebc_value: weights not set");
+  const ebc_config *c = &s->cfg;
+  for (int i = 0; i < 11; ++i)
+    if (s->lin[i].out > 512 || s->lin[i].in > 1024) return fail(s, EBC_ERR_INVALID, "ebc_value: layer too wide for the oracle scratch");
+  const int n = c->max_humans + c->max_statics, D = s->D, A = c->n_actions;
+  if (!row_count && !s->bound) return fail(s, EBC_ERR_UNBOUND, "ebc_value: state not bound");
+#pragma omp parallel for schedule(dynamic, 16) num_threads(g_threads)
+  for (int64_t i = 0; i < n_states; ++i) {
+    int rows;
+    if (row_count) rows = row_count[i];
+    else {
+      const int64_t e = i / A;
+      rows = s->st.hum_count[e] + s->st.stat_count[e];
+    }
+    values[i] = value_forward(s, vin + (size_t)i * n * D, rows, D);
+  }
+  return EBC_OK;
+}
+
+/* K5: multi_human_rl.py:25-26,72-82. */
+int ebc_ref_select(ebc_sim *s, const double *reward, const float *values, double *action_values,
+                   int32_t *argmax, uint8_t *nan_flag) {
+  if (!s || !s->bound) return fail(s, EBC_ERR_UNBOUND, "ebc_select: state not bound");
+  const ebc_config *c = &s->cfg;
+  const int A = c->n_actions;
+  for (int e = 0; e < c->n_episodes; ++e) {
+    const float *rp = s->st.rob_pv + (size_t)e * 4;
+    const float *rg = s->st.rob_gr + (size_t)e * 4;
+    const double disc = pow(c->gamma, c->time_step * (double)rg[2]);
+    double best = -INFINITY;
+    int arg = -1;
+    for (int a = 0; a < A; ++a) {
+      const double v = reward[(size_t)e * A + a] + disc * (double)values[(size_t)e * A + a];
+      if (action_values) action_values[(size_t)e * A + a] = v;
+      if (v > best) { best = v; arg = a; }
+    }
+    if (nan_flag) nan_flag[e] = (uint8_t)(arg < 0);
+    if (arg < 0) arg = 0;
+    /* policy.py:43-54 reach_destination -> zero action */
+    const double dy = (double)rp[1] - (double)rg[1], dx = (double)rp[0] - (double)rg[0];
+    if (sqrt(dy * dy + dx * dx) < (double)rg[3]) arg = 0;
+    argmax[e] = arg;
+  }
+  return EBC_OK;
+}
+
+/* K2: env.step(update=True), env.py:388-466 + compute_step_update :340-386 + agent.py:202-228. */
+int ebc_ref_step(ebc_sim *s, const int32_t *action_idx, const double *action, const uint8_t *active,
+                 double *reward, uint8_t *done, uint8_t *event, double *dmin, double *dist_to_goal) {
+  if (!s || !s->bound) return fail(s, EBC_ERR_UNBOUND, "ebc_step: state not bound");
+  if ((action_idx == NULL) == (action == NULL)) return fail(s, EBC_ERR_INVALID, "ebc_step: give exactly one of action_idx / action");
+  if (action_idx && !s->have_actions) return fail(s, EBC_ERR_UNBOUND, "ebc_step: action table not set");
+  const ebc_config *c = &s->cfg;
+  const int Hm = c->max_humans;
+  const double dt = c->time_step;
+#pragma omp parallel for schedule(static) num_threads(g_threads)
+  for (int e = 0; e < c->n_episodes; ++e) {
+    if (active && !active[e]) continue;
+    double a0, a1;
+    if (action_idx) {
+      int ai = action_idx[e];
+      if (ai < 0 || ai >= c->n_actions) ai = 0;
+      a0 = s->actions[ai * 2]; a1 = s->actions[ai * 2 + 1];
+    } else { a0 = action[(size_t)e * 2]; a1 = action[(size_t)e * 2 + 1]; }
+    outcome_t o;
+    evaluate_action(s, e, a0, a1, &o);
+    if (reward) reward[e] = o.reward;
+    if (done) done[e] = (uint8_t)o.done;
+    if (event) event[e] = (uint8_t)o.event;
+    if (dmin) { dmin[(size_t)e * 3] = o.dmin[0]; dmin[(size_t)e * 3 + 1] = o.dmin[1]; dmin[(size_t)e * 3 + 2] = o.dmin[2]; }
+    if (dist_to_goal) dist_to_goal[e] = o.dist_to_goal;
+    /* robot.step(action): agent.py:202-228 */
+    float *rp = s->st.rob_pv + (size_t)e * 4;
+    rp[0] = (float)o.end_x;
+    rp[1] = (float)o.end_y;
+    if (c->robot_kinematics == EBC_KIN_HOLONOMIC) {
+      rp[2] = (float)a0;
+      rp[3] = (float)a1;
+    } else {
+      const double th = fmod((double)s->st.rob_theta[e] + a1, 2.0 * M_PI);
+      const double thw = th < 0.0 ? th + 2.0 * M_PI : th; /* Python % is non-negative */
+      s->st.rob_theta[e] = (float)thw;
+      rp[2] = (float)(a0 * cos(thw));
+      rp[3] = (float)(a0 * sin(thw));
+    }
+    /* humans: agent.step(ActionXY) holonomic */
+    const int H = s->st.hum_count[e];
+    float *pv = s->st.hum_pv + (size_t)e * Hm * 4;
+    const float *nv = s->st.hum_nv + (size_t)e * Hm * 2;
+    for (int h = 0; h < H; ++h) {
+      pv[h * 4] = (float)((double)pv[h * 4] + (double)nv[h * 2] * dt);
+      pv[h * 4 + 1] = (float)((double)pv[h * 4 + 1] + (double)nv[h * 2 + 1] * dt);
+      pv[h * 4 + 2] = nv[h * 2];
+      pv[h * 4 + 3] = nv[h * 2 + 1];
+    }
+    s->st.time[e] += dt;
+  }
+  return EBC_OK;
+}

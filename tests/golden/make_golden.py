@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""Generate golden input/output vectors by running the UNMODIFIED reference.
+
+Runs only in the build container (needs /root/reference); the outputs (*.npz, *.json in
+this directory) are committed and are what the tests read on the GPU box.
+
+    PYTHONPATH=oracle/shims:/root/reference python tests/golden/make_golden.py   (cwd = /root/reference)
+or simply
+    python tests/golden/make_golden.py          (re-executes itself with that environment)
+
+What is recorded (all from reference code, nothing from this repo's package):
+  * the reference's own known-answer cases (tests/test_collisions.py:13-143)
+  * the action tables of rl/policy/cadrl.py:91-116
+  * step traces: from an fp32-representable state, the humans' ORCA actions, all 81
+    onestep_lookahead outcomes, the rotated value-network inputs and outputs, the argmax,
+    and the committed env.step result; the state is re-rounded to fp32 after every step so
+    that every step is a single-step comparison "from identical states".
+  * episode outcomes of the reference's fixed scenes (tests/test_collisions_simulation.py).
+  * a few generated scenes (scene_generator.py) for the host-side scene generator.
+
+`rvo2` is supplied by oracle/shims/rvo2.py (the C restatement in oracle/ebc_oracle.c); see
+that file's header for what this does and does not pin.
+"""
+import configparser
+import json
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("EBC_REFERENCE", "/root/reference")
+
+if os.environ.get("EBC_GOLDEN_CHILD") != "1":
+    env = dict(os.environ)
+    env["EBC_GOLDEN_CHILD"] = "1"
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(REPO, "oracle", "shims"), REF, os.path.join(REF, "tests")])
+    sys.exit(subprocess.call([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], cwd=REF, env=env))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import gym  # noqa: E402
+from simulator.agents.robot import Robot  # noqa: E402
+from simulator.utils.state import ObservableState  # noqa: E402
+from simulator.utils.info import *  # noqa: E402,F401,F403
+from simulator.utils import info as info_mod  # noqa: E402
+from rl.policy.policy_factory import policy_factory  # noqa: E402
+
+torch.set_num_threads(1)
+
+EVENT_CODE = {"Nothing": 0, "Danger": 1, "ReachGoal": 2, "CollisionAdult": 3, "CollisionBicycle": 4,
+              "CollisionChild": 5, "CollisionObstacle": 6, "Timeout": 7}
+
+
+def f32(x):
+    return float(np.float32(x))
+
+
+def make(env_cfg_path, policy_cfg_path, model_path, policy_name, phase="test", env_overrides=None,
+         policy_overrides=None):
+    env_config = configparser.RawConfigParser()
+    env_config.read(env_cfg_path)
+    for (sec, key), val in (env_overrides or {}).items():
+        env_config.set(sec, key, str(val))
+    env = gym.make("EntityBasedCollisionAvoidance-v0")
+    env.configure(env_config)
+    env.get_local_map_angular = lambda *a, **k: None  # unused by every shipped policy
+    robot = Robot(env_config, "robot")
+    env.set_robot(robot)
+    policy = policy_factory[policy_name]()
+    policy_config = None
+    if policy_cfg_path is not None:
+        policy_config = configparser.RawConfigParser()
+        policy_config.read(policy_cfg_path)
+        for (sec, key), val in (policy_overrides or {}).items():
+            policy_config.set(sec, key, str(val))
+        policy.configure(policy_config)
+    if model_path is not None:
+        policy.get_model().load_state_dict(torch.load(model_path, map_location="cpu"))
+    robot.set_policy(policy)
+    policy.set_phase(phase)
+    policy.set_device("cpu")
+    return env, policy, robot, env_config, policy_config
+
+
+def humans_of(env):
+    return env.scene.adults + env.scene.bicycles + env.scene.children
+
+
+def round_state_to_f32(env):
+    """Make the reference state fp32-representable so that both sides see identical inputs."""
+    for ag in [env.robot] + humans_of(env):
+        for name in ("px", "py", "vx", "vy", "gx", "gy", "radius", "v_pref", "theta"):
+            setattr(ag, name, f32(getattr(ag, name)))
+    new_static = []
+    for s in env.scene.static_obstacles_as_pedestrians:
+        new_static.append(ObservableState(f32(s.px), f32(s.py), 0, 0, f32(s.radius), s.obj_type))
+    env.scene.static_obstacles_as_pedestrians = new_static
+    ob = [h.get_observable_state() for h in humans_of(env)]
+    ob += env.scene.static_obstacles_as_pedestrians
+    return ob
+
+
+def snapshot(env):
+    hs = humans_of(env)
+    rb = env.robot
+    d = {
+        "hum_pv": np.array([[h.px, h.py, h.vx, h.vy] for h in hs], dtype=np.float64).reshape(-1, 4),
+        "hum_gr": np.array([[h.gx, h.gy, h.v_pref, h.radius] for h in hs], dtype=np.float64).reshape(-1, 4),
+        "hum_type": np.array([int(h.agent_type) for h in hs], dtype=np.uint8),
+        "stat": np.array([[s.px, s.py, s.radius, 0.0] for s in env.scene.static_obstacles_as_pedestrians],
+                         dtype=np.float64).reshape(-1, 4),
+        "rob_pv": np.array([rb.px, rb.py, rb.vx, rb.vy], dtype=np.float64),
+        "rob_gr": np.array([rb.gx, rb.gy, rb.v_pref, rb.radius], dtype=np.float64),
+        "rob_theta": np.float64(rb.theta),
+        "time": np.float64(env.global_time),
+    }
+    return d
+
+
+def config_dict(env, env_config, policy, policy_config):
+    rw = env.reward
+    kin = getattr(policy, "kinematics", "holonomic")
+    d = {
+        "time_step": env.time_step, "time_limit": float(env.time_limit),
+        "new_reward": int(bool(rw.new_reward)),
+        "has_max_goal_distance": int(rw.max_goal_distance is not None),
+        "time_max": rw.time_max if rw.time_max is not None else 0.0,
+        "time_good": rw.time_good,
+        "max_goal_distance": rw.max_goal_distance if rw.max_goal_distance is not None else 0.0,
+        "success_reward": rw.success_reward,
+        "collision_penalty_adult": rw.collision_penalty_adult or 0.0,
+        "collision_penalty_bicycle": rw.collision_penalty_bicycle or 0.0,
+        "collision_penalty_obstacle": rw.collision_penalty_obstacle or 0.0,
+        "collision_penalty_child": rw.collision_penalty_child or 0.0,
+        "discomfort_dist_adult": rw.discomfort_dist_adult,
+        "discomfort_dist_bicycle": rw.discomfort_dist_bicycle,
+        "discomfort_dist_child": rw.discomfort_dist_child,
+        "discomfort_penalty_factor_adult": rw.discomfort_penalty_factor_adult,
+        "discomfort_penalty_factor_bicycle": rw.discomfort_penalty_factor_bicycle,
+        "discomfort_penalty_factor_child": rw.discomfort_penalty_factor_child,
+        "rotation_penalty_factor": rw.rotation_penalty_factor,
+        "map_size_m": env.scene.map_size_m, "map_resolution": env.scene.map_resolution,
+        "robot_kinematics": 0 if kin == "holonomic" else 1,
+        "rotate_theta": int(kin == "unicycle"),
+        "with_agent_type": int(bool(getattr(policy, "with_agent_type", False))),
+        "robot_visible": int(bool(env.robot.visible)),
+        "gamma": getattr(policy, "gamma", None) or 0.9,
+        "human_policy": [0 if env_config.get(sec, "policy", fallback="orca") == "orca" else 1
+                         for sec in ("adults", "bicycles", "children") if True],
+    }
+    return d
+
+
+def info_fields(info):
+    def g(name):
+        v = getattr(info, name, None)
+        return np.nan if v is None else float(v)
+    return np.array([g("dist_to_goal"), g("dmin_adult"), g("dmin_bicycle"), g("dmin_child"), g("min_dist")],
+                    dtype=np.float64)
+
+
+def trace(name, env, policy, robot, env_config, policy_config, reset_kwargs, n_steps, tensor_steps,
+          out):
+    """Record a step trace.  `tensor_steps` = steps whose full value-net inputs are kept."""
+    env.reset("test", **reset_kwargs)
+    ob = round_state_to_f32(env)
+    sarl = hasattr(policy, "action_space")
+    rec = {"cfg": config_dict(env, env_config, policy, policy_config), "steps": []}
+    zero = (env.scene.map == 0)
+    rec_map = np.packbits(zero.astype(np.uint8), axis=None)
+    arrays = {"map_zero_packed": rec_map, "map_shape": np.array(env.scene.map.shape)}
+
+    look = []
+    orig_look = env.onestep_lookahead
+
+    def look_wrap(action):
+        r = orig_look(action)
+        look.append(r)
+        return r
+
+    env.onestep_lookahead = look_wrap
+    vin, vout = [], []
+    if sarl and policy.get_model() is not None:
+        def fwd_hook(m, i, o):
+            vin.append(i[0].detach().numpy().copy())
+            vout.append(float(o.item()))
+
+        policy.get_model().register_forward_hook(fwd_hook)
+    orca_actions = []
+    orig_update = env.compute_step_update
+
+    def update_wrap(action, agents_actions, all_agents):
+        orca_actions.append([(a.vx, a.vy) for a in agents_actions])
+        return orig_update(action, agents_actions, all_agents)
+
+    env.compute_step_update = update_wrap
+
+    done = False
+    t = 0
+    while not done and t < n_steps:
+        del look[:], vin[:], vout[:], orca_actions[:]
+        snap = snapshot(env)
+        for k, v in snap.items():
+            arrays["s%03d_%s" % (t, k)] = v
+        action = robot.act(ob, local_map=None, env=env)
+        step = {"t": t}
+        if sarl and len(look) > 0:
+            A = len(policy.action_space)
+            assert len(look) == A and len(vout) == A
+            arrays["s%03d_la_reward" % t] = np.array([r[1] for r in look], dtype=np.float64)
+            arrays["s%03d_la_done" % t] = np.array([r[2] for r in look], dtype=np.uint8)
+            arrays["s%03d_la_event" % t] = np.array([EVENT_CODE[type(r[3]).__name__] for r in look], dtype=np.uint8)
+            arrays["s%03d_la_value" % t] = np.array(vout, dtype=np.float32)
+            arrays["s%03d_action_values" % t] = np.array(policy.action_values, dtype=np.float64)
+            if t in tensor_steps:
+                arrays["s%03d_vin" % t] = np.concatenate(vin, axis=0).astype(np.float32)  # A x n x D
+                arrays["s%03d_la_next" % t] = np.array(
+                    [[[o.px, o.py, o.vx, o.vy, o.radius, int(o.obj_type)] for o in r[0]] for r in look],
+                    dtype=np.float64)
+            step["argmax"] = policy.action_space.index(action)
+            vals = np.array(policy.action_values)
+            srt = np.sort(vals)[::-1]
+            step["top2_gap"] = float(srt[0] - srt[1])
+        elif sarl:
+            step["argmax"] = 0  # reach_destination short-cut (multi_human_rl.py:25-26)
+            step["top2_gap"] = None
+        arrays["s%03d_action" % t] = np.array(list(action), dtype=np.float64)
+        ob_next, _, reward, done, info = env.step(action)
+        arrays["s%03d_orca" % t] = np.array(orca_actions[-1], dtype=np.float64).reshape(-1, 2)
+        step.update({"reward": float(reward), "done": bool(done), "event": EVENT_CODE[type(info).__name__]})
+        arrays["s%03d_info" % t] = info_fields(info)
+        after = snapshot(env)
+        for k in ("hum_pv", "rob_pv", "rob_theta", "time"):
+            arrays["s%03d_after_%s" % (t, k)] = after[k]
+        rec["steps"].append(step)
+        ob = round_state_to_f32(env)
+        t += 1
+    rec["n_steps"] = t
+    rec["final_event"] = rec["steps"][-1]["event"]
+    rec["final_time"] = float(env.global_time)
+    if sarl:
+        rec["actions"] = [list(a) for a in policy.action_space]
+        arrays["actions"] = np.array([list(a) for a in policy.action_space], dtype=np.float64)
+    env.onestep_lookahead = orig_look
+    env.compute_step_update = orig_update
+    arrays["meta_json"] = np.frombuffer(json.dumps(rec).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(out, name + ".npz"), **arrays)
+    print("  %-34s steps=%d final_event=%d t=%.2f" % (name, t, rec["final_event"], rec["final_time"]))
+    return rec
+
+
+def save_weights(path, out_name, out):
+    sd = torch.load(path, map_location="cpu")
+    np.savez_compressed(os.path.join(out, out_name), **{k: v.numpy() for k, v in sd.items()})
+
+
+def collisions_known_answers(out):
+    """tests/test_collisions.py:13-143 restated as data: inputs + the asserted boolean."""
+    import re
+    src = open(os.path.join(REF, "tests", "test_collisions.py")).read()
+    cases = []
+    for block in src.split("    def test_")[1:]:
+        nums = lambda pat: [float(x) for x in re.search(pat, block).groups()]  # noqa: E731
+        rs = nums(r"robot\.set\(([-\d.]+), ([-\d.]+), ")
+        rr = nums(r"robot\.radius = ([-\d.]+)")
+        as_ = nums(r"adult\.set\(([-\d.]+), ([-\d.]+), ")
+        ar = nums(r"adult\.radius = ([-\d.]+)")
+        ts = nums(r"time_step = ([-\d.]+)")
+        ac = nums(r"ActionXY\(([-\d.]+), ([-\d.]+)\)")
+        exp = re.search(r"assertEqual\(result\[1\], (True|False)\)", block).group(1) == "True"
+        cases.append({"name": block.split("(")[0], "robot_pos": rs, "robot_radius": rr[0], "adult_pos": as_,
+                      "adult_radius": ar[0], "time_step": ts[0], "action": ac, "collision": exp})
+    # cross-check against the reference function itself
+    from simulator.agents.agents import Adult
+    from simulator.utils.collisions import compute_collision_agent_with_robot
+    from simulator.utils.action import ActionXY
+    cfg = configparser.RawConfigParser()
+    cfg.read("configs/env_configs/env_adults_5_bikes_5_static_5.config")
+    for c in cases:
+        robot = Robot(cfg, "robot")
+        robot.kinematics = "holonomic"
+        robot.set(c["robot_pos"][0], c["robot_pos"][1], 0, 0, 0, 0, np.pi / 2)
+        robot.radius = c["robot_radius"]
+        adult = Adult(cfg, "adults")
+        adult.set(c["adult_pos"][0], c["adult_pos"][1], 0, 0, 0, 0, 0)
+        adult.radius = c["adult_radius"]
+        dmin, coll = compute_collision_agent_with_robot(adult, robot, ActionXY(*c["action"]), float("inf"), c["time_step"])
+        assert coll == c["collision"], c
+        c["dmin"] = None if np.isinf(dmin) else dmin
+    json.dump(cases, open(os.path.join(out, "collisions_known_answers.json"), "w"), indent=1)
+    print("  collisions_known_answers.json: %d cases" % len(cases))
+
+
+def action_tables(out):
+    from rl.policy.cadrl import CADRL
+    res = {}
+    for kin in ("holonomic", "unicycle"):
+        for vp in (0.6, 0.7, 1.0):
+            p = CADRL()
+            p.kinematics = kin
+            p.speed_samples = 5
+            p.rotation_samples = 16
+            p.build_action_space(vp)
+            res["%s_%g" % (kin, vp)] = np.array([list(a) for a in p.action_space], dtype=np.float64)
+    np.savez_compressed(os.path.join(out, "action_tables.npz"), **res)
+    print("  action_tables.npz")
+
+
+def scenes(out):
+    """Generated scenes for a few seeds (host scene generator)."""
+    res = {}
+    for tag, cfgp, over in [
+        ("adults5", "configs/test_configs/test_env_configs/env_adults_5.config", None),
+        ("ebcadrl", "data/eb-cadrl/adults_8_bikes_8_child_8_static_3_35_sec_new_reward_fix_static.config", None),
+    ]:
+        env, policy, robot, ec, pc = make(cfgp, None, None, "linear", env_overrides=over)
+        for seed in (1002, 1003, 1000000):
+            env.reset("test", scene_number=seed)
+            s = snapshot(env)
+            for k in ("hum_pv", "hum_gr", "hum_type", "stat"):
+                res["%s_%d_%s" % (tag, seed, k)] = s[k]
+            res["%s_%d_map_zero" % (tag, seed)] = np.packbits((env.scene.map == 0).astype(np.uint8), axis=None)
+            res["%s_%d_obstacles" % (tag, seed)] = np.array(
+                [[o.location_x, o.location_y, o.dim[0], o.dim[1]] for o in env.scene.obstacles], dtype=np.int64).reshape(-1, 4)
+    np.savez_compressed(os.path.join(out, "scenes.npz"), **res)
+    print("  scenes.npz")
+
+
+def main():
+    out = HERE
+    POL = "configs/test_configs/test_policy_configs/policy.config"
+    BASE_W = "model_weights/sarl_model_baseline.pth"
+    EB_ENV = "data/eb-cadrl/adults_8_bikes_8_child_8_static_3_35_sec_new_reward_fix_static.config"
+    EB_POL = "data/eb-cadrl/policy_x2_agent_type.config"
+    EB_W = "data/eb-cadrl/rl_model_val.pth"
+    print("writing goldens to", out)
+    collisions_known_answers(out)
+    action_tables(out)
+    save_weights(BASE_W, "weights_sarl_baseline.npz", out)
+    save_weights(EB_W, "weights_ebcadrl.npz", out)
+
+    # cfg1: the reference's own CPU-runnable case (BASELINE.json configs[0]); full episode
+    e = make("configs/test_configs/test_env_configs/env_adults_5.config", POL, BASE_W, "sarl")
+    trace("trace_cfg1_adults5_seed1002", *e, {"test_case": 2}, 400, {0, 10, 40}, out)
+    # with walls + bicycles (static discs in the observation, obstacle grid test live)
+    e = make("configs/test_configs/test_env_configs/env_adults_3_bikes_3_static_2.config", POL, BASE_W, "sarl")
+    trace("trace_adults3_bikes3_static2_seed1002", *e, {"test_case": 2}, 400, {0, 20}, out)
+    # EB-CADRL shipped config: 24 humans (maxNeighbors truncation live), 3 walls, D = 17
+    e = make(EB_ENV, EB_POL, EB_W, "sarl")
+    trace("trace_ebcadrl_h24_seed1000000", *e, {"scene_number": 1000000}, 16, {0, 8}, out)
+    # cfg2 shape: 4 adults + 3 bicycles + 3 children + 3 walls, D = 17
+    ov = {("sim", "adult_num"): 4, ("sim", "bicycle_num"): 3, ("sim", "children_num"): 3}
+    e = make(EB_ENV, EB_POL, EB_W, "sarl", env_overrides=ov)
+    trace("trace_cfg2_h10_seed7", *e, {"scene_number": 7}, 400, {0, 12}, out)
+    e = make(EB_ENV, EB_POL, EB_W, "sarl", env_overrides=ov)
+    trace("trace_cfg2_h10_seed11", *e, {"scene_number": 11}, 400, {3}, out)
+    # unicycle robot, kinematics string "unicycle" (theta_rel live) and "nonholonomic" (theta_rel = 0)
+    for kin in ("unicycle", "nonholonomic"):
+        e = make("configs/test_configs/test_env_configs/env_adults_5.config", POL, BASE_W, "sarl",
+                 policy_overrides={("action_space", "kinematics"): kin},
+                 env_overrides={("reward", "rotation_penalty_factor"): -0.01})
+        trace("trace_%s_adults5_seed1003" % kin, *e, {"test_case": 3}, 60, {0, 5}, out)
+    # robot visible to the humans (env.py:401-402)
+    e = make("configs/test_configs/test_env_configs/env_adults_5.config", POL, BASE_W, "sarl",
+             env_overrides={("robot", "visible"): "true"})
+    trace("trace_visible_adults5_seed1004", *e, {"test_case": 4}, 40, {0}, out)
+    # linear robot on the reference's fixed collision scenes (tests/test_collisions_simulation.py:12-39)
+    scenes_dir = os.path.join(REF, "tests", "test_scenes", "test_collisions")
+    for cfgp, names in [
+        ("configs/test_configs/test_env_configs/env_adults_5_bikes_5_static_5.config",
+         ["collision_with_adult", "collision_with_bicycle", "collision_with_static", "no_collisions"]),
+        ("configs/test_configs/test_env_configs/env_adults_5_bikes_0_static_5.config",
+         ["bikes_0_collision_with_adult_1", "bikes_0_collision_with_adult_2", "bikes_0_no_collisions"]),
+        ("configs/test_configs/test_env_configs/env_adults_5_child_5_static_5.config", ["collision_with_child"]),
+    ]:
+        for nm in names:
+            e = make(cfgp, None, None, "linear")
+            trace("scene_" + nm, *e, {"load_scene_path": os.path.join(scenes_dir, nm + ".json")}, 400, set(), out)
+    # ORCA robot (imitation learning, rl/train.py:99-143): safety_space 0.15 since the robot is invisible
+    e = make(EB_ENV, None, None, "orca", env_overrides=ov)
+    e[1].safety_space = 0.15
+    trace("trace_orca_robot_h10_seed5", *e, {"scene_number": 5}, 60, set(), out)
+    scenes(out)
+
+
+if __name__ == "__main__":
+    main()
