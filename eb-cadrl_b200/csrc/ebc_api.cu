@@ -1,0 +1,172 @@
+// ebc_api.cu — the extern "C" entry points of include/ebcadrl.h (libebcadrl.so).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "ebc_internal.cuh"
+
+static char g_create_err[256] = "";
+
+int ebc_fail(ebc_sim *s, int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(s ? s->err : g_create_err, 256, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int ebc_check_launch(ebc_sim *s, const char *what) {
+  const cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return ebc_fail(s, EBC_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
+  s->launches += 1;
+  return EBC_OK;
+}
+
+extern "C" {
+
+int ebc_abi_version(void) { return EBC_ABI_VERSION; }
+
+const char *ebc_last_error(const ebc_sim *s) { return s ? s->err : g_create_err; }
+
+int ebc_create(const ebc_config *cfg, int device, ebc_sim **out) {
+  if (!cfg || !out) return ebc_fail(nullptr, EBC_ERR_INVALID, "ebc_create: null argument");
+  *out = nullptr;
+  if (cfg->abi_version != EBC_ABI_VERSION)
+    return ebc_fail(nullptr, EBC_ERR_INVALID, "ebc_create: abi_version %d != %d", cfg->abi_version, EBC_ABI_VERSION);
+  if (cfg->n_episodes < 1 || cfg->max_humans < 1 || cfg->max_humans > 64 || cfg->max_statics < 0 ||
+      cfg->max_humans + cfg->max_statics > 64 || cfg->max_rects < 0 || cfg->n_actions < 1 || cfg->n_actions > 256 ||
+      cfg->orca_max_neighbors < 0 || cfg->orca_max_neighbors > 32 ||
+      cfg->max_humans + (cfg->robot_visible ? 1 : 0) > 64)
+    return ebc_fail(nullptr, EBC_ERR_INVALID,
+                    "ebc_create: config out of range (1<=Hmax<=64, Hmax+Smax<=64, 1<=A<=256, max_neighbors<=32)");
+  if (!(cfg->time_step > 0.0) || !(cfg->map_resolution > 0.0))
+    return ebc_fail(nullptr, EBC_ERR_INVALID, "ebc_create: time_step and map_resolution must be positive");
+  int count = 0;
+  cudaError_t err = cudaGetDeviceCount(&count);
+  if (err != cudaSuccess || count < 1)
+    return ebc_fail(nullptr, EBC_ERR_CUDA, "ebc_create: no CUDA device (%s); the hot path has no CPU fallback",
+                    cudaGetErrorString(err));
+  if (device < 0 || device >= count) return ebc_fail(nullptr, EBC_ERR_INVALID, "ebc_create: device %d of %d", device, count);
+  if ((err = cudaSetDevice(device)) != cudaSuccess)
+    return ebc_fail(nullptr, EBC_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(err));
+  ebc_sim *s = new (std::nothrow) ebc_sim();
+  if (!s) return ebc_fail(nullptr, EBC_ERR_NOMEM, "ebc_create: out of host memory");
+  memset(s, 0, sizeof(*s));
+  s->cfg = *cfg;
+  s->device = device;
+  cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&s->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  if ((err = cudaMalloc(&s->d_actions, sizeof(double) * 2 * (size_t)cfg->n_actions)) != cudaSuccess) {
+    delete s;
+    return ebc_fail(nullptr, EBC_ERR_NOMEM, "cudaMalloc actions: %s", cudaGetErrorString(err));
+  }
+  *out = s;
+  return EBC_OK;
+}
+
+void ebc_destroy(ebc_sim *s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  if (s->d_actions) cudaFree(s->d_actions);
+  ebc_value_release(s);
+  delete s;
+}
+
+int ebc_bind(ebc_sim *s, const ebc_state *st) {
+  if (!s || !st) return EBC_ERR_INVALID;
+  if (!st->hum_pv || !st->hum_gr || !st->hum_type || !st->hum_count || !st->hum_nv || !st->stat_count ||
+      !st->rect_count || !st->rob_pv || !st->rob_gr || !st->rob_theta || !st->time ||
+      (s->cfg.max_statics > 0 && !st->stat) || (s->cfg.max_rects > 0 && !st->rect))
+    return ebc_fail(s, EBC_ERR_INVALID, "ebc_bind: null state array");
+  if (((uintptr_t)st->hum_pv | (uintptr_t)st->hum_gr | (uintptr_t)st->stat | (uintptr_t)st->rob_pv |
+       (uintptr_t)st->rob_gr) & 15u)
+    return ebc_fail(s, EBC_ERR_INVALID, "ebc_bind: float4 arrays must be 16-byte aligned");
+  if (((uintptr_t)st->hum_nv | (uintptr_t)st->rect | (uintptr_t)st->time) & 7u)
+    return ebc_fail(s, EBC_ERR_INVALID, "ebc_bind: hum_nv / rect / time must be 8-byte aligned");
+  s->st = *st;
+  s->bound = true;
+  return EBC_OK;
+}
+
+int ebc_set_actions(ebc_sim *s, const double *actions, int32_t n) {
+  if (!s) return EBC_ERR_INVALID;
+  if (!actions || n != s->cfg.n_actions) return ebc_fail(s, EBC_ERR_INVALID, "ebc_set_actions: expected %d actions", s->cfg.n_actions);
+  cudaSetDevice(s->device);
+  const cudaError_t err = cudaMemcpy(s->d_actions, actions, sizeof(double) * 2 * (size_t)n, cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) return ebc_fail(s, EBC_ERR_CUDA, "ebc_set_actions: %s", cudaGetErrorString(err));
+  s->have_actions = true;
+  return EBC_OK;
+}
+
+int ebc_set_weights(ebc_sim *s, const ebc_weights *w) {
+  if (!s || !w) return EBC_ERR_INVALID;
+  cudaSetDevice(s->device);
+  return ebc_value_prepare(s, w);
+}
+
+#define REQUIRE_BOUND(name) \
+  if (!s) return EBC_ERR_INVALID; \
+  if (!s->bound) return ebc_fail(s, EBC_ERR_UNBOUND, name ": state not bound (call ebc_bind)")
+
+int ebc_orca(ebc_sim *s, void *stream) {
+  REQUIRE_BOUND("ebc_orca");
+  return ebc_launch_orca(s, (cudaStream_t)stream);
+}
+
+int ebc_robot_orca(ebc_sim *s, double safety_space, double *out_action, void *stream) {
+  REQUIRE_BOUND("ebc_robot_orca");
+  if (!out_action) return ebc_fail(s, EBC_ERR_INVALID, "ebc_robot_orca: null output");
+  return ebc_launch_robot_orca(s, safety_space, out_action, (cudaStream_t)stream);
+}
+
+int ebc_lookahead(ebc_sim *s, float *vin, double *reward, uint8_t *done, uint8_t *event, void *stream) {
+  REQUIRE_BOUND("ebc_lookahead");
+  if (!s->have_actions) return ebc_fail(s, EBC_ERR_UNBOUND, "ebc_lookahead: action table not set");
+  return ebc_launch_lookahead(s, vin, reward, done, event, (cudaStream_t)stream);
+}
+
+int ebc_value(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row_count, float *values, void *stream) {
+  if (!s) return EBC_ERR_INVALID;
+  if (!s->have_weights) return ebc_fail(s, EBC_ERR_UNBOUND, "ebc_value: weights not set");
+  if (!vin || !values || n_states < 0) return ebc_fail(s, EBC_ERR_INVALID, "ebc_value: bad argument");
+  return ebc_launch_value(s, vin, n_states, row_count, values, (cudaStream_t)stream);
+}
+
+int ebc_select(ebc_sim *s, const double *reward, const float *values, double *action_values, int32_t *argmax,
+               uint8_t *nan_flag, void *stream) {
+  REQUIRE_BOUND("ebc_select");
+  if (!reward || !values || !argmax) return ebc_fail(s, EBC_ERR_INVALID, "ebc_select: null argument");
+  return ebc_launch_select(s, reward, values, action_values, argmax, nan_flag, (cudaStream_t)stream);
+}
+
+static int step_common(ebc_sim *s, bool fused, const int32_t *action_idx, const double *action, const uint8_t *active,
+                       double *reward, uint8_t *done, uint8_t *event, double *dmin, double *dist_to_goal, void *stream) {
+  REQUIRE_BOUND("ebc_step");
+  if ((action_idx == nullptr) == (action == nullptr))
+    return ebc_fail(s, EBC_ERR_INVALID, "ebc_step: give exactly one of action_idx / action");
+  if (action_idx && !s->have_actions) return ebc_fail(s, EBC_ERR_UNBOUND, "ebc_step: action table not set");
+  return ebc_launch_step(s, fused, action_idx, action, active, reward, done, event, dmin, dist_to_goal,
+                         (cudaStream_t)stream);
+}
+
+int ebc_step(ebc_sim *s, const int32_t *action_idx, const double *action, const uint8_t *active, double *reward,
+             uint8_t *done, uint8_t *event, double *dmin, double *dist_to_goal, void *stream) {
+  return step_common(s, false, action_idx, action, active, reward, done, event, dmin, dist_to_goal, stream);
+}
+
+int ebc_orca_step(ebc_sim *s, const int32_t *action_idx, const double *action, const uint8_t *active, double *reward,
+                  uint8_t *done, uint8_t *event, double *dmin, double *dist_to_goal, void *stream) {
+  return step_common(s, true, action_idx, action, active, reward, done, event, dmin, dist_to_goal, stream);
+}
+
+int ebc_transform(ebc_sim *s, float *out, void *stream) {
+  REQUIRE_BOUND("ebc_transform");
+  if (!out) return ebc_fail(s, EBC_ERR_INVALID, "ebc_transform: null output");
+  return ebc_launch_transform(s, out, (cudaStream_t)stream);
+}
+
+int64_t ebc_launch_count(const ebc_sim *s) { return s ? s->launches : 0; }
+
+}  // extern "C"

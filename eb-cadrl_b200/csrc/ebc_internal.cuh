@@ -1,0 +1,59 @@
+// Internal declarations shared by the translation units of libebcadrl.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ebcadrl.h"
+
+#define EBC_WARPS_PER_BLOCK 8
+#define EBC_THREADS (EBC_WARPS_PER_BLOCK * 32)
+
+// Value-network geometry, computed once in ebc_set_weights (host) and passed by value.
+struct ValueLayer {
+  const float *wt;   // transposed + padded weights [in][out_pad] (device)
+  const float *bias; // [out_pad] (device)
+  int in, out, out_pad;
+};
+
+struct ValueNet {
+  int D, self_dim, with_global;
+  ValueLayer l[11];      // mlp1[2] mlp2[2] att[3] mlp3[4]; att[0] is split: l[4] = local half
+  ValueLayer att0_glob;  // global-state half of attention.0 (bias folded here)
+};
+
+struct ebc_sim {
+  ebc_config cfg;
+  ebc_state st;
+  int device;
+  bool bound, have_actions, have_weights;
+  double *d_actions;     // [A*2]
+  ValueNet net;
+  float *d_weights;      // one slab
+  float *d_joint;        // [cap_states * (self_dim + H2)] scratch for mlp3
+  int64_t joint_cap;
+  int64_t launches;
+  int sm_count;
+  int max_smem_optin;
+  char err[256];
+};
+
+int ebc_fail(ebc_sim *s, int code, const char *fmt, ...);
+int ebc_check_launch(ebc_sim *s, const char *what);
+
+// ebc_sim.cu
+int ebc_launch_orca(ebc_sim *s, cudaStream_t st);
+int ebc_launch_robot_orca(ebc_sim *s, double safety, double *out, cudaStream_t st);
+int ebc_launch_lookahead(ebc_sim *s, float *vin, double *reward, uint8_t *done, uint8_t *event,
+                         cudaStream_t st);
+int ebc_launch_select(ebc_sim *s, const double *reward, const float *values, double *action_values,
+                      int32_t *argmax, uint8_t *nan_flag, cudaStream_t st);
+int ebc_launch_step(ebc_sim *s, bool fused_orca, const int32_t *action_idx, const double *action,
+                    const uint8_t *active, double *reward, uint8_t *done, uint8_t *event, double *dmin,
+                    double *dist_to_goal, cudaStream_t st);
+int ebc_launch_transform(ebc_sim *s, float *out, cudaStream_t st);
+
+// ebc_value.cu
+int ebc_value_prepare(ebc_sim *s, const ebc_weights *w);
+void ebc_value_release(ebc_sim *s);
+int ebc_launch_value(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row_count,
+                     float *values, cudaStream_t st);

@@ -1,0 +1,846 @@
+// ebc_sim.cu — simulation kernels of the EB-CADRL hot path for sm_100a.
+//
+//   K1 orca_kernel        warp per human: RVO2 neighbour selection + ORCA half-planes + the
+//                         incremental 2-D linear program, lines distributed one per lane
+//                         (simulator/policy/orca.py:85-157 -> rvo2 doStep)
+//   K3 lookahead_kernel   warp per (episode, action): swept-disc collisions, occupancy-grid
+//                         test, reward/done/event, next states, rotated joint-state rows
+//                         (simulator/env.py:207-209,388-466; rl/policy/cadrl.py:118-165,236-337)
+//   K5 select_kernel      warp per episode: reward + gamma^(dt v_pref) V, first-max argmax
+//                         (rl/policy/multi_human_rl.py:72-82)
+//   K2 step_kernel        committed env.step (+ optionally fused ORCA, block per episode)
+//                         (simulator/env.py:340-466, simulator/agents/agent.py:202-228)
+//
+// This translation unit is compiled with -fmad=false: RVO2 is fp32 without contraction and
+// the reference's Python float arithmetic is fp64 without contraction; every predicate
+// (collision, reach-goal, discomfort, grid index) is evaluated in fp64 from the fp32 state
+// in the reference's operation order so that flags are bit-exact against the oracle.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "ebc_internal.cuh"
+
+#define FULL 0xffffffffu
+#define RVO_EPSILON 0.00001f
+
+namespace {
+
+struct Line { float px, py, dx, dy; };
+
+__device__ __forceinline__ float det2(float ax, float ay, float bx, float by) { return ax * by - ay * bx; }
+__device__ __forceinline__ float dot2(float ax, float ay, float bx, float by) { return ax * bx + ay * by; }
+
+__device__ __forceinline__ float warp_min_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_min_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+
+// RVO2 linearProgram1 with the scan over earlier lines done by the lanes that hold them.
+// tLeft only grows and tRight only shrinks along the sequential scan, so "fails at some
+// prefix" == "fails at the end", and the parallel-line failure is order-free (Appendix A.3).
+__device__ bool lp1_warp(const Line &L, int lane, int i, float radius, float ox, float oy, bool dir_opt,
+                         float &rx, float &ry) {
+  const float pix = __shfl_sync(FULL, L.px, i), piy = __shfl_sync(FULL, L.py, i);
+  const float dix = __shfl_sync(FULL, L.dx, i), diy = __shfl_sync(FULL, L.dy, i);
+  const float dp = dot2(pix, piy, dix, diy);
+  const float disc = dp * dp + radius * radius - dot2(pix, piy, pix, piy);
+  if (disc < 0.0f) return false;
+  const float s = sqrtf(disc);
+  float tl = -dp - s;
+  float tr = -dp + s;
+  const float den = det2(dix, diy, L.dx, L.dy);
+  const float num = det2(L.dx, L.dy, pix - L.px, piy - L.py);
+  const bool act = lane < i;
+  const bool par = fabsf(den) <= RVO_EPSILON;
+  const bool bad = act && par && (num < 0.0f);
+  const float t = num / den;
+  const float cr = warp_min_f((act && !par && den >= 0.0f) ? t : INFINITY);
+  const float cl = warp_max_f((act && !par && den < 0.0f) ? t : -INFINITY);
+  tr = fminf(tr, cr);
+  tl = fmaxf(tl, cl);
+  if (__any_sync(FULL, bad) || tl > tr) return false;
+  float tt;
+  if (dir_opt) {
+    tt = (dot2(ox, oy, dix, diy) > 0.0f) ? tr : tl;
+  } else {
+    tt = dot2(dix, diy, ox - pix, oy - piy);
+    if (tt < tl) tt = tl;
+    else if (tt > tr) tt = tr;
+  }
+  rx = pix + tt * dix;
+  ry = piy + tt * diy;
+  return true;
+}
+
+// RVO2 linearProgram2: the result only changes inside lp1, so the sequential "first violated
+// line at or after i" is one ballot.
+__device__ int lp2_warp(const Line &L, int lane, int n, float radius, float ox, float oy, bool dir_opt,
+                        float &rx, float &ry) {
+  if (dir_opt) {
+    rx = ox * radius;
+    ry = oy * radius;
+  } else if (dot2(ox, oy, ox, oy) > radius * radius) {
+    const float inv = 1.0f / sqrtf(dot2(ox, oy, ox, oy));
+    rx = (ox * inv) * radius;
+    ry = (oy * inv) * radius;
+  } else {
+    rx = ox;
+    ry = oy;
+  }
+  int i = 0;
+  for (;;) {
+    const bool viol = lane >= i && lane < n && det2(L.dx, L.dy, L.px - rx, L.py - ry) > 0.0f;
+    const unsigned m = __ballot_sync(FULL, viol);
+    if (m == 0u) return n;
+    i = __ffs(m) - 1;
+    const float tx = rx, ty = ry;
+    if (!lp1_warp(L, lane, i, radius, ox, oy, dir_opt, rx, ry)) {
+      rx = tx;
+      ry = ty;
+      return i;
+    }
+    ++i;
+  }
+}
+
+// RVO2 linearProgram3 (no obstacle lines on the reference's live path).
+__device__ void lp3_warp(const Line &L, int lane, int n, int begin, float radius, float &rx, float &ry) {
+  float distance = 0.0f;
+  for (int i = begin; i < n; ++i) {
+    const float pix = __shfl_sync(FULL, L.px, i), piy = __shfl_sync(FULL, L.py, i);
+    const float dix = __shfl_sync(FULL, L.dx, i), diy = __shfl_sync(FULL, L.dy, i);
+    if (det2(dix, diy, pix - rx, piy - ry) > distance) {
+      Line P;
+      bool valid = lane < i;
+      const float d = det2(dix, diy, L.dx, L.dy);
+      if (fabsf(d) <= RVO_EPSILON) {
+        if (dot2(dix, diy, L.dx, L.dy) > 0.0f) valid = false;
+        P.px = 0.5f * (pix + L.px);
+        P.py = 0.5f * (piy + L.py);
+      } else {
+        const float t = det2(L.dx, L.dy, pix - L.px, piy - L.py) / d;
+        P.px = pix + t * dix;
+        P.py = piy + t * diy;
+      }
+      const float ddx = L.dx - dix, ddy = L.dy - diy;
+      const float inv = 1.0f / sqrtf(dot2(ddx, ddy, ddx, ddy));
+      P.dx = ddx * inv;
+      P.dy = ddy * inv;
+      const unsigned vm = __ballot_sync(FULL, valid);
+      const int m = __popc(vm);
+      int src = (int)__fns(vm, 0, lane + 1);   // lane k takes the k-th surviving line (order kept)
+      if (lane >= m) src = lane;
+      Line Q;
+      Q.px = __shfl_sync(FULL, P.px, src);
+      Q.py = __shfl_sync(FULL, P.py, src);
+      Q.dx = __shfl_sync(FULL, P.dx, src);
+      Q.dy = __shfl_sync(FULL, P.dy, src);
+      const float tx = rx, ty = ry;
+      if (lp2_warp(Q, lane, m, radius, -diy, dix, true, rx, ry) < m) {
+        rx = tx;
+        ry = ty;
+      }
+      distance = det2(dix, diy, pix - rx, piy - ry);
+    }
+  }
+}
+
+// One RVO2 agent step by one warp.  Candidates (the other agents, in the reference's list
+// order) sit two per lane: index lane and lane + 32.  `scratch` = 32*5 floats of this warp.
+__device__ void orca_agent_warp(int lane, float px, float py, float vx, float vy, float radius, float max_speed,
+                                float prefx, float prefy, const float (&cpx)[2], const float (&cpy)[2],
+                                const float (&cvx)[2], const float (&cvy)[2], const float (&crad)[2],
+                                const bool (&cval)[2], int n_chunks, float neighbor_dist, int max_nb,
+                                float time_horizon, float time_step, float *scratch, float &outx, float &outy) {
+  // Agent::insertAgentNeighbor == keep the max_nb smallest (distSq, arrival index) below range
+  float d[2];
+  unsigned vmask[2] = {0u, 0u};
+  const float range_sq = neighbor_dist * neighbor_dist;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const float ddx = px - cpx[c], ddy = py - cpy[c];
+    d[c] = dot2(ddx, ddy, ddx, ddy);
+    const bool ok = (c < n_chunks) && cval[c] && (d[c] < range_sq);
+    vmask[c] = __ballot_sync(FULL, ok);
+  }
+  int rank[2] = {0, 0};
+#pragma unroll
+  for (int c2 = 0; c2 < 2; ++c2) {
+    if (c2 >= n_chunks) break;
+    unsigned m = vmask[c2];
+    while (m) {
+      const int l = __ffs(m) - 1;
+      m &= m - 1;
+      const float dk = __shfl_sync(FULL, d[c2], l);
+      const int k = l + 32 * c2;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int me = lane + 32 * c;
+        rank[c] += (dk < d[c] || (dk == d[c] && k < me)) ? 1 : 0;
+      }
+    }
+  }
+  const int total = __popc(vmask[0]) + __popc(vmask[1]);
+  const int cnt = total < max_nb ? total : max_nb;
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    if ((vmask[c] >> lane) & 1u) {
+      if (rank[c] < cnt) {
+        float *s = scratch + rank[c] * 5;
+        s[0] = cpx[c]; s[1] = cpy[c]; s[2] = cvx[c]; s[3] = cvy[c]; s[4] = crad[c];
+      }
+    }
+  }
+  __syncwarp();
+  Line L = {0.0f, 0.0f, 1.0f, 0.0f};
+  if (lane < cnt) {
+    const float *s = scratch + lane * 5;
+    const float rpx = s[0] - px, rpy = s[1] - py;
+    const float rvx = vx - s[2], rvy = vy - s[3];
+    const float dist_sq = dot2(rpx, rpy, rpx, rpy);
+    const float R = radius + s[4];
+    const float R_sq = R * R;
+    const float inv_th = 1.0f / time_horizon;
+    float ux, uy;
+    if (dist_sq > R_sq) {
+      const float wx = rvx - inv_th * rpx, wy = rvy - inv_th * rpy;
+      const float wlen_sq = dot2(wx, wy, wx, wy);
+      const float dp1 = dot2(wx, wy, rpx, rpy);
+      if (dp1 < 0.0f && dp1 * dp1 > R_sq * wlen_sq) {
+        const float wlen = sqrtf(wlen_sq);
+        const float inv = 1.0f / wlen;
+        const float uwx = wx * inv, uwy = wy * inv;
+        L.dx = uwy;
+        L.dy = -uwx;
+        const float sc = R * inv_th - wlen;
+        ux = sc * uwx;
+        uy = sc * uwy;
+      } else {
+        const float leg = sqrtf(dist_sq - R_sq);
+        const float inv = 1.0f / dist_sq;
+        if (det2(rpx, rpy, wx, wy) > 0.0f) {
+          L.dx = (rpx * leg - rpy * R) * inv;
+          L.dy = (rpx * R + rpy * leg) * inv;
+        } else {
+          L.dx = (-(rpx * leg + rpy * R)) * inv;
+          L.dy = (-(-rpx * R + rpy * leg)) * inv;
+        }
+        const float dp2 = dot2(rvx, rvy, L.dx, L.dy);
+        ux = dp2 * L.dx - rvx;
+        uy = dp2 * L.dy - rvy;
+      }
+    } else {
+      const float inv_ts = 1.0f / time_step;
+      const float wx = rvx - inv_ts * rpx, wy = rvy - inv_ts * rpy;
+      const float wlen = sqrtf(dot2(wx, wy, wx, wy));
+      const float inv = 1.0f / wlen;
+      const float uwx = wx * inv, uwy = wy * inv;
+      L.dx = uwy;
+      L.dy = -uwx;
+      const float sc = R * inv_ts - wlen;
+      ux = sc * uwx;
+      uy = sc * uwy;
+    }
+    L.px = vx + 0.5f * ux;
+    L.py = vy + 0.5f * uy;
+  }
+  __syncwarp();
+  float rx, ry;
+  const int fail = lp2_warp(L, lane, cnt, max_speed, prefx, prefy, false, rx, ry);
+  if (fail < cnt) lp3_warp(L, lane, cnt, fail, max_speed, rx, ry);
+  outx = rx;
+  outy = ry;
+}
+
+// simulator/policy/orca.py:113-119,136-140 (float64 in Python, narrowed at the rvo2 boundary)
+__device__ __forceinline__ void orca_self_params(float px, float py, float gx, float gy, float radius,
+                                                 double safety, float &r_out, float &prefx, float &prefy) {
+  r_out = (float)((double)radius + 0.01 + safety);
+  const double vx = (double)gx - (double)px, vy = (double)gy - (double)py;
+  const double speed = sqrt(vx * vx + vy * vy);
+  if (speed > 1.0) {
+    prefx = (float)(vx / speed);
+    prefy = (float)(vy / speed);
+  } else {
+    prefx = (float)vx;
+    prefy = (float)vy;
+  }
+}
+
+// Policy of human h of episode e, computed by one warp (env.py:392-405).
+__device__ void human_policy_warp(const ebc_config &c, const ebc_state &st, int e, int h, int H, int lane,
+                                  float *scratch, float &nvx, float &nvy) {
+  const int Hm = c.max_humans;
+  const float4 *pv = reinterpret_cast<const float4 *>(st.hum_pv) + (size_t)e * Hm;
+  const float4 *gr = reinterpret_cast<const float4 *>(st.hum_gr) + (size_t)e * Hm;
+  const float4 me_pv = pv[h], me_gr = gr[h];
+  int ty = st.hum_type[(size_t)e * Hm + h];
+  if (ty > 2) ty = 0;
+  if (c.human_policy[ty] == EBC_POLICY_LINEAR) {   // simulator/policy/linear.py:17-23
+    const double th = atan2((double)me_gr.y - (double)me_pv.y, (double)me_gr.x - (double)me_pv.x);
+    nvx = (float)(cos(th) * (double)me_gr.z);
+    nvy = (float)(sin(th) * (double)me_gr.z);
+    return;
+  }
+  const int n_cand = H + (c.robot_visible ? 1 : 0);
+  const int n_chunks = (n_cand + 31) >> 5;
+  float cpx[2], cpy[2], cvx[2], cvy[2], crad[2];
+  bool cval[2];
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    const int j = lane + 32 * ch;
+    cval[ch] = false;
+    cpx[ch] = cpy[ch] = cvx[ch] = cvy[ch] = crad[ch] = 0.0f;
+    if (j < H && j != h) {
+      const float4 p = pv[j];
+      cpx[ch] = p.x; cpy[ch] = p.y; cvx[ch] = p.z; cvy[ch] = p.w;
+      crad[ch] = (float)((double)gr[j].w + 0.01 + c.orca_safety_space);
+      cval[ch] = true;
+    } else if (j == H && c.robot_visible) {   // env.py:401-402: robot appended last
+      const float4 p = reinterpret_cast<const float4 *>(st.rob_pv)[e];
+      cpx[ch] = p.x; cpy[ch] = p.y; cvx[ch] = p.z; cvy[ch] = p.w;
+      crad[ch] = (float)((double)st.rob_gr[(size_t)e * 4 + 3] + 0.01 + c.orca_safety_space);
+      cval[ch] = true;
+    }
+  }
+  float r_self, prefx, prefy;
+  orca_self_params(me_pv.x, me_pv.y, me_gr.x, me_gr.y, me_gr.w, c.orca_safety_space, r_self, prefx, prefy);
+  orca_agent_warp(lane, me_pv.x, me_pv.y, me_pv.z, me_pv.w, r_self, me_gr.z, prefx, prefy, cpx, cpy, cvx, cvy,
+                  crad, cval, n_chunks, c.orca_neighbor_dist, c.orca_max_neighbors, c.orca_time_horizon,
+                  (float)c.time_step, scratch, nvx, nvy);
+}
+
+__global__ void __launch_bounds__(EBC_THREADS) orca_kernel(const ebc_config c, const ebc_state st) {
+  __shared__ float scratch[EBC_WARPS_PER_BLOCK][32 * 5];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * EBC_WARPS_PER_BLOCK + warp;
+  const int e = (int)(w / c.max_humans), h = (int)(w % c.max_humans);
+  if (e >= c.n_episodes) return;
+  const int H = st.hum_count[e];
+  if (h >= H) return;
+  float nvx, nvy;
+  human_policy_warp(c, st, e, h, H, lane, scratch[warp], nvx, nvy);
+  if (lane == 0)
+    reinterpret_cast<float2 *>(st.hum_nv)[(size_t)e * c.max_humans + h] = make_float2(nvx, nvy);
+}
+
+// Robot as ORCA agent 0 over humans + static discs (rl/train.py:99-143).
+__global__ void __launch_bounds__(EBC_THREADS) robot_orca_kernel(const ebc_config c, const ebc_state st,
+                                                                 double safety, double *out) {
+  __shared__ float scratch[EBC_WARPS_PER_BLOCK][32 * 5];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * EBC_WARPS_PER_BLOCK + warp;
+  if (e >= c.n_episodes) return;
+  const int Hm = c.max_humans, Sm = c.max_statics;
+  const int H = st.hum_count[e], S = st.stat_count[e];
+  const float4 *pv = reinterpret_cast<const float4 *>(st.hum_pv) + (size_t)e * Hm;
+  const float4 *gr = reinterpret_cast<const float4 *>(st.hum_gr) + (size_t)e * Hm;
+  const float4 *sd = reinterpret_cast<const float4 *>(st.stat) + (size_t)e * Sm;
+  float cpx[2], cpy[2], cvx[2], cvy[2], crad[2];
+  bool cval[2];
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    const int j = lane + 32 * ch;
+    cval[ch] = false;
+    cpx[ch] = cpy[ch] = cvx[ch] = cvy[ch] = crad[ch] = 0.0f;
+    if (j < H) {
+      const float4 p = pv[j];
+      cpx[ch] = p.x; cpy[ch] = p.y; cvx[ch] = p.z; cvy[ch] = p.w;
+      crad[ch] = (float)((double)gr[j].w + 0.01 + safety);
+      cval[ch] = true;
+    } else if (j < H + S) {
+      const float4 p = sd[j - H];
+      cpx[ch] = p.x; cpy[ch] = p.y;
+      crad[ch] = (float)((double)p.z + 0.01 + safety);
+      cval[ch] = true;
+    }
+  }
+  const float4 rp = reinterpret_cast<const float4 *>(st.rob_pv)[e];
+  const float4 rg = reinterpret_cast<const float4 *>(st.rob_gr)[e];
+  float r_self, prefx, prefy, vx, vy;
+  orca_self_params(rp.x, rp.y, rg.x, rg.y, rg.w, safety, r_self, prefx, prefy);
+  orca_agent_warp(lane, rp.x, rp.y, rp.z, rp.w, r_self, rg.z, prefx, prefy, cpx, cpy, cvx, cvy, crad, cval,
+                  (H + S + 31) >> 5, c.orca_neighbor_dist, c.orca_max_neighbors, c.orca_time_horizon,
+                  (float)c.time_step, scratch[warp], vx, vy);
+  if (lane == 0) {
+    out[(size_t)e * 2] = (double)vx;
+    out[(size_t)e * 2 + 1] = (double)vy;
+  }
+}
+
+// simulator/utils/collisions.py:4-26 with (x3, y3) = (0, 0)
+__device__ __forceinline__ double point_to_segment_dist0(double x1, double y1, double x2, double y2) {
+  const double px = x2 - x1, py = y2 - y1;
+  if (px == 0.0 && py == 0.0) return sqrt((0.0 - x1) * (0.0 - x1) + (0.0 - y1) * (0.0 - y1));
+  double u = ((0.0 - x1) * px + (0.0 - y1) * py) / (px * px + py * py);
+  if (u > 1.0) u = 1.0;
+  else if (u < 0.0) u = 0.0;
+  const double x = x1 + u * px, y = y1 + u * py;
+  return sqrt((x - 0.0) * (x - 0.0) + (y - 0.0) * (y - 0.0));
+}
+
+struct Outcome {
+  double dmin[3];
+  double end_x, end_y, dist_to_goal, reward;
+  int done, event;
+};
+
+// The humans of one episode, two per lane.
+struct EpisodeHumans {
+  float4 pv[2];
+  float rad[2];
+  int type[2];   // -1 = empty slot
+};
+
+__device__ __forceinline__ void load_humans(const ebc_config &c, const ebc_state &st, int e, int H, int lane,
+                                            EpisodeHumans &hm) {
+  const int Hm = c.max_humans;
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    const int h = lane + 32 * ch;
+    hm.type[ch] = -1;
+    hm.pv[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+    hm.rad[ch] = 0.f;
+    if (h < H) {
+      hm.pv[ch] = reinterpret_cast<const float4 *>(st.hum_pv)[(size_t)e * Hm + h];
+      hm.rad[ch] = st.hum_gr[((size_t)e * Hm + h) * 4 + 3];
+      hm.type[ch] = st.hum_type[(size_t)e * Hm + h];
+    }
+  }
+}
+
+// env.py:424-444 for one (episode, action), cooperatively by one warp; result warp-uniform.
+__device__ void evaluate_action_warp(const ebc_config &c, const ebc_state &st, int e, int lane,
+                                     const EpisodeHumans &hm, const float4 rp, const float4 rg, double theta,
+                                     double gt, double a0, double a1, Outcome &o) {
+  const double rpx = rp.x, rpy = rp.y, rrad = rg.w;
+  const double dt = c.time_step;
+  double avx, avy;
+  if (c.robot_kinematics == EBC_KIN_HOLONOMIC) {   // collisions.py:37-42, agent.py:164-176
+    avx = a0;
+    avy = a1;
+    o.end_x = rpx + a0 * dt;
+    o.end_y = rpy + a1 * dt;
+  } else {
+    const double th = theta + a1;
+    avx = a0 * cos(a1 + theta);
+    avy = a0 * sin(a1 + theta);
+    o.end_x = rpx + cos(th) * a0 * dt;
+    o.end_y = rpy + sin(th) * a0 * dt;
+  }
+  // env.py:303-338: per type, list order, dmin frozen at the first collision
+  double closest[2];
+  unsigned long long collm = 0ull, typem[3] = {0ull, 0ull, 0ull};
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    const bool valid = hm.type[ch] >= 0 && hm.type[ch] <= 2;
+    const double px = (double)hm.pv[ch].x - rpx, py = (double)hm.pv[ch].y - rpy;
+    const double vx = (double)hm.pv[ch].z - avx, vy = (double)hm.pv[ch].w - avy;
+    const double ex = px + vx * dt, ey = py + vy * dt;
+    closest[ch] = point_to_segment_dist0(px, py, ex, ey) - (double)hm.rad[ch] - rrad;
+    collm |= (unsigned long long)__ballot_sync(FULL, valid && closest[ch] < 0.0) << (32 * ch);
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+      typem[t] |= (unsigned long long)__ballot_sync(FULL, valid && hm.type[ch] == t) << (32 * ch);
+  }
+  bool coll[3];
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    const unsigned long long cm = collm & typem[t];
+    coll[t] = cm != 0ull;
+    const int first = coll[t] ? (__ffsll((long long)cm) - 1) : 64;
+    double local = INFINITY;
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch)
+      if (hm.type[ch] == t && lane + 32 * ch < first) local = fmin(local, closest[ch]);
+    o.dmin[t] = warp_min_d(local);
+  }
+  // env.py:227-261 on the rectangle list
+  bool coll_obst = false;
+  {
+    const int ix = (int)rint((o.end_x + c.map_size_m / 2.0) / c.map_resolution);
+    const int iy = (int)rint((o.end_y + c.map_size_m / 2.0) / c.map_resolution);
+    const int sz = (int)ceil(rrad / sqrt(2.0) / c.map_resolution);
+    const int G = (int)rint(c.map_size_m / c.map_resolution);
+    int sx = ix - sz, ex = sx + sz * 2, sy = iy - sz, ey = sy + sz * 2;
+    sx = max(sx, 0); ex = min(ex, G); sy = max(sy, 0); ey = min(ey, G);
+    const int R = st.rect_count[e];
+    bool hit = false;
+    if (ex > sx && ey > sy) {
+      const short4 *rc = reinterpret_cast<const short4 *>(st.rect) + (size_t)e * c.max_rects;
+      for (int j = lane; j < R; j += 32) {
+        const short4 r = rc[j];
+        hit |= (sx < r.z && r.x < ex && sy < r.w && r.y < ey);
+      }
+    }
+    coll_obst = __any_sync(FULL, hit);
+  }
+  // reward.py:80-181
+  const double gdx = o.end_x - (double)rg.x, gdy = o.end_y - (double)rg.y;
+  const double dist = sqrt(gdx * gdx + gdy * gdy);
+  o.dist_to_goal = dist;
+  const bool reaching = dist < rrad;
+  const double goal_reward = c.has_max_goal_distance ? 1.0 - dist / c.max_goal_distance : 0.0;
+  double reward = c.new_reward ? goal_reward : 0.0;
+  int done, ev;
+  if (gt >= c.time_limit) { done = 1; ev = EBC_EV_TIMEOUT; }
+  else if (coll[EBC_CHILD]) { reward += c.collision_penalty_child; done = 1; ev = EBC_EV_COLLISION_CHILD; }
+  else if (coll[EBC_BICYCLE]) { reward += c.collision_penalty_bicycle; done = 1; ev = EBC_EV_COLLISION_BICYCLE; }
+  else if (coll[EBC_ADULT]) { reward += c.collision_penalty_adult; done = 1; ev = EBC_EV_COLLISION_ADULT; }
+  else if (coll_obst) { reward += c.collision_penalty_obstacle; done = 1; ev = EBC_EV_COLLISION_OBSTACLE; }
+  else if (reaching) {
+    if (c.new_reward) {
+      double tr;
+      if (gt < c.time_good) tr = 1.0;
+      else if (gt <= c.time_max) tr = (c.time_max - gt) / (c.time_max - c.time_good);
+      else tr = 0.0;
+      reward += tr;
+    } else {
+      reward += c.success_reward;
+    }
+    done = 1; ev = EBC_EV_REACH_GOAL;
+  } else if (o.dmin[EBC_CHILD] < c.discomfort_dist_child) {
+    reward = (o.dmin[EBC_CHILD] - c.discomfort_dist_child) * c.discomfort_penalty_factor_child * dt;
+    done = 0; ev = EBC_EV_DANGER;
+  } else if (o.dmin[EBC_BICYCLE] < c.discomfort_dist_bicycle) {
+    reward = (o.dmin[EBC_BICYCLE] - c.discomfort_dist_bicycle) * c.discomfort_penalty_factor_bicycle * dt;
+    done = 0; ev = EBC_EV_DANGER;
+  } else if (o.dmin[EBC_ADULT] < c.discomfort_dist_adult) {
+    reward = (o.dmin[EBC_ADULT] - c.discomfort_dist_adult) * c.discomfort_penalty_factor_adult * dt;
+    done = 0; ev = EBC_EV_DANGER;
+  } else if (c.robot_kinematics != EBC_KIN_HOLONOMIC && fabs(a1) > 0.0 && c.rotation_penalty_factor != 0.0) {
+    reward = fabs(a1) * c.rotation_penalty_factor;
+    done = 0; ev = EBC_EV_NOTHING;
+  } else { reward = 0.0; done = 0; ev = EBC_EV_NOTHING; }
+  o.reward = reward; o.done = done; o.event = ev;
+}
+
+// rl/policy/cadrl.py:236-337, one row, fp32 (-fmad=false keeps torch's separate mul/add).
+// robot = (px, py, vx, vy, radius, gx, gy, v_pref, theta), entity = (px1, py1, vx1, vy1, radius1, type)
+struct RobotRow { float px, py, vx, vy, radius, gx, gy, v_pref, theta; };
+
+__device__ __forceinline__ void rotate_row(const RobotRow &r, float px1, float py1, float vx1, float vy1,
+                                           float radius1, int type1, int rotate_theta, int D, float *out) {
+  const float dx = r.gx - r.px, dy = r.gy - r.py;
+  const float rot = atan2f(r.gy - r.py, r.gx - r.px);
+  const float cr = cosf(rot), sr = sinf(rot);
+  out[0] = sqrtf(dx * dx + dy * dy);
+  out[1] = r.v_pref;
+  out[2] = rotate_theta ? r.theta - rot : 0.0f;
+  out[3] = r.radius;
+  out[4] = r.vx * cr + r.vy * sr;
+  out[5] = r.vy * cr - r.vx * sr;
+  out[6] = (px1 - r.px) * cr + (py1 - r.py) * sr;
+  out[7] = (py1 - r.py) * cr - (px1 - r.px) * sr;
+  out[8] = vx1 * cr + vy1 * sr;
+  out[9] = vy1 * cr - vx1 * sr;
+  out[10] = radius1;
+  const float ax = r.px - px1, ay = r.py - py1;
+  out[11] = sqrtf(ax * ax + ay * ay);
+  out[12] = r.radius + radius1;
+  if (D == 17) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out[13 + k] = (k == type1) ? 1.0f : 0.0f;
+  }
+}
+
+// Build the n x D rows of one state into `tile` (this warp's shared-memory staging area), then
+// stream them out with coalesced stores.  next_state: humans advanced by their ORCA action
+// (agent.py:80-93) when true, current state (multi_human_rl.py:128-149) when false.
+__device__ void build_rows_warp(const ebc_config &c, const ebc_state &st, int e, int lane, int H, int S,
+                                const RobotRow &rr, bool next_state, float *tile, float *dst) {
+  const int Hm = c.max_humans, Sm = c.max_statics, n = Hm + Sm;
+  const int D = c.with_agent_type ? 17 : 13;
+  const double dt = c.time_step;
+  for (int r = lane; r < n; r += 32) {
+    float *row = tile + r * D;
+    if (r < H) {
+      const float4 p = reinterpret_cast<const float4 *>(st.hum_pv)[(size_t)e * Hm + r];
+      const float rad = st.hum_gr[((size_t)e * Hm + r) * 4 + 3];
+      const int ty = st.hum_type[(size_t)e * Hm + r];
+      if (next_state) {
+        const float2 nv = reinterpret_cast<const float2 *>(st.hum_nv)[(size_t)e * Hm + r];
+        const float npx = (float)((double)p.x + (double)nv.x * dt);
+        const float npy = (float)((double)p.y + (double)nv.y * dt);
+        rotate_row(rr, npx, npy, nv.x, nv.y, rad, ty, c.rotate_theta, D, row);
+      } else {
+        rotate_row(rr, p.x, p.y, p.z, p.w, rad, ty, c.rotate_theta, D, row);
+      }
+    } else if (r < H + S) {   // env.py:457-458 static discs, type 3
+      const float4 p = reinterpret_cast<const float4 *>(st.stat)[(size_t)e * Sm + (r - H)];
+      rotate_row(rr, p.x, p.y, 0.0f, 0.0f, p.z, EBC_ADULT_STATIC, c.rotate_theta, D, row);
+    } else {
+      for (int k = 0; k < D; ++k) row[k] = 0.0f;
+    }
+  }
+  __syncwarp();
+  const int total = n * D;
+  for (int i = lane; i < total; i += 32) dst[i] = tile[i];
+  __syncwarp();
+}
+
+// K3
+__global__ void __launch_bounds__(EBC_THREADS)
+lookahead_kernel(const ebc_config c, const ebc_state st, const double *__restrict__ actions, float *vin,
+                 double *reward, uint8_t *done, uint8_t *event) {
+  extern __shared__ float tiles[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int A = c.n_actions;
+  const long long w = (long long)blockIdx.x * EBC_WARPS_PER_BLOCK + warp;
+  const int e = (int)(w / A), a = (int)(w % A);
+  if (e >= c.n_episodes) return;
+  const int n = c.max_humans + c.max_statics, D = c.with_agent_type ? 17 : 13;
+  const int H = st.hum_count[e], S = st.stat_count[e];
+  EpisodeHumans hm;
+  load_humans(c, st, e, H, lane, hm);
+  const float4 rp = reinterpret_cast<const float4 *>(st.rob_pv)[e];
+  const float4 rg = reinterpret_cast<const float4 *>(st.rob_gr)[e];
+  const double theta = (double)st.rob_theta[e];
+  const double a0 = actions[a * 2], a1 = actions[a * 2 + 1];
+  Outcome o;
+  evaluate_action_warp(c, st, e, lane, hm, rp, rg, theta, st.time[e], a0, a1, o);
+  const size_t ea = (size_t)e * A + a;
+  if (lane == 0) {
+    if (reward) reward[ea] = o.reward;
+    if (done) done[ea] = (uint8_t)o.done;
+    if (event) event[ea] = (uint8_t)o.event;
+  }
+  if (!vin) return;
+  // rl/policy/cadrl.py:118-165 propagate(robot) in fp64, narrowed like torch.Tensor([...])
+  RobotRow rr;
+  const double dt = c.time_step;
+  if (c.robot_kinematics == EBC_KIN_HOLONOMIC) {
+    rr.px = (float)((double)rp.x + a0 * dt);
+    rr.py = (float)((double)rp.y + a1 * dt);
+    rr.vx = (float)a0;
+    rr.vy = (float)a1;
+    rr.theta = (float)theta;
+  } else {
+    const double nth = theta + a1;
+    const double nvx = a0 * cos(nth), nvy = a0 * sin(nth);
+    rr.px = (float)((double)rp.x + nvx * dt);
+    rr.py = (float)((double)rp.y + nvy * dt);
+    rr.vx = (float)nvx;
+    rr.vy = (float)nvy;
+    rr.theta = (float)nth;
+  }
+  rr.radius = rg.w; rr.gx = rg.x; rr.gy = rg.y; rr.v_pref = rg.z;
+  build_rows_warp(c, st, e, lane, H, S, rr, true, tiles + (size_t)warp * n * D, vin + ea * (size_t)n * D);
+}
+
+// rl/policy/multi_human_rl.py:128-149
+__global__ void __launch_bounds__(EBC_THREADS) transform_kernel(const ebc_config c, const ebc_state st, float *out) {
+  extern __shared__ float tiles[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * EBC_WARPS_PER_BLOCK + warp;
+  if (e >= c.n_episodes) return;
+  const int n = c.max_humans + c.max_statics, D = c.with_agent_type ? 17 : 13;
+  const float4 rp = reinterpret_cast<const float4 *>(st.rob_pv)[e];
+  const float4 rg = reinterpret_cast<const float4 *>(st.rob_gr)[e];
+  RobotRow rr;
+  rr.px = rp.x; rr.py = rp.y; rr.vx = rp.z; rr.vy = rp.w;
+  rr.radius = rg.w; rr.gx = rg.x; rr.gy = rg.y; rr.v_pref = rg.z; rr.theta = st.rob_theta[e];
+  build_rows_warp(c, st, e, lane, st.hum_count[e], st.stat_count[e], rr, false, tiles + (size_t)warp * n * D,
+                  out + (size_t)e * n * D);
+}
+
+// K5
+__global__ void __launch_bounds__(EBC_THREADS)
+select_kernel(const ebc_config c, const ebc_state st, const double *__restrict__ reward,
+              const float *__restrict__ values, double *action_values, int32_t *argmax, uint8_t *nan_flag) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * EBC_WARPS_PER_BLOCK + warp;
+  if (e >= c.n_episodes) return;
+  const int A = c.n_actions;
+  const float4 rp = reinterpret_cast<const float4 *>(st.rob_pv)[e];
+  const float4 rg = reinterpret_cast<const float4 *>(st.rob_gr)[e];
+  const double disc = pow(c.gamma, c.time_step * (double)rg.z);
+  double best = -INFINITY;
+  int arg = 0x7fffffff;
+  for (int a = lane; a < A; a += 32) {
+    const double v = reward[(size_t)e * A + a] + disc * (double)values[(size_t)e * A + a];
+    if (action_values) action_values[(size_t)e * A + a] = v;
+    if (v > best) { best = v; arg = a; }   // strict '>' keeps the first maximum of this lane's stride
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(FULL, best, o);
+    const int oa = __shfl_xor_sync(FULL, arg, o);
+    if (oa != 0x7fffffff && (arg == 0x7fffffff || ob > best || (ob == best && oa < arg))) { best = ob; arg = oa; }
+  }
+  if (lane == 0) {
+    const bool none = arg == 0x7fffffff;
+    if (nan_flag) nan_flag[e] = none ? 1 : 0;
+    if (none) arg = 0;
+    const double dy = (double)rp.y - (double)rg.y, dx = (double)rp.x - (double)rg.x;   // policy.py:43-54
+    if (sqrt(dy * dy + dx * dx) < (double)rg.w) arg = 0;
+    argmax[e] = arg;
+  }
+}
+
+// Commit of one episode by one warp (env.py:340-386,424-466; agent.py:202-228).
+__device__ void commit_episode_warp(const ebc_config &c, const ebc_state &st, int e, int lane,
+                                    const double *actions, const int32_t *action_idx, const double *action,
+                                    double *reward, uint8_t *done, uint8_t *event, double *dmin, double *dist_to_goal) {
+  const int Hm = c.max_humans;
+  const int H = st.hum_count[e];
+  double a0, a1;
+  if (action_idx) {
+    int ai = action_idx[e];
+    if (ai < 0 || ai >= c.n_actions) ai = 0;
+    a0 = actions[ai * 2];
+    a1 = actions[ai * 2 + 1];
+  } else {
+    a0 = action[(size_t)e * 2];
+    a1 = action[(size_t)e * 2 + 1];
+  }
+  EpisodeHumans hm;
+  load_humans(c, st, e, H, lane, hm);
+  const float4 rp = reinterpret_cast<const float4 *>(st.rob_pv)[e];
+  const float4 rg = reinterpret_cast<const float4 *>(st.rob_gr)[e];
+  const double theta = (double)st.rob_theta[e];
+  const double gt = st.time[e];
+  Outcome o;
+  evaluate_action_warp(c, st, e, lane, hm, rp, rg, theta, gt, a0, a1, o);
+  const double dt = c.time_step;
+  // humans: agent.step(ActionXY), holonomic
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    const int h = lane + 32 * ch;
+    if (h < H) {
+      const float2 nv = reinterpret_cast<const float2 *>(st.hum_nv)[(size_t)e * Hm + h];
+      float4 p;
+      p.x = (float)((double)hm.pv[ch].x + (double)nv.x * dt);
+      p.y = (float)((double)hm.pv[ch].y + (double)nv.y * dt);
+      p.z = nv.x;
+      p.w = nv.y;
+      reinterpret_cast<float4 *>(st.hum_pv)[(size_t)e * Hm + h] = p;
+    }
+  }
+  if (lane == 0) {
+    if (reward) reward[e] = o.reward;
+    if (done) done[e] = (uint8_t)o.done;
+    if (event) event[e] = (uint8_t)o.event;
+    if (dmin) { dmin[(size_t)e * 3] = o.dmin[0]; dmin[(size_t)e * 3 + 1] = o.dmin[1]; dmin[(size_t)e * 3 + 2] = o.dmin[2]; }
+    if (dist_to_goal) dist_to_goal[e] = o.dist_to_goal;
+    float4 np;
+    np.x = (float)o.end_x;
+    np.y = (float)o.end_y;
+    if (c.robot_kinematics == EBC_KIN_HOLONOMIC) {
+      np.z = (float)a0;
+      np.w = (float)a1;
+    } else {
+      const double two_pi = 2.0 * 3.14159265358979323846;
+      double th = fmod(theta + a1, two_pi);
+      if (th < 0.0) th += two_pi;   // Python % is non-negative
+      st.rob_theta[e] = (float)th;
+      np.z = (float)(a0 * cos(th));
+      np.w = (float)(a0 * sin(th));
+    }
+    reinterpret_cast<float4 *>(st.rob_pv)[e] = np;
+    st.time[e] = gt + dt;
+  }
+}
+
+// K2, warp per episode; hum_nv comes from a preceding orca_kernel.
+__global__ void __launch_bounds__(EBC_THREADS)
+step_kernel(const ebc_config c, const ebc_state st, const double *__restrict__ actions, const int32_t *action_idx,
+            const double *action, const uint8_t *active, double *reward, uint8_t *done, uint8_t *event,
+            double *dmin, double *dist_to_goal) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * EBC_WARPS_PER_BLOCK + warp;
+  if (e >= c.n_episodes) return;
+  if (active && !active[e]) return;
+  commit_episode_warp(c, st, e, lane, actions, action_idx, action, reward, done, event, dmin, dist_to_goal);
+}
+
+// K1 + K2 fused, block per episode: every warp solves humans' LPs from the untouched state,
+// the block synchronises, then warp 0 commits.  One launch per env step on the policy-free path.
+__global__ void __launch_bounds__(512)
+orca_step_kernel(const ebc_config c, const ebc_state st, const double *__restrict__ actions,
+                 const int32_t *action_idx, const double *action, const uint8_t *active, double *reward,
+                 uint8_t *done, uint8_t *event, double *dmin, double *dist_to_goal) {
+  __shared__ float scratch[16][32 * 5];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+  const int e = blockIdx.x;
+  if (active && !active[e]) return;
+  const int H = st.hum_count[e];
+  for (int h = warp; h < H; h += n_warps) {
+    float nvx, nvy;
+    human_policy_warp(c, st, e, h, H, lane, scratch[warp], nvx, nvy);
+    if (lane == 0)
+      reinterpret_cast<float2 *>(st.hum_nv)[(size_t)e * c.max_humans + h] = make_float2(nvx, nvy);
+  }
+  __syncthreads();   // all reads of the old state are done; hum_nv is visible block-wide
+  if (warp == 0)
+    commit_episode_warp(c, st, e, lane, actions, action_idx, action, reward, done, event, dmin, dist_to_goal);
+}
+
+}  // namespace
+
+int ebc_launch_orca(ebc_sim *s, cudaStream_t stream) {
+  const long long warps = (long long)s->cfg.n_episodes * s->cfg.max_humans;
+  const int blocks = (int)((warps + EBC_WARPS_PER_BLOCK - 1) / EBC_WARPS_PER_BLOCK);
+  orca_kernel<<<blocks, EBC_THREADS, 0, stream>>>(s->cfg, s->st);
+  return ebc_check_launch(s, "orca_kernel");
+}
+
+int ebc_launch_robot_orca(ebc_sim *s, double safety, double *out, cudaStream_t stream) {
+  const int blocks = (s->cfg.n_episodes + EBC_WARPS_PER_BLOCK - 1) / EBC_WARPS_PER_BLOCK;
+  robot_orca_kernel<<<blocks, EBC_THREADS, 0, stream>>>(s->cfg, s->st, safety, out);
+  return ebc_check_launch(s, "robot_orca_kernel");
+}
+
+int ebc_launch_lookahead(ebc_sim *s, float *vin, double *reward, uint8_t *done, uint8_t *event,
+                         cudaStream_t stream) {
+  const long long warps = (long long)s->cfg.n_episodes * s->cfg.n_actions;
+  const int blocks = (int)((warps + EBC_WARPS_PER_BLOCK - 1) / EBC_WARPS_PER_BLOCK);
+  const int n = s->cfg.max_humans + s->cfg.max_statics, D = s->cfg.with_agent_type ? 17 : 13;
+  const size_t smem = (size_t)EBC_WARPS_PER_BLOCK * n * D * sizeof(float);
+  lookahead_kernel<<<blocks, EBC_THREADS, smem, stream>>>(s->cfg, s->st, s->d_actions, vin, reward, done, event);
+  return ebc_check_launch(s, "lookahead_kernel");
+}
+
+int ebc_launch_transform(ebc_sim *s, float *out, cudaStream_t stream) {
+  const int blocks = (s->cfg.n_episodes + EBC_WARPS_PER_BLOCK - 1) / EBC_WARPS_PER_BLOCK;
+  const int n = s->cfg.max_humans + s->cfg.max_statics, D = s->cfg.with_agent_type ? 17 : 13;
+  const size_t smem = (size_t)EBC_WARPS_PER_BLOCK * n * D * sizeof(float);
+  transform_kernel<<<blocks, EBC_THREADS, smem, stream>>>(s->cfg, s->st, out);
+  return ebc_check_launch(s, "transform_kernel");
+}
+
+int ebc_launch_select(ebc_sim *s, const double *reward, const float *values, double *action_values,
+                      int32_t *argmax, uint8_t *nan_flag, cudaStream_t stream) {
+  const int blocks = (s->cfg.n_episodes + EBC_WARPS_PER_BLOCK - 1) / EBC_WARPS_PER_BLOCK;
+  select_kernel<<<blocks, EBC_THREADS, 0, stream>>>(s->cfg, s->st, reward, values, action_values, argmax, nan_flag);
+  return ebc_check_launch(s, "select_kernel");
+}
+
+int ebc_launch_step(ebc_sim *s, bool fused_orca, const int32_t *action_idx, const double *action,
+                    const uint8_t *active, double *reward, uint8_t *done, uint8_t *event, double *dmin,
+                    double *dist_to_goal, cudaStream_t stream) {
+  if (fused_orca) {
+    int warps = s->cfg.max_humans < 16 ? s->cfg.max_humans : 16;
+    if (warps < 1) warps = 1;
+    orca_step_kernel<<<s->cfg.n_episodes, warps * 32, 0, stream>>>(s->cfg, s->st, s->d_actions, action_idx, action,
+                                                                  active, reward, done, event, dmin, dist_to_goal);
+    return ebc_check_launch(s, "orca_step_kernel");
+  }
+  const int blocks = (s->cfg.n_episodes + EBC_WARPS_PER_BLOCK - 1) / EBC_WARPS_PER_BLOCK;
+  step_kernel<<<blocks, EBC_THREADS, 0, stream>>>(s->cfg, s->st, s->d_actions, action_idx, action, active, reward,
+                                                  done, event, dmin, dist_to_goal);
+  return ebc_check_launch(s, "step_kernel");
+}

@@ -1,8 +1,8 @@
 """ctypes view of include/ebcadrl.h — the C ABI of the B200 hot path.
 
 The product library is eb-cadrl_b200/lib/libebcadrl.so (CUDA, sm_100a).  There is no CPU
-fallback: `load()` raises if the library is missing.  (tests/ load the CPU oracle through
-tests/oracle_backend.py with the same struct definitions; nothing in this package does.)
+fallback: `load()` raises if the library is missing.  (The CPU checker used by tests/ lives outside this
+package and reuses these struct definitions; nothing in this package loads it.)
 """
 import ctypes
 import os

@@ -1,0 +1,305 @@
+"""Parity of the CUDA hot path (libebcadrl.so, through the C ABI) against the CPU oracle and the
+reference's golden vectors.  Needs a B200: every test is marked `gpu`.
+
+Bars (north_star): ORCA velocities (fp32, no FMA on both sides), collision / done / event flags,
+dmin and rewards (fp64 in the reference's operation order): BIT-EXACT versus the oracle.
+Rotated rows: 4e-6 (atan2f / cosf / sinf differ by ulps between CUDA and glibc).  Values: 1e-4
+(fp32 FFMA vs correctly-rounded).  Argmax: identical wherever the top-2 gap exceeds 5e-4.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle_backend as ob
+from ebc import synth
+from ebc.actions import build_action_space
+from ebc.config import SimConfig
+from ebc.engine import BatchedSim
+
+pytestmark = pytest.mark.gpu
+
+VIN_TOL = 4e-6
+VALUE_TOL = 1e-4
+ARGMAX_GAP = 5e-4
+
+
+def pair(cfg, N, H, S, R, oracle, A=81, actions=None, weights=None):
+    sims = []
+    for dev, be in (("cuda:0", None), ("cpu", oracle)):
+        s = BatchedSim(cfg, N, H, S, R, A, device=dev, backend=be)
+        if actions is not None:
+            s.set_actions(actions)
+        if weights is not None:
+            s.set_weights(weights)
+        sims.append(s)
+    return sims
+
+
+def np_(t):
+    return t.detach().cpu().numpy()
+
+
+def assert_same_bits(a, b, what):
+    a, b = np_(a), np_(b)
+    same = (a == b) | (np.isnan(a) & np.isnan(b))
+    assert same.all(), "%s: %d / %d differ, first at %s: %r vs %r" % (
+        what, (~same).sum(), same.size, np.argwhere(~same)[0], a[~same][0], b[~same][0])
+
+
+@pytest.mark.parametrize("name", sorted(ob.TRACE_WEIGHTS))
+def test_golden_traces(oracle, name):
+    """Every recorded step of a reference trace becomes one episode of a batch."""
+    tr = ob.Trace(name)
+    H, S, R = tr.dims()
+    N = tr.n_steps
+    g, r = pair(tr.sim_config(), N, H, S, R, oracle, actions=tr.z["actions"],
+                weights=ob.load_weights(ob.TRACE_WEIGHTS[name]))
+    for t in range(N):
+        tr.load_into(g, t, episode=t)
+        tr.load_into(r, t, episode=t)
+    for s in (g, r):
+        s.decide()
+    torch.cuda.synchronize()
+    exact_f64 = tr.cfg_dict["robot_kinematics"] == 0   # unicycle: CUDA cos/sin(double) vs glibc
+    assert_same_bits(g.hum_nv, r.hum_nv, "ORCA velocities")
+    ref_orca = np.stack([tr.get(t, "orca") for t in range(N)])
+    assert np.array_equal(np_(g.hum_nv)[:, :H].astype(np.float64), ref_orca), "ORCA vs reference golden"
+    assert_same_bits(g.la_event, r.la_event, "lookahead events")
+    assert_same_bits(g.la_done, r.la_done, "lookahead done")
+    has = [t for t in range(N) if tr.has(t, "la_event")]
+    ref_ev = np.stack([tr.get(t, "la_event") for t in has])
+    assert np.array_equal(np_(g.la_event)[has], ref_ev), "lookahead events vs reference golden"
+    if exact_f64:
+        assert_same_bits(g.la_reward, r.la_reward, "lookahead rewards")
+    else:
+        np.testing.assert_allclose(np_(g.la_reward), np_(r.la_reward), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(np_(g.vin), np_(r.vin), rtol=0, atol=VIN_TOL)
+    np.testing.assert_allclose(np_(g.values), np_(r.values), rtol=0, atol=VALUE_TOL)
+    ref_val = np.stack([tr.get(t, "la_value") for t in has])
+    np.testing.assert_allclose(np_(g.values)[has], ref_val, rtol=0, atol=2e-4)
+    flips = 0
+    for t in has:
+        if int(g.argmax[t]) != tr.steps[t]["argmax"]:
+            flips += 1
+            assert tr.steps[t]["top2_gap"] < ARGMAX_GAP, (name, t, tr.steps[t]["top2_gap"])
+    assert flips <= max(1, len(has) // 50), flips
+    # committed step with the reference's action
+    act = np.stack([tr.get(t, "action") for t in range(N)])
+    for s in (g, r):
+        s.step(action=torch.as_tensor(act, dtype=torch.float64, device=s.device))
+    torch.cuda.synchronize()
+    assert_same_bits(g.event, r.event, "step events")
+    assert np.array_equal(np_(g.event), np.array([st["event"] for st in tr.steps], np.uint8))
+    assert_same_bits(g.done, r.done, "step done")
+    if exact_f64:
+        for k in ("reward", "dmin", "dist_to_goal", "hum_pv", "rob_pv", "rob_theta", "time"):
+            assert_same_bits(getattr(g, k), getattr(r, k), "step " + k)
+    else:
+        for k in ("reward", "dmin", "dist_to_goal", "hum_pv", "rob_pv", "rob_theta", "time"):
+            a, b = np_(getattr(g, k)), np_(getattr(r, k))
+            fin = np.isfinite(b)
+            assert np.array_equal(np.isfinite(a), fin)
+            np.testing.assert_allclose(a[fin], b[fin], rtol=0, atol=1e-6)
+
+
+def random_batch(N, H, S, R, seed, dense=False):
+    rng = np.random.default_rng(seed)
+    span = 3.0 if dense else 6.0
+    d = {}
+    d["hum_count"] = rng.integers(1, H + 1, N).astype(np.int32)
+    d["hum_pv"] = np.concatenate([rng.uniform(-span, span, (N, H, 2)), rng.uniform(-1, 1, (N, H, 2))], 2).astype(np.float32)
+    d["hum_gr"] = np.concatenate([rng.uniform(-span, span, (N, H, 2)), rng.uniform(0.3, 1.5, (N, H, 1)),
+                                  rng.uniform(0.1, 0.6, (N, H, 1))], 2).astype(np.float32)
+    d["hum_type"] = np.sort(rng.integers(0, 3, (N, H)), axis=1).astype(np.uint8)
+    # ragged: types must stay sorted within the first hum_count entries -> sort prefix only
+    for e in range(N):
+        c = d["hum_count"][e]
+        d["hum_type"][e, :c] = np.sort(rng.integers(0, 3, c))
+    # some exact duplicates of distance (ties) and a few goals within 1 m (pref-velocity branch)
+    d["hum_gr"][::7, 0, :2] = d["hum_pv"][::7, 0, :2] + 0.3
+    d["stat_count"] = rng.integers(0, S + 1, N).astype(np.int32)
+    d["stat"] = np.concatenate([rng.uniform(-span, span, (N, max(S, 1), 2)), rng.uniform(0.3, 0.8, (N, max(S, 1), 1)),
+                                np.zeros((N, max(S, 1), 1))], 2).astype(np.float32)
+    d["rect_count"] = rng.integers(0, R + 1, N).astype(np.int32)
+    x0 = rng.integers(0, 80, (N, max(R, 1), 2))
+    wh = rng.integers(1, 31, (N, max(R, 1), 2))
+    d["rect"] = np.concatenate([x0, np.minimum(x0 + wh, 90)], 2).astype(np.int16)
+    d["rob_pv"] = np.concatenate([rng.uniform(-4, 4, (N, 2)), rng.uniform(-1, 1, (N, 2))], 1).astype(np.float32)
+    d["rob_gr"] = np.concatenate([rng.uniform(-4, 4, (N, 2)), rng.uniform(0.5, 1.0, (N, 1)),
+                                  rng.uniform(0.2, 0.4, (N, 1))], 1).astype(np.float32)
+    d["rob_gr"][::11, :2] = d["rob_pv"][::11, :2] + 0.05      # already at the goal -> stop action
+    d["rob_theta"] = rng.uniform(0, 2 * np.pi, N).astype(np.float32)
+    d["time"] = (rng.integers(0, 110, N) * 0.25).astype(np.float64)   # some past the time limit
+    return d
+
+
+def random_cfg(kin="holonomic", typed=True, visible=False):
+    c = SimConfig()
+    c.time_limit = 25.0
+    c.new_reward, c.max_goal_distance, c.time_max, c.time_good = True, 10.0, 25.0, 10.0
+    c.collision_penalty_adult, c.collision_penalty_bicycle = -1.0, -1.5
+    c.collision_penalty_child, c.collision_penalty_obstacle = -2.0, -0.5
+    c.discomfort_dist_adult, c.discomfort_dist_bicycle, c.discomfort_dist_child = 0.1, 0.2, 0.2
+    c.discomfort_penalty_factor_bicycle = c.discomfort_penalty_factor_child = 1.0
+    c.rotation_penalty_factor = -0.01 if kin != "holonomic" else 0.0
+    c.robot_kinematics, c.with_agent_type, c.robot_visible = kin, typed, visible
+    return c
+
+
+@pytest.mark.parametrize("H,S,R,dense,kin,visible", [
+    (10, 6, 3, False, "holonomic", False),
+    (24, 6, 3, True, "holonomic", False),      # > 10 neighbours: maxNeighbors truncation, LP3 (infeasible) live
+    (5, 0, 0, False, "unicycle", False),
+    (40, 8, 4, True, "holonomic", True),       # two candidates per lane + visible robot
+])
+def test_random_batches(oracle, H, S, R, dense, kin, visible):
+    N = 1536
+    cfg = random_cfg(kin, typed=True, visible=visible)
+    actions = build_action_space(0.8, kin)
+    g, r = pair(cfg, N, H, S, R, oracle, actions=actions)
+    batch = random_batch(N, H, S, R, seed=H * 100 + S, dense=dense)
+    for s in (g, r):
+        s.load_episodes(0, **batch)
+        s.orca()
+        s.lookahead()
+    torch.cuda.synchronize()
+    exact = kin == "holonomic"
+    assert_same_bits(g.hum_nv, r.hum_nv, "ORCA velocities")
+    assert_same_bits(g.la_event, r.la_event, "lookahead events")
+    assert_same_bits(g.la_done, r.la_done, "lookahead done")
+    if exact:
+        assert_same_bits(g.la_reward, r.la_reward, "lookahead rewards")
+    else:
+        np.testing.assert_allclose(np_(g.la_reward), np_(r.la_reward), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(np_(g.vin), np_(r.vin), rtol=0, atol=2e-5)   # positions up to ~12 m here
+    # events of every class must actually occur in this batch
+    seen = set(np.unique(np_(g.la_event)).tolist())
+    assert {0, 1, 7}.issubset(seen) and len(seen) >= 5, seen
+    idx = torch.as_tensor(np.random.default_rng(1).integers(0, 81, N), dtype=torch.int32)
+    active = torch.as_tensor((np.arange(N) % 5 != 0).astype(np.uint8))
+    before = np_(g.hum_pv).copy()
+    g.step(action_idx=idx.cuda(), active=active.cuda())
+    r.step(action_idx=idx, active=active)
+    torch.cuda.synchronize()
+    assert_same_bits(g.event, r.event, "step events")
+    for k in ("done", "hum_pv", "time") + (("reward", "dmin", "dist_to_goal", "rob_pv", "rob_theta") if exact else ()):
+        assert_same_bits(getattr(g, k), getattr(r, k), "step " + k)
+    assert np.array_equal(np_(g.hum_pv)[::5], before[::5]), "inactive episodes must not move"
+    # robot as ORCA agent (imitation learning)
+    ga, ra = g.robot_orca(0.15), r.robot_orca(0.15)
+    torch.cuda.synchronize()
+    assert_same_bits(ga, ra, "robot ORCA action")
+    # rotated current state (replay sample)
+    np.testing.assert_allclose(np_(g.transform()), np_(r.transform()), rtol=0, atol=2e-5)
+
+
+def test_fused_orca_step_equals_two_launches(oracle):
+    N, H, S, R = 1024, 10, 6, 3
+    cfg = random_cfg()
+    actions = build_action_space(0.8)
+    a = BatchedSim(cfg, N, H, S, R, 81, device="cuda:0")
+    b = BatchedSim(cfg, N, H, S, R, 81, device="cuda:0")
+    batch = random_batch(N, H, S, R, seed=5)
+    idx = torch.as_tensor(np.random.default_rng(2).integers(0, 81, N), dtype=torch.int32, device="cuda:0")
+    for s in (a, b):
+        s.set_actions(actions)
+        s.load_episodes(0, **batch)
+    for _ in range(6):
+        a.orca(); a.step(action_idx=idx)
+        b.step(action_idx=idx, fused_orca=True)
+    torch.cuda.synchronize()
+    for k in ("hum_pv", "hum_nv", "rob_pv", "time", "event", "reward", "dmin"):
+        assert_same_bits(getattr(a, k), getattr(b, k), k)
+
+
+def test_value_network_vs_torch_fp32(oracle):
+    """K4 against a plain PyTorch fp32 restatement of rl/policy/sarl.py:38-82 (ragged row counts)."""
+    w = ob.load_weights("weights_ebcadrl.npz")
+    cfg = random_cfg()
+    n_states, H, S = 4000, 10, 6
+    n, D = H + S, 17
+    sim = BatchedSim(cfg, 1, H, S, 0, 81, device="cuda:0")
+    sim.set_weights(w)
+    rng = np.random.default_rng(3)
+    x = rng.normal(0, 1, (n_states, n, D)).astype(np.float32)
+    cnt = rng.integers(1, n + 1, n_states).astype(np.int32)
+    for i in range(n_states):
+        x[i, cnt[i]:] = 0
+    xt = torch.as_tensor(x, device="cuda:0")
+    ct = torch.as_tensor(cnt, device="cuda:0")
+    got = sim.value(xt, ct)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    W = {k: torch.as_tensor(v, device="cuda:0", dtype=torch.float64) for k, v in w.items()}
+
+    def lin(x, k, relu):
+        y = x @ W[k + ".weight"].T + W[k + ".bias"]
+        return torch.relu(y) if relu else y
+
+    xd = xt.double()
+    h1 = lin(lin(xd, "mlp1.0", True), "mlp1.2", True)
+    h2 = lin(lin(h1, "mlp2.0", True), "mlp2.2", False)
+    mask = (torch.arange(n, device="cuda:0")[None] < ct[:, None]).double()
+    g = (h1 * mask[..., None]).sum(1, keepdim=True) / ct[:, None, None].double()
+    a = lin(lin(lin(torch.cat([h1, g.expand(-1, n, -1)], 2), "attention.0", True), "attention.2", True), "attention.4", False)[..., 0]
+    e = torch.exp(a) * (a != 0) * mask
+    wts = e / e.sum(1, keepdim=True)
+    f = (wts[..., None] * h2).sum(1)
+    j = torch.cat([xd[:, 0, :6], f], 1)
+    v = lin(lin(lin(lin(j, "mlp3.0", True), "mlp3.2", True), "mlp3.4", True), "mlp3.6", False)[:, 0]
+    torch.cuda.synchronize()
+    err = (got.double() - v).abs().max().item()
+    scale = v.abs().max().item()
+    assert err < 1e-4 * max(1.0, scale), (err, scale)
+
+
+def test_full_size_properties():
+    """BASELINE configs[1] at full size (N = 4096): size-independent properties."""
+    N = 4096
+    shape = synth.CFG2
+    cfg = random_cfg()
+    w = ob.load_weights("weights_ebcadrl.npz")
+    scenes = synth.generate(shape, np.arange(N))
+    perm = np.random.default_rng(0).permutation(N)
+    a = BatchedSim(cfg, N, shape.H, shape.Smax, shape.Rmax, 81, device="cuda:0")
+    b = BatchedSim(cfg, N, shape.H, shape.Smax, shape.Rmax, 81, device="cuda:0")
+    actions = build_action_space(shape.robot_v_pref)
+    for s, sc in ((a, scenes), (b, {k: v[perm] for k, v in scenes.items()})):
+        s.set_actions(actions)
+        s.set_weights(w)
+        synth.load(s, sc)
+    for t in range(3):
+        snap = {k: getattr(a, k).clone() for k in ("hum_pv", "rob_pv", "time", "rob_theta")}
+        am, bm = a.decide().clone(), b.decide().clone()
+        torch.cuda.synchronize()
+        # the lookahead must not mutate the episode state (env.onestep_lookahead, update=False)
+        for k, v in snap.items():
+            assert torch.equal(getattr(a, k), v), k
+        # episodes are independent: permuting the batch permutes the results, bit for bit
+        assert torch.equal(am[torch.as_tensor(perm, device="cuda:0")], bm)
+        assert torch.equal(a.values[torch.as_tensor(perm, device="cuda:0")], b.values)
+        # ORCA respects the speed disc (maxSpeed = v_pref)
+        sp = torch.linalg.norm(a.hum_nv, dim=2)
+        assert (sp <= a.hum_gr[:, :, 2] * (1 + 1e-5) + 1e-6).all()
+        # action 0 is "stop": its lookahead reward never contains a goal-progress term larger than any other's
+        assert (a.nan_flag == 0).all()
+        a.step(action_idx=am)
+        b.step(action_idx=bm)
+    torch.cuda.synchronize()
+    assert torch.equal(a.hum_pv[torch.as_tensor(perm, device="cuda:0")], b.hum_pv)
+    assert float(a.time[0]) == 0.75
+
+
+def test_error_codes():
+    import ctypes
+    from ebc import abi
+    lib = abi.load()
+    cfg = random_cfg().to_abi(4, 3, 0, 0, 81)
+    h = abi.SIM()
+    assert lib.ebc_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == 0
+    assert lib.ebc_orca(h, None) == -2 and b"not bound" in lib.ebc_last_error(h)
+    assert lib.ebc_value(h, None, 0, None, None, None) == -2
+    bad = random_cfg().to_abi(4, 70, 0, 0, 81)
+    h2 = abi.SIM()
+    assert lib.ebc_create(ctypes.byref(bad), 0, ctypes.byref(h2)) == -1
+    assert b"out of range" in lib.ebc_last_error(None)
+    lib.ebc_destroy(h)
