@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the EB-CADRL hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[1] — EB-CADRL entity-typed agents + static
+obstacles, 10 humans (4 adults + 3 bicycles + 3 children), 3 walls (6 static discs, n = 16 rows,
+D = 17), 81 holonomic actions, 4096 parallel episodes PER GPU (weak scaling), synthetic scenes
+(ebc/synth.py, counter-based RNG keyed by the global episode id), EB-CADRL value network
+(379,202 parameters; the shipped rl_model_val weights fixture, else seeded random init).
+
+One "step" = what the reference does per env step with the policy in the loop
+(rl/utils/explorer.py:41-46): robot decision by one-step lookahead over all 81 actions
+(ORCA for the humans, lookahead expansion, value network, argmax) + the committed env.step
++ re-initialisation of finished episodes.  Reported:
+    value                 agent-steps/s  = episodes * (H + 1) / step time      (whole job, all GPUs)
+    lookahead_evals_per_sec              = episodes * 81 / step time
+    sim_only              the policy-free path (ORCA + step in one launch), its own timing
+    roofline              the dominant kernel pair (K4 value network)
+    e2e                   the same step through the host-facing API: pinned host state -> device,
+                          decide + step, observation / reward / done / event -> pinned host
+    cpu_baseline          the CPU oracle (port of the reference path) on this box's cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "eb-cadrl_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+EPISODES_PER_GPU = 4096
+N_ACTIONS = 81
+METRIC = "agent_steps_per_sec"
+UNIT = "agent-steps/s"
+
+
+def workload():
+    from ebc import synth
+    from ebc.config import SimConfig
+    shape = synth.CFG2
+    c = SimConfig()   # reward block of data/eb-cadrl/adults_8_..._fix_static.config:26-44
+    c.time_step, c.time_limit = 0.25, 35.0
+    c.new_reward, c.time_max, c.time_good, c.max_goal_distance = True, 35.0, 10.0, 10.0
+    c.success_reward = 1.0
+    c.collision_penalty_adult, c.collision_penalty_bicycle = -1.0, -1.5
+    c.collision_penalty_child, c.collision_penalty_obstacle = -2.0, -0.5
+    c.discomfort_dist = c.discomfort_dist_adult = 0.1
+    c.discomfort_dist_bicycle = c.discomfort_dist_child = 0.2
+    c.discomfort_penalty_factor_adult = 0.5
+    c.discomfort_penalty_factor_bicycle = c.discomfort_penalty_factor_child = 1.0
+    c.map_size_m, c.map_resolution = shape.map_size_m, shape.map_resolution
+    c.robot_kinematics, c.with_agent_type, c.gamma = "holonomic", True, 0.9
+    return shape, c
+
+
+def value_net_weights(D=17, seed=0):
+    path = os.path.join(ROOT, "tests", "golden", "weights_ebcadrl.npz")
+    if os.path.exists(path):
+        z = np.load(path)
+        return {k: z[k] for k in z.files}, "rl_model_val fixture"
+    rng = np.random.default_rng(seed)
+    dims = {"mlp1": [D, 300, 200], "mlp2": [200, 200, 100], "attention": [400, 200, 200, 1],
+            "mlp3": [106, 300, 200, 200, 1]}
+    sd = {}
+    for name, ds in dims.items():
+        for i in range(len(ds) - 1):
+            b = 1.0 / np.sqrt(ds[i])
+            sd["%s.%d.weight" % (name, 2 * i)] = rng.uniform(-b, b, (ds[i + 1], ds[i])).astype(np.float32)
+            sd["%s.%d.bias" % (name, 2 * i)] = rng.uniform(-b, b, ds[i + 1]).astype(np.float32)
+    return sd, "seeded random init"
+
+
+def flops_per_eval(sd, n):
+    """2 * (n * M_e + M_s) of SURVEY §8d from the actual layer shapes."""
+    me = sum(int(np.prod(sd[k].shape)) for k in sd if k.endswith("weight") and not k.startswith("mlp3"))
+    ms = sum(int(np.prod(sd[k].shape)) for k in sd if k.endswith("weight") and k.startswith("mlp3"))
+    return 2 * (n * me + ms)
+
+
+class ClockSampler(threading.Thread):
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        rows = [r for r in self.rows if len(r) == 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i] == "Active" for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows), "reasons": reasons}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "tensor_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "MEASURED_PEAKS.json (bf16 sustained, copy bandwidth)"}
+    return {"hbm_gbs": 6650.0, "tensor_tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def cpu_oracle_rate(shape, cfg, weights, episodes, steps, threads, full_loop=True):
+    """agent-steps/s of the CPU oracle on `episodes` episodes of the same workload."""
+    import oracle_backend as ob
+    from ebc import synth
+    from ebc.actions import build_action_space
+    from ebc.engine import BatchedSim
+    be = ob.OracleBackend()
+    be.set_threads(threads)
+    sim = BatchedSim(cfg, episodes, shape.H, shape.Smax, shape.Rmax, N_ACTIONS, device="cpu", backend=be)
+    sim.set_actions(build_action_space(shape.robot_v_pref))
+    sim.set_weights(weights)
+    synth.load(sim, synth.generate(shape, np.arange(episodes)))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        if full_loop:
+            sim.decide()
+            sim.step(action_idx=sim.argmax)
+        else:
+            sim.step(action_idx=torch.zeros(episodes, dtype=torch.int32), fused_orca=True)
+    dt = time.perf_counter() - t0
+    return episodes * (shape.H + 1) * steps / dt, dt
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's own CPU implementation of the path.  The reference is pure
+    Python + the un-vendored rvo2 and cannot travel to the GPU box, so this is the oracle port
+    (oracle/ebc_oracle.c, the restatement pinned against the reference's golden vectors) with all
+    host threads, each step a bounded sample of the workload."""
+    if rank != 0:
+        return
+    shape, cfg = workload()
+    weights, wsrc = value_net_weights()
+    threads = os.cpu_count() or 1
+    sample = max(2 * threads, 16)
+    steps = max(1, args.steps)
+    for _ in range(min(args.warmup, 1)):
+        cpu_oracle_rate(shape, cfg, weights, sample, 1, threads)
+    rate, dt = cpu_oracle_rate(shape, cfg, weights, sample, steps, threads)
+    desc = "%d episodes x %d full steps (decision over 81 actions + env.step) of %s" % (sample, steps, shape.name)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": shape.name, "episodes_per_step": sample, "humans": shape.H, "actions": N_ACTIONS,
+                   "weights": wsrc},
+        "lookahead_evals_per_sec": rate / (shape.H + 1) * N_ACTIONS,
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--episodes", type=int, default=EPISODES_PER_GPU, help="episodes per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    if args.warmup < 3:
+        args.warmup = 3
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dist = None
+
+    from ebc import synth
+    from ebc.actions import build_action_space
+    from ebc.engine import BatchedSim
+    shape, cfg = workload()
+    weights, wsrc = value_net_weights()
+    N = args.episodes
+    ids = np.arange(rank * N, (rank + 1) * N)           # episodes shard trivially: no data-path collective
+    scenes = synth.generate(shape, ids)
+    sim = BatchedSim(cfg, N, shape.H, shape.Smax, shape.Rmax, N_ACTIONS, device=dev)
+    sim.set_actions(build_action_space(shape.robot_v_pref))
+    sim.set_weights(weights)
+    synth.load(sim, scenes)
+    pool = sim.make_pool(scenes)
+    n_rows = shape.H + shape.Smax
+    H = shape.H
+
+    def one_step(marks=None):
+        def mark():
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append(e)
+        mark(); sim.orca()
+        mark(); sim.lookahead()
+        mark(); sim.value()
+        mark(); sim.select()
+        mark(); sim.step(action_idx=sim.argmax)
+        mark(); sim.reset(pool, mask=sim.done)
+        mark()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = sim.launch_count()
+    marks = []
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin.record()
+    for _ in range(args.steps):
+        one_step(marks)
+    t_end.record()
+    barrier()
+    launches = sim.launch_count() - launches0
+    elapsed_ms = t_begin.elapsed_time(t_end)
+    phase_names = ["orca", "lookahead", "value", "select", "step", "reset"]
+    phase_ms = dict.fromkeys(phase_names, 0.0)
+    for s in range(args.steps):
+        m = marks[s * 7:(s + 1) * 7]
+        for i, nm in enumerate(phase_names):
+            phase_ms[nm] += m[i].elapsed_time(m[i + 1])
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: the same step through the host-facing API (pinned host buffers) ------------
+    h_pv = torch.empty_like(sim.hum_pv, device="cpu").pin_memory()
+    h_rob = torch.empty_like(sim.rob_pv, device="cpu").pin_memory()
+    h_out = {k: torch.empty_like(getattr(sim, k), device="cpu").pin_memory()
+             for k in ("reward", "done", "event", "argmax")}
+    h_pv.copy_(sim.hum_pv); h_rob.copy_(sim.rob_pv)
+    torch.cuda.synchronize()
+    h2d = h_pv.numel() * 4 + h_rob.numel() * 4
+    d2h = h2d + sum(t.numel() * t.element_size() for t in h_out.values())
+
+    def e2e_step():
+        sim.hum_pv.copy_(h_pv, non_blocking=True)       # the caller's observation / robot state -> device
+        sim.rob_pv.copy_(h_rob, non_blocking=True)
+        sim.decide()
+        sim.step(action_idx=sim.argmax)
+        h_pv.copy_(sim.hum_pv, non_blocking=True)       # new observation, reward, done, info -> host
+        h_rob.copy_(sim.rob_pv, non_blocking=True)
+        for k, t in h_out.items():
+            t.copy_(getattr(sim, k), non_blocking=True)
+        torch.cuda.synchronize()                        # the host consumes the result every step
+        sim.reset(pool, mask=sim.done)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- sim-only path: ORCA + committed step in one launch, L2 flushed between iterations ----
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    zero_idx = torch.zeros(N, dtype=torch.int32, device=dev)
+    sim_ms, sim_iters = 0.0, 30
+    for it in range(sim_iters + 3):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        sim.step(action_idx=zero_idx, fused_orca=True)
+        b.record()
+        torch.cuda.synchronize()
+        if it >= 3:
+            sim_ms += a.elapsed_time(b)
+        sim.reset(pool, mask=sim.done)
+    del flush
+
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    elapsed_ms = allmax(elapsed_ms)
+    e2e_s = allmax(e2e_s)
+    sim_ms = allmax(sim_ms)
+    value_ms = allmax(phase_ms["value"])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    total_eps = N * world
+    step_s = elapsed_ms / 1e3 / args.steps
+    peaks = measured_peaks()
+    fl = flops_per_eval(weights, n_rows) * N * N_ACTIONS            # per GPU per value phase
+    achieved_tf = fl / (value_ms / 1e3 / args.steps) / 1e12
+    sim_step_s = sim_ms / 1e3 / sim_iters
+    sim_bytes = N * (48 * H + 90)
+    line = {
+        "metric": METRIC, "value": total_eps * (H + 1) / step_s, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": shape.name, "episodes_per_gpu": N, "humans": H, "static_discs": shape.Smax,
+                   "rows_per_state": n_rows, "D": cfg.D, "actions": N_ACTIONS, "weights": wsrc,
+                   "parallelism": "episodes sharded over %d GPU(s), no data-path collective" % world,
+                   "l2": "per-step working set %.0f MB (value-net input) exceeds the 126 MB L2; "
+                         "sim_only flushes L2 between iterations" % (N * N_ACTIONS * n_rows * cfg.D * 4 / 1e6)},
+        "lookahead_evals_per_sec": total_eps * N_ACTIONS / step_s,
+        "phase_ms_per_step": {k: v / args.steps for k, v in phase_ms.items()},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"kernel": "K4 value network (value_entity_kernel + value_mlp3_kernel), fp32 FFMA path",
+                     "bound": "tensor", "achieved": achieved_tf, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
+                     "frac": achieved_tf / peaks["tensor_tflops"], "traffic": None,
+                     "peak_source": peaks["source"],
+                     "note": "algorithmic FLOPs 2*(n*M_e+M_s) per (episode, action); this round's kernel is fp32 "
+                             "SIMT (argmax-parity mode), FP32-ALU roof 74 TFLOP/s -> frac_alu below",
+                     "frac_alu": achieved_tf / 74.0},
+        "sim_only": {"agent_steps_per_sec": total_eps * (H + 1) / sim_step_s, "ms_per_step": sim_step_s * 1e3,
+                     "launches_per_step": 1,
+                     "roofline": {"bound": "hbm", "achieved": sim_bytes / sim_step_s / 1e9, "peak": peaks["hbm_gbs"],
+                                  "unit": "GB/s", "frac": sim_bytes / sim_step_s / 1e9 / peaks["hbm_gbs"],
+                                  "note": "48*H+90 algorithmic bytes per episode-step; latency/ALU-bound at this size"}},
+        "e2e": {"value": total_eps * (H + 1) / (e2e_s / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+    }
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sample = max(4 * threads, 32)
+        rate, dt = cpu_oracle_rate(shape, cfg, weights, sample, 2, threads)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "%d episodes x 2 full steps of %s, %.1f s" % (sample, shape.name, dt)}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

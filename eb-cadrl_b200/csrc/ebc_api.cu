@@ -167,6 +167,16 @@ int ebc_transform(ebc_sim *s, float *out, void *stream) {
   return ebc_launch_transform(s, out, (cudaStream_t)stream);
 }
 
+int ebc_reset(ebc_sim *s, const ebc_state *pool, int32_t pool_size, const int32_t *pool_index, const uint8_t *mask,
+              void *stream) {
+  REQUIRE_BOUND("ebc_reset");
+  if (!pool || pool_size < 1 || !pool->hum_pv || !pool->hum_gr || !pool->hum_type || !pool->hum_count ||
+      !pool->stat_count || !pool->rect_count || !pool->rob_pv || !pool->rob_gr || !pool->rob_theta || !pool->time ||
+      (s->cfg.max_statics > 0 && !pool->stat) || (s->cfg.max_rects > 0 && !pool->rect))
+    return ebc_fail(s, EBC_ERR_INVALID, "ebc_reset: bad scene pool");
+  return ebc_launch_reset(s, pool, pool_size, pool_index, mask, (cudaStream_t)stream);
+}
+
 int64_t ebc_launch_count(const ebc_sim *s) { return s ? s->launches : 0; }
 
 }  // extern "C"

@@ -51,6 +51,8 @@ int ebc_launch_step(ebc_sim *s, bool fused_orca, const int32_t *action_idx, cons
                     const uint8_t *active, double *reward, uint8_t *done, uint8_t *event, double *dmin,
                     double *dist_to_goal, cudaStream_t st);
 int ebc_launch_transform(ebc_sim *s, float *out, cudaStream_t st);
+int ebc_launch_reset(ebc_sim *s, const ebc_state *pool, int pool_size, const int32_t *pool_index,
+                     const uint8_t *mask, cudaStream_t st);
 
 // ebc_value.cu
 int ebc_value_prepare(ebc_sim *s, const ebc_weights *w);

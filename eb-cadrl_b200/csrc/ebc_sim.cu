@@ -789,7 +789,46 @@ orca_step_kernel(const ebc_config c, const ebc_state st, const double *__restric
     commit_episode_warp(c, st, e, lane, actions, action_idx, action, reward, done, event, dmin, dist_to_goal);
 }
 
+// env.reset from a device-resident scene pool; one warp per episode, lanes copy 16-byte words.
+__global__ void __launch_bounds__(EBC_THREADS)
+reset_kernel(const ebc_config c, const ebc_state st, const ebc_state pool, int pool_size,
+             const int32_t *pool_index, const uint8_t *mask) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * EBC_WARPS_PER_BLOCK + warp;
+  if (e >= c.n_episodes) return;
+  if (mask && !mask[e]) return;
+  int q = pool_index ? pool_index[e] : e;
+  if (q < 0 || q >= pool_size) q = ((q % pool_size) + pool_size) % pool_size;
+  const int Hm = c.max_humans, Sm = c.max_statics, Rm = c.max_rects;
+  for (int h = lane; h < Hm; h += 32) {
+    reinterpret_cast<float4 *>(st.hum_pv)[(size_t)e * Hm + h] = reinterpret_cast<const float4 *>(pool.hum_pv)[(size_t)q * Hm + h];
+    reinterpret_cast<float4 *>(st.hum_gr)[(size_t)e * Hm + h] = reinterpret_cast<const float4 *>(pool.hum_gr)[(size_t)q * Hm + h];
+    st.hum_type[(size_t)e * Hm + h] = pool.hum_type[(size_t)q * Hm + h];
+    reinterpret_cast<float2 *>(st.hum_nv)[(size_t)e * Hm + h] = make_float2(0.f, 0.f);
+  }
+  for (int k = lane; k < Sm; k += 32)
+    reinterpret_cast<float4 *>(st.stat)[(size_t)e * Sm + k] = reinterpret_cast<const float4 *>(pool.stat)[(size_t)q * Sm + k];
+  for (int j = lane; j < Rm; j += 32)
+    reinterpret_cast<short4 *>(st.rect)[(size_t)e * Rm + j] = reinterpret_cast<const short4 *>(pool.rect)[(size_t)q * Rm + j];
+  if (lane == 0) {
+    st.hum_count[e] = pool.hum_count[q];
+    st.stat_count[e] = pool.stat_count[q];
+    st.rect_count[e] = pool.rect_count[q];
+    reinterpret_cast<float4 *>(st.rob_pv)[e] = reinterpret_cast<const float4 *>(pool.rob_pv)[q];
+    reinterpret_cast<float4 *>(st.rob_gr)[e] = reinterpret_cast<const float4 *>(pool.rob_gr)[q];
+    st.rob_theta[e] = pool.rob_theta[q];
+    st.time[e] = pool.time[q];
+  }
+}
+
 }  // namespace
+
+int ebc_launch_reset(ebc_sim *s, const ebc_state *pool, int pool_size, const int32_t *pool_index,
+                     const uint8_t *mask, cudaStream_t stream) {
+  const int blocks = (s->cfg.n_episodes + EBC_WARPS_PER_BLOCK - 1) / EBC_WARPS_PER_BLOCK;
+  reset_kernel<<<blocks, EBC_THREADS, 0, stream>>>(s->cfg, s->st, *pool, pool_size, pool_index, mask);
+  return ebc_check_launch(s, "reset_kernel");
+}
 
 int ebc_launch_orca(ebc_sim *s, cudaStream_t stream) {
   const long long warps = (long long)s->cfg.n_episodes * s->cfg.max_humans;

@@ -73,6 +73,7 @@ PROTOTYPES = {
     "ebc_step": (c_i32, [SIM, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "ebc_orca_step": (c_i32, [SIM, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "ebc_transform": (c_i32, [SIM, vp, vp]),
+    "ebc_reset": (c_i32, [SIM, ctypes.POINTER(EbcState), c_i32, vp, vp, vp]),
     "ebc_launch_count": (ctypes.c_int64, [SIM]),
 }
 

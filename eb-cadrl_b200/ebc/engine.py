@@ -235,6 +235,16 @@ class BatchedSim(object):
                      _ptr(self.done), _ptr(self.event), _ptr(self.dmin), _ptr(self.dist_to_goal),
                      stream=self._stream())
 
+    def make_pool(self, scenes):
+        """Upload pre-generated scenes (dict of numpy arrays in the ebc_state layout, any count P)
+        as a device-resident pool for `reset`."""
+        return ScenePool(self, scenes)
+
+    def reset(self, pool, pool_index=None, mask=None):
+        """env.reset for the masked episodes from a device scene pool (simulator/env.py:128-205)."""
+        self.be.call("reset", self.h, ctypes.byref(pool.state), pool.size, _ptr(pool_index), _ptr(mask),
+                     stream=self._stream())
+
     def transform(self, out=None):
         if out is None:
             out = torch.zeros(self.N, self.n, self.D, dtype=torch.float32, device=self.device)
@@ -243,3 +253,32 @@ class BatchedSim(object):
 
     def launch_count(self):
         return self.be.launch_count(self.h)
+
+
+class ScenePool(object):
+    """P pre-generated scenes resident on the device, in the ebc_state layout of `sim`."""
+    _FIELDS = (("hum_pv", torch.float32), ("hum_gr", torch.float32), ("hum_type", torch.uint8),
+               ("hum_count", torch.int32), ("stat", torch.float32), ("stat_count", torch.int32),
+               ("rect", torch.int16), ("rect_count", torch.int32), ("rob_pv", torch.float32),
+               ("rob_gr", torch.float32), ("rob_theta", torch.float32), ("time", torch.float64))
+
+    def __init__(self, sim, scenes):
+        self.size = int(len(scenes["hum_count"]))
+        self.tensors = {}
+        shapes = {"hum_pv": (sim.Hmax, 4), "hum_gr": (sim.Hmax, 4), "hum_type": (sim.Hmax,),
+                  "stat": (max(sim.Smax, 1), 4), "rect": (max(sim.Rmax, 1), 4)}
+        st = abi.EbcState()
+        for name, dtype in self._FIELDS:
+            src = scenes.get(name)
+            if src is None:
+                t = torch.zeros((self.size,) + shapes.get(name, ()), dtype=dtype)
+            else:
+                t = torch.as_tensor(np.ascontiguousarray(src), dtype=dtype)
+                if name in shapes:
+                    assert tuple(t.shape[1:]) == shapes[name], (name, tuple(t.shape), shapes[name])
+            t = t.to(sim.device).contiguous()
+            self.tensors[name] = t
+            setattr(st, name, t.data_ptr())
+        self.nv = torch.zeros(self.size, sim.Hmax, 2, dtype=torch.float32, device=sim.device)
+        st.hum_nv = self.nv.data_ptr()
+        self.state = st

@@ -223,6 +223,14 @@ int ebc_orca_step(ebc_sim *sim, const int32_t *action_idx, const double *action,
  * (rl/policy/multi_human_rl.py:128-149): out [N*n*D]. */
 int ebc_transform(ebc_sim *sim, float *out, void *stream);
 
+/* Device-side env.reset (simulator/env.py:128-205) from a pool of pre-generated scenes:
+ * for every episode e with mask[e] != 0 (mask NULL = all), copy scene pool_index[e]
+ * (pool_index NULL = e) of `pool` -- an ebc_state of `pool_size` episodes with the same
+ * Hmax / Smax / Rmax, device arrays -- into the bound state: robot at its start with v = 0,
+ * global_time = 0 (whatever the pool holds), hum_nv cleared. */
+int ebc_reset(ebc_sim *sim, const ebc_state *pool, int32_t pool_size, const int32_t *pool_index,
+              const uint8_t *mask, void *stream);
+
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t ebc_launch_count(const ebc_sim *sim);
 
@@ -244,6 +252,8 @@ int ebc_ref_step(ebc_sim *sim, const int32_t *action_idx, const double *action,
                  const uint8_t *active, double *reward, uint8_t *done, uint8_t *event,
                  double *dmin, double *dist_to_goal);
 int ebc_ref_transform(ebc_sim *sim, float *out);
+int ebc_ref_reset(ebc_sim *sim, const ebc_state *pool, int32_t pool_size, const int32_t *pool_index,
+                  const uint8_t *mask);
 void ebc_ref_set_threads(int n);   /* OpenMP threads over episodes (cpu_baseline leg) */
 
 #ifdef __cplusplus

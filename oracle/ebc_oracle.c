@@ -935,3 +935,31 @@ int ebc_ref_step(ebc_sim *s, const int32_t *action_idx, const double *action, co
   }
   return EBC_OK;
 }
+
+/* env.reset from a scene pool: simulator/env.py:128-205 (state hand-over only). */
+int ebc_ref_reset(ebc_sim *s, const ebc_state *pool, int32_t pool_size, const int32_t *pool_index,
+                  const uint8_t *mask) {
+  if (!s || !s->bound) return fail(s, EBC_ERR_UNBOUND, "ebc_reset: state not bound");
+  if (!pool || pool_size < 1) return fail(s, EBC_ERR_INVALID, "ebc_reset: bad pool");
+  const ebc_config *c = &s->cfg;
+  const int Hm = c->max_humans, Sm = c->max_statics, Rm = c->max_rects;
+  for (int e = 0; e < c->n_episodes; ++e) {
+    if (mask && !mask[e]) continue;
+    int q = pool_index ? pool_index[e] : e;
+    if (q < 0 || q >= pool_size) q = ((q % pool_size) + pool_size) % pool_size;
+    memcpy(s->st.hum_pv + (size_t)e * Hm * 4, pool->hum_pv + (size_t)q * Hm * 4, sizeof(float) * 4 * Hm);
+    memcpy(s->st.hum_gr + (size_t)e * Hm * 4, pool->hum_gr + (size_t)q * Hm * 4, sizeof(float) * 4 * Hm);
+    memcpy(s->st.hum_type + (size_t)e * Hm, pool->hum_type + (size_t)q * Hm, Hm);
+    memset(s->st.hum_nv + (size_t)e * Hm * 2, 0, sizeof(float) * 2 * Hm);
+    s->st.hum_count[e] = pool->hum_count[q];
+    if (Sm) memcpy(s->st.stat + (size_t)e * Sm * 4, pool->stat + (size_t)q * Sm * 4, sizeof(float) * 4 * Sm);
+    s->st.stat_count[e] = pool->stat_count[q];
+    if (Rm) memcpy(s->st.rect + (size_t)e * Rm * 4, pool->rect + (size_t)q * Rm * 4, sizeof(int16_t) * 4 * Rm);
+    s->st.rect_count[e] = pool->rect_count[q];
+    memcpy(s->st.rob_pv + (size_t)e * 4, pool->rob_pv + (size_t)q * 4, sizeof(float) * 4);
+    memcpy(s->st.rob_gr + (size_t)e * 4, pool->rob_gr + (size_t)q * 4, sizeof(float) * 4);
+    s->st.rob_theta[e] = pool->rob_theta[q];
+    s->st.time[e] = pool->time[q];
+  }
+  return EBC_OK;
+}

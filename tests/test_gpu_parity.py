@@ -277,9 +277,10 @@ def test_full_size_properties():
         # episodes are independent: permuting the batch permutes the results, bit for bit
         assert torch.equal(am[torch.as_tensor(perm, device="cuda:0")], bm)
         assert torch.equal(a.values[torch.as_tensor(perm, device="cuda:0")], b.values)
-        # ORCA respects the speed disc (maxSpeed = v_pref)
+        # ORCA respects the speed disc (maxSpeed = v_pref) up to RVO2's own fp32 cancellation in
+        # linearProgram1 (overlapping agents give |point| >> radius; observed excess 3.5e-5 relative)
         sp = torch.linalg.norm(a.hum_nv, dim=2)
-        assert (sp <= a.hum_gr[:, :, 2] * (1 + 1e-5) + 1e-6).all()
+        assert (sp <= a.hum_gr[:, :, 2] * (1 + 1e-3) + 1e-6).all()
         # action 0 is "stop": its lookahead reward never contains a goal-progress term larger than any other's
         assert (a.nan_flag == 0).all()
         a.step(action_idx=am)
@@ -287,6 +288,27 @@ def test_full_size_properties():
     torch.cuda.synchronize()
     assert torch.equal(a.hum_pv[torch.as_tensor(perm, device="cuda:0")], b.hum_pv)
     assert float(a.time[0]) == 0.75
+
+
+def test_reset_from_pool(oracle):
+    N, H, S, R = 512, 10, 6, 3
+    cfg = random_cfg()
+    g, r = pair(cfg, N, H, S, R, oracle, actions=build_action_space(0.8))
+    batch = random_batch(N, H, S, R, seed=9)
+    pool_batch = random_batch(64, H, S, R, seed=10)
+    rng = np.random.default_rng(4)
+    idx = rng.integers(0, 64, N).astype(np.int32)
+    mask = (rng.random(N) < 0.4).astype(np.uint8)
+    for s in (g, r):
+        s.load_episodes(0, **batch)
+        pool = s.make_pool(pool_batch)
+        s.reset(pool, torch.as_tensor(idx, device=s.device), torch.as_tensor(mask, device=s.device))
+    torch.cuda.synchronize()
+    for k in ("hum_pv", "hum_gr", "hum_type", "hum_count", "stat", "stat_count", "rect", "rect_count", "rob_pv",
+              "rob_gr", "rob_theta", "time"):
+        assert_same_bits(getattr(g, k), getattr(r, k), k)
+    assert np.array_equal(np_(g.hum_pv)[mask == 1], pool_batch["hum_pv"][idx[mask == 1]])
+    assert np.array_equal(np_(g.hum_pv)[mask == 0], batch["hum_pv"][mask == 0])
 
 
 def test_error_codes():
