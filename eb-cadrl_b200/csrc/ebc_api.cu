@@ -71,6 +71,7 @@ void ebc_destroy(ebc_sim *s) {
   cudaSetDevice(s->device);
   if (s->d_actions) cudaFree(s->d_actions);
   ebc_value_release(s);
+  ebc_tc_release(s);
   delete s;
 }
 
@@ -103,8 +104,28 @@ int ebc_set_actions(ebc_sim *s, const double *actions, int32_t n) {
 int ebc_set_weights(ebc_sim *s, const ebc_weights *w) {
   if (!s || !w) return EBC_ERR_INVALID;
   cudaSetDevice(s->device);
-  return ebc_value_prepare(s, w);
+  int rc = ebc_value_prepare(s, w);
+  if (rc) return rc;
+  // tensor-core programs: [0] bf16, [1] bf16x3.  A shape that does not fit keeps the FFMA path.
+  const int r0 = ebc_tc_prepare(s, w, 0, 1), r1 = ebc_tc_prepare(s, w, 1, 3);
+  if (r0 < 0) return r0;
+  if (r1 < 0) return r1;
+  if (r0 || r1) { s->tc[0].ready = s->tc[1].ready = 0; s->value_mode = EBC_VALUE_FP32; }
+  else if (!s->value_mode_forced) s->value_mode = EBC_VALUE_TC_FP32;
+  return EBC_OK;
 }
+
+int ebc_set_value_mode(ebc_sim *s, int32_t mode) {
+  if (!s) return EBC_ERR_INVALID;
+  if (mode < EBC_VALUE_FP32 || mode > EBC_VALUE_TC_BF16) return ebc_fail(s, EBC_ERR_INVALID, "ebc_set_value_mode: unknown mode %d", mode);
+  if (mode != EBC_VALUE_FP32 && s->have_weights && !s->tc[mode == EBC_VALUE_TC_BF16 ? 0 : 1].ready)
+    return ebc_fail(s, EBC_ERR_INVALID, "ebc_set_value_mode: this network's shape does not fit the tensor-core tiling");
+  s->value_mode = mode;
+  s->value_mode_forced = 1;
+  return EBC_OK;
+}
+
+int ebc_get_value_mode(const ebc_sim *s) { return s ? s->value_mode : EBC_ERR_INVALID; }
 
 #define REQUIRE_BOUND(name) \
   if (!s) return EBC_ERR_INVALID; \
@@ -131,6 +152,20 @@ int ebc_value(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row
   if (!s) return EBC_ERR_INVALID;
   if (!s->have_weights) return ebc_fail(s, EBC_ERR_UNBOUND, "ebc_value: weights not set");
   if (!vin || !values || n_states < 0) return ebc_fail(s, EBC_ERR_INVALID, "ebc_value: bad argument");
+  {
+    // scratch for the pooled per-state features; grows monotonically, outside any timed steady state
+    const int jd = s->net.self_dim + s->net.l[3].out;
+    if (n_states > s->joint_cap) {
+      if (s->d_joint) cudaFree(s->d_joint);
+      s->d_joint = nullptr;
+      cudaError_t err = cudaMalloc(&s->d_joint, (size_t)n_states * jd * sizeof(float));
+      if (err != cudaSuccess) return ebc_fail(s, EBC_ERR_NOMEM, "cudaMalloc joint scratch: %s", cudaGetErrorString(err));
+      s->joint_cap = n_states;
+    }
+  }
+  if (!row_count && !s->bound) return ebc_fail(s, EBC_ERR_UNBOUND, "ebc_value: state not bound");
+  if (s->value_mode != EBC_VALUE_FP32 && s->tc[s->value_mode == EBC_VALUE_TC_BF16 ? 0 : 1].ready)
+    return ebc_launch_value_tc(s, s->value_mode, vin, n_states, row_count, values, (cudaStream_t)stream);
   return ebc_launch_value(s, vin, n_states, row_count, values, (cudaStream_t)stream);
 }
 

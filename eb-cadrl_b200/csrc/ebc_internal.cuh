@@ -21,6 +21,37 @@ struct ValueNet {
   ValueLayer att0_glob;  // global-state half of attention.0 (bias folded here)
 };
 
+// ---- tensor-core (tcgen05) value path, ebc_value_tc.cu -------------------------------------------
+enum { ST_L0A = 0, ST_L0B = 1, ST_L1A = 2, ST_L1B = 3, ST_L2 = 4, ST_L3 = 5, ST_L4 = 6, ST_L5 = 7, ST_COUNT = 8 };
+
+struct TcStage {         // one GEMM stage: acc[:, acc_col : acc_col + np] (+)= A[:, 0 : 16*ksteps] . W^T
+  int np;                // padded N (multiple of 16, <= 208)
+  int ksteps;            // K / 16
+  int acc_col;           // first TMEM column of the accumulator
+  int accumulate;        // add to the existing accumulator (second K chunk)
+  int n_lo;              // first output column of this stage within its layer (bias offset)
+};
+
+struct TcProgram {
+  TcStage st[ST_COUNT];
+  int n_wide;                    // 1 or 2 halves of the wide first layer
+  const uint8_t *wpack;          // packed bf16 weight slabs (device)
+  const uint32_t *slab_off, *slab_bytes;
+  int n_slabs;                   // slabs consumed per tile
+  const float *bias[6];          // padded fp32 biases (device)
+  const float *w6;               // last (N = 1) layer weights, padded
+  float b6;
+  const float *zero_bias;
+  const float *wg;               // global half of attention.0, fp32 [h1][a1p]
+  int with_global, h1d, h2d;
+};
+
+struct TcPrograms {
+  TcProgram entity, mlp3;
+  uint8_t *slab;                 // one device allocation
+  int ready;
+};
+
 struct ebc_sim {
   ebc_config cfg;
   ebc_state st;
@@ -31,6 +62,9 @@ struct ebc_sim {
   float *d_weights;      // one slab
   float *d_joint;        // [cap_states * (self_dim + H2)] scratch for mlp3
   int64_t joint_cap;
+  TcPrograms tc[2];      // [0] bf16 operands, [1] bf16x3 (fp32-accurate)
+  int value_mode;        // EBC_VALUE_*
+  int value_mode_forced; // set explicitly by ebc_set_value_mode
   int64_t launches;
   int sm_count;
   int max_smem_optin;
@@ -59,3 +93,9 @@ int ebc_value_prepare(ebc_sim *s, const ebc_weights *w);
 void ebc_value_release(ebc_sim *s);
 int ebc_launch_value(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row_count,
                      float *values, cudaStream_t st);
+
+// ebc_value_tc.cu
+int ebc_tc_prepare(ebc_sim *s, const ebc_weights *w, int mode_index, int nsplit);
+void ebc_tc_release(ebc_sim *s);
+int ebc_launch_value_tc(ebc_sim *s, int mode, const float *vin, int64_t n_states, const int32_t *row_count,
+                        float *values, cudaStream_t st);

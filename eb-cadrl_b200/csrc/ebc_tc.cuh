@@ -1,0 +1,155 @@
+// ebc_tc.cuh — sm_100a tensor-core building blocks for K4 (tcgen05 + TMEM + bulk async copies).
+//
+// Operand layout (both A = activations and B = weights): K-major, no swizzle, the canonical UMMA
+// "interleave" layout ((8,n),2):((1,SBO),LBO) in 16-byte units (cute/atom/mma_traits_sm100.hpp):
+//     byte_offset(row r, element k) = (k / 8) * (R * 16) + r * 16 + (k % 8) * 2        (bf16, R rows)
+// i.e. one 16-byte "k-chunk" of every row is contiguous, rows 16 B apart (a core matrix = 8 rows x 16 B
+// = 128 contiguous bytes), SBO = 128 B between 8-row groups, LBO = R*16 B between the two k-chunks that
+// one K=16 MMA consumes.  The epilogue writes this layout with conflict-free 16-byte stores (lane = row)
+// and the host pre-packs the weights into the same image so that a slab is one cp.async.bulk.
+//
+// fp32-accurate mode: every fp32 value v is split into three bf16 parts v1 + v2 + v3 (24 mantissa bits);
+// a product a*b is accumulated as the six MMAs a1b1 + a1b2 + a2b1 + a2b2 + a1b3 + a3b1 into one fp32 TMEM
+// accumulator (dropped terms are O(2^-24)).  Fast mode: one part, one MMA (bf16 operands).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tc {
+
+constexpr int TILE_M = 128;          // rows per CTA tile = TMEM lanes
+constexpr int A_CHUNK_BYTES = TILE_M * 16;   // one 8-element k-chunk of all 128 rows
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ---------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded: a protocol bug becomes a trapped launch (cudaErrorLaunchFailure), never a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// ---- async (bulk) copy global -> shared, completion on an mbarrier (UBLKCP) -----------------------
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// generic-proxy smem writes -> visible to the async proxy (UMMA operand reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- TMEM -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot_in_smem, uint32_t ncols) {   // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {          // whole warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 16 consecutive fp32 columns of this thread's TMEM lane (lane = 32 * (warp % 4) + laneid)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- UMMA -----------------------------------------------------------------------------------------
+// shared-memory matrix descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);          // start address, bits [0,14)
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;    // leading byte offset, bits [16,30)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;    // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                              // descriptor version (sm_100)
+  return d;                                            // base_offset 0, lbo_mode 0, layout SWIZZLE_NONE
+}
+// instruction descriptor for kind::f16, bf16 x bf16 -> fp32, A and B K-major (cute::UMMA::InstrDescriptor)
+__device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+// all previously issued MMAs of this thread done -> one arrival on `bar`
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- fp32 -> bf16 parts --------------------------------------------------------------------------
+template <int NSPLIT>
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16 (&p)[NSPLIT]) {
+  p[0] = __float2bfloat16_rn(v);
+  if (NSPLIT > 1) {
+    const float r1 = v - __bfloat162float(p[0]);
+    p[1] = __float2bfloat16_rn(r1);
+    if (NSPLIT > 2) p[2] = __float2bfloat16_rn(r1 - __bfloat162float(p[1]));
+  }
+}
+
+// Store 8 consecutive k-elements (k0 % 8 == 0) of row `row` into the NSPLIT A images.
+// a_base: shared memory, image s at a_base + s * image_bytes.
+template <int NSPLIT>
+__device__ __forceinline__ void store_a8(uint8_t *a_base, uint32_t image_bytes, int row, int k0, const float (&v)[8]) {
+  __nv_bfloat16 parts[8][NSPLIT];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split_bf16<NSPLIT>(v[i], parts[i]);
+#pragma unroll
+  for (int s = 0; s < NSPLIT; ++s) {
+    uint4 w;
+    uint32_t *pw = reinterpret_cast<uint32_t *>(&w);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint16_t lo = __bfloat16_as_ushort(parts[2 * i][s]), hi = __bfloat16_as_ushort(parts[2 * i + 1][s]);
+      pw[i] = (uint32_t)lo | ((uint32_t)hi << 16);
+    }
+    *reinterpret_cast<uint4 *>(a_base + (size_t)s * image_bytes + (size_t)(k0 >> 3) * A_CHUNK_BYTES + (size_t)row * 16) = w;
+  }
+}
+
+// (a part, b part) pairs accumulated per k-step, smallest magnitude first
+template <int NSPLIT> struct Terms;
+template <> struct Terms<1> { static constexpr int N = 1; __device__ static int a(int) { return 0; } __device__ static int b(int) { return 0; } };
+template <> struct Terms<3> {
+  static constexpr int N = 6;
+  __device__ static int a(int t) { const int v[6] = {2, 0, 1, 1, 0, 0}; return v[t]; }
+  __device__ static int b(int t) { const int v[6] = {0, 2, 1, 0, 1, 0}; return v[t]; }
+};
+
+}  // namespace tc

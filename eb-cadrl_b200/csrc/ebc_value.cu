@@ -398,14 +398,6 @@ int ebc_launch_value(ebc_sim *s, const float *vin, int64_t n_states, const int32
   const ValueNet &net = s->net;
   const int n = s->cfg.max_humans + s->cfg.max_statics;
   const int jd = net.self_dim + net.l[3].out;
-  if (n_states > s->joint_cap) {
-    // scratch grows monotonically; allocation is outside any timed steady state
-    if (s->d_joint) cudaFree(s->d_joint);
-    s->d_joint = nullptr;
-    cudaError_t err = cudaMalloc(&s->d_joint, (size_t)n_states * jd * sizeof(float));
-    if (err != cudaSuccess) return ebc_fail(s, EBC_ERR_NOMEM, "cudaMalloc joint scratch: %s", cudaGetErrorString(err));
-    s->joint_cap = n_states;
-  }
   EntityParams p;
   p.net = net;
   p.vin = vin; p.row_count = row_count;
@@ -443,7 +435,6 @@ int ebc_launch_value(ebc_sim *s, const float *vin, int64_t n_states, const int32
   const size_t smem_b = (size_t)off * sizeof(float);
   if (smem_a > (size_t)s->max_smem_optin || smem_b > (size_t)s->max_smem_optin)
     return ebc_fail(s, EBC_ERR_INVALID, "value network too wide for shared memory (%zu / %zu B needed)", smem_a, smem_b);
-  if (!row_count && !s->bound) return ebc_fail(s, EBC_ERR_UNBOUND, "ebc_value: state not bound");
   cudaFuncSetAttribute(value_entity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
   cudaFuncSetAttribute(value_mlp3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
   const long long tiles_a = (n_states + ts - 1) / ts;

@@ -1,0 +1,671 @@
+// ebc_value_tc.cu — K4 on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+// One CTA owns a tile of 128 entity rows (whole states) and walks the whole per-entity part of
+// rl/policy/sarl.py:38-82 with the activations never leaving the SM:
+//   X -> mlp1.0 -> mlp1.2 (= H1) -> { mlp2.0 -> mlp2.2 (= H2),  attention.0 (+ global half as a per-state
+//   bias) -> attention.2 -> attention.4 score } -> masked softmax -> pooled H2 -> joint[state]
+// and a second kernel runs mlp3 over tiles of 128 states.  Per GEMM stage: thread 0 streams the
+// pre-packed weight slabs L2 -> shared memory with cp.async.bulk (mbarrier full/empty ring) and issues
+// the tcgen05.mma's (A = activations in shared memory, canonical K-major layout written by the previous
+// epilogue; B = weight slab; D = fp32 accumulator in TMEM); tcgen05.commit signals the epilogue; the 128
+// threads (thread = row = TMEM lane) read the accumulator with tcgen05.ld, apply bias / ReLU, split the
+// fp32 value into bf16 parts and store the next stage's A operand.  See ebc_tc.cuh for the layout and
+// the fp32-accurate operand splitting.
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "ebc_internal.cuh"
+#include "ebc_tc.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int KMAX = 208;                       // widest A operand chunk kept in shared memory
+constexpr int MAX_TS = 16;                      // states per entity tile
+constexpr int TMEM_COLS = 512;
+
+template <int NSPLIT> struct Cfg {
+  static constexpr int STAGES = NSPLIT == 1 ? 6 : 2;
+  static constexpr uint32_t A_IMAGE = TILE_M * KMAX * 2;                 // bytes per split image of A
+  static constexpr uint32_t A_BYTES = NSPLIT * A_IMAGE;
+  static constexpr uint32_t STAGE_BYTES = NSPLIT * KMAX * 32;            // one k-step slab, all splits
+  static constexpr uint32_t W_BYTES = STAGES * STAGE_BYTES;
+};
+
+struct Smem {   // offsets (bytes) into dynamic shared memory, 128-byte aligned
+  uint32_t a, w, gv, g, sc, xs, bars, total;
+};
+
+template <int NSPLIT>
+__host__ __device__ inline Smem smem_layout() {
+  Smem s;
+  uint32_t off = 0;
+  s.a = off; off += Cfg<NSPLIT>::A_BYTES;
+  s.w = off; off += Cfg<NSPLIT>::W_BYTES;
+  s.gv = off; off += MAX_TS * KMAX * 4;
+  s.g = off; off += MAX_TS * KMAX * 4;
+  s.sc = off; off += TILE_M * 4 * 2;            // scores / softmax weights
+  s.xs = off; off += MAX_TS * 8 * 4;            // self-state part of each state's first row
+  s.bars = off; off += 256;
+  s.total = off;
+  return s;
+}
+
+// Ring of weight slabs + the single MMA-issuing thread's cursor.
+template <int NSPLIT>
+struct Pipe {
+  uint64_t *full, *empty, *acc_bar;
+  uint8_t *wbuf;
+  const uint8_t *wpack;      // packed weights (global)
+  const TcStage *stages;     // per-tile program (global)
+  int n_stage_slabs;         // slabs per tile
+  const uint32_t *slab_off;  // [n_stage_slabs] byte offset of each slab of the per-tile sequence
+  const uint32_t *slab_bytes;
+  long long loaded, consumed, total;   // running slab indices over all tiles of this CTA
+  uint32_t acc_phase;
+
+  __device__ void prefetch() {
+    constexpr int ST = Cfg<NSPLIT>::STAGES;
+    while (loaded < total && loaded < consumed + ST) {
+      const int st = (int)(loaded % ST);
+      const uint32_t ph = (uint32_t)((loaded / ST) & 1);
+      mbar_wait(&empty[st], ph ^ 1u);
+      const int i = (int)(loaded % n_stage_slabs);
+      mbar_arrive_expect_tx(&full[st], slab_bytes[i]);
+      bulk_g2s(wbuf + (size_t)st * Cfg<NSPLIT>::STAGE_BYTES, wpack + slab_off[i], slab_bytes[i], &full[st]);
+      ++loaded;
+    }
+  }
+
+  // thread 0: issue one GEMM stage.  a_smem = shared address of A image 0.
+  __device__ void mma_stage(const TcStage &S, uint32_t a_smem, uint32_t tmem_base) {
+    constexpr int ST = Cfg<NSPLIT>::STAGES;
+    const uint32_t idesc = make_idesc_bf16(TILE_M, S.np);
+    const uint32_t d = tmem_base + S.acc_col;
+    for (int ks = 0; ks < S.ksteps; ++ks) {
+      prefetch();
+      const int st = (int)(consumed % ST);
+      const uint32_t ph = (uint32_t)((consumed / ST) & 1);
+      mbar_wait(&full[st], ph);
+      tc_fence_after();
+      const uint32_t b_smem = smem_u32(wbuf + (size_t)st * Cfg<NSPLIT>::STAGE_BYTES);
+#pragma unroll
+      for (int t = 0; t < Terms<NSPLIT>::N; ++t) {
+        const uint64_t ad = make_smem_desc(a_smem + Terms<NSPLIT>::a(t) * Cfg<NSPLIT>::A_IMAGE + (uint32_t)ks * 2 * A_CHUNK_BYTES,
+                                           A_CHUNK_BYTES, 128);
+        const uint64_t bd = make_smem_desc(b_smem + Terms<NSPLIT>::b(t) * (uint32_t)S.np * 32, (uint32_t)S.np * 16, 128);
+        umma_bf16(d, ad, bd, idesc, S.accumulate || ks > 0 || t > 0);
+      }
+      umma_commit(&empty[st]);   // frees the slab when these MMAs have read it
+      ++consumed;
+    }
+  }
+  __device__ void commit_acc() { umma_commit(acc_bar); }
+  __device__ void wait_acc() {
+    mbar_wait(acc_bar, acc_phase);
+    acc_phase ^= 1u;
+    tc_fence_after();
+  }
+};
+
+// accumulator columns [col0, col0 + ncols) of this thread's row -> relu?(x + bias (+ gv)) -> A operand,
+// k index = k_dst0 + (c - col0).  ncols % 16 == 0.
+template <int NSPLIT>
+__device__ __forceinline__ void epi_to_a(uint32_t tmem_row, int col0, int ncols, const float *__restrict__ bias,
+                                         const float *gv_row, bool relu, uint8_t *a_base, int row, int k_dst0) {
+  for (int c = 0; c < ncols; c += 16) {
+    float v[16];
+    tmem_ld16(tmem_row + col0 + c, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float x = v[i] + __ldg(bias + c + i);
+      if (gv_row) x += gv_row[c + i];
+      v[i] = (relu && x < 0.0f) ? 0.0f : x;
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float u[8] = {v[8 * h], v[8 * h + 1], v[8 * h + 2], v[8 * h + 3], v[8 * h + 4], v[8 * h + 5], v[8 * h + 6], v[8 * h + 7]};
+      store_a8<NSPLIT>(a_base, Cfg<NSPLIT>::A_IMAGE, row, k_dst0 + c + 8 * h, u);
+    }
+  }
+}
+
+// score-style epilogue: sum_c relu(acc[c] + bias[c]) * w[c]
+__device__ __forceinline__ float epi_dot(uint32_t tmem_row, int col0, int ncols, const float *__restrict__ bias,
+                                         const float *__restrict__ w) {
+  float acc = 0.0f;
+  for (int c = 0; c < ncols; c += 16) {
+    float v[16];
+    tmem_ld16(tmem_row + col0 + c, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float x = v[i] + __ldg(bias + c + i);
+      acc = fmaf(x > 0.0f ? x : 0.0f, __ldg(w + c + i), acc);
+    }
+  }
+  return acc;
+}
+
+__device__ __forceinline__ void block_sync_after_smem_writes() {
+  fence_proxy_async();      // generic-proxy A-operand writes -> async proxy (UMMA)
+  tc_fence_before();        // order this thread's tcgen05.ld's before the barrier
+  __syncthreads();
+  tc_fence_after();
+}
+
+struct TcEntityParams {
+  TcProgram prog;
+  const float *vin;
+  const int32_t *row_count, *hum_count, *stat_count;
+  int n_actions;
+  long long n_states;
+  int n, ts, D;
+  float *joint;
+  int jd;          // self_dim + H2
+  int self_dim;
+};
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(TILE_M, 1) tc_entity_kernel(const TcEntityParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const Smem L = smem_layout<NSPLIT>();
+  uint8_t *A = smem + L.a;
+  float *GV = reinterpret_cast<float *>(smem + L.gv), *G = reinterpret_cast<float *>(smem + L.g);
+  float *SC = reinterpret_cast<float *>(smem + L.sc), *XS = reinterpret_cast<float *>(smem + L.xs);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
+  __shared__ uint32_t tmem_slot;
+  __shared__ int cnt[MAX_TS];
+  const TcProgram &P = p.prog;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr int ST = Cfg<NSPLIT>::STAGES;
+
+  Pipe<NSPLIT> pipe;
+  pipe.full = bars; pipe.empty = bars + ST; pipe.acc_bar = bars + 2 * ST;
+  pipe.wbuf = smem + L.w; pipe.wpack = P.wpack; pipe.stages = nullptr;
+  pipe.n_stage_slabs = P.n_slabs; pipe.slab_off = P.slab_off; pipe.slab_bytes = P.slab_bytes;
+  pipe.loaded = pipe.consumed = 0; pipe.acc_phase = 0;
+  const long long n_tiles = (p.n_states + p.ts - 1) / p.ts;
+  const long long my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  pipe.total = my_tiles * P.n_slabs;
+
+  if (tid == 0) {
+    for (int i = 0; i < ST; ++i) { mbar_init(&pipe.full[i], 1); mbar_init(&pipe.empty[i], 1); }
+    mbar_init(pipe.acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);   // this warp's lane quarter
+  const uint32_t a_smem = smem_u32(A);
+  const int n = p.n, ts = p.ts, D = p.D;
+
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long s0 = tile * ts;
+    const int ns = (int)min((long long)ts, p.n_states - s0);
+    const int rows = ns * n;
+    if (tid < MAX_TS) {
+      int c = 0;
+      if (tid < ns) {
+        if (p.row_count) c = p.row_count[s0 + tid];
+        else {
+          const long long e = (s0 + tid) / p.n_actions;
+          c = p.hum_count[e] + p.stat_count[e];
+        }
+        c = min(max(c, 0), n);
+      }
+      cnt[tid] = c;
+    }
+    // ---- X -> A (K padded to 32) ----------------------------------------------------------------
+    {
+      float x[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) x[k] = 0.0f;
+      if (tid < rows) {
+        const float *src = p.vin + ((size_t)s0 * n + tid) * D;
+        for (int k = 0; k < D; ++k) x[k] = __ldg(src + k);
+        if (tid % n == 0)
+          for (int k = 0; k < p.self_dim; ++k) XS[(tid / n) * 8 + k] = x[k];
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float u[8] = {x[8 * c], x[8 * c + 1], x[8 * c + 2], x[8 * c + 3], x[8 * c + 4], x[8 * c + 5], x[8 * c + 6], x[8 * c + 7]};
+        store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, tid, 8 * c, u);
+      }
+    }
+    block_sync_after_smem_writes();
+    // ---- mlp1.0 (wide: one or two N halves) ----------------------------------------------------------
+    if (tid == 0) {
+      for (int h = 0; h < P.n_wide; ++h) pipe.mma_stage(P.st[ST_L0A + h], a_smem, tmem_base);
+      pipe.commit_acc();
+    }
+    pipe.wait_acc();
+    // ---- mlp1.2, K chunked by the wide halves ------------------------------------------------------
+    for (int h = 0; h < P.n_wide; ++h) {
+      const TcStage &W = P.st[ST_L0A + h];
+      epi_to_a<NSPLIT>(tmem_row, W.acc_col, W.np, P.bias[0] + W.n_lo, nullptr, true, A, tid, 0);
+      block_sync_after_smem_writes();
+      if (tid == 0) { pipe.mma_stage(P.st[ST_L1A + h], a_smem, tmem_base); pipe.commit_acc(); }
+      pipe.wait_acc();
+    }
+    // ---- H1 -> A; mlp2.0 and attention.0 (local half) share it ---------------------------------------
+    {
+      const TcStage &S = P.st[ST_L1A];
+      epi_to_a<NSPLIT>(tmem_row, S.acc_col, S.np, P.bias[1], nullptr, true, A, tid, 0);
+    }
+    block_sync_after_smem_writes();
+    if (tid == 0) {
+      pipe.mma_stage(P.st[ST_L2], a_smem, tmem_base);
+      pipe.mma_stage(P.st[ST_L4], a_smem, tmem_base);
+      pipe.commit_acc();
+    }
+    // meanwhile: global state G = mean over the state's rows of H1 (read back from the A images),
+    // GV = attention.0.bias + W_att0[:, h1:] . G   (sarl.py:51-63)
+    const int h1d = P.h1d, a1p = P.st[ST_L4].np;
+    if (P.with_global) {
+      for (int i = tid; i < ts * h1d; i += TILE_M) {
+        const int s = i / h1d, k = i % h1d;
+        const int c = cnt[s];
+        float acc = 0.0f;
+        for (int r = 0; r < c; ++r) {
+          const size_t off = (size_t)(k >> 3) * A_CHUNK_BYTES + (size_t)(s * n + r) * 16 + (size_t)(k & 7) * 2;
+          float v = 0.0f;
+#pragma unroll
+          for (int sp = 0; sp < NSPLIT; ++sp)
+            v += __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(A + (size_t)sp * Cfg<NSPLIT>::A_IMAGE + off));
+          acc += v;
+        }
+        G[s * KMAX + k] = c > 0 ? acc / (float)c : 0.0f;
+      }
+      __syncthreads();
+      for (int i = tid; i < ts * a1p; i += TILE_M) {
+        const int s = i / a1p, c = i % a1p;
+        float acc = __ldg(P.bias[4] + c);
+        for (int k = 0; k < h1d; ++k) acc = fmaf(G[s * KMAX + k], __ldg(P.wg + (size_t)k * a1p + c), acc);
+        GV[s * KMAX + c] = acc;
+      }
+    } else {
+      for (int i = tid; i < ts * a1p; i += TILE_M) GV[(i / a1p) * KMAX + (i % a1p)] = __ldg(P.bias[4] + (i % a1p));
+    }
+    __syncthreads();
+    pipe.wait_acc();
+    // ---- T2 -> A; mlp2.2 ---------------------------------------------------------------------------
+    {
+      const TcStage &S = P.st[ST_L2];
+      epi_to_a<NSPLIT>(tmem_row, S.acc_col, S.np, P.bias[2], nullptr, true, A, tid, 0);
+    }
+    block_sync_after_smem_writes();
+    if (tid == 0) { pipe.mma_stage(P.st[ST_L3], a_smem, tmem_base); pipe.commit_acc(); }
+    pipe.wait_acc();
+    // ---- U = relu(att0 + GV[state]) -> A; attention.2 ----------------------------------------------------
+    {
+      const TcStage &S = P.st[ST_L4];
+      const int s = min(tid / n, ts - 1);
+      epi_to_a<NSPLIT>(tmem_row, S.acc_col, S.np, P.zero_bias, GV + s * KMAX, true, A, tid, 0);
+    }
+    block_sync_after_smem_writes();
+    if (tid == 0) { pipe.mma_stage(P.st[ST_L5], a_smem, tmem_base); pipe.commit_acc(); }
+    pipe.wait_acc();
+    // ---- attention.4 score, masked softmax, pooling (sarl.py:64-78) ----------------------------------------
+    {
+      const TcStage &S = P.st[ST_L5];
+      SC[tid] = epi_dot(tmem_row, S.acc_col, S.np, P.bias[5], P.w6) + P.b6;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < ts) {
+      const int c = cnt[tid];
+      float sum = 0.0f;
+      for (int r = 0; r < c; ++r) {
+        const float sc = SC[tid * n + r];
+        const float e = (sc != 0.0f) ? expf(sc) : 0.0f;
+        SC[TILE_M + tid * n + r] = e;
+        sum += e;
+      }
+      for (int r = 0; r < n; ++r) SC[TILE_M + tid * n + r] = (r < c) ? SC[TILE_M + tid * n + r] / sum : 0.0f;
+    }
+    __syncthreads();
+    // weighted H2 rows -> scratch (the A region is free: all MMAs that read it have completed)
+    float *PS = reinterpret_cast<float *>(A);
+    const int h2p = P.st[ST_L3].np, h2d = P.h2d;
+    {
+      const float wrow = (tid < ts * n) ? SC[TILE_M + tid] : 0.0f;
+      for (int c = 0; c < h2p; c += 16) {
+        float v[16];
+        tmem_ld16(tmem_row + P.st[ST_L3].acc_col + c, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c + i < h2d) PS[(c + i) * (TILE_M + 4) + tid] = (v[i] + __ldg(P.bias[3] + c + i)) * wrow;
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    for (int i = tid; i < ns * p.jd; i += TILE_M) {
+      const int s = i / p.jd, k = i % p.jd;
+      float v;
+      if (k < p.self_dim) v = XS[s * 8 + k];
+      else {
+        v = 0.0f;
+        const int c = cnt[s], col = k - p.self_dim;
+        for (int r = 0; r < c; ++r) v += PS[col * (TILE_M + 4) + s * n + r];
+      }
+      p.joint[(size_t)(s0 + s) * p.jd + k] = v;
+    }
+    __syncthreads();   // PS / SC / XS / cnt are rewritten by the next tile
+    tc_fence_after();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+struct TcMlp3Params {
+  TcProgram prog;
+  const float *joint;
+  float *values;
+  long long n_states;
+  int jd;
+};
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(TILE_M, 1) tc_mlp3_kernel(const TcMlp3Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const Smem L = smem_layout<NSPLIT>();
+  uint8_t *A = smem + L.a;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
+  __shared__ uint32_t tmem_slot;
+  const TcProgram &P = p.prog;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr int ST = Cfg<NSPLIT>::STAGES;
+  Pipe<NSPLIT> pipe;
+  pipe.full = bars; pipe.empty = bars + ST; pipe.acc_bar = bars + 2 * ST;
+  pipe.wbuf = smem + L.w; pipe.wpack = P.wpack; pipe.stages = nullptr;
+  pipe.n_stage_slabs = P.n_slabs; pipe.slab_off = P.slab_off; pipe.slab_bytes = P.slab_bytes;
+  pipe.loaded = pipe.consumed = 0; pipe.acc_phase = 0;
+  const long long n_tiles = (p.n_states + TILE_M - 1) / TILE_M;
+  const long long my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  pipe.total = my_tiles * P.n_slabs;
+  if (tid == 0) {
+    for (int i = 0; i < ST; ++i) { mbar_init(&pipe.full[i], 1); mbar_init(&pipe.empty[i], 1); }
+    mbar_init(pipe.acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t a_smem = smem_u32(A);
+  const int jd = p.jd, kp = P.st[ST_L0A].ksteps * 16;
+
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long s0 = tile * TILE_M;
+    const bool live = s0 + tid < p.n_states;
+    // joint row -> A (K padded to a multiple of 16)
+    for (int k0 = 0; k0 < kp; k0 += 8) {
+      float u[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) u[j] = (live && k0 + j < jd) ? __ldg(p.joint + (size_t)(s0 + tid) * jd + k0 + j) : 0.0f;
+      store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, tid, k0, u);
+    }
+    block_sync_after_smem_writes();
+    if (tid == 0) {
+      for (int h = 0; h < P.n_wide; ++h) pipe.mma_stage(P.st[ST_L0A + h], a_smem, tmem_base);
+      pipe.commit_acc();
+    }
+    pipe.wait_acc();
+    for (int h = 0; h < P.n_wide; ++h) {
+      const TcStage &W = P.st[ST_L0A + h];
+      epi_to_a<NSPLIT>(tmem_row, W.acc_col, W.np, P.bias[0] + W.n_lo, nullptr, true, A, tid, 0);
+      block_sync_after_smem_writes();
+      if (tid == 0) { pipe.mma_stage(P.st[ST_L1A + h], a_smem, tmem_base); pipe.commit_acc(); }
+      pipe.wait_acc();
+    }
+    {
+      const TcStage &S = P.st[ST_L1A];
+      epi_to_a<NSPLIT>(tmem_row, S.acc_col, S.np, P.bias[1], nullptr, true, A, tid, 0);
+    }
+    block_sync_after_smem_writes();
+    if (tid == 0) { pipe.mma_stage(P.st[ST_L2], a_smem, tmem_base); pipe.commit_acc(); }
+    pipe.wait_acc();
+    {
+      const TcStage &S = P.st[ST_L2];
+      const float v = epi_dot(tmem_row, S.acc_col, S.np, P.bias[2], P.w6) + P.b6;
+      if (live) p.values[s0 + tid] = v;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Host: pack weights into slab images and build the two per-tile programs.
+// ---------------------------------------------------------------------------------------------------
+inline int pad16(int x) { return (x + 15) / 16 * 16; }
+
+struct Packer {
+  int nsplit;
+  std::vector<uint8_t> bytes;
+  std::vector<uint32_t> slab_off, slab_bytes;
+
+  static uint16_t bf16_rn(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);
+    const uint32_t r = 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)((u + r) >> 16);
+  }
+  static float bf16_to_f(uint16_t h) {
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+  }
+  // GEMM stage over W[n_lo:n_lo+np (zero past n_hi)][k_lo:k_lo+16*ksteps (zero past k_hi)], W is [out][ld]
+  void add_stage(const float *W, int ld, int n_lo, int n_hi, int np, int k_lo, int k_hi, int ksteps, int k_col_off) {
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const uint32_t off = (uint32_t)bytes.size();
+      const uint32_t sz = (uint32_t)nsplit * (uint32_t)np * 32u;
+      bytes.resize(off + sz, 0);
+      for (int c = 0; c < 2; ++c)
+        for (int nn = 0; nn < np; ++nn)
+          for (int j = 0; j < 8; ++j) {
+            const int n = n_lo + nn, k = k_lo + ks * 16 + c * 8 + j;
+            float v = (n < n_hi && k < k_hi) ? W[(size_t)n * ld + k_col_off + k] : 0.0f;
+            for (int s = 0; s < nsplit; ++s) {
+              const uint16_t h = bf16_rn(v);
+              v -= bf16_to_f(h);
+              uint8_t *dst = bytes.data() + off + (size_t)s * np * 32 + (size_t)c * np * 16 + (size_t)nn * 16 + j * 2;
+              memcpy(dst, &h, 2);
+            }
+          }
+      slab_off.push_back(off);
+      slab_bytes.push_back(sz);
+    }
+  }
+};
+
+template <int NSPLIT>
+int launch_tc(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row_count, float *values, cudaStream_t stream) {
+  const Smem L = smem_layout<NSPLIT>();
+  if ((int)L.total + 1024 > s->max_smem_optin) return ebc_fail(s, EBC_ERR_INVALID, "tensor-core value path needs %u B of shared memory", L.total);
+  const int n = s->cfg.max_humans + s->cfg.max_statics;
+  TcEntityParams p;
+  p.prog = s->tc[NSPLIT == 1 ? 0 : 1].entity;
+  p.vin = vin; p.row_count = row_count; p.hum_count = s->st.hum_count; p.stat_count = s->st.stat_count;
+  p.n_actions = s->cfg.n_actions; p.n_states = n_states; p.n = n; p.D = s->net.D;
+  int ts = TILE_M / n;
+  if (ts < 1) ts = 1;
+  if (ts > MAX_TS) ts = MAX_TS;
+  p.ts = ts;
+  p.joint = s->d_joint; p.jd = s->net.self_dim + s->net.l[3].out; p.self_dim = s->net.self_dim;
+  TcMlp3Params q;
+  q.prog = s->tc[NSPLIT == 1 ? 0 : 1].mlp3;
+  q.joint = s->d_joint; q.values = values; q.n_states = n_states; q.jd = p.jd;
+  cudaFuncSetAttribute(tc_entity_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+  cudaFuncSetAttribute(tc_mlp3_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+  const long long tiles_a = (n_states + ts - 1) / ts, tiles_b = (n_states + TILE_M - 1) / TILE_M;
+  const int grid_a = (int)(tiles_a < s->sm_count ? tiles_a : s->sm_count);
+  const int grid_b = (int)(tiles_b < s->sm_count ? tiles_b : s->sm_count);
+  tc_entity_kernel<NSPLIT><<<grid_a, TILE_M, L.total, stream>>>(p);
+  int rc = ebc_check_launch(s, "tc_entity_kernel");
+  if (rc) return rc;
+  tc_mlp3_kernel<NSPLIT><<<grid_b, TILE_M, L.total, stream>>>(q);
+  return ebc_check_launch(s, "tc_mlp3_kernel");
+}
+
+}  // namespace
+
+// Build both programs (entity part, mlp3) for one operand-splitting mode.  Returns 0 if the network's
+// shape fits the tensor-core path, 1 if it does not (caller keeps the FFMA path), < 0 on error.
+int ebc_tc_prepare(ebc_sim *s, const ebc_weights *w, int mode_index, int nsplit) {
+  const ebc_linear *m10 = &w->mlp1[0], *m12 = &w->mlp1[1], *m20 = &w->mlp2[0], *m22 = &w->mlp2[1];
+  const ebc_linear *a0 = &w->attention[0], *a2 = &w->attention[1], *a4 = &w->attention[2];
+  const ebc_linear *p0 = &w->mlp3[0], *p2 = &w->mlp3[1], *p4 = &w->mlp3[2], *p6 = &w->mlp3[3];
+  const int h1 = m12->out_dim;
+  auto fits = [&](int wide_out, int mid, int last_in) {
+    return pad16(wide_out) <= 2 * KMAX && pad16(mid) <= KMAX && pad16(last_in) <= KMAX;
+  };
+  if (!fits(m10->out_dim, h1, h1) || pad16(m20->out_dim) > KMAX || pad16(m22->out_dim) > KMAX ||
+      pad16(a0->out_dim) > KMAX || pad16(a2->out_dim) > KMAX || m10->in_dim > 32 ||
+      !fits(p0->out_dim, p2->out_dim, p4->out_dim) || pad16(p0->in_dim) > KMAX ||
+      (size_t)m22->out_dim * (TILE_M + 4) * 4 > (size_t)TILE_M * KMAX * 2 /* pooling scratch aliases one A image */ ||
+      w->self_state_dim > 8)
+    return 1;
+  TcPrograms &T = s->tc[mode_index];
+  std::vector<float> fl;   // biases, w6, wg (fp32 side data)
+  auto push_f = [&](const float *src, int nreal, int npad) {
+    const size_t off = fl.size();
+    fl.resize(off + npad, 0.0f);
+    for (int i = 0; i < nreal; ++i) fl[off + i] = src[i];
+    return off;
+  };
+  auto wide_split = [&](int out, int &np0, int &np1) {
+    const int op = pad16(out);
+    if (op <= KMAX) { np0 = op; np1 = 0; }
+    else { np0 = pad16((op / 2 + 15) / 16 * 16); if (np0 > KMAX) np0 = KMAX; np1 = op - np0; }
+  };
+  // ---- a chain  IN -> wide (ReLU) -> mid (ReLU) -> ...  shared by both kernels -----------------------------
+  auto build_front = [&](Packer &pk, TcProgram &P, const ebc_linear *wide, const ebc_linear *mid, int in_pad,
+                         size_t &b_wide, size_t &b_mid) {
+    int np0, np1;
+    wide_split(wide->out_dim, np0, np1);
+    P.n_wide = np1 ? 2 : 1;
+    const int midp = pad16(mid->out_dim);
+    const int col_mid = TMEM_COLS - midp;
+    if (np0 + np1 > col_mid) return 1;
+    int lo = 0;
+    for (int h = 0; h < P.n_wide; ++h) {
+      const int np = h ? np1 : np0;
+      TcStage &S = P.st[ST_L0A + h];
+      S.np = np; S.ksteps = in_pad / 16; S.acc_col = lo; S.accumulate = 0; S.n_lo = lo;
+      pk.add_stage(wide->weight, wide->in_dim, lo, wide->out_dim, np, 0, wide->in_dim, S.ksteps, 0);
+      lo += np;
+    }
+    lo = 0;
+    for (int h = 0; h < P.n_wide; ++h) {
+      const int kp = h ? np1 : np0;
+      TcStage &S = P.st[ST_L1A + h];
+      S.np = midp; S.ksteps = kp / 16; S.acc_col = col_mid; S.accumulate = h; S.n_lo = 0;
+      pk.add_stage(mid->weight, mid->in_dim, 0, mid->out_dim, midp, lo, mid->in_dim, S.ksteps, 0);
+      lo += kp;
+    }
+    b_wide = push_f(wide->bias, wide->out_dim, np0 + np1);
+    b_mid = push_f(mid->bias, mid->out_dim, midp);
+    return 0;
+  };
+  auto simple_stage = [&](Packer &pk, TcStage &S, const ebc_linear *l, int in_real, int in_pad, int acc_col, int k_col_off) {
+    S.np = pad16(l->out_dim); S.ksteps = in_pad / 16; S.acc_col = acc_col; S.accumulate = 0; S.n_lo = 0;
+    pk.add_stage(l->weight, l->in_dim, 0, l->out_dim, S.np, 0, in_real, S.ksteps, k_col_off);
+  };
+
+  Packer pe; pe.nsplit = nsplit;
+  Packer pm; pm.nsplit = nsplit;
+  TcProgram E, M;
+  memset(&E, 0, sizeof(E));
+  memset(&M, 0, sizeof(M));
+  size_t be0, be1, bm0, bm1;
+  if (build_front(pe, E, m10, m12, 32, be0, be1)) return 1;
+  const int h1p = pad16(h1);
+  simple_stage(pe, E.st[ST_L2], m20, h1, h1p, 0, 0);                               // mlp2.0
+  simple_stage(pe, E.st[ST_L4], a0, h1, h1p, E.st[ST_L2].np, 0);                   // attention.0, local half
+  simple_stage(pe, E.st[ST_L3], m22, m20->out_dim, pad16(m20->out_dim), 0, 0);     // mlp2.2
+  simple_stage(pe, E.st[ST_L5], a2, a0->out_dim, pad16(a0->out_dim), E.st[ST_L4].acc_col, 0);   // attention.2
+  if (E.st[ST_L2].np + E.st[ST_L4].np > TMEM_COLS) return 1;
+  const size_t be2 = push_f(m20->bias, m20->out_dim, E.st[ST_L2].np);
+  const size_t be3 = push_f(m22->bias, m22->out_dim, E.st[ST_L3].np);
+  const size_t be4 = push_f(a0->bias, a0->out_dim, E.st[ST_L4].np);
+  const size_t be5 = push_f(a2->bias, a2->out_dim, E.st[ST_L5].np);
+  const size_t we6 = push_f(a4->weight, a4->in_dim, E.st[ST_L5].np);
+  const size_t zero = push_f(nullptr, 0, KMAX);
+  // global half of attention.0, fp32, [k][a1p]
+  const int a1p = E.st[ST_L4].np;
+  const size_t wg = fl.size();
+  if (w->with_global_state) {
+    fl.resize(wg + (size_t)h1 * a1p, 0.0f);
+    for (int c = 0; c < a0->out_dim; ++c)
+      for (int k = 0; k < h1; ++k) fl[wg + (size_t)k * a1p + c] = a0->weight[(size_t)c * a0->in_dim + h1 + k];
+  }
+  if (build_front(pm, M, p0, p2, pad16(p0->in_dim), bm0, bm1)) return 1;
+  simple_stage(pm, M.st[ST_L2], p4, p2->out_dim, pad16(p2->out_dim), 0, 0);        // mlp3.4
+  const size_t bm2 = push_f(p4->bias, p4->out_dim, M.st[ST_L2].np);
+  const size_t wm6 = push_f(p6->weight, p6->in_dim, M.st[ST_L2].np);
+
+  // ---- upload ---------------------------------------------------------------------------------------
+  const size_t n_e = pe.slab_off.size(), n_m = pm.slab_off.size();
+  const size_t bytes_total = pe.bytes.size() + pm.bytes.size() + fl.size() * 4 + (n_e + n_m) * 8 + 1024;
+  uint8_t *d = nullptr;
+  cudaError_t err = cudaMalloc(&d, bytes_total);
+  if (err != cudaSuccess) return ebc_fail(s, EBC_ERR_NOMEM, "cudaMalloc tc weights: %s", cudaGetErrorString(err));
+  size_t off = 0;
+  auto up = [&](const void *src, size_t nbytes) {
+    const size_t o = off;
+    if (nbytes) cudaMemcpy(d + o, src, nbytes, cudaMemcpyHostToDevice);
+    off += (nbytes + 127) / 128 * 128;
+    return o;
+  };
+  const size_t o_pe = up(pe.bytes.data(), pe.bytes.size());
+  const size_t o_pm = up(pm.bytes.data(), pm.bytes.size());
+  const size_t o_fl = up(fl.data(), fl.size() * 4);
+  const size_t o_eo = up(pe.slab_off.data(), n_e * 4), o_eb = up(pe.slab_bytes.data(), n_e * 4);
+  const size_t o_mo = up(pm.slab_off.data(), n_m * 4), o_mb = up(pm.slab_bytes.data(), n_m * 4);
+  if (cudaGetLastError() != cudaSuccess) { cudaFree(d); return ebc_fail(s, EBC_ERR_CUDA, "tc weight upload failed"); }
+  const float *dfl = reinterpret_cast<const float *>(d + o_fl);
+  E.wpack = d + o_pe; E.n_slabs = (int)n_e;
+  E.slab_off = reinterpret_cast<const uint32_t *>(d + o_eo); E.slab_bytes = reinterpret_cast<const uint32_t *>(d + o_eb);
+  E.bias[0] = dfl + be0; E.bias[1] = dfl + be1; E.bias[2] = dfl + be2; E.bias[3] = dfl + be3;
+  E.bias[4] = dfl + be4; E.bias[5] = dfl + be5; E.w6 = dfl + we6; E.b6 = a4->bias[0]; E.zero_bias = dfl + zero;
+  E.wg = dfl + wg; E.with_global = w->with_global_state ? 1 : 0; E.h1d = h1; E.h2d = m22->out_dim;
+  M.wpack = d + o_pm; M.n_slabs = (int)n_m;
+  M.slab_off = reinterpret_cast<const uint32_t *>(d + o_mo); M.slab_bytes = reinterpret_cast<const uint32_t *>(d + o_mb);
+  M.bias[0] = dfl + bm0; M.bias[1] = dfl + bm1; M.bias[2] = dfl + bm2; M.w6 = dfl + wm6; M.b6 = p6->bias[0];
+  M.zero_bias = dfl + zero;
+  if (T.slab) cudaFree(T.slab);
+  T.slab = d;
+  T.entity = E;
+  T.mlp3 = M;
+  T.ready = 1;
+  return 0;
+}
+
+void ebc_tc_release(ebc_sim *s) {
+  for (int i = 0; i < 2; ++i) {
+    if (s->tc[i].slab) cudaFree(s->tc[i].slab);
+    s->tc[i].slab = nullptr;
+    s->tc[i].ready = 0;
+  }
+}
+
+int ebc_launch_value_tc(ebc_sim *s, int mode, const float *vin, int64_t n_states, const int32_t *row_count,
+                        float *values, cudaStream_t stream) {
+  if (mode == EBC_VALUE_TC_BF16) return launch_tc<1>(s, vin, n_states, row_count, values, stream);
+  return launch_tc<3>(s, vin, n_states, row_count, values, stream);
+}

@@ -15,6 +15,7 @@ EV_NOTHING, EV_DANGER, EV_REACH_GOAL, EV_COLLISION_ADULT, EV_COLLISION_BICYCLE, 
     EV_COLLISION_CHILD, EV_COLLISION_OBSTACLE, EV_TIMEOUT = range(8)
 
 KIN_HOLONOMIC, KIN_UNICYCLE = 0, 1
+VALUE_FP32, VALUE_TC_FP32, VALUE_TC_BF16 = 0, 1, 2
 POLICY_ORCA, POLICY_LINEAR = 0, 1
 
 c_i32, c_f64, c_f32 = ctypes.c_int32, ctypes.c_double, ctypes.c_float
@@ -65,6 +66,8 @@ PROTOTYPES = {
     "ebc_bind": (c_i32, [SIM, ctypes.POINTER(EbcState)]),
     "ebc_set_actions": (c_i32, [SIM, vp, c_i32]),
     "ebc_set_weights": (c_i32, [SIM, ctypes.POINTER(EbcWeights)]),
+    "ebc_set_value_mode": (c_i32, [SIM, c_i32]),
+    "ebc_get_value_mode": (c_i32, [SIM]),
     "ebc_orca": (c_i32, [SIM, vp]),
     "ebc_robot_orca": (c_i32, [SIM, c_f64, vp, vp]),
     "ebc_lookahead": (c_i32, [SIM, vp, vp, vp, vp, vp]),

@@ -163,6 +163,17 @@ int ebc_set_actions(ebc_sim *sim, const double *actions, int32_t n_actions);
 
 int ebc_set_weights(ebc_sim *sim, const ebc_weights *w);
 
+/* Arithmetic of K4 (the value network).  All three are this library's own kernels.
+ *   EBC_VALUE_FP32     fp32 FFMA (CUDA cores): the round-1 parity path
+ *   EBC_VALUE_TC_FP32  tcgen05 tensor cores, every fp32 operand split into three bf16 parts and
+ *                      six MMAs per product: fp32-accurate (what argmax parity needs), DEFAULT when
+ *                      the network's shape fits the tensor-core tiling
+ *   EBC_VALUE_TC_BF16  tcgen05, plain bf16 operands, fp32 accumulation: fast mode, NOT argmax-exact
+ *                      (rl/policy/sarl.py:38-82 evaluated with bf16 inputs; agreement rate is reported) */
+enum { EBC_VALUE_FP32 = 0, EBC_VALUE_TC_FP32 = 1, EBC_VALUE_TC_BF16 = 2 };
+int ebc_set_value_mode(ebc_sim *sim, int32_t mode);
+int ebc_get_value_mode(const ebc_sim *sim);
+
 /* ---- the hot path ---------------------------------------------------------------- */
 
 /* K1. Human policy step: state.hum_nv[e,h] <- policy_h(current state).

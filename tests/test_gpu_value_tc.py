@@ -1,0 +1,97 @@
+"""K4 on the tensor cores (tcgen05): fp32-accurate mode and bf16 fast mode against a torch fp64
+restatement of rl/policy/sarl.py:38-82 and against the FFMA path.  Needs a B200."""
+import numpy as np
+import pytest
+import torch
+
+import oracle_backend as ob
+from ebc.config import SimConfig
+from ebc.engine import BatchedSim
+
+pytestmark = pytest.mark.gpu
+
+
+def torch_value(w, x, cnt):
+    """fp64 reference of the value network with ragged row counts."""
+    W = {k: torch.as_tensor(v, device=x.device, dtype=torch.float64) for k, v in w.items()}
+    n = x.shape[1]
+
+    def lin(t, k, relu):
+        y = t @ W[k + ".weight"].T + W[k + ".bias"]
+        return torch.relu(y) if relu else y
+
+    xd = x.double()
+    h1 = lin(lin(xd, "mlp1.0", True), "mlp1.2", True)
+    h2 = lin(lin(h1, "mlp2.0", True), "mlp2.2", False)
+    mask = (torch.arange(n, device=x.device)[None] < cnt[:, None]).double()
+    g = (h1 * mask[..., None]).sum(1, keepdim=True) / cnt[:, None, None].double()
+    a = lin(lin(lin(torch.cat([h1, g.expand(-1, n, -1)], 2), "attention.0", True), "attention.2", True),
+            "attention.4", False)[..., 0]
+    e = torch.exp(a) * (a != 0) * mask
+    wts = e / e.sum(1, keepdim=True)
+    f = (wts[..., None] * h2).sum(1)
+    j = torch.cat([xd[:, 0, :6], f], 1)
+    return lin(lin(lin(lin(j, "mlp3.0", True), "mlp3.2", True), "mlp3.4", True), "mlp3.6", False)[:, 0]
+
+
+def make_inputs(n_states, n, D, seed, ragged=True):
+    rng = np.random.default_rng(seed)
+    x = rng.normal(0, 1, (n_states, n, D)).astype(np.float32)
+    cnt = rng.integers(1, n + 1, n_states).astype(np.int32) if ragged else np.full(n_states, n, np.int32)
+    for i in range(n_states):
+        x[i, cnt[i]:] = 0
+    return torch.as_tensor(x, device="cuda:0"), torch.as_tensor(cnt, device="cuda:0")
+
+
+@pytest.mark.parametrize("weights,H,S,typed", [("weights_ebcadrl.npz", 10, 6, True),
+                                                ("weights_sarl_baseline.npz", 5, 0, False),
+                                                ("weights_ebcadrl.npz", 24, 6, True)])
+@pytest.mark.parametrize("n_states", [37, 3000])
+def test_tc_modes_vs_fp64(weights, H, S, typed, n_states):
+    w = ob.load_weights(weights)
+    cfg = SimConfig()
+    cfg.with_agent_type = typed
+    sim = BatchedSim(cfg, 1, H, S, 0, 81, device="cuda:0")
+    sim.set_weights(w)
+    assert sim.value_mode() == "tc_fp32"          # default when the network fits the tiling
+    x, cnt = make_inputs(n_states, H + S, cfg.D, seed=n_states + H)
+    ref = torch_value(w, x, cnt)
+    scale = max(1.0, ref.abs().max().item())
+    out = {}
+    for mode in ("fp32", "tc_fp32", "tc_bf16"):
+        sim.set_value_mode(mode)
+        out[mode] = sim.value(x, cnt).double()
+        torch.cuda.synchronize()
+    err = {m: (v - ref).abs().max().item() for m, v in out.items()}
+    print(weights, H + S, n_states, err)
+    assert err["fp32"] < 1e-4 * scale
+    assert err["tc_fp32"] < 2e-5 * scale, err     # fp32-accurate: as good as (or better than) FFMA
+    assert err["tc_bf16"] < 0.1 * scale, err      # bf16 operands: percent-level
+    assert err["tc_bf16"] > err["tc_fp32"]
+
+
+def test_tc_matches_golden_argmax(oracle):
+    """End to end on a reference trace: tensor-core fp32-accurate values keep the reference's argmax."""
+    name = "trace_cfg2_h10_seed7"
+    tr = ob.Trace(name)
+    H, S, R = tr.dims()
+    N = tr.n_steps
+    g = BatchedSim(tr.sim_config(), N, H, S, R, 81, device="cuda:0")
+    g.set_actions(tr.z["actions"])
+    g.set_weights(ob.load_weights(ob.TRACE_WEIGHTS[name]))
+    for t in range(N):
+        tr.load_into(g, t, episode=t)
+    res = {}
+    for mode in ("tc_fp32", "tc_bf16"):
+        g.set_value_mode(mode)
+        g.decide()
+        torch.cuda.synchronize()
+        has = [t for t in range(N) if tr.has(t, "la_value")]
+        ref_val = np.stack([tr.get(t, "la_value") for t in has])
+        dv = np.abs(g.values.cpu().numpy()[has] - ref_val).max()
+        flips = sum(int(g.argmax[t]) != tr.steps[t]["argmax"] for t in has)
+        big = sum(int(g.argmax[t]) != tr.steps[t]["argmax"] and tr.steps[t]["top2_gap"] >= 5e-4 for t in has)
+        res[mode] = (dv, flips, big, len(has))
+    print(res)
+    assert res["tc_fp32"][0] < 2e-4 and res["tc_fp32"][2] == 0 and res["tc_fp32"][1] <= 2
+    assert res["tc_bf16"][0] < 0.1
