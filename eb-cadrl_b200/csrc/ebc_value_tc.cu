@@ -1,16 +1,16 @@
 // ebc_value_tc.cu — K4 on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
 //
-// One CTA owns a tile of 128 entity rows (whole states) and walks the whole per-entity part of
-// rl/policy/sarl.py:38-82 with the activations never leaving the SM:
+// One CTA (512 threads) owns a tile of 128 entity rows (whole states) and walks the whole per-entity
+// part of rl/policy/sarl.py:38-82 with the activations never leaving the SM:
 //   X -> mlp1.0 -> mlp1.2 (= H1) -> { mlp2.0 -> mlp2.2 (= H2),  attention.0 (+ global half as a per-state
 //   bias) -> attention.2 -> attention.4 score } -> masked softmax -> pooled H2 -> joint[state]
 // and a second kernel runs mlp3 over tiles of 128 states.  Per GEMM stage: thread 0 streams the
 // pre-packed weight slabs L2 -> shared memory with cp.async.bulk (mbarrier full/empty ring) and issues
 // the tcgen05.mma's (A = activations in shared memory, canonical K-major layout written by the previous
-// epilogue; B = weight slab; D = fp32 accumulator in TMEM); tcgen05.commit signals the epilogue; the 128
-// threads (thread = row = TMEM lane) read the accumulator with tcgen05.ld, apply bias / ReLU, split the
-// fp32 value into bf16 parts and store the next stage's A operand.  See ebc_tc.cuh for the layout and
-// the fp32-accurate operand splitting.
+// epilogue; B = weight slab; D = fp32 accumulator in TMEM); tcgen05.commit signals the epilogue.  In the
+// epilogue warp w reads TMEM lane quarter (w % 4) (row = lane) and the 16-column blocks b with
+// b % 4 == w / 4, applies bias / ReLU, splits the fp32 value into bf16 parts and stores the next
+// stage's A operand.  See ebc_tc.cuh for the layout and the fp32-accurate operand splitting.
 #include <stdio.h>
 #include <string.h>
 
@@ -23,9 +23,12 @@ namespace {
 
 using namespace tc;
 
+constexpr int NT = 512;                         // threads per CTA: 4 lane quarters x 4 column groups
+constexpr int NCG = NT / TILE_M;                // column groups
 constexpr int KMAX = 208;                       // widest A operand chunk kept in shared memory
 constexpr int MAX_TS = 16;                      // states per entity tile
 constexpr int TMEM_COLS = 512;
+constexpr int PS_LD = TILE_M + 4;
 
 template <int NSPLIT> struct Cfg {
   static constexpr int STAGES = NSPLIT == 1 ? 6 : 2;
@@ -35,7 +38,7 @@ template <int NSPLIT> struct Cfg {
   static constexpr uint32_t W_BYTES = STAGES * STAGE_BYTES;
 };
 
-struct Smem {   // offsets (bytes) into dynamic shared memory, 128-byte aligned
+struct Smem {   // offsets (bytes) into dynamic shared memory
   uint32_t a, w, gv, g, sc, xs, bars, total;
 };
 
@@ -45,9 +48,9 @@ __host__ __device__ inline Smem smem_layout() {
   uint32_t off = 0;
   s.a = off; off += Cfg<NSPLIT>::A_BYTES;
   s.w = off; off += Cfg<NSPLIT>::W_BYTES;
-  s.gv = off; off += MAX_TS * KMAX * 4;
-  s.g = off; off += MAX_TS * KMAX * 4;
-  s.sc = off; off += TILE_M * 4 * 2;            // scores / softmax weights
+  s.gv = off; off += MAX_TS * KMAX * 4;         // GV[state][col]
+  s.g = off; off += KMAX * MAX_TS * 4;          // G[k][state]
+  s.sc = off; off += TILE_M * 4 * (NCG + 1);    // partial scores per column group, then softmax weights
   s.xs = off; off += MAX_TS * 8 * 4;            // self-state part of each state's first row
   s.bars = off; off += 256;
   s.total = off;
@@ -60,7 +63,6 @@ struct Pipe {
   uint64_t *full, *empty, *acc_bar;
   uint8_t *wbuf;
   const uint8_t *wpack;      // packed weights (global)
-  const TcStage *stages;     // per-tile program (global)
   int n_stage_slabs;         // slabs per tile
   const uint32_t *slab_off;  // [n_stage_slabs] byte offset of each slab of the per-tile sequence
   const uint32_t *slab_bytes;
@@ -74,8 +76,9 @@ struct Pipe {
       const uint32_t ph = (uint32_t)((loaded / ST) & 1);
       mbar_wait(&empty[st], ph ^ 1u);
       const int i = (int)(loaded % n_stage_slabs);
-      mbar_arrive_expect_tx(&full[st], slab_bytes[i]);
-      bulk_g2s(wbuf + (size_t)st * Cfg<NSPLIT>::STAGE_BYTES, wpack + slab_off[i], slab_bytes[i], &full[st]);
+      const uint32_t bytes = __ldg(slab_bytes + i);
+      mbar_arrive_expect_tx(&full[st], bytes);
+      bulk_g2s(wbuf + (size_t)st * Cfg<NSPLIT>::STAGE_BYTES, wpack + __ldg(slab_off + i), bytes, &full[st]);
       ++loaded;
     }
   }
@@ -102,6 +105,7 @@ struct Pipe {
       umma_commit(&empty[st]);   // frees the slab when these MMAs have read it
       ++consumed;
     }
+    prefetch();                  // keep the ring full across the epilogue that follows
   }
   __device__ void commit_acc() { umma_commit(acc_bar); }
   __device__ void wait_acc() {
@@ -111,12 +115,12 @@ struct Pipe {
   }
 };
 
-// accumulator columns [col0, col0 + ncols) of this thread's row -> relu?(x + bias (+ gv)) -> A operand,
-// k index = k_dst0 + (c - col0).  ncols % 16 == 0.
+// accumulator columns [col0, col0 + ncols) of this thread's row, this thread's column group
+// -> relu?(x + bias (+ gv)) -> A operand, k index = (c - col0).  ncols % 16 == 0.
 template <int NSPLIT>
-__device__ __forceinline__ void epi_to_a(uint32_t tmem_row, int col0, int ncols, const float *__restrict__ bias,
-                                         const float *gv_row, bool relu, uint8_t *a_base, int row, int k_dst0) {
-  for (int c = 0; c < ncols; c += 16) {
+__device__ __forceinline__ void epi_to_a(uint32_t tmem_row, int cg, int col0, int ncols, const float *__restrict__ bias,
+                                         const float *gv_row, bool relu, uint8_t *a_base, int row) {
+  for (int c = 16 * cg; c < ncols; c += 16 * NCG) {
     float v[16];
     tmem_ld16(tmem_row + col0 + c, v);
 #pragma unroll
@@ -128,16 +132,16 @@ __device__ __forceinline__ void epi_to_a(uint32_t tmem_row, int col0, int ncols,
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const float u[8] = {v[8 * h], v[8 * h + 1], v[8 * h + 2], v[8 * h + 3], v[8 * h + 4], v[8 * h + 5], v[8 * h + 6], v[8 * h + 7]};
-      store_a8<NSPLIT>(a_base, Cfg<NSPLIT>::A_IMAGE, row, k_dst0 + c + 8 * h, u);
+      store_a8<NSPLIT>(a_base, Cfg<NSPLIT>::A_IMAGE, row, c + 8 * h, u);
     }
   }
 }
 
-// score-style epilogue: sum_c relu(acc[c] + bias[c]) * w[c]
-__device__ __forceinline__ float epi_dot(uint32_t tmem_row, int col0, int ncols, const float *__restrict__ bias,
+// partial of sum_c relu(acc[c] + bias[c]) * w[c] over this thread's column group
+__device__ __forceinline__ float epi_dot(uint32_t tmem_row, int cg, int col0, int ncols, const float *__restrict__ bias,
                                          const float *__restrict__ w) {
   float acc = 0.0f;
-  for (int c = 0; c < ncols; c += 16) {
+  for (int c = 16 * cg; c < ncols; c += 16 * NCG) {
     float v[16];
     tmem_ld16(tmem_row + col0 + c, v);
 #pragma unroll
@@ -156,6 +160,23 @@ __device__ __forceinline__ void block_sync_after_smem_writes() {
   tc_fence_after();
 }
 
+template <int NSPLIT>
+__device__ __forceinline__ void pipe_init(Pipe<NSPLIT> &pipe, uint8_t *smem, const Smem &L, const TcProgram &P,
+                                          long long my_tiles) {
+  constexpr int ST = Cfg<NSPLIT>::STAGES;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
+  pipe.full = bars; pipe.empty = bars + ST; pipe.acc_bar = bars + 2 * ST;
+  pipe.wbuf = smem + L.w; pipe.wpack = P.wpack;
+  pipe.n_stage_slabs = P.n_slabs; pipe.slab_off = P.slab_off; pipe.slab_bytes = P.slab_bytes;
+  pipe.loaded = pipe.consumed = 0; pipe.acc_phase = 0;
+  pipe.total = my_tiles * P.n_slabs;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < ST; ++i) { mbar_init(&pipe.full[i], 1); mbar_init(&pipe.empty[i], 1); }
+    mbar_init(pipe.acc_bar, 1);
+    fence_barrier_init();
+  }
+}
+
 struct TcEntityParams {
   TcProgram prog;
   const float *vin;
@@ -169,41 +190,31 @@ struct TcEntityParams {
 };
 
 template <int NSPLIT>
-__global__ void __launch_bounds__(TILE_M, 1) tc_entity_kernel(const TcEntityParams p) {
+__global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const Smem L = smem_layout<NSPLIT>();
   uint8_t *A = smem + L.a;
   float *GV = reinterpret_cast<float *>(smem + L.gv), *G = reinterpret_cast<float *>(smem + L.g);
   float *SC = reinterpret_cast<float *>(smem + L.sc), *XS = reinterpret_cast<float *>(smem + L.xs);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
   __shared__ uint32_t tmem_slot;
   __shared__ int cnt[MAX_TS];
   const TcProgram &P = p.prog;
   const int tid = threadIdx.x, warp = tid >> 5;
-  constexpr int ST = Cfg<NSPLIT>::STAGES;
+  const int row = ((warp & 3) << 5) | (tid & 31);   // TMEM lane quarter of this warp
+  const int cg = warp >> 2;                         // column group
 
   Pipe<NSPLIT> pipe;
-  pipe.full = bars; pipe.empty = bars + ST; pipe.acc_bar = bars + 2 * ST;
-  pipe.wbuf = smem + L.w; pipe.wpack = P.wpack; pipe.stages = nullptr;
-  pipe.n_stage_slabs = P.n_slabs; pipe.slab_off = P.slab_off; pipe.slab_bytes = P.slab_bytes;
-  pipe.loaded = pipe.consumed = 0; pipe.acc_phase = 0;
   const long long n_tiles = (p.n_states + p.ts - 1) / p.ts;
-  const long long my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-  pipe.total = my_tiles * P.n_slabs;
-
-  if (tid == 0) {
-    for (int i = 0; i < ST; ++i) { mbar_init(&pipe.full[i], 1); mbar_init(&pipe.empty[i], 1); }
-    mbar_init(pipe.acc_bar, 1);
-    fence_barrier_init();
-  }
+  pipe_init<NSPLIT>(pipe, smem, L, P, (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
   if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);   // this warp's lane quarter
+  const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   const uint32_t a_smem = smem_u32(A);
   const int n = p.n, ts = p.ts, D = p.D;
+  const int h1d = P.h1d, a1p = P.st[ST_L4].np, h2d = P.h2d;
 
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long s0 = tile * ts;
@@ -221,22 +232,18 @@ __global__ void __launch_bounds__(TILE_M, 1) tc_entity_kernel(const TcEntityPara
       }
       cnt[tid] = c;
     }
-    // ---- X -> A (K padded to 32) ----------------------------------------------------------------
+    // ---- X -> A (K padded to 32): thread (row, cg) converts k-chunk cg -------------------------------
     {
-      float x[32];
+      float u[8];
+      const float *src = p.vin + ((size_t)s0 * n + row) * D;
 #pragma unroll
-      for (int k = 0; k < 32; ++k) x[k] = 0.0f;
-      if (tid < rows) {
-        const float *src = p.vin + ((size_t)s0 * n + tid) * D;
-        for (int k = 0; k < D; ++k) x[k] = __ldg(src + k);
-        if (tid % n == 0)
-          for (int k = 0; k < p.self_dim; ++k) XS[(tid / n) * 8 + k] = x[k];
+      for (int j = 0; j < 8; ++j) {
+        const int k = 8 * cg + j;
+        u[j] = (row < rows && k < D) ? __ldg(src + k) : 0.0f;
       }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float u[8] = {x[8 * c], x[8 * c + 1], x[8 * c + 2], x[8 * c + 3], x[8 * c + 4], x[8 * c + 5], x[8 * c + 6], x[8 * c + 7]};
-        store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, tid, 8 * c, u);
-      }
+      store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, row, 8 * cg, u);
+      if (cg == 0 && row < rows && row % n == 0)
+        for (int k = 0; k < p.self_dim; ++k) XS[(row / n) * 8 + k] = u[k];
     }
     block_sync_after_smem_writes();
     // ---- mlp1.0 (wide: one or two N halves) ----------------------------------------------------------
@@ -248,7 +255,7 @@ __global__ void __launch_bounds__(TILE_M, 1) tc_entity_kernel(const TcEntityPara
     // ---- mlp1.2, K chunked by the wide halves ------------------------------------------------------
     for (int h = 0; h < P.n_wide; ++h) {
       const TcStage &W = P.st[ST_L0A + h];
-      epi_to_a<NSPLIT>(tmem_row, W.acc_col, W.np, P.bias[0] + W.n_lo, nullptr, true, A, tid, 0);
+      epi_to_a<NSPLIT>(tmem_row, cg, W.acc_col, W.np, P.bias[0] + W.n_lo, nullptr, true, A, row);
       block_sync_after_smem_writes();
       if (tid == 0) { pipe.mma_stage(P.st[ST_L1A + h], a_smem, tmem_base); pipe.commit_acc(); }
       pipe.wait_acc();
@@ -256,7 +263,7 @@ __global__ void __launch_bounds__(TILE_M, 1) tc_entity_kernel(const TcEntityPara
     // ---- H1 -> A; mlp2.0 and attention.0 (local half) share it ---------------------------------------
     {
       const TcStage &S = P.st[ST_L1A];
-      epi_to_a<NSPLIT>(tmem_row, S.acc_col, S.np, P.bias[1], nullptr, true, A, tid, 0);
+      epi_to_a<NSPLIT>(tmem_row, cg, S.acc_col, S.np, P.bias[1], nullptr, true, A, row);
     }
     block_sync_after_smem_writes();
     if (tid == 0) {
@@ -264,12 +271,11 @@ __global__ void __launch_bounds__(TILE_M, 1) tc_entity_kernel(const TcEntityPara
       pipe.mma_stage(P.st[ST_L4], a_smem, tmem_base);
       pipe.commit_acc();
     }
-    // meanwhile: global state G = mean over the state's rows of H1 (read back from the A images),
-    // GV = attention.0.bias + W_att0[:, h1:] . G   (sarl.py:51-63)
-    const int h1d = P.h1d, a1p = P.st[ST_L4].np;
+    // meanwhile (the MMAs run asynchronously): global state G = mean over the state's rows of H1, read
+    // back from the A images, and GV = attention.0.bias + W_att0[:, h1:] . G   (sarl.py:51-63)
     if (P.with_global) {
-      for (int i = tid; i < ts * h1d; i += TILE_M) {
-        const int s = i / h1d, k = i % h1d;
+      for (int i = tid; i < ts * h1d; i += NT) {
+        const int s = i % ts, k = i / ts;
         const int c = cnt[s];
         float acc = 0.0f;
         for (int r = 0; r < c; ++r) {
@@ -280,24 +286,39 @@ __global__ void __launch_bounds__(TILE_M, 1) tc_entity_kernel(const TcEntityPara
             v += __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(A + (size_t)sp * Cfg<NSPLIT>::A_IMAGE + off));
           acc += v;
         }
-        G[s * KMAX + k] = c > 0 ? acc / (float)c : 0.0f;
+        G[k * MAX_TS + s] = c > 0 ? acc / (float)c : 0.0f;
       }
       __syncthreads();
-      for (int i = tid; i < ts * a1p; i += TILE_M) {
-        const int s = i / a1p, c = i % a1p;
-        float acc = __ldg(P.bias[4] + c);
-        for (int k = 0; k < h1d; ++k) acc = fmaf(G[s * KMAX + k], __ldg(P.wg + (size_t)k * a1p + c), acc);
-        GV[s * KMAX + c] = acc;
+      // thread -> one output column, 8 states: each weight is fetched once per 8 states
+      const int c = tid & 255, sh = tid >> 8;
+      if (c < a1p && sh * 8 < ts) {
+        float acc[8];
+        const float b = __ldg(P.bias[4] + c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = b;
+        const float *wcol = P.wg + c;
+#pragma unroll 4
+        for (int k = 0; k < h1d; ++k) {
+          const float wv = __ldg(wcol + (size_t)k * a1p);
+          const float4 g0 = *reinterpret_cast<const float4 *>(G + k * MAX_TS + sh * 8);
+          const float4 g1 = *reinterpret_cast<const float4 *>(G + k * MAX_TS + sh * 8 + 4);
+          acc[0] = fmaf(g0.x, wv, acc[0]); acc[1] = fmaf(g0.y, wv, acc[1]);
+          acc[2] = fmaf(g0.z, wv, acc[2]); acc[3] = fmaf(g0.w, wv, acc[3]);
+          acc[4] = fmaf(g1.x, wv, acc[4]); acc[5] = fmaf(g1.y, wv, acc[5]);
+          acc[6] = fmaf(g1.z, wv, acc[6]); acc[7] = fmaf(g1.w, wv, acc[7]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) GV[(sh * 8 + j) * KMAX + c] = acc[j];
       }
     } else {
-      for (int i = tid; i < ts * a1p; i += TILE_M) GV[(i / a1p) * KMAX + (i % a1p)] = __ldg(P.bias[4] + (i % a1p));
+      for (int i = tid; i < ts * a1p; i += NT) GV[(i / a1p) * KMAX + (i % a1p)] = __ldg(P.bias[4] + (i % a1p));
     }
     __syncthreads();
     pipe.wait_acc();
     // ---- T2 -> A; mlp2.2 ---------------------------------------------------------------------------
     {
       const TcStage &S = P.st[ST_L2];
-      epi_to_a<NSPLIT>(tmem_row, S.acc_col, S.np, P.bias[2], nullptr, true, A, tid, 0);
+      epi_to_a<NSPLIT>(tmem_row, cg, S.acc_col, S.np, P.bias[2], nullptr, true, A, row);
     }
     block_sync_after_smem_writes();
     if (tid == 0) { pipe.mma_stage(P.st[ST_L3], a_smem, tmem_base); pipe.commit_acc(); }
@@ -305,8 +326,8 @@ __global__ void __launch_bounds__(TILE_M, 1) tc_entity_kernel(const TcEntityPara
     // ---- U = relu(att0 + GV[state]) -> A; attention.2 ----------------------------------------------------
     {
       const TcStage &S = P.st[ST_L4];
-      const int s = min(tid / n, ts - 1);
-      epi_to_a<NSPLIT>(tmem_row, S.acc_col, S.np, P.zero_bias, GV + s * KMAX, true, A, tid, 0);
+      const int s = min(row / n, ts - 1);
+      epi_to_a<NSPLIT>(tmem_row, cg, S.acc_col, S.np, P.zero_bias, GV + s * KMAX, true, A, row);
     }
     block_sync_after_smem_writes();
     if (tid == 0) { pipe.mma_stage(P.st[ST_L5], a_smem, tmem_base); pipe.commit_acc(); }
@@ -314,45 +335,47 @@ __global__ void __launch_bounds__(TILE_M, 1) tc_entity_kernel(const TcEntityPara
     // ---- attention.4 score, masked softmax, pooling (sarl.py:64-78) ----------------------------------------
     {
       const TcStage &S = P.st[ST_L5];
-      SC[tid] = epi_dot(tmem_row, S.acc_col, S.np, P.bias[5], P.w6) + P.b6;
+      SC[cg * TILE_M + row] = epi_dot(tmem_row, cg, S.acc_col, S.np, P.bias[5], P.w6);
     }
     tc_fence_before();
     __syncthreads();
+    float *WT = SC + NCG * TILE_M;   // softmax weight per row
     if (tid < ts) {
       const int c = cnt[tid];
       float sum = 0.0f;
       for (int r = 0; r < c; ++r) {
-        const float sc = SC[tid * n + r];
+        const int rr = tid * n + r;
+        const float sc = ((SC[rr] + SC[TILE_M + rr]) + (SC[2 * TILE_M + rr] + SC[3 * TILE_M + rr])) + P.b6;
         const float e = (sc != 0.0f) ? expf(sc) : 0.0f;
-        SC[TILE_M + tid * n + r] = e;
+        WT[rr] = e;
         sum += e;
       }
-      for (int r = 0; r < n; ++r) SC[TILE_M + tid * n + r] = (r < c) ? SC[TILE_M + tid * n + r] / sum : 0.0f;
+      for (int r = 0; r < n; ++r) WT[tid * n + r] = (r < c) ? WT[tid * n + r] / sum : 0.0f;
     }
     __syncthreads();
     // weighted H2 rows -> scratch (the A region is free: all MMAs that read it have completed)
     float *PS = reinterpret_cast<float *>(A);
-    const int h2p = P.st[ST_L3].np, h2d = P.h2d;
     {
-      const float wrow = (tid < ts * n) ? SC[TILE_M + tid] : 0.0f;
-      for (int c = 0; c < h2p; c += 16) {
+      const float wrow = (row < ts * n) ? WT[row] : 0.0f;
+      const TcStage &S = P.st[ST_L3];
+      for (int c = 16 * cg; c < S.np; c += 16 * NCG) {
         float v[16];
-        tmem_ld16(tmem_row + P.st[ST_L3].acc_col + c, v);
+        tmem_ld16(tmem_row + S.acc_col + c, v);
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (c + i < h2d) PS[(c + i) * (TILE_M + 4) + tid] = (v[i] + __ldg(P.bias[3] + c + i)) * wrow;
+          if (c + i < h2d) PS[(c + i) * PS_LD + row] = (v[i] + __ldg(P.bias[3] + c + i)) * wrow;
       }
     }
     tc_fence_before();
     __syncthreads();
-    for (int i = tid; i < ns * p.jd; i += TILE_M) {
+    for (int i = tid; i < ns * p.jd; i += NT) {
       const int s = i / p.jd, k = i % p.jd;
       float v;
       if (k < p.self_dim) v = XS[s * 8 + k];
       else {
         v = 0.0f;
         const int c = cnt[s], col = k - p.self_dim;
-        for (int r = 0; r < c; ++r) v += PS[col * (TILE_M + 4) + s * n + r];
+        for (int r = 0; r < c; ++r) v += PS[col * PS_LD + s * n + r];
       }
       p.joint[(size_t)(s0 + s) * p.jd + k] = v;
     }
@@ -372,46 +395,37 @@ struct TcMlp3Params {
 };
 
 template <int NSPLIT>
-__global__ void __launch_bounds__(TILE_M, 1) tc_mlp3_kernel(const TcMlp3Params p) {
+__global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const Smem L = smem_layout<NSPLIT>();
   uint8_t *A = smem + L.a;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
+  float *SC = reinterpret_cast<float *>(smem + L.sc);
   __shared__ uint32_t tmem_slot;
   const TcProgram &P = p.prog;
   const int tid = threadIdx.x, warp = tid >> 5;
-  constexpr int ST = Cfg<NSPLIT>::STAGES;
+  const int row = ((warp & 3) << 5) | (tid & 31);
+  const int cg = warp >> 2;
   Pipe<NSPLIT> pipe;
-  pipe.full = bars; pipe.empty = bars + ST; pipe.acc_bar = bars + 2 * ST;
-  pipe.wbuf = smem + L.w; pipe.wpack = P.wpack; pipe.stages = nullptr;
-  pipe.n_stage_slabs = P.n_slabs; pipe.slab_off = P.slab_off; pipe.slab_bytes = P.slab_bytes;
-  pipe.loaded = pipe.consumed = 0; pipe.acc_phase = 0;
   const long long n_tiles = (p.n_states + TILE_M - 1) / TILE_M;
-  const long long my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-  pipe.total = my_tiles * P.n_slabs;
-  if (tid == 0) {
-    for (int i = 0; i < ST; ++i) { mbar_init(&pipe.full[i], 1); mbar_init(&pipe.empty[i], 1); }
-    mbar_init(pipe.acc_bar, 1);
-    fence_barrier_init();
-  }
+  pipe_init<NSPLIT>(pipe, smem, L, P, (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
   if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   const uint32_t a_smem = smem_u32(A);
   const int jd = p.jd, kp = P.st[ST_L0A].ksteps * 16;
 
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long s0 = tile * TILE_M;
-    const bool live = s0 + tid < p.n_states;
-    // joint row -> A (K padded to a multiple of 16)
-    for (int k0 = 0; k0 < kp; k0 += 8) {
+    const bool live = s0 + row < p.n_states;
+    // joint row -> A (K padded to a multiple of 16), k-chunks interleaved over the column groups
+    for (int k0 = 8 * cg; k0 < kp; k0 += 8 * NCG) {
       float u[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) u[j] = (live && k0 + j < jd) ? __ldg(p.joint + (size_t)(s0 + tid) * jd + k0 + j) : 0.0f;
-      store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, tid, k0, u);
+      for (int j = 0; j < 8; ++j) u[j] = (live && k0 + j < jd) ? __ldg(p.joint + (size_t)(s0 + row) * jd + k0 + j) : 0.0f;
+      store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, row, k0, u);
     }
     block_sync_after_smem_writes();
     if (tid == 0) {
@@ -421,30 +435,33 @@ __global__ void __launch_bounds__(TILE_M, 1) tc_mlp3_kernel(const TcMlp3Params p
     pipe.wait_acc();
     for (int h = 0; h < P.n_wide; ++h) {
       const TcStage &W = P.st[ST_L0A + h];
-      epi_to_a<NSPLIT>(tmem_row, W.acc_col, W.np, P.bias[0] + W.n_lo, nullptr, true, A, tid, 0);
+      epi_to_a<NSPLIT>(tmem_row, cg, W.acc_col, W.np, P.bias[0] + W.n_lo, nullptr, true, A, row);
       block_sync_after_smem_writes();
       if (tid == 0) { pipe.mma_stage(P.st[ST_L1A + h], a_smem, tmem_base); pipe.commit_acc(); }
       pipe.wait_acc();
     }
     {
       const TcStage &S = P.st[ST_L1A];
-      epi_to_a<NSPLIT>(tmem_row, S.acc_col, S.np, P.bias[1], nullptr, true, A, tid, 0);
+      epi_to_a<NSPLIT>(tmem_row, cg, S.acc_col, S.np, P.bias[1], nullptr, true, A, row);
     }
     block_sync_after_smem_writes();
     if (tid == 0) { pipe.mma_stage(P.st[ST_L2], a_smem, tmem_base); pipe.commit_acc(); }
     pipe.wait_acc();
     {
       const TcStage &S = P.st[ST_L2];
-      const float v = epi_dot(tmem_row, S.acc_col, S.np, P.bias[2], P.w6) + P.b6;
-      if (live) p.values[s0 + tid] = v;
+      SC[cg * TILE_M + row] = epi_dot(tmem_row, cg, S.acc_col, S.np, P.bias[2], P.w6);
     }
     tc_fence_before();
+    __syncthreads();
+    if (tid < TILE_M && s0 + tid < p.n_states)
+      p.values[s0 + tid] = ((SC[tid] + SC[TILE_M + tid]) + (SC[2 * TILE_M + tid] + SC[3 * TILE_M + tid])) + P.b6;
     __syncthreads();
     tc_fence_after();
   }
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
+
 
 // ---------------------------------------------------------------------------------------------------
 // Host: pack weights into slab images and build the two per-tile programs.
@@ -515,10 +532,10 @@ int launch_tc(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row
   const long long tiles_a = (n_states + ts - 1) / ts, tiles_b = (n_states + TILE_M - 1) / TILE_M;
   const int grid_a = (int)(tiles_a < s->sm_count ? tiles_a : s->sm_count);
   const int grid_b = (int)(tiles_b < s->sm_count ? tiles_b : s->sm_count);
-  tc_entity_kernel<NSPLIT><<<grid_a, TILE_M, L.total, stream>>>(p);
+  tc_entity_kernel<NSPLIT><<<grid_a, NT, L.total, stream>>>(p);
   int rc = ebc_check_launch(s, "tc_entity_kernel");
   if (rc) return rc;
-  tc_mlp3_kernel<NSPLIT><<<grid_b, TILE_M, L.total, stream>>>(q);
+  tc_mlp3_kernel<NSPLIT><<<grid_b, NT, L.total, stream>>>(q);
   return ebc_check_launch(s, "tc_mlp3_kernel");
 }
 
