@@ -1,16 +1,22 @@
 // ebc_value_tc.cu — K4 on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
 //
-// One CTA (512 threads) owns a tile of 128 entity rows (whole states) and walks the whole per-entity
-// part of rl/policy/sarl.py:38-82 with the activations never leaving the SM:
+// One CTA owns a tile of 128 entity rows (whole states) and walks the whole per-entity part of
+// rl/policy/sarl.py:38-82 with the activations never leaving the SM:
 //   X -> mlp1.0 -> mlp1.2 (= H1) -> { mlp2.0 -> mlp2.2 (= H2),  attention.0 (+ global half as a per-state
 //   bias) -> attention.2 -> attention.4 score } -> masked softmax -> pooled H2 -> joint[state]
-// and a second kernel runs mlp3 over tiles of 128 states.  Per GEMM stage: thread 0 streams the
-// pre-packed weight slabs L2 -> shared memory with cp.async.bulk (mbarrier full/empty ring) and issues
-// the tcgen05.mma's (A = activations in shared memory, canonical K-major layout written by the previous
-// epilogue; B = weight slab; D = fp32 accumulator in TMEM); tcgen05.commit signals the epilogue.  In the
-// epilogue warp w reads TMEM lane quarter (w % 4) (row = lane) and the 16-column blocks b with
-// b % 4 == w / 4, applies bias / ReLU, splits the fp32 value into bf16 parts and stores the next
-// stage's A operand.  See ebc_tc.cuh for the layout and the fp32-accurate operand splitting.
+// and a second kernel runs mlp3 over tiles of 128 states.
+//
+// Warp roles (544 threads):
+//   warp 16, one elected lane  streams the pre-packed weight slabs L2 -> shared memory with cp.async.bulk
+//                              (mbarrier full/empty ring) and issues the tcgen05.mma's: A = activations in
+//                              shared memory (canonical K-major layout written by the previous epilogue),
+//                              B = weight slab, D = fp32 accumulator in TMEM; tcgen05.commit -> acc barrier
+//   warps 0-15 (512 threads)   epilogue crew: warp w reads TMEM lane quarter (w % 4) (row = lane) and the
+//                              16-column blocks b with b % 4 == w / 4, applies bias / ReLU, splits the fp32
+//                              value into bf16 parts, stores the next stage's A operand and arrives on the
+//                              "A ready" mbarrier; crew-only synchronisation uses named barrier 1
+// so the global-state (mean / attention bias) work of the crew overlaps the MMAs of mlp2.0 / attention.0.
+// See ebc_tc.cuh for the operand layout and the fp32-accurate bf16x3 operand splitting.
 #include <stdio.h>
 #include <string.h>
 
@@ -23,15 +29,16 @@ namespace {
 
 using namespace tc;
 
-constexpr int NT = 512;                         // threads per CTA: 4 lane quarters x 4 column groups
-constexpr int NCG = NT / TILE_M;                // column groups
+constexpr int NCREW = 512;                      // epilogue threads: 4 lane quarters x 4 column groups
+constexpr int NT = NCREW + 32;                  // + the MMA / loader warp
+constexpr int NCG = NCREW / TILE_M;             // column groups
 constexpr int KMAX = 208;                       // widest A operand chunk kept in shared memory
-constexpr int MAX_TS = 16;                      // states per entity tile
 constexpr int TMEM_COLS = 512;
 constexpr int PS_LD = TILE_M + 4;
 
 template <int NSPLIT> struct Cfg {
-  static constexpr int STAGES = NSPLIT == 1 ? 6 : 2;
+  static constexpr int STAGES = NSPLIT == 1 ? 8 : 3;
+  static constexpr int MAX_TS = NSPLIT == 1 ? 16 : 8;                    // states per entity tile
   static constexpr uint32_t A_IMAGE = TILE_M * KMAX * 2;                 // bytes per split image of A
   static constexpr uint32_t A_BYTES = NSPLIT * A_IMAGE;
   static constexpr uint32_t STAGE_BYTES = NSPLIT * KMAX * 32;            // one k-step slab, all splits
@@ -39,7 +46,7 @@ template <int NSPLIT> struct Cfg {
 };
 
 struct Smem {   // offsets (bytes) into dynamic shared memory
-  uint32_t a, w, gv, g, sc, xs, bars, total;
+  uint32_t a, w, gv, sc, xs, bars, total;
 };
 
 template <int NSPLIT>
@@ -48,27 +55,32 @@ __host__ __device__ inline Smem smem_layout() {
   uint32_t off = 0;
   s.a = off; off += Cfg<NSPLIT>::A_BYTES;
   s.w = off; off += Cfg<NSPLIT>::W_BYTES;
-  s.gv = off; off += MAX_TS * KMAX * 4;         // GV[state][col]
-  s.g = off; off += KMAX * MAX_TS * 4;          // G[k][state]
-  s.sc = off; off += TILE_M * 4 * (NCG + 1);    // partial scores per column group, then softmax weights
-  s.xs = off; off += MAX_TS * 8 * 4;            // self-state part of each state's first row
+  s.gv = off; off += Cfg<NSPLIT>::MAX_TS * KMAX * 4;   // G[k][state] first, then GV[state][col] in place
+  s.sc = off; off += TILE_M * 4 * (NCG + 1);           // partial scores per column group, softmax weights
+  s.xs = off; off += 16 * 8 * 4;                        // self-state part of each state's first row
   s.bars = off; off += 256;
   s.total = off;
   return s;
 }
 
-// Ring of weight slabs + the single MMA-issuing thread's cursor.
+__device__ __forceinline__ void crew_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCREW) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Ring of weight slabs + the MMA-issuing thread's cursor; barriers shared with the crew.
 template <int NSPLIT>
 struct Pipe {
-  uint64_t *full, *empty, *acc_bar;
+  uint64_t *full, *empty, *acc_bar, *a_bar;
   uint8_t *wbuf;
   const uint8_t *wpack;      // packed weights (global)
   int n_stage_slabs;         // slabs per tile
   const uint32_t *slab_off;  // [n_stage_slabs] byte offset of each slab of the per-tile sequence
   const uint32_t *slab_bytes;
   long long loaded, consumed, total;   // running slab indices over all tiles of this CTA
-  uint32_t acc_phase;
+  uint32_t acc_phase, a_phase;
 
+  // ---- MMA thread -----------------------------------------------------------------------------------
   __device__ void prefetch() {
     constexpr int ST = Cfg<NSPLIT>::STAGES;
     while (loaded < total && loaded < consumed + ST) {
@@ -82,8 +94,11 @@ struct Pipe {
       ++loaded;
     }
   }
-
-  // thread 0: issue one GEMM stage.  a_smem = shared address of A image 0.
+  __device__ void wait_a() {           // the crew has written (and fenced) the A operand
+    mbar_wait(a_bar, a_phase);
+    a_phase ^= 1u;
+    tc_fence_after();
+  }
   __device__ void mma_stage(const TcStage &S, uint32_t a_smem, uint32_t tmem_base) {
     constexpr int ST = Cfg<NSPLIT>::STAGES;
     const uint32_t idesc = make_idesc_bf16(TILE_M, S.np);
@@ -105,13 +120,20 @@ struct Pipe {
       umma_commit(&empty[st]);   // frees the slab when these MMAs have read it
       ++consumed;
     }
-    prefetch();                  // keep the ring full across the epilogue that follows
+    prefetch();                  // keep the ring full while the crew runs the next epilogue
   }
   __device__ void commit_acc() { umma_commit(acc_bar); }
+
+  // ---- crew -------------------------------------------------------------------------------------------
   __device__ void wait_acc() {
     mbar_wait(acc_bar, acc_phase);
     acc_phase ^= 1u;
     tc_fence_after();
+  }
+  __device__ void signal_a() {         // after this thread's A-operand stores / TMEM reads
+    fence_proxy_async();               // generic-proxy smem writes -> async proxy (UMMA)
+    tc_fence_before();                 // this thread's tcgen05.ld's are ordered before the arrive
+    mbar_arrive(a_bar);
   }
 };
 
@@ -153,26 +175,20 @@ __device__ __forceinline__ float epi_dot(uint32_t tmem_row, int cg, int col0, in
   return acc;
 }
 
-__device__ __forceinline__ void block_sync_after_smem_writes() {
-  fence_proxy_async();      // generic-proxy A-operand writes -> async proxy (UMMA)
-  tc_fence_before();        // order this thread's tcgen05.ld's before the barrier
-  __syncthreads();
-  tc_fence_after();
-}
-
 template <int NSPLIT>
 __device__ __forceinline__ void pipe_init(Pipe<NSPLIT> &pipe, uint8_t *smem, const Smem &L, const TcProgram &P,
                                           long long my_tiles) {
   constexpr int ST = Cfg<NSPLIT>::STAGES;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
-  pipe.full = bars; pipe.empty = bars + ST; pipe.acc_bar = bars + 2 * ST;
+  pipe.full = bars; pipe.empty = bars + ST; pipe.acc_bar = bars + 2 * ST; pipe.a_bar = bars + 2 * ST + 1;
   pipe.wbuf = smem + L.w; pipe.wpack = P.wpack;
   pipe.n_stage_slabs = P.n_slabs; pipe.slab_off = P.slab_off; pipe.slab_bytes = P.slab_bytes;
-  pipe.loaded = pipe.consumed = 0; pipe.acc_phase = 0;
+  pipe.loaded = pipe.consumed = 0; pipe.acc_phase = 0; pipe.a_phase = 0;
   pipe.total = my_tiles * P.n_slabs;
   if (threadIdx.x == 0) {
     for (int i = 0; i < ST; ++i) { mbar_init(&pipe.full[i], 1); mbar_init(&pipe.empty[i], 1); }
     mbar_init(pipe.acc_bar, 1);
+    mbar_init(pipe.a_bar, NCREW);
     fence_barrier_init();
   }
 }
@@ -192,16 +208,15 @@ struct TcEntityParams {
 template <int NSPLIT>
 __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int MAX_TS = Cfg<NSPLIT>::MAX_TS;
   const Smem L = smem_layout<NSPLIT>();
   uint8_t *A = smem + L.a;
-  float *GV = reinterpret_cast<float *>(smem + L.gv), *G = reinterpret_cast<float *>(smem + L.g);
+  float *GV = reinterpret_cast<float *>(smem + L.gv);   // holds G[k][MAX_TS] first, GV[state][KMAX] afterwards
   float *SC = reinterpret_cast<float *>(smem + L.sc), *XS = reinterpret_cast<float *>(smem + L.xs);
   __shared__ uint32_t tmem_slot;
-  __shared__ int cnt[MAX_TS];
+  __shared__ int cnt[16];
   const TcProgram &P = p.prog;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int row = ((warp & 3) << 5) | (tid & 31);   // TMEM lane quarter of this warp
-  const int cg = warp >> 2;                         // column group
 
   Pipe<NSPLIT> pipe;
   const long long n_tiles = (p.n_states + p.ts - 1) / p.ts;
@@ -211,177 +226,196 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   const uint32_t a_smem = smem_u32(A);
-  const int n = p.n, ts = p.ts, D = p.D;
-  const int h1d = P.h1d, a1p = P.st[ST_L4].np, h2d = P.h2d;
 
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long s0 = tile * ts;
-    const int ns = (int)min((long long)ts, p.n_states - s0);
-    const int rows = ns * n;
-    if (tid < MAX_TS) {
-      int c = 0;
-      if (tid < ns) {
-        if (p.row_count) c = p.row_count[s0 + tid];
-        else {
-          const long long e = (s0 + tid) / p.n_actions;
-          c = p.hum_count[e] + p.stat_count[e];
+  if (warp == NCREW / 32) {
+    // =================================== MMA / loader warp ===================================
+    if ((tid & 31) == 0) {
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        pipe.wait_a();
+        for (int h = 0; h < P.n_wide; ++h) pipe.mma_stage(P.st[ST_L0A + h], a_smem, tmem_base);
+        pipe.commit_acc();
+        for (int h = 0; h < P.n_wide; ++h) {
+          pipe.wait_a();
+          pipe.mma_stage(P.st[ST_L1A + h], a_smem, tmem_base);
+          pipe.commit_acc();
         }
-        c = min(max(c, 0), n);
+        pipe.wait_a();
+        pipe.mma_stage(P.st[ST_L2], a_smem, tmem_base);
+        pipe.mma_stage(P.st[ST_L4], a_smem, tmem_base);
+        pipe.commit_acc();
+        pipe.wait_a();
+        pipe.mma_stage(P.st[ST_L3], a_smem, tmem_base);
+        pipe.commit_acc();
+        pipe.wait_a();
+        pipe.mma_stage(P.st[ST_L5], a_smem, tmem_base);
+        pipe.commit_acc();
       }
-      cnt[tid] = c;
     }
-    // ---- X -> A (K padded to 32): thread (row, cg) converts k-chunk cg -------------------------------
-    {
-      float u[8];
-      const float *src = p.vin + ((size_t)s0 * n + row) * D;
+  } else {
+    // ======================================= epilogue crew =======================================
+    const int row = ((warp & 3) << 5) | (tid & 31);   // TMEM lane quarter of this warp
+    const int cg = warp >> 2;                         // column group
+    const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const int n = p.n, ts = p.ts, D = p.D;
+    const int h1d = P.h1d, a1p = P.st[ST_L4].np, h2d = P.h2d;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long s0 = tile * ts;
+      const int ns = (int)min((long long)ts, p.n_states - s0);
+      const int rows = ns * n;
+      if (tid < 16) {
+        int c = 0;
+        if (tid < ns) {
+          if (p.row_count) c = p.row_count[s0 + tid];
+          else {
+            const long long e = (s0 + tid) / p.n_actions;
+            c = p.hum_count[e] + p.stat_count[e];
+          }
+          c = min(max(c, 0), n);
+        }
+        cnt[tid] = c;
+      }
+      // ---- X -> A (K padded to 32): thread (row, cg) converts k-chunk cg ------------------------------
+      {
+        float u[8];
+        const float *src = p.vin + ((size_t)s0 * n + row) * D;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int k = 8 * cg + j;
-        u[j] = (row < rows && k < D) ? __ldg(src + k) : 0.0f;
+        for (int j = 0; j < 8; ++j) {
+          const int k = 8 * cg + j;
+          u[j] = (row < rows && k < D) ? __ldg(src + k) : 0.0f;
+        }
+        store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, row, 8 * cg, u);
+        if (cg == 0 && row < rows && row % n == 0)
+          for (int k = 0; k < p.self_dim; ++k) XS[(row / n) * 8 + k] = u[k];
       }
-      store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, row, 8 * cg, u);
-      if (cg == 0 && row < rows && row % n == 0)
-        for (int k = 0; k < p.self_dim; ++k) XS[(row / n) * 8 + k] = u[k];
-    }
-    block_sync_after_smem_writes();
-    // ---- mlp1.0 (wide: one or two N halves) ----------------------------------------------------------
-    if (tid == 0) {
-      for (int h = 0; h < P.n_wide; ++h) pipe.mma_stage(P.st[ST_L0A + h], a_smem, tmem_base);
-      pipe.commit_acc();
-    }
-    pipe.wait_acc();
-    // ---- mlp1.2, K chunked by the wide halves ------------------------------------------------------
-    for (int h = 0; h < P.n_wide; ++h) {
-      const TcStage &W = P.st[ST_L0A + h];
-      epi_to_a<NSPLIT>(tmem_row, cg, W.acc_col, W.np, P.bias[0] + W.n_lo, nullptr, true, A, row);
-      block_sync_after_smem_writes();
-      if (tid == 0) { pipe.mma_stage(P.st[ST_L1A + h], a_smem, tmem_base); pipe.commit_acc(); }
+      pipe.signal_a();
+      // ---- mlp1.0 -> mlp1.2, K chunked by the wide halves ------------------------------------------
       pipe.wait_acc();
-    }
-    // ---- H1 -> A; mlp2.0 and attention.0 (local half) share it ---------------------------------------
-    {
-      const TcStage &S = P.st[ST_L1A];
-      epi_to_a<NSPLIT>(tmem_row, cg, S.acc_col, S.np, P.bias[1], nullptr, true, A, row);
-    }
-    block_sync_after_smem_writes();
-    if (tid == 0) {
-      pipe.mma_stage(P.st[ST_L2], a_smem, tmem_base);
-      pipe.mma_stage(P.st[ST_L4], a_smem, tmem_base);
-      pipe.commit_acc();
-    }
-    // meanwhile (the MMAs run asynchronously): global state G = mean over the state's rows of H1, read
-    // back from the A images, and GV = attention.0.bias + W_att0[:, h1:] . G   (sarl.py:51-63)
-    if (P.with_global) {
-      for (int i = tid; i < ts * h1d; i += NT) {
-        const int s = i % ts, k = i / ts;
-        const int c = cnt[s];
-        float acc = 0.0f;
-        for (int r = 0; r < c; ++r) {
-          const size_t off = (size_t)(k >> 3) * A_CHUNK_BYTES + (size_t)(s * n + r) * 16 + (size_t)(k & 7) * 2;
-          float v = 0.0f;
-#pragma unroll
-          for (int sp = 0; sp < NSPLIT; ++sp)
-            v += __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(A + (size_t)sp * Cfg<NSPLIT>::A_IMAGE + off));
-          acc += v;
-        }
-        G[k * MAX_TS + s] = c > 0 ? acc / (float)c : 0.0f;
+      for (int h = 0; h < P.n_wide; ++h) {
+        const TcStage &W = P.st[ST_L0A + h];
+        epi_to_a<NSPLIT>(tmem_row, cg, W.acc_col, W.np, P.bias[0] + W.n_lo, nullptr, true, A, row);
+        pipe.signal_a();
+        pipe.wait_acc();
       }
-      __syncthreads();
-      // thread -> one output column, 8 states: each weight is fetched once per 8 states
-      const int c = tid & 255, sh = tid >> 8;
-      if (c < a1p && sh * 8 < ts) {
+      // ---- H1 -> A; mlp2.0 and attention.0 (local half) share it -------------------------------------
+      {
+        const TcStage &S = P.st[ST_L1A];
+        epi_to_a<NSPLIT>(tmem_row, cg, S.acc_col, S.np, P.bias[1], nullptr, true, A, row);
+      }
+      pipe.signal_a();
+      // while those MMAs run: global state G = mean over the state's rows of H1 (read back from the A
+      // images), then GV = attention.0.bias + W_att0[:, h1:] . G in place   (sarl.py:51-63)
+      crew_sync();   // every crew thread's H1 stores (and cnt) are visible
+      if (P.with_global) {
+        for (int i = tid; i < ts * h1d; i += NCREW) {
+          const int s = i % ts, k = i / ts;
+          const int c = cnt[s];
+          float acc = 0.0f;
+          for (int r = 0; r < c; ++r) {
+            const size_t off = (size_t)(k >> 3) * A_CHUNK_BYTES + (size_t)(s * n + r) * 16 + (size_t)(k & 7) * 2;
+            float v = 0.0f;
+#pragma unroll
+            for (int sp = 0; sp < NSPLIT; ++sp)
+              v += __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(A + (size_t)sp * Cfg<NSPLIT>::A_IMAGE + off));
+            acc += v;
+          }
+          GV[k * MAX_TS + s] = c > 0 ? acc / (float)c : 0.0f;
+        }
+        crew_sync();
+        // thread -> one output column, 8 states: each weight is fetched once per 8 states
+        const int c = tid & 255, sh = tid >> 8;
+        const bool live = c < a1p && sh * 8 < ts;
         float acc[8];
-        const float b = __ldg(P.bias[4] + c);
+        if (live) {
+          const float b = __ldg(P.bias[4] + c);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = b;
-        const float *wcol = P.wg + c;
+          for (int j = 0; j < 8; ++j) acc[j] = b;
+          const float *wcol = P.wg + c;
 #pragma unroll 4
-        for (int k = 0; k < h1d; ++k) {
-          const float wv = __ldg(wcol + (size_t)k * a1p);
-          const float4 g0 = *reinterpret_cast<const float4 *>(G + k * MAX_TS + sh * 8);
-          const float4 g1 = *reinterpret_cast<const float4 *>(G + k * MAX_TS + sh * 8 + 4);
-          acc[0] = fmaf(g0.x, wv, acc[0]); acc[1] = fmaf(g0.y, wv, acc[1]);
-          acc[2] = fmaf(g0.z, wv, acc[2]); acc[3] = fmaf(g0.w, wv, acc[3]);
-          acc[4] = fmaf(g1.x, wv, acc[4]); acc[5] = fmaf(g1.y, wv, acc[5]);
-          acc[6] = fmaf(g1.z, wv, acc[6]); acc[7] = fmaf(g1.w, wv, acc[7]);
+          for (int k = 0; k < h1d; ++k) {
+            const float wv = __ldg(wcol + (size_t)k * a1p);
+            const float4 g0 = *reinterpret_cast<const float4 *>(GV + k * MAX_TS + sh * 8);
+            const float4 g1 = *reinterpret_cast<const float4 *>(GV + k * MAX_TS + sh * 8 + 4);
+            acc[0] = fmaf(g0.x, wv, acc[0]); acc[1] = fmaf(g0.y, wv, acc[1]);
+            acc[2] = fmaf(g0.z, wv, acc[2]); acc[3] = fmaf(g0.w, wv, acc[3]);
+            acc[4] = fmaf(g1.x, wv, acc[4]); acc[5] = fmaf(g1.y, wv, acc[5]);
+            acc[6] = fmaf(g1.z, wv, acc[6]); acc[7] = fmaf(g1.w, wv, acc[7]);
+          }
         }
+        crew_sync();   // all reads of G done: overwrite in place with GV
+        if (live) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) GV[(sh * 8 + j) * KMAX + c] = acc[j];
+          for (int j = 0; j < 8; ++j) GV[(sh * 8 + j) * KMAX + c] = acc[j];
+        }
+      } else {
+        for (int i = tid; i < ts * a1p; i += NCREW) GV[(i / a1p) * KMAX + (i % a1p)] = __ldg(P.bias[4] + (i % a1p));
       }
-    } else {
-      for (int i = tid; i < ts * a1p; i += NT) GV[(i / a1p) * KMAX + (i % a1p)] = __ldg(P.bias[4] + (i % a1p));
-    }
-    __syncthreads();
-    pipe.wait_acc();
-    // ---- T2 -> A; mlp2.2 ---------------------------------------------------------------------------
-    {
-      const TcStage &S = P.st[ST_L2];
-      epi_to_a<NSPLIT>(tmem_row, cg, S.acc_col, S.np, P.bias[2], nullptr, true, A, row);
-    }
-    block_sync_after_smem_writes();
-    if (tid == 0) { pipe.mma_stage(P.st[ST_L3], a_smem, tmem_base); pipe.commit_acc(); }
-    pipe.wait_acc();
-    // ---- U = relu(att0 + GV[state]) -> A; attention.2 ----------------------------------------------------
-    {
-      const TcStage &S = P.st[ST_L4];
-      const int s = min(row / n, ts - 1);
-      epi_to_a<NSPLIT>(tmem_row, cg, S.acc_col, S.np, P.zero_bias, GV + s * KMAX, true, A, row);
-    }
-    block_sync_after_smem_writes();
-    if (tid == 0) { pipe.mma_stage(P.st[ST_L5], a_smem, tmem_base); pipe.commit_acc(); }
-    pipe.wait_acc();
-    // ---- attention.4 score, masked softmax, pooling (sarl.py:64-78) ----------------------------------------
-    {
-      const TcStage &S = P.st[ST_L5];
-      SC[cg * TILE_M + row] = epi_dot(tmem_row, cg, S.acc_col, S.np, P.bias[5], P.w6);
-    }
-    tc_fence_before();
-    __syncthreads();
-    float *WT = SC + NCG * TILE_M;   // softmax weight per row
-    if (tid < ts) {
-      const int c = cnt[tid];
-      float sum = 0.0f;
-      for (int r = 0; r < c; ++r) {
-        const int rr = tid * n + r;
-        const float sc = ((SC[rr] + SC[TILE_M + rr]) + (SC[2 * TILE_M + rr] + SC[3 * TILE_M + rr])) + P.b6;
-        const float e = (sc != 0.0f) ? expf(sc) : 0.0f;
-        WT[rr] = e;
-        sum += e;
+      crew_sync();
+      pipe.wait_acc();
+      // ---- T2 -> A; mlp2.2 -------------------------------------------------------------------------
+      {
+        const TcStage &S = P.st[ST_L2];
+        epi_to_a<NSPLIT>(tmem_row, cg, S.acc_col, S.np, P.bias[2], nullptr, true, A, row);
       }
-      for (int r = 0; r < n; ++r) WT[tid * n + r] = (r < c) ? WT[tid * n + r] / sum : 0.0f;
-    }
-    __syncthreads();
-    // weighted H2 rows -> scratch (the A region is free: all MMAs that read it have completed)
-    float *PS = reinterpret_cast<float *>(A);
-    {
-      const float wrow = (row < ts * n) ? WT[row] : 0.0f;
-      const TcStage &S = P.st[ST_L3];
-      for (int c = 16 * cg; c < S.np; c += 16 * NCG) {
-        float v[16];
-        tmem_ld16(tmem_row + S.acc_col + c, v);
+      pipe.signal_a();
+      pipe.wait_acc();
+      // ---- U = relu(att0 + GV[state]) -> A; attention.2 --------------------------------------------------
+      {
+        const TcStage &S = P.st[ST_L4];
+        const int s = min(row / n, ts - 1);
+        epi_to_a<NSPLIT>(tmem_row, cg, S.acc_col, S.np, P.zero_bias, GV + s * KMAX, true, A, row);
+      }
+      pipe.signal_a();
+      pipe.wait_acc();
+      // ---- attention.4 score, masked softmax, pooling (sarl.py:64-78) --------------------------------------
+      {
+        const TcStage &S = P.st[ST_L5];
+        SC[cg * TILE_M + row] = epi_dot(tmem_row, cg, S.acc_col, S.np, P.bias[5], P.w6);
+      }
+      crew_sync();
+      float *WT = SC + NCG * TILE_M;   // softmax weight per row
+      if (tid < ts) {
+        const int c = cnt[tid];
+        float sum = 0.0f;
+        for (int r = 0; r < c; ++r) {
+          const int rr = tid * n + r;
+          const float sc = ((SC[rr] + SC[TILE_M + rr]) + (SC[2 * TILE_M + rr] + SC[3 * TILE_M + rr])) + P.b6;
+          const float e = (sc != 0.0f) ? expf(sc) : 0.0f;
+          WT[rr] = e;
+          sum += e;
+        }
+        for (int r = 0; r < n; ++r) WT[tid * n + r] = (r < c) ? WT[tid * n + r] / sum : 0.0f;
+      }
+      crew_sync();
+      // weighted H2 rows -> scratch (the A region is free: all MMAs that read it have completed)
+      float *PS = reinterpret_cast<float *>(A);
+      {
+        const float wrow = (row < ts * n) ? WT[row] : 0.0f;
+        const TcStage &S = P.st[ST_L3];
+        for (int c = 16 * cg; c < S.np; c += 16 * NCG) {
+          float v[16];
+          tmem_ld16(tmem_row + S.acc_col + c, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (c + i < h2d) PS[(c + i) * PS_LD + row] = (v[i] + __ldg(P.bias[3] + c + i)) * wrow;
+          for (int i = 0; i < 16; ++i)
+            if (c + i < h2d) PS[(c + i) * PS_LD + row] = (v[i] + __ldg(P.bias[3] + c + i)) * wrow;
+        }
       }
-    }
-    tc_fence_before();
-    __syncthreads();
-    for (int i = tid; i < ns * p.jd; i += NT) {
-      const int s = i / p.jd, k = i % p.jd;
-      float v;
-      if (k < p.self_dim) v = XS[s * 8 + k];
-      else {
-        v = 0.0f;
-        const int c = cnt[s], col = k - p.self_dim;
-        for (int r = 0; r < c; ++r) v += PS[col * PS_LD + s * n + r];
+      crew_sync();
+      for (int i = tid; i < ns * p.jd; i += NCREW) {
+        const int s = i / p.jd, k = i % p.jd;
+        float v;
+        if (k < p.self_dim) v = XS[s * 8 + k];
+        else {
+          v = 0.0f;
+          const int c = cnt[s], col = k - p.self_dim;
+          for (int r = 0; r < c; ++r) v += PS[col * PS_LD + s * n + r];
+        }
+        p.joint[(size_t)(s0 + s) * p.jd + k] = v;
       }
-      p.joint[(size_t)(s0 + s) * p.jd + k] = v;
+      crew_sync();   // PS (aliases A) / SC / XS / cnt are rewritten by the next tile
     }
-    __syncthreads();   // PS / SC / XS / cnt are rewritten by the next tile
-    tc_fence_after();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
@@ -403,8 +437,6 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
   __shared__ uint32_t tmem_slot;
   const TcProgram &P = p.prog;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int row = ((warp & 3) << 5) | (tid & 31);
-  const int cg = warp >> 2;
   Pipe<NSPLIT> pipe;
   const long long n_tiles = (p.n_states + TILE_M - 1) / TILE_M;
   pipe_init<NSPLIT>(pipe, smem, L, P, (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
@@ -413,51 +445,64 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   const uint32_t a_smem = smem_u32(A);
-  const int jd = p.jd, kp = P.st[ST_L0A].ksteps * 16;
 
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long s0 = tile * TILE_M;
-    const bool live = s0 + row < p.n_states;
-    // joint row -> A (K padded to a multiple of 16), k-chunks interleaved over the column groups
-    for (int k0 = 8 * cg; k0 < kp; k0 += 8 * NCG) {
-      float u[8];
+  if (warp == NCREW / 32) {
+    if ((tid & 31) == 0) {
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        pipe.wait_a();
+        for (int h = 0; h < P.n_wide; ++h) pipe.mma_stage(P.st[ST_L0A + h], a_smem, tmem_base);
+        pipe.commit_acc();
+        for (int h = 0; h < P.n_wide; ++h) {
+          pipe.wait_a();
+          pipe.mma_stage(P.st[ST_L1A + h], a_smem, tmem_base);
+          pipe.commit_acc();
+        }
+        pipe.wait_a();
+        pipe.mma_stage(P.st[ST_L2], a_smem, tmem_base);
+        pipe.commit_acc();
+      }
+    }
+  } else {
+    const int row = ((warp & 3) << 5) | (tid & 31);
+    const int cg = warp >> 2;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const int jd = p.jd, kp = P.st[ST_L0A].ksteps * 16;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long s0 = tile * TILE_M;
+      const bool live = s0 + row < p.n_states;
+      // joint row -> A (K padded to a multiple of 16), k-chunks interleaved over the column groups
+      for (int k0 = 8 * cg; k0 < kp; k0 += 8 * NCG) {
+        float u[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) u[j] = (live && k0 + j < jd) ? __ldg(p.joint + (size_t)(s0 + row) * jd + k0 + j) : 0.0f;
-      store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, row, k0, u);
-    }
-    block_sync_after_smem_writes();
-    if (tid == 0) {
-      for (int h = 0; h < P.n_wide; ++h) pipe.mma_stage(P.st[ST_L0A + h], a_smem, tmem_base);
-      pipe.commit_acc();
-    }
-    pipe.wait_acc();
-    for (int h = 0; h < P.n_wide; ++h) {
-      const TcStage &W = P.st[ST_L0A + h];
-      epi_to_a<NSPLIT>(tmem_row, cg, W.acc_col, W.np, P.bias[0] + W.n_lo, nullptr, true, A, row);
-      block_sync_after_smem_writes();
-      if (tid == 0) { pipe.mma_stage(P.st[ST_L1A + h], a_smem, tmem_base); pipe.commit_acc(); }
+        for (int j = 0; j < 8; ++j) u[j] = (live && k0 + j < jd) ? __ldg(p.joint + (size_t)(s0 + row) * jd + k0 + j) : 0.0f;
+        store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, row, k0, u);
+      }
+      pipe.signal_a();
       pipe.wait_acc();
+      for (int h = 0; h < P.n_wide; ++h) {
+        const TcStage &W = P.st[ST_L0A + h];
+        epi_to_a<NSPLIT>(tmem_row, cg, W.acc_col, W.np, P.bias[0] + W.n_lo, nullptr, true, A, row);
+        pipe.signal_a();
+        pipe.wait_acc();
+      }
+      {
+        const TcStage &S = P.st[ST_L1A];
+        epi_to_a<NSPLIT>(tmem_row, cg, S.acc_col, S.np, P.bias[1], nullptr, true, A, row);
+      }
+      pipe.signal_a();
+      pipe.wait_acc();
+      {
+        const TcStage &S = P.st[ST_L2];
+        SC[cg * TILE_M + row] = epi_dot(tmem_row, cg, S.acc_col, S.np, P.bias[2], P.w6);
+      }
+      crew_sync();
+      if (tid < TILE_M && s0 + tid < p.n_states)
+        p.values[s0 + tid] = ((SC[tid] + SC[TILE_M + tid]) + (SC[2 * TILE_M + tid] + SC[3 * TILE_M + tid])) + P.b6;
+      crew_sync();   // SC is rewritten by the next tile; the next A stores follow every TMEM read above
     }
-    {
-      const TcStage &S = P.st[ST_L1A];
-      epi_to_a<NSPLIT>(tmem_row, cg, S.acc_col, S.np, P.bias[1], nullptr, true, A, row);
-    }
-    block_sync_after_smem_writes();
-    if (tid == 0) { pipe.mma_stage(P.st[ST_L2], a_smem, tmem_base); pipe.commit_acc(); }
-    pipe.wait_acc();
-    {
-      const TcStage &S = P.st[ST_L2];
-      SC[cg * TILE_M + row] = epi_dot(tmem_row, cg, S.acc_col, S.np, P.bias[2], P.w6);
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (tid < TILE_M && s0 + tid < p.n_states)
-      p.values[s0 + tid] = ((SC[tid] + SC[TILE_M + tid]) + (SC[2 * TILE_M + tid] + SC[3 * TILE_M + tid])) + P.b6;
-    __syncthreads();
-    tc_fence_after();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
@@ -521,7 +566,7 @@ int launch_tc(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row
   p.n_actions = s->cfg.n_actions; p.n_states = n_states; p.n = n; p.D = s->net.D;
   int ts = TILE_M / n;
   if (ts < 1) ts = 1;
-  if (ts > MAX_TS) ts = MAX_TS;
+  if (ts > Cfg<NSPLIT>::MAX_TS) ts = Cfg<NSPLIT>::MAX_TS;
   p.ts = ts;
   p.joint = s->d_joint; p.jd = s->net.self_dim + s->net.l[3].out; p.self_dim = s->net.self_dim;
   TcMlp3Params q;
