@@ -212,6 +212,14 @@ int ebc_reset(ebc_sim *s, const ebc_state *pool, int32_t pool_size, const int32_
   return ebc_launch_reset(s, pool, pool_size, pool_index, mask, (cudaStream_t)stream);
 }
 
+int ebc_debug_trace(ebc_sim *s, long long *out, int32_t n) {
+  if (!s || !out || n < 1) return EBC_ERR_INVALID;
+  if (!s->d_trace) return ebc_fail(s, EBC_ERR_UNBOUND, "ebc_debug_trace: run ebc_value with EBC_TC_TRACE=1 first");
+  cudaDeviceSynchronize();
+  const cudaError_t err = cudaMemcpy(out, s->d_trace, sizeof(long long) * (size_t)(n < 4096 ? n : 4096), cudaMemcpyDeviceToHost);
+  return err == cudaSuccess ? EBC_OK : ebc_fail(s, EBC_ERR_CUDA, "ebc_debug_trace: %s", cudaGetErrorString(err));
+}
+
 int64_t ebc_launch_count(const ebc_sim *s) { return s ? s->launches : 0; }
 
 }  // extern "C"

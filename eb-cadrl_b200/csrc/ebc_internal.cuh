@@ -63,6 +63,7 @@ struct ebc_sim {
   float *d_joint;        // [cap_states * (self_dim + H2)] scratch for mlp3
   int64_t joint_cap;
   TcPrograms tc[2];      // [0] bf16 operands, [1] bf16x3 (fp32-accurate)
+  long long *d_trace;    // EBC_TC_TRACE=1: clock64 stamps of CTA 0 (diagnostics)
   int value_mode;        // EBC_VALUE_*
   int value_mode_forced; // set explicitly by ebc_set_value_mode
   int64_t launches;

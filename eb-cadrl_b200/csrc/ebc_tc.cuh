@@ -85,6 +85,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// split form: issue now, wait later (software-pipelined epilogues)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // ---- UMMA -----------------------------------------------------------------------------------------
 // shared-memory matrix descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor bit layout)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -123,21 +133,33 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16 (&p)[NSPLIT]) 
   }
 }
 
+// bf16x2 pack of (lo, hi) with round-to-nearest-even: one cvt for two values
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 // Store 8 consecutive k-elements (k0 % 8 == 0) of row `row` into the NSPLIT A images.
-// a_base: shared memory, image s at a_base + s * image_bytes.
+// a_base: shared memory, image s at a_base + s * image_bytes.  Parts are peeled two values at a time:
+// p = bf16x2(v), v -= float(p) (exact), repeat.
 template <int NSPLIT>
 __device__ __forceinline__ void store_a8(uint8_t *a_base, uint32_t image_bytes, int row, int k0, const float (&v)[8]) {
-  __nv_bfloat16 parts[8][NSPLIT];
+  float r[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) split_bf16<NSPLIT>(v[i], parts[i]);
+  for (int i = 0; i < 8; ++i) r[i] = v[i];
 #pragma unroll
   for (int s = 0; s < NSPLIT; ++s) {
     uint4 w;
     uint32_t *pw = reinterpret_cast<uint32_t *>(&w);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const uint16_t lo = __bfloat16_as_ushort(parts[2 * i][s]), hi = __bfloat16_as_ushort(parts[2 * i + 1][s]);
-      pw[i] = (uint32_t)lo | ((uint32_t)hi << 16);
+      const uint32_t pk = pack_bf16x2(r[2 * i], r[2 * i + 1]);
+      pw[i] = pk;
+      if (s + 1 < NSPLIT) {
+        r[2 * i] -= __uint_as_float(pk << 16);
+        r[2 * i + 1] -= __uint_as_float(pk & 0xFFFF0000u);
+      }
     }
     *reinterpret_cast<uint4 *>(a_base + (size_t)s * image_bytes + (size_t)(k0 >> 3) * A_CHUNK_BYTES + (size_t)row * 16) = w;
   }

@@ -18,6 +18,7 @@
 // so the global-state (mean / attention bias) work of the crew overlaps the MMAs of mlp2.0 / attention.0.
 // See ebc_tc.cuh for the operand layout and the fp32-accurate bf16x3 operand splitting.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -30,7 +31,8 @@ namespace {
 using namespace tc;
 
 constexpr int NCREW = 512;                      // epilogue threads: 4 lane quarters x 4 column groups
-constexpr int NT = NCREW + 32;                  // + the MMA / loader warp
+constexpr int NT = NCREW + 64;                  // + the MMA warp (16) and the weight-loader warp (17)
+constexpr int MAX_SLABS = 120;                  // slabs per tile (entity program: 75, mlp3: 46)
 constexpr int NCG = NCREW / TILE_M;             // column groups
 constexpr int KMAX = 208;                       // widest A operand chunk kept in shared memory
 constexpr int TMEM_COLS = 512;
@@ -46,7 +48,7 @@ template <int NSPLIT> struct Cfg {
 };
 
 struct Smem {   // offsets (bytes) into dynamic shared memory
-  uint32_t a, w, gv, sc, xs, bars, total;
+  uint32_t a, w, gv, sc, xs, tab, bars, total;
 };
 
 template <int NSPLIT>
@@ -58,6 +60,7 @@ __host__ __device__ inline Smem smem_layout() {
   s.gv = off; off += Cfg<NSPLIT>::MAX_TS * KMAX * 4;   // G[k][state] first, then GV[state][col] in place
   s.sc = off; off += TILE_M * 4 * (NCG + 1);           // partial scores per column group, softmax weights
   s.xs = off; off += 16 * 8 * 4;                        // self-state part of each state's first row
+  s.tab = off; off += MAX_SLABS * 8;                    // (offset, bytes) of every slab of the per-tile program
   s.bars = off; off += 256;
   s.total = off;
   return s;
@@ -75,25 +78,28 @@ struct Pipe {
   uint8_t *wbuf;
   const uint8_t *wpack;      // packed weights (global)
   int n_stage_slabs;         // slabs per tile
-  const uint32_t *slab_off;  // [n_stage_slabs] byte offset of each slab of the per-tile sequence
-  const uint32_t *slab_bytes;
-  long long loaded, consumed, total;   // running slab indices over all tiles of this CTA
+  const uint2 *tab;          // shared memory: (byte offset, bytes) of each slab of the per-tile sequence
+  long long consumed, total; // running slab index / slab count over all tiles of this CTA
   uint32_t acc_phase, a_phase;
+  long long *trace;          // optional clock64() trace of CTA 0's crew thread 0 (EBC_TC_TRACE=1)
+  int trace_pos;
+  __device__ __forceinline__ void stamp() {
+    if (trace && threadIdx.x == 0 && blockIdx.x == 0 && trace_pos < 4096) trace[trace_pos++] = clock64();
+  }
 
-  // ---- MMA thread -----------------------------------------------------------------------------------
-  __device__ void prefetch() {
+  // ---- loader thread: streams every slab of every tile of this CTA through the ring ---------------------
+  __device__ void loader_loop() {
     constexpr int ST = Cfg<NSPLIT>::STAGES;
-    while (loaded < total && loaded < consumed + ST) {
-      const int st = (int)(loaded % ST);
-      const uint32_t ph = (uint32_t)((loaded / ST) & 1);
+    for (long long i = 0; i < total; ++i) {
+      const int st = (int)(i % ST);
+      const uint32_t ph = (uint32_t)((i / ST) & 1);
       mbar_wait(&empty[st], ph ^ 1u);
-      const int i = (int)(loaded % n_stage_slabs);
-      const uint32_t bytes = __ldg(slab_bytes + i);
-      mbar_arrive_expect_tx(&full[st], bytes);
-      bulk_g2s(wbuf + (size_t)st * Cfg<NSPLIT>::STAGE_BYTES, wpack + __ldg(slab_off + i), bytes, &full[st]);
-      ++loaded;
+      const uint2 sl = tab[(int)(i % n_stage_slabs)];
+      mbar_arrive_expect_tx(&full[st], sl.y);
+      bulk_g2s(wbuf + (size_t)st * Cfg<NSPLIT>::STAGE_BYTES, wpack + sl.x, sl.y, &full[st]);
     }
   }
+  // ---- MMA thread -----------------------------------------------------------------------------------
   __device__ void wait_a() {           // the crew has written (and fenced) the A operand
     mbar_wait(a_bar, a_phase);
     a_phase ^= 1u;
@@ -104,7 +110,6 @@ struct Pipe {
     const uint32_t idesc = make_idesc_bf16(TILE_M, S.np);
     const uint32_t d = tmem_base + S.acc_col;
     for (int ks = 0; ks < S.ksteps; ++ks) {
-      prefetch();
       const int st = (int)(consumed % ST);
       const uint32_t ph = (uint32_t)((consumed / ST) & 1);
       mbar_wait(&full[st], ph);
@@ -120,7 +125,6 @@ struct Pipe {
       umma_commit(&empty[st]);   // frees the slab when these MMAs have read it
       ++consumed;
     }
-    prefetch();                  // keep the ring full while the crew runs the next epilogue
   }
   __device__ void commit_acc() { umma_commit(acc_bar); }
 
@@ -129,8 +133,10 @@ struct Pipe {
     mbar_wait(acc_bar, acc_phase);
     acc_phase ^= 1u;
     tc_fence_after();
+    stamp();
   }
-  __device__ void signal_a() {         // after this thread's A-operand stores / TMEM reads
+  __device__ void signal_a() {
+    stamp();         // after this thread's A-operand stores / TMEM reads
     fence_proxy_async();               // generic-proxy smem writes -> async proxy (UMMA)
     tc_fence_before();                 // this thread's tcgen05.ld's are ordered before the arrive
     mbar_arrive(a_bar);
@@ -139,9 +145,13 @@ struct Pipe {
 
 // accumulator columns [col0, col0 + ncols) of this thread's row, this thread's column group
 // -> relu?(x + bias (+ gv)) -> A operand, k index = (c - col0).  ncols % 16 == 0.
-template <int NSPLIT>
+// With GSUM (n divides 32, so a state's rows are an aligned lane group of this warp): also reduce the
+// activated fp32 values over the state's real rows with shuffles and store the mean to g_out[col * g_ld + state]
+// -- the global state of sarl.py:51-60, taken from registers instead of re-reading the bf16 images.
+template <int NSPLIT, bool GSUM>
 __device__ __forceinline__ void epi_to_a(uint32_t tmem_row, int cg, int col0, int ncols, const float *__restrict__ bias,
-                                         const float *gv_row, bool relu, uint8_t *a_base, int row) {
+                                         const float *gv_row, bool relu, uint8_t *a_base, int row,
+                                         int n = 1, int row_cnt = 0, float *g_out = nullptr, int g_ld = 0) {
   for (int c = 16 * cg; c < ncols; c += 16 * NCG) {
     float v[16];
     tmem_ld16(tmem_row + col0 + c, v);
@@ -155,6 +165,43 @@ __device__ __forceinline__ void epi_to_a(uint32_t tmem_row, int cg, int col0, in
     for (int h = 0; h < 2; ++h) {
       const float u[8] = {v[8 * h], v[8 * h + 1], v[8 * h + 2], v[8 * h + 3], v[8 * h + 4], v[8 * h + 5], v[8 * h + 6], v[8 * h + 7]};
       store_a8<NSPLIT>(a_base, Cfg<NSPLIT>::A_IMAGE, row, c + 8 * h, u);
+    }
+    if (GSUM) {
+      const int r_in = row % n;                 // row index inside its state
+      const bool real = r_in < row_cnt;         // padding rows do not enter the mean
+      const float inv = row_cnt > 0 ? 1.0f / (float)row_cnt : 0.0f;
+      if (n == 16) {
+        // transpose-reduce over the 16 lanes of the state: 8 + 4 + 2 + 1 shuffles instead of 16 x 4;
+        // lane l of the group ends with the sum of column c + l
+        const int lane = threadIdx.x & 31;
+        float w8[8], w4[4], w2[2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float lo = real ? v[i] : 0.0f, hi = real ? v[i + 8] : 0.0f;
+          const float send = (lane & 8) ? lo : hi, keep = (lane & 8) ? hi : lo;
+          w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float send = (lane & 4) ? w8[i] : w8[i + 4], keep = (lane & 4) ? w8[i + 4] : w8[i];
+          w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float send = (lane & 2) ? w4[i] : w4[i + 2], keep = (lane & 2) ? w4[i + 2] : w4[i];
+          w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        const float send = (lane & 1) ? w2[0] : w2[1], keep = (lane & 1) ? w2[1] : w2[0];
+        const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        g_out[(c + (lane & 15)) * g_ld + row / n] = tot * inv;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float x = real ? v[i] : 0.0f;
+          for (int o = 1; o < n; o <<= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+          if (r_in == 0) g_out[(c + i) * g_ld + row / n] = x * inv;
+        }
+      }
     }
   }
 }
@@ -182,8 +229,12 @@ __device__ __forceinline__ void pipe_init(Pipe<NSPLIT> &pipe, uint8_t *smem, con
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
   pipe.full = bars; pipe.empty = bars + ST; pipe.acc_bar = bars + 2 * ST; pipe.a_bar = bars + 2 * ST + 1;
   pipe.wbuf = smem + L.w; pipe.wpack = P.wpack;
-  pipe.n_stage_slabs = P.n_slabs; pipe.slab_off = P.slab_off; pipe.slab_bytes = P.slab_bytes;
-  pipe.loaded = pipe.consumed = 0; pipe.acc_phase = 0; pipe.a_phase = 0;
+  pipe.n_stage_slabs = P.n_slabs;
+  uint2 *tab = reinterpret_cast<uint2 *>(smem + L.tab);
+  for (int i = threadIdx.x; i < P.n_slabs; i += blockDim.x) tab[i] = make_uint2(__ldg(P.slab_off + i), __ldg(P.slab_bytes + i));
+  pipe.tab = tab;
+  pipe.consumed = 0; pipe.acc_phase = 0; pipe.a_phase = 0;
+  pipe.trace = nullptr; pipe.trace_pos = 0;
   pipe.total = my_tiles * P.n_slabs;
   if (threadIdx.x == 0) {
     for (int i = 0; i < ST; ++i) { mbar_init(&pipe.full[i], 1); mbar_init(&pipe.empty[i], 1); }
@@ -203,6 +254,7 @@ struct TcEntityParams {
   float *joint;
   int jd;          // self_dim + H2
   int self_dim;
+  long long *trace;
 };
 
 template <int NSPLIT>
@@ -221,6 +273,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
   Pipe<NSPLIT> pipe;
   const long long n_tiles = (p.n_states + p.ts - 1) / p.ts;
   pipe_init<NSPLIT>(pipe, smem, L, P, (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  pipe.trace = p.trace;
   if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -252,6 +305,8 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
         pipe.commit_acc();
       }
     }
+  } else if (warp == NCREW / 32 + 1) {
+    if ((tid & 31) == 0) pipe.loader_loop();
   } else {
     // ======================================= epilogue crew =======================================
     const int row = ((warp & 3) << 5) | (tid & 31);   // TMEM lane quarter of this warp
@@ -259,6 +314,20 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
     const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const int n = p.n, ts = p.ts, D = p.D;
     const int h1d = P.h1d, a1p = P.st[ST_L4].np, h2d = P.h2d;
+    // this thread's 8 input values of a tile (k-chunk cg of row `row`), fetched one tile ahead so that the
+    // HBM latency of the value-network input hides behind the previous tile's tail
+    float xu[8];
+    auto load_x = [&](long long t) {
+      const long long t0 = t * ts;
+      const int trows = (int)min((long long)ts, p.n_states - t0) * n;
+      const float *src = p.vin + ((size_t)t0 * n + row) * D;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = 8 * cg + j;
+        xu[j] = (row < trows && k < D) ? __ldg(src + k) : 0.0f;
+      }
+    };
+    if (blockIdx.x < n_tiles) load_x(blockIdx.x);
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long s0 = tile * ts;
       const int ns = (int)min((long long)ts, p.n_states - s0);
@@ -275,51 +344,51 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
         }
         cnt[tid] = c;
       }
-      // ---- X -> A (K padded to 32): thread (row, cg) converts k-chunk cg ------------------------------
-      {
-        float u[8];
-        const float *src = p.vin + ((size_t)s0 * n + row) * D;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int k = 8 * cg + j;
-          u[j] = (row < rows && k < D) ? __ldg(src + k) : 0.0f;
-        }
-        store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, row, 8 * cg, u);
-        if (cg == 0 && row < rows && row % n == 0)
-          for (int k = 0; k < p.self_dim; ++k) XS[(row / n) * 8 + k] = u[k];
-      }
+      // ---- X -> A (K padded to 32): thread (row, cg) converts k-chunk cg (values prefetched below) -------
+      store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, row, 8 * cg, xu);
+      if (cg == 0 && row < rows && row % n == 0)
+        for (int k = 0; k < p.self_dim; ++k) XS[(row / n) * 8 + k] = xu[k];
       pipe.signal_a();
       // ---- mlp1.0 -> mlp1.2, K chunked by the wide halves ------------------------------------------
       pipe.wait_acc();
       for (int h = 0; h < P.n_wide; ++h) {
         const TcStage &W = P.st[ST_L0A + h];
-        epi_to_a<NSPLIT>(tmem_row, cg, W.acc_col, W.np, P.bias[0] + W.n_lo, nullptr, true, A, row);
+        epi_to_a<NSPLIT, false>(tmem_row, cg, W.acc_col, W.np, P.bias[0] + W.n_lo, nullptr, true, A, row);
         pipe.signal_a();
         pipe.wait_acc();
       }
       // ---- H1 -> A; mlp2.0 and attention.0 (local half) share it -------------------------------------
+      const bool gsum = P.with_global && (32 % n == 0);
       {
         const TcStage &S = P.st[ST_L1A];
-        epi_to_a<NSPLIT>(tmem_row, cg, S.acc_col, S.np, P.bias[1], nullptr, true, A, row);
+        if (gsum) {
+          crew_sync();   // cnt[] of this tile is visible
+          const int st_of_row = min(row / n, ts - 1);
+          epi_to_a<NSPLIT, true>(tmem_row, cg, S.acc_col, S.np, P.bias[1], nullptr, true, A, row, n, cnt[st_of_row], GV, MAX_TS);
+        } else {
+          epi_to_a<NSPLIT, false>(tmem_row, cg, S.acc_col, S.np, P.bias[1], nullptr, true, A, row);
+        }
       }
       pipe.signal_a();
-      // while those MMAs run: global state G = mean over the state's rows of H1 (read back from the A
-      // images), then GV = attention.0.bias + W_att0[:, h1:] . G in place   (sarl.py:51-63)
-      crew_sync();   // every crew thread's H1 stores (and cnt) are visible
+      // while those MMAs run: GV = attention.0.bias + W_att0[:, h1:] . G in place   (sarl.py:51-63)
+      crew_sync();   // every crew thread's H1 stores, G partials and cnt are visible
       if (P.with_global) {
-        for (int i = tid; i < ts * h1d; i += NCREW) {
-          const int s = i % ts, k = i / ts;
-          const int c = cnt[s];
-          float acc = 0.0f;
-          for (int r = 0; r < c; ++r) {
-            const size_t off = (size_t)(k >> 3) * A_CHUNK_BYTES + (size_t)(s * n + r) * 16 + (size_t)(k & 7) * 2;
-            float v = 0.0f;
+        if (!gsum) {
+          // generic row counts: mean over the state's rows of H1, read back from the A images
+          for (int i = tid; i < ts * h1d; i += NCREW) {
+            const int k = i % h1d, s = i / h1d;
+            const int c = cnt[s];
+            float acc = 0.0f;
+            for (int r = 0; r < c; ++r) {
+              const size_t off = (size_t)(k >> 3) * A_CHUNK_BYTES + (size_t)(s * n + r) * 16 + (size_t)(k & 7) * 2;
+              float v = 0.0f;
 #pragma unroll
-            for (int sp = 0; sp < NSPLIT; ++sp)
-              v += __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(A + (size_t)sp * Cfg<NSPLIT>::A_IMAGE + off));
-            acc += v;
+              for (int sp = 0; sp < NSPLIT; ++sp)
+                v += __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(A + (size_t)sp * Cfg<NSPLIT>::A_IMAGE + off));
+              acc += v;
+            }
+            GV[k * MAX_TS + s] = c > 0 ? acc / (float)c : 0.0f;
           }
-          GV[k * MAX_TS + s] = c > 0 ? acc / (float)c : 0.0f;
         }
         crew_sync();
         // thread -> one output column, 8 states: each weight is fetched once per 8 states
@@ -331,8 +400,25 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] = b;
           const float *wcol = P.wg + c;
-#pragma unroll 4
-          for (int k = 0; k < h1d; ++k) {
+          // the weights come from L2 (no L1 to speak of with 227 KB of shared memory in use): keep 20
+          // independent loads in flight per thread, the loop is latency-bound otherwise
+          constexpr int UK = 10;
+          int k = 0;
+          for (; k + UK <= h1d; k += UK) {
+            float wv[UK];
+#pragma unroll
+            for (int j = 0; j < UK; ++j) wv[j] = __ldg(wcol + (size_t)(k + j) * a1p);
+#pragma unroll
+            for (int j = 0; j < UK; ++j) {
+              const float4 g0 = *reinterpret_cast<const float4 *>(GV + (k + j) * MAX_TS + sh * 8);
+              const float4 g1 = *reinterpret_cast<const float4 *>(GV + (k + j) * MAX_TS + sh * 8 + 4);
+              acc[0] = fmaf(g0.x, wv[j], acc[0]); acc[1] = fmaf(g0.y, wv[j], acc[1]);
+              acc[2] = fmaf(g0.z, wv[j], acc[2]); acc[3] = fmaf(g0.w, wv[j], acc[3]);
+              acc[4] = fmaf(g1.x, wv[j], acc[4]); acc[5] = fmaf(g1.y, wv[j], acc[5]);
+              acc[6] = fmaf(g1.z, wv[j], acc[6]); acc[7] = fmaf(g1.w, wv[j], acc[7]);
+            }
+          }
+          for (; k < h1d; ++k) {
             const float wv = __ldg(wcol + (size_t)k * a1p);
             const float4 g0 = *reinterpret_cast<const float4 *>(GV + k * MAX_TS + sh * 8);
             const float4 g1 = *reinterpret_cast<const float4 *>(GV + k * MAX_TS + sh * 8 + 4);
@@ -355,7 +441,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
       // ---- T2 -> A; mlp2.2 -------------------------------------------------------------------------
       {
         const TcStage &S = P.st[ST_L2];
-        epi_to_a<NSPLIT>(tmem_row, cg, S.acc_col, S.np, P.bias[2], nullptr, true, A, row);
+        epi_to_a<NSPLIT, false>(tmem_row, cg, S.acc_col, S.np, P.bias[2], nullptr, true, A, row);
       }
       pipe.signal_a();
       pipe.wait_acc();
@@ -363,9 +449,10 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
       {
         const TcStage &S = P.st[ST_L4];
         const int s = min(row / n, ts - 1);
-        epi_to_a<NSPLIT>(tmem_row, cg, S.acc_col, S.np, P.zero_bias, GV + s * KMAX, true, A, row);
+        epi_to_a<NSPLIT, false>(tmem_row, cg, S.acc_col, S.np, P.zero_bias, GV + s * KMAX, true, A, row);
       }
       pipe.signal_a();
+      if (tile + gridDim.x < n_tiles) load_x(tile + gridDim.x);   // next tile's input, consumed after the tail
       pipe.wait_acc();
       // ---- attention.4 score, masked softmax, pooling (sarl.py:64-78) --------------------------------------
       {
@@ -463,6 +550,8 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
         pipe.commit_acc();
       }
     }
+  } else if (warp == NCREW / 32 + 1) {
+    if ((tid & 31) == 0) pipe.loader_loop();
   } else {
     const int row = ((warp & 3) << 5) | (tid & 31);
     const int cg = warp >> 2;
@@ -482,13 +571,13 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
       pipe.wait_acc();
       for (int h = 0; h < P.n_wide; ++h) {
         const TcStage &W = P.st[ST_L0A + h];
-        epi_to_a<NSPLIT>(tmem_row, cg, W.acc_col, W.np, P.bias[0] + W.n_lo, nullptr, true, A, row);
+        epi_to_a<NSPLIT, false>(tmem_row, cg, W.acc_col, W.np, P.bias[0] + W.n_lo, nullptr, true, A, row);
         pipe.signal_a();
         pipe.wait_acc();
       }
       {
         const TcStage &S = P.st[ST_L1A];
-        epi_to_a<NSPLIT>(tmem_row, cg, S.acc_col, S.np, P.bias[1], nullptr, true, A, row);
+        epi_to_a<NSPLIT, false>(tmem_row, cg, S.acc_col, S.np, P.bias[1], nullptr, true, A, row);
       }
       pipe.signal_a();
       pipe.wait_acc();
@@ -569,6 +658,12 @@ int launch_tc(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row
   if (ts > Cfg<NSPLIT>::MAX_TS) ts = Cfg<NSPLIT>::MAX_TS;
   p.ts = ts;
   p.joint = s->d_joint; p.jd = s->net.self_dim + s->net.l[3].out; p.self_dim = s->net.self_dim;
+  p.trace = nullptr;
+  if (getenv("EBC_TC_TRACE")) {
+    if (!s->d_trace) { cudaMalloc(&s->d_trace, 4096 * sizeof(long long)); }
+    cudaMemsetAsync(s->d_trace, 0, 4096 * sizeof(long long), stream);
+    p.trace = s->d_trace;
+  }
   TcMlp3Params q;
   q.prog = s->tc[NSPLIT == 1 ? 0 : 1].mlp3;
   q.joint = s->d_joint; q.values = values; q.n_states = n_states; q.jd = p.jd;
@@ -683,6 +778,7 @@ int ebc_tc_prepare(ebc_sim *s, const ebc_weights *w, int mode_index, int nsplit)
 
   // ---- upload ---------------------------------------------------------------------------------------
   const size_t n_e = pe.slab_off.size(), n_m = pm.slab_off.size();
+  if (n_e > (size_t)MAX_SLABS || n_m > (size_t)MAX_SLABS) return 1;
   const size_t bytes_total = pe.bytes.size() + pm.bytes.size() + fl.size() * 4 + (n_e + n_m) * 8 + 1024;
   uint8_t *d = nullptr;
   cudaError_t err = cudaMalloc(&d, bytes_total);
@@ -719,6 +815,8 @@ int ebc_tc_prepare(ebc_sim *s, const ebc_weights *w, int mode_index, int nsplit)
 }
 
 void ebc_tc_release(ebc_sim *s) {
+  if (s->d_trace) cudaFree(s->d_trace);
+  s->d_trace = nullptr;
   for (int i = 0; i < 2; ++i) {
     if (s->tc[i].slab) cudaFree(s->tc[i].slab);
     s->tc[i].slab = nullptr;

@@ -77,6 +77,7 @@ PROTOTYPES = {
     "ebc_orca_step": (c_i32, [SIM, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "ebc_transform": (c_i32, [SIM, vp, vp]),
     "ebc_reset": (c_i32, [SIM, ctypes.POINTER(EbcState), c_i32, vp, vp, vp]),
+    "ebc_debug_trace": (c_i32, [SIM, vp, c_i32]),
     "ebc_launch_count": (ctypes.c_int64, [SIM]),
 }
 

@@ -242,6 +242,10 @@ int ebc_transform(ebc_sim *sim, float *out, void *stream);
 int ebc_reset(ebc_sim *sim, const ebc_state *pool, int32_t pool_size, const int32_t *pool_index,
               const uint8_t *mask, void *stream);
 
+/* Diagnostics: with EBC_TC_TRACE=1 in the environment the tensor-core K4 kernel records clock64()
+ * stamps of CTA 0 (phase boundaries of its first tiles); this copies up to 4096 of them to the host. */
+int ebc_debug_trace(ebc_sim *sim, long long *out, int32_t n);
+
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t ebc_launch_count(const ebc_sim *sim);
 
