@@ -38,6 +38,9 @@ for p in (os.path.join(ROOT, "eb-cadrl_b200"), os.path.join(ROOT, "tests")):
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the committed
+# `ncu --set full` capture (profiles/); None until a capture of that mode exists
+ROOFLINE_TRAFFIC = {"fp32": 492.2e6, "tc_fp32": None, "tc_bf16": None}
 EPISODES_PER_GPU = 4096
 N_ACTIONS = 81
 METRIC = "agent_steps_per_sec"
@@ -188,6 +191,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--episodes", type=int, default=EPISODES_PER_GPU, help="episodes per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--value-mode", default="tc_fp32", choices=["fp32", "tc_fp32", "tc_bf16"],
+                    help="K4 arithmetic; tc_fp32 (tcgen05, fp32-accurate operand splitting) is the parity mode")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -218,6 +223,7 @@ def main():
     sim = BatchedSim(cfg, N, shape.H, shape.Smax, shape.Rmax, N_ACTIONS, device=dev)
     sim.set_actions(build_action_space(shape.robot_v_pref))
     sim.set_weights(weights)
+    sim.set_value_mode(args.value_mode)
     synth.load(sim, scenes)
     pool = sim.make_pool(scenes)
     n_rows = shape.H + shape.Smax
@@ -267,6 +273,23 @@ def main():
         for i, nm in enumerate(phase_names):
             phase_ms[nm] += m[i].elapsed_time(m[i + 1])
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- side measurement: K4 in the other tensor-core mode on the same states + argmax agreement ------
+    other = "tc_bf16" if args.value_mode != "tc_bf16" else "tc_fp32"
+    sim.orca(); sim.lookahead(); sim.value(); sim.select()
+    ref_arg = sim.argmax.clone()
+    sim.set_value_mode(other)
+    sim.value()
+    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    o0.record()
+    for _ in range(5):
+        sim.value()
+    o1.record()
+    sim.select()
+    torch.cuda.synchronize()
+    other_ms = o0.elapsed_time(o1) / 5
+    other_agree = float((sim.argmax == ref_arg).float().mean().item())
+    sim.set_value_mode(args.value_mode)
 
     # ---- e2e: the same step through the host-facing API (pinned host buffers) ------------
     h_pv = torch.empty_like(sim.hum_pv, device="cpu").pin_memory()
@@ -351,13 +374,22 @@ def main():
         "phase_ms_per_step": {k: v / args.steps for k, v in phase_ms.items()},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": "K4 value network (value_entity_kernel + value_mlp3_kernel), fp32 FFMA path",
+        "roofline": {"kernel": {"fp32": "K4 value network: value_entity_kernel + value_mlp3_kernel (fp32 FFMA)",
+                                "tc_fp32": "K4 value network: tc_entity_kernel<3> + tc_mlp3_kernel<3> (tcgen05, bf16x3 "
+                                           "operand splitting = 6 MMAs per product, fp32-accurate)",
+                                "tc_bf16": "K4 value network: tc_entity_kernel<1> + tc_mlp3_kernel<1> (tcgen05, bf16 operands)"
+                                }[args.value_mode],
                      "bound": "tensor", "achieved": achieved_tf, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
-                     "frac": achieved_tf / peaks["tensor_tflops"], "traffic": None,
+                     "frac": achieved_tf / peaks["tensor_tflops"], "traffic": ROOFLINE_TRAFFIC.get(args.value_mode),
                      "peak_source": peaks["source"],
-                     "note": "algorithmic FLOPs 2*(n*M_e+M_s) per (episode, action); this round's kernel is fp32 "
-                             "SIMT (argmax-parity mode), FP32-ALU roof 74 TFLOP/s -> frac_alu below",
-                     "frac_alu": achieved_tf / 74.0},
+                     "mma_issue_factor": {"fp32": 0, "tc_fp32": 6, "tc_bf16": 1}[args.value_mode],
+                     "note": "achieved = algorithmic FLOPs 2*(n*M_e+M_s) per (episode, action) / K4 time from CUDA events "
+                             "inside the timed region.  In tc_fp32 every product costs 6 bf16 MMAs (and the global half of "
+                             "attention.0 is hoisted to a per-state bias), so the tensor pipe executes ~5x the algorithmic "
+                             "FLOPs: tensor-pipe-equivalent fraction = frac * 6 * 205/245."},
+        "value_mode": args.value_mode,
+        "other_value_mode": {"mode": other, "k4_ms": other_ms, "achieved_tflops": fl / (other_ms / 1e3) / 1e12,
+                             "argmax_agreement_with_%s" % args.value_mode: other_agree},
         "sim_only": {"agent_steps_per_sec": total_eps * (H + 1) / sim_step_s, "ms_per_step": sim_step_s * 1e3,
                      "launches_per_step": 1,
                      "roofline": {"bound": "hbm", "achieved": sim_bytes / sim_step_s / 1e9, "peak": peaks["hbm_gbs"],

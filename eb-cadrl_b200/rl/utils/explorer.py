@@ -1,0 +1,146 @@
+"""Explorer (rl/utils/explorer.py:20-340, rl/utils/parallel_explorer.py:148-338): run k episodes, keep the
+reference's statistics and log lines, fill the replay memory.
+
+The reference runs one episode at a time (or 8 in a process pool); here the k episodes are one batch on the
+device (ebc.batched_env.BatchedEnv.run_episodes).  Memory semantics are kept: the sequential Explorer stores
+only success / collision episodes (explorer.py:82-92), the parallel one stores all of them
+(parallel_explorer.py:185-192) -> `store_all`; imitation learning uses discounted returns, RL uses the TD
+target r + gamma^(dt v_pref) V_target(s') with the terminal state's value = its reward (explorer.py:151-200).
+With torch.distributed initialised, every rank runs its slice of the seeds and the outcome counters are
+all-gathered before logging (the only collective of evaluation)."""
+import copy
+import logging
+
+import numpy as np
+import torch
+
+from ebc import abi
+
+_COLLISIONS = (abi.EV_COLLISION_ADULT, abi.EV_COLLISION_BICYCLE, abi.EV_COLLISION_CHILD, abi.EV_COLLISION_OBSTACLE)
+
+
+class Explorer(object):
+    PHASES = ["val", "test"]
+    ORCA_POLICY = "ORCA"
+
+    def __init__(self, env, robot=None, device="cuda:0", memory=None, gamma=None, target_policy=None):
+        self.env = env                      # ebc.batched_env.BatchedEnv
+        self.robot = robot if robot is not None else env.robot
+        self.device = device
+        self.memory = memory
+        self.gamma = gamma
+        self.target_policy = target_policy
+        self.target_model = None
+        self.metrics = {}
+
+    def update_target_model(self, target_model):
+        self.target_model = copy.deepcopy(target_model)
+
+    # ---- statistics (explorer.py:96-126, 214-340) ----------------------------------------------------------
+    def _gather(self, stats):
+        import torch.distributed as dist
+        arrays = {k: np.asarray(getattr(stats, k)) for k in ("event", "time", "steps", "cum_reward", "too_close",
+                                                             "min_dist_sum")}
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            out = [None] * dist.get_world_size()
+            dist.all_gather_object(out, arrays)
+            arrays = {k: np.concatenate([o[k] for o in out]) for k in arrays}
+        return arrays
+
+    def log_results(self, arrays, phase, episode=None, seeds=None, print_failure=False):
+        ev, n = arrays["event"], len(arrays["event"])
+        rate = lambda code: float((ev == code).sum()) / n  # noqa: E731
+        success = ev == abi.EV_REACH_GOAL
+        m = {
+            "success_rate": rate(abi.EV_REACH_GOAL), "collision_rate": 0.0,
+            "collision_rate_adult": rate(abi.EV_COLLISION_ADULT), "collision_rate_bicycle": rate(abi.EV_COLLISION_BICYCLE),
+            "collision_rate_child": rate(abi.EV_COLLISION_CHILD), "collision_rate_obstacle": rate(abi.EV_COLLISION_OBSTACLE),
+            "timeout_rate": rate(abi.EV_TIMEOUT),
+            "avg_nav_time": float(arrays["time"][success].mean()) if success.any() else float(self.env.time_limit),
+            "total_reward": float(arrays["cum_reward"].mean()) if n else 0.0,
+        }
+        extra = "" if episode is None else "in episode {} ".format(episode)
+        logging.info("{:<5} {}has success rate: {:.2f}, self.collision rate: {:.2f}, nav time: {:.2f}, total reward: {:.4f}".format(
+            phase.upper(), extra, m["success_rate"], m["collision_rate"], m["avg_nav_time"], m["total_reward"]))
+        logging.info("{:<5} {}self.collision rate adult: {:.2f}, self.collision rate bicycle: {:.2f},"
+                     "self.collision rate child: {:.2f}, self.collision rate obstacle: {:.4f}".format(
+                         phase.upper(), extra, m["collision_rate_adult"], m["collision_rate_bicycle"],
+                         m["collision_rate_child"], m["collision_rate_obstacle"]))
+        if phase in self.PHASES:
+            num_step = int(arrays["steps"].sum())
+            close = int(arrays["too_close"].sum())
+            m["danger_frequency"] = close / max(num_step, 1)
+            m["avg_min_dist"] = float(arrays["min_dist_sum"].sum() / close) if close else 0.0
+            logging.info("Frequency of being in danger: {:.2f} and average min separate distance in danger: {:.2f}".format(
+                m["danger_frequency"], m["avg_min_dist"]))
+        if print_failure and seeds is not None:
+            for name, code in (("Collision adult", abi.EV_COLLISION_ADULT), ("Collision bicycle", abi.EV_COLLISION_BICYCLE),
+                               ("Collision child", abi.EV_COLLISION_CHILD), ("Collision obstacle", abi.EV_COLLISION_OBSTACLE),
+                               ("Timeout", abi.EV_TIMEOUT)):
+                cases = [int(s) for s, e in zip(seeds, ev) if e == code]
+                logging.info("%s cases: %s", name, " ".join(str(c) for c in cases))
+        self.metrics = m
+        return m
+
+    # ---- episodes ----------------------------------------------------------------------------------------
+    def run_k_episodes(self, num_episodes, phase, update_memory=False, imitation_learning=False, episode=None,
+                       print_failure=False, seeds=None, epsilon=None, store_all=False, safety_space=0.0):
+        env = self.env
+        if seeds is None:
+            off = env.COUNTER_OFFSET[phase]
+            start = env.scene.case_counter[phase]
+            seeds = [off + start + i for i in range(num_episodes)]
+            env.scene.case_counter[phase] = (start + num_episodes) % env.scene.case_size[phase]
+        all_stats, done_seeds = [], []
+        for lo in range(0, len(seeds), env.N):
+            chunk = list(seeds[lo:lo + env.N])
+            pad = env.N - len(chunk)
+            stats, traj = env.run_episodes(phase, chunk + chunk[:1] * pad, epsilon=epsilon, record=update_memory,
+                                           imitation=imitation_learning, safety_space=safety_space)
+            keep = slice(0, len(chunk))
+            if update_memory:
+                self.update_memory(traj, stats, imitation_learning, store_all, keep)
+            for k in ("event", "time", "steps", "cum_reward", "too_close", "min_dist_sum"):
+                setattr(stats, k, getattr(stats, k)[keep])
+            all_stats.append(stats)
+            done_seeds += chunk
+        merged = type("S", (), {k: np.concatenate([getattr(s, k) for s in all_stats]) for k in (
+            "event", "time", "steps", "cum_reward", "too_close", "min_dist_sum")})()
+        arrays = self._gather(merged)
+        return self.log_results(arrays, phase, episode, done_seeds, print_failure)
+
+    @torch.no_grad()
+    def update_memory(self, traj, stats, imitation_learning=False, store_all=False, keep=slice(None)):
+        if self.memory is None or self.gamma is None:
+            raise ValueError("Memory or gamma value is not set!")
+        states, rewards, alive, rows = traj["states"], traj["rewards"], traj["alive"], traj["rows"]
+        T, N = rewards.shape
+        ev = torch.as_tensor(stats.event, device=rewards.device)
+        use = torch.zeros(N, dtype=torch.bool, device=rewards.device)
+        use[keep] = True
+        if not store_all:       # only success / collision episodes (explorer.py:82-92)
+            ok = ev == abi.EV_REACH_GOAL
+            for c in _COLLISIONS:
+                ok |= ev == c
+            use &= ok
+        gamma_bar = self.gamma ** (self.env.time_step * self.env.robot.v_pref)
+        if imitation_learning:
+            # value_i = sum_{t >= i} gamma_bar^(t - i) r_t  (explorer.py:159-173), one backward scan
+            values = torch.zeros_like(rewards)
+            run = torch.zeros(N, dtype=rewards.dtype, device=rewards.device)
+            for t in range(T - 1, -1, -1):
+                run = torch.where(alive[t], rewards[t] + gamma_bar * run, run)
+                values[t] = run
+        else:
+            # value_i = r_i + gamma_bar V_target(s_{i+1}); terminal: r_i  (explorer.py:174-186)
+            model = self.target_model.to(states.device)
+            values = rewards.clone()
+            for t in range(T - 1):
+                nxt = alive[t + 1]
+                if bool(nxt.any()):
+                    v = model(states[t + 1][nxt], rows[nxt]).reshape(-1).double()
+                    values[t, nxt] += gamma_bar * v
+        sel = alive & use[None]
+        t_idx, e_idx = sel.nonzero(as_tuple=True)
+        if len(t_idx):
+            self.memory.push_batch(states[t_idx, e_idx], rows[e_idx], values[t_idx, e_idx].float())

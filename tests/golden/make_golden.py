@@ -327,8 +327,42 @@ def scenes(out):
     print("  scenes.npz")
 
 
+def copy_configs(out):
+    """INI fixtures: the reference's own config files (data, key names verbatim) that the tests configure the
+    env / policy / trainer with on the GPU box, where /root/reference does not exist."""
+    import shutil
+    dst = os.path.join(out, "configs")
+    os.makedirs(dst, exist_ok=True)
+    for src, name in [
+        ("configs/test_configs/test_env_configs/env_adults_5.config", "env_adults_5.config"),
+        ("configs/test_configs/test_env_configs/env_adults_3_bikes_3_static_2.config", "env_adults_3_bikes_3_static_2.config"),
+        ("configs/test_configs/test_env_configs/env_adults_5_bikes_5_static_5.config", "env_adults_5_bikes_5_static_5.config"),
+        ("configs/test_configs/test_env_configs/env_adults_3_bikes_3_child_3_static_3_fast_train.config", "env_fast_train.config"),
+        ("configs/test_configs/test_policy_configs/policy.config", "policy.config"),
+        ("configs/test_configs/test_train_configs/test_train.config", "test_train.config"),
+        ("data/eb-cadrl/adults_8_bikes_8_child_8_static_3_35_sec_new_reward_fix_static.config", "env_ebcadrl.config"),
+        ("data/eb-cadrl/policy_x2_agent_type.config", "policy_ebcadrl.config"),
+        ("data/eb-cadrl/train_50k_8x.config", "train_50k_8x.config"),
+    ]:
+        shutil.copy(os.path.join(REF, src), os.path.join(dst, name))
+    print("  configs/: 9 INI fixtures")
+    # the reference's fixed test scenes (tests/test_scenes/test_collisions/*.json): golden inputs of its
+    # episode-outcome tests, replayed through our env API by tests/test_gpu_mirror.py
+    sdst = os.path.join(out, "scenes")
+    os.makedirs(sdst, exist_ok=True)
+    src_dir = os.path.join(REF, "tests", "test_scenes", "test_collisions")
+    for f in sorted(os.listdir(src_dir)):
+        shutil.copy(os.path.join(src_dir, f), os.path.join(sdst, f))
+    for cfgname in ("env_adults_5_bikes_0_static_5.config", "env_adults_5_child_5_static_5.config"):
+        shutil.copy(os.path.join(REF, "configs/test_configs/test_env_configs", cfgname), os.path.join(dst, cfgname))
+    print("  scenes/: %d JSON scenes" % len(os.listdir(sdst)))
+
+
 def main():
     out = HERE
+    if "--configs-only" in sys.argv:
+        copy_configs(out)
+        return
     POL = "configs/test_configs/test_policy_configs/policy.config"
     BASE_W = "model_weights/sarl_model_baseline.pth"
     EB_ENV = "data/eb-cadrl/adults_8_bikes_8_child_8_static_3_35_sec_new_reward_fix_static.config"
@@ -382,6 +416,7 @@ def main():
     e[1].safety_space = 0.15
     trace("trace_orca_robot_h10_seed5", *e, {"scene_number": 5}, 60, set(), out)
     scenes(out)
+    copy_configs(out)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,159 @@
+"""The reference's Python API (simulator.* / rl.* under the same names) driving the CUDA hot path.
+These read like the reference's own tests (tests/test_collisions.py, test_collisions_simulation.py,
+test_basic_simulation.py, test_basic_train.py).  Needs a B200."""
+import configparser
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle_backend as ob
+
+pytestmark = pytest.mark.gpu
+CFG = os.path.join(ob.GOLDEN, "configs")
+SCENES = os.path.join(ob.GOLDEN, "scenes")
+
+
+def test_collision_agent_with_robot_known_answers():
+    """tests/test_collisions.py:13-143 verbatim in spirit: Robot/Adult objects, ActionXY, expected booleans."""
+    from simulator.agents.agents import Adult
+    from simulator.agents.robot import Robot
+    from simulator.utils.action import ActionXY
+    from simulator.utils.collisions import compute_collision_agent_with_robot, point_to_segment_dist
+    cp = configparser.RawConfigParser()
+    cp.read(os.path.join(CFG, "env_adults_5_bikes_5_static_5.config"))
+    cases = [((0, 0), 1, (0, -2), 0.9, 0.07, (-1, -1), False), ((0, 0), 1, (0, -2), 0.9, 0.12, (-1, -1), True)]
+    import json
+    cases = json.load(open(os.path.join(ob.GOLDEN, "collisions_known_answers.json")))
+    for c in cases:
+        robot = Robot(cp, "robot")
+        robot.kinematics = "holonomic"
+        robot.set(c["robot_pos"][0], c["robot_pos"][1], 0, 0, 0, 0, np.pi / 2)
+        robot.radius = c["robot_radius"]
+        adult = Adult(cp, "adults")
+        adult.set(c["adult_pos"][0], c["adult_pos"][1], 0, 0, 0, 0, 0)
+        adult.radius = c["adult_radius"]
+        dmin, coll = compute_collision_agent_with_robot(adult, robot, ActionXY(*c["action"]), float("inf"), c["time_step"])
+        assert coll == c["collision"], c["name"]
+    assert abs(point_to_segment_dist(0, 0, 2, 0, 1, 1) - 1.0) < 1e-6
+    assert abs(point_to_segment_dist(0, 0, 2, 0, 3, 0) - 1.0) < 1e-6
+
+
+SCENE_RESULTS = [
+    ("env_adults_5_bikes_5_static_5.config", "collision_with_adult.json", "CollisionAdult"),
+    ("env_adults_5_bikes_5_static_5.config", "collision_with_bicycle.json", "CollisionBicycle"),
+    ("env_adults_5_bikes_5_static_5.config", "collision_with_static.json", "CollisionObstacle"),
+    ("env_adults_5_bikes_5_static_5.config", "no_collisions.json", "Reaching goal"),
+    ("env_adults_5_bikes_0_static_5.config", "bikes_0_collision_with_adult_1.json", "CollisionAdult"),
+    ("env_adults_5_bikes_0_static_5.config", "bikes_0_collision_with_adult_2.json", "CollisionAdult"),
+    ("env_adults_5_bikes_0_static_5.config", "bikes_0_no_collisions.json", "Reaching goal"),
+    ("env_adults_5_child_5_static_5.config", "collision_with_child.json", "CollisionChild"),
+]
+
+
+@pytest.mark.parametrize("cfg,scene,expected", SCENE_RESULTS)
+def test_collision_scenes_through_env_api(cfg, scene, expected):
+    """tests/test_collisions_simulation.py:42-69: linear robot, ORCA humans, fixed JSON scene -> Info class."""
+    from simulator.utils.test_utils import configure_env_policy_robot
+    env, policy, robot = configure_env_policy_robot(os.path.join(CFG, cfg), os.path.join(CFG, "policy.config"),
+                                                    policy="linear")
+    ob_, local_map = env.reset("test", load_scene_path=os.path.join(SCENES, scene))
+    done, steps = False, 0
+    while not done and steps < 500:
+        action = robot.act(ob_, local_map=local_map, env=env)
+        ob_, _, reward, done, info = env.step(action)
+        steps += 1
+    assert str(info) == expected, (scene, str(info))
+
+
+def test_basic_simulation_matches_reference_trace():
+    """tests/test_basic_simulation.py (SARL baseline, env_adults_5, test case 2) through our env/robot/policy
+    objects, compared step by step with the reference's own run (golden trace): same actions, same events,
+    same final 'Reaching goal' after 85 steps."""
+    from simulator.utils.info import ReachGoal
+    from simulator.utils.test_utils import configure_env_policy_robot
+    tr = ob.Trace("trace_cfg1_adults5_seed1002")
+    env, policy, robot = configure_env_policy_robot(os.path.join(CFG, "env_adults_5.config"),
+                                                    os.path.join(CFG, "policy.config"),
+                                                    os.path.join(ob.GOLDEN, "weights_sarl_baseline.npz"))
+    ob_, local_map = env.reset("test", test_case=2)
+    # same scene as the reference generated for seed 1002
+    assert np.allclose([[h.px, h.py] for h in env.scene.adults], tr.get(0, "hum_pv")[:, :2], atol=1e-6)
+    done, t, mismatched = False, 0, 0
+    while not done and t < 200:
+        action = robot.act(ob_, local_map=local_map, env=env)
+        ref = tr.get(t, "action")
+        if not np.allclose(list(action), ref, atol=1e-12):
+            mismatched += 1
+            assert tr.steps[t]["top2_gap"] is None or tr.steps[t]["top2_gap"] < 5e-4, (t, action, ref)
+            break        # trajectories legitimately diverge after a near-tie
+        assert np.allclose(policy.action_values, tr.get(t, "action_values"), atol=2e-4)
+        ob_, _, reward, done, info = env.step(action)
+        assert abs(reward - tr.steps[t]["reward"]) < 1e-5 and done == tr.steps[t]["done"]
+        assert np.allclose([[h.px, h.py, h.vx, h.vy] for h in env.scene.adults], tr.get(t, "after_hum_pv"), atol=1e-5)
+        t += 1
+    if not mismatched:
+        assert isinstance(info, ReachGoal) and t == tr.n_steps == 85 and abs(env.global_time - 21.25) < 1e-9
+
+
+def test_onestep_lookahead_does_not_mutate_and_matches_trace():
+    from simulator.utils.test_utils import configure_env_policy_robot
+    tr = ob.Trace("trace_cfg1_adults5_seed1002")
+    env, policy, robot = configure_env_policy_robot(os.path.join(CFG, "env_adults_5.config"),
+                                                    os.path.join(CFG, "policy.config"),
+                                                    os.path.join(ob.GOLDEN, "weights_sarl_baseline.npz"))
+    env.reset("test", test_case=2)
+    policy.build_action_space(robot.v_pref)
+    before = env.native.hum_pv.clone()
+    for a in (0, 7, 60):
+        ob_, reward, done, info = env.onestep_lookahead(policy.action_space[a])
+        assert abs(reward - tr.get(0, "la_reward")[a]) < 1e-5 and done == bool(tr.get(0, "la_done")[a])
+        nxt = np.array([[o.px, o.py, o.vx, o.vy] for o in ob_])
+        assert np.allclose(nxt, tr.get(0, "la_next")[a][:, :4], atol=1e-5)
+    assert torch.equal(env.native.hum_pv, before) and env.global_time == 0
+
+
+def test_batched_env_equals_single_env():
+    """BatchedEnv.run_episodes (N episodes at once) ends every episode like the N = 1 API loop does."""
+    from ebc.batched_env import BatchedEnv
+    from rl.policy.policy_factory import policy_factory
+    from simulator.utils.test_utils import configure_env_policy_robot
+    cp = configparser.RawConfigParser(); cp.read(os.path.join(CFG, "env_adults_5.config"))
+    pc = configparser.RawConfigParser(); pc.read(os.path.join(CFG, "policy.config"))
+    pol = policy_factory["sarl"]()
+    pol.configure(pc)
+    pol.get_model().load_state_dict({k: torch.as_tensor(v) for k, v in ob.load_weights("weights_sarl_baseline.npz").items()})
+    pol.set_phase("test"); pol.set_device("cuda:0")
+    seeds = [1000, 1001, 1002, 1003]
+    benv = BatchedEnv(cp, pol, len(seeds), "cuda:0")
+    stats, _ = benv.run_episodes("test", seeds)
+    env, policy, robot = configure_env_policy_robot(os.path.join(CFG, "env_adults_5.config"), os.path.join(CFG, "policy.config"),
+                                                    os.path.join(ob.GOLDEN, "weights_sarl_baseline.npz"))
+    for i, seed in enumerate(seeds):
+        ob_, lm = env.reset("test", scene_number=seed)
+        done, t = False, 0
+        while not done and t < 200:
+            ob_, _, r, done, info = env.step(robot.act(ob_, env=env))
+            t += 1
+        assert t == stats.steps[i] and str(info) == ["", "Too close", "Reaching goal", "CollisionAdult", "CollisionBicycle",
+                                                       "CollisionChild", "CollisionObstacle", "Timeout"][stats.event[i]]
+        assert abs(env.global_time - stats.time[i]) < 1e-9
+
+
+def test_basic_train(tmp_path):
+    """tests/test_basic_train.py:46-92: IL warm-up with the ORCA robot, RL iterations, checkpoints, no exception."""
+    from rl import train
+    out = str(tmp_path / "out")
+    episode = train.run_train(train.parse_arguments([
+        "--env_config", os.path.join(CFG, "env_fast_train.config"), "--policy", "sarl",
+        "--policy_config", os.path.join(CFG, "policy.config"), "--train_config", os.path.join(CFG, "test_train.config"),
+        "--output_dir", out, "--episodes_per_iter", "8"]))
+    assert episode >= 2
+    for f in ("il_model.pth", "output.log", "env.config", "policy.config", "train.config", "rl_model_%d.pth" % episode):
+        assert os.path.exists(os.path.join(out, f)), f
+    sd = torch.load(os.path.join(out, "rl_model_%d.pth" % episode))
+    assert set(sd) >= {"mlp1.0.weight", "mlp3.6.bias", "attention.4.weight"}
+    assert all(torch.isfinite(v).all() for v in sd.values())
+    log = open(os.path.join(out, "output.log")).read()
+    assert "TRAIN" in log and "has success rate" in log

@@ -1,0 +1,147 @@
+"""Host-side mirror of the reference API: CPU-only checks (no compute on the device)."""
+import configparser
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import oracle_backend as ob
+
+CFG = os.path.join(ob.GOLDEN, "configs")
+
+
+def read(name):
+    cp = configparser.RawConfigParser()
+    assert cp.read(os.path.join(CFG, name))
+    return cp
+
+
+@pytest.mark.parametrize("tag,cfg", [("adults5", "env_adults_5.config"), ("ebcadrl", "env_ebcadrl.config")])
+def test_scene_generator_replays_reference_rng(tag, cfg):
+    """Same seed -> same agents, static discs and occupancy grid as the reference (tests/golden/scenes.npz)."""
+    from simulator.agents.robot import Robot
+    from simulator.scene.scene_generator import SceneGenerator
+    z = np.load(os.path.join(ob.GOLDEN, "scenes.npz"))
+    cp = read(cfg)
+    sg = SceneGenerator(cp)
+    rb = Robot(cp, "robot")
+    rb.policy = type("P", (), dict(multiagent_training=True, name="x", kinematics="holonomic"))()
+    sg.set_robot(rb)
+    for seed in (1002, 1003, 1000000):
+        rb.set(0, -sg.circle_radius, 0, sg.circle_radius, 0, 0, np.pi / 2)
+        sg.generate_random_scene({"test": 1000, "train": 2000, "val": 0}, "test", scene_number=seed)
+        hs = sg.adults + sg.bicycles + sg.children
+        assert np.array_equal(np.array([[h.px, h.py, h.vx, h.vy] for h in hs]), z["%s_%d_hum_pv" % (tag, seed)])
+        assert np.array_equal(np.array([[h.gx, h.gy, h.v_pref, h.radius] for h in hs]), z["%s_%d_hum_gr" % (tag, seed)])
+        assert np.array_equal(np.array([int(h.agent_type) for h in hs], np.uint8), z["%s_%d_hum_type" % (tag, seed)])
+        st = np.array([[s.px, s.py, s.radius, 0.0] for s in sg.static_obstacles_as_pedestrians]).reshape(-1, 4)
+        assert np.array_equal(st, z["%s_%d_stat" % (tag, seed)])
+        assert np.array_equal(np.packbits((sg.map == 0).astype(np.uint8), axis=None), z["%s_%d_map_zero" % (tag, seed)])
+
+
+def test_scene_save_load_round_trip(tmp_path):
+    """tests/test_save_load_map.py of the reference: scene.map identical after save_scene -> load_scene."""
+    from simulator.agents.robot import Robot
+    from simulator.scene.scene_generator import SceneGenerator
+    cp = read("env_adults_3_bikes_3_static_2.config")
+    sg = SceneGenerator(cp)
+    rb = Robot(cp, "robot")
+    rb.policy = type("P", (), dict(multiagent_training=True, name="x", kinematics="holonomic"))()
+    rb.set(0, -sg.circle_radius, 0, sg.circle_radius, 0, 0, np.pi / 2)
+    sg.set_robot(rb)
+    path = str(tmp_path / "scene.json")
+    sg.generate_random_scene({"test": 1000, "train": 2000, "val": 0}, "test", save_scene_path=path, scene_number=5)
+    grid, discs = sg.map.copy(), [(s.px, s.py, s.radius) for s in sg.static_obstacles_as_pedestrians]
+    agents = [(a.px, a.py, a.gx, a.gy) for a in sg.adults + sg.bicycles]
+    sg.load_scene("test", path)
+    assert np.array_equal(sg.map, grid)
+    assert discs == [(s.px, s.py, s.radius) for s in sg.static_obstacles_as_pedestrians]
+    assert agents == [(a.px, a.py, a.gx, a.gy) for a in sg.adults + sg.bicycles]
+
+
+def test_value_network_state_dict_and_masking():
+    """Shipped state_dicts load unchanged; zero-padded rows + row_count reproduce the unpadded forward."""
+    from rl.policy.policy_factory import policy_factory
+    pol = policy_factory["sarl"]()
+    pol.configure(read("policy_ebcadrl.config"))
+    sd = {k: torch.as_tensor(v) for k, v in ob.load_weights("weights_ebcadrl.npz").items()}
+    pol.get_model().load_state_dict(sd)
+    assert sum(p.numel() for p in pol.get_model().parameters()) == 379202
+    x = torch.randn(3, 7, 17)
+    pad = torch.cat([x, torch.zeros(3, 5, 17)], 1)
+    a = pol.get_model()(x)
+    b = pol.get_model()(pad, torch.tensor([7, 7, 7]))
+    assert torch.allclose(a, b, atol=1e-6)
+    with pytest.raises(NotImplementedError):
+        policy_factory["lstm_rl"]()
+
+
+def test_info_and_state_layout():
+    from simulator.utils import info
+    from simulator.utils.state import FullState, ObservableState
+    row = FullState(1, 2, 3, 4, 5, 6, 7, 8, 9) + ObservableState(10, 11, 12, 13, 14, 2)
+    assert row == (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 2)       # state.py:19-30,65-66
+    d = info.from_code(1, 3.0, (0.5, 0.15, float("inf")), (0.1, 0.2, 0.2))
+    assert isinstance(d, info.Danger) and d.min_dist == 0.15 and str(d) == "Too close"
+    assert str(info.from_code(2, 0.1, (1, 1, 1))) == "Reaching goal"
+    assert info.from_code(0, 0.0, (1, 2, 3)).dist_to_goal is None
+
+
+def _rank_main(rank, world, port, tmp):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from rl.policy.policy_factory import policy_factory
+    from rl.utils.explorer import Explorer
+    from rl.utils.memory import ReplayMemory
+    from rl.utils.trainer import Trainer
+    torch.manual_seed(0)
+    pol = policy_factory["sarl"]()
+    pol.configure(read("policy.config"))
+    model = pol.get_model()
+    mem = ReplayMemory(64, device="cpu")
+    g = torch.Generator().manual_seed(100 + rank)             # every rank owns a different replay shard
+    mem.push_batch(torch.randn(40, 5, 13, generator=g), torch.full((40,), 5), torch.randn(40, generator=g))
+    tr = Trainer(model, mem, "cpu", 8, policy=pol)
+    tr.set_optimizer(0.01)
+    tr.optimize_batch(3)
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    out = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(out, flat)
+    same = all(torch.equal(out[0], o) for o in out)            # grad all-reduce keeps the replicas identical
+    # episode statistics: rank-local arrays are gathered before logging
+    ex = Explorer(type("E", (), dict(time_limit=25, N=1))(), robot=object(), device="cpu")
+    stats = type("S", (), dict(event=np.array([2, 3]) if rank == 0 else np.array([2, 7]), time=np.array([5.0, 6.0]),
+                               steps=np.array([20, 24]), cum_reward=np.array([0.5, -0.2]), too_close=np.array([1, 0]),
+                               min_dist_sum=np.array([0.1, 0.0])))()
+    arrays = ex._gather(stats)
+    m = ex.log_results(arrays, "test")
+    torch.save({"same": same, "version": pol.weights_version, "n": len(arrays["event"]), "sr": m["success_rate"]},
+               os.path.join(tmp, "r%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_training_and_stats(tmp_path):
+    """world_size 2 on CPU: the N > 1 host logic (gradient all-reduce, statistics gather)."""
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_rank_main, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        d = torch.load(os.path.join(str(tmp_path), "r%d.pt" % r))
+        assert d["same"] and d["version"] == 3 and d["n"] == 4 and d["sr"] == 0.5
+
+
+def test_episode_sharding_is_independent_of_world_size():
+    """Synthetic scenes are keyed by the global episode id: any split over ranks gives the same episodes."""
+    from ebc import synth
+    whole = synth.generate(synth.CFG2, np.arange(64))
+    for world in (2, 4, 8):
+        per = 64 // world
+        parts = [synth.generate(synth.CFG2, np.arange(r * per, (r + 1) * per)) for r in range(world)]
+        for k in whole:
+            assert np.array_equal(np.concatenate([p[k] for p in parts]), whole[k]), (world, k)
