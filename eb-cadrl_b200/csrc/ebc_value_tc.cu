@@ -74,17 +74,20 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // Ring of weight slabs + the MMA-issuing thread's cursor; barriers shared with the crew.
 template <int NSPLIT>
 struct Pipe {
-  uint64_t *full, *empty, *acc_bar, *a_bar;
+  uint64_t *full, *empty, *acc_bar, *a_bar, *kbar;   // kbar[b]: k-step b of the A operand is written
   uint8_t *wbuf;
   const uint8_t *wpack;      // packed weights (global)
   int n_stage_slabs;         // slabs per tile
   const uint2 *tab;          // shared memory: (byte offset, bytes) of each slab of the per-tile sequence
   long long consumed, total; // running slab index / slab count over all tiles of this CTA
-  uint32_t acc_phase, a_phase;
+  uint32_t acc_phase, a_phase, k_phase;   // k_phase: one parity bit per kbar (MMA thread)
   long long *trace;          // optional clock64() trace of CTA 0's crew thread 0 (EBC_TC_TRACE=1)
   int trace_pos;
   __device__ __forceinline__ void stamp() {
-    if (trace && threadIdx.x == 0 && blockIdx.x == 0 && trace_pos < 4096) trace[trace_pos++] = clock64();
+    if (trace && threadIdx.x == 0 && blockIdx.x == 0 && trace_pos < 2048) trace[trace_pos++] = clock64();
+  }
+  __device__ __forceinline__ void stamp_mma() {   // MMA thread's own stamps live in the upper half
+    if (trace && blockIdx.x == 0 && trace_pos < 2048) trace[2048 + trace_pos++] = clock64();
   }
 
   // ---- loader thread: streams every slab of every tile of this CTA through the ring ---------------------
@@ -105,11 +108,19 @@ struct Pipe {
     a_phase ^= 1u;
     tc_fence_after();
   }
-  __device__ void mma_stage(const TcStage &S, uint32_t a_smem, uint32_t tmem_base) {
+  // pipelined: the crew is still writing the A operand; k-step ks is issued as soon as its two k-chunks
+  // (one 16-column block of the previous stage's epilogue) have been stored and fenced by all 128 rows.
+  __device__ void mma_stage(const TcStage &S, uint32_t a_smem, uint32_t tmem_base, bool pipelined = false) {
     constexpr int ST = Cfg<NSPLIT>::STAGES;
     const uint32_t idesc = make_idesc_bf16(TILE_M, S.np);
     const uint32_t d = tmem_base + S.acc_col;
     for (int ks = 0; ks < S.ksteps; ++ks) {
+      if (pipelined) {
+        mbar_wait(&kbar[ks], (k_phase >> ks) & 1u);
+        k_phase ^= 1u << ks;
+        tc_fence_after();
+        if (ks == 0 || ks == S.ksteps - 1) stamp_mma();
+      }
       const int st = (int)(consumed % ST);
       const uint32_t ph = (uint32_t)((consumed / ST) & 1);
       mbar_wait(&full[st], ph);
@@ -151,7 +162,8 @@ struct Pipe {
 template <int NSPLIT, bool GSUM>
 __device__ __forceinline__ void epi_to_a(uint32_t tmem_row, int cg, int col0, int ncols, const float *__restrict__ bias,
                                          const float *gv_row, bool relu, uint8_t *a_base, int row,
-                                         int n = 1, int row_cnt = 0, float *g_out = nullptr, int g_ld = 0) {
+                                         uint64_t *kbar = nullptr, int n = 1, int row_cnt = 0, float *g_out = nullptr,
+                                         int g_ld = 0) {
   for (int c = 16 * cg; c < ncols; c += 16 * NCG) {
     float v[16];
     tmem_ld16(tmem_row + col0 + c, v);
@@ -165,6 +177,11 @@ __device__ __forceinline__ void epi_to_a(uint32_t tmem_row, int cg, int col0, in
     for (int h = 0; h < 2; ++h) {
       const float u[8] = {v[8 * h], v[8 * h + 1], v[8 * h + 2], v[8 * h + 3], v[8 * h + 4], v[8 * h + 5], v[8 * h + 6], v[8 * h + 7]};
       store_a8<NSPLIT>(a_base, Cfg<NSPLIT>::A_IMAGE, row, c + 8 * h, u);
+    }
+    if (kbar) {               // this block is k-step c/16 of the next stage: hand it to the MMA warp now
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&kbar[c >> 4]);
     }
     if (GSUM) {
       const int r_in = row % n;                 // row index inside its state
@@ -228,6 +245,7 @@ __device__ __forceinline__ void pipe_init(Pipe<NSPLIT> &pipe, uint8_t *smem, con
   constexpr int ST = Cfg<NSPLIT>::STAGES;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
   pipe.full = bars; pipe.empty = bars + ST; pipe.acc_bar = bars + 2 * ST; pipe.a_bar = bars + 2 * ST + 1;
+  pipe.kbar = bars + 2 * ST + 2; pipe.k_phase = 0;
   pipe.wbuf = smem + L.w; pipe.wpack = P.wpack;
   pipe.n_stage_slabs = P.n_slabs;
   uint2 *tab = reinterpret_cast<uint2 *>(smem + L.tab);
@@ -240,6 +258,7 @@ __device__ __forceinline__ void pipe_init(Pipe<NSPLIT> &pipe, uint8_t *smem, con
     for (int i = 0; i < ST; ++i) { mbar_init(&pipe.full[i], 1); mbar_init(&pipe.empty[i], 1); }
     mbar_init(pipe.acc_bar, 1);
     mbar_init(pipe.a_bar, NCREW);
+    for (int i = 0; i < KMAX / 16; ++i) mbar_init(&pipe.kbar[i], TILE_M);
     fence_barrier_init();
   }
 }
@@ -289,13 +308,11 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
         for (int h = 0; h < P.n_wide; ++h) pipe.mma_stage(P.st[ST_L0A + h], a_smem, tmem_base);
         pipe.commit_acc();
         for (int h = 0; h < P.n_wide; ++h) {
-          pipe.wait_a();
-          pipe.mma_stage(P.st[ST_L1A + h], a_smem, tmem_base);
+          pipe.mma_stage(P.st[ST_L1A + h], a_smem, tmem_base, true);   // chases the wide-half epilogue
           pipe.commit_acc();
         }
-        pipe.wait_a();
-        pipe.mma_stage(P.st[ST_L2], a_smem, tmem_base);
-        pipe.mma_stage(P.st[ST_L4], a_smem, tmem_base);
+        pipe.mma_stage(P.st[ST_L2], a_smem, tmem_base, true);          // chases the H1 epilogue
+        pipe.mma_stage(P.st[ST_L4], a_smem, tmem_base);                // H1 fully written and its accumulator read
         pipe.commit_acc();
         pipe.wait_a();
         pipe.mma_stage(P.st[ST_L3], a_smem, tmem_base);
@@ -353,8 +370,8 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
       pipe.wait_acc();
       for (int h = 0; h < P.n_wide; ++h) {
         const TcStage &W = P.st[ST_L0A + h];
-        epi_to_a<NSPLIT, false>(tmem_row, cg, W.acc_col, W.np, P.bias[0] + W.n_lo, nullptr, true, A, row);
-        pipe.signal_a();
+        epi_to_a<NSPLIT, false>(tmem_row, cg, W.acc_col, W.np, P.bias[0] + W.n_lo, nullptr, true, A, row, pipe.kbar);
+        pipe.stamp();
         pipe.wait_acc();
       }
       // ---- H1 -> A; mlp2.0 and attention.0 (local half) share it -------------------------------------
@@ -364,12 +381,13 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
         if (gsum) {
           crew_sync();   // cnt[] of this tile is visible
           const int st_of_row = min(row / n, ts - 1);
-          epi_to_a<NSPLIT, true>(tmem_row, cg, S.acc_col, S.np, P.bias[1], nullptr, true, A, row, n, cnt[st_of_row], GV, MAX_TS);
+          epi_to_a<NSPLIT, true>(tmem_row, cg, S.acc_col, S.np, P.bias[1], nullptr, true, A, row, pipe.kbar, n,
+                                 cnt[st_of_row], GV, MAX_TS);
         } else {
-          epi_to_a<NSPLIT, false>(tmem_row, cg, S.acc_col, S.np, P.bias[1], nullptr, true, A, row);
+          epi_to_a<NSPLIT, false>(tmem_row, cg, S.acc_col, S.np, P.bias[1], nullptr, true, A, row, pipe.kbar);
         }
       }
-      pipe.signal_a();
+      pipe.stamp();
       // while those MMAs run: GV = attention.0.bias + W_att0[:, h1:] . G in place   (sarl.py:51-63)
       crew_sync();   // every crew thread's H1 stores, G partials and cnt are visible
       if (P.with_global) {
@@ -461,44 +479,90 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
       }
       crew_sync();
       float *WT = SC + NCG * TILE_M;   // softmax weight per row
-      if (tid < ts) {
-        const int c = cnt[tid];
-        float sum = 0.0f;
-        for (int r = 0; r < c; ++r) {
-          const int rr = tid * n + r;
-          const float sc = ((SC[rr] + SC[TILE_M + rr]) + (SC[2 * TILE_M + rr] + SC[3 * TILE_M + rr])) + P.b6;
-          const float e = (sc != 0.0f) ? expf(sc) : 0.0f;
-          WT[rr] = e;
-          sum += e;
-        }
-        for (int r = 0; r < n; ++r) WT[tid * n + r] = (r < c) ? WT[tid * n + r] / sum : 0.0f;
-      }
-      crew_sync();
-      // weighted H2 rows -> scratch (the A region is free: all MMAs that read it have completed)
-      float *PS = reinterpret_cast<float *>(A);
-      {
-        const float wrow = (row < ts * n) ? WT[row] : 0.0f;
+      if (n == 16) {
+        // a state = 16 aligned lanes of this warp: softmax and pooling stay in registers (shuffles), the
+        // pooled feature goes straight to the joint row -- no scratch, no further block synchronisation
+        const int lane = tid & 31, st_of_row = row >> 4;
+        const int c_real = cnt[min(st_of_row, ts - 1)];
+        const float sc = ((SC[row] + SC[TILE_M + row]) + (SC[2 * TILE_M + row] + SC[3 * TILE_M + row])) + P.b6;
+        const bool real = st_of_row < ns && (row & 15) < c_real;
+        float e = (real && sc != 0.0f) ? expf(sc) : 0.0f;
+        float sum = e;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float wrow = e / sum;          // NaN like the reference when every score is exactly 0
         const TcStage &S = P.st[ST_L3];
         for (int c = 16 * cg; c < S.np; c += 16 * NCG) {
           float v[16];
           tmem_ld16(tmem_row + S.acc_col + c, v);
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (c + i < h2d) PS[(c + i) * PS_LD + row] = (v[i] + __ldg(P.bias[3] + c + i)) * wrow;
+          for (int i = 0; i < 16; ++i) v[i] = real ? (v[i] + __ldg(P.bias[3] + c + i)) * wrow : 0.0f;
+          float w8[8], w4[4], w2[2];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float send = (lane & 8) ? v[i] : v[i + 8], keep = (lane & 8) ? v[i + 8] : v[i];
+            w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float send = (lane & 4) ? w8[i] : w8[i + 4], keep = (lane & 4) ? w8[i + 4] : w8[i];
+            w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const float send = (lane & 2) ? w4[i] : w4[i + 2], keep = (lane & 2) ? w4[i + 2] : w4[i];
+            w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+          }
+          const float send = (lane & 1) ? w2[0] : w2[1], keep = (lane & 1) ? w2[1] : w2[0];
+          const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+          const int col = c + (lane & 15);
+          if (st_of_row < ns && col < h2d) p.joint[(size_t)(s0 + st_of_row) * p.jd + p.self_dim + col] = tot;
+        }
+        if (tid < ns * p.self_dim) {
+          const int s = tid / p.self_dim, k = tid % p.self_dim;
+          p.joint[(size_t)(s0 + s) * p.jd + k] = XS[s * 8 + k];
+        }
+      } else {
+        if (tid < ts) {
+          const int c = cnt[tid];
+          float sum = 0.0f;
+          for (int r = 0; r < c; ++r) {
+            const int rr = tid * n + r;
+            const float sc = ((SC[rr] + SC[TILE_M + rr]) + (SC[2 * TILE_M + rr] + SC[3 * TILE_M + rr])) + P.b6;
+            const float e = (sc != 0.0f) ? expf(sc) : 0.0f;
+            WT[rr] = e;
+            sum += e;
+          }
+          for (int r = 0; r < n; ++r) WT[tid * n + r] = (r < c) ? WT[tid * n + r] / sum : 0.0f;
+        }
+        crew_sync();
+        // weighted H2 rows -> scratch (the A region is free: all MMAs that read it have completed)
+        float *PS = reinterpret_cast<float *>(A);
+        {
+          const float wrow = (row < ts * n) ? WT[row] : 0.0f;
+          const TcStage &S = P.st[ST_L3];
+          for (int c = 16 * cg; c < S.np; c += 16 * NCG) {
+            float v[16];
+            tmem_ld16(tmem_row + S.acc_col + c, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c + i < h2d) PS[(c + i) * PS_LD + row] = (v[i] + __ldg(P.bias[3] + c + i)) * wrow;
+          }
+        }
+        crew_sync();
+        for (int i = tid; i < ns * p.jd; i += NCREW) {
+          const int s = i / p.jd, k = i % p.jd;
+          float v;
+          if (k < p.self_dim) v = XS[s * 8 + k];
+          else {
+            v = 0.0f;
+            const int c = cnt[s], col = k - p.self_dim;
+            for (int r = 0; r < c; ++r) v += PS[col * PS_LD + s * n + r];
+          }
+          p.joint[(size_t)(s0 + s) * p.jd + k] = v;
         }
       }
-      crew_sync();
-      for (int i = tid; i < ns * p.jd; i += NCREW) {
-        const int s = i / p.jd, k = i % p.jd;
-        float v;
-        if (k < p.self_dim) v = XS[s * 8 + k];
-        else {
-          v = 0.0f;
-          const int c = cnt[s], col = k - p.self_dim;
-          for (int r = 0; r < c; ++r) v += PS[col * PS_LD + s * n + r];
-        }
-        p.joint[(size_t)(s0 + s) * p.jd + k] = v;
-      }
+      tc_fence_before();
       crew_sync();   // PS (aliases A) / SC / XS / cnt are rewritten by the next tile
     }
   }
@@ -541,12 +605,10 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
         for (int h = 0; h < P.n_wide; ++h) pipe.mma_stage(P.st[ST_L0A + h], a_smem, tmem_base);
         pipe.commit_acc();
         for (int h = 0; h < P.n_wide; ++h) {
-          pipe.wait_a();
-          pipe.mma_stage(P.st[ST_L1A + h], a_smem, tmem_base);
+          pipe.mma_stage(P.st[ST_L1A + h], a_smem, tmem_base, true);
           pipe.commit_acc();
         }
-        pipe.wait_a();
-        pipe.mma_stage(P.st[ST_L2], a_smem, tmem_base);
+        pipe.mma_stage(P.st[ST_L2], a_smem, tmem_base, true);
         pipe.commit_acc();
       }
     }
@@ -571,15 +633,13 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
       pipe.wait_acc();
       for (int h = 0; h < P.n_wide; ++h) {
         const TcStage &W = P.st[ST_L0A + h];
-        epi_to_a<NSPLIT, false>(tmem_row, cg, W.acc_col, W.np, P.bias[0] + W.n_lo, nullptr, true, A, row);
-        pipe.signal_a();
+        epi_to_a<NSPLIT, false>(tmem_row, cg, W.acc_col, W.np, P.bias[0] + W.n_lo, nullptr, true, A, row, pipe.kbar);
         pipe.wait_acc();
       }
       {
         const TcStage &S = P.st[ST_L1A];
-        epi_to_a<NSPLIT, false>(tmem_row, cg, S.acc_col, S.np, P.bias[1], nullptr, true, A, row);
+        epi_to_a<NSPLIT, false>(tmem_row, cg, S.acc_col, S.np, P.bias[1], nullptr, true, A, row, pipe.kbar);
       }
-      pipe.signal_a();
       pipe.wait_acc();
       {
         const TcStage &S = P.st[ST_L2];
