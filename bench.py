@@ -40,7 +40,7 @@ import torch  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the committed
 # `ncu --set full` capture (profiles/); None until a capture of that mode exists
-ROOFLINE_TRAFFIC = {"fp32": 492.2e6, "tc_fp32": 490.3e6, "tc_bf16": None}
+ROOFLINE_TRAFFIC = {"fp32": 492.2e6, "tc_fp32": 490.3e6, "tc_fp16x2": None, "tc_bf16": None}
 EPISODES_PER_GPU = 4096
 N_ACTIONS = 81
 METRIC = "agent_steps_per_sec"
@@ -191,8 +191,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--episodes", type=int, default=EPISODES_PER_GPU, help="episodes per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--value-mode", default="tc_fp32", choices=["fp32", "tc_fp32", "tc_bf16"],
-                    help="K4 arithmetic; tc_fp32 (tcgen05, fp32-accurate operand splitting) is the parity mode")
+    ap.add_argument("--value-mode", default="tc_fp16x2", choices=["fp32", "tc_fp32", "tc_fp16x2", "tc_bf16"],
+                    help="K4 arithmetic; tc_fp16x2 (tcgen05, fp32-accurate operand splitting) is the parity mode")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -275,7 +275,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- side measurement: K4 in the other tensor-core mode on the same states + argmax agreement ------
-    other = "tc_bf16" if args.value_mode != "tc_bf16" else "tc_fp32"
+    other = "tc_bf16" if args.value_mode != "tc_bf16" else "tc_fp16x2"
     sim.orca(); sim.lookahead(); sim.value(); sim.select()
     ref_arg = sim.argmax.clone()
     sim.set_value_mode(other)
@@ -377,16 +377,18 @@ def main():
         "roofline": {"kernel": {"fp32": "K4 value network: value_entity_kernel + value_mlp3_kernel (fp32 FFMA)",
                                 "tc_fp32": "K4 value network: tc_entity_kernel<3> + tc_mlp3_kernel<3> (tcgen05, bf16x3 "
                                            "operand splitting = 6 MMAs per product, fp32-accurate)",
+                                "tc_fp16x2": "K4 value network: tc_entity_kernel<2> + tc_mlp3_kernel<2> (tcgen05, fp16x2 "
+                                             "operand splitting = 3 MMAs per product, fp32-accurate)",
                                 "tc_bf16": "K4 value network: tc_entity_kernel<1> + tc_mlp3_kernel<1> (tcgen05, bf16 operands)"
                                 }[args.value_mode],
                      "bound": "tensor", "achieved": achieved_tf, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
                      "frac": achieved_tf / peaks["tensor_tflops"], "traffic": ROOFLINE_TRAFFIC.get(args.value_mode),
                      "peak_source": peaks["source"],
-                     "mma_issue_factor": {"fp32": 0, "tc_fp32": 6, "tc_bf16": 1}[args.value_mode],
+                     "mma_issue_factor": {"fp32": 0, "tc_fp32": 6, "tc_fp16x2": 3, "tc_bf16": 1}[args.value_mode],
                      "note": "achieved = algorithmic FLOPs 2*(n*M_e+M_s) per (episode, action) / K4 time from CUDA events "
-                             "inside the timed region.  In tc_fp32 every product costs 6 bf16 MMAs (and the global half of "
-                             "attention.0 is hoisted to a per-state bias), so the tensor pipe executes ~5x the algorithmic "
-                             "FLOPs: tensor-pipe-equivalent fraction = frac * 6 * 205/245."},
+                             "inside the timed region.  The fp32-accurate modes issue mma_issue_factor fp16/bf16 MMAs per "
+                             "product, so the tensor pipe executes that multiple of the algorithmic FLOPs: "
+                             "tensor-pipe-equivalent fraction ~ frac * mma_issue_factor."},
         "value_mode": args.value_mode,
         "other_value_mode": {"mode": other, "k4_ms": other_ms, "achieved_tflops": fl / (other_ms / 1e3) / 1e12,
                              "argmax_agreement_with_%s" % args.value_mode: other_agree},

@@ -17,6 +17,8 @@ int ebc_fail(ebc_sim *s, int code, const char *fmt, ...) {
   return code;
 }
 
+static int ebc_tc_index(int mode) { return mode == EBC_VALUE_TC_BF16 ? 0 : (mode == EBC_VALUE_TC_FP16X2 ? 1 : 2); }
+
 int ebc_check_launch(ebc_sim *s, const char *what) {
   const cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return ebc_fail(s, EBC_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
@@ -106,19 +108,20 @@ int ebc_set_weights(ebc_sim *s, const ebc_weights *w) {
   cudaSetDevice(s->device);
   int rc = ebc_value_prepare(s, w);
   if (rc) return rc;
-  // tensor-core programs: [0] bf16, [1] bf16x3.  A shape that does not fit keeps the FFMA path.
-  const int r0 = ebc_tc_prepare(s, w, 0, 1), r1 = ebc_tc_prepare(s, w, 1, 3);
+  // tensor-core programs: [0] bf16, [1] fp16x2 (default), [2] bf16x3.  A shape that does not fit keeps the FFMA path.
+  const int r0 = ebc_tc_prepare(s, w, 0, 1), r1 = ebc_tc_prepare(s, w, 1, 2), r2 = ebc_tc_prepare(s, w, 2, 3);
   if (r0 < 0) return r0;
   if (r1 < 0) return r1;
-  if (r0 || r1) { s->tc[0].ready = s->tc[1].ready = 0; s->value_mode = EBC_VALUE_FP32; }
-  else if (!s->value_mode_forced) s->value_mode = EBC_VALUE_TC_FP32;
+  if (r2 < 0) return r2;
+  if (r0 || r1 || r2) { s->tc[0].ready = s->tc[1].ready = s->tc[2].ready = 0; s->value_mode = EBC_VALUE_FP32; }
+  else if (!s->value_mode_forced) s->value_mode = EBC_VALUE_TC_FP16X2;
   return EBC_OK;
 }
 
 int ebc_set_value_mode(ebc_sim *s, int32_t mode) {
   if (!s) return EBC_ERR_INVALID;
-  if (mode < EBC_VALUE_FP32 || mode > EBC_VALUE_TC_BF16) return ebc_fail(s, EBC_ERR_INVALID, "ebc_set_value_mode: unknown mode %d", mode);
-  if (mode != EBC_VALUE_FP32 && s->have_weights && !s->tc[mode == EBC_VALUE_TC_BF16 ? 0 : 1].ready)
+  if (mode < EBC_VALUE_FP32 || mode > EBC_VALUE_TC_FP16X2) return ebc_fail(s, EBC_ERR_INVALID, "ebc_set_value_mode: unknown mode %d", mode);
+  if (mode != EBC_VALUE_FP32 && s->have_weights && !s->tc[ebc_tc_index(mode)].ready)
     return ebc_fail(s, EBC_ERR_INVALID, "ebc_set_value_mode: this network's shape does not fit the tensor-core tiling");
   s->value_mode = mode;
   s->value_mode_forced = 1;
@@ -164,7 +167,7 @@ int ebc_value(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row
     }
   }
   if (!row_count && !s->bound) return ebc_fail(s, EBC_ERR_UNBOUND, "ebc_value: state not bound");
-  if (s->value_mode != EBC_VALUE_FP32 && s->tc[s->value_mode == EBC_VALUE_TC_BF16 ? 0 : 1].ready)
+  if (s->value_mode != EBC_VALUE_FP32 && s->tc[ebc_tc_index(s->value_mode)].ready)
     return ebc_launch_value_tc(s, s->value_mode, vin, n_states, row_count, values, (cudaStream_t)stream);
   return ebc_launch_value(s, vin, n_states, row_count, values, (cudaStream_t)stream);
 }

@@ -62,7 +62,7 @@ struct ebc_sim {
   float *d_weights;      // one slab
   float *d_joint;        // [cap_states * (self_dim + H2)] scratch for mlp3
   int64_t joint_cap;
-  TcPrograms tc[2];      // [0] bf16 operands, [1] bf16x3 (fp32-accurate)
+  TcPrograms tc[3];      // indexed by operand parts - 1: [0] bf16, [1] fp16x2, [2] bf16x3
   long long *d_trace;    // EBC_TC_TRACE=1: clock64 stamps of CTA 0 (diagnostics)
   int value_mode;        // EBC_VALUE_*
   int value_mode_forced; // set explicitly by ebc_set_value_mode

@@ -13,6 +13,7 @@
 // accumulator (dropped terms are O(2^-24)).  Fast mode: one part, one MMA (bf16 operands).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -106,8 +107,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   return d;                                            // base_offset 0, lbo_mode 0, layout SWIZZLE_NONE
 }
 // instruction descriptor for kind::f16, bf16 x bf16 -> fp32, A and B K-major (cute::UMMA::InstrDescriptor)
-__device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// fmt: 1 = bf16, 0 = fp16 (cute::UMMA::F16F32Format)
+__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N, uint32_t fmt) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
   asm volatile(
@@ -122,27 +124,45 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// ---- fp32 -> bf16 parts --------------------------------------------------------------------------
-template <int NSPLIT>
-__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16 (&p)[NSPLIT]) {
-  p[0] = __float2bfloat16_rn(v);
-  if (NSPLIT > 1) {
-    const float r1 = v - __bfloat162float(p[0]);
-    p[1] = __float2bfloat16_rn(r1);
-    if (NSPLIT > 2) p[2] = __float2bfloat16_rn(r1 - __bfloat162float(p[1]));
-  }
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
-// bf16x2 pack of (lo, hi) with round-to-nearest-even: one cvt for two values
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
+// ---- fp32 -> bf16 parts --------------------------------------------------------------------------
+// Operand element format of a splitting mode: NSPLIT 1 and 3 -> bf16 parts, NSPLIT 2 -> fp16 parts
+// (two fp16 parts carry 22 mantissa bits; three bf16 parts carry 24).
+template <int NSPLIT> struct Fmt {
+  static constexpr uint32_t IDESC = 1;   // bf16
+  __device__ static __forceinline__ uint32_t pack2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+  }
+  __device__ static __forceinline__ float lo(uint32_t pk) { return __uint_as_float(pk << 16); }
+  __device__ static __forceinline__ float hi(uint32_t pk) { return __uint_as_float(pk & 0xFFFF0000u); }
+  __device__ static __forceinline__ float from16(uint16_t h) { return __uint_as_float((uint32_t)h << 16); }
+};
+template <> struct Fmt<2> {
+  static constexpr uint32_t IDESC = 0;   // fp16
+  __device__ static __forceinline__ uint32_t pack2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&h);
+  }
+  __device__ static __forceinline__ float lo(uint32_t pk) { return __half2float(__ushort_as_half((unsigned short)(pk & 0xFFFFu))); }
+  __device__ static __forceinline__ float hi(uint32_t pk) { return __half2float(__ushort_as_half((unsigned short)(pk >> 16))); }
+  __device__ static __forceinline__ float from16(uint16_t h) { return __half2float(__ushort_as_half(h)); }
+};
 
 // Store 8 consecutive k-elements (k0 % 8 == 0) of row `row` into the NSPLIT A images.
 // a_base: shared memory, image s at a_base + s * image_bytes.  Parts are peeled two values at a time:
-// p = bf16x2(v), v -= float(p) (exact), repeat.
+// p = round16(v), v -= float(p) (exact), repeat.
 template <int NSPLIT>
 __device__ __forceinline__ void store_a8(uint8_t *a_base, uint32_t image_bytes, int row, int k0, const float (&v)[8]) {
   float r[8];
@@ -154,11 +174,11 @@ __device__ __forceinline__ void store_a8(uint8_t *a_base, uint32_t image_bytes, 
     uint32_t *pw = reinterpret_cast<uint32_t *>(&w);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const uint32_t pk = pack_bf16x2(r[2 * i], r[2 * i + 1]);
+      const uint32_t pk = Fmt<NSPLIT>::pack2(r[2 * i], r[2 * i + 1]);
       pw[i] = pk;
       if (s + 1 < NSPLIT) {
-        r[2 * i] -= __uint_as_float(pk << 16);
-        r[2 * i + 1] -= __uint_as_float(pk & 0xFFFF0000u);
+        r[2 * i] -= Fmt<NSPLIT>::lo(pk);
+        r[2 * i + 1] -= Fmt<NSPLIT>::hi(pk);
       }
     }
     *reinterpret_cast<uint4 *>(a_base + (size_t)s * image_bytes + (size_t)(k0 >> 3) * A_CHUNK_BYTES + (size_t)row * 16) = w;
@@ -168,6 +188,11 @@ __device__ __forceinline__ void store_a8(uint8_t *a_base, uint32_t image_bytes, 
 // (a part, b part) pairs accumulated per k-step, smallest magnitude first
 template <int NSPLIT> struct Terms;
 template <> struct Terms<1> { static constexpr int N = 1; __device__ static int a(int) { return 0; } __device__ static int b(int) { return 0; } };
+template <> struct Terms<2> {
+  static constexpr int N = 3;
+  __device__ static int a(int t) { const int v[3] = {1, 0, 0}; return v[t]; }
+  __device__ static int b(int t) { const int v[3] = {0, 1, 0}; return v[t]; }
+};
 template <> struct Terms<3> {
   static constexpr int N = 6;
   __device__ static int a(int t) { const int v[6] = {2, 0, 1, 1, 0, 0}; return v[t]; }

@@ -17,6 +17,7 @@
 //                              "A ready" mbarrier; crew-only synchronisation uses named barrier 1
 // so the global-state (mean / attention bias) work of the crew overlaps the MMAs of mlp2.0 / attention.0.
 // See ebc_tc.cuh for the operand layout and the fp32-accurate bf16x3 operand splitting.
+#include <cuda_fp16.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -39,8 +40,8 @@ constexpr int TMEM_COLS = 512;
 constexpr int PS_LD = TILE_M + 4;
 
 template <int NSPLIT> struct Cfg {
-  static constexpr int STAGES = NSPLIT == 1 ? 8 : 3;
-  static constexpr int MAX_TS = NSPLIT == 1 ? 16 : 8;                    // states per entity tile
+  static constexpr int STAGES = NSPLIT == 1 ? 8 : (NSPLIT == 2 ? 6 : 3);
+  static constexpr int MAX_TS = NSPLIT == 3 ? 8 : 16;                    // states per entity tile
   static constexpr uint32_t A_IMAGE = TILE_M * KMAX * 2;                 // bytes per split image of A
   static constexpr uint32_t A_BYTES = NSPLIT * A_IMAGE;
   static constexpr uint32_t STAGE_BYTES = NSPLIT * KMAX * 32;            // one k-step slab, all splits
@@ -71,7 +72,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Ring of weight slabs + the MMA-issuing thread's cursor; barriers shared with the crew.
+// Ring of weight slabs + the MMA warp's cursor; barriers shared with the crew.
 template <int NSPLIT>
 struct Pipe {
   uint64_t *full, *empty, *acc_bar, *a_bar, *kbar;   // kbar[b]: k-step b of the A operand is written
@@ -79,30 +80,34 @@ struct Pipe {
   const uint8_t *wpack;      // packed weights (global)
   int n_stage_slabs;         // slabs per tile
   const uint2 *tab;          // shared memory: (byte offset, bytes) of each slab of the per-tile sequence
-  long long consumed, total; // running slab index / slab count over all tiles of this CTA
-  uint32_t acc_phase, a_phase, k_phase;   // k_phase: one parity bit per kbar (MMA thread)
+  long long total;           // slab count over all tiles of this CTA (loader)
+  uint32_t st, ph;           // MMA warp: ring slot of the next slab and its full-barrier parity
+  bool leader;               // MMA warp: the lane that issues tcgen05.mma / tcgen05.commit
+  uint32_t acc_phase, a_phase, k_phase;   // k_phase: one parity bit per kbar (MMA warp)
   long long *trace;          // optional clock64() trace of CTA 0's crew thread 0 (EBC_TC_TRACE=1)
   int trace_pos;
   __device__ __forceinline__ void stamp() {
     if (trace && threadIdx.x == 0 && blockIdx.x == 0 && trace_pos < 2048) trace[trace_pos++] = clock64();
   }
-  __device__ __forceinline__ void stamp_mma() {   // MMA thread's own stamps live in the upper half
-    if (trace && blockIdx.x == 0 && trace_pos < 2048) trace[2048 + trace_pos++] = clock64();
+  __device__ __forceinline__ void stamp_mma() {   // MMA warp's own stamps live in the upper half
+    if (trace && leader && blockIdx.x == 0 && trace_pos < 2048) trace[2048 + trace_pos++] = clock64();
   }
 
   // ---- loader thread: streams every slab of every tile of this CTA through the ring ---------------------
   __device__ void loader_loop() {
-    constexpr int ST = Cfg<NSPLIT>::STAGES;
+    constexpr uint32_t ST = Cfg<NSPLIT>::STAGES;
+    uint32_t slot = 0, parity = 1, idx = 0;          // parity of the "slot is free" wait: passes on the first lap
     for (long long i = 0; i < total; ++i) {
-      const int st = (int)(i % ST);
-      const uint32_t ph = (uint32_t)((i / ST) & 1);
-      mbar_wait(&empty[st], ph ^ 1u);
-      const uint2 sl = tab[(int)(i % n_stage_slabs)];
-      mbar_arrive_expect_tx(&full[st], sl.y);
-      bulk_g2s(wbuf + (size_t)st * Cfg<NSPLIT>::STAGE_BYTES, wpack + sl.x, sl.y, &full[st]);
+      mbar_wait(&empty[slot], parity);
+      const uint2 sl = tab[idx];
+      mbar_arrive_expect_tx(&full[slot], sl.y);
+      bulk_g2s(wbuf + (size_t)slot * Cfg<NSPLIT>::STAGE_BYTES, wpack + sl.x, sl.y, &full[slot]);
+      if (++slot == ST) { slot = 0; parity ^= 1u; }
+      if (++idx == (uint32_t)n_stage_slabs) idx = 0;
     }
   }
-  // ---- MMA thread -----------------------------------------------------------------------------------
+  // ---- MMA warp: every lane runs the loops (warp-uniform values -> uniform registers, no per-instruction
+  //      election loops), one elected lane issues the tcgen05 instructions ---------------------------------
   __device__ void wait_a() {           // the crew has written (and fenced) the A operand
     mbar_wait(a_bar, a_phase);
     a_phase ^= 1u;
@@ -111,33 +116,39 @@ struct Pipe {
   // pipelined: the crew is still writing the A operand; k-step ks is issued as soon as its two k-chunks
   // (one 16-column block of the previous stage's epilogue) have been stored and fenced by all 128 rows.
   __device__ void mma_stage(const TcStage &S, uint32_t a_smem, uint32_t tmem_base, bool pipelined = false) {
-    constexpr int ST = Cfg<NSPLIT>::STAGES;
-    const uint32_t idesc = make_idesc_bf16(TILE_M, S.np);
+    constexpr uint32_t ST = Cfg<NSPLIT>::STAGES;
+    const uint32_t idesc = make_idesc_f16(TILE_M, S.np, Fmt<NSPLIT>::IDESC);
     const uint32_t d = tmem_base + S.acc_col;
-    for (int ks = 0; ks < S.ksteps; ++ks) {
+    const uint32_t np = (uint32_t)S.np;
+    const int ksteps = S.ksteps;
+    // descriptors differ only in the 14-bit start-address field (16-byte units): build once, add offsets
+    const uint64_t a_desc0 = make_smem_desc(a_smem, A_CHUNK_BYTES, 128);
+    const uint64_t b_desc0 = make_smem_desc(smem_u32(wbuf), np * 16, 128);
+    for (int ks = 0; ks < ksteps; ++ks) {
       if (pipelined) {
         mbar_wait(&kbar[ks], (k_phase >> ks) & 1u);
         k_phase ^= 1u << ks;
-        tc_fence_after();
-        if (ks == 0 || ks == S.ksteps - 1) stamp_mma();
+        if (ks == 0 || ks == ksteps - 1) stamp_mma();
       }
-      const int st = (int)(consumed % ST);
-      const uint32_t ph = (uint32_t)((consumed / ST) & 1);
       mbar_wait(&full[st], ph);
       tc_fence_after();
-      const uint32_t b_smem = smem_u32(wbuf + (size_t)st * Cfg<NSPLIT>::STAGE_BYTES);
+      const uint64_t ad = a_desc0 + (uint64_t)((uint32_t)ks * (2 * A_CHUNK_BYTES / 16));
+      const uint64_t bd = b_desc0 + (uint64_t)(st * (Cfg<NSPLIT>::STAGE_BYTES / 16));
+      if (leader) {
 #pragma unroll
-      for (int t = 0; t < Terms<NSPLIT>::N; ++t) {
-        const uint64_t ad = make_smem_desc(a_smem + Terms<NSPLIT>::a(t) * Cfg<NSPLIT>::A_IMAGE + (uint32_t)ks * 2 * A_CHUNK_BYTES,
-                                           A_CHUNK_BYTES, 128);
-        const uint64_t bd = make_smem_desc(b_smem + Terms<NSPLIT>::b(t) * (uint32_t)S.np * 32, (uint32_t)S.np * 16, 128);
-        umma_bf16(d, ad, bd, idesc, S.accumulate || ks > 0 || t > 0);
+        for (int t = 0; t < Terms<NSPLIT>::N; ++t)
+          umma_bf16(d, ad + (uint64_t)(Terms<NSPLIT>::a(t) * (Cfg<NSPLIT>::A_IMAGE / 16)),
+                    bd + (uint64_t)(Terms<NSPLIT>::b(t) * np * 2), idesc, S.accumulate || ks > 0 || t > 0);
+        umma_commit(&empty[st]);   // frees the slab when these MMAs have read it
       }
-      umma_commit(&empty[st]);   // frees the slab when these MMAs have read it
-      ++consumed;
+      __syncwarp();
+      if (++st == ST) { st = 0; ph ^= 1u; }
     }
   }
-  __device__ void commit_acc() { umma_commit(acc_bar); }
+  __device__ void commit_acc() {
+    if (leader) umma_commit(acc_bar);
+    __syncwarp();
+  }
 
   // ---- crew -------------------------------------------------------------------------------------------
   __device__ void wait_acc() {
@@ -251,7 +262,7 @@ __device__ __forceinline__ void pipe_init(Pipe<NSPLIT> &pipe, uint8_t *smem, con
   uint2 *tab = reinterpret_cast<uint2 *>(smem + L.tab);
   for (int i = threadIdx.x; i < P.n_slabs; i += blockDim.x) tab[i] = make_uint2(__ldg(P.slab_off + i), __ldg(P.slab_bytes + i));
   pipe.tab = tab;
-  pipe.consumed = 0; pipe.acc_phase = 0; pipe.a_phase = 0;
+  pipe.st = 0; pipe.ph = 0; pipe.leader = false; pipe.acc_phase = 0; pipe.a_phase = 0;
   pipe.trace = nullptr; pipe.trace_pos = 0;
   pipe.total = my_tiles * P.n_slabs;
   if (threadIdx.x == 0) {
@@ -287,7 +298,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
   __shared__ uint32_t tmem_slot;
   __shared__ int cnt[16];
   const TcProgram &P = p.prog;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
 
   Pipe<NSPLIT> pipe;
   const long long n_tiles = (p.n_states + p.ts - 1) / p.ts;
@@ -301,26 +312,25 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
   const uint32_t a_smem = smem_u32(A);
 
   if (warp == NCREW / 32) {
-    // =================================== MMA / loader warp ===================================
-    if ((tid & 31) == 0) {
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        pipe.wait_a();
-        for (int h = 0; h < P.n_wide; ++h) pipe.mma_stage(P.st[ST_L0A + h], a_smem, tmem_base);
-        pipe.commit_acc();
-        for (int h = 0; h < P.n_wide; ++h) {
-          pipe.mma_stage(P.st[ST_L1A + h], a_smem, tmem_base, true);   // chases the wide-half epilogue
-          pipe.commit_acc();
-        }
-        pipe.mma_stage(P.st[ST_L2], a_smem, tmem_base, true);          // chases the H1 epilogue
-        pipe.mma_stage(P.st[ST_L4], a_smem, tmem_base);                // H1 fully written and its accumulator read
-        pipe.commit_acc();
-        pipe.wait_a();
-        pipe.mma_stage(P.st[ST_L3], a_smem, tmem_base);
-        pipe.commit_acc();
-        pipe.wait_a();
-        pipe.mma_stage(P.st[ST_L5], a_smem, tmem_base);
+    // =================================== MMA warp (converged) ===================================
+    pipe.leader = elect_one();
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      pipe.wait_a();
+      for (int h = 0; h < P.n_wide; ++h) pipe.mma_stage(P.st[ST_L0A + h], a_smem, tmem_base);
+      pipe.commit_acc();
+      for (int h = 0; h < P.n_wide; ++h) {
+        pipe.mma_stage(P.st[ST_L1A + h], a_smem, tmem_base, true);   // chases the wide-half epilogue
         pipe.commit_acc();
       }
+      pipe.mma_stage(P.st[ST_L2], a_smem, tmem_base, true);          // chases the H1 epilogue
+      pipe.mma_stage(P.st[ST_L4], a_smem, tmem_base);                // H1 fully written and its accumulator read
+      pipe.commit_acc();
+      pipe.wait_a();
+      pipe.mma_stage(P.st[ST_L3], a_smem, tmem_base);
+      pipe.commit_acc();
+      pipe.wait_a();
+      pipe.mma_stage(P.st[ST_L5], a_smem, tmem_base);
+      pipe.commit_acc();
     }
   } else if (warp == NCREW / 32 + 1) {
     if ((tid & 31) == 0) pipe.loader_loop();
@@ -402,7 +412,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
               float v = 0.0f;
 #pragma unroll
               for (int sp = 0; sp < NSPLIT; ++sp)
-                v += __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(A + (size_t)sp * Cfg<NSPLIT>::A_IMAGE + off));
+                v += Fmt<NSPLIT>::from16(*reinterpret_cast<const uint16_t *>(A + (size_t)sp * Cfg<NSPLIT>::A_IMAGE + off));
               acc += v;
             }
             GV[k * MAX_TS + s] = c > 0 ? acc / (float)c : 0.0f;
@@ -587,7 +597,7 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
   float *SC = reinterpret_cast<float *>(smem + L.sc);
   __shared__ uint32_t tmem_slot;
   const TcProgram &P = p.prog;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   Pipe<NSPLIT> pipe;
   const long long n_tiles = (p.n_states + TILE_M - 1) / TILE_M;
   pipe_init<NSPLIT>(pipe, smem, L, P, (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
@@ -599,18 +609,17 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
   const uint32_t a_smem = smem_u32(A);
 
   if (warp == NCREW / 32) {
-    if ((tid & 31) == 0) {
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        pipe.wait_a();
-        for (int h = 0; h < P.n_wide; ++h) pipe.mma_stage(P.st[ST_L0A + h], a_smem, tmem_base);
-        pipe.commit_acc();
-        for (int h = 0; h < P.n_wide; ++h) {
-          pipe.mma_stage(P.st[ST_L1A + h], a_smem, tmem_base, true);
-          pipe.commit_acc();
-        }
-        pipe.mma_stage(P.st[ST_L2], a_smem, tmem_base, true);
+    pipe.leader = elect_one();
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      pipe.wait_a();
+      for (int h = 0; h < P.n_wide; ++h) pipe.mma_stage(P.st[ST_L0A + h], a_smem, tmem_base);
+      pipe.commit_acc();
+      for (int h = 0; h < P.n_wide; ++h) {
+        pipe.mma_stage(P.st[ST_L1A + h], a_smem, tmem_base, true);
         pipe.commit_acc();
       }
+      pipe.mma_stage(P.st[ST_L2], a_smem, tmem_base, true);
+      pipe.commit_acc();
     }
   } else if (warp == NCREW / 32 + 1) {
     if ((tid & 31) == 0) pipe.loader_loop();
@@ -667,6 +676,19 @@ struct Packer {
   std::vector<uint8_t> bytes;
   std::vector<uint32_t> slab_off, slab_bytes;
 
+  static uint16_t round16(float f, int fp16) {
+    if (!fp16) return bf16_rn(f);
+    const __half h = __float2half_rn(f);
+    uint16_t u;
+    memcpy(&u, &h, 2);
+    return u;
+  }
+  static float back16(uint16_t u, int fp16) {
+    if (!fp16) return bf16_to_f(u);
+    __half h;
+    memcpy(&h, &u, 2);
+    return __half2float(h);
+  }
   static uint16_t bf16_rn(float f) {
     uint32_t u;
     memcpy(&u, &f, 4);
@@ -692,8 +714,8 @@ struct Packer {
             const int n = n_lo + nn, k = k_lo + ks * 16 + c * 8 + j;
             float v = (n < n_hi && k < k_hi) ? W[(size_t)n * ld + k_col_off + k] : 0.0f;
             for (int s = 0; s < nsplit; ++s) {
-              const uint16_t h = bf16_rn(v);
-              v -= bf16_to_f(h);
+              const uint16_t h = round16(v, nsplit == 2);
+              v -= back16(h, nsplit == 2);
               uint8_t *dst = bytes.data() + off + (size_t)s * np * 32 + (size_t)c * np * 16 + (size_t)nn * 16 + j * 2;
               memcpy(dst, &h, 2);
             }
@@ -710,7 +732,7 @@ int launch_tc(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row
   if ((int)L.total + 1024 > s->max_smem_optin) return ebc_fail(s, EBC_ERR_INVALID, "tensor-core value path needs %u B of shared memory", L.total);
   const int n = s->cfg.max_humans + s->cfg.max_statics;
   TcEntityParams p;
-  p.prog = s->tc[NSPLIT == 1 ? 0 : 1].entity;
+  p.prog = s->tc[NSPLIT - 1].entity;
   p.vin = vin; p.row_count = row_count; p.hum_count = s->st.hum_count; p.stat_count = s->st.stat_count;
   p.n_actions = s->cfg.n_actions; p.n_states = n_states; p.n = n; p.D = s->net.D;
   int ts = TILE_M / n;
@@ -725,7 +747,7 @@ int launch_tc(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row
     p.trace = s->d_trace;
   }
   TcMlp3Params q;
-  q.prog = s->tc[NSPLIT == 1 ? 0 : 1].mlp3;
+  q.prog = s->tc[NSPLIT - 1].mlp3;
   q.joint = s->d_joint; q.values = values; q.n_states = n_states; q.jd = p.jd;
   cudaFuncSetAttribute(tc_entity_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
   cudaFuncSetAttribute(tc_mlp3_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
@@ -877,7 +899,7 @@ int ebc_tc_prepare(ebc_sim *s, const ebc_weights *w, int mode_index, int nsplit)
 void ebc_tc_release(ebc_sim *s) {
   if (s->d_trace) cudaFree(s->d_trace);
   s->d_trace = nullptr;
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 3; ++i) {
     if (s->tc[i].slab) cudaFree(s->tc[i].slab);
     s->tc[i].slab = nullptr;
     s->tc[i].ready = 0;
@@ -887,5 +909,6 @@ void ebc_tc_release(ebc_sim *s) {
 int ebc_launch_value_tc(ebc_sim *s, int mode, const float *vin, int64_t n_states, const int32_t *row_count,
                         float *values, cudaStream_t stream) {
   if (mode == EBC_VALUE_TC_BF16) return launch_tc<1>(s, vin, n_states, row_count, values, stream);
+  if (mode == EBC_VALUE_TC_FP16X2) return launch_tc<2>(s, vin, n_states, row_count, values, stream);
   return launch_tc<3>(s, vin, n_states, row_count, values, stream);
 }

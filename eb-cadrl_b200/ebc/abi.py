@@ -15,7 +15,7 @@ EV_NOTHING, EV_DANGER, EV_REACH_GOAL, EV_COLLISION_ADULT, EV_COLLISION_BICYCLE, 
     EV_COLLISION_CHILD, EV_COLLISION_OBSTACLE, EV_TIMEOUT = range(8)
 
 KIN_HOLONOMIC, KIN_UNICYCLE = 0, 1
-VALUE_FP32, VALUE_TC_FP32, VALUE_TC_BF16 = 0, 1, 2
+VALUE_FP32, VALUE_TC_FP32, VALUE_TC_BF16, VALUE_TC_FP16X2 = 0, 1, 2, 3
 POLICY_ORCA, POLICY_LINEAR = 0, 1
 
 c_i32, c_f64, c_f32 = ctypes.c_int32, ctypes.c_double, ctypes.c_float

@@ -161,15 +161,17 @@ class BatchedSim(object):
         self._have_weights = True
 
     def set_value_mode(self, mode):
-        """K4 arithmetic: 'fp32' (FFMA), 'tc_fp32' (tcgen05, bf16x3 operand splitting, fp32-accurate,
-        default when the network fits) or 'tc_bf16' (tcgen05, plain bf16 operands, fast, not argmax-exact)."""
-        code = {"fp32": abi.VALUE_FP32, "tc_fp32": abi.VALUE_TC_FP32, "tc_bf16": abi.VALUE_TC_BF16}[mode]
+        """K4 arithmetic: 'fp32' (FFMA), 'tc_fp16x2' (tcgen05, two fp16 parts per operand, 3 MMAs per product,
+        fp32-accurate, default when the network fits), 'tc_fp32' (tcgen05, three bf16 parts, 6 MMAs per product,
+        fp32-accurate) or 'tc_bf16' (tcgen05, plain bf16 operands, fast, not argmax-exact)."""
+        code = {"fp32": abi.VALUE_FP32, "tc_fp32": abi.VALUE_TC_FP32, "tc_bf16": abi.VALUE_TC_BF16,
+                "tc_fp16x2": abi.VALUE_TC_FP16X2}[mode]
         rc = self.be.lib.ebc_set_value_mode(self.h, code)
         if rc != 0:
             raise abi.EbcError("ebc_set_value_mode: %s" % self.be.last_error(self.h))
 
     def value_mode(self):
-        return {0: "fp32", 1: "tc_fp32", 2: "tc_bf16"}[self.be.lib.ebc_get_value_mode(self.h)]
+        return {0: "fp32", 1: "tc_fp32", 2: "tc_bf16", 3: "tc_fp16x2"}[self.be.lib.ebc_get_value_mode(self.h)]
 
     # ---- scene upload -------------------------------------------------------------
     def load_episodes(self, first, hum_pv, hum_gr, hum_type, hum_count, stat=None, stat_count=None,

@@ -163,14 +163,17 @@ int ebc_set_actions(ebc_sim *sim, const double *actions, int32_t n_actions);
 
 int ebc_set_weights(ebc_sim *sim, const ebc_weights *w);
 
-/* Arithmetic of K4 (the value network).  All three are this library's own kernels.
- *   EBC_VALUE_FP32     fp32 FFMA (CUDA cores): the round-1 parity path
- *   EBC_VALUE_TC_FP32  tcgen05 tensor cores, every fp32 operand split into three bf16 parts and
- *                      six MMAs per product: fp32-accurate (what argmax parity needs), DEFAULT when
- *                      the network's shape fits the tensor-core tiling
- *   EBC_VALUE_TC_BF16  tcgen05, plain bf16 operands, fp32 accumulation: fast mode, NOT argmax-exact
- *                      (rl/policy/sarl.py:38-82 evaluated with bf16 inputs; agreement rate is reported) */
-enum { EBC_VALUE_FP32 = 0, EBC_VALUE_TC_FP32 = 1, EBC_VALUE_TC_BF16 = 2 };
+/* Arithmetic of K4 (the value network).  All four are this library's own kernels.
+ *   EBC_VALUE_FP32      fp32 FFMA (CUDA cores): the first parity path, kept as a cross-check
+ *   EBC_VALUE_TC_FP16X2 tcgen05 tensor cores, every fp32 operand split into two fp16 parts (22 mantissa
+ *                       bits; absolute floor 2^-25 per operand) and three MMAs per product (hi*hi + lo*hi +
+ *                       hi*lo) into one fp32 TMEM accumulator: fp32-accurate (what argmax parity needs),
+ *                       DEFAULT when the network's shape fits the tensor-core tiling.  An activation
+ *                       beyond the fp16 range (65504) turns the value into NaN, which ebc_select flags
+ *   EBC_VALUE_TC_FP32   same with three bf16 parts (24 bits, fp32 range) and six MMAs per product
+ *   EBC_VALUE_TC_BF16   tcgen05, plain bf16 operands, fp32 accumulation: fast mode, NOT argmax-exact
+ *                       (rl/policy/sarl.py:38-82 evaluated with bf16 inputs; agreement rate is reported) */
+enum { EBC_VALUE_FP32 = 0, EBC_VALUE_TC_FP32 = 1, EBC_VALUE_TC_BF16 = 2, EBC_VALUE_TC_FP16X2 = 3 };
 int ebc_set_value_mode(ebc_sim *sim, int32_t mode);
 int ebc_get_value_mode(const ebc_sim *sim);
 

@@ -157,3 +157,38 @@ def test_basic_train(tmp_path):
     assert all(torch.isfinite(v).all() for v in sd.values())
     log = open(os.path.join(out, "output.log")).read()
     assert "TRAIN" in log and "has success rate" in log
+
+
+def test_test_set_rates_match_reference():
+    """north_star item 3: test-set success / collision / timeout rates against the reference's own run of the
+    same 96 test seeds (tests/golden/outcomes_cfg1.json, produced by tests/golden/make_outcomes.py).
+    Stated tolerance: each rate within 0.08 absolute (two-sigma binomial at n = 96 is 0.10) and at least 85 %
+    of the individual episodes end in the same Info class (fp32 state + RVO2 chaos make long rollouts diverge)."""
+    import json
+    from ebc.batched_env import BatchedEnv
+    from rl.policy.policy_factory import policy_factory
+    rows = json.load(open(os.path.join(ob.GOLDEN, "outcomes_cfg1.json")))
+    seeds = [r["seed"] for r in rows]
+    cp = configparser.RawConfigParser(); cp.read(os.path.join(CFG, "env_adults_5.config"))
+    pc = configparser.RawConfigParser(); pc.read(os.path.join(CFG, "policy.config"))
+    pol = policy_factory["sarl"]()
+    pol.configure(pc)
+    pol.get_model().load_state_dict({k: torch.as_tensor(v) for k, v in ob.load_weights("weights_sarl_baseline.npz").items()})
+    pol.set_phase("test"); pol.set_device("cuda:0")
+    env = BatchedEnv(cp, pol, len(seeds), "cuda:0")
+    stats, _ = env.run_episodes("test", seeds)
+    names = ["Nothing", "Danger", "ReachGoal", "CollisionAdult", "CollisionBicycle", "CollisionChild", "CollisionObstacle", "Timeout"]
+    mine = [names[e] for e in stats.event]
+    ref = [r["info"] for r in rows]
+    n = len(rows)
+    for cls in ("ReachGoal", "Timeout", "CollisionAdult"):
+        a, b = sum(m == cls for m in mine) / n, sum(r == cls for r in ref) / n
+        print(cls, "ours %.3f reference %.3f" % (a, b))
+        assert abs(a - b) <= 0.08, (cls, a, b)
+    same = sum(m == r for m, r in zip(mine, ref)) / n
+    print("per-episode agreement %.3f" % same)
+    assert same >= 0.85
+    ok = [i for i in range(n) if mine[i] == ref[i] == "ReachGoal"]
+    dt = np.array([abs(stats.time[i] - rows[i]["time"]) for i in ok])
+    print("median |nav time difference| on common successes: %.2f s" % np.median(dt))
+    assert np.median(dt) <= 0.5

@@ -53,12 +53,12 @@ def test_tc_modes_vs_fp64(weights, H, S, typed, n_states):
     cfg.with_agent_type = typed
     sim = BatchedSim(cfg, 1, H, S, 0, 81, device="cuda:0")
     sim.set_weights(w)
-    assert sim.value_mode() == "tc_fp32"          # default when the network fits the tiling
+    assert sim.value_mode() == "tc_fp16x2"        # default when the network fits the tiling
     x, cnt = make_inputs(n_states, H + S, cfg.D, seed=n_states + H)
     ref = torch_value(w, x, cnt)
     scale = max(1.0, ref.abs().max().item())
     out = {}
-    for mode in ("fp32", "tc_fp32", "tc_bf16"):
+    for mode in ("fp32", "tc_fp32", "tc_fp16x2", "tc_bf16"):
         sim.set_value_mode(mode)
         out[mode] = sim.value(x, cnt).double()
         torch.cuda.synchronize()
@@ -66,6 +66,7 @@ def test_tc_modes_vs_fp64(weights, H, S, typed, n_states):
     print(weights, H + S, n_states, err)
     assert err["fp32"] < 1e-4 * scale
     assert err["tc_fp32"] < 2e-5 * scale, err     # fp32-accurate: as good as (or better than) FFMA
+    assert err["tc_fp16x2"] < 4e-5 * scale, err   # two fp16 parts (22 bits), 3 MMAs per product
     assert err["tc_bf16"] < 0.1 * scale, err      # bf16 operands: percent-level
     assert err["tc_bf16"] > err["tc_fp32"]
 
@@ -82,7 +83,7 @@ def test_tc_matches_golden_argmax(oracle):
     for t in range(N):
         tr.load_into(g, t, episode=t)
     res = {}
-    for mode in ("tc_fp32", "tc_bf16"):
+    for mode in ("tc_fp32", "tc_fp16x2", "tc_bf16"):
         g.set_value_mode(mode)
         g.decide()
         torch.cuda.synchronize()
@@ -94,4 +95,5 @@ def test_tc_matches_golden_argmax(oracle):
         res[mode] = (dv, flips, big, len(has))
     print(res)
     assert res["tc_fp32"][0] < 2e-4 and res["tc_fp32"][2] == 0 and res["tc_fp32"][1] <= 2
+    assert res["tc_fp16x2"][0] < 2e-4 and res["tc_fp16x2"][2] == 0 and res["tc_fp16x2"][1] <= 2
     assert res["tc_bf16"][0] < 0.1

@@ -1,0 +1,24 @@
+"""K4 (value network) alone on the bench workload: a short command for ncu captures.
+    python tools/k4_only.py [mode] [iterations]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "eb-cadrl_b200")); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
+import numpy as np, torch
+import bench
+from ebc import synth
+from ebc.actions import build_action_space
+from ebc.engine import BatchedSim
+shape, cfg = bench.workload(); w, _ = bench.value_net_weights()
+N = 4096
+sim = BatchedSim(cfg, N, shape.H, shape.Smax, shape.Rmax, 81, device="cuda:0")
+sim.set_actions(build_action_space(shape.robot_v_pref)); sim.set_weights(w)
+synth.load(sim, synth.generate(shape, np.arange(N)))
+sim.set_value_mode(sys.argv[1] if len(sys.argv) > 1 else "tc_fp16x2")
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+sim.orca(); sim.lookahead()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+sim.value(); torch.cuda.synchronize()
+a.record()
+for _ in range(iters): sim.value()
+b.record(); torch.cuda.synchronize()
+print("K4 %s: %.3f ms per call" % (sim.value_mode(), a.elapsed_time(b) / iters))
