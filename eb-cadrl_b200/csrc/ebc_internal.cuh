@@ -22,7 +22,7 @@ struct ValueNet {
 };
 
 // ---- tensor-core (tcgen05) value path, ebc_value_tc.cu -------------------------------------------
-enum { ST_L0A = 0, ST_L0B = 1, ST_L1A = 2, ST_L1B = 3, ST_L2 = 4, ST_L3 = 5, ST_L4 = 6, ST_L5 = 7, ST_COUNT = 8 };
+enum { ST_L0A = 0, ST_L0B = 1, ST_L1A = 2, ST_L1B = 3, ST_L2 = 4, ST_L3 = 5, ST_L4 = 6, ST_L5 = 7, ST_L4G = 8, ST_COUNT = 9 };
 
 struct TcStage {         // one GEMM stage: acc[:, acc_col : acc_col + np] (+)= A[:, 0 : 16*ksteps] . W^T
   int np;                // padded N (multiple of 16, <= 208)
@@ -30,6 +30,7 @@ struct TcStage {         // one GEMM stage: acc[:, acc_col : acc_col + np] (+)= 
   int acc_col;           // first TMEM column of the accumulator
   int accumulate;        // add to the existing accumulator (second K chunk)
   int n_lo;              // first output column of this stage within its layer (bias offset)
+  int n_real;            // real output columns of this stage (the rest of np is padding)
 };
 
 struct TcProgram {
@@ -41,8 +42,6 @@ struct TcProgram {
   const float *bias[6];          // padded fp32 biases (device)
   const float *w6;               // last (N = 1) layer weights, padded
   float b6;
-  const float *zero_bias;
-  const float *wg;               // global half of attention.0, fp32 [h1][a1p]
   int with_global, h1d, h2d;
 };
 

@@ -2,21 +2,27 @@
 //
 // One CTA owns a tile of 128 entity rows (whole states) and walks the whole per-entity part of
 // rl/policy/sarl.py:38-82 with the activations never leaving the SM:
-//   X -> mlp1.0 -> mlp1.2 (= H1) -> { mlp2.0 -> mlp2.2 (= H2),  attention.0 (+ global half as a per-state
-//   bias) -> attention.2 -> attention.4 score } -> masked softmax -> pooled H2 -> joint[state]
+//   X -> mlp1.0 -> mlp1.2 (= H1) -> { mlp2.0 -> mlp2.2 (= H2),  attention.0 on [H1, mean_state(H1)]
+//   -> attention.2 -> attention.4 score } -> masked softmax -> pooled H2 -> joint[state]
 // and a second kernel runs mlp3 over tiles of 128 states.
 //
-// Warp roles (544 threads):
-//   warp 16, one elected lane  streams the pre-packed weight slabs L2 -> shared memory with cp.async.bulk
-//                              (mbarrier full/empty ring) and issues the tcgen05.mma's: A = activations in
-//                              shared memory (canonical K-major layout written by the previous epilogue),
-//                              B = weight slab, D = fp32 accumulator in TMEM; tcgen05.commit -> acc barrier
+// Warp roles (576 threads):
+//   warp 17, one lane          streams the pre-packed weight slabs L2 -> shared memory with cp.async.bulk
+//                              (mbarrier full/empty ring)
+//   warp 16 (converged)        waits on the barriers and issues the tcgen05.mma's from one elected lane:
+//                              A = activations in shared memory (canonical K-major layout written by the
+//                              previous epilogue), B = weight slab, D = fp32 accumulator in TMEM
 //   warps 0-15 (512 threads)   epilogue crew: warp w reads TMEM lane quarter (w % 4) (row = lane) and the
 //                              16-column blocks b with b % 4 == w / 4, applies bias / ReLU, splits the fp32
-//                              value into bf16 parts, stores the next stage's A operand and arrives on the
-//                              "A ready" mbarrier; crew-only synchronisation uses named barrier 1
-// so the global-state (mean / attention bias) work of the crew overlaps the MMAs of mlp2.0 / attention.0.
-// See ebc_tc.cuh for the operand layout and the fp32-accurate bf16x3 operand splitting.
+//                              value into 16-bit parts and stores the next stage's A operand
+// Every stage boundary is a chase in both directions, one 16-column block (= one k-step) at a time:
+//   kbar[b]   crew -> MMA warp: block b of the next A operand is written (the next stage's k-step b may issue)
+//   afree[b]  MMA warp -> crew: the MMAs that read block b of the current A operand have completed
+//             (tcgen05.commit after that k-step), so the following epilogue may overwrite it
+// so the tensor pipe and the epilogue crew work on the same tile at the same time.  The global state of
+// sarl.py:51-60 is an extra K chunk of attention.0: the crew writes the per-state mean of H1 (replicated
+// over the state's rows) as an A operand and the tensor core multiplies it with the global half of the weights.
+// See ebc_tc.cuh for the operand layout and the fp32-accurate operand splitting.
 #include <cuda_fp16.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -33,9 +39,10 @@ using namespace tc;
 
 constexpr int NCREW = 512;                      // epilogue threads: 4 lane quarters x 4 column groups
 constexpr int NT = NCREW + 64;                  // + the MMA warp (16) and the weight-loader warp (17)
-constexpr int MAX_SLABS = 120;                  // slabs per tile (entity program: 75, mlp3: 46)
+constexpr int MAX_SLABS = 120;                  // slabs per tile (entity program: 88, mlp3: 46)
 constexpr int NCG = NCREW / TILE_M;             // column groups
 constexpr int KMAX = 208;                       // widest A operand chunk kept in shared memory
+constexpr int NKB = KMAX / 16;                  // 16-column blocks of an A operand
 constexpr int TMEM_COLS = 512;
 constexpr int PS_LD = TILE_M + 4;
 
@@ -49,7 +56,7 @@ template <int NSPLIT> struct Cfg {
 };
 
 struct Smem {   // offsets (bytes) into dynamic shared memory
-  uint32_t a, w, gv, sc, xs, tab, bars, total;
+  uint32_t a, w, g, sc, xs, tab, bars, total;
 };
 
 template <int NSPLIT>
@@ -58,11 +65,11 @@ __host__ __device__ inline Smem smem_layout() {
   uint32_t off = 0;
   s.a = off; off += Cfg<NSPLIT>::A_BYTES;
   s.w = off; off += Cfg<NSPLIT>::W_BYTES;
-  s.gv = off; off += Cfg<NSPLIT>::MAX_TS * KMAX * 4;   // G[k][state] first, then GV[state][col] in place
+  s.g = off; off += Cfg<NSPLIT>::MAX_TS * KMAX * 4;    // G[k][state]: per-state mean of H1
   s.sc = off; off += TILE_M * 4 * (NCG + 1);           // partial scores per column group, softmax weights
   s.xs = off; off += 16 * 8 * 4;                        // self-state part of each state's first row
   s.tab = off; off += MAX_SLABS * 8;                    // (offset, bytes) of every slab of the per-tile program
-  s.bars = off; off += 256;
+  s.bars = off; off += 512;
   s.total = off;
   return s;
 }
@@ -71,11 +78,12 @@ __device__ __forceinline__ void crew_sync() { asm volatile("bar.sync 1, %0;" ::"
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ uint32_t low_bits(int n) { return (1u << n) - 1u; }
 
 // Ring of weight slabs + the MMA warp's cursor; barriers shared with the crew.
 template <int NSPLIT>
 struct Pipe {
-  uint64_t *full, *empty, *acc_bar, *a_bar, *kbar;   // kbar[b]: k-step b of the A operand is written
+  uint64_t *full, *empty, *acc_bar, *a_bar, *kbar, *afree;
   uint8_t *wbuf;
   const uint8_t *wpack;      // packed weights (global)
   int n_stage_slabs;         // slabs per tile
@@ -83,12 +91,15 @@ struct Pipe {
   long long total;           // slab count over all tiles of this CTA (loader)
   uint32_t st, ph;           // MMA warp: ring slot of the next slab and its full-barrier parity
   bool leader;               // MMA warp: the lane that issues tcgen05.mma / tcgen05.commit
-  uint32_t acc_phase, a_phase, k_phase;   // k_phase: one parity bit per kbar (MMA warp)
+  uint32_t acc_phase, a_phase;
+  uint32_t k_phase;          // MMA warp: expected parity of every kbar, one bit each
+  uint32_t f_phase;          // crew: expected parity of every afree barrier, one bit each
   long long *trace;          // optional clock64() trace of CTA 0's crew thread 0 (EBC_TC_TRACE=1)
   int trace_pos;
   __device__ __forceinline__ void stamp() {
     if (trace && threadIdx.x == 0 && blockIdx.x == 0 && trace_pos < 2048) trace[trace_pos++] = clock64();
   }
+
   __device__ __forceinline__ void stamp_mma() {   // MMA warp's own stamps live in the upper half
     if (trace && leader && blockIdx.x == 0 && trace_pos < 2048) trace[2048 + trace_pos++] = clock64();
   }
@@ -113,9 +124,10 @@ struct Pipe {
     a_phase ^= 1u;
     tc_fence_after();
   }
-  // pipelined: the crew is still writing the A operand; k-step ks is issued as soon as its two k-chunks
-  // (one 16-column block of the previous stage's epilogue) have been stored and fenced by all 128 rows.
-  __device__ void mma_stage(const TcStage &S, uint32_t a_smem, uint32_t tmem_base, bool pipelined = false) {
+  // chase:    the crew is still writing the A operand; k-step ks is issued as soon as its two k-chunks (one
+  //           16-column block of the previous stage's epilogue) have been stored and fenced by all 128 rows
+  // commit_k: signal afree[ks] when the MMAs issued up to and including k-step ks have completed
+  __device__ void mma_stage(const TcStage &S, uint32_t a_smem, uint32_t tmem_base, bool chase, bool commit_k) {
     constexpr uint32_t ST = Cfg<NSPLIT>::STAGES;
     const uint32_t idesc = make_idesc_f16(TILE_M, S.np, Fmt<NSPLIT>::IDESC);
     const uint32_t d = tmem_base + S.acc_col;
@@ -124,25 +136,51 @@ struct Pipe {
     // descriptors differ only in the 14-bit start-address field (16-byte units): build once, add offsets
     const uint64_t a_desc0 = make_smem_desc(a_smem, A_CHUNK_BYTES, 128);
     const uint64_t b_desc0 = make_smem_desc(smem_u32(wbuf), np * 16, 128);
-    for (int ks = 0; ks < ksteps; ++ks) {
-      if (pipelined) {
-        mbar_wait(&kbar[ks], (k_phase >> ks) & 1u);
-        k_phase ^= 1u << ks;
-        if (ks == 0 || ks == ksteps - 1) stamp_mma();
+    // Up to four k-steps per trip: lanes 0-3 test kbar[ks .. ks+3], lanes 4-7 test the next four ring slots
+    // (non-blocking mbarrier.test_wait, one instruction for all eight barriers), then every k-step whose two
+    // barriers have completed is issued in order.  One barrier round trip per k-step would leave the tensor
+    // pipe waiting on this warp's own latency (measured: ~500 cycles per k-step against 312 of MMA work).
+    const uint32_t lane = threadIdx.x & 31;
+    int ks = 0;
+    uint32_t idle = 0;
+    while (ks < ksteps) {
+      bool ok = false;
+      if (lane < 4) {
+        const int k = ks + (int)lane;
+        ok = !chase || (k < ksteps && mbar_test(&kbar[k], (k_phase >> k) & 1u));
+      } else if (lane < 8) {
+        uint32_t slot = st + lane - 4, par = ph;
+        if (slot >= ST) { slot -= ST; par ^= 1u; }
+        ok = mbar_test(&full[slot], par);
       }
-      mbar_wait(&full[st], ph);
+      const uint32_t m = __ballot_sync(0xffffffffu, ok);
+      __syncwarp();                      // the observations of lanes 0-7 are ordered before the leader's MMAs
+      const uint32_t both = m & (m >> 4) & 0xFu;
+      int nready = __ffs((int)~both) - 1;            // k-steps ks .. ks + nready - 1 are ready (in order)
+      if (nready > ksteps - ks) nready = ksteps - ks;
+      if (nready == 0) {
+        if (++idle > (1u << 22)) __trap();   // bounded like mbar_wait: a protocol bug traps instead of hanging
+        continue;
+      }
+      if (trace && leader && blockIdx.x == 0 && trace_pos < 2048)   // diagnostics: (clock, idle polls, barrier mask)
+        trace[2048 + trace_pos++] = (clock64() << 16) | (long long)((idle > 255 ? 255 : idle) << 8) | (long long)(m & 0xFFu);
+      idle = 0;
       tc_fence_after();
-      const uint64_t ad = a_desc0 + (uint64_t)((uint32_t)ks * (2 * A_CHUNK_BYTES / 16));
-      const uint64_t bd = b_desc0 + (uint64_t)(st * (Cfg<NSPLIT>::STAGE_BYTES / 16));
-      if (leader) {
+      for (int j = 0; j < nready; ++j, ++ks) {
+        if (chase) k_phase ^= 1u << ks;
+        const uint64_t ad = a_desc0 + (uint64_t)((uint32_t)ks * (2 * A_CHUNK_BYTES / 16));
+        const uint64_t bd = b_desc0 + (uint64_t)(st * (Cfg<NSPLIT>::STAGE_BYTES / 16));
+        if (leader) {
 #pragma unroll
-        for (int t = 0; t < Terms<NSPLIT>::N; ++t)
-          umma_bf16(d, ad + (uint64_t)(Terms<NSPLIT>::a(t) * (Cfg<NSPLIT>::A_IMAGE / 16)),
-                    bd + (uint64_t)(Terms<NSPLIT>::b(t) * np * 2), idesc, S.accumulate || ks > 0 || t > 0);
-        umma_commit(&empty[st]);   // frees the slab when these MMAs have read it
+          for (int t = 0; t < Terms<NSPLIT>::N; ++t)
+            umma_bf16(d, ad + (uint64_t)(Terms<NSPLIT>::a(t) * (Cfg<NSPLIT>::A_IMAGE / 16)),
+                      bd + (uint64_t)(Terms<NSPLIT>::b(t) * np * 2), idesc, S.accumulate || ks > 0 || t > 0);
+          umma_commit(&empty[st]);   // frees the slab when these MMAs have read it
+          if (commit_k) umma_commit(&afree[ks]);
+        }
+        if (++st == ST) { st = 0; ph ^= 1u; }
       }
       __syncwarp();
-      if (++st == ST) { st = 0; ph ^= 1u; }
     }
   }
   __device__ void commit_acc() {
@@ -163,37 +201,51 @@ struct Pipe {
     tc_fence_before();                 // this thread's tcgen05.ld's are ordered before the arrive
     mbar_arrive(a_bar);
   }
+  // block b of the A operand may be overwritten: the MMAs of the last commit_k stage that read it are done
+  __device__ __forceinline__ void wait_free(int b) { mbar_wait(&afree[b], (f_phase >> b) & 1u); }
+  // hand block b of the A operand (this thread's row) to the MMA warp
+  __device__ __forceinline__ void publish(int b) {
+    fence_proxy_async();
+    tc_fence_before();
+    mbar_arrive(&kbar[b]);
+  }
 };
 
 // accumulator columns [col0, col0 + ncols) of this thread's row, this thread's column group
-// -> relu?(x + bias (+ gv)) -> A operand, k index = (c - col0).  ncols % 16 == 0.
+// -> relu(x + bias), columns >= n_real forced to 0 -> block (c / 16) of the A operand, published to the MMA warp.
+// n_free: blocks below this index wait for afree (the previous commit_k stage read them).
 // With GSUM (n divides 32, so a state's rows are an aligned lane group of this warp): also reduce the
 // activated fp32 values over the state's real rows with shuffles and store the mean to g_out[col * g_ld + state]
-// -- the global state of sarl.py:51-60, taken from registers instead of re-reading the bf16 images.
+// -- the global state of sarl.py:51-60, taken from registers instead of re-reading the 16-bit images.
 template <int NSPLIT, bool GSUM>
-__device__ __forceinline__ void epi_to_a(uint32_t tmem_row, int cg, int col0, int ncols, const float *__restrict__ bias,
-                                         const float *gv_row, bool relu, uint8_t *a_base, int row,
-                                         uint64_t *kbar = nullptr, int n = 1, int row_cnt = 0, float *g_out = nullptr,
-                                         int g_ld = 0) {
+__device__ __forceinline__ void epi_to_a(Pipe<NSPLIT> &pipe, uint32_t tmem_row, int cg, int col0, int ncols, int n_real,
+                                         const float *__restrict__ bias, uint8_t *a_base, int row, bool chase,
+                                         int n_free, int n = 1, int row_cnt = 0, float *g_out = nullptr, int g_ld = 0) {
   for (int c = 16 * cg; c < ncols; c += 16 * NCG) {
     float v[16];
     tmem_ld16(tmem_row + col0 + c, v);
+    const float4 *b4 = reinterpret_cast<const float4 *>(bias + c);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      float x = v[i] + __ldg(bias + c + i);
-      if (gv_row) x += gv_row[c + i];
-      v[i] = (relu && x < 0.0f) ? 0.0f : x;
+    for (int q = 0; q < 4; ++q) {
+      const float4 bb = __ldg(b4 + q);
+      const float x0 = v[4 * q] + bb.x, x1 = v[4 * q + 1] + bb.y, x2 = v[4 * q + 2] + bb.z, x3 = v[4 * q + 3] + bb.w;
+      v[4 * q] = x0 < 0.0f ? 0.0f : x0;           // ReLU that keeps NaN (a range overflow must stay visible)
+      v[4 * q + 1] = x1 < 0.0f ? 0.0f : x1;
+      v[4 * q + 2] = x2 < 0.0f ? 0.0f : x2;
+      v[4 * q + 3] = x3 < 0.0f ? 0.0f : x3;
     }
+    if (c + 16 > n_real) {   // padding columns may alias another accumulator's columns: they carry exact zeros
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (c + i >= n_real) v[i] = 0.0f;
+    }
+    if ((c >> 4) < n_free) pipe.wait_free(c >> 4);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const float u[8] = {v[8 * h], v[8 * h + 1], v[8 * h + 2], v[8 * h + 3], v[8 * h + 4], v[8 * h + 5], v[8 * h + 6], v[8 * h + 7]};
       store_a8<NSPLIT>(a_base, Cfg<NSPLIT>::A_IMAGE, row, c + 8 * h, u);
     }
-    if (kbar) {               // this block is k-step c/16 of the next stage: hand it to the MMA warp now
-      fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive(&kbar[c >> 4]);
-    }
+    if (chase) pipe.publish(c >> 4);
     if (GSUM) {
       const int r_in = row % n;                 // row index inside its state
       const bool real = r_in < row_cnt;         // padding rows do not enter the mean
@@ -234,6 +286,25 @@ __device__ __forceinline__ void epi_to_a(uint32_t tmem_row, int cg, int col0, in
   }
 }
 
+// The per-state mean of H1 (G[k][state]) as the A operand of the global half of attention.0: row r carries the
+// mean of its own state, so [H1 | G] . [W_local | W_global]^T accumulates in one TMEM accumulator (sarl.py:51-63).
+template <int NSPLIT>
+__device__ __forceinline__ void gx_to_a(Pipe<NSPLIT> &pipe, const float *G, int g_ld, int state, int cg, int h1d, int h1p,
+                                        uint8_t *a_base, int row, int n_free) {
+  for (int c = 16 * cg; c < h1p; c += 16 * NCG) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (c + i < h1d) ? G[(c + i) * g_ld + state] : 0.0f;
+    if ((c >> 4) < n_free) pipe.wait_free(c >> 4);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float u[8] = {v[8 * h], v[8 * h + 1], v[8 * h + 2], v[8 * h + 3], v[8 * h + 4], v[8 * h + 5], v[8 * h + 6], v[8 * h + 7]};
+      store_a8<NSPLIT>(a_base, Cfg<NSPLIT>::A_IMAGE, row, c + 8 * h, u);
+    }
+    pipe.publish(c >> 4);
+  }
+}
+
 // partial of sum_c relu(acc[c] + bias[c]) * w[c] over this thread's column group
 __device__ __forceinline__ float epi_dot(uint32_t tmem_row, int cg, int col0, int ncols, const float *__restrict__ bias,
                                          const float *__restrict__ w) {
@@ -256,7 +327,9 @@ __device__ __forceinline__ void pipe_init(Pipe<NSPLIT> &pipe, uint8_t *smem, con
   constexpr int ST = Cfg<NSPLIT>::STAGES;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
   pipe.full = bars; pipe.empty = bars + ST; pipe.acc_bar = bars + 2 * ST; pipe.a_bar = bars + 2 * ST + 1;
-  pipe.kbar = bars + 2 * ST + 2; pipe.k_phase = 0;
+  pipe.kbar = bars + 2 * ST + 2; pipe.afree = pipe.kbar + NKB;
+  static_assert((2 * ST + 2 + 2 * NKB) * 8 <= 512, "barrier region");
+  pipe.k_phase = 0; pipe.f_phase = 0;
   pipe.wbuf = smem + L.w; pipe.wpack = P.wpack;
   pipe.n_stage_slabs = P.n_slabs;
   uint2 *tab = reinterpret_cast<uint2 *>(smem + L.tab);
@@ -269,7 +342,7 @@ __device__ __forceinline__ void pipe_init(Pipe<NSPLIT> &pipe, uint8_t *smem, con
     for (int i = 0; i < ST; ++i) { mbar_init(&pipe.full[i], 1); mbar_init(&pipe.empty[i], 1); }
     mbar_init(pipe.acc_bar, 1);
     mbar_init(pipe.a_bar, NCREW);
-    for (int i = 0; i < KMAX / 16; ++i) mbar_init(&pipe.kbar[i], TILE_M);
+    for (int i = 0; i < NKB; ++i) { mbar_init(&pipe.kbar[i], TILE_M); mbar_init(&pipe.afree[i], 1); }
     fence_barrier_init();
   }
 }
@@ -293,7 +366,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
   constexpr int MAX_TS = Cfg<NSPLIT>::MAX_TS;
   const Smem L = smem_layout<NSPLIT>();
   uint8_t *A = smem + L.a;
-  float *GV = reinterpret_cast<float *>(smem + L.gv);   // holds G[k][MAX_TS] first, GV[state][KMAX] afterwards
+  float *G = reinterpret_cast<float *>(smem + L.g);     // G[k][MAX_TS]
   float *SC = reinterpret_cast<float *>(smem + L.sc), *XS = reinterpret_cast<float *>(smem + L.xs);
   __shared__ uint32_t tmem_slot;
   __shared__ int cnt[16];
@@ -315,22 +388,19 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
     // =================================== MMA warp (converged) ===================================
     pipe.leader = elect_one();
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      pipe.wait_a();
-      for (int h = 0; h < P.n_wide; ++h) pipe.mma_stage(P.st[ST_L0A + h], a_smem, tmem_base);
-      pipe.commit_acc();
-      for (int h = 0; h < P.n_wide; ++h) {
-        pipe.mma_stage(P.st[ST_L1A + h], a_smem, tmem_base, true);   // chases the wide-half epilogue
-        pipe.commit_acc();
-      }
-      pipe.mma_stage(P.st[ST_L2], a_smem, tmem_base, true);          // chases the H1 epilogue
-      pipe.mma_stage(P.st[ST_L4], a_smem, tmem_base);                // H1 fully written and its accumulator read
-      pipe.commit_acc();
-      pipe.wait_a();
-      pipe.mma_stage(P.st[ST_L3], a_smem, tmem_base);
-      pipe.commit_acc();
-      pipe.wait_a();
-      pipe.mma_stage(P.st[ST_L5], a_smem, tmem_base);
-      pipe.commit_acc();
+      pipe.wait_a();                                                               // X staged
+      for (int h = 0; h < P.n_wide; ++h) pipe.mma_stage(P.st[ST_L0A + h], a_smem, tmem_base, false, false);
+      pipe.commit_acc();                                                           // #1: mlp1.0 done
+      for (int h = 0; h < P.n_wide; ++h)                                           // chases the wide-half epilogues
+        pipe.mma_stage(P.st[ST_L1A + h], a_smem, tmem_base, true, h + 1 < P.n_wide);
+      pipe.commit_acc();                                                           // #2: mlp1.2 done
+      pipe.mma_stage(P.st[ST_L2], a_smem, tmem_base, true, false);                 // chases the H1 epilogue
+      pipe.mma_stage(P.st[ST_L4], a_smem, tmem_base, false, true);                 // H1 complete, its accumulator read
+      if (P.with_global) pipe.mma_stage(P.st[ST_L4G], a_smem, tmem_base, true, true);   // chases the G operand
+      pipe.commit_acc();                                                           // #3: mlp2.0 / attention.0 done
+      pipe.mma_stage(P.st[ST_L3], a_smem, tmem_base, true, true);                  // chases the T2 epilogue
+      pipe.mma_stage(P.st[ST_L5], a_smem, tmem_base, true, false);                 // chases the U epilogue
+      pipe.commit_acc();                                                           // #4: mlp2.2 / attention.2 done
     }
   } else if (warp == NCREW / 32 + 1) {
     if ((tid & 31) == 0) pipe.loader_loop();
@@ -340,7 +410,8 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
     const int cg = warp >> 2;                         // column group
     const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const int n = p.n, ts = p.ts, D = p.D;
-    const int h1d = P.h1d, a1p = P.st[ST_L4].np, h2d = P.h2d;
+    const int h1d = P.h1d, h2d = P.h2d;
+    const int h1b = P.st[ST_L2].ksteps;               // 16-column blocks of H1 (= k-steps of its readers)
     // this thread's 8 input values of a tile (k-chunk cg of row `row`), fetched one tile ahead so that the
     // HBM latency of the value-network input hides behind the previous tile's tail
     float xu[8];
@@ -376,34 +447,38 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
       if (cg == 0 && row < rows && row % n == 0)
         for (int k = 0; k < p.self_dim; ++k) XS[(row / n) * 8 + k] = xu[k];
       pipe.signal_a();
-      // ---- mlp1.0 -> mlp1.2, K chunked by the wide halves ------------------------------------------
-      pipe.wait_acc();
+      // ---- mlp1.0 -> mlp1.2, K chunked by the wide halves; the second half overwrites the blocks of the first
+      //      as mlp1.2's first K chunk releases them --------------------------------------------------------
+      pipe.wait_acc();                                                             // #1
       for (int h = 0; h < P.n_wide; ++h) {
         const TcStage &W = P.st[ST_L0A + h];
-        epi_to_a<NSPLIT, false>(tmem_row, cg, W.acc_col, W.np, P.bias[0] + W.n_lo, nullptr, true, A, row, pipe.kbar);
+        const int n_free = h ? P.st[ST_L1A + h - 1].ksteps : 0;
+        epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, W.acc_col, W.np, W.n_real, P.bias[0] + W.n_lo, A, row, true, n_free);
+        if (h) pipe.f_phase ^= low_bits(n_free);
         pipe.stamp();
-        pipe.wait_acc();
       }
       // ---- H1 -> A; mlp2.0 and attention.0 (local half) share it -------------------------------------
+      pipe.wait_acc();                                                             // #2
       const bool gsum = P.with_global && (32 % n == 0);
+      const int st_of_row = min(row / n, ts - 1);
       {
         const TcStage &S = P.st[ST_L1A];
         if (gsum) {
           crew_sync();   // cnt[] of this tile is visible
-          const int st_of_row = min(row / n, ts - 1);
-          epi_to_a<NSPLIT, true>(tmem_row, cg, S.acc_col, S.np, P.bias[1], nullptr, true, A, row, pipe.kbar, n,
-                                 cnt[st_of_row], GV, MAX_TS);
+          epi_to_a<NSPLIT, true>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, P.bias[1], A, row, true, 0, n,
+                                 cnt[st_of_row], G, MAX_TS);
         } else {
-          epi_to_a<NSPLIT, false>(tmem_row, cg, S.acc_col, S.np, P.bias[1], nullptr, true, A, row, pipe.kbar);
+          epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, P.bias[1], A, row, true, 0);
         }
       }
       pipe.stamp();
-      // while those MMAs run: GV = attention.0.bias + W_att0[:, h1:] . G in place   (sarl.py:51-63)
-      crew_sync();   // every crew thread's H1 stores, G partials and cnt are visible
+      // ---- global state: G -> A as the second K chunk of attention.0 (sarl.py:51-63) -----------------------
       if (P.with_global) {
-        if (!gsum) {
-          // generic row counts: mean over the state's rows of H1, read back from the A images
-          for (int i = tid; i < ts * h1d; i += NCREW) {
+        if (gsum) {
+          __syncwarp();    // G[., state] of this warp's states and column group was written by this warp
+        } else {
+          crew_sync();     // every H1 block is in the A images
+          for (int i = tid; i < ts * h1d; i += NCREW) {   // generic row counts: mean read back from the images
             const int k = i % h1d, s = i / h1d;
             const int c = cnt[s];
             float acc = 0.0f;
@@ -415,73 +490,33 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
                 v += Fmt<NSPLIT>::from16(*reinterpret_cast<const uint16_t *>(A + (size_t)sp * Cfg<NSPLIT>::A_IMAGE + off));
               acc += v;
             }
-            GV[k * MAX_TS + s] = c > 0 ? acc / (float)c : 0.0f;
+            G[k * MAX_TS + s] = c > 0 ? acc / (float)c : 0.0f;
           }
+          crew_sync();
         }
-        crew_sync();
-        // thread -> one output column, 8 states: each weight is fetched once per 8 states
-        const int c = tid & 255, sh = tid >> 8;
-        const bool live = c < a1p && sh * 8 < ts;
-        float acc[8];
-        if (live) {
-          const float b = __ldg(P.bias[4] + c);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = b;
-          const float *wcol = P.wg + c;
-          // the weights come from L2 (no L1 to speak of with 227 KB of shared memory in use): keep 20
-          // independent loads in flight per thread, the loop is latency-bound otherwise
-          constexpr int UK = 10;
-          int k = 0;
-          for (; k + UK <= h1d; k += UK) {
-            float wv[UK];
-#pragma unroll
-            for (int j = 0; j < UK; ++j) wv[j] = __ldg(wcol + (size_t)(k + j) * a1p);
-#pragma unroll
-            for (int j = 0; j < UK; ++j) {
-              const float4 g0 = *reinterpret_cast<const float4 *>(GV + (k + j) * MAX_TS + sh * 8);
-              const float4 g1 = *reinterpret_cast<const float4 *>(GV + (k + j) * MAX_TS + sh * 8 + 4);
-              acc[0] = fmaf(g0.x, wv[j], acc[0]); acc[1] = fmaf(g0.y, wv[j], acc[1]);
-              acc[2] = fmaf(g0.z, wv[j], acc[2]); acc[3] = fmaf(g0.w, wv[j], acc[3]);
-              acc[4] = fmaf(g1.x, wv[j], acc[4]); acc[5] = fmaf(g1.y, wv[j], acc[5]);
-              acc[6] = fmaf(g1.z, wv[j], acc[6]); acc[7] = fmaf(g1.w, wv[j], acc[7]);
-            }
-          }
-          for (; k < h1d; ++k) {
-            const float wv = __ldg(wcol + (size_t)k * a1p);
-            const float4 g0 = *reinterpret_cast<const float4 *>(GV + k * MAX_TS + sh * 8);
-            const float4 g1 = *reinterpret_cast<const float4 *>(GV + k * MAX_TS + sh * 8 + 4);
-            acc[0] = fmaf(g0.x, wv, acc[0]); acc[1] = fmaf(g0.y, wv, acc[1]);
-            acc[2] = fmaf(g0.z, wv, acc[2]); acc[3] = fmaf(g0.w, wv, acc[3]);
-            acc[4] = fmaf(g1.x, wv, acc[4]); acc[5] = fmaf(g1.y, wv, acc[5]);
-            acc[6] = fmaf(g1.z, wv, acc[6]); acc[7] = fmaf(g1.w, wv, acc[7]);
-          }
-        }
-        crew_sync();   // all reads of G done: overwrite in place with GV
-        if (live) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) GV[(sh * 8 + j) * KMAX + c] = acc[j];
-        }
-      } else {
-        for (int i = tid; i < ts * a1p; i += NCREW) GV[(i / a1p) * KMAX + (i % a1p)] = __ldg(P.bias[4] + (i % a1p));
+        gx_to_a<NSPLIT>(pipe, G, MAX_TS, st_of_row, cg, h1d, 16 * h1b, A, row, h1b);
+        pipe.f_phase ^= low_bits(h1b);                  // attention.0 (local half) released every H1 block
+        pipe.stamp();
       }
-      crew_sync();
-      pipe.wait_acc();
-      // ---- T2 -> A; mlp2.2 -------------------------------------------------------------------------
+      // ---- T2 = relu(mlp2.0) -> A; mlp2.2 chases it --------------------------------------------------------
       {
         const TcStage &S = P.st[ST_L2];
-        epi_to_a<NSPLIT, false>(tmem_row, cg, S.acc_col, S.np, P.bias[2], nullptr, true, A, row);
+        epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, P.bias[2], A, row, true, h1b);
+        pipe.f_phase ^= low_bits(h1b);                  // attention.0's last K chunk released its blocks
       }
-      pipe.signal_a();
-      pipe.wait_acc();
-      // ---- U = relu(att0 + GV[state]) -> A; attention.2 --------------------------------------------------
+      pipe.stamp();
+      crew_sync();       // every read of the mlp2.0 accumulator is done: attention.2 will reuse its columns
+      pipe.wait_acc();                                                             // #3: attention.0 complete
+      // ---- U = relu(attention.0) -> A; attention.2 chases it ----------------------------------------------
       {
         const TcStage &S = P.st[ST_L4];
-        const int s = min(row / n, ts - 1);
-        epi_to_a<NSPLIT, false>(tmem_row, cg, S.acc_col, S.np, P.zero_bias, GV + s * KMAX, true, A, row);
+        const int n_free = P.st[ST_L3].ksteps;
+        epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, P.bias[4], A, row, true, n_free);
+        pipe.f_phase ^= low_bits(n_free);
       }
-      pipe.signal_a();
+      pipe.stamp();
       if (tile + gridDim.x < n_tiles) load_x(tile + gridDim.x);   // next tile's input, consumed after the tail
-      pipe.wait_acc();
+      pipe.wait_acc();                                                             // #4
       // ---- attention.4 score, masked softmax, pooling (sarl.py:64-78) --------------------------------------
       {
         const TcStage &S = P.st[ST_L5];
@@ -492,10 +527,10 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
       if (n == 16) {
         // a state = 16 aligned lanes of this warp: softmax and pooling stay in registers (shuffles), the
         // pooled feature goes straight to the joint row -- no scratch, no further block synchronisation
-        const int lane = tid & 31, st_of_row = row >> 4;
-        const int c_real = cnt[min(st_of_row, ts - 1)];
+        const int lane = tid & 31, st_row = row >> 4;
+        const int c_real = cnt[min(st_row, ts - 1)];
         const float sc = ((SC[row] + SC[TILE_M + row]) + (SC[2 * TILE_M + row] + SC[3 * TILE_M + row])) + P.b6;
-        const bool real = st_of_row < ns && (row & 15) < c_real;
+        const bool real = st_row < ns && (row & 15) < c_real;
         float e = (real && sc != 0.0f) ? expf(sc) : 0.0f;
         float sum = e;
 #pragma unroll
@@ -506,7 +541,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
           float v[16];
           tmem_ld16(tmem_row + S.acc_col + c, v);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = real ? (v[i] + __ldg(P.bias[3] + c + i)) * wrow : 0.0f;
+          for (int i = 0; i < 16; ++i) v[i] = (real && c + i < h2d) ? (v[i] + __ldg(P.bias[3] + c + i)) * wrow : 0.0f;
           float w8[8], w4[4], w2[2];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -526,7 +561,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
           const float send = (lane & 1) ? w2[0] : w2[1], keep = (lane & 1) ? w2[1] : w2[0];
           const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 1);
           const int col = c + (lane & 15);
-          if (st_of_row < ns && col < h2d) p.joint[(size_t)(s0 + st_of_row) * p.jd + p.self_dim + col] = tot;
+          if (st_row < ns && col < h2d) p.joint[(size_t)(s0 + st_row) * p.jd + p.self_dim + col] = tot;
         }
         if (tid < ns * p.self_dim) {
           const int s = tid / p.self_dim, k = tid % p.self_dim;
@@ -612,13 +647,11 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
     pipe.leader = elect_one();
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       pipe.wait_a();
-      for (int h = 0; h < P.n_wide; ++h) pipe.mma_stage(P.st[ST_L0A + h], a_smem, tmem_base);
+      for (int h = 0; h < P.n_wide; ++h) pipe.mma_stage(P.st[ST_L0A + h], a_smem, tmem_base, false, false);
       pipe.commit_acc();
-      for (int h = 0; h < P.n_wide; ++h) {
-        pipe.mma_stage(P.st[ST_L1A + h], a_smem, tmem_base, true);
-        pipe.commit_acc();
-      }
-      pipe.mma_stage(P.st[ST_L2], a_smem, tmem_base, true);
+      for (int h = 0; h < P.n_wide; ++h) pipe.mma_stage(P.st[ST_L1A + h], a_smem, tmem_base, true, h + 1 < P.n_wide);
+      pipe.commit_acc();
+      pipe.mma_stage(P.st[ST_L2], a_smem, tmem_base, true, false);
       pipe.commit_acc();
     }
   } else if (warp == NCREW / 32 + 1) {
@@ -642,12 +675,14 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
       pipe.wait_acc();
       for (int h = 0; h < P.n_wide; ++h) {
         const TcStage &W = P.st[ST_L0A + h];
-        epi_to_a<NSPLIT, false>(tmem_row, cg, W.acc_col, W.np, P.bias[0] + W.n_lo, nullptr, true, A, row, pipe.kbar);
-        pipe.wait_acc();
+        const int n_free = h ? P.st[ST_L1A + h - 1].ksteps : 0;
+        epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, W.acc_col, W.np, W.n_real, P.bias[0] + W.n_lo, A, row, true, n_free);
+        if (h) pipe.f_phase ^= low_bits(n_free);
       }
+      pipe.wait_acc();
       {
         const TcStage &S = P.st[ST_L1A];
-        epi_to_a<NSPLIT, false>(tmem_row, cg, S.acc_col, S.np, P.bias[1], nullptr, true, A, row, pipe.kbar);
+        epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, P.bias[1], A, row, true, 0);
       }
       pipe.wait_acc();
       {
@@ -657,6 +692,7 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
       crew_sync();
       if (tid < TILE_M && s0 + tid < p.n_states)
         p.values[s0 + tid] = ((SC[tid] + SC[TILE_M + tid]) + (SC[2 * TILE_M + tid] + SC[3 * TILE_M + tid])) + P.b6;
+      tc_fence_before();
       crew_sync();   // SC is rewritten by the next tile; the next A stores follow every TMEM read above
     }
   }
@@ -806,6 +842,7 @@ int ebc_tc_prepare(ebc_sim *s, const ebc_weights *w, int mode_index, int nsplit)
       const int np = h ? np1 : np0;
       TcStage &S = P.st[ST_L0A + h];
       S.np = np; S.ksteps = in_pad / 16; S.acc_col = lo; S.accumulate = 0; S.n_lo = lo;
+      S.n_real = wide->out_dim - lo < np ? wide->out_dim - lo : np;
       pk.add_stage(wide->weight, wide->in_dim, lo, wide->out_dim, np, 0, wide->in_dim, S.ksteps, 0);
       lo += np;
     }
@@ -813,7 +850,7 @@ int ebc_tc_prepare(ebc_sim *s, const ebc_weights *w, int mode_index, int nsplit)
     for (int h = 0; h < P.n_wide; ++h) {
       const int kp = h ? np1 : np0;
       TcStage &S = P.st[ST_L1A + h];
-      S.np = midp; S.ksteps = kp / 16; S.acc_col = col_mid; S.accumulate = h; S.n_lo = 0;
+      S.np = midp; S.ksteps = kp / 16; S.acc_col = col_mid; S.accumulate = h; S.n_lo = 0; S.n_real = mid->out_dim;
       pk.add_stage(mid->weight, mid->in_dim, 0, mid->out_dim, midp, lo, mid->in_dim, S.ksteps, 0);
       lo += kp;
     }
@@ -823,6 +860,7 @@ int ebc_tc_prepare(ebc_sim *s, const ebc_weights *w, int mode_index, int nsplit)
   };
   auto simple_stage = [&](Packer &pk, TcStage &S, const ebc_linear *l, int in_real, int in_pad, int acc_col, int k_col_off) {
     S.np = pad16(l->out_dim); S.ksteps = in_pad / 16; S.acc_col = acc_col; S.accumulate = 0; S.n_lo = 0;
+    S.n_real = l->out_dim;
     pk.add_stage(l->weight, l->in_dim, 0, l->out_dim, S.np, 0, in_real, S.ksteps, k_col_off);
   };
 
@@ -834,25 +872,34 @@ int ebc_tc_prepare(ebc_sim *s, const ebc_weights *w, int mode_index, int nsplit)
   size_t be0, be1, bm0, bm1;
   if (build_front(pe, E, m10, m12, 32, be0, be1)) return 1;
   const int h1p = pad16(h1);
+  // TMEM columns of the second half of the chain.  mlp2.0 (L2), attention.0 (L4) and mlp2.2 (L3) are alive
+  // together (L3 chases the epilogue of L2 while L4 waits for its own epilogue); attention.2 (L5) reuses L2's
+  // columns.  When the padded widths do not fit in 512 columns the accumulators are packed at their REAL
+  // widths rounded to 8: a stage's zero-weight padding columns then alias the first columns of its neighbour,
+  // which is harmless because (i) the MMA warp issues L2, L4, L3 in that order, so a stage's (zero) padding
+  // writes land before its neighbour's first MMA, and (ii) every epilogue forces padding columns to zero.
+  const int np2 = pad16(m20->out_dim), np4 = pad16(a0->out_dim), np3 = pad16(m22->out_dim), np5 = pad16(a2->out_dim);
+  int c4 = np2, c3 = np2 + np4;
+  if (c3 + np3 > TMEM_COLS) {
+    c4 = (m20->out_dim + 7) / 8 * 8;
+    c3 = c4 + (a0->out_dim + 7) / 8 * 8;
+    if (c3 + np3 > TMEM_COLS) return 1;
+  }
+  if (np5 > c3) return 1;
+  // slab order = issue order of the MMA warp: L2, L4, L4G, L3, L5
   simple_stage(pe, E.st[ST_L2], m20, h1, h1p, 0, 0);                               // mlp2.0
-  simple_stage(pe, E.st[ST_L4], a0, h1, h1p, E.st[ST_L2].np, 0);                   // attention.0, local half
-  simple_stage(pe, E.st[ST_L3], m22, m20->out_dim, pad16(m20->out_dim), 0, 0);     // mlp2.2
-  simple_stage(pe, E.st[ST_L5], a2, a0->out_dim, pad16(a0->out_dim), E.st[ST_L4].acc_col, 0);   // attention.2
-  if (E.st[ST_L2].np + E.st[ST_L4].np > TMEM_COLS) return 1;
+  simple_stage(pe, E.st[ST_L4], a0, h1, h1p, c4, 0);                               // attention.0, local half
+  if (w->with_global_state) {                                                      // attention.0, global half
+    simple_stage(pe, E.st[ST_L4G], a0, h1, h1p, c4, h1);
+    E.st[ST_L4G].accumulate = 1;
+  }
+  simple_stage(pe, E.st[ST_L3], m22, m20->out_dim, pad16(m20->out_dim), c3, 0);    // mlp2.2
+  simple_stage(pe, E.st[ST_L5], a2, a0->out_dim, pad16(a0->out_dim), 0, 0);        // attention.2
   const size_t be2 = push_f(m20->bias, m20->out_dim, E.st[ST_L2].np);
   const size_t be3 = push_f(m22->bias, m22->out_dim, E.st[ST_L3].np);
   const size_t be4 = push_f(a0->bias, a0->out_dim, E.st[ST_L4].np);
   const size_t be5 = push_f(a2->bias, a2->out_dim, E.st[ST_L5].np);
   const size_t we6 = push_f(a4->weight, a4->in_dim, E.st[ST_L5].np);
-  const size_t zero = push_f(nullptr, 0, KMAX);
-  // global half of attention.0, fp32, [k][a1p]
-  const int a1p = E.st[ST_L4].np;
-  const size_t wg = fl.size();
-  if (w->with_global_state) {
-    fl.resize(wg + (size_t)h1 * a1p, 0.0f);
-    for (int c = 0; c < a0->out_dim; ++c)
-      for (int k = 0; k < h1; ++k) fl[wg + (size_t)k * a1p + c] = a0->weight[(size_t)c * a0->in_dim + h1 + k];
-  }
   if (build_front(pm, M, p0, p2, pad16(p0->in_dim), bm0, bm1)) return 1;
   simple_stage(pm, M.st[ST_L2], p4, p2->out_dim, pad16(p2->out_dim), 0, 0);        // mlp3.4
   const size_t bm2 = push_f(p4->bias, p4->out_dim, M.st[ST_L2].np);
@@ -882,12 +929,11 @@ int ebc_tc_prepare(ebc_sim *s, const ebc_weights *w, int mode_index, int nsplit)
   E.wpack = d + o_pe; E.n_slabs = (int)n_e;
   E.slab_off = reinterpret_cast<const uint32_t *>(d + o_eo); E.slab_bytes = reinterpret_cast<const uint32_t *>(d + o_eb);
   E.bias[0] = dfl + be0; E.bias[1] = dfl + be1; E.bias[2] = dfl + be2; E.bias[3] = dfl + be3;
-  E.bias[4] = dfl + be4; E.bias[5] = dfl + be5; E.w6 = dfl + we6; E.b6 = a4->bias[0]; E.zero_bias = dfl + zero;
-  E.wg = dfl + wg; E.with_global = w->with_global_state ? 1 : 0; E.h1d = h1; E.h2d = m22->out_dim;
+  E.bias[4] = dfl + be4; E.bias[5] = dfl + be5; E.w6 = dfl + we6; E.b6 = a4->bias[0];
+  E.with_global = w->with_global_state ? 1 : 0; E.h1d = h1; E.h2d = m22->out_dim;
   M.wpack = d + o_pm; M.n_slabs = (int)n_m;
   M.slab_off = reinterpret_cast<const uint32_t *>(d + o_mo); M.slab_bytes = reinterpret_cast<const uint32_t *>(d + o_mb);
   M.bias[0] = dfl + bm0; M.bias[1] = dfl + bm1; M.bias[2] = dfl + bm2; M.w6 = dfl + wm6; M.b6 = p6->bias[0];
-  M.zero_bias = dfl + zero;
   if (T.slab) cudaFree(T.slab);
   T.slab = d;
   T.entity = E;

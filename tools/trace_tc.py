@@ -20,20 +20,23 @@ buf=(ctypes.c_longlong*4096)()
 sim.be.lib.ebc_debug_trace(sim.h, buf, 4096)
 raw=np.array(buf[:], dtype=np.int64); t=raw[:2048]; t=t[t>0]; tm=raw[2048:]; tm=tm[tm>0]
 d=np.diff(t)
-per=12
-names=["MMA L0 (sigX->acc)","epi wide0","MMA L1A","epi wide1","MMA L1B","epi H1","MMA L2+L4 (G/GV overlapped)","epi T2","MMA L3","epi U","MMA L5","tail (score,softmax,pool,joint)+X stage"]
+per=11
+names=["MMA mlp1.0 (X signalled -> acc)","epilogue wide half 0","epilogue wide half 1 (chases mlp1.2a)","wait mlp1.2 complete",
+       "epilogue H1 (+ state means)","G operand (chases attention.0 local)","epilogue T2 (chases attention.0 global)",
+       "crew sync + wait attention.0 complete","epilogue U (chases mlp2.2)","wait attention.2 complete",
+       "tail (score, softmax, pooling, joint) + next X"]
 ntile=(len(t)-1)//per
 arr=d[:ntile*per].reshape(ntile,per).astype(float)
 mhz=1965.0
 print("mode",mode,"tiles traced",ntile)
-for i,nm in enumerate(names): print("%-45s mean %8.0f cyc = %6.2f us   (min %7.0f max %7.0f)"%(nm,arr[2:,i].mean(),arr[2:,i].mean()/mhz,arr[2:,i].min(),arr[2:,i].max()))
+for i,nm in enumerate(names): print("%-48s mean %8.0f cyc = %6.2f us   (min %7.0f max %7.0f)"%(nm,arr[2:,i].mean(),arr[2:,i].mean()/mhz,arr[2:,i].min(),arr[2:,i].max()))
 print("per tile total %.1f us"%(arr[2:].sum(1).mean()/mhz))
-
-if len(tm) >= 60:
-    # MMA-thread stamps: (kbar[0] passed, kbar[last] passed) for L1A, L1B, L2 of every tile = 6 per tile
-    tile = 20
-    base = t[tile*per]            # crew: signal_a(X) of that tile
-    print("tile %d timeline (us from X signal):" % tile)
-    crew = (t[tile*per:(tile+1)*per] - base)/mhz
-    print("  crew stamps:", np.round(crew,2))
-    print("  mma  stamps:", np.round((tm[tile*6:(tile+1)*6] - base)/mhz,2), "(kbar first/last passed for L1A, L1B, L2)")
+if len(tm) >= 400:
+    # MMA-warp stamps per tile: X seen, then "all k-steps issued" for L0a, L0b, L1A, L1B, L2, L4, L4G, L3, L5
+    mper = 10
+    mt = tm[:(len(tm)//mper)*mper].reshape(-1, mper)
+    for tile in (20, 21):
+        base = t[tile*per]            # crew: signal_a(X) of that tile
+        print("tile %d (us from the crew's X signal):" % tile)
+        print("  crew: X, acc1, W0a, W0b, acc2, H1, G, T2, acc3, U, acc4 :", np.round((t[tile*per:(tile+1)*per] - base)/mhz,2))
+        print("  mma : Xseen, L0a, L0b, L1A, L1B, L2, L4, L4G, L3, L5 issued:", np.round((mt[tile] - base)/mhz,2))
