@@ -33,8 +33,17 @@ struct TcStage {         // one GEMM stage: acc[:, acc_col : acc_col + np] (+)= 
   int n_real;            // real output columns of this stage (the rest of np is padding)
 };
 
+struct TcSched {         // one entry of the MMA warp's per-tile schedule
+  uint8_t stage;         // ST_*
+  uint8_t chase;         // k-step b waits for block b of the A operand (the producing epilogue is still running)
+  uint8_t commit_k;      // release block b of the A operand to the next epilogue as soon as its MMAs complete
+  uint8_t commit_acc;    // then tell the crew that every MMA issued so far has completed
+};
+
 struct TcProgram {
   TcStage st[ST_COUNT];
+  TcSched sched[12];
+  int n_sched;
   int n_wide;                    // 1 or 2 halves of the wide first layer
   const uint8_t *wpack;          // packed bf16 weight slabs (device)
   const uint32_t *slab_off, *slab_bytes;

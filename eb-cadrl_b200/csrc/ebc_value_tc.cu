@@ -38,7 +38,7 @@ namespace {
 using namespace tc;
 
 constexpr int NCREW = 512;                      // epilogue threads: 4 lane quarters x 4 column groups
-constexpr int NT = NCREW + 64;                  // + the MMA warp (16) and the weight-loader warp (17)
+constexpr int NT = NCREW + 96;                  // + the MMA warp (16), the weight-loader warp (17), the scout warp (18)
 constexpr int MAX_SLABS = 120;                  // slabs per tile (entity program: 88, mlp3: 46)
 constexpr int NCG = NCREW / TILE_M;             // column groups
 constexpr int KMAX = 208;                       // widest A operand chunk kept in shared memory
@@ -65,7 +65,7 @@ __host__ __device__ inline Smem smem_layout() {
   uint32_t off = 0;
   s.a = off; off += Cfg<NSPLIT>::A_BYTES;
   s.w = off; off += Cfg<NSPLIT>::W_BYTES;
-  s.g = off; off += Cfg<NSPLIT>::MAX_TS * KMAX * 4;    // G[k][state]: per-state mean of H1
+  s.g = off; off += Cfg<NSPLIT>::MAX_TS * KMAX * 4;    // G[state][k]: per-state mean of H1
   s.sc = off; off += TILE_M * 4 * (NCG + 1);           // partial scores per column group, softmax weights
   s.xs = off; off += 16 * 8 * 4;                        // self-state part of each state's first row
   s.tab = off; off += MAX_SLABS * 8;                    // (offset, bytes) of every slab of the per-tile program
@@ -89,6 +89,8 @@ struct Pipe {
   int n_stage_slabs;         // slabs per tile
   const uint2 *tab;          // shared memory: (byte offset, bytes) of each slab of the per-tile sequence
   long long total;           // slab count over all tiles of this CTA (loader)
+  uint32_t *ready;           // scout -> MMA warp: k-steps (counted over the whole launch) whose operands are in place
+  uint32_t issued, seen;     // MMA warp: k-steps issued so far / the scout's count when last read
   uint32_t st, ph;           // MMA warp: ring slot of the next slab and its full-barrier parity
   bool leader;               // MMA warp: the lane that issues tcgen05.mma / tcgen05.commit
   uint32_t acc_phase, a_phase;
@@ -98,10 +100,6 @@ struct Pipe {
   int trace_pos;
   __device__ __forceinline__ void stamp() {
     if (trace && threadIdx.x == 0 && blockIdx.x == 0 && trace_pos < 2048) trace[trace_pos++] = clock64();
-  }
-
-  __device__ __forceinline__ void stamp_mma() {   // MMA warp's own stamps live in the upper half
-    if (trace && leader && blockIdx.x == 0 && trace_pos < 2048) trace[2048 + trace_pos++] = clock64();
   }
 
   // ---- loader thread: streams every slab of every tile of this CTA through the ring ---------------------
@@ -117,12 +115,64 @@ struct Pipe {
       if (++idx == (uint32_t)n_stage_slabs) idx = 0;
     }
   }
+  // ---- scout thread: follows the per-tile schedule one k-step at a time, waits (blocking, hardware-suspended
+  //      mbarrier.try_wait) until that k-step's A block and weight slab are there, and publishes the running
+  //      count of issuable k-steps.  The MMA warp then needs one shared-memory load per batch instead of one
+  //      mbarrier round trip per k-step: the tensor pipe's queue is shallow, so every cycle the issuing warp
+  //      spends polling is a cycle the pipe idles (measured: ~450 polling cycles per 1250 cycles of MMA work).
+  __device__ void scout_loop(const TcProgram &P, long long my_tiles) {   // whole warp, converged
+    constexpr uint32_t ST = Cfg<NSPLIT>::STAGES;
+    constexpr uint32_t LOOK = ST < 8 ? ST : 8;        // k-steps examined per poll
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t count = 0, slot = 0, par = 0, kph = 0, aph = 0;
+    for (long long t = 0; t < my_tiles; ++t) {
+      mbar_wait(a_bar, aph);              // the tile's input operand is staged
+      aph ^= 1u;
+      for (int i = 0; i < P.n_sched; ++i) {
+        const int ksteps = P.st[P.sched[i].stage].ksteps;
+        const bool chase = P.sched[i].chase != 0;
+        int ks = 0;
+        uint32_t idle = 0;
+        while (ks < ksteps) {
+          // lanes 0-7 test kbar[ks ..], lanes 8-15 the next ring slots: one non-blocking test for all of them
+          bool ok = false;
+          if (lane < 8) {
+            const int k = ks + (int)lane;
+            ok = !chase || (k < ksteps && mbar_test(&kbar[k], (kph >> k) & 1u));
+          } else if (lane < 8 + LOOK) {
+            uint32_t sl = slot + lane - 8, pp = par;
+            if (sl >= ST) { sl -= ST; pp ^= 1u; }
+            ok = mbar_test(&full[sl], pp);
+          }
+          const uint32_t m = __ballot_sync(0xffffffffu, ok);
+          const uint32_t both = m & (m >> 8) & 0xFFu;
+          int nready = __ffs((int)~both) - 1;            // leading k-steps with both barriers complete
+          if (nready > ksteps - ks) nready = ksteps - ks;
+          if (nready == 0) {
+            // sleep (hardware-suspended) on the first barrier that is missing, then look again
+            if (chase && !(m & 1u)) mbar_try_wait(&kbar[ks], (kph >> ks) & 1u);
+            else mbar_try_wait(&full[slot], par);
+            if (++idle > (1u << 22)) __trap();
+            continue;
+          }
+          idle = 0;
+          if (chase) kph ^= low_bits(nready) << ks;
+          ks += nready;
+          slot += (uint32_t)nready;
+          if (slot >= ST) { slot -= ST; par ^= 1u; }
+          count += (uint32_t)nready;
+          __syncwarp();                   // the observations of lanes 0-15 are ordered before the release below
+          if (lane == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(ready)), "r"(count) : "memory");
+        }
+      }
+    }
+  }
   // ---- MMA warp: every lane runs the loops (warp-uniform values -> uniform registers, no per-instruction
   //      election loops), one elected lane issues the tcgen05 instructions ---------------------------------
-  __device__ void wait_a() {           // the crew has written (and fenced) the A operand
-    mbar_wait(a_bar, a_phase);
-    a_phase ^= 1u;
-    tc_fence_after();
+  __device__ __forceinline__ uint32_t ready_count() {
+    uint32_t r;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(r) : "r"(smem_u32(ready)) : "memory");
+    return r;
   }
   // chase:    the crew is still writing the A operand; k-step ks is issued as soon as its two k-chunks (one
   //           16-column block of the previous stage's epilogue) have been stored and fenced by all 128 rows
@@ -136,56 +186,47 @@ struct Pipe {
     // descriptors differ only in the 14-bit start-address field (16-byte units): build once, add offsets
     const uint64_t a_desc0 = make_smem_desc(a_smem, A_CHUNK_BYTES, 128);
     const uint64_t b_desc0 = make_smem_desc(smem_u32(wbuf), np * 16, 128);
-    // Up to four k-steps per trip: lanes 0-3 test kbar[ks .. ks+3], lanes 4-7 test the next four ring slots
-    // (non-blocking mbarrier.test_wait, one instruction for all eight barriers), then every k-step whose two
-    // barriers have completed is issued in order.  One barrier round trip per k-step would leave the tensor
-    // pipe waiting on this warp's own latency (measured: ~500 cycles per k-step against 312 of MMA work).
-    const uint32_t lane = threadIdx.x & 31;
-    int ks = 0;
-    uint32_t idle = 0;
-    while (ks < ksteps) {
-      bool ok = false;
-      if (lane < 4) {
-        const int k = ks + (int)lane;
-        ok = !chase || (k < ksteps && mbar_test(&kbar[k], (k_phase >> k) & 1u));
-      } else if (lane < 8) {
-        uint32_t slot = st + lane - 4, par = ph;
-        if (slot >= ST) { slot -= ST; par ^= 1u; }
-        ok = mbar_test(&full[slot], par);
-      }
-      const uint32_t m = __ballot_sync(0xffffffffu, ok);
-      __syncwarp();                      // the observations of lanes 0-7 are ordered before the leader's MMAs
-      const uint32_t both = m & (m >> 4) & 0xFu;
-      int nready = __ffs((int)~both) - 1;            // k-steps ks .. ks + nready - 1 are ready (in order)
-      if (nready > ksteps - ks) nready = ksteps - ks;
-      if (nready == 0) {
-        if (++idle > (1u << 22)) __trap();   // bounded like mbar_wait: a protocol bug traps instead of hanging
-        continue;
-      }
-      if (trace && leader && blockIdx.x == 0 && trace_pos < 2048)   // diagnostics: (clock, idle polls, barrier mask)
-        trace[2048 + trace_pos++] = (clock64() << 16) | (long long)((idle > 255 ? 255 : idle) << 8) | (long long)(m & 0xFFu);
-      idle = 0;
-      tc_fence_after();
-      for (int j = 0; j < nready; ++j, ++ks) {
-        if (chase) k_phase ^= 1u << ks;
-        const uint64_t ad = a_desc0 + (uint64_t)((uint32_t)ks * (2 * A_CHUNK_BYTES / 16));
-        const uint64_t bd = b_desc0 + (uint64_t)(st * (Cfg<NSPLIT>::STAGE_BYTES / 16));
-        if (leader) {
-#pragma unroll
-          for (int t = 0; t < Terms<NSPLIT>::N; ++t)
-            umma_bf16(d, ad + (uint64_t)(Terms<NSPLIT>::a(t) * (Cfg<NSPLIT>::A_IMAGE / 16)),
-                      bd + (uint64_t)(Terms<NSPLIT>::b(t) * np * 2), idesc, S.accumulate || ks > 0 || t > 0);
-          umma_commit(&empty[st]);   // frees the slab when these MMAs have read it
-          if (commit_k) umma_commit(&afree[ks]);
+    // The k-step loop is warp-uniform (trip count from the program, counters incremented unconditionally), so
+    // the descriptors stay in uniform registers; the only data-dependent part is the wait below, which carries
+    // no state.  `seen` caches the scout's count: one shared-memory load per batch of cleared k-steps.
+    for (int ks = 0; ks < ksteps; ++ks) {
+      if ((int)(seen - issued) <= 0) {
+        uint32_t idle = 0;
+        while ((int)((seen = ready_count()) - issued) <= 0) {
+          __nanosleep(40);                     // the scout sleeps on the barriers; this warp only watches its count
+          if (++idle > (1u << 24)) __trap();   // bounded: a protocol bug traps instead of hanging
         }
-        if (++st == ST) { st = 0; ph ^= 1u; }
+        tc_fence_after();
+        if (trace && leader && blockIdx.x == 0 && trace_pos < 2040)   // diagnostics: (clock, cleared k-steps)
+          trace[2048 + trace_pos++] = (clock64() << 16) | (long long)((seen - issued) & 0xFFFFu);
+      }
+      ++issued;
+      if (chase) k_phase ^= 1u << ks;
+      const uint64_t ad = a_desc0 + (uint64_t)((uint32_t)ks * (2 * A_CHUNK_BYTES / 16));
+      const uint64_t bd = b_desc0 + (uint64_t)(st * (Cfg<NSPLIT>::STAGE_BYTES / 16));
+      if (leader) {
+#pragma unroll
+        for (int t = 0; t < Terms<NSPLIT>::N; ++t)
+          umma_bf16(d, ad + (uint64_t)(Terms<NSPLIT>::a(t) * (Cfg<NSPLIT>::A_IMAGE / 16)),
+                    bd + (uint64_t)(Terms<NSPLIT>::b(t) * np * 2), idesc, S.accumulate || ks > 0 || t > 0);
+        umma_commit(&empty[st]);   // frees the slab when these MMAs have read it
+        if (commit_k) umma_commit(&afree[ks]);
       }
       __syncwarp();
+      if (++st == ST) { st = 0; ph ^= 1u; }
     }
   }
-  __device__ void commit_acc() {
-    if (leader) umma_commit(acc_bar);
-    __syncwarp();
+  // one tile of the program: every stage of the schedule, accumulator commits where the crew waits for them
+  __device__ void mma_tile(const TcProgram &P, uint32_t a_smem, uint32_t tmem_base) {
+    mbar_wait(a_bar, a_phase);          // sleep until the tile's input is staged (the scout clears it right after)
+    a_phase ^= 1u;
+    for (int i = 0; i < P.n_sched; ++i) {
+      mma_stage(P.st[P.sched[i].stage], a_smem, tmem_base, P.sched[i].chase != 0, P.sched[i].commit_k != 0);
+      if (P.sched[i].commit_acc) {
+        if (leader) umma_commit(acc_bar);
+        __syncwarp();
+      }
+    }
   }
 
   // ---- crew -------------------------------------------------------------------------------------------
@@ -214,13 +255,21 @@ struct Pipe {
 // accumulator columns [col0, col0 + ncols) of this thread's row, this thread's column group
 // -> relu(x + bias), columns >= n_real forced to 0 -> block (c / 16) of the A operand, published to the MMA warp.
 // n_free: blocks below this index wait for afree (the previous commit_k stage read them).
+// wait_first: the accumulator itself is only known to be complete once afree of this thread's first block has
+// fired (the releasing stage was issued after the stage that produced the accumulator): wait before loading.
 // With GSUM (n divides 32, so a state's rows are an aligned lane group of this warp): also reduce the
 // activated fp32 values over the state's real rows with shuffles and store the mean to g_out[col * g_ld + state]
 // -- the global state of sarl.py:51-60, taken from registers instead of re-reading the 16-bit images.
+// g_out is [state][g_ld]: the 16 lanes of a state store 16 consecutive floats (conflict-free).
 template <int NSPLIT, bool GSUM>
 __device__ __forceinline__ void epi_to_a(Pipe<NSPLIT> &pipe, uint32_t tmem_row, int cg, int col0, int ncols, int n_real,
                                          const float *__restrict__ bias, uint8_t *a_base, int row, bool chase,
-                                         int n_free, int n = 1, int row_cnt = 0, float *g_out = nullptr, int g_ld = 0) {
+                                         int n_free, int n = 1, int row_cnt = 0, float *g_out = nullptr, int g_ld = 0,
+                                         int g_states = 0, bool wait_first = false) {
+  if (wait_first && 16 * cg < ncols) {
+    pipe.wait_free(cg < n_free ? cg : 0);
+    tc_fence_after();
+  }
   for (int c = 16 * cg; c < ncols; c += 16 * NCG) {
     float v[16];
     tmem_ld16(tmem_row + col0 + c, v);
@@ -273,13 +322,13 @@ __device__ __forceinline__ void epi_to_a(Pipe<NSPLIT> &pipe, uint32_t tmem_row, 
         }
         const float send = (lane & 1) ? w2[0] : w2[1], keep = (lane & 1) ? w2[1] : w2[0];
         const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-        g_out[(c + (lane & 15)) * g_ld + row / n] = tot * inv;
+        if (row / n < g_states) g_out[(row / n) * g_ld + c + (lane & 15)] = tot * inv;
       } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float x = real ? v[i] : 0.0f;
           for (int o = 1; o < n; o <<= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-          if (r_in == 0) g_out[(c + i) * g_ld + row / n] = x * inv;
+          if (r_in == 0 && row / n < g_states) g_out[(row / n) * g_ld + c + i] = x * inv;
         }
       }
     }
@@ -293,8 +342,17 @@ __device__ __forceinline__ void gx_to_a(Pipe<NSPLIT> &pipe, const float *G, int 
                                         uint8_t *a_base, int row, int n_free) {
   for (int c = 16 * cg; c < h1p; c += 16 * NCG) {
     float v[16];
+    const float4 *g4 = reinterpret_cast<const float4 *>(G + state * g_ld + c);   // one address per state: broadcast
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = (c + i < h1d) ? G[(c + i) * g_ld + state] : 0.0f;
+    for (int q = 0; q < 4; ++q) {
+      const float4 g = g4[q];
+      v[4 * q] = g.x; v[4 * q + 1] = g.y; v[4 * q + 2] = g.z; v[4 * q + 3] = g.w;
+    }
+    if (c + 16 > h1d) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (c + i >= h1d) v[i] = 0.0f;
+    }
     if ((c >> 4) < n_free) pipe.wait_free(c >> 4);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -312,10 +370,15 @@ __device__ __forceinline__ float epi_dot(uint32_t tmem_row, int cg, int col0, in
   for (int c = 16 * cg; c < ncols; c += 16 * NCG) {
     float v[16];
     tmem_ld16(tmem_row + col0 + c, v);
+    const float4 *b4 = reinterpret_cast<const float4 *>(bias + c), *w4 = reinterpret_cast<const float4 *>(w + c);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float x = v[i] + __ldg(bias + c + i);
-      acc = fmaf(x > 0.0f ? x : 0.0f, __ldg(w + c + i), acc);
+    for (int q = 0; q < 4; ++q) {
+      const float4 bb = __ldg(b4 + q), ww = __ldg(w4 + q);
+      const float x0 = v[4 * q] + bb.x, x1 = v[4 * q + 1] + bb.y, x2 = v[4 * q + 2] + bb.z, x3 = v[4 * q + 3] + bb.w;
+      acc = fmaf(x0 < 0.0f ? 0.0f : x0, ww.x, acc);
+      acc = fmaf(x1 < 0.0f ? 0.0f : x1, ww.y, acc);
+      acc = fmaf(x2 < 0.0f ? 0.0f : x2, ww.z, acc);
+      acc = fmaf(x3 < 0.0f ? 0.0f : x3, ww.w, acc);
     }
   }
   return acc;
@@ -328,7 +391,9 @@ __device__ __forceinline__ void pipe_init(Pipe<NSPLIT> &pipe, uint8_t *smem, con
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
   pipe.full = bars; pipe.empty = bars + ST; pipe.acc_bar = bars + 2 * ST; pipe.a_bar = bars + 2 * ST + 1;
   pipe.kbar = bars + 2 * ST + 2; pipe.afree = pipe.kbar + NKB;
-  static_assert((2 * ST + 2 + 2 * NKB) * 8 <= 512, "barrier region");
+  pipe.ready = reinterpret_cast<uint32_t *>(pipe.afree + NKB);
+  pipe.issued = 0; pipe.seen = 0;
+  static_assert((2 * ST + 3 + 2 * NKB) * 8 <= 512, "barrier region");
   pipe.k_phase = 0; pipe.f_phase = 0;
   pipe.wbuf = smem + L.w; pipe.wpack = P.wpack;
   pipe.n_stage_slabs = P.n_slabs;
@@ -342,6 +407,7 @@ __device__ __forceinline__ void pipe_init(Pipe<NSPLIT> &pipe, uint8_t *smem, con
     for (int i = 0; i < ST; ++i) { mbar_init(&pipe.full[i], 1); mbar_init(&pipe.empty[i], 1); }
     mbar_init(pipe.acc_bar, 1);
     mbar_init(pipe.a_bar, NCREW);
+    *pipe.ready = 0;
     for (int i = 0; i < NKB; ++i) { mbar_init(&pipe.kbar[i], TILE_M); mbar_init(&pipe.afree[i], 1); }
     fence_barrier_init();
   }
@@ -366,7 +432,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
   constexpr int MAX_TS = Cfg<NSPLIT>::MAX_TS;
   const Smem L = smem_layout<NSPLIT>();
   uint8_t *A = smem + L.a;
-  float *G = reinterpret_cast<float *>(smem + L.g);     // G[k][MAX_TS]
+  float *G = reinterpret_cast<float *>(smem + L.g);     // G[state][KMAX]
   float *SC = reinterpret_cast<float *>(smem + L.sc), *XS = reinterpret_cast<float *>(smem + L.xs);
   __shared__ uint32_t tmem_slot;
   __shared__ int cnt[16];
@@ -386,24 +452,15 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
 
   if (warp == NCREW / 32) {
     // =================================== MMA warp (converged) ===================================
+    // schedule (built on the host, P.sched): mlp1.0 halves | commit #1 | mlp1.2 K chunks chasing the wide-half
+    // epilogues | commit #2 | mlp2.0 chasing the H1 epilogue, attention.0 local (H1 complete), attention.0 global
+    // chasing the G operand | commit #3 | mlp2.2 chasing the T2 epilogue, attention.2 chasing the U epilogue | commit #4
     pipe.leader = elect_one();
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      pipe.wait_a();                                                               // X staged
-      for (int h = 0; h < P.n_wide; ++h) pipe.mma_stage(P.st[ST_L0A + h], a_smem, tmem_base, false, false);
-      pipe.commit_acc();                                                           // #1: mlp1.0 done
-      for (int h = 0; h < P.n_wide; ++h)                                           // chases the wide-half epilogues
-        pipe.mma_stage(P.st[ST_L1A + h], a_smem, tmem_base, true, h + 1 < P.n_wide);
-      pipe.commit_acc();                                                           // #2: mlp1.2 done
-      pipe.mma_stage(P.st[ST_L2], a_smem, tmem_base, true, false);                 // chases the H1 epilogue
-      pipe.mma_stage(P.st[ST_L4], a_smem, tmem_base, false, true);                 // H1 complete, its accumulator read
-      if (P.with_global) pipe.mma_stage(P.st[ST_L4G], a_smem, tmem_base, true, true);   // chases the G operand
-      pipe.commit_acc();                                                           // #3: mlp2.0 / attention.0 done
-      pipe.mma_stage(P.st[ST_L3], a_smem, tmem_base, true, true);                  // chases the T2 epilogue
-      pipe.mma_stage(P.st[ST_L5], a_smem, tmem_base, true, false);                 // chases the U epilogue
-      pipe.commit_acc();                                                           // #4: mlp2.2 / attention.2 done
-    }
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) pipe.mma_tile(P, a_smem, tmem_base);
   } else if (warp == NCREW / 32 + 1) {
     if ((tid & 31) == 0) pipe.loader_loop();
+  } else if (warp == NCREW / 32 + 2) {
+    pipe.scout_loop(P, (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
   } else {
     // ======================================= epilogue crew =======================================
     const int row = ((warp & 3) << 5) | (tid & 31);   // TMEM lane quarter of this warp
@@ -466,7 +523,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
         if (gsum) {
           crew_sync();   // cnt[] of this tile is visible
           epi_to_a<NSPLIT, true>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, P.bias[1], A, row, true, 0, n,
-                                 cnt[st_of_row], G, MAX_TS);
+                                 cnt[st_of_row], G, KMAX, ts);
         } else {
           epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, P.bias[1], A, row, true, 0);
         }
@@ -490,18 +547,19 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
                 v += Fmt<NSPLIT>::from16(*reinterpret_cast<const uint16_t *>(A + (size_t)sp * Cfg<NSPLIT>::A_IMAGE + off));
               acc += v;
             }
-            G[k * MAX_TS + s] = c > 0 ? acc / (float)c : 0.0f;
+            G[s * KMAX + k] = c > 0 ? acc / (float)c : 0.0f;
           }
           crew_sync();
         }
-        gx_to_a<NSPLIT>(pipe, G, MAX_TS, st_of_row, cg, h1d, 16 * h1b, A, row, h1b);
+        gx_to_a<NSPLIT>(pipe, G, KMAX, st_of_row, cg, h1d, 16 * h1b, A, row, h1b);
         pipe.f_phase ^= low_bits(h1b);                  // attention.0 (local half) released every H1 block
         pipe.stamp();
       }
       // ---- T2 = relu(mlp2.0) -> A; mlp2.2 chases it --------------------------------------------------------
       {
         const TcStage &S = P.st[ST_L2];
-        epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, P.bias[2], A, row, true, h1b);
+        epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, P.bias[2], A, row, true, h1b, 1, 0, nullptr,
+                                0, 0, true);
         pipe.f_phase ^= low_bits(h1b);                  // attention.0's last K chunk released its blocks
       }
       pipe.stamp();
@@ -541,7 +599,12 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
           float v[16];
           tmem_ld16(tmem_row + S.acc_col + c, v);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = (real && c + i < h2d) ? (v[i] + __ldg(P.bias[3] + c + i)) * wrow : 0.0f;
+          for (int q = 0; q < 4; ++q) {
+            const float4 bb = __ldg(reinterpret_cast<const float4 *>(P.bias[3] + c) + q);
+            v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = (real && c + i < h2d) ? v[i] * wrow : 0.0f;
           float w8[8], w4[4], w2[2];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -645,17 +708,11 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
 
   if (warp == NCREW / 32) {
     pipe.leader = elect_one();
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      pipe.wait_a();
-      for (int h = 0; h < P.n_wide; ++h) pipe.mma_stage(P.st[ST_L0A + h], a_smem, tmem_base, false, false);
-      pipe.commit_acc();
-      for (int h = 0; h < P.n_wide; ++h) pipe.mma_stage(P.st[ST_L1A + h], a_smem, tmem_base, true, h + 1 < P.n_wide);
-      pipe.commit_acc();
-      pipe.mma_stage(P.st[ST_L2], a_smem, tmem_base, true, false);
-      pipe.commit_acc();
-    }
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) pipe.mma_tile(P, a_smem, tmem_base);
   } else if (warp == NCREW / 32 + 1) {
     if ((tid & 31) == 0) pipe.loader_loop();
+  } else if (warp == NCREW / 32 + 2) {
+    pipe.scout_loop(P, (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
   } else {
     const int row = ((warp & 3) << 5) | (tid & 31);
     const int cg = warp >> 2;
@@ -900,7 +957,29 @@ int ebc_tc_prepare(ebc_sim *s, const ebc_weights *w, int mode_index, int nsplit)
   const size_t be4 = push_f(a0->bias, a0->out_dim, E.st[ST_L4].np);
   const size_t be5 = push_f(a2->bias, a2->out_dim, E.st[ST_L5].np);
   const size_t we6 = push_f(a4->weight, a4->in_dim, E.st[ST_L5].np);
+  {
+    auto add = [](TcProgram &Q, int stage, int chase, int commit_k, int commit_acc) {
+      TcSched &e = Q.sched[Q.n_sched++];
+      e.stage = (uint8_t)stage; e.chase = (uint8_t)chase; e.commit_k = (uint8_t)commit_k; e.commit_acc = (uint8_t)commit_acc;
+    };
+    for (int h = 0; h < E.n_wide; ++h) add(E, ST_L0A + h, 0, 0, h + 1 == E.n_wide);
+    for (int h = 0; h < E.n_wide; ++h) add(E, ST_L1A + h, 1, h + 1 < E.n_wide, h + 1 == E.n_wide);
+    add(E, ST_L2, 1, 0, 0);
+    add(E, ST_L4, 0, 1, !w->with_global_state);
+    if (w->with_global_state) add(E, ST_L4G, 1, 1, 1);
+    add(E, ST_L3, 1, 1, 0);
+    add(E, ST_L5, 1, 0, 1);
+  }
   if (build_front(pm, M, p0, p2, pad16(p0->in_dim), bm0, bm1)) return 1;
+  {
+    auto add = [](TcProgram &Q, int stage, int chase, int commit_k, int commit_acc) {
+      TcSched &e = Q.sched[Q.n_sched++];
+      e.stage = (uint8_t)stage; e.chase = (uint8_t)chase; e.commit_k = (uint8_t)commit_k; e.commit_acc = (uint8_t)commit_acc;
+    };
+    for (int h = 0; h < M.n_wide; ++h) add(M, ST_L0A + h, 0, 0, h + 1 == M.n_wide);
+    for (int h = 0; h < M.n_wide; ++h) add(M, ST_L1A + h, 1, h + 1 < M.n_wide, h + 1 == M.n_wide);
+    add(M, ST_L2, 1, 0, 1);
+  }
   simple_stage(pm, M.st[ST_L2], p4, p2->out_dim, pad16(p2->out_dim), 0, 0);        // mlp3.4
   const size_t bm2 = push_f(p4->bias, p4->out_dim, M.st[ST_L2].np);
   const size_t wm6 = push_f(p6->weight, p6->in_dim, M.st[ST_L2].np);

@@ -11,7 +11,7 @@ from ebc.engine import BatchedSim
 pytestmark = pytest.mark.gpu
 
 
-def torch_value(w, x, cnt):
+def torch_value(w, x, cnt, with_global=True):
     """fp64 reference of the value network with ragged row counts."""
     W = {k: torch.as_tensor(v, device=x.device, dtype=torch.float64) for k, v in w.items()}
     n = x.shape[1]
@@ -25,8 +25,8 @@ def torch_value(w, x, cnt):
     h2 = lin(lin(h1, "mlp2.0", True), "mlp2.2", False)
     mask = (torch.arange(n, device=x.device)[None] < cnt[:, None]).double()
     g = (h1 * mask[..., None]).sum(1, keepdim=True) / cnt[:, None, None].double()
-    a = lin(lin(lin(torch.cat([h1, g.expand(-1, n, -1)], 2), "attention.0", True), "attention.2", True),
-            "attention.4", False)[..., 0]
+    att_in = torch.cat([h1, g.expand(-1, n, -1)], 2) if with_global else h1
+    a = lin(lin(lin(att_in, "attention.0", True), "attention.2", True), "attention.4", False)[..., 0]
     e = torch.exp(a) * (a != 0) * mask
     wts = e / e.sum(1, keepdim=True)
     f = (wts[..., None] * h2).sum(1)
@@ -97,3 +97,34 @@ def test_tc_matches_golden_argmax(oracle):
     assert res["tc_fp32"][0] < 2e-4 and res["tc_fp32"][2] == 0 and res["tc_fp32"][1] <= 2
     assert res["tc_fp16x2"][0] < 2e-4 and res["tc_fp16x2"][2] == 0 and res["tc_fp16x2"][1] <= 2
     assert res["tc_bf16"][0] < 0.1
+
+
+@pytest.mark.parametrize("n,with_global", [(16, False), (7, False), (8, True), (32, True)])
+def test_tc_random_networks(n, with_global):
+    """Shapes the shipped checkpoints do not cover: no global state (sarl.py:28-32 with_global_state = False,
+    the MMA schedule then has no global K chunk), odd widths (padding columns that alias a neighbouring
+    accumulator must stay exact zeros), row counts that do / do not divide the warp."""
+    rng = np.random.default_rng(100 + n)
+    D = 13
+    dims = {"mlp1": [D, 250 if with_global else 168, 120], "mlp2": [120, 104, 52], "attention": [240 if with_global else 120, 88, 72, 1],
+            "mlp3": [58, 180, 90, 70, 1]}
+    w = {}
+    for name, ds in dims.items():
+        for i in range(len(ds) - 1):
+            b = 1.0 / np.sqrt(ds[i])
+            w["%s.%d.weight" % (name, 2 * i)] = rng.uniform(-b, b, (ds[i + 1], ds[i])).astype(np.float32)
+            w["%s.%d.bias" % (name, 2 * i)] = rng.uniform(-b, b, ds[i + 1]).astype(np.float32)
+    cfg = SimConfig()
+    cfg.with_agent_type = False
+    sim = BatchedSim(cfg, 1, n, 0, 0, 81, device="cuda:0")
+    sim.set_weights(w, with_global_state=with_global)
+    x, cnt = make_inputs(1111, n, cfg.D, seed=n)
+    ref = torch_value(w, x, cnt, with_global)
+    scale = max(1.0, ref.abs().max().item())
+    for mode in ("fp32", "tc_fp16x2", "tc_fp32"):
+        sim.set_value_mode(mode)
+        out = sim.value(x, cnt).double()
+        torch.cuda.synchronize()
+        err = (out - ref).abs().max().item()
+        print(n, with_global, mode, err)
+        assert err < 5e-5 * scale, (mode, err)

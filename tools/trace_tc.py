@@ -31,12 +31,12 @@ mhz=1965.0
 print("mode",mode,"tiles traced",ntile)
 for i,nm in enumerate(names): print("%-48s mean %8.0f cyc = %6.2f us   (min %7.0f max %7.0f)"%(nm,arr[2:,i].mean(),arr[2:,i].mean()/mhz,arr[2:,i].min(),arr[2:,i].max()))
 print("per tile total %.1f us"%(arr[2:].sum(1).mean()/mhz))
-if len(tm) >= 400:
-    # MMA-warp stamps per tile: X seen, then "all k-steps issued" for L0a, L0b, L1A, L1B, L2, L4, L4G, L3, L5
-    mper = 10
-    mt = tm[:(len(tm)//mper)*mper].reshape(-1, mper)
-    for tile in (20, 21):
-        base = t[tile*per]            # crew: signal_a(X) of that tile
-        print("tile %d (us from the crew's X signal):" % tile)
-        print("  crew: X, acc1, W0a, W0b, acc2, H1, G, T2, acc3, U, acc4 :", np.round((t[tile*per:(tile+1)*per] - base)/mhz,2))
-        print("  mma : Xseen, L0a, L0b, L1A, L1B, L2, L4, L4G, L3, L5 issued:", np.round((mt[tile] - base)/mhz,2))
+# MMA-warp entries (upper half): (clock << 16) | k-steps issued in that batch
+if len(tm) > 0:
+    clk = tm >> 16; batch = tm & 0xffff
+    for tile in (20,):
+        base = t[tile*per]; end = t[(tile+1)*per]
+        print("tile %d, crew stamps (us): X, acc1, W0a, W0b, acc2, H1, G, T2, acc3, U, acc4, next X" % tile)
+        print("  ", np.round((t[tile*per:(tile+1)*per+1] - base)/mhz, 2))
+        sel = (clk >= base - 200) & (clk <= end)
+        print("  MMA warp batches (us: k-steps):", " ".join("%.2f:%d" % ((c - base)/mhz, b) for c, b in zip(clk[sel], batch[sel])))
