@@ -47,7 +47,9 @@ constexpr int TMEM_COLS = 512;
 constexpr int PS_LD = TILE_M + 4;
 
 template <int NSPLIT> struct Cfg {
-  static constexpr int STAGES = NSPLIT == 1 ? 8 : (NSPLIT == 2 ? 6 : 3);
+  // ring depth: a slot is busy from the issue of its bulk copy (L2 latency ~ 1000 cycles) until the MMAs that
+  // read it have completed and the loader has seen that; at one k-step per ~312 cycles this needs >= 7 slots
+  static constexpr int STAGES = NSPLIT == 1 ? 16 : (NSPLIT == 2 ? 8 : 3);
   static constexpr int MAX_TS = NSPLIT == 3 ? 8 : 16;                    // states per entity tile
   static constexpr uint32_t A_IMAGE = TILE_M * KMAX * 2;                 // bytes per split image of A
   static constexpr uint32_t A_BYTES = NSPLIT * A_IMAGE;
@@ -91,10 +93,9 @@ struct Pipe {
   long long total;           // slab count over all tiles of this CTA (loader)
   uint32_t *ready;           // scout -> MMA warp: k-steps (counted over the whole launch) whose operands are in place
   uint32_t issued, seen;     // MMA warp: k-steps issued so far / the scout's count when last read
-  uint32_t st, ph;           // MMA warp: ring slot of the next slab and its full-barrier parity
+  uint32_t st;               // MMA warp: ring slot of the next slab
   bool leader;               // MMA warp: the lane that issues tcgen05.mma / tcgen05.commit
   uint32_t acc_phase, a_phase;
-  uint32_t k_phase;          // MMA warp: expected parity of every kbar, one bit each
   uint32_t f_phase;          // crew: expected parity of every afree barrier, one bit each
   long long *trace;          // optional clock64() trace of CTA 0's crew thread 0 (EBC_TC_TRACE=1)
   int trace_pos;
@@ -177,51 +178,53 @@ struct Pipe {
   // chase:    the crew is still writing the A operand; k-step ks is issued as soon as its two k-chunks (one
   //           16-column block of the previous stage's epilogue) have been stored and fenced by all 128 rows
   // commit_k: signal afree[ks] when the MMAs issued up to and including k-step ks have completed
-  __device__ void mma_stage(const TcStage &S, uint32_t a_smem, uint32_t tmem_base, bool chase, bool commit_k) {
+  __device__ void mma_stage(const TcStage &S, uint32_t a_smem, uint32_t tmem_base, bool commit_k) {
     constexpr uint32_t ST = Cfg<NSPLIT>::STAGES;
     const uint32_t idesc = make_idesc_f16(TILE_M, S.np, Fmt<NSPLIT>::IDESC);
     const uint32_t d = tmem_base + S.acc_col;
     const uint32_t np = (uint32_t)S.np;
     const int ksteps = S.ksteps;
-    // descriptors differ only in the 14-bit start-address field (16-byte units): build once, add offsets
-    const uint64_t a_desc0 = make_smem_desc(a_smem, A_CHUNK_BYTES, 128);
-    const uint64_t b_desc0 = make_smem_desc(smem_u32(wbuf), np * 16, 128);
-    // The k-step loop is warp-uniform (trip count from the program, counters incremented unconditionally), so
-    // the descriptors stay in uniform registers; the only data-dependent part is the wait below, which carries
-    // no state.  `seen` caches the scout's count: one shared-memory load per batch of cleared k-steps.
+    const bool acc0 = S.accumulate != 0;
+    // A descriptor = {start address >> 4 | LBO << 16, SBO | version}: only the low word changes (32-bit adds)
+    constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
+    const uint32_t a_lo0 = ((a_smem >> 4) & 0x3FFFu) | ((uint32_t)(A_CHUNK_BYTES >> 4) << 16);
+    const uint32_t b_lo0 = ((smem_u32(wbuf) >> 4) & 0x3FFFu) | (np << 16);
+    const uint32_t base = issued;                 // schedule index of this stage's first k-step
+    uint32_t avail = seen - base;                 // cleared k-steps of this stage (the scout may be further ahead)
+    // The k-step loop is warp-uniform (trip count from the program, counters incremented unconditionally); the
+    // only data-dependent part is the wait below, which carries no state besides the cached count.
     for (int ks = 0; ks < ksteps; ++ks) {
-      if ((int)(seen - issued) <= 0) {
+      if ((int)avail <= ks) {
         uint32_t idle = 0;
-        while ((int)((seen = ready_count()) - issued) <= 0) {
+        while ((int)(avail = (seen = ready_count()) - base) <= ks) {
           __nanosleep(40);                     // the scout sleeps on the barriers; this warp only watches its count
           if (++idle > (1u << 24)) __trap();   // bounded: a protocol bug traps instead of hanging
         }
         tc_fence_after();
         if (trace && leader && blockIdx.x == 0 && trace_pos < 2040)   // diagnostics: (clock, cleared k-steps)
-          trace[2048 + trace_pos++] = (clock64() << 16) | (long long)((seen - issued) & 0xFFFFu);
+          trace[2048 + trace_pos++] = (clock64() << 16) | (long long)((avail - (uint32_t)ks) & 0xFFFFu);
       }
-      ++issued;
-      if (chase) k_phase ^= 1u << ks;
-      const uint64_t ad = a_desc0 + (uint64_t)((uint32_t)ks * (2 * A_CHUNK_BYTES / 16));
-      const uint64_t bd = b_desc0 + (uint64_t)(st * (Cfg<NSPLIT>::STAGE_BYTES / 16));
+      const uint32_t a_lo = a_lo0 + (uint32_t)ks * (2 * A_CHUNK_BYTES / 16);
+      const uint32_t b_lo = b_lo0 + st * (Cfg<NSPLIT>::STAGE_BYTES / 16);
       if (leader) {
 #pragma unroll
         for (int t = 0; t < Terms<NSPLIT>::N; ++t)
-          umma_bf16(d, ad + (uint64_t)(Terms<NSPLIT>::a(t) * (Cfg<NSPLIT>::A_IMAGE / 16)),
-                    bd + (uint64_t)(Terms<NSPLIT>::b(t) * np * 2), idesc, S.accumulate || ks > 0 || t > 0);
+          umma_f16(d, a_lo + (uint32_t)(Terms<NSPLIT>::a(t) * (Cfg<NSPLIT>::A_IMAGE / 16)),
+                   b_lo + (uint32_t)(Terms<NSPLIT>::b(t)) * np * 2, DESC_HI, idesc, acc0 || ks > 0 || t > 0);
         umma_commit(&empty[st]);   // frees the slab when these MMAs have read it
         if (commit_k) umma_commit(&afree[ks]);
       }
       __syncwarp();
-      if (++st == ST) { st = 0; ph ^= 1u; }
+      if (++st == ST) st = 0;
     }
+    issued = base + (uint32_t)ksteps;
   }
   // one tile of the program: every stage of the schedule, accumulator commits where the crew waits for them
   __device__ void mma_tile(const TcProgram &P, uint32_t a_smem, uint32_t tmem_base) {
     mbar_wait(a_bar, a_phase);          // sleep until the tile's input is staged (the scout clears it right after)
     a_phase ^= 1u;
     for (int i = 0; i < P.n_sched; ++i) {
-      mma_stage(P.st[P.sched[i].stage], a_smem, tmem_base, P.sched[i].chase != 0, P.sched[i].commit_k != 0);
+      mma_stage(P.st[P.sched[i].stage], a_smem, tmem_base, P.sched[i].commit_k != 0);
       if (P.sched[i].commit_acc) {
         if (leader) umma_commit(acc_bar);
         __syncwarp();
@@ -394,13 +397,13 @@ __device__ __forceinline__ void pipe_init(Pipe<NSPLIT> &pipe, uint8_t *smem, con
   pipe.ready = reinterpret_cast<uint32_t *>(pipe.afree + NKB);
   pipe.issued = 0; pipe.seen = 0;
   static_assert((2 * ST + 3 + 2 * NKB) * 8 <= 512, "barrier region");
-  pipe.k_phase = 0; pipe.f_phase = 0;
+  pipe.f_phase = 0;
   pipe.wbuf = smem + L.w; pipe.wpack = P.wpack;
   pipe.n_stage_slabs = P.n_slabs;
   uint2 *tab = reinterpret_cast<uint2 *>(smem + L.tab);
   for (int i = threadIdx.x; i < P.n_slabs; i += blockDim.x) tab[i] = make_uint2(__ldg(P.slab_off + i), __ldg(P.slab_bytes + i));
   pipe.tab = tab;
-  pipe.st = 0; pipe.ph = 0; pipe.leader = false; pipe.acc_phase = 0; pipe.a_phase = 0;
+  pipe.st = 0; pipe.leader = false; pipe.acc_phase = 0; pipe.a_phase = 0;
   pipe.trace = nullptr; pipe.trace_pos = 0;
   pipe.total = my_tiles * P.n_slabs;
   if (threadIdx.x == 0) {
