@@ -47,10 +47,17 @@ METRIC = "agent_steps_per_sec"
 UNIT = "agent-steps/s"
 
 
-def workload():
+WORKLOADS = {   # name -> (synth shape, robot kinematics, entity-typed rows, weights fixture, episodes per GPU)
+    "cfg2": ("CFG2", "holonomic", True, "weights_ebcadrl.npz", 4096),          # BASELINE configs[1]: the bench line
+    "cfg3": ("CFG3", "unicycle", False, "weights_sarl_baseline.npz", 16384),   # configs[2] (side measurement)
+    "cfg4": ("CFG4", "holonomic", True, "weights_ebcadrl.npz", 8192),          # configs[3], one GPU's shard
+}
+
+
+def workload(name="cfg2"):
     from ebc import synth
     from ebc.config import SimConfig
-    shape = synth.CFG2
+    shape = getattr(synth, WORKLOADS[name][0])
     c = SimConfig()   # reward block of data/eb-cadrl/adults_8_..._fix_static.config:26-44
     c.time_step, c.time_limit = 0.25, 35.0
     c.new_reward, c.time_max, c.time_good, c.max_goal_distance = True, 35.0, 10.0, 10.0
@@ -62,15 +69,15 @@ def workload():
     c.discomfort_penalty_factor_adult = 0.5
     c.discomfort_penalty_factor_bicycle = c.discomfort_penalty_factor_child = 1.0
     c.map_size_m, c.map_resolution = shape.map_size_m, shape.map_resolution
-    c.robot_kinematics, c.with_agent_type, c.gamma = "holonomic", True, 0.9
+    c.robot_kinematics, c.with_agent_type, c.gamma = WORKLOADS[name][1], WORKLOADS[name][2], 0.9
     return shape, c
 
 
-def value_net_weights(D=17, seed=0):
-    path = os.path.join(ROOT, "tests", "golden", "weights_ebcadrl.npz")
+def value_net_weights(D=17, seed=0, fixture="weights_ebcadrl.npz"):
+    path = os.path.join(ROOT, "tests", "golden", fixture)
     if os.path.exists(path):
         z = np.load(path)
-        return {k: z[k] for k in z.files}, "rl_model_val fixture"
+        return {k: z[k] for k in z.files}, ("rl_model_val fixture" if fixture == "weights_ebcadrl.npz" else fixture)
     rng = np.random.default_rng(seed)
     dims = {"mlp1": [D, 300, 200], "mlp2": [200, 200, 100], "attention": [400, 200, 200, 1],
             "mlp3": [106, 300, 200, 200, 1]}
@@ -131,7 +138,7 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "tensor_tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
-def cpu_oracle_rate(shape, cfg, weights, episodes, steps, threads, full_loop=True):
+def cpu_oracle_rate(shape, cfg, weights, episodes, steps, threads, full_loop=True, kin="holonomic"):
     """agent-steps/s of the CPU oracle on `episodes` episodes of the same workload."""
     import oracle_backend as ob
     from ebc import synth
@@ -140,7 +147,7 @@ def cpu_oracle_rate(shape, cfg, weights, episodes, steps, threads, full_loop=Tru
     be = ob.OracleBackend()
     be.set_threads(threads)
     sim = BatchedSim(cfg, episodes, shape.H, shape.Smax, shape.Rmax, N_ACTIONS, device="cpu", backend=be)
-    sim.set_actions(build_action_space(shape.robot_v_pref))
+    sim.set_actions(build_action_space(shape.robot_v_pref, kin))
     sim.set_weights(weights)
     synth.load(sim, synth.generate(shape, np.arange(episodes)))
     t0 = time.perf_counter()
@@ -189,7 +196,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--episodes", type=int, default=EPISODES_PER_GPU, help="episodes per GPU")
+    ap.add_argument("--episodes", type=int, default=None, help="episodes per GPU (default: the workload's)")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
+                    help="cfg2 = BASELINE configs[1], the bench line; cfg3 / cfg4 are side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--value-mode", default="tc_fp16x2", choices=["fp32", "tc_fp32", "tc_fp16x2", "tc_bf16"],
                     help="K4 arithmetic; tc_fp16x2 (tcgen05, fp32-accurate operand splitting) is the parity mode")
@@ -215,13 +224,13 @@ def main():
     from ebc import synth
     from ebc.actions import build_action_space
     from ebc.engine import BatchedSim
-    shape, cfg = workload()
-    weights, wsrc = value_net_weights()
-    N = args.episodes
+    shape, cfg = workload(args.workload)
+    weights, wsrc = value_net_weights(fixture=WORKLOADS[args.workload][3])
+    N = args.episodes or WORKLOADS[args.workload][4]
     ids = np.arange(rank * N, (rank + 1) * N)           # episodes shard trivially: no data-path collective
     scenes = synth.generate(shape, ids)
     sim = BatchedSim(cfg, N, shape.H, shape.Smax, shape.Rmax, N_ACTIONS, device=dev)
-    sim.set_actions(build_action_space(shape.robot_v_pref))
+    sim.set_actions(build_action_space(shape.robot_v_pref, cfg.robot_kinematics))
     sim.set_weights(weights)
     sim.set_value_mode(args.value_mode)
     synth.load(sim, scenes)
@@ -382,7 +391,7 @@ def main():
                                 "tc_bf16": "K4 value network: tc_entity_kernel<1> + tc_mlp3_kernel<1> (tcgen05, bf16 operands)"
                                 }[args.value_mode],
                      "bound": "tensor", "achieved": achieved_tf, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
-                     "frac": achieved_tf / peaks["tensor_tflops"], "traffic": ROOFLINE_TRAFFIC.get(args.value_mode),
+                     "frac": achieved_tf / peaks["tensor_tflops"], "traffic": ROOFLINE_TRAFFIC.get(args.value_mode) if args.workload == "cfg2" and N == 4096 else None,
                      "peak_source": peaks["source"],
                      "mma_issue_factor": {"fp32": 0, "tc_fp32": 6, "tc_fp16x2": 3, "tc_bf16": 1}[args.value_mode],
                      "note": "achieved = algorithmic FLOPs 2*(n*M_e+M_s) per (episode, action) / K4 time from CUDA events "
@@ -403,7 +412,7 @@ def main():
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         sample = max(4 * threads, 32)
-        rate, dt = cpu_oracle_rate(shape, cfg, weights, sample, 2, threads)
+        rate, dt = cpu_oracle_rate(shape, cfg, weights, sample, 2, threads, kin=cfg.robot_kinematics)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": "%d episodes x 2 full steps of %s, %.1f s" % (sample, shape.name, dt)}
     print(json.dumps(line), flush=True)

@@ -290,6 +290,69 @@ def test_full_size_properties():
     assert float(a.time[0]) == 0.75
 
 
+@pytest.mark.parametrize("shape_name,N,kin,weights,typed,steps", [
+    ("CFG3", 16384, "unicycle", "weights_sarl_baseline.npz", False, 2),     # BASELINE configs[2]
+    ("CFG4", 8192, "holonomic", "weights_ebcadrl.npz", True, 1),            # configs[3], one GPU's shard of 65536
+])
+def test_full_size_other_configs(oracle, shape_name, N, kin, weights, typed, steps):
+    """BASELINE configs[2] and [3] at the per-GPU size: permutation equivariance bit for bit, lookahead leaves
+    the state alone, ORCA speed bound, no NaN; plus a strided sample of episodes replayed on the oracle
+    (events / argmax exact, values within 1e-4)."""
+    shape = getattr(synth, shape_name)
+    cfg = random_cfg(kin, typed=typed)
+    cfg.map_size_m, cfg.map_resolution = shape.map_size_m, shape.map_resolution
+    w = ob.load_weights(weights)
+    scenes = synth.generate(shape, np.arange(N))
+    perm = np.random.default_rng(1).permutation(N)
+    dperm = torch.as_tensor(perm, device="cuda:0")
+    actions = build_action_space(shape.robot_v_pref, kin)
+    sims = []
+    for sc in (scenes, {k: v[perm] for k, v in scenes.items()}):
+        s = BatchedSim(cfg, N, shape.H, shape.Smax, shape.Rmax, 81, device="cuda:0")
+        s.set_actions(actions)
+        s.set_weights(w)
+        synth.load(s, sc)
+        sims.append(s)
+    a, b = sims
+    # the oracle replays a strided sample of 64 episodes
+    pick = np.arange(0, N, N // 64)
+    r = BatchedSim(cfg, len(pick), shape.H, shape.Smax, shape.Rmax, 81, device="cpu", backend=oracle)
+    r.set_actions(actions)
+    r.set_weights(w)
+    synth.load(r, {k: v[pick] for k, v in scenes.items()})
+    for t in range(steps):
+        snap = {k: getattr(a, k).clone() for k in ("hum_pv", "rob_pv", "time", "rob_theta")}
+        am, bm = a.decide().clone(), b.decide().clone()
+        rm = r.decide().clone()
+        torch.cuda.synchronize()
+        for k, v in snap.items():
+            assert torch.equal(getattr(a, k), v), k
+        assert torch.equal(am[dperm], bm)
+        assert torch.equal(a.values[dperm], b.values)
+        assert torch.equal(a.la_event[dperm], b.la_event)
+        sp = torch.linalg.norm(a.hum_nv, dim=2)
+        assert (sp <= a.hum_gr[:, :, 2] * (1 + 1e-2) + 1e-6).all()
+        assert (a.nan_flag == 0).all()
+        # against the oracle on the sample
+        assert np.array_equal(np_(a.la_event)[pick], np_(r.la_event)), "lookahead events"
+        assert np.array_equal(np_(a.hum_nv)[pick], np_(r.hum_nv)), "ORCA velocities"
+        dv = np.abs(np_(a.values)[pick] - np_(r.values)).max()
+        assert dv < 1e-4, dv
+        # argmax: exact unless the two best action values are closer than the value tolerance
+        ga, ra = np_(am)[pick], np_(rm)
+        av = np_(r.action_values)
+        for i in np.nonzero(ga != ra)[0]:
+            assert abs(av[i, ga[i]] - av[i, ra[i]]) < 2e-4, (i, ga[i], ra[i])
+        assert (ga != ra).mean() <= 0.02
+        a.step(action_idx=am)
+        b.step(action_idx=bm)
+        r.step(action_idx=torch.as_tensor(ga.astype(np.int32)))
+        torch.cuda.synchronize()
+        assert np.array_equal(np_(a.event)[pick], np_(r.event)), "step events"
+        assert np.array_equal(np_(a.hum_pv)[pick], np_(r.hum_pv)), "human states after the step"
+    assert torch.equal(a.hum_pv[dperm], b.hum_pv)
+
+
 def test_reset_from_pool(oracle):
     N, H, S, R = 512, 10, 6, 3
     cfg = random_cfg()
