@@ -197,8 +197,8 @@ struct Pipe {
       if ((int)avail <= ks) {
         uint32_t idle = 0;
         while ((int)(avail = (seen = ready_count()) - base) <= ks) {
-          __nanosleep(40);                     // the scout sleeps on the barriers; this warp only watches its count
-          if (++idle > (1u << 24)) __trap();   // bounded: a protocol bug traps instead of hanging
+          // the scout sleeps on the barriers; this warp only watches its count (a shared-memory load per trip)
+          if (++idle > (1u << 26)) __trap();   // bounded: a protocol bug traps instead of hanging
         }
         tc_fence_after();
         if (trace && leader && blockIdx.x == 0 && trace_pos < 2040)   // diagnostics: (clock, cleared k-steps)
@@ -475,14 +475,28 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
     // this thread's 8 input values of a tile (k-chunk cg of row `row`), fetched one tile ahead so that the
     // HBM latency of the value-network input hides behind the previous tile's tail
     float xu[8];
+    int cnt_next = 0;                                 // threads 0-15: row count of state tid of the next tile
     auto load_x = [&](long long t) {
       const long long t0 = t * ts;
-      const int trows = (int)min((long long)ts, p.n_states - t0) * n;
+      const int tstates = (int)min((long long)ts, p.n_states - t0);
+      const int trows = tstates * n;
       const float *src = p.vin + ((size_t)t0 * n + row) * D;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int k = 8 * cg + j;
         xu[j] = (row < trows && k < D) ? __ldg(src + k) : 0.0f;
+      }
+      if (tid < 16) {
+        int c = 0;
+        if (tid < tstates) {
+          if (p.row_count) c = __ldg(p.row_count + t0 + tid);
+          else {
+            const long long e = (t0 + tid) / p.n_actions;
+            c = __ldg(p.hum_count + e) + __ldg(p.stat_count + e);
+          }
+          c = min(max(c, 0), n);
+        }
+        cnt_next = c;
       }
     };
     if (blockIdx.x < n_tiles) load_x(blockIdx.x);
@@ -490,18 +504,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
       const long long s0 = tile * ts;
       const int ns = (int)min((long long)ts, p.n_states - s0);
       const int rows = ns * n;
-      if (tid < 16) {
-        int c = 0;
-        if (tid < ns) {
-          if (p.row_count) c = p.row_count[s0 + tid];
-          else {
-            const long long e = (s0 + tid) / p.n_actions;
-            c = p.hum_count[e] + p.stat_count[e];
-          }
-          c = min(max(c, 0), n);
-        }
-        cnt[tid] = c;
-      }
+      if (tid < 16) cnt[tid] = cnt_next;
       // ---- X -> A (K padded to 32): thread (row, cg) converts k-chunk cg (values prefetched below) -------
       store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, row, 8 * cg, xu);
       if (cg == 0 && row < rows && row % n == 0)
