@@ -167,7 +167,12 @@ def run_train(args):
 
 
 def main(argv=None):
-    run_train(parse_arguments(argv))
+    try:
+        run_train(parse_arguments(argv))
+    finally:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":
