@@ -45,12 +45,15 @@ constexpr int KMAX = 208;                       // widest A operand chunk kept i
 constexpr int NKB = KMAX / 16;                  // 16-column blocks of an A operand
 constexpr int TMEM_COLS = 512;
 constexpr int PS_LD = TILE_M + 4;
+constexpr int MAX_STATES = 32;                  // states per entity tile (rows per state >= 4)
 
 template <int NSPLIT> struct Cfg {
   // ring depth: a slot is busy from the issue of its bulk copy (L2 latency ~ 1000 cycles) until the MMAs that
   // read it have completed and the loader has seen that; at one k-step per ~312 cycles this needs >= 7 slots
   static constexpr int STAGES = NSPLIT == 1 ? 16 : (NSPLIT == 2 ? 8 : 3);
-  static constexpr int MAX_TS = NSPLIT == 3 ? 8 : 16;                    // states per entity tile
+  // bytes of the per-state mean G[state][h1 padded]: 16 states of the widest layer (8 in the bf16x3 mode, whose
+  // operand images leave less room); narrower layers fit more states per tile
+  static constexpr uint32_t G_BYTES = (NSPLIT == 3 ? 8 : 16) * KMAX * 4;
   static constexpr uint32_t A_IMAGE = TILE_M * KMAX * 2;                 // bytes per split image of A
   static constexpr uint32_t A_BYTES = NSPLIT * A_IMAGE;
   static constexpr uint32_t STAGE_BYTES = NSPLIT * KMAX * 32;            // one k-step slab, all splits
@@ -67,9 +70,9 @@ __host__ __device__ inline Smem smem_layout() {
   uint32_t off = 0;
   s.a = off; off += Cfg<NSPLIT>::A_BYTES;
   s.w = off; off += Cfg<NSPLIT>::W_BYTES;
-  s.g = off; off += Cfg<NSPLIT>::MAX_TS * KMAX * 4;    // G[state][k]: per-state mean of H1
+  s.g = off; off += Cfg<NSPLIT>::G_BYTES;              // G[state][k]: per-state mean of H1
   s.sc = off; off += TILE_M * 4 * (NCG + 1);           // partial scores per column group, softmax weights
-  s.xs = off; off += 16 * 8 * 4;                        // self-state part of each state's first row
+  s.xs = off; off += MAX_STATES * 8 * 4;                // self-state part of each state's first row
   s.tab = off; off += MAX_SLABS * 8;                    // (offset, bytes) of every slab of the per-tile program
   s.bars = off; off += 512;
   s.total = off;
@@ -432,13 +435,12 @@ struct TcEntityParams {
 template <int NSPLIT>
 __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr int MAX_TS = Cfg<NSPLIT>::MAX_TS;
   const Smem L = smem_layout<NSPLIT>();
   uint8_t *A = smem + L.a;
   float *G = reinterpret_cast<float *>(smem + L.g);     // G[state][KMAX]
   float *SC = reinterpret_cast<float *>(smem + L.sc), *XS = reinterpret_cast<float *>(smem + L.xs);
   __shared__ uint32_t tmem_slot;
-  __shared__ int cnt[16];
+  __shared__ int cnt[MAX_STATES];
   const TcProgram &P = p.prog;
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
 
@@ -472,10 +474,11 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
     const int n = p.n, ts = p.ts, D = p.D;
     const int h1d = P.h1d, h2d = P.h2d;
     const int h1b = P.st[ST_L2].ksteps;               // 16-column blocks of H1 (= k-steps of its readers)
+    const int g_ld = 16 * h1b;                        // row stride of G
     // this thread's 8 input values of a tile (k-chunk cg of row `row`), fetched one tile ahead so that the
     // HBM latency of the value-network input hides behind the previous tile's tail
     float xu[8];
-    int cnt_next = 0;                                 // threads 0-15: row count of state tid of the next tile
+    int cnt_next = 0;                                 // threads 0-31: row count of state tid of the next tile
     auto load_x = [&](long long t) {
       const long long t0 = t * ts;
       const int tstates = (int)min((long long)ts, p.n_states - t0);
@@ -486,7 +489,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
         const int k = 8 * cg + j;
         xu[j] = (row < trows && k < D) ? __ldg(src + k) : 0.0f;
       }
-      if (tid < 16) {
+      if (tid < MAX_STATES) {
         int c = 0;
         if (tid < tstates) {
           if (p.row_count) c = __ldg(p.row_count + t0 + tid);
@@ -504,7 +507,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
       const long long s0 = tile * ts;
       const int ns = (int)min((long long)ts, p.n_states - s0);
       const int rows = ns * n;
-      if (tid < 16) cnt[tid] = cnt_next;
+      if (tid < MAX_STATES) cnt[tid] = cnt_next;
       // ---- X -> A (K padded to 32): thread (row, cg) converts k-chunk cg (values prefetched below) -------
       store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, row, 8 * cg, xu);
       if (cg == 0 && row < rows && row % n == 0)
@@ -529,7 +532,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
         if (gsum) {
           crew_sync();   // cnt[] of this tile is visible
           epi_to_a<NSPLIT, true>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, P.bias[1], A, row, true, 0, n,
-                                 cnt[st_of_row], G, KMAX, ts);
+                                 cnt[st_of_row], G, g_ld, ts);
         } else {
           epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, P.bias[1], A, row, true, 0);
         }
@@ -553,11 +556,11 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
                 v += Fmt<NSPLIT>::from16(*reinterpret_cast<const uint16_t *>(A + (size_t)sp * Cfg<NSPLIT>::A_IMAGE + off));
               acc += v;
             }
-            G[s * KMAX + k] = c > 0 ? acc / (float)c : 0.0f;
+            G[s * g_ld + k] = c > 0 ? acc / (float)c : 0.0f;
           }
           crew_sync();
         }
-        gx_to_a<NSPLIT>(pipe, G, KMAX, st_of_row, cg, h1d, 16 * h1b, A, row, h1b);
+        gx_to_a<NSPLIT>(pipe, G, g_ld, st_of_row, cg, h1d, 16 * h1b, A, row, h1b);
         pipe.f_phase ^= low_bits(h1b);                  // attention.0 (local half) released every H1 block
         pipe.stamp();
       }
@@ -836,7 +839,11 @@ int launch_tc(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row
   p.n_actions = s->cfg.n_actions; p.n_states = n_states; p.n = n; p.D = s->net.D;
   int ts = TILE_M / n;
   if (ts < 1) ts = 1;
-  if (ts > Cfg<NSPLIT>::MAX_TS) ts = Cfg<NSPLIT>::MAX_TS;
+  if (ts > MAX_STATES) ts = MAX_STATES;
+  if (s->net.with_global) {                      // G[state][h1 padded] must fit its shared-memory region
+    const int g_cap = (int)(Cfg<NSPLIT>::G_BYTES / (4u * (uint32_t)p.prog.st[ST_L2].ksteps * 16u));
+    if (ts > g_cap) ts = g_cap;
+  }
   p.ts = ts;
   p.joint = s->d_joint; p.jd = s->net.self_dim + s->net.l[3].out; p.self_dim = s->net.self_dim;
   p.trace = nullptr;
