@@ -215,6 +215,25 @@ int ebc_reset(ebc_sim *s, const ebc_state *pool, int32_t pool_size, const int32_
   return ebc_launch_reset(s, pool, pool_size, pool_index, mask, (cudaStream_t)stream);
 }
 
+int ebc_generate(ebc_sim *s, const ebc_scene_shape *shape, uint64_t seed, const int64_t *episode_ids, const uint8_t *mask,
+                 void *stream) {
+  REQUIRE_BOUND("ebc_generate");
+  if (!shape || !episode_ids) return ebc_fail(s, EBC_ERR_INVALID, "ebc_generate: null shape or episode ids");
+  if (shape->n_types < 1 || shape->n_types > 4 || shape->max_tries < 1 || shape->rule < 0 || shape->rule > 2)
+    return ebc_fail(s, EBC_ERR_INVALID, "ebc_generate: bad shape");
+  int humans = 0;
+  for (int t = 0; t < shape->n_types; ++t) {
+    if (shape->type_count[t] < 0) return ebc_fail(s, EBC_ERR_INVALID, "ebc_generate: negative group size");
+    humans += shape->type_count[t];
+  }
+  if (humans > s->cfg.max_humans || humans > 64)
+    return ebc_fail(s, EBC_ERR_INVALID, "ebc_generate: %d humans do not fit (Hmax %d, generator limit 64)", humans, s->cfg.max_humans);
+  if (shape->num_walls > s->cfg.max_rects || shape->num_walls * shape->discs_per_wall > s->cfg.max_statics)
+    return ebc_fail(s, EBC_ERR_INVALID, "ebc_generate: %d walls x %d discs do not fit (Rmax %d, Smax %d)", shape->num_walls,
+                    shape->discs_per_wall, s->cfg.max_rects, s->cfg.max_statics);
+  return ebc_launch_generate(s, shape, seed, episode_ids, mask, (cudaStream_t)stream);
+}
+
 int ebc_debug_trace(ebc_sim *s, long long *out, int32_t n) {
   if (!s || !out || n < 1) return EBC_ERR_INVALID;
   if (!s->d_trace) return ebc_fail(s, EBC_ERR_UNBOUND, "ebc_debug_trace: run ebc_value with EBC_TC_TRACE=1 first");

@@ -97,6 +97,9 @@ int ebc_launch_transform(ebc_sim *s, float *out, cudaStream_t st);
 int ebc_launch_reset(ebc_sim *s, const ebc_state *pool, int pool_size, const int32_t *pool_index,
                      const uint8_t *mask, cudaStream_t st);
 
+int ebc_launch_generate(ebc_sim *s, const ebc_scene_shape *shape, uint64_t seed, const int64_t *episode_ids,
+                        const uint8_t *mask, cudaStream_t st);
+
 // ebc_value.cu
 int ebc_value_prepare(ebc_sim *s, const ebc_weights *w);
 void ebc_value_release(ebc_sim *s);

@@ -821,7 +821,145 @@ reset_kernel(const ebc_config c, const ebc_state st, const ebc_state pool, int p
   }
 }
 
+// ---- scene generator: thread per episode, counter-based draws, fp64 in the host generator's
+//      operation order (this unit is compiled without FMA contraction), narrowed to fp32 at the end ----------
+__device__ __forceinline__ unsigned long long gen_mix(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__device__ __forceinline__ double gen_uniform(unsigned long long seed, unsigned long long episode, unsigned long long stream,
+                                              unsigned long long draw) {
+  unsigned long long h = gen_mix(seed ^ gen_mix(episode));
+  h = gen_mix(h ^ (stream * 0xD6E8FEB86659FD93ull));
+  h = gen_mix(h ^ (draw * 0xCA5A826395121157ull));
+  return (double)(h >> 11) * (1.0 / 9007199254740992.0);
+}
+
+__global__ void __launch_bounds__(128)
+generate_kernel(const ebc_config c, const ebc_state st, const ebc_scene_shape sh, unsigned long long seed,
+                const long long *episode_ids, const uint8_t *mask) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= c.n_episodes) return;
+  if (mask && !mask[e]) return;
+  const unsigned long long id = (unsigned long long)episode_ids[e];
+  const int Hm = c.max_humans, Sm = c.max_statics, Rm = c.max_rects;
+  const double R = sh.circle_radius, hw = sh.square_width / 2.0, dd = sh.discomfort_dist;
+  double px[64], py[64], rad[64];
+  int H = 0;
+  for (int t = 0; t < sh.n_types; ++t) H += sh.type_count[t];
+  // scene_generator.py:292-328: per-agent preferred speed and radius, group by group
+  int h0 = 0;
+  for (int t = 0; t < sh.n_types; ++t) {
+    int first_of_type = h0;                     // first agent of the same list (groups may repeat a type)
+    for (int u = t - 1, hu = h0; u >= 0; --u) {
+      hu -= sh.type_count[u];
+      if (sh.type_code[u] == sh.type_code[t] && sh.type_count[u] > 0) first_of_type = hu;
+    }
+    for (int k = 0; k < sh.type_count[t]; ++k) {
+      const int h = h0 + k;
+      const double vpref = sh.v_pref_lo[t] + (sh.v_pref_hi[t] - sh.v_pref_lo[t]) * gen_uniform(seed, id, 1000 + h, 0);
+      rad[h] = sh.radius_lo[t] + (sh.radius_hi[t] - sh.radius_lo[t]) * gen_uniform(seed, id, 1000 + h, 1);
+      const bool circle = sh.rule == 1 || (sh.rule == 2 && h < H / 2);
+      double x = 0, y = 0, tx = 0, ty = 0;
+      for (int attempt = 0; attempt < sh.max_tries; ++attempt) {
+        const unsigned long long d0 = (unsigned long long)attempt * 8ull;
+        if (circle) {           // :593-618: start on the circle, goal opposite
+          const double ang = gen_uniform(seed, id, 2000 + h, d0) * 2.0 * 3.141592653589793;
+          x = R * cos(ang); y = R * sin(ang);
+          tx = -x; ty = -y;
+        } else {                // :672-712: start on one side of the square, goal on the opposite side
+          const long long side = (long long)floor(gen_uniform(seed, id, 2000 + h, d0) * 4.0);
+          const double a = -hw + 2.0 * hw * gen_uniform(seed, id, 2000 + h, d0 + 1);
+          const double b = -hw + 2.0 * hw * gen_uniform(seed, id, 2000 + h, d0 + 2);
+          x = side == 0 ? a : (side == 1 ? a : (side == 2 ? -hw : hw));
+          y = side == 0 ? hw : (side == 1 ? -hw : a);
+          tx = side == 0 ? b : (side == 1 ? b : (side == 2 ? hw : -hw));
+          ty = side == 0 ? -hw : (side == 1 ? hw : b);
+        }
+        // :683-693: reject starts too close to the robot or to agents of the same list placed earlier
+        bool ok = hypot(x - 0.0, y + R) >= rad[h] + sh.robot_radius + dd;
+        for (int j = first_of_type; j < h && ok; ++j) ok = hypot(x - px[j], y - py[j]) >= rad[h] + rad[j] + dd;
+        if (ok || attempt == sh.max_tries - 1) break;
+      }
+      px[h] = x; py[h] = y;
+      reinterpret_cast<float4 *>(st.hum_pv)[(size_t)e * Hm + h] = make_float4((float)x, (float)y, 0.f, 0.f);
+      reinterpret_cast<float4 *>(st.hum_gr)[(size_t)e * Hm + h] = make_float4((float)tx, (float)ty, (float)vpref, (float)rad[h]);
+      st.hum_type[(size_t)e * Hm + h] = (uint8_t)sh.type_code[t];
+      reinterpret_cast<float2 *>(st.hum_nv)[(size_t)e * Hm + h] = make_float2(0.f, 0.f);
+    }
+    h0 += sh.type_count[t];
+  }
+  for (int h = H; h < Hm; ++h) {
+    reinterpret_cast<float4 *>(st.hum_pv)[(size_t)e * Hm + h] = make_float4(0.f, 0.f, 0.f, 0.f);
+    reinterpret_cast<float4 *>(st.hum_gr)[(size_t)e * Hm + h] = make_float4(0.f, 0.f, 0.f, 0.f);
+    st.hum_type[(size_t)e * Hm + h] = 0;
+    reinterpret_cast<float2 *>(st.hum_nv)[(size_t)e * Hm + h] = make_float2(0.f, 0.f);
+  }
+  st.hum_count[e] = H;
+  // walls (:205-290) -> grid rectangle (:888-922) + static discs (:380-422)
+  const double res = sh.map_resolution;
+  const double G = rint(sh.map_size_m / res);
+  const double clear = sh.robot_radius + dd;
+  int n_stat = 0;
+  for (int w = 0; w < sh.num_walls; ++w) {
+    double lx = 0, ly = 0, xd = 1, yd = 1;
+    for (int attempt = 0; attempt < sh.max_tries; ++attempt) {
+      const unsigned long long d0 = (unsigned long long)attempt * 8ull;
+      const double cx = floor(-G / 2.0 + G * gen_uniform(seed, id, 3000 + w, d0));
+      const double cy = floor(-G / 2.0 + G * gen_uniform(seed, id, 3000 + w, d0 + 1));
+      const double length = floor((double)sh.wall_len_lo +
+                                  (double)(sh.wall_len_hi - sh.wall_len_lo + 1) * gen_uniform(seed, id, 3000 + w, d0 + 3));
+      const bool horiz = gen_uniform(seed, id, 3000 + w, d0 + 2) > 0.5;
+      const double xdim = horiz ? length : 1.0, ydim = horiz ? 1.0 : length;
+      const double xm = cx * res, ym = cy * res;
+      const bool near_start = fabs(xm - 0.0) < xdim / 2 + clear && fabs(ym + R) < ydim / 2 + clear;
+      const bool near_goal = fabs(xm - 0.0) < xdim / 2 + clear && fabs(ym - R) < ydim / 2 + clear;
+      lx = cx; ly = cy; xd = xdim; yd = ydim;
+      if (!(near_start || near_goal) || attempt == sh.max_tries - 1) break;
+    }
+    const double dimx = rint(xd / res), dimy = rint(yd / res);
+    const double locx = rint(lx + G / 2.0), locy = rint(ly + G / 2.0);
+    const double x0 = rint(locx - dimx / 2.0), y0 = rint(locy - dimy / 2.0);
+    short4 r;
+    r.x = (short)fmin(fmax(x0, 0.0), G); r.y = (short)fmin(fmax(y0, 0.0), G);
+    r.z = (short)fmin(fmax(x0 + dimx, 0.0), G); r.w = (short)fmin(fmax(y0 + dimy, 0.0), G);
+    reinterpret_cast<short4 *>(st.rect)[(size_t)e * Rm + w] = r;
+    const double xm = lx * res, ym = ly * res;
+    const bool horiz = xd > yd;
+    const double rr = (horiz ? yd : xd) / 2.0 * sqrt(2.0);
+    const double hi = horiz ? xm + xd / 2.0 : ym + yd / 2.0;
+    double pos = (horiz ? xm - xd / 2.0 : ym - yd / 2.0) + rr;
+    for (int k = 0; k < sh.discs_per_wall; ++k) {
+      if (pos < hi && n_stat < Sm) {
+        reinterpret_cast<float4 *>(st.stat)[(size_t)e * Sm + n_stat] =
+            make_float4((float)(horiz ? pos : xm), (float)(horiz ? ym : pos), (float)rr, 0.f);
+        ++n_stat;
+      }
+      pos = pos + 2.0 * rr;
+    }
+  }
+  for (int k = n_stat; k < Sm; ++k) reinterpret_cast<float4 *>(st.stat)[(size_t)e * Sm + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int w = sh.num_walls; w < Rm; ++w) reinterpret_cast<short4 *>(st.rect)[(size_t)e * Rm + w] = make_short4(0, 0, 0, 0);
+  st.stat_count[e] = n_stat;
+  st.rect_count[e] = sh.num_walls;
+  // env.py:128-140: robot at (0, -R) facing +y, goal (0, R), at rest; global_time = 0
+  reinterpret_cast<float4 *>(st.rob_pv)[e] = make_float4(0.f, (float)(-R), 0.f, 0.f);
+  reinterpret_cast<float4 *>(st.rob_gr)[e] = make_float4(0.f, (float)R, (float)sh.robot_v_pref, (float)sh.robot_radius);
+  st.rob_theta[e] = (float)(3.141592653589793 / 2);
+  st.time[e] = 0.0;
+}
+
 }  // namespace
+
+int ebc_launch_generate(ebc_sim *s, const ebc_scene_shape *shape, uint64_t seed, const int64_t *episode_ids,
+                        const uint8_t *mask, cudaStream_t stream) {
+  const int blocks = (s->cfg.n_episodes + 127) / 128;
+  generate_kernel<<<blocks, 128, 0, stream>>>(s->cfg, s->st, *shape, (unsigned long long)seed,
+                                              reinterpret_cast<const long long *>(episode_ids), mask);
+  return ebc_check_launch(s, "generate_kernel");
+}
 
 int ebc_launch_reset(ebc_sim *s, const ebc_state *pool, int pool_size, const int32_t *pool_index,
                      const uint8_t *mask, cudaStream_t stream) {

@@ -57,6 +57,15 @@ class EbcWeights(ctypes.Structure):
 
 
 # name -> (restype, argtypes) for every entry point include/ebcadrl.h declares for libebcadrl.so
+class EbcSceneShape(ctypes.Structure):
+    _fields_ = [("n_types", c_i32), ("type_code", c_i32 * 4), ("type_count", c_i32 * 4),
+                ("v_pref_lo", c_f64 * 4), ("v_pref_hi", c_f64 * 4), ("radius_lo", c_f64 * 4), ("radius_hi", c_f64 * 4),
+                ("rule", c_i32), ("num_walls", c_i32), ("wall_len_lo", c_i32), ("wall_len_hi", c_i32),
+                ("discs_per_wall", c_i32), ("max_tries", c_i32),
+                ("square_width", c_f64), ("circle_radius", c_f64), ("robot_radius", c_f64), ("robot_v_pref", c_f64),
+                ("map_size_m", c_f64), ("map_resolution", c_f64), ("discomfort_dist", c_f64)]
+
+
 SIM = vp
 PROTOTYPES = {
     "ebc_create": (c_i32, [ctypes.POINTER(EbcConfig), c_i32, ctypes.POINTER(SIM)]),
@@ -77,6 +86,7 @@ PROTOTYPES = {
     "ebc_orca_step": (c_i32, [SIM, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "ebc_transform": (c_i32, [SIM, vp, vp]),
     "ebc_reset": (c_i32, [SIM, ctypes.POINTER(EbcState), c_i32, vp, vp, vp]),
+    "ebc_generate": (c_i32, [SIM, ctypes.POINTER(EbcSceneShape), ctypes.c_uint64, vp, vp, vp]),
     "ebc_debug_trace": (c_i32, [SIM, vp, c_i32]),
     "ebc_launch_count": (ctypes.c_int64, [SIM]),
 }

@@ -253,6 +253,13 @@ class BatchedSim(object):
         as a device-resident pool for `reset`."""
         return ScenePool(self, scenes)
 
+    def generate(self, shape, episode_ids, mask=None, seed=None):
+        """env.reset with a scene generated on the device for the masked episodes: `shape` is an
+        ebc.synth.SceneShape, `episode_ids` an int64 device tensor of GLOBAL episode ids (the generator's key)."""
+        from . import synth
+        self.be.call("generate", self.h, ctypes.byref(shape.to_abi()), ctypes.c_uint64(synth.SEED_BASE if seed is None else seed),
+                     _ptr(episode_ids), _ptr(mask), stream=self._stream())
+
     def reset(self, pool, pool_index=None, mask=None):
         """env.reset for the masked episodes from a device scene pool (simulator/env.py:128-205)."""
         self.be.call("reset", self.h, ctypes.byref(pool.state), pool.size, _ptr(pool_index), _ptr(mask),

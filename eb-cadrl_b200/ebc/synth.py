@@ -62,6 +62,22 @@ class SceneShape(object):
     def Rmax(self):
         return max(self.num_walls, 1)
 
+    def to_abi(self, max_tries=64):
+        """ebc_scene_shape for the device generator (ebc_generate): same distribution, same draws as generate()."""
+        from . import abi
+        s = abi.EbcSceneShape()
+        s.n_types = len(self.types)
+        for i, (code, count, (v0, v1), (r0, r1)) in enumerate(self.types):
+            s.type_code[i], s.type_count[i] = code, count
+            s.v_pref_lo[i], s.v_pref_hi[i], s.radius_lo[i], s.radius_hi[i] = v0, v1, r0, r1
+        s.rule = {"square_crossing": 0, "circle_crossing": 1, "mixed": 2}[self.rule]
+        s.num_walls, s.wall_len_lo, s.wall_len_hi = self.num_walls, self.wall_len[0], self.wall_len[1]
+        s.discs_per_wall, s.max_tries = self.discs_per_wall, max_tries
+        s.square_width, s.circle_radius = self.square_width, self.circle_radius
+        s.robot_radius, s.robot_v_pref = self.robot_radius, self.robot_v_pref
+        s.map_size_m, s.map_resolution, s.discomfort_dist = self.map_size_m, self.map_resolution, self.discomfort_dist
+        return s
+
 
 # BASELINE.json configs[1]: ranges from data/eb-cadrl/adults_8_..._fix_static.config:61-88
 CFG2 = SceneShape("cfg2_h10_typed_3walls", [(0, 4, (0.4, 0.8), (0.2, 0.4)), (1, 3, (0.5, 1.5), (0.3, 0.6)),

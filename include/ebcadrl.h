@@ -245,6 +245,32 @@ int ebc_transform(ebc_sim *sim, float *out, void *stream);
 int ebc_reset(ebc_sim *sim, const ebc_state *pool, int32_t pool_size, const int32_t *pool_index,
               const uint8_t *mask, void *stream);
 
+/* Shape of a generated scene: the distribution of simulator/scene/scene_generator.py (square_crossing
+ * :672-712, circle_crossing :593-618, walls :205-290, static discs :380-422, grid rectangles :888-922)
+ * driven by a counter-based generator -- every draw is splitmix64(seed, global episode id, stream, draw),
+ * so an episode's scene does not depend on the batch or on how episodes are sharded over ranks.  It does
+ * NOT replay numpy's MT19937 stream (that is the host parity path of the Python mirror). */
+typedef struct ebc_scene_shape {
+  int32_t n_types;            /* human groups, in list order (adults, bicycles, children) */
+  int32_t type_code[4];       /* EBC_TYPE_* of each group */
+  int32_t type_count[4];
+  double v_pref_lo[4], v_pref_hi[4], radius_lo[4], radius_hi[4];
+  int32_t rule;               /* 0 square_crossing, 1 circle_crossing, 2 mixed (first half circle) */
+  int32_t num_walls;
+  int32_t wall_len_lo, wall_len_hi;   /* metres, inclusive */
+  int32_t discs_per_wall;     /* static discs a wall of wall_len_hi decomposes into */
+  int32_t max_tries;          /* rejection-sampling attempts per placement; the last one is accepted */
+  double square_width, circle_radius, robot_radius, robot_v_pref;
+  double map_size_m, map_resolution, discomfort_dist;
+} ebc_scene_shape;
+
+/* env.reset with a freshly generated scene (simulator/env.py:128-205 + scene_generator.py) for the episodes
+ * e with mask[e] != 0 (mask NULL = all): episode_ids[e] (device, int64, the GLOBAL episode id that keys the
+ * generator) -> humans with rejection sampling against the robot start and same-type agents, walls with
+ * start / goal exclusion, their grid rectangles and static discs, robot at (0, -R) -> (0, R), time = 0. */
+int ebc_generate(ebc_sim *sim, const ebc_scene_shape *shape, uint64_t seed, const int64_t *episode_ids,
+                 const uint8_t *mask, void *stream);
+
 /* Diagnostics: with EBC_TC_TRACE=1 in the environment the tensor-core K4 kernel records clock64()
  * stamps of CTA 0 (phase boundaries of its first tiles); this copies up to 4096 of them to the host. */
 int ebc_debug_trace(ebc_sim *sim, long long *out, int32_t n);

@@ -388,3 +388,35 @@ def test_error_codes():
     assert lib.ebc_create(ctypes.byref(bad), 0, ctypes.byref(h2)) == -1
     assert b"out of range" in lib.ebc_last_error(None)
     lib.ebc_destroy(h)
+
+
+@pytest.mark.parametrize("shape_name,N", [("CFG2", 4096), ("CFG3", 2048), ("CFG4", 2048), ("CFG1", 512)])
+def test_device_scene_generator_matches_host(shape_name, N):
+    """the device generator (ebc_generate, thread per episode, counter-based draws) against the host
+    generator of ebc/synth.py (numpy float64, same draws): humans with rejection sampling, walls with start / goal
+    exclusion, grid rectangles, static discs, robot.  Integer outputs and counts exact; fp32 state bit-exact except
+    where CUDA's and glibc's cos/sin/hypot differ in the last double ulp before narrowing (none observed; bar 1e-6)."""
+    shape = getattr(synth, shape_name)
+    ids = np.arange(7000, 7000 + N)                      # global episode ids: any shard gives the same scenes
+    host = synth.generate(shape, ids)
+    sim = BatchedSim(SimConfig(), N, shape.H, max(shape.Smax, 1), shape.Rmax, 81, device="cuda:0")
+    sim.hum_pv.fill_(7.0); sim.stat.fill_(7.0); sim.hum_nv.fill_(7.0); sim.time.fill_(3.0)   # must all be overwritten
+    mask = torch.ones(N, dtype=torch.uint8, device="cuda:0")
+    mask[5] = 0                                            # a masked episode keeps its state
+    sim.generate(shape, torch.as_tensor(ids, dtype=torch.int64, device="cuda:0"), mask=mask)
+    torch.cuda.synchronize()
+    keep = np.arange(N) != 5
+    for k in ("hum_count", "stat_count", "rect_count", "hum_type", "rect"):
+        assert np.array_equal(np_(getattr(sim, k))[keep], host[k][keep]), k
+    for k in ("hum_pv", "hum_gr", "stat", "rob_pv", "rob_gr", "rob_theta", "time"):
+        a, b = np_(getattr(sim, k))[keep], host[k][keep]
+        np.testing.assert_allclose(a, b.reshape(a.shape), rtol=0, atol=1e-6, err_msg=k)
+        assert (a != b.reshape(a.shape)).mean() < 1e-4, k
+    assert float(sim.hum_pv[5, 0, 0]) == 7.0 and float(sim.time[5]) == 3.0
+    assert (np_(sim.hum_nv)[keep] == 0).all()
+    # and the generated batch is a valid starting state: one full decision + step runs on it
+    sim.set_actions(build_action_space(shape.robot_v_pref))
+    sim.orca()
+    sim.step(action_idx=torch.zeros(N, dtype=torch.int32, device="cuda:0"))
+    torch.cuda.synchronize()
+    assert np.isfinite(np_(sim.hum_pv)[keep]).all()
