@@ -442,10 +442,12 @@ __device__ void evaluate_action_warp(const ebc_config &c, const ebc_state &st, i
     o.end_y = rpy + sin(th) * a0 * dt;
   }
   // env.py:303-338: per type, list order, dmin frozen at the first collision
-  double closest[2];
+  double closest[2] = {INFINITY, INFINITY};
   unsigned long long collm = 0ull, typem[3] = {0ull, 0ull, 0ull};
+  const int n_ch = c.max_humans > 32 ? 2 : 1;      // lanes hold humans 32..63 only when the batch has that many
 #pragma unroll
   for (int ch = 0; ch < 2; ++ch) {
+    if (ch >= n_ch) break;
     const bool valid = hm.type[ch] >= 0 && hm.type[ch] <= 2;
     const double px = (double)hm.pv[ch].x - rpx, py = (double)hm.pv[ch].y - rpy;
     const double vx = (double)hm.pv[ch].z - avx, vy = (double)hm.pv[ch].w - avy;
