@@ -44,7 +44,6 @@ constexpr int NCG = NCREW / TILE_M;             // column groups
 constexpr int KMAX = 208;                       // widest A operand chunk kept in shared memory
 constexpr int NKB = KMAX / 16;                  // 16-column blocks of an A operand
 constexpr int TMEM_COLS = 512;
-constexpr int PS_LD = TILE_M + 4;
 constexpr int MAX_STATES = 32;                  // states per entity tile (rows per state >= 4)
 
 template <int NSPLIT> struct Cfg {
@@ -271,7 +270,7 @@ template <int NSPLIT, bool GSUM>
 __device__ __forceinline__ void epi_to_a(Pipe<NSPLIT> &pipe, uint32_t tmem_row, int cg, int col0, int ncols, int n_real,
                                          const float *__restrict__ bias, uint8_t *a_base, int row, bool chase,
                                          int n_free, int n = 1, int row_cnt = 0, float *g_out = nullptr, int g_ld = 0,
-                                         int g_states = 0, bool wait_first = false) {
+                                         int g_states = 0, bool wait_first = false, int g_sid = 0, int g_rin = 0) {
   if (wait_first && 16 * cg < ncols) {
     pipe.wait_free(cg < n_free ? cg : 0);
     tc_fence_after();
@@ -302,7 +301,7 @@ __device__ __forceinline__ void epi_to_a(Pipe<NSPLIT> &pipe, uint32_t tmem_row, 
     }
     if (chase) pipe.publish(c >> 4);
     if (GSUM) {
-      const int r_in = row % n;                 // row index inside its state
+      const int r_in = g_rin;                   // row index inside its state
       const bool real = r_in < row_cnt;         // padding rows do not enter the mean
       const float inv = row_cnt > 0 ? 1.0f / (float)row_cnt : 0.0f;
       if (n == 16) {
@@ -328,13 +327,13 @@ __device__ __forceinline__ void epi_to_a(Pipe<NSPLIT> &pipe, uint32_t tmem_row, 
         }
         const float send = (lane & 1) ? w2[0] : w2[1], keep = (lane & 1) ? w2[1] : w2[0];
         const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-        if (row / n < g_states) g_out[(row / n) * g_ld + c + (lane & 15)] = tot * inv;
+        if (g_sid < g_states) g_out[g_sid * g_ld + c + (lane & 15)] = tot * inv;
       } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float x = real ? v[i] : 0.0f;
           for (int o = 1; o < n; o <<= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-          if (r_in == 0 && row / n < g_states) g_out[(row / n) * g_ld + c + i] = x * inv;
+          if (r_in == 0 && g_sid < g_states) g_out[g_sid * g_ld + c + i] = x * inv;
         }
       }
     }
@@ -477,17 +476,35 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
     const int g_ld = 16 * h1b;                        // row stride of G
     // this thread's 8 input values of a tile (k-chunk cg of row `row`), fetched one tile ahead so that the
     // HBM latency of the value-network input hides behind the previous tile's tail
+    // Row -> (state, row inside the state).  States are packed so that the position of a state's rows relative
+    // to the warp boundaries depends on n only: floor(32 / n) whole states per warp when n <= 32 (the remaining
+    // lanes of the warp are padding rows), a whole number of warps per state otherwise.  Every per-state
+    // reduction then adds in an order that does not depend on where the state sits in the batch, and results
+    // are bit-identical under any permutation of the episodes.  For n | 32 this is the plain row = s n + r.
+    const int spw = n <= 32 ? 32 / n : 0, wps = (n + 31) >> 5;     // states per warp / warps per state
+    int my_sid, my_rin;
+    bool my_row;
+    if (n <= 32) {
+      const int sl = (row & 31) / n;
+      my_sid = (row >> 5) * spw + sl;
+      my_rin = (row & 31) - sl * n;
+      my_row = sl < spw;
+    } else {
+      my_sid = (row >> 5) / wps;
+      my_rin = ((row >> 5) % wps) * 32 + (row & 31);
+      my_row = my_rin < n;
+    }
+    my_row = my_row && my_sid < ts;
     float xu[8];
     int cnt_next = 0;                                 // threads 0-31: row count of state tid of the next tile
     auto load_x = [&](long long t) {
       const long long t0 = t * ts;
       const int tstates = (int)min((long long)ts, p.n_states - t0);
-      const int trows = tstates * n;
-      const float *src = p.vin + ((size_t)t0 * n + row) * D;
+      const float *src = p.vin + ((size_t)(t0 + my_sid) * n + my_rin) * D;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int k = 8 * cg + j;
-        xu[j] = (row < trows && k < D) ? __ldg(src + k) : 0.0f;
+        xu[j] = (my_row && my_sid < tstates && k < D) ? __ldg(src + k) : 0.0f;
       }
       if (tid < MAX_STATES) {
         int c = 0;
@@ -506,12 +523,11 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long s0 = tile * ts;
       const int ns = (int)min((long long)ts, p.n_states - s0);
-      const int rows = ns * n;
       if (tid < MAX_STATES) cnt[tid] = cnt_next;
       // ---- X -> A (K padded to 32): thread (row, cg) converts k-chunk cg (values prefetched below) -------
       store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, row, 8 * cg, xu);
-      if (cg == 0 && row < rows && row % n == 0)
-        for (int k = 0; k < p.self_dim; ++k) XS[(row / n) * 8 + k] = xu[k];
+      if (cg == 0 && my_row && my_sid < ns && my_rin == 0)
+        for (int k = 0; k < p.self_dim; ++k) XS[my_sid * 8 + k] = xu[k];
       pipe.signal_a();
       // ---- mlp1.0 -> mlp1.2, K chunked by the wide halves; the second half overwrites the blocks of the first
       //      as mlp1.2's first K chunk releases them --------------------------------------------------------
@@ -526,13 +542,13 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
       // ---- H1 -> A; mlp2.0 and attention.0 (local half) share it -------------------------------------
       pipe.wait_acc();                                                             // #2
       const bool gsum = P.with_global && (32 % n == 0);
-      const int st_of_row = min(row / n, ts - 1);
+      const int st_of_row = min(my_sid, ts - 1);
       {
         const TcStage &S = P.st[ST_L1A];
         if (gsum) {
           crew_sync();   // cnt[] of this tile is visible
           epi_to_a<NSPLIT, true>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, P.bias[1], A, row, true, 0, n,
-                                 cnt[st_of_row], G, g_ld, ts);
+                                 cnt[st_of_row], G, g_ld, ts, false, my_sid, my_rin);
         } else {
           epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, P.bias[1], A, row, true, 0);
         }
@@ -549,7 +565,8 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
             const int c = cnt[s];
             float acc = 0.0f;
             for (int r = 0; r < c; ++r) {
-              const size_t off = (size_t)(k >> 3) * A_CHUNK_BYTES + (size_t)(s * n + r) * 16 + (size_t)(k & 7) * 2;
+              const int trow = n <= 32 ? ((s / spw) << 5) + (s % spw) * n + r : ((s * wps + (r >> 5)) << 5) + (r & 31);
+              const size_t off = (size_t)(k >> 3) * A_CHUNK_BYTES + (size_t)trow * 16 + (size_t)(k & 7) * 2;
               float v = 0.0f;
 #pragma unroll
               for (int sp = 0; sp < NSPLIT; ++sp)
@@ -590,7 +607,6 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
         SC[cg * TILE_M + row] = epi_dot(tmem_row, cg, S.acc_col, S.np, P.bias[5], P.w6);
       }
       crew_sync();
-      float *WT = SC + NCG * TILE_M;   // softmax weight per row
       if (n == 16) {
         // a state = 16 aligned lanes of this warp: softmax and pooling stay in registers (shuffles), the
         // pooled feature goes straight to the joint row -- no scratch, no further block synchronisation
@@ -640,30 +656,63 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
           p.joint[(size_t)(s0 + s) * p.jd + k] = XS[s * 8 + k];
         }
       } else {
-        if (tid < ts) {
-          const int c = cnt[tid];
-          float sum = 0.0f;
-          for (int r = 0; r < c; ++r) {
-            const int rr = tid * n + r;
-            const float sc = ((SC[rr] + SC[TILE_M + rr]) + (SC[2 * TILE_M + rr] + SC[3 * TILE_M + rr])) + P.b6;
-            const float e = (sc != 0.0f) ? expf(sc) : 0.0f;
-            WT[rr] = e;
-            sum += e;
+        // any row count: a state's rows are a contiguous run of rows, i.e. at most one run of lanes per warp.
+        // Sums over a state = segmented shuffle reduction inside each warp, one partial per (lane quarter, state)
+        // in shared memory, added in a fixed order (deterministic, no atomics).  Scratch aliases the A region,
+        // which is free: every MMA that read it has completed.
+        const int lane = tid & 31, q = warp & 3;
+        const int sid = my_row ? my_sid : -1 - (row >> 5);         // padding rows: a run of their own
+        const int r_in = my_rin;
+        const bool in_tile = my_row && my_sid < ns;
+        const bool real = in_tile && r_in < cnt[min(my_sid, MAX_STATES - 1)];
+        const int sid_up = __shfl_up_sync(0xffffffffu, sid, 1);
+        const bool head = lane == 0 || sid_up != sid;              // first lane of this state's run in the warp
+        float *PSUM = reinterpret_cast<float *>(A);                // [4][MAX_STATES]
+        float *PJ = PSUM + 4 * MAX_STATES;                         // [4][ts][np3]
+        const TcStage &S = P.st[ST_L3];
+        const float sc = ((SC[row] + SC[TILE_M + row]) + (SC[2 * TILE_M + row] + SC[3 * TILE_M + row])) + P.b6;
+        const float e = (real && sc != 0.0f) ? expf(sc) : 0.0f;
+        {
+          float es = e;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const float y = __shfl_down_sync(0xffffffffu, es, o);
+            const int s2 = __shfl_down_sync(0xffffffffu, sid, o);
+            if (lane + o < 32 && s2 == sid) es += y;
           }
-          for (int r = 0; r < n; ++r) WT[tid * n + r] = (r < c) ? WT[tid * n + r] / sum : 0.0f;
+          if (cg == 0 && head && in_tile) PSUM[q * MAX_STATES + sid] = es;
         }
         crew_sync();
-        // weighted H2 rows -> scratch (the A region is free: all MMAs that read it have completed)
-        float *PS = reinterpret_cast<float *>(A);
-        {
-          const float wrow = (row < ts * n) ? WT[row] : 0.0f;
-          const TcStage &S = P.st[ST_L3];
-          for (int c = 16 * cg; c < S.np; c += 16 * NCG) {
-            float v[16];
-            tmem_ld16(tmem_row + S.acc_col + c, v);
+        const int q_lo = n <= 32 ? my_sid / spw : my_sid * wps;    // lane quarters the state spans
+        const int q_hi = n <= 32 ? q_lo : q_lo + wps - 1;
+        float sum = 0.0f;
+        if (in_tile)
+          for (int qq = q_lo; qq <= q_hi; ++qq) sum += PSUM[qq * MAX_STATES + sid];
+        const float wrow = e / sum;          // NaN like the reference when every score of the state is exactly 0
+        for (int c = 16 * cg; c < S.np; c += 16 * NCG) {
+          float v[16];
+          tmem_ld16(tmem_row + S.acc_col + c, v);
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (c + i < h2d) PS[(c + i) * PS_LD + row] = (v[i] + __ldg(P.bias[3] + c + i)) * wrow;
+          for (int qd = 0; qd < 4; ++qd) {
+            const float4 bb = __ldg(reinterpret_cast<const float4 *>(P.bias[3] + c) + qd);
+            v[4 * qd] += bb.x; v[4 * qd + 1] += bb.y; v[4 * qd + 2] += bb.z; v[4 * qd + 3] += bb.w;
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = (real && c + i < h2d) ? v[i] * wrow : 0.0f;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int s2 = __shfl_down_sync(0xffffffffu, sid, o);
+            const bool take = lane + o < 32 && s2 == sid;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float y = __shfl_down_sync(0xffffffffu, v[i], o);
+              if (take) v[i] += y;
+            }
+          }
+          if (head && in_tile) {
+            float4 *dst = reinterpret_cast<float4 *>(PJ + ((size_t)q * ts + sid) * S.np + c);
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) dst[qd] = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
           }
         }
         crew_sync();
@@ -673,8 +722,9 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
           if (k < p.self_dim) v = XS[s * 8 + k];
           else {
             v = 0.0f;
-            const int c = cnt[s], col = k - p.self_dim;
-            for (int r = 0; r < c; ++r) v += PS[col * PS_LD + s * n + r];
+            const int col = k - p.self_dim;
+            const int a_lo = n <= 32 ? s / spw : s * wps, a_hi = n <= 32 ? a_lo : a_lo + wps - 1;
+            for (int qq = a_lo; qq <= a_hi; ++qq) v += PJ[((size_t)qq * ts + s) * S.np + col];
           }
           p.joint[(size_t)(s0 + s) * p.jd + k] = v;
         }
@@ -837,13 +887,16 @@ int launch_tc(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row
   p.prog = s->tc[NSPLIT - 1].entity;
   p.vin = vin; p.row_count = row_count; p.hum_count = s->st.hum_count; p.stat_count = s->st.stat_count;
   p.n_actions = s->cfg.n_actions; p.n_states = n_states; p.n = n; p.D = s->net.D;
-  int ts = TILE_M / n;
-  if (ts < 1) ts = 1;
+  // states per 128-row tile: whole states per warp (n <= 32) or whole warps per state (see the kernel)
+  int ts = n <= 32 ? 4 * (32 / n) : 4 / ((n + 31) / 32);
+  if (ts < 1) return ebc_fail(s, EBC_ERR_INVALID, "tensor-core value path: %d rows per state do not fit a 128-row tile", n);
   if (ts > MAX_STATES) ts = MAX_STATES;
   if (s->net.with_global) {                      // G[state][h1 padded] must fit its shared-memory region
     const int g_cap = (int)(Cfg<NSPLIT>::G_BYTES / (4u * (uint32_t)p.prog.st[ST_L2].ksteps * 16u));
     if (ts > g_cap) ts = g_cap;
   }
+  // generic row counts pool through a scratch that aliases the operand images: [4][32] + [4][ts][np3] floats
+  while (n != 16 && ts > 1 && 512u + 16u * (uint32_t)ts * (uint32_t)p.prog.st[ST_L3].np > Cfg<NSPLIT>::A_BYTES) --ts;
   p.ts = ts;
   p.joint = s->d_joint; p.jd = s->net.self_dim + s->net.l[3].out; p.self_dim = s->net.self_dim;
   p.trace = nullptr;
@@ -882,7 +935,6 @@ int ebc_tc_prepare(ebc_sim *s, const ebc_weights *w, int mode_index, int nsplit)
   if (!fits(m10->out_dim, h1, h1) || pad16(m20->out_dim) > KMAX || pad16(m22->out_dim) > KMAX ||
       pad16(a0->out_dim) > KMAX || pad16(a2->out_dim) > KMAX || m10->in_dim > 32 ||
       !fits(p0->out_dim, p2->out_dim, p4->out_dim) || pad16(p0->in_dim) > KMAX ||
-      (size_t)m22->out_dim * (TILE_M + 4) * 4 > (size_t)TILE_M * KMAX * 2 /* pooling scratch aliases one A image */ ||
       w->self_state_dim > 8)
     return 1;
   TcPrograms &T = s->tc[mode_index];

@@ -7,10 +7,11 @@ import bench
 from ebc import synth
 from ebc.actions import build_action_space
 from ebc.engine import BatchedSim
-shape,cfg=bench.workload(); w,_=bench.value_net_weights()
-N=4096
+WL=os.environ.get("WORKLOAD","cfg2")
+shape,cfg=bench.workload(WL); w,_=bench.value_net_weights(fixture=bench.WORKLOADS[WL][3])
+N=min(bench.WORKLOADS[WL][4],4096)
 sim=BatchedSim(cfg,N,shape.H,shape.Smax,shape.Rmax,81,device="cuda:0")
-sim.set_actions(build_action_space(shape.robot_v_pref)); sim.set_weights(w)
+sim.set_actions(build_action_space(shape.robot_v_pref, cfg.robot_kinematics)); sim.set_weights(w)
 synth.load(sim, synth.generate(shape,np.arange(N)))
 mode = sys.argv[1] if len(sys.argv)>1 else "tc_fp32"
 sim.set_value_mode(mode)
