@@ -270,7 +270,8 @@ template <int NSPLIT, bool GSUM>
 __device__ __forceinline__ void epi_to_a(Pipe<NSPLIT> &pipe, uint32_t tmem_row, int cg, int col0, int ncols, int n_real,
                                          const float *__restrict__ bias, uint8_t *a_base, int row, bool chase,
                                          int n_free, int n = 1, int row_cnt = 0, float *g_out = nullptr, int g_ld = 0,
-                                         int g_states = 0, bool wait_first = false, int g_sid = 0, int g_rin = 0) {
+                                         int g_states = 0, bool wait_first = false, int g_sid = 0, int g_rin = 0,
+                                         int g_seg = 0, int g_part = 0) {
   if (wait_first && 16 * cg < ncols) {
     pipe.wait_free(cg < n_free ? cg : 0);
     tc_fence_after();
@@ -328,12 +329,37 @@ __device__ __forceinline__ void epi_to_a(Pipe<NSPLIT> &pipe, uint32_t tmem_row, 
         const float send = (lane & 1) ? w2[0] : w2[1], keep = (lane & 1) ? w2[1] : w2[0];
         const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 1);
         if (g_sid < g_states) g_out[g_sid * g_ld + c + (lane & 15)] = tot * inv;
-      } else {
+      } else if (32 % n == 0) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float x = real ? v[i] : 0.0f;
           for (int o = 1; o < n; o <<= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
           if (r_in == 0 && g_sid < g_states) g_out[g_sid * g_ld + c + i] = x * inv;
+        }
+      } else {
+        // any row count: the state's rows are one run of lanes of this warp (g_seg identifies the run; a state
+        // longer than a warp leaves one partial per warp, g_part).  Segmented shuffle reduction, the run's
+        // first lane stores.  The order of the additions depends on n only (see the row packing in the kernel).
+        const int lane = threadIdx.x & 31;
+        float x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = real ? v[i] : 0.0f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int s2 = __shfl_down_sync(0xffffffffu, g_seg, o);
+          const bool take = lane + o < 32 && s2 == g_seg;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float y = __shfl_down_sync(0xffffffffu, x[i], o);
+            if (take) x[i] += y;
+          }
+        }
+        const int up = __shfl_up_sync(0xffffffffu, g_seg, 1);
+        if ((lane == 0 || up != g_seg) && g_seg >= 0 && g_sid < g_states) {
+          float4 *dst = reinterpret_cast<float4 *>(g_out + ((size_t)g_part * g_states + g_sid) * g_ld + c);
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd)
+            dst[qd] = make_float4(x[4 * qd] * inv, x[4 * qd + 1] * inv, x[4 * qd + 2] * inv, x[4 * qd + 3] * inv);
         }
       }
     }
@@ -344,7 +370,7 @@ __device__ __forceinline__ void epi_to_a(Pipe<NSPLIT> &pipe, uint32_t tmem_row, 
 // mean of its own state, so [H1 | G] . [W_local | W_global]^T accumulates in one TMEM accumulator (sarl.py:51-63).
 template <int NSPLIT>
 __device__ __forceinline__ void gx_to_a(Pipe<NSPLIT> &pipe, const float *G, int g_ld, int state, int cg, int h1d, int h1p,
-                                        uint8_t *a_base, int row, int n_free) {
+                                        uint8_t *a_base, int row, int n_free, int n_parts, int part_stride) {
   for (int c = 16 * cg; c < h1p; c += 16 * NCG) {
     float v[16];
     const float4 *g4 = reinterpret_cast<const float4 *>(G + state * g_ld + c);   // one address per state: broadcast
@@ -352,6 +378,14 @@ __device__ __forceinline__ void gx_to_a(Pipe<NSPLIT> &pipe, const float *G, int 
     for (int q = 0; q < 4; ++q) {
       const float4 g = g4[q];
       v[4 * q] = g.x; v[4 * q + 1] = g.y; v[4 * q + 2] = g.z; v[4 * q + 3] = g.w;
+    }
+    for (int pt = 1; pt < n_parts; ++pt) {       // a state longer than a warp: one partial mean per warp, fixed order
+      const float4 *h4 = reinterpret_cast<const float4 *>(G + (size_t)pt * part_stride + state * g_ld + c);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 g = h4[q];
+        v[4 * q] += g.x; v[4 * q + 1] += g.y; v[4 * q + 2] += g.z; v[4 * q + 3] += g.w;
+      }
     }
     if (c + 16 > h1d) {
 #pragma unroll
@@ -541,14 +575,13 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
       }
       // ---- H1 -> A; mlp2.0 and attention.0 (local half) share it -------------------------------------
       pipe.wait_acc();                                                             // #2
-      const bool gsum = P.with_global && (32 % n == 0);
       const int st_of_row = min(my_sid, ts - 1);
       {
         const TcStage &S = P.st[ST_L1A];
-        if (gsum) {
+        if (P.with_global && n <= 32) {
           crew_sync();   // cnt[] of this tile is visible
           epi_to_a<NSPLIT, true>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, P.bias[1], A, row, true, 0, n,
-                                 cnt[st_of_row], G, g_ld, ts, false, my_sid, my_rin);
+                                 cnt[st_of_row], G, g_ld, ts, false, my_sid, my_rin, my_row ? my_sid : -1 - (row >> 5), 0);
         } else {
           epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, P.bias[1], A, row, true, 0);
         }
@@ -556,16 +589,17 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
       pipe.stamp();
       // ---- global state: G -> A as the second K chunk of attention.0 (sarl.py:51-63) -----------------------
       if (P.with_global) {
-        if (gsum) {
-          __syncwarp();    // G[., state] of this warp's states and column group was written by this warp
+        if (n <= 32) {
+          __syncwarp();    // G[., state] for this thread's blocks was written by this warp
         } else {
+          // states longer than a warp (few per tile): the mean is read back from the operand images, rows in order
           crew_sync();     // every H1 block is in the A images
-          for (int i = tid; i < ts * h1d; i += NCREW) {   // generic row counts: mean read back from the images
+          for (int i = tid; i < ts * h1d; i += NCREW) {
             const int k = i % h1d, s = i / h1d;
             const int c = cnt[s];
             float acc = 0.0f;
             for (int r = 0; r < c; ++r) {
-              const int trow = n <= 32 ? ((s / spw) << 5) + (s % spw) * n + r : ((s * wps + (r >> 5)) << 5) + (r & 31);
+              const int trow = ((s * wps + (r >> 5)) << 5) + (r & 31);
               const size_t off = (size_t)(k >> 3) * A_CHUNK_BYTES + (size_t)trow * 16 + (size_t)(k & 7) * 2;
               float v = 0.0f;
 #pragma unroll
@@ -577,7 +611,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
           }
           crew_sync();
         }
-        gx_to_a<NSPLIT>(pipe, G, g_ld, st_of_row, cg, h1d, 16 * h1b, A, row, h1b);
+        gx_to_a<NSPLIT>(pipe, G, g_ld, st_of_row, cg, h1d, 16 * h1b, A, row, h1b, 1, 0);
         pipe.f_phase ^= low_bits(h1b);                  // attention.0 (local half) released every H1 block
         pipe.stamp();
       }
