@@ -395,6 +395,7 @@ __device__ __forceinline__ double point_to_segment_dist0(double x1, double y1, d
 struct Outcome {
   double dmin[3];
   double end_x, end_y, dist_to_goal, reward;
+  double cs, sn;   // cos / sin of the robot's heading after the action (non-holonomic), computed once per action
   int done, event;
 };
 
@@ -432,14 +433,18 @@ __device__ void evaluate_action_warp(const ebc_config &c, const ebc_state &st, i
   if (c.robot_kinematics == EBC_KIN_HOLONOMIC) {   // collisions.py:37-42, agent.py:164-176
     avx = a0;
     avy = a1;
+    o.cs = 0.0; o.sn = 0.0;
     o.end_x = rpx + a0 * dt;
     o.end_y = rpy + a1 * dt;
   } else {
+    // collisions.py:39-41 uses action.r + theta, agent.py:172-183 theta + action.r: the same double
     const double th = theta + a1;
-    avx = a0 * cos(a1 + theta);
-    avy = a0 * sin(a1 + theta);
-    o.end_x = rpx + cos(th) * a0 * dt;
-    o.end_y = rpy + sin(th) * a0 * dt;
+    o.cs = cos(th);
+    o.sn = sin(th);
+    avx = a0 * o.cs;
+    avy = a0 * o.sn;
+    o.end_x = rpx + o.cs * a0 * dt;
+    o.end_y = rpy + o.sn * a0 * dt;
   }
   // env.py:303-338: per type, list order, dmin frozen at the first collision
   double closest[2] = {INFINITY, INFINITY};
@@ -632,7 +637,7 @@ lookahead_kernel(const ebc_config c, const ebc_state st, const double *__restric
     rr.theta = (float)theta;
   } else {
     const double nth = theta + a1;
-    const double nvx = a0 * cos(nth), nvy = a0 * sin(nth);
+    const double nvx = a0 * o.cs, nvy = a0 * o.sn;   // cos / sin of theta + a1, already computed for the collision test
     rr.px = (float)((double)rp.x + nvx * dt);
     rr.py = (float)((double)rp.y + nvy * dt);
     rr.vx = (float)nvx;
