@@ -18,6 +18,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "ebc_internal.cuh"
 
@@ -423,6 +424,49 @@ __device__ __forceinline__ void load_humans(const ebc_config &c, const ebc_state
   }
 }
 
+// reward.py:80-181 and the Info classes: the priority chain from the three dmin / four collision flags
+__device__ __forceinline__ void classify_outcome(const ebc_config &c, const float4 rg, double gt, double a1,
+                                                 const bool (&coll)[3], bool coll_obst, Outcome &o) {
+  const double rrad = rg.w, dt = c.time_step;
+  const double gdx = o.end_x - (double)rg.x, gdy = o.end_y - (double)rg.y;
+  const double dist = sqrt(gdx * gdx + gdy * gdy);
+  o.dist_to_goal = dist;
+  const bool reaching = dist < rrad;
+  const double goal_reward = c.has_max_goal_distance ? 1.0 - dist / c.max_goal_distance : 0.0;
+  double reward = c.new_reward ? goal_reward : 0.0;
+  int done, ev;
+  if (gt >= c.time_limit) { done = 1; ev = EBC_EV_TIMEOUT; }
+  else if (coll[EBC_CHILD]) { reward += c.collision_penalty_child; done = 1; ev = EBC_EV_COLLISION_CHILD; }
+  else if (coll[EBC_BICYCLE]) { reward += c.collision_penalty_bicycle; done = 1; ev = EBC_EV_COLLISION_BICYCLE; }
+  else if (coll[EBC_ADULT]) { reward += c.collision_penalty_adult; done = 1; ev = EBC_EV_COLLISION_ADULT; }
+  else if (coll_obst) { reward += c.collision_penalty_obstacle; done = 1; ev = EBC_EV_COLLISION_OBSTACLE; }
+  else if (reaching) {
+    if (c.new_reward) {
+      double tr;
+      if (gt < c.time_good) tr = 1.0;
+      else if (gt <= c.time_max) tr = (c.time_max - gt) / (c.time_max - c.time_good);
+      else tr = 0.0;
+      reward += tr;
+    } else {
+      reward += c.success_reward;
+    }
+    done = 1; ev = EBC_EV_REACH_GOAL;
+  } else if (o.dmin[EBC_CHILD] < c.discomfort_dist_child) {
+    reward = (o.dmin[EBC_CHILD] - c.discomfort_dist_child) * c.discomfort_penalty_factor_child * dt;
+    done = 0; ev = EBC_EV_DANGER;
+  } else if (o.dmin[EBC_BICYCLE] < c.discomfort_dist_bicycle) {
+    reward = (o.dmin[EBC_BICYCLE] - c.discomfort_dist_bicycle) * c.discomfort_penalty_factor_bicycle * dt;
+    done = 0; ev = EBC_EV_DANGER;
+  } else if (o.dmin[EBC_ADULT] < c.discomfort_dist_adult) {
+    reward = (o.dmin[EBC_ADULT] - c.discomfort_dist_adult) * c.discomfort_penalty_factor_adult * dt;
+    done = 0; ev = EBC_EV_DANGER;
+  } else if (c.robot_kinematics != EBC_KIN_HOLONOMIC && fabs(a1) > 0.0 && c.rotation_penalty_factor != 0.0) {
+    reward = fabs(a1) * c.rotation_penalty_factor;
+    done = 0; ev = EBC_EV_NOTHING;
+  } else { reward = 0.0; done = 0; ev = EBC_EV_NOTHING; }
+  o.reward = reward; o.done = done; o.event = ev;
+}
+
 // env.py:424-444 for one (episode, action), cooperatively by one warp; result warp-uniform.
 __device__ void evaluate_action_warp(const ebc_config &c, const ebc_state &st, int e, int lane,
                                      const EpisodeHumans &hm, const float4 rp, const float4 rg, double theta,
@@ -495,44 +539,84 @@ __device__ void evaluate_action_warp(const ebc_config &c, const ebc_state &st, i
     }
     coll_obst = __any_sync(FULL, hit);
   }
-  // reward.py:80-181
-  const double gdx = o.end_x - (double)rg.x, gdy = o.end_y - (double)rg.y;
-  const double dist = sqrt(gdx * gdx + gdy * gdy);
-  o.dist_to_goal = dist;
-  const bool reaching = dist < rrad;
-  const double goal_reward = c.has_max_goal_distance ? 1.0 - dist / c.max_goal_distance : 0.0;
-  double reward = c.new_reward ? goal_reward : 0.0;
-  int done, ev;
-  if (gt >= c.time_limit) { done = 1; ev = EBC_EV_TIMEOUT; }
-  else if (coll[EBC_CHILD]) { reward += c.collision_penalty_child; done = 1; ev = EBC_EV_COLLISION_CHILD; }
-  else if (coll[EBC_BICYCLE]) { reward += c.collision_penalty_bicycle; done = 1; ev = EBC_EV_COLLISION_BICYCLE; }
-  else if (coll[EBC_ADULT]) { reward += c.collision_penalty_adult; done = 1; ev = EBC_EV_COLLISION_ADULT; }
-  else if (coll_obst) { reward += c.collision_penalty_obstacle; done = 1; ev = EBC_EV_COLLISION_OBSTACLE; }
-  else if (reaching) {
-    if (c.new_reward) {
-      double tr;
-      if (gt < c.time_good) tr = 1.0;
-      else if (gt <= c.time_max) tr = (c.time_max - gt) / (c.time_max - c.time_good);
-      else tr = 0.0;
-      reward += tr;
-    } else {
-      reward += c.success_reward;
+  classify_outcome(c, rg, gt, a1, coll, coll_obst, o);
+}
+
+// K3 with several (episode, action) pairs per warp: a group of G lanes (8 or 16) does what the warp does in
+// evaluate_action_warp when the episode has at most G humans.  Same arithmetic in the same order; ballots and
+// reductions are confined to the group.
+template <int G>
+__device__ __forceinline__ unsigned group_ballot(bool pred, int sub) {
+  return (__ballot_sync(FULL, pred) >> (sub * G)) & ((1u << G) - 1u);
+}
+template <int G>
+__device__ void evaluate_action_group(const ebc_config &c, const ebc_state &st, int e, int l, int sub, int H,
+                                      const float4 rp, const float4 rg, double theta, double gt, double a0, double a1,
+                                      Outcome &o) {
+  const double rpx = rp.x, rpy = rp.y, rrad = rg.w;
+  const double dt = c.time_step;
+  double avx, avy;
+  if (c.robot_kinematics == EBC_KIN_HOLONOMIC) {
+    avx = a0;
+    avy = a1;
+    o.cs = 0.0; o.sn = 0.0;
+    o.end_x = rpx + a0 * dt;
+    o.end_y = rpy + a1 * dt;
+  } else {
+    const double th = theta + a1;
+    o.cs = cos(th);
+    o.sn = sin(th);
+    avx = a0 * o.cs;
+    avy = a0 * o.sn;
+    o.end_x = rpx + o.cs * a0 * dt;
+    o.end_y = rpy + o.sn * a0 * dt;
+  }
+  float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+  float rad = 0.f;
+  int type = -1;
+  if (l < H) {
+    const size_t i = (size_t)e * c.max_humans + l;
+    pv = reinterpret_cast<const float4 *>(st.hum_pv)[i];
+    rad = st.hum_gr[i * 4 + 3];
+    type = st.hum_type[i];
+  }
+  const bool valid = type >= 0 && type <= 2;
+  const double px = (double)pv.x - rpx, py = (double)pv.y - rpy;
+  const double vx = (double)pv.z - avx, vy = (double)pv.w - avy;
+  const double ex = px + vx * dt, ey = py + vy * dt;
+  const double closest = point_to_segment_dist0(px, py, ex, ey) - (double)rad - rrad;
+  const unsigned collm = group_ballot<G>(valid && closest < 0.0, sub);
+  bool coll[3];
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    const unsigned cm = collm & group_ballot<G>(valid && type == t, sub);
+    coll[t] = cm != 0u;
+    const int first = coll[t] ? (__ffs((int)cm) - 1) : 64;
+    double local = (type == t && l < first) ? closest : INFINITY;
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) local = fmin(local, __shfl_xor_sync(FULL, local, off));
+    o.dmin[t] = local;
+  }
+  bool coll_obst = false;
+  {
+    const int ix = (int)rint((o.end_x + c.map_size_m / 2.0) / c.map_resolution);
+    const int iy = (int)rint((o.end_y + c.map_size_m / 2.0) / c.map_resolution);
+    const int sz = (int)ceil(rrad / sqrt(2.0) / c.map_resolution);
+    const int GR = (int)rint(c.map_size_m / c.map_resolution);
+    int sx = ix - sz, exx = sx + sz * 2, sy = iy - sz, eyy = sy + sz * 2;
+    sx = max(sx, 0); exx = min(exx, GR); sy = max(sy, 0); eyy = min(eyy, GR);
+    const int R = st.rect_count[e];
+    bool hit = false;
+    if (exx > sx && eyy > sy) {
+      const short4 *rc = reinterpret_cast<const short4 *>(st.rect) + (size_t)e * c.max_rects;
+      for (int j = l; j < R; j += G) {
+        const short4 r = rc[j];
+        hit |= (sx < r.z && r.x < exx && sy < r.w && r.y < eyy);
+      }
     }
-    done = 1; ev = EBC_EV_REACH_GOAL;
-  } else if (o.dmin[EBC_CHILD] < c.discomfort_dist_child) {
-    reward = (o.dmin[EBC_CHILD] - c.discomfort_dist_child) * c.discomfort_penalty_factor_child * dt;
-    done = 0; ev = EBC_EV_DANGER;
-  } else if (o.dmin[EBC_BICYCLE] < c.discomfort_dist_bicycle) {
-    reward = (o.dmin[EBC_BICYCLE] - c.discomfort_dist_bicycle) * c.discomfort_penalty_factor_bicycle * dt;
-    done = 0; ev = EBC_EV_DANGER;
-  } else if (o.dmin[EBC_ADULT] < c.discomfort_dist_adult) {
-    reward = (o.dmin[EBC_ADULT] - c.discomfort_dist_adult) * c.discomfort_penalty_factor_adult * dt;
-    done = 0; ev = EBC_EV_DANGER;
-  } else if (c.robot_kinematics != EBC_KIN_HOLONOMIC && fabs(a1) > 0.0 && c.rotation_penalty_factor != 0.0) {
-    reward = fabs(a1) * c.rotation_penalty_factor;
-    done = 0; ev = EBC_EV_NOTHING;
-  } else { reward = 0.0; done = 0; ev = EBC_EV_NOTHING; }
-  o.reward = reward; o.done = done; o.event = ev;
+    coll_obst = group_ballot<G>(hit, sub) != 0u;
+  }
+  classify_outcome(c, rg, gt, a1, coll, coll_obst, o);
 }
 
 // rl/policy/cadrl.py:236-337, one row, fp32 (-fmad=false keeps torch's separate mul/add).
@@ -646,6 +730,84 @@ lookahead_kernel(const ebc_config c, const ebc_state st, const double *__restric
   }
   rr.radius = rg.w; rr.gx = rg.x; rr.gy = rg.y; rr.v_pref = rg.z;
   build_rows_warp(c, st, e, lane, H, S, rr, true, tiles + (size_t)warp * n * D, vin + ea * (size_t)n * D);
+}
+
+// K3 for episodes with at most G rows per state (G = 8 or 16): 32 / G (episode, action) pairs per warp, lane l of
+// a group holds human l for the outcome and row l for the rotated joint state.  Bit-identical to lookahead_kernel.
+template <int G>
+__global__ void __launch_bounds__(EBC_THREADS)
+lookahead_group_kernel(const ebc_config c, const ebc_state st, const double *__restrict__ actions, float *vin,
+                       double *reward, uint8_t *done, uint8_t *event) {
+  extern __shared__ float tiles[];
+  constexpr int GPW = 32 / G;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane / G, l = lane % G;
+  const int A = c.n_actions;
+  const long long total = (long long)c.n_episodes * A;
+  const long long w0 = ((long long)blockIdx.x * EBC_WARPS_PER_BLOCK + warp) * GPW;
+  if (w0 >= total) return;                       // warp-uniform
+  const long long w = w0 + sub;
+  const bool live = w < total;                   // trailing groups of the last warp idle along (shuffles are warp-wide)
+  const long long wc = live ? w : total - 1;
+  const int e = (int)(wc / A), a = (int)(wc % A);
+  const int n = c.max_humans + c.max_statics, D = c.with_agent_type ? 17 : 13;
+  const int H = st.hum_count[e], S = st.stat_count[e];
+  const float4 rp = reinterpret_cast<const float4 *>(st.rob_pv)[e];
+  const float4 rg = reinterpret_cast<const float4 *>(st.rob_gr)[e];
+  const double theta = (double)st.rob_theta[e];
+  const double a0 = actions[a * 2], a1 = actions[a * 2 + 1];
+  Outcome o;
+  evaluate_action_group<G>(c, st, e, l, sub, H, rp, rg, theta, st.time[e], a0, a1, o);
+  const size_t ea = (size_t)e * A + a;
+  if (live && l == 0) {
+    if (reward) reward[ea] = o.reward;
+    if (done) done[ea] = (uint8_t)o.done;
+    if (event) event[ea] = (uint8_t)o.event;
+  }
+  if (!vin) return;
+  RobotRow rr;
+  const double dt = c.time_step;
+  if (c.robot_kinematics == EBC_KIN_HOLONOMIC) {
+    rr.px = (float)((double)rp.x + a0 * dt);
+    rr.py = (float)((double)rp.y + a1 * dt);
+    rr.vx = (float)a0;
+    rr.vy = (float)a1;
+    rr.theta = (float)theta;
+  } else {
+    const double nth = theta + a1;
+    const double nvx = a0 * o.cs, nvy = a0 * o.sn;
+    rr.px = (float)((double)rp.x + nvx * dt);
+    rr.py = (float)((double)rp.y + nvy * dt);
+    rr.vx = (float)nvx;
+    rr.vy = (float)nvy;
+    rr.theta = (float)nth;
+  }
+  rr.radius = rg.w; rr.gx = rg.x; rr.gy = rg.y; rr.v_pref = rg.z;
+  // rows (n <= G): lane l builds row l in the group's tile, then the group copies it out contiguously
+  float *tile = tiles + (size_t)(warp * GPW + sub) * n * D;
+  if (l < n) {
+    float *row = tile + l * D;
+    const int Hm = c.max_humans, Sm = c.max_statics;
+    if (l < H) {
+      const float4 p = reinterpret_cast<const float4 *>(st.hum_pv)[(size_t)e * Hm + l];
+      const float rad = st.hum_gr[((size_t)e * Hm + l) * 4 + 3];
+      const int ty = st.hum_type[(size_t)e * Hm + l];
+      const float2 nv = reinterpret_cast<const float2 *>(st.hum_nv)[(size_t)e * Hm + l];
+      const float npx = (float)((double)p.x + (double)nv.x * dt);
+      const float npy = (float)((double)p.y + (double)nv.y * dt);
+      rotate_row(rr, npx, npy, nv.x, nv.y, rad, ty, c.rotate_theta, D, row);
+    } else if (l < H + S) {
+      const float4 p = reinterpret_cast<const float4 *>(st.stat)[(size_t)e * Sm + (l - H)];
+      rotate_row(rr, p.x, p.y, 0.0f, 0.0f, p.z, EBC_ADULT_STATIC, c.rotate_theta, D, row);
+    } else {
+      for (int k = 0; k < D; ++k) row[k] = 0.0f;
+    }
+  }
+  __syncwarp();
+  if (live) {
+    float *dst = vin + ea * (size_t)n * D;
+    const int cnt = n * D;
+    for (int i = l; i < cnt; i += G) dst[i] = tile[i];
+  }
 }
 
 // rl/policy/multi_human_rl.py:128-149
@@ -990,11 +1152,21 @@ int ebc_launch_robot_orca(ebc_sim *s, double safety, double *out, cudaStream_t s
 
 int ebc_launch_lookahead(ebc_sim *s, float *vin, double *reward, uint8_t *done, uint8_t *event,
                          cudaStream_t stream) {
-  const long long warps = (long long)s->cfg.n_episodes * s->cfg.n_actions;
-  const int blocks = (int)((warps + EBC_WARPS_PER_BLOCK - 1) / EBC_WARPS_PER_BLOCK);
+  const long long pairs = (long long)s->cfg.n_episodes * s->cfg.n_actions;
   const int n = s->cfg.max_humans + s->cfg.max_statics, D = s->cfg.with_agent_type ? 17 : 13;
-  const size_t smem = (size_t)EBC_WARPS_PER_BLOCK * n * D * sizeof(float);
-  lookahead_kernel<<<blocks, EBC_THREADS, smem, stream>>>(s->cfg, s->st, s->d_actions, vin, reward, done, event);
+  // small states: several (episode, action) pairs per warp (EBC_LOOKAHEAD_GROUP=32 forces one per warp)
+  const char *env = getenv("EBC_LOOKAHEAD_GROUP");
+  const int group = env ? atoi(env) : (n <= 8 ? 8 : (n <= 16 ? 16 : 32));
+  const int gpw = group == 8 || group == 16 ? 32 / group : 1;
+  const long long warps = (pairs + gpw - 1) / gpw;
+  const int blocks = (int)((warps + EBC_WARPS_PER_BLOCK - 1) / EBC_WARPS_PER_BLOCK);
+  const size_t smem = (size_t)EBC_WARPS_PER_BLOCK * gpw * n * D * sizeof(float);
+  if (group == 8 && n <= 8)
+    lookahead_group_kernel<8><<<blocks, EBC_THREADS, smem, stream>>>(s->cfg, s->st, s->d_actions, vin, reward, done, event);
+  else if (group == 16 && n <= 16)
+    lookahead_group_kernel<16><<<blocks, EBC_THREADS, smem, stream>>>(s->cfg, s->st, s->d_actions, vin, reward, done, event);
+  else
+    lookahead_kernel<<<blocks, EBC_THREADS, smem, stream>>>(s->cfg, s->st, s->d_actions, vin, reward, done, event);
   return ebc_check_launch(s, "lookahead_kernel");
 }
 
