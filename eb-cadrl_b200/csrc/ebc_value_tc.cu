@@ -38,7 +38,8 @@ namespace {
 using namespace tc;
 
 constexpr int NCREW = 512;                      // epilogue threads: 4 lane quarters x 4 column groups
-constexpr int NT = NCREW + 96;                  // + the MMA warp (16), the weight-loader warp (17), the scout warp (18)
+constexpr int NLOAD = 2;                        // weight-loader threads (one per warp), slabs dealt round-robin
+constexpr int NT = NCREW + 64 + 32 * NLOAD;     // + the MMA warp (16), the scout warp (17), the loader warps (18, 19)
 constexpr int MAX_SLABS = 120;                  // slabs per tile (entity program: 88, mlp3: 46)
 constexpr int NCG = NCREW / TILE_M;             // column groups
 constexpr int KMAX = 208;                       // widest A operand chunk kept in shared memory
@@ -105,17 +106,23 @@ struct Pipe {
     if (trace && threadIdx.x == 0 && blockIdx.x == 0 && trace_pos < 2048) trace[trace_pos++] = clock64();
   }
 
-  // ---- loader thread: streams every slab of every tile of this CTA through the ring ---------------------
-  __device__ void loader_loop() {
+  // ---- loader threads: stream every slab of every tile of this CTA through the ring.  One thread needs ~390
+  //      cycles per slab (an mbarrier.try_wait costs ~170 cycles even when the slot is free, arrive.expect_tx +
+  //      cp.async.bulk ~190), which is more than the 312 cycles the tensor pipe spends on a k-step: NLOAD threads
+  //      in different warps take every NLOAD-th slab each --------------------------------------------------------
+  __device__ void loader_loop(int which) {
     constexpr uint32_t ST = Cfg<NSPLIT>::STAGES;
-    uint32_t slot = 0, parity = 1, idx = 0;          // parity of the "slot is free" wait: passes on the first lap
-    for (long long i = 0; i < total; ++i) {
+    uint32_t slot = (uint32_t)which % ST, parity = 1u ^ (((uint32_t)which / ST) & 1u);   // "slot is free": passes on lap 0
+    uint32_t idx = (uint32_t)which % (uint32_t)n_stage_slabs;
+    for (long long i = which; i < total; i += NLOAD) {
       mbar_wait(&empty[slot], parity);
       const uint2 sl = tab[idx];
       mbar_arrive_expect_tx(&full[slot], sl.y);
       bulk_g2s(wbuf + (size_t)slot * Cfg<NSPLIT>::STAGE_BYTES, wpack + sl.x, sl.y, &full[slot]);
-      if (++slot == ST) { slot = 0; parity ^= 1u; }
-      if (++idx == (uint32_t)n_stage_slabs) idx = 0;
+      slot += NLOAD;
+      while (slot >= ST) { slot -= ST; parity ^= 1u; }
+      idx += NLOAD;
+      while (idx >= (uint32_t)n_stage_slabs) idx -= (uint32_t)n_stage_slabs;
     }
   }
   // ---- scout thread: follows the per-tile schedule one k-step at a time, waits (blocking, hardware-suspended
@@ -496,9 +503,9 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
     pipe.leader = elect_one();
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) pipe.mma_tile(P, a_smem, tmem_base);
   } else if (warp == NCREW / 32 + 1) {
-    if ((tid & 31) == 0) pipe.loader_loop();
-  } else if (warp == NCREW / 32 + 2) {
     pipe.scout_loop(P, (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  } else if (warp >= NCREW / 32 + 2) {
+    if ((tid & 31) == 0) pipe.loader_loop(warp - (NCREW / 32 + 2));
   } else {
     // ======================================= epilogue crew =======================================
     const int row = ((warp & 3) << 5) | (tid & 31);   // TMEM lane quarter of this warp
@@ -803,9 +810,9 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
     pipe.leader = elect_one();
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) pipe.mma_tile(P, a_smem, tmem_base);
   } else if (warp == NCREW / 32 + 1) {
-    if ((tid & 31) == 0) pipe.loader_loop();
-  } else if (warp == NCREW / 32 + 2) {
     pipe.scout_loop(P, (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  } else if (warp >= NCREW / 32 + 2) {
+    if ((tid & 31) == 0) pipe.loader_loop(warp - (NCREW / 32 + 2));
   } else {
     const int row = ((warp & 3) << 5) | (tid & 31);
     const int cg = warp >> 2;
