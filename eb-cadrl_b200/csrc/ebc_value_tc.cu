@@ -200,9 +200,11 @@ struct Pipe {
     const uint32_t b_lo0 = ((smem_u32(wbuf) >> 4) & 0x3FFFu) | (np << 16);
     const uint32_t base = issued;                 // schedule index of this stage's first k-step
     uint32_t avail = seen - base;                 // cleared k-steps of this stage (the scout may be further ahead)
-    // The k-step loop is warp-uniform (trip count from the program, counters incremented unconditionally); the
-    // only data-dependent part is the wait below, which carries no state besides the cached count.
-    for (int ks = 0; ks < ksteps; ++ks) {
+    // Up to four cleared k-steps are issued per trip: their descriptor words are computed first (independent
+    // instruction chains), then the MMAs and commits go out back to back, so that this warp's own latency per
+    // k-step stays well below the 312 cycles the tensor pipe needs for it.
+    int ks = 0;
+    while (ks < ksteps) {
       if ((int)avail <= ks) {
         uint32_t idle = 0;
         while ((int)(avail = (seen = ready_count()) - base) <= ks) {
@@ -213,18 +215,34 @@ struct Pipe {
         if (trace && leader && blockIdx.x == 0 && trace_pos < 2040)   // diagnostics: (clock, cleared k-steps)
           trace[2048 + trace_pos++] = (clock64() << 16) | (long long)((avail - (uint32_t)ks) & 0xFFFFu);
       }
-      const uint32_t a_lo = a_lo0 + (uint32_t)ks * (2 * A_CHUNK_BYTES / 16);
-      const uint32_t b_lo = b_lo0 + st * (Cfg<NSPLIT>::STAGE_BYTES / 16);
+      int nb = ((int)avail < ksteps ? (int)avail : ksteps) - ks;
+      if (nb > 4) nb = 4;
+      uint32_t a_lo[4], b_lo[4], slot[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t sj = st + (uint32_t)j;
+        if (sj >= ST) sj -= ST;
+        slot[j] = sj;
+        a_lo[j] = a_lo0 + (uint32_t)(ks + j) * (2 * A_CHUNK_BYTES / 16);
+        b_lo[j] = b_lo0 + sj * (Cfg<NSPLIT>::STAGE_BYTES / 16);
+      }
       if (leader) {
 #pragma unroll
-        for (int t = 0; t < Terms<NSPLIT>::N; ++t)
-          umma_f16(d, a_lo + (uint32_t)(Terms<NSPLIT>::a(t) * (Cfg<NSPLIT>::A_IMAGE / 16)),
-                   b_lo + (uint32_t)(Terms<NSPLIT>::b(t)) * np * 2, DESC_HI, idesc, acc0 || ks > 0 || t > 0);
-        umma_commit(&empty[st]);   // frees the slab when these MMAs have read it
-        if (commit_k) umma_commit(&afree[ks]);
+        for (int j = 0; j < 4; ++j) {
+          if (j < nb) {
+#pragma unroll
+            for (int t = 0; t < Terms<NSPLIT>::N; ++t)
+              umma_f16(d, a_lo[j] + (uint32_t)(Terms<NSPLIT>::a(t) * (Cfg<NSPLIT>::A_IMAGE / 16)),
+                       b_lo[j] + (uint32_t)(Terms<NSPLIT>::b(t)) * np * 2, DESC_HI, idesc, acc0 || ks + j > 0 || t > 0);
+            umma_commit(&empty[slot[j]]);   // frees the slab when these MMAs have read it
+            if (commit_k) umma_commit(&afree[ks + j]);
+          }
+        }
       }
       __syncwarp();
-      if (++st == ST) st = 0;
+      ks += nb;
+      st += (uint32_t)nb;
+      if (st >= ST) st -= ST;
     }
     issued = base + (uint32_t)ksteps;
   }
