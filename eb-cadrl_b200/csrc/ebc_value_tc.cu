@@ -6,15 +6,16 @@
 //   -> attention.2 -> attention.4 score } -> masked softmax -> pooled H2 -> joint[state]
 // and a second kernel runs mlp3 over tiles of 128 states.
 //
-// Warp roles (576 threads):
-//   warp 17, one lane          streams the pre-packed weight slabs L2 -> shared memory with cp.async.bulk
-//                              (mbarrier full/empty ring)
-//   warp 16 (converged)        waits on the barriers and issues the tcgen05.mma's from one elected lane:
-//                              A = activations in shared memory (canonical K-major layout written by the
-//                              previous epilogue), B = weight slab, D = fp32 accumulator in TMEM
+// Warp roles (640 threads):
 //   warps 0-15 (512 threads)   epilogue crew: warp w reads TMEM lane quarter (w % 4) (row = lane) and the
 //                              16-column blocks b with b % 4 == w / 4, applies bias / ReLU, splits the fp32
 //                              value into 16-bit parts and stores the next stage's A operand
+//   warp 16 (converged)        issues the tcgen05.mma's from one elected lane, up to four k-steps per trip:
+//                              A = activations in shared memory (canonical K-major layout written by the
+//                              previous epilogue), B = weight slab, D = fp32 accumulator in TMEM
+//   warp 17 (converged)        scout: polls the hand-over barriers and publishes how many k-steps may issue
+//   warps 18-19, one lane each stream the pre-packed weight slabs L2 -> shared memory with cp.async.bulk
+//                              (mbarrier full/empty ring), every other slab each
 // Every stage boundary is a chase in both directions, one 16-column block (= one k-step) at a time:
 //   kbar[b]   crew -> MMA warp: block b of the next A operand is written (the next stage's k-step b may issue)
 //   afree[b]  MMA warp -> crew: the MMAs that read block b of the current A operand have completed
