@@ -56,7 +56,6 @@ struct TcProgram {
 
 struct TcPrograms {
   TcProgram entity, mlp3;
-  const uint8_t *entity_wpack_pair;   // the entity program's slabs laid out for a CTA pair (half of N per CTA)
   uint8_t *slab;                 // one device allocation
   int ready;
 };

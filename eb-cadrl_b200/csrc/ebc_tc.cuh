@@ -70,22 +70,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-// ---- CTA pair (cluster of two; cta_group::2) ----------------------------------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// one arrival on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank) {
-  uint32_t addr;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(addr) : "r"(smem_u32(bar)), "r"(rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
-}
 // generic-proxy smem writes -> visible to the async proxy (UMMA operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -97,14 +81,6 @@ __device__ __forceinline__ void tmem_alloc(uint32_t *slot_in_smem, uint32_t ncol
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {          // whole warp
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t *slot_in_smem, uint32_t ncols) {   // whole warp, both CTAs
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {          // whole warp, both CTAs
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -166,26 +142,6 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint32_t a_lo, uint32_
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
       ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
-}
-// CTA pair: M = 256 (128 rows per CTA), B split by N between the two CTAs' shared memories; issued by the
-// leader CTA (rank 0) only, descriptors are shared-memory offsets valid in both CTAs
-__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
-                                              bool accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-      "mov.b64 da, {%1, %3};\n\t"
-      "mov.b64 db, {%2, %3};\n\t"
-      "setp.ne.b32 p, %5, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
-      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"((uint32_t)accumulate)
-      : "memory");
-}
-// all previously issued pair MMAs done -> one arrival on the barrier at this offset in BOTH CTAs
-__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"((uint16_t)3)
-               : "memory");
 }
 // all previously issued MMAs of this thread done -> one arrival on `bar`
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {

@@ -55,8 +55,6 @@ template <int NSPLIT> struct Cfg {
   // bytes of the per-state mean G[state][h1 padded]: 16 states of the widest layer (8 in the bf16x3 mode, whose
   // operand images leave less room); narrower layers fit more states per tile
   static constexpr uint32_t G_BYTES = (NSPLIT == 3 ? 8 : 16) * KMAX * 4;
-  // a CTA pair keeps half of every slab per CTA: twice the slots in the same bytes (capped by the barrier table)
-  static constexpr int MAX_STAGES = NSPLIT == 2 ? 16 : STAGES;
   static constexpr uint32_t A_IMAGE = TILE_M * KMAX * 2;                 // bytes per split image of A
   static constexpr uint32_t A_BYTES = NSPLIT * A_IMAGE;
   static constexpr uint32_t STAGE_BYTES = NSPLIT * KMAX * 32;            // one k-step slab, all splits
@@ -77,7 +75,7 @@ __host__ __device__ inline Smem smem_layout() {
   s.sc = off; off += TILE_M * 4 * (NCG + 1);           // partial scores per column group, softmax weights
   s.xs = off; off += MAX_STATES * 8 * 4;                // self-state part of each state's first row
   s.tab = off; off += MAX_SLABS * 8;                    // (offset, bytes) of every slab of the per-tile program
-  s.bars = off; off += 768;
+  s.bars = off; off += 512;
   s.total = off;
   return s;
 }
@@ -91,11 +89,7 @@ __device__ __forceinline__ uint32_t low_bits(int n) { return (1u << n) - 1u; }
 // Ring of weight slabs + the MMA warp's cursor; barriers shared with the crew.
 template <int NSPLIT>
 struct Pipe {
-  uint64_t *full, *empty, *pfull, *acc_bar, *a_bar, *kbar, *afree;
-  int ncta;                  // 1, or 2 = CTA pair (cluster of two, tcgen05 cta_group::2: M = 256 over two SMs)
-  uint32_t rank;             // rank in the pair; rank 0 issues the MMAs
-  uint32_t nst;              // ring slots in use (STAGES * ncta, <= MAX_STAGES)
-  uint32_t slot_bytes;       // bytes of one ring slot (one CTA's share of a slab)
+  uint64_t *full, *empty, *acc_bar, *a_bar, *kbar, *afree;
   uint8_t *wbuf;
   const uint8_t *wpack;      // packed weights (global)
   int n_stage_slabs;         // slabs per tile
@@ -116,47 +110,20 @@ struct Pipe {
   // ---- loader threads: stream every slab of every tile of this CTA through the ring.  One thread needs ~390
   //      cycles per slab (an mbarrier.try_wait costs ~170 cycles even when the slot is free, arrive.expect_tx +
   //      cp.async.bulk ~190), which is more than the 312 cycles the tensor pipe spends on a k-step: NLOAD threads
-  //      in different warps take every NLOAD-th slab each.  A CTA of a pair loads its half of every slab. ------
+  //      in different warps take every NLOAD-th slab each --------------------------------------------------------
   __device__ void loader_loop(int which) {
-    const uint32_t ST = nst;
+    constexpr uint32_t ST = Cfg<NSPLIT>::STAGES;
     uint32_t slot = (uint32_t)which % ST, parity = 1u ^ (((uint32_t)which / ST) & 1u);   // "slot is free": passes on lap 0
     uint32_t idx = (uint32_t)which % (uint32_t)n_stage_slabs;
-    long long mine = 0;
-    for (long long i = which; i < total; i += NLOAD, ++mine) {
+    for (long long i = which; i < total; i += NLOAD) {
       mbar_wait(&empty[slot], parity);
       const uint2 sl = tab[idx];
-      const uint32_t share = sl.y / (uint32_t)ncta;  // a CTA of a pair loads its half of the slab (its N rows)
-      mbar_arrive_expect_tx(&full[slot], share);
-      bulk_g2s(wbuf + (size_t)slot * slot_bytes, wpack + sl.x + rank * share, share, &full[slot]);
+      mbar_arrive_expect_tx(&full[slot], sl.y);
+      bulk_g2s(wbuf + (size_t)slot * Cfg<NSPLIT>::STAGE_BYTES, wpack + sl.x, sl.y, &full[slot]);
       slot += NLOAD;
       while (slot >= ST) { slot -= ST; parity ^= 1u; }
       idx += NLOAD;
       while (idx >= (uint32_t)n_stage_slabs) idx -= (uint32_t)n_stage_slabs;
-    }
-    // tail (pairs only): the release of every slab this thread loaded has landed before this CTA may exit (the
-    // commits are multicast by the leader's MMAs into both CTAs)
-    if (ncta == 2) {
-      uint32_t period = ST, g = NLOAD;           // distinct slots this thread visits per lap: ST / gcd(ST, NLOAD)
-      for (uint32_t a = ST, b2 = NLOAD; b2; ) { const uint32_t t2 = a % b2; a = b2; b2 = t2; g = a; }
-      period = ST / g;
-      const long long last = mine < (long long)period ? mine : (long long)period;
-      for (long long i = 0; i < last; ++i) {
-        mbar_wait(&empty[slot], parity);
-        slot += NLOAD;
-        while (slot >= ST) { slot -= ST; parity ^= 1u; }
-      }
-    }
-  }
-  // ---- relay threads (rank 1 of a pair; its MMA and scout warps have nothing else to do): tell the leader that
-  //      this CTA's half of a slab has landed, every other slab each --------------------------------------------
-  __device__ void relay_loop(int which) {
-    const uint32_t ST = nst;
-    uint32_t slot = (uint32_t)which % ST, parity = ((uint32_t)which / ST) & 1u;
-    for (long long i = which; i < total; i += 2) {
-      mbar_wait(&full[slot], parity);
-      mbar_arrive_remote(&pfull[slot], 0);
-      slot += 2;
-      while (slot >= ST) { slot -= ST; parity ^= 1u; }
     }
   }
   // ---- scout thread: follows the per-tile schedule one k-step at a time, waits (blocking, hardware-suspended
@@ -165,8 +132,8 @@ struct Pipe {
   //      mbarrier round trip per k-step: the tensor pipe's queue is shallow, so every cycle the issuing warp
   //      spends polling is a cycle the pipe idles (measured: ~450 polling cycles per 1250 cycles of MMA work).
   __device__ void scout_loop(const TcProgram &P, long long my_tiles) {   // whole warp, converged
-    const uint32_t ST = nst;
-    const uint32_t LOOK = ST < 8 ? ST : 8;            // k-steps examined per poll
+    constexpr uint32_t ST = Cfg<NSPLIT>::STAGES;
+    constexpr uint32_t LOOK = ST < 8 ? ST : 8;        // k-steps examined per poll
     const uint32_t lane = threadIdx.x & 31;
     uint32_t count = 0, slot = 0, par = 0, kph = 0, aph = 0;
     for (long long t = 0; t < my_tiles; ++t) {
@@ -187,20 +154,15 @@ struct Pipe {
             uint32_t sl = slot + lane - 8, pp = par;
             if (sl >= ST) { sl -= ST; pp ^= 1u; }
             ok = mbar_test(&full[sl], pp);
-          } else if (lane >= 16 && lane < 16 + LOOK) {   // the partner's half of the same slabs
-            uint32_t sl = slot + lane - 16, pp = par;
-            if (sl >= ST) { sl -= ST; pp ^= 1u; }
-            ok = ncta == 1 || mbar_test(&pfull[sl], pp);
           }
           const uint32_t m = __ballot_sync(0xffffffffu, ok);
-          const uint32_t both = m & (m >> 8) & (m >> 16) & 0xFFu;
+          const uint32_t both = m & (m >> 8) & 0xFFu;
           int nready = __ffs((int)~both) - 1;            // leading k-steps with both barriers complete
           if (nready > ksteps - ks) nready = ksteps - ks;
           if (nready == 0) {
             // sleep (hardware-suspended) on the first barrier that is missing, then look again
             if (chase && !(m & 1u)) mbar_try_wait(&kbar[ks], (kph >> ks) & 1u);
-            else if (!(m & 0x100u)) mbar_try_wait(&full[slot], par);
-            else mbar_try_wait(&pfull[slot], par);
+            else mbar_try_wait(&full[slot], par);
             if (++idle > (1u << 22)) __trap();
             continue;
           }
@@ -227,10 +189,10 @@ struct Pipe {
   //           16-column block of the previous stage's epilogue) have been stored and fenced by all 128 rows
   // commit_k: signal afree[ks] when the MMAs issued up to and including k-step ks have completed
   __device__ void mma_stage(const TcStage &S, uint32_t a_smem, uint32_t tmem_base, bool commit_k) {
-    const uint32_t ST = nst;
-    const uint32_t idesc = make_idesc_f16(TILE_M * ncta, S.np, Fmt<NSPLIT>::IDESC);
+    constexpr uint32_t ST = Cfg<NSPLIT>::STAGES;
+    const uint32_t idesc = make_idesc_f16(TILE_M, S.np, Fmt<NSPLIT>::IDESC);
     const uint32_t d = tmem_base + S.acc_col;
-    const uint32_t np = (uint32_t)S.np / (uint32_t)ncta;      // B rows held by one CTA
+    const uint32_t np = (uint32_t)S.np;
     const int ksteps = S.ksteps;
     const bool acc0 = S.accumulate != 0;
     // A descriptor = {start address >> 4 | LBO << 16, SBO | version}: only the low word changes (32-bit adds)
@@ -263,27 +225,18 @@ struct Pipe {
         if (sj >= ST) sj -= ST;
         slot[j] = sj;
         a_lo[j] = a_lo0 + (uint32_t)(ks + j) * (2 * A_CHUNK_BYTES / 16);
-        b_lo[j] = b_lo0 + sj * (slot_bytes / 16);
+        b_lo[j] = b_lo0 + sj * (Cfg<NSPLIT>::STAGE_BYTES / 16);
       }
       if (leader) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if (j < nb) {
-            if (ncta == 1) {
 #pragma unroll
-              for (int t = 0; t < Terms<NSPLIT>::N; ++t)
-                umma_f16(d, a_lo[j] + (uint32_t)(Terms<NSPLIT>::a(t) * (Cfg<NSPLIT>::A_IMAGE / 16)),
-                         b_lo[j] + (uint32_t)(Terms<NSPLIT>::b(t)) * np * 2, DESC_HI, idesc, acc0 || ks + j > 0 || t > 0);
-              umma_commit(&empty[slot[j]]);   // frees the slab when these MMAs have read it
-              if (commit_k) umma_commit(&afree[ks + j]);
-            } else {
-#pragma unroll
-              for (int t = 0; t < Terms<NSPLIT>::N; ++t)
-                umma_f16_pair(d, a_lo[j] + (uint32_t)(Terms<NSPLIT>::a(t) * (Cfg<NSPLIT>::A_IMAGE / 16)),
-                              b_lo[j] + (uint32_t)(Terms<NSPLIT>::b(t)) * np * 2, DESC_HI, idesc, acc0 || ks + j > 0 || t > 0);
-              umma_commit_pair(&empty[slot[j]]);
-              if (commit_k) umma_commit_pair(&afree[ks + j]);
-            }
+            for (int t = 0; t < Terms<NSPLIT>::N; ++t)
+              umma_f16(d, a_lo[j] + (uint32_t)(Terms<NSPLIT>::a(t) * (Cfg<NSPLIT>::A_IMAGE / 16)),
+                       b_lo[j] + (uint32_t)(Terms<NSPLIT>::b(t)) * np * 2, DESC_HI, idesc, acc0 || ks + j > 0 || t > 0);
+            umma_commit(&empty[slot[j]]);   // frees the slab when these MMAs have read it
+            if (commit_k) umma_commit(&afree[ks + j]);
           }
         }
       }
@@ -301,10 +254,7 @@ struct Pipe {
     for (int i = 0; i < P.n_sched; ++i) {
       mma_stage(P.st[P.sched[i].stage], a_smem, tmem_base, P.sched[i].commit_k != 0);
       if (P.sched[i].commit_acc) {
-        if (leader) {
-          if (ncta == 1) umma_commit(acc_bar);
-          else umma_commit_pair(acc_bar);
-        }
+        if (leader) umma_commit(acc_bar);
         __syncwarp();
       }
     }
@@ -317,27 +267,19 @@ struct Pipe {
     tc_fence_after();
     stamp();
   }
-  // one arrival per crew warp on a barrier of the CTA that issues the MMAs (rank 0 of a pair)
-  __device__ __forceinline__ void arrive_leader(uint64_t *bar) {
-    __syncwarp();                      // every lane's stores and fences are ordered before lane 0's arrival
-    if ((threadIdx.x & 31) == 0) {
-      if (rank == 0) mbar_arrive(bar);
-      else mbar_arrive_remote(bar, 0);
-    }
-  }
   __device__ void signal_a() {
     stamp();         // after this thread's A-operand stores / TMEM reads
     fence_proxy_async();               // generic-proxy smem writes -> async proxy (UMMA)
     tc_fence_before();                 // this thread's tcgen05.ld's are ordered before the arrive
-    arrive_leader(a_bar);
+    mbar_arrive(a_bar);
   }
   // block b of the A operand may be overwritten: the MMAs of the last commit_k stage that read it are done
   __device__ __forceinline__ void wait_free(int b) { mbar_wait(&afree[b], (f_phase >> b) & 1u); }
   // hand block b of the A operand (this thread's row) to the MMA warp
-  __device__ __forceinline__ void publish(int b) {      // called by all 32 lanes of a warp together
+  __device__ __forceinline__ void publish(int b) {
     fence_proxy_async();
     tc_fence_before();
-    arrive_leader(&kbar[b]);
+    mbar_arrive(&kbar[b]);
   }
 };
 
@@ -509,19 +451,14 @@ __device__ __forceinline__ float epi_dot(uint32_t tmem_row, int cg, int col0, in
 
 template <int NSPLIT>
 __device__ __forceinline__ void pipe_init(Pipe<NSPLIT> &pipe, uint8_t *smem, const Smem &L, const TcProgram &P,
-                                          long long my_tiles, int ncta) {
-  constexpr int MST = Cfg<NSPLIT>::MAX_STAGES;
+                                          long long my_tiles) {
+  constexpr int ST = Cfg<NSPLIT>::STAGES;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
-  pipe.full = bars; pipe.empty = bars + MST; pipe.pfull = bars + 2 * MST;
-  pipe.acc_bar = bars + 3 * MST; pipe.a_bar = bars + 3 * MST + 1;
-  pipe.kbar = bars + 3 * MST + 2; pipe.afree = pipe.kbar + NKB;
+  pipe.full = bars; pipe.empty = bars + ST; pipe.acc_bar = bars + 2 * ST; pipe.a_bar = bars + 2 * ST + 1;
+  pipe.kbar = bars + 2 * ST + 2; pipe.afree = pipe.kbar + NKB;
   pipe.ready = reinterpret_cast<uint32_t *>(pipe.afree + NKB);
-  static_assert((3 * MST + 3 + 2 * NKB) * 8 <= 768, "barrier region");
-  pipe.ncta = ncta;
-  pipe.rank = ncta == 2 ? cluster_ctarank() : 0u;
-  pipe.nst = (uint32_t)(Cfg<NSPLIT>::STAGES * ncta < MST ? Cfg<NSPLIT>::STAGES * ncta : MST);
-  pipe.slot_bytes = Cfg<NSPLIT>::W_BYTES / pipe.nst / 128u * 128u;
   pipe.issued = 0; pipe.seen = 0;
+  static_assert((2 * ST + 3 + 2 * NKB) * 8 <= 512, "barrier region");
   pipe.f_phase = 0;
   pipe.wbuf = smem + L.w; pipe.wpack = P.wpack;
   pipe.n_stage_slabs = P.n_slabs;
@@ -532,11 +469,11 @@ __device__ __forceinline__ void pipe_init(Pipe<NSPLIT> &pipe, uint8_t *smem, con
   pipe.trace = nullptr; pipe.trace_pos = 0;
   pipe.total = my_tiles * P.n_slabs;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < MST; ++i) { mbar_init(&pipe.full[i], 1); mbar_init(&pipe.empty[i], 1); mbar_init(&pipe.pfull[i], 1); }
+    for (int i = 0; i < ST; ++i) { mbar_init(&pipe.full[i], 1); mbar_init(&pipe.empty[i], 1); }
     mbar_init(pipe.acc_bar, 1);
-    mbar_init(pipe.a_bar, (NCREW / 32) * ncta);                     // one arrival per crew warp (of both CTAs)
+    mbar_init(pipe.a_bar, NCREW);
     *pipe.ready = 0;
-    for (int i = 0; i < NKB; ++i) { mbar_init(&pipe.kbar[i], (TILE_M / 32) * ncta); mbar_init(&pipe.afree[i], 1); }
+    for (int i = 0; i < NKB; ++i) { mbar_init(&pipe.kbar[i], TILE_M); mbar_init(&pipe.afree[i], 1); }
     fence_barrier_init();
   }
 }
@@ -552,7 +489,6 @@ struct TcEntityParams {
   int jd;          // self_dim + H2
   int self_dim;
   long long *trace;
-  int ncta;        // 1, or 2 = launched as clusters of two CTAs that share every MMA (cta_group::2)
 };
 
 template <int NSPLIT>
@@ -568,21 +504,12 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
 
   Pipe<NSPLIT> pipe;
-  // A CTA pair walks tile pairs (base, base + 1) in lockstep: rank r owns tile base + r (an empty tile when it
-  // does not exist), the MMAs cover both tiles at once.  A single CTA is the degenerate pair.
-  const int ncta = p.ncta;
   const long long n_tiles = (p.n_states + p.ts - 1) / p.ts;
-  const long long base0 = (long long)(blockIdx.x / ncta) * ncta;
-  const long long my_trips = base0 < n_tiles ? (n_tiles - base0 + gridDim.x - 1) / gridDim.x : 0;
-  pipe_init<NSPLIT>(pipe, smem, L, P, my_trips, ncta);
+  pipe_init<NSPLIT>(pipe, smem, L, P, (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
   pipe.trace = p.trace;
-  if (warp == 0) {
-    if (ncta == 1) tmem_alloc(&tmem_slot, TMEM_COLS);
-    else tmem_alloc_pair(&tmem_slot, TMEM_COLS);
-  }
+  if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
-  if (ncta == 2) cluster_sync_all();     // the partner's barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   const uint32_t a_smem = smem_u32(A);
@@ -592,15 +519,10 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
     // schedule (built on the host, P.sched): mlp1.0 halves | commit #1 | mlp1.2 K chunks chasing the wide-half
     // epilogues | commit #2 | mlp2.0 chasing the H1 epilogue, attention.0 local (H1 complete), attention.0 global
     // chasing the G operand | commit #3 | mlp2.2 chasing the T2 epilogue, attention.2 chasing the U epilogue | commit #4
-    if (pipe.rank == 0) {
-      pipe.leader = elect_one();
-      for (long long t = 0; t < my_trips; ++t) pipe.mma_tile(P, a_smem, tmem_base);
-    } else if ((tid & 31) == 0) {
-      pipe.relay_loop(0);
-    }
+    pipe.leader = elect_one();
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) pipe.mma_tile(P, a_smem, tmem_base);
   } else if (warp == NCREW / 32 + 1) {
-    if (pipe.rank == 0) pipe.scout_loop(P, my_trips);
-    else if ((tid & 31) == 0) pipe.relay_loop(1);
+    pipe.scout_loop(P, (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
   } else if (warp >= NCREW / 32 + 2) {
     if ((tid & 31) == 0) pipe.loader_loop(warp - (NCREW / 32 + 2));
   } else {
@@ -637,7 +559,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
     int cnt_next = 0;                                 // threads 0-31: row count of state tid of the next tile
     auto load_x = [&](long long t) {
       const long long t0 = t * ts;
-      const int tstates = (int)max(0LL, min((long long)ts, p.n_states - t0));
+      const int tstates = (int)min((long long)ts, p.n_states - t0);
       const float *src = p.vin + ((size_t)(t0 + my_sid) * n + my_rin) * D;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -657,11 +579,10 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
         cnt_next = c;
       }
     };
-    if (my_trips > 0) load_x(base0 + pipe.rank);
-    for (long long base = base0; base < n_tiles; base += gridDim.x) {
-      const long long tile = base + pipe.rank;
+    if (blockIdx.x < n_tiles) load_x(blockIdx.x);
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long s0 = tile * ts;
-      const int ns = (int)max(0LL, min((long long)ts, p.n_states - s0));
+      const int ns = (int)min((long long)ts, p.n_states - s0);
       if (tid < MAX_STATES) cnt[tid] = cnt_next;
       // ---- X -> A (K padded to 32): thread (row, cg) converts k-chunk cg (values prefetched below) -------
       store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, row, 8 * cg, xu);
@@ -738,7 +659,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
         pipe.f_phase ^= low_bits(n_free);
       }
       pipe.stamp();
-      if (base + gridDim.x < n_tiles) load_x(tile + gridDim.x);   // next tile's input, consumed after the tail
+      if (tile + gridDim.x < n_tiles) load_x(tile + gridDim.x);   // next tile's input, consumed after the tail
       pipe.wait_acc();                                                             // #4
       // ---- attention.4 score, masked softmax, pooling (sarl.py:64-78) --------------------------------------
       {
@@ -874,11 +795,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
   }
   tc_fence_before();
   __syncthreads();
-  if (ncta == 2) cluster_sync_all();     // nobody leaves (or frees tensor memory) while the partner still works
-  if (warp == 0) {
-    if (ncta == 1) tmem_dealloc(tmem_base, TMEM_COLS);
-    else tmem_dealloc_pair(tmem_base, TMEM_COLS);
-  }
+  if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 struct TcMlp3Params {
@@ -900,8 +817,7 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   Pipe<NSPLIT> pipe;
   const long long n_tiles = (p.n_states + TILE_M - 1) / TILE_M;
-  const long long my_trips = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-  pipe_init<NSPLIT>(pipe, smem, L, P, my_trips, 1);
+  pipe_init<NSPLIT>(pipe, smem, L, P, (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
   if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -911,9 +827,9 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
 
   if (warp == NCREW / 32) {
     pipe.leader = elect_one();
-    for (long long t = 0; t < my_trips; ++t) pipe.mma_tile(P, a_smem, tmem_base);
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) pipe.mma_tile(P, a_smem, tmem_base);
   } else if (warp == NCREW / 32 + 1) {
-    pipe.scout_loop(P, my_trips);
+    pipe.scout_loop(P, (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
   } else if (warp >= NCREW / 32 + 2) {
     if ((tid & 31) == 0) pipe.loader_loop(warp - (NCREW / 32 + 2));
   } else {
@@ -969,9 +885,8 @@ inline int pad16(int x) { return (x + 15) / 16 * 16; }
 
 struct Packer {
   int nsplit;
-  std::vector<uint8_t> bytes;      // slab images for one CTA: [part][k-chunk][np rows][8 k]
-  std::vector<uint8_t> bytes2;     // same slabs for a CTA pair: [half of the N rows][part][k-chunk][np/2 rows][8 k]
-  std::vector<uint32_t> slab_off, slab_bytes;   // identical for both layouts
+  std::vector<uint8_t> bytes;
+  std::vector<uint32_t> slab_off, slab_bytes;
 
   static uint16_t round16(float f, int fp16) {
     if (!fp16) return bf16_rn(f);
@@ -1005,8 +920,6 @@ struct Packer {
       const uint32_t off = (uint32_t)bytes.size();
       const uint32_t sz = (uint32_t)nsplit * (uint32_t)np * 32u;
       bytes.resize(off + sz, 0);
-      bytes2.resize(off + sz, 0);
-      const int nh = np / 2;
       for (int c = 0; c < 2; ++c)
         for (int nn = 0; nn < np; ++nn)
           for (int j = 0; j < 8; ++j) {
@@ -1017,9 +930,6 @@ struct Packer {
               v -= back16(h, nsplit == 2);
               uint8_t *dst = bytes.data() + off + (size_t)s * np * 32 + (size_t)c * np * 16 + (size_t)nn * 16 + j * 2;
               memcpy(dst, &h, 2);
-              uint8_t *dst2 = bytes2.data() + off + (size_t)(nn / nh) * (sz / 2) + (size_t)s * nh * 32 + (size_t)c * nh * 16 +
-                              (size_t)(nn % nh) * 16 + j * 2;
-              memcpy(dst2, &h, 2);
             }
           }
       slab_off.push_back(off);
@@ -1063,23 +973,7 @@ int launch_tc(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row
   const long long tiles_a = (n_states + ts - 1) / ts, tiles_b = (n_states + TILE_M - 1) / TILE_M;
   const int grid_a = (int)(tiles_a < s->sm_count ? tiles_a : s->sm_count);
   const int grid_b = (int)(tiles_b < s->sm_count ? tiles_b : s->sm_count);
-  // one CTA per tile by default; EBC_TC_NCTA=2 runs CTA pairs (cta_group::2, M = 256 over two SMs)
-  const char *env_ncta = getenv("EBC_TC_NCTA");
-  p.ncta = env_ncta && atoi(env_ncta) == 2 && s->sm_count >= 2 ? 2 : 1;
-  {
-    if (p.ncta == 2) p.prog.wpack = s->tc[NSPLIT - 1].entity_wpack_pair;
-    const long long groups = (tiles_a + p.ncta - 1) / p.ncta;
-    const long long max_groups = s->sm_count / p.ncta;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)p.ncta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cudaLaunchConfig_t lc;
-    memset(&lc, 0, sizeof(lc));
-    lc.gridDim = dim3((unsigned)(p.ncta * (groups < max_groups ? groups : max_groups)));
-    lc.blockDim = dim3(NT); lc.dynamicSmemBytes = L.total; lc.stream = stream; lc.attrs = attr; lc.numAttrs = 1;
-    const cudaError_t err = cudaLaunchKernelEx(&lc, tc_entity_kernel<NSPLIT>, p);
-    if (err != cudaSuccess) return ebc_fail(s, EBC_ERR_CUDA, "tc_entity_kernel launch: %s", cudaGetErrorString(err));
-  }
+  tc_entity_kernel<NSPLIT><<<grid_a, NT, L.total, stream>>>(p);
   int rc = ebc_check_launch(s, "tc_entity_kernel");
   if (rc) return rc;
   tc_mlp3_kernel<NSPLIT><<<grid_b, NT, L.total, stream>>>(q);
@@ -1218,7 +1112,7 @@ int ebc_tc_prepare(ebc_sim *s, const ebc_weights *w, int mode_index, int nsplit)
   // ---- upload ---------------------------------------------------------------------------------------
   const size_t n_e = pe.slab_off.size(), n_m = pm.slab_off.size();
   if (n_e > (size_t)MAX_SLABS || n_m > (size_t)MAX_SLABS) return 1;
-  const size_t bytes_total = 2 * pe.bytes.size() + pm.bytes.size() + fl.size() * 4 + (n_e + n_m) * 8 + 2048;
+  const size_t bytes_total = pe.bytes.size() + pm.bytes.size() + fl.size() * 4 + (n_e + n_m) * 8 + 1024;
   uint8_t *d = nullptr;
   cudaError_t err = cudaMalloc(&d, bytes_total);
   if (err != cudaSuccess) return ebc_fail(s, EBC_ERR_NOMEM, "cudaMalloc tc weights: %s", cudaGetErrorString(err));
@@ -1230,7 +1124,6 @@ int ebc_tc_prepare(ebc_sim *s, const ebc_weights *w, int mode_index, int nsplit)
     return o;
   };
   const size_t o_pe = up(pe.bytes.data(), pe.bytes.size());
-  const size_t o_pe2 = up(pe.bytes2.data(), pe.bytes2.size());
   const size_t o_pm = up(pm.bytes.data(), pm.bytes.size());
   const size_t o_fl = up(fl.data(), fl.size() * 4);
   const size_t o_eo = up(pe.slab_off.data(), n_e * 4), o_eb = up(pe.slab_bytes.data(), n_e * 4);
@@ -1248,7 +1141,6 @@ int ebc_tc_prepare(ebc_sim *s, const ebc_weights *w, int mode_index, int nsplit)
   if (T.slab) cudaFree(T.slab);
   T.slab = d;
   T.entity = E;
-  T.entity_wpack_pair = d + o_pe2;
   T.mlp3 = M;
   T.ready = 1;
   return 0;
