@@ -62,7 +62,7 @@ template <int NSPLIT> struct Cfg {
 };
 
 struct Smem {   // offsets (bytes) into dynamic shared memory
-  uint32_t a, w, g, sc, xs, tab, bars, total;
+  uint32_t a, w, g, sc, xs, tab, bars, misc, total;
 };
 
 template <int NSPLIT>
@@ -72,10 +72,11 @@ __host__ __device__ inline Smem smem_layout() {
   s.a = off; off += Cfg<NSPLIT>::A_BYTES;
   s.w = off; off += Cfg<NSPLIT>::W_BYTES;
   s.g = off; off += Cfg<NSPLIT>::G_BYTES;              // G[state][k]: per-state mean of H1
-  s.sc = off; off += TILE_M * 4 * (NCG + 1);           // partial scores per column group, softmax weights
-  s.xs = off; off += MAX_STATES * 8 * 4;                // self-state part of each state's first row
+  s.sc = off; off += TILE_M * 4 * NCG;                 // partial scores per column group
+  s.xs = off; off += 2 * MAX_STATES * 8 * 4;            // self-state part of each state's first row, two tiles
   s.tab = off; off += MAX_SLABS * 8;                    // (offset, bytes) of every slab of the per-tile program
-  s.bars = off; off += 512;
+  s.bars = off; off += 512;                             // mbarriers + the scout's counter
+  s.misc = off; off += 16 + 2 * MAX_STATES * 4;         // TMEM base address, row counts of two tiles
   s.total = off;
   return s;
 }
@@ -498,8 +499,8 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
   uint8_t *A = smem + L.a;
   float *G = reinterpret_cast<float *>(smem + L.g);     // G[state][KMAX]
   float *SC = reinterpret_cast<float *>(smem + L.sc), *XS = reinterpret_cast<float *>(smem + L.xs);
-  __shared__ uint32_t tmem_slot;
-  __shared__ int cnt[MAX_STATES];
+  uint32_t &tmem_slot = *reinterpret_cast<uint32_t *>(smem + L.misc);     // no static shared memory: the dynamic
+  int (*cnt2)[MAX_STATES] = reinterpret_cast<int (*)[MAX_STATES]>(smem + L.misc + 16);   // region needs every byte
   const TcProgram &P = p.prog;
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
 
@@ -579,16 +580,29 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
         cnt_next = c;
       }
     };
+    // X -> A (K padded to 32): thread (row, cg) converts k-chunk cg of the values prefetched by load_x; the
+    // per-tile side data (row counts, self states) is double-buffered because the next tile's input is staged
+    // -- and its mlp1.0 runs -- while this tile's softmax and pooling are still in progress
+    float *XS2 = XS;
+    auto stage_x = [&](int buf, long long t) {
+      const int tstates = (int)min((long long)ts, p.n_states - t * ts);
+      if (tid < MAX_STATES) cnt2[buf][tid] = cnt_next;
+      store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, row, 8 * cg, xu);
+      if (cg == 0 && my_row && my_sid < tstates && my_rin == 0)
+        for (int k = 0; k < p.self_dim; ++k) XS2[buf * MAX_STATES * 8 + my_sid * 8 + k] = xu[k];
+      pipe.signal_a();
+    };
+    const bool early_x = n == 16;       // the generic tail's scratch aliases the operand images: no early staging
+    int cur = 0;
+    bool staged = false;
     if (blockIdx.x < n_tiles) load_x(blockIdx.x);
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long s0 = tile * ts;
       const int ns = (int)min((long long)ts, p.n_states - s0);
-      if (tid < MAX_STATES) cnt[tid] = cnt_next;
-      // ---- X -> A (K padded to 32): thread (row, cg) converts k-chunk cg (values prefetched below) -------
-      store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, row, 8 * cg, xu);
-      if (cg == 0 && my_row && my_sid < ns && my_rin == 0)
-        for (int k = 0; k < p.self_dim; ++k) XS[my_sid * 8 + k] = xu[k];
-      pipe.signal_a();
+      if (!staged) stage_x(cur, tile);
+      staged = false;
+      int *cnt = cnt2[cur];
+      float *XS = XS2 + cur * MAX_STATES * 8;
       // ---- mlp1.0 -> mlp1.2, K chunked by the wide halves; the second half overwrites the blocks of the first
       //      as mlp1.2's first K chunk releases them --------------------------------------------------------
       pipe.wait_acc();                                                             // #1
@@ -667,6 +681,13 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
         SC[cg * TILE_M + row] = epi_dot(tmem_row, cg, S.acc_col, S.np, P.bias[5], P.w6);
       }
       crew_sync();
+      if (early_x && tile + gridDim.x < n_tiles) {
+        // every read of the attention.2 accumulator is done and no MMA reads the operand images any more: hand
+        // the next tile's input over now, its mlp1.0 (columns [0, 304)) runs under this tile's softmax / pooling
+        // (which read the mlp2.2 accumulator at [400, 512) only)
+        stage_x(cur ^ 1, tile + gridDim.x);
+        staged = true;
+      }
       if (n == 16) {
         // a state = 16 aligned lanes of this warp: softmax and pooling stay in registers (shuffles), the
         // pooled feature goes straight to the joint row -- no scratch, no further block synchronisation
@@ -790,7 +811,8 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
         }
       }
       tc_fence_before();
-      crew_sync();   // PS (aliases A) / SC / XS / cnt are rewritten by the next tile
+      crew_sync();   // scratch (aliases A) / SC / XS / cnt are rewritten by the next tile
+      cur ^= 1;
     }
   }
   tc_fence_before();
@@ -812,7 +834,7 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
   const Smem L = smem_layout<NSPLIT>();
   uint8_t *A = smem + L.a;
   float *SC = reinterpret_cast<float *>(smem + L.sc);
-  __shared__ uint32_t tmem_slot;
+  uint32_t &tmem_slot = *reinterpret_cast<uint32_t *>(smem + L.misc);
   const TcProgram &P = p.prog;
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   Pipe<NSPLIT> pipe;
@@ -941,7 +963,8 @@ struct Packer {
 template <int NSPLIT>
 int launch_tc(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row_count, float *values, cudaStream_t stream) {
   const Smem L = smem_layout<NSPLIT>();
-  if ((int)L.total + 1024 > s->max_smem_optin) return ebc_fail(s, EBC_ERR_INVALID, "tensor-core value path needs %u B of shared memory", L.total);
+  if ((int)L.total > s->max_smem_optin)
+    return ebc_fail(s, EBC_ERR_INVALID, "tensor-core value path needs %u B of shared memory", L.total);
   const int n = s->cfg.max_humans + s->cfg.max_statics;
   TcEntityParams p;
   p.prog = s->tc[NSPLIT - 1].entity;
