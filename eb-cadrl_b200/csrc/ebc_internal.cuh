@@ -52,6 +52,7 @@ struct TcProgram {
   const float *w6;               // last (N = 1) layer weights, padded
   float b6;
   int with_global, h1d, h2d;
+  int early_x;                   // the next tile's input may be staged before this tile's pooling (TMEM ranges disjoint)
 };
 
 struct TcPrograms {

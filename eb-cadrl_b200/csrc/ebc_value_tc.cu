@@ -592,7 +592,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
         for (int k = 0; k < p.self_dim; ++k) XS2[buf * MAX_STATES * 8 + my_sid * 8 + k] = xu[k];
       pipe.signal_a();
     };
-    const bool early_x = n == 16;       // the generic tail's scratch aliases the operand images: no early staging
+    const bool early_x = P.early_x != 0;
     int cur = 0;
     bool staged = false;
     if (blockIdx.x < n_tiles) load_x(blockIdx.x);
@@ -748,7 +748,8 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
         const bool real = in_tile && r_in < cnt[min(my_sid, MAX_STATES - 1)];
         const int sid_up = __shfl_up_sync(0xffffffffu, sid, 1);
         const bool head = lane == 0 || sid_up != sid;              // first lane of this state's run in the warp
-        float *PSUM = reinterpret_cast<float *>(A);                // [4][MAX_STATES]
+        // (behind the four k-chunks of the first image that the next tile's input occupies)
+        float *PSUM = reinterpret_cast<float *>(A + 4 * A_CHUNK_BYTES);   // [4][MAX_STATES]
         float *PJ = PSUM + 4 * MAX_STATES;                         // [4][ts][np3]
         const TcStage &S = P.st[ST_L3];
         const float sc = ((SC[row] + SC[TILE_M + row]) + (SC[2 * TILE_M + row] + SC[3 * TILE_M + row])) + P.b6;
@@ -979,7 +980,8 @@ int launch_tc(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row
     if (ts > g_cap) ts = g_cap;
   }
   // generic row counts pool through a scratch that aliases the operand images: [4][32] + [4][ts][np3] floats
-  while (n != 16 && ts > 1 && 512u + 16u * (uint32_t)ts * (uint32_t)p.prog.st[ST_L3].np > Cfg<NSPLIT>::A_BYTES) --ts;
+  // (one image minus the four k-chunks that hold the next tile's input)
+  while (n != 16 && ts > 1 && 512u + 16u * (uint32_t)ts * (uint32_t)p.prog.st[ST_L3].np > Cfg<NSPLIT>::A_IMAGE - 4u * A_CHUNK_BYTES) --ts;
   p.ts = ts;
   p.joint = s->d_joint; p.jd = s->net.self_dim + s->net.l[3].out; p.self_dim = s->net.self_dim;
   p.trace = nullptr;
@@ -1090,6 +1092,7 @@ int ebc_tc_prepare(ebc_sim *s, const ebc_weights *w, int mode_index, int nsplit)
     c3 = c4 + (a0->out_dim + 7) / 8 * 8;
     if (c3 + np3 > TMEM_COLS) return 1;
   }
+  c3 = TMEM_COLS - np3;   // as high as it goes (>= the minimum above): the next tile's mlp1.0 starts under this tile's pooling
   if (np5 > c3) return 1;
   // slab order = issue order of the MMA warp: L2, L4, L4G, L3, L5
   simple_stage(pe, E.st[ST_L2], m20, h1, h1p, 0, 0);                               // mlp2.0
@@ -1158,6 +1161,8 @@ int ebc_tc_prepare(ebc_sim *s, const ebc_weights *w, int mode_index, int nsplit)
   E.bias[0] = dfl + be0; E.bias[1] = dfl + be1; E.bias[2] = dfl + be2; E.bias[3] = dfl + be3;
   E.bias[4] = dfl + be4; E.bias[5] = dfl + be5; E.w6 = dfl + we6; E.b6 = a4->bias[0];
   E.with_global = w->with_global_state ? 1 : 0; E.h1d = h1; E.h2d = m22->out_dim;
+  // the next tile's mlp1.0 may overwrite columns [0, wide) while this tile's pooling still reads the mlp2.2 accumulator
+  E.early_x = (E.st[ST_L0A].np + (E.n_wide > 1 ? E.st[ST_L0B].np : 0)) <= c3 ? 1 : 0;
   M.wpack = d + o_pm; M.n_slabs = (int)n_m;
   M.slab_off = reinterpret_cast<const uint32_t *>(d + o_mo); M.slab_bytes = reinterpret_cast<const uint32_t *>(d + o_mb);
   M.bias[0] = dfl + bm0; M.bias[1] = dfl + bm1; M.bias[2] = dfl + bm2; M.w6 = dfl + wm6; M.b6 = p6->bias[0];
