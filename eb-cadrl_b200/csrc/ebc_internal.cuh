@@ -31,6 +31,8 @@ struct TcStage {         // one GEMM stage: acc[:, acc_col : acc_col + np] (+)= 
   int accumulate;        // add to the existing accumulator (second K chunk)
   int n_lo;              // first output column of this stage within its layer (bias offset)
   int n_real;            // real output columns of this stage (the rest of np is padding)
+  int bias_k;            // >= 0: the bias rides in the GEMM -- column bias_k of this stage's A operand is a constant
+                         // one (written by whoever produces that operand) and row bias_k of the weights is the bias
 };
 
 struct TcSched {         // one entry of the MMA warp's per-tile schedule

@@ -293,12 +293,22 @@ struct Pipe {
 // activated fp32 values over the state's real rows with shuffles and store the mean to g_out[col * g_ld + state]
 // -- the global state of sarl.py:51-60, taken from registers instead of re-reading the 16-bit images.
 // g_out is [state][g_ld]: the 16 lanes of a state store 16 consecutive floats (conflict-free).
+struct EpiExtra {
+  int one_col = -1;          // output column forced to 1.0 (carries the next layer's bias through its GEMM), or -1
+  bool wait_first = false;   // see epi_to_a
+  int n = 1, row_cnt = 0;    // GSUM: rows per state, real rows of this row's state
+  float *g_out = nullptr;    // GSUM: G[state][g_ld]
+  int g_ld = 0, g_states = 0, g_sid = 0, g_rin = 0, g_seg = 0, g_part = 0;
+};
+
 template <int NSPLIT, bool GSUM>
 __device__ __forceinline__ void epi_to_a(Pipe<NSPLIT> &pipe, uint32_t tmem_row, int cg, int col0, int ncols, int n_real,
                                          const float *__restrict__ bias, uint8_t *a_base, int row, bool chase,
-                                         int n_free, int n = 1, int row_cnt = 0, float *g_out = nullptr, int g_ld = 0,
-                                         int g_states = 0, bool wait_first = false, int g_sid = 0, int g_rin = 0,
-                                         int g_seg = 0, int g_part = 0) {
+                                         int n_free, const EpiExtra &x = EpiExtra()) {
+  const int n = x.n, row_cnt = x.row_cnt, g_ld = x.g_ld, g_states = x.g_states, g_sid = x.g_sid, g_rin = x.g_rin;
+  const int g_seg = x.g_seg, g_part = x.g_part, one_col = x.one_col;
+  const bool wait_first = x.wait_first;
+  float *g_out = x.g_out;
   if (wait_first && 16 * cg < ncols) {
     pipe.wait_free(cg < n_free ? cg : 0);
     tc_fence_after();
@@ -306,20 +316,20 @@ __device__ __forceinline__ void epi_to_a(Pipe<NSPLIT> &pipe, uint32_t tmem_row, 
   for (int c = 16 * cg; c < ncols; c += 16 * NCG) {
     float v[16];
     tmem_ld16(tmem_row + col0 + c, v);
-    const float4 *b4 = reinterpret_cast<const float4 *>(bias + c);
+    if (bias) {              // the bias is added here unless it rode in the GEMM (TcStage::bias_k)
+      const float4 *b4 = reinterpret_cast<const float4 *>(bias + c);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 bb = __ldg(b4 + q);
-      const float x0 = v[4 * q] + bb.x, x1 = v[4 * q + 1] + bb.y, x2 = v[4 * q + 2] + bb.z, x3 = v[4 * q + 3] + bb.w;
-      v[4 * q] = x0 < 0.0f ? 0.0f : x0;           // ReLU that keeps NaN (a range overflow must stay visible)
-      v[4 * q + 1] = x1 < 0.0f ? 0.0f : x1;
-      v[4 * q + 2] = x2 < 0.0f ? 0.0f : x2;
-      v[4 * q + 3] = x3 < 0.0f ? 0.0f : x3;
+      for (int q = 0; q < 4; ++q) {
+        const float4 bb = __ldg(b4 + q);
+        v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
+      }
     }
-    if (c + 16 > n_real) {   // padding columns may alias another accumulator's columns: they carry exact zeros
 #pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = v[i] < 0.0f ? 0.0f : v[i];   // ReLU that keeps NaN (an overflow must stay visible)
+    if (c + 16 > n_real) {   // padding columns may alias another accumulator's columns: they carry exact zeros,
+#pragma unroll               // except the constant-one column that carries the next layer's bias through its GEMM
       for (int i = 0; i < 16; ++i)
-        if (c + i >= n_real) v[i] = 0.0f;
+        if (c + i >= n_real) v[i] = (c + i == one_col) ? 1.0f : 0.0f;
     }
     if ((c >> 4) < n_free) pipe.wait_free(c >> 4);
 #pragma unroll
@@ -436,11 +446,19 @@ __device__ __forceinline__ float epi_dot(uint32_t tmem_row, int cg, int col0, in
   for (int c = 16 * cg; c < ncols; c += 16 * NCG) {
     float v[16];
     tmem_ld16(tmem_row + col0 + c, v);
-    const float4 *b4 = reinterpret_cast<const float4 *>(bias + c), *w4 = reinterpret_cast<const float4 *>(w + c);
+    const float4 *w4 = reinterpret_cast<const float4 *>(w + c);
+    if (bias) {              // unless the bias rode in the GEMM
+      const float4 *b4 = reinterpret_cast<const float4 *>(bias + c);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 bb = __ldg(b4 + q);
+        v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
+      }
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float4 bb = __ldg(b4 + q), ww = __ldg(w4 + q);
-      const float x0 = v[4 * q] + bb.x, x1 = v[4 * q + 1] + bb.y, x2 = v[4 * q + 2] + bb.z, x3 = v[4 * q + 3] + bb.w;
+      const float4 ww = __ldg(w4 + q);
+      const float x0 = v[4 * q], x1 = v[4 * q + 1], x2 = v[4 * q + 2], x3 = v[4 * q + 3];
       acc = fmaf(x0 < 0.0f ? 0.0f : x0, ww.x, acc);
       acc = fmaf(x1 < 0.0f ? 0.0f : x1, ww.y, acc);
       acc = fmaf(x2 < 0.0f ? 0.0f : x2, ww.z, acc);
@@ -556,6 +574,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
       my_row = my_rin < n;
     }
     my_row = my_row && my_sid < ts;
+    const int one0 = P.st[ST_L0A].bias_k;             // constant-one input column: mlp1.0's bias rides in its GEMM
     float xu[8];
     int cnt_next = 0;                                 // threads 0-31: row count of state tid of the next tile
     auto load_x = [&](long long t) {
@@ -565,7 +584,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int k = 8 * cg + j;
-        xu[j] = (my_row && my_sid < tstates && k < D) ? __ldg(src + k) : 0.0f;
+        xu[j] = k == one0 ? 1.0f : ((my_row && my_sid < tstates && k < D) ? __ldg(src + k) : 0.0f);
       }
       if (tid < MAX_STATES) {
         int c = 0;
@@ -609,7 +628,10 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
       for (int h = 0; h < P.n_wide; ++h) {
         const TcStage &W = P.st[ST_L0A + h];
         const int n_free = h ? P.st[ST_L1A + h - 1].ksteps : 0;
-        epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, W.acc_col, W.np, W.n_real, P.bias[0] + W.n_lo, A, row, true, n_free);
+        EpiExtra ex;
+        ex.one_col = P.st[ST_L1A + h].bias_k;     // this half is K chunk h of mlp1.2
+        epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, W.acc_col, W.np, W.n_real, W.bias_k >= 0 ? nullptr : P.bias[0] + W.n_lo, A,
+                                row, true, n_free, ex);
         if (h) pipe.f_phase ^= low_bits(n_free);
         pipe.stamp();
       }
@@ -618,12 +640,16 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
       const int st_of_row = min(my_sid, ts - 1);
       {
         const TcStage &S = P.st[ST_L1A];
+        const bool b_in = S.bias_k >= 0 || (P.n_wide > 1 && P.st[ST_L1B].bias_k >= 0);   // bias rode in one K chunk
+        EpiExtra ex;
+        ex.one_col = P.st[ST_L2].bias_k;          // H1 is the A operand of mlp2.0 and attention.0
         if (P.with_global && n <= 32) {
           crew_sync();   // cnt[] of this tile is visible
-          epi_to_a<NSPLIT, true>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, P.bias[1], A, row, true, 0, n,
-                                 cnt[st_of_row], G, g_ld, ts, false, my_sid, my_rin, my_row ? my_sid : -1 - (row >> 5), 0);
+          ex.n = n; ex.row_cnt = cnt[st_of_row]; ex.g_out = G; ex.g_ld = g_ld; ex.g_states = ts;
+          ex.g_sid = my_sid; ex.g_rin = my_rin; ex.g_seg = my_row ? my_sid : -1 - (row >> 5);
+          epi_to_a<NSPLIT, true>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, b_in ? nullptr : P.bias[1], A, row, true, 0, ex);
         } else {
-          epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, P.bias[1], A, row, true, 0);
+          epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, b_in ? nullptr : P.bias[1], A, row, true, 0, ex);
         }
       }
       pipe.stamp();
@@ -658,8 +684,11 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
       // ---- T2 = relu(mlp2.0) -> A; mlp2.2 chases it --------------------------------------------------------
       {
         const TcStage &S = P.st[ST_L2];
-        epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, P.bias[2], A, row, true, h1b, 1, 0, nullptr,
-                                0, 0, true);
+        EpiExtra ex;
+        ex.one_col = P.st[ST_L3].bias_k;
+        ex.wait_first = true;
+        epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, S.bias_k >= 0 ? nullptr : P.bias[2], A, row, true,
+                                h1b, ex);
         pipe.f_phase ^= low_bits(h1b);                  // attention.0's last K chunk released its blocks
       }
       pipe.stamp();
@@ -669,7 +698,10 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
       {
         const TcStage &S = P.st[ST_L4];
         const int n_free = P.st[ST_L3].ksteps;
-        epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, P.bias[4], A, row, true, n_free);
+        EpiExtra ex;
+        ex.one_col = P.st[ST_L5].bias_k;
+        epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, S.bias_k >= 0 ? nullptr : P.bias[4], A, row, true,
+                                n_free, ex);
         pipe.f_phase ^= low_bits(n_free);
       }
       pipe.stamp();
@@ -678,7 +710,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
       // ---- attention.4 score, masked softmax, pooling (sarl.py:64-78) --------------------------------------
       {
         const TcStage &S = P.st[ST_L5];
-        SC[cg * TILE_M + row] = epi_dot(tmem_row, cg, S.acc_col, S.np, P.bias[5], P.w6);
+        SC[cg * TILE_M + row] = epi_dot(tmem_row, cg, S.acc_col, S.np, S.bias_k >= 0 ? nullptr : P.bias[5], P.w6);
       }
       crew_sync();
       if (early_x && tile + gridDim.x < n_tiles) {
@@ -704,10 +736,12 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
         for (int c = 16 * cg; c < S.np; c += 16 * NCG) {
           float v[16];
           tmem_ld16(tmem_row + S.acc_col + c, v);
+          if (S.bias_k < 0) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 bb = __ldg(reinterpret_cast<const float4 *>(P.bias[3] + c) + q);
-            v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
+            for (int q = 0; q < 4; ++q) {
+              const float4 bb = __ldg(reinterpret_cast<const float4 *>(P.bias[3] + c) + q);
+              v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
+            }
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = (real && c + i < h2d) ? v[i] * wrow : 0.0f;
@@ -774,10 +808,12 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
         for (int c = 16 * cg; c < S.np; c += 16 * NCG) {
           float v[16];
           tmem_ld16(tmem_row + S.acc_col + c, v);
+          if (S.bias_k < 0) {
 #pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            const float4 bb = __ldg(reinterpret_cast<const float4 *>(P.bias[3] + c) + qd);
-            v[4 * qd] += bb.x; v[4 * qd + 1] += bb.y; v[4 * qd + 2] += bb.z; v[4 * qd + 3] += bb.w;
+            for (int qd = 0; qd < 4; ++qd) {
+              const float4 bb = __ldg(reinterpret_cast<const float4 *>(P.bias[3] + c) + qd);
+              v[4 * qd] += bb.x; v[4 * qd + 1] += bb.y; v[4 * qd + 2] += bb.z; v[4 * qd + 3] += bb.w;
+            }
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = (real && c + i < h2d) ? v[i] * wrow : 0.0f;
@@ -859,7 +895,7 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
     const int row = ((warp & 3) << 5) | (tid & 31);
     const int cg = warp >> 2;
     const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    const int jd = p.jd, kp = P.st[ST_L0A].ksteps * 16;
+    const int jd = p.jd, kp = P.st[ST_L0A].ksteps * 16, one0 = P.st[ST_L0A].bias_k;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long s0 = tile * TILE_M;
       const bool live = s0 + row < p.n_states;
@@ -867,7 +903,8 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
       for (int k0 = 8 * cg; k0 < kp; k0 += 8 * NCG) {
         float u[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) u[j] = (live && k0 + j < jd) ? __ldg(p.joint + (size_t)(s0 + row) * jd + k0 + j) : 0.0f;
+        for (int j = 0; j < 8; ++j)
+          u[j] = k0 + j == one0 ? 1.0f : ((live && k0 + j < jd) ? __ldg(p.joint + (size_t)(s0 + row) * jd + k0 + j) : 0.0f);
         store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, row, k0, u);
       }
       pipe.signal_a();
@@ -875,18 +912,24 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
       for (int h = 0; h < P.n_wide; ++h) {
         const TcStage &W = P.st[ST_L0A + h];
         const int n_free = h ? P.st[ST_L1A + h - 1].ksteps : 0;
-        epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, W.acc_col, W.np, W.n_real, P.bias[0] + W.n_lo, A, row, true, n_free);
+        EpiExtra ex;
+        ex.one_col = P.st[ST_L1A + h].bias_k;
+        epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, W.acc_col, W.np, W.n_real, W.bias_k >= 0 ? nullptr : P.bias[0] + W.n_lo, A,
+                                row, true, n_free, ex);
         if (h) pipe.f_phase ^= low_bits(n_free);
       }
       pipe.wait_acc();
       {
         const TcStage &S = P.st[ST_L1A];
-        epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, P.bias[1], A, row, true, 0);
+        const bool b_in = S.bias_k >= 0 || (P.n_wide > 1 && P.st[ST_L1B].bias_k >= 0);
+        EpiExtra ex;
+        ex.one_col = P.st[ST_L2].bias_k;
+        epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, b_in ? nullptr : P.bias[1], A, row, true, 0, ex);
       }
       pipe.wait_acc();
       {
         const TcStage &S = P.st[ST_L2];
-        SC[cg * TILE_M + row] = epi_dot(tmem_row, cg, S.acc_col, S.np, P.bias[2], P.w6);
+        SC[cg * TILE_M + row] = epi_dot(tmem_row, cg, S.acc_col, S.np, S.bias_k >= 0 ? nullptr : P.bias[2], P.w6);
       }
       crew_sync();
       if (tid < TILE_M && s0 + tid < p.n_states)
@@ -938,7 +981,9 @@ struct Packer {
     return f;
   }
   // GEMM stage over W[n_lo:n_lo+np (zero past n_hi)][k_lo:k_lo+16*ksteps (zero past k_hi)], W is [out][ld]
-  void add_stage(const float *W, int ld, int n_lo, int n_hi, int np, int k_lo, int k_hi, int ksteps, int k_col_off) {
+  // bias / bias_k: row bias_k (stage-local k) of the weights carries the bias (its A column is a constant one)
+  void add_stage(const float *W, int ld, int n_lo, int n_hi, int np, int k_lo, int k_hi, int ksteps, int k_col_off,
+                 const float *bias = nullptr, int bias_k = -1) {
     for (int ks = 0; ks < ksteps; ++ks) {
       const uint32_t off = (uint32_t)bytes.size();
       const uint32_t sz = (uint32_t)nsplit * (uint32_t)np * 32u;
@@ -948,6 +993,7 @@ struct Packer {
           for (int j = 0; j < 8; ++j) {
             const int n = n_lo + nn, k = k_lo + ks * 16 + c * 8 + j;
             float v = (n < n_hi && k < k_hi) ? W[(size_t)n * ld + k_col_off + k] : 0.0f;
+            if (bias && ks * 16 + c * 8 + j == bias_k) v = n < n_hi ? bias[n] : 0.0f;
             for (int s = 0; s < nsplit; ++s) {
               const uint16_t h = round16(v, nsplit == 2);
               v -= back16(h, nsplit == 2);
@@ -1050,7 +1096,8 @@ int ebc_tc_prepare(ebc_sim *s, const ebc_weights *w, int mode_index, int nsplit)
       TcStage &S = P.st[ST_L0A + h];
       S.np = np; S.ksteps = in_pad / 16; S.acc_col = lo; S.accumulate = 0; S.n_lo = lo;
       S.n_real = wide->out_dim - lo < np ? wide->out_dim - lo : np;
-      pk.add_stage(wide->weight, wide->in_dim, lo, wide->out_dim, np, 0, wide->in_dim, S.ksteps, 0);
+      S.bias_k = wide->in_dim < in_pad ? wide->in_dim : -1;        // a spare K column carries the bias
+      pk.add_stage(wide->weight, wide->in_dim, lo, wide->out_dim, np, 0, wide->in_dim, S.ksteps, 0, wide->bias, S.bias_k);
       lo += np;
     }
     lo = 0;
@@ -1058,17 +1105,22 @@ int ebc_tc_prepare(ebc_sim *s, const ebc_weights *w, int mode_index, int nsplit)
       const int kp = h ? np1 : np0;
       TcStage &S = P.st[ST_L1A + h];
       S.np = midp; S.ksteps = kp / 16; S.acc_col = col_mid; S.accumulate = h; S.n_lo = 0; S.n_real = mid->out_dim;
-      pk.add_stage(mid->weight, mid->in_dim, 0, mid->out_dim, midp, lo, mid->in_dim, S.ksteps, 0);
+      // the first padding column of the wide layer (global K index wide->out_dim), in whichever K chunk holds it
+      const int bk = mid->in_dim < np0 + np1 ? mid->in_dim - lo : -1;
+      S.bias_k = bk >= 0 && bk < kp ? bk : -1;
+      pk.add_stage(mid->weight, mid->in_dim, 0, mid->out_dim, midp, lo, mid->in_dim, S.ksteps, 0, mid->bias, S.bias_k);
       lo += kp;
     }
     b_wide = push_f(wide->bias, wide->out_dim, np0 + np1);
     b_mid = push_f(mid->bias, mid->out_dim, midp);
     return 0;
   };
-  auto simple_stage = [&](Packer &pk, TcStage &S, const ebc_linear *l, int in_real, int in_pad, int acc_col, int k_col_off) {
+  auto simple_stage = [&](Packer &pk, TcStage &S, const ebc_linear *l, int in_real, int in_pad, int acc_col, int k_col_off,
+                          bool with_bias = true) {
     S.np = pad16(l->out_dim); S.ksteps = in_pad / 16; S.acc_col = acc_col; S.accumulate = 0; S.n_lo = 0;
     S.n_real = l->out_dim;
-    pk.add_stage(l->weight, l->in_dim, 0, l->out_dim, S.np, 0, in_real, S.ksteps, k_col_off);
+    S.bias_k = (with_bias && in_real < in_pad) ? in_real : -1;
+    pk.add_stage(l->weight, l->in_dim, 0, l->out_dim, S.np, 0, in_real, S.ksteps, k_col_off, l->bias, S.bias_k);
   };
 
   Packer pe; pe.nsplit = nsplit;
@@ -1098,7 +1150,7 @@ int ebc_tc_prepare(ebc_sim *s, const ebc_weights *w, int mode_index, int nsplit)
   simple_stage(pe, E.st[ST_L2], m20, h1, h1p, 0, 0);                               // mlp2.0
   simple_stage(pe, E.st[ST_L4], a0, h1, h1p, c4, 0);                               // attention.0, local half
   if (w->with_global_state) {                                                      // attention.0, global half
-    simple_stage(pe, E.st[ST_L4G], a0, h1, h1p, c4, h1);
+    simple_stage(pe, E.st[ST_L4G], a0, h1, h1p, c4, h1, false);   // the local half already carries the bias
     E.st[ST_L4G].accumulate = 1;
   }
   simple_stage(pe, E.st[ST_L3], m22, m20->out_dim, pad16(m20->out_dim), c3, 0);    // mlp2.2
