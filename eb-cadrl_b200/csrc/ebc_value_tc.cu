@@ -86,6 +86,12 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ uint32_t low_bits(int n) { return (1u << n) - 1u; }
+// max(x, 0) in one instruction that propagates NaN (fmaxf would return 0)
+__device__ __forceinline__ float relu_nan(float x) {
+  float y;
+  asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // Ring of weight slabs + the MMA warp's cursor; barriers shared with the crew.
 template <int NSPLIT>
@@ -325,7 +331,7 @@ __device__ __forceinline__ void epi_to_a(Pipe<NSPLIT> &pipe, uint32_t tmem_row, 
       }
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = v[i] < 0.0f ? 0.0f : v[i];   // ReLU that keeps NaN (an overflow must stay visible)
+    for (int i = 0; i < 16; ++i) v[i] = relu_nan(v[i]);   // ReLU that keeps NaN (an overflow must stay visible)
     if (c + 16 > n_real) {   // padding columns may alias another accumulator's columns: they carry exact zeros,
 #pragma unroll               // except the constant-one column that carries the next layer's bias through its GEMM
       for (int i = 0; i < 16; ++i)
@@ -459,10 +465,10 @@ __device__ __forceinline__ float epi_dot(uint32_t tmem_row, int cg, int col0, in
     for (int q = 0; q < 4; ++q) {
       const float4 ww = __ldg(w4 + q);
       const float x0 = v[4 * q], x1 = v[4 * q + 1], x2 = v[4 * q + 2], x3 = v[4 * q + 3];
-      acc = fmaf(x0 < 0.0f ? 0.0f : x0, ww.x, acc);
-      acc = fmaf(x1 < 0.0f ? 0.0f : x1, ww.y, acc);
-      acc = fmaf(x2 < 0.0f ? 0.0f : x2, ww.z, acc);
-      acc = fmaf(x3 < 0.0f ? 0.0f : x3, ww.w, acc);
+      acc = fmaf(relu_nan(x0), ww.x, acc);
+      acc = fmaf(relu_nan(x1), ww.y, acc);
+      acc = fmaf(relu_nan(x2), ww.z, acc);
+      acc = fmaf(relu_nan(x3), ww.w, acc);
     }
   }
   return acc;

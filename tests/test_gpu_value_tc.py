@@ -128,3 +128,30 @@ def test_tc_random_networks(n, with_global):
         err = (out - ref).abs().max().item()
         print(n, with_global, mode, err)
         assert err < 5e-5 * scale, (mode, err)
+
+
+def test_nan_and_overflow_stay_visible():
+    """A NaN (or, in the fp16-split mode, an activation beyond the fp16 range) must come out as NaN for that state --
+    the ReLU keeps NaN, nothing clamps -- so that K5's nan_flag / the reference's ValueError can fire; the other
+    states of the same tile are unaffected."""
+    w = ob.load_weights("weights_ebcadrl.npz")
+    cfg = SimConfig()
+    cfg.with_agent_type = True
+    sim = BatchedSim(cfg, 1, 10, 6, 0, 81, device="cuda:0")
+    sim.set_weights(w)
+    x, cnt = make_inputs(300, 16, cfg.D, seed=5, ragged=False)
+    clean = {}
+    for mode in ("fp32", "tc_fp16x2", "tc_fp32"):
+        sim.set_value_mode(mode)
+        clean[mode] = sim.value(x, cnt).clone()
+    x[7, 3, 2] = float("nan")
+    x[130, 0, 1] = 1e30          # overflows every 16-bit part and the fp32 products
+    for mode in ("fp32", "tc_fp16x2", "tc_fp32"):
+        sim.set_value_mode(mode)
+        out = sim.value(x, cnt)
+        torch.cuda.synchronize()
+        assert torch.isnan(out[7]), mode
+        assert not torch.isfinite(out[130]) or out[130].abs() > 1e6, (mode, out[130])
+        ok = torch.ones(300, dtype=torch.bool, device="cuda:0")
+        ok[7] = ok[130] = False
+        assert torch.equal(out[ok], clean[mode][ok]), mode
