@@ -161,7 +161,9 @@ int ebc_value(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row
     if (n_states > s->joint_cap) {
       if (s->d_joint) cudaFree(s->d_joint);
       s->d_joint = nullptr;
-      cudaError_t err = cudaMalloc(&s->d_joint, (size_t)n_states * jd * sizeof(float));
+      // (the tensor-core kernels keep it in 128-state tiles of 8-column chunks: both dimensions rounded up)
+      const size_t cap_floats = (size_t)((n_states + 127) / 128 * 128) * (size_t)((jd + 7) / 8 * 8);
+      cudaError_t err = cudaMalloc(&s->d_joint, cap_floats * sizeof(float));
       if (err != cudaSuccess) return ebc_fail(s, EBC_ERR_NOMEM, "cudaMalloc joint scratch: %s", cudaGetErrorString(err));
       s->joint_cap = n_states;
     }

@@ -52,6 +52,8 @@ struct TcProgram {
   int n_slabs;                   // slabs consumed per tile
   const float *bias[6];          // padded fp32 biases (device)
   const float *w6;               // last (N = 1) layer weights, padded
+  float w6c[208];                // the same in the kernel's parameter block: warp-uniform constant-bank reads in the
+                                 // score / value epilogue instead of dependent global loads
   float b6;
   int with_global, h1d, h2d;
   int early_x;                   // the next tile's input may be staged before this tile's pooling (TMEM ranges disjoint)

@@ -81,6 +81,15 @@ __host__ __device__ inline Smem smem_layout() {
   return s;
 }
 
+// The pooled per-state features ("joint", the input of mlp3) travel between the two kernels in the layout the mlp3
+// kernel stages them in: [tile of 128 states][k-chunk of 8 columns][state in tile][8 floats], so that its thread
+// (row, chunk) reads 32 contiguous bytes and a warp 1 KB -- a row-major [state][jd] scratch costs one 32-byte sector
+// per lane and load instruction there, which starves the shared-memory pipe the MMAs read their operands through.
+__host__ __device__ __forceinline__ size_t joint_index(long long state, int k, int n_chunks) {
+  return ((((size_t)(state >> 7)) * n_chunks + (size_t)(k >> 3)) * TILE_M + (size_t)(state & 127)) * 8 + (size_t)(k & 7);
+}
+static_assert(TILE_M == 128, "joint_index assumes 128 states per mlp3 tile");
+
 __device__ __forceinline__ void crew_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCREW) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -452,7 +461,6 @@ __device__ __forceinline__ float epi_dot(uint32_t tmem_row, int cg, int col0, in
   for (int c = 16 * cg; c < ncols; c += 16 * NCG) {
     float v[16];
     tmem_ld16(tmem_row + col0 + c, v);
-    const float4 *w4 = reinterpret_cast<const float4 *>(w + c);
     if (bias) {              // unless the bias rode in the GEMM
       const float4 *b4 = reinterpret_cast<const float4 *>(bias + c);
 #pragma unroll
@@ -461,15 +469,9 @@ __device__ __forceinline__ float epi_dot(uint32_t tmem_row, int cg, int col0, in
         v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
       }
     }
+    // w lives in the kernel's parameter block and c is warp-uniform: constant-bank operands, no load latency
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 ww = __ldg(w4 + q);
-      const float x0 = v[4 * q], x1 = v[4 * q + 1], x2 = v[4 * q + 2], x3 = v[4 * q + 3];
-      acc = fmaf(relu_nan(x0), ww.x, acc);
-      acc = fmaf(relu_nan(x1), ww.y, acc);
-      acc = fmaf(relu_nan(x2), ww.z, acc);
-      acc = fmaf(relu_nan(x3), ww.w, acc);
-    }
+    for (int i = 0; i < 16; ++i) acc = fmaf(relu_nan(v[i]), w[c + i], acc);
   }
   return acc;
 }
@@ -512,6 +514,7 @@ struct TcEntityParams {
   int n, ts, D;
   float *joint;
   int jd;          // self_dim + H2
+  int jch;         // k-chunks of a joint row: (jd + 7) / 8
   int self_dim;
   long long *trace;
 };
@@ -613,8 +616,11 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
       const int tstates = (int)min((long long)ts, p.n_states - t * ts);
       if (tid < MAX_STATES) cnt2[buf][tid] = cnt_next;
       store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, row, 8 * cg, xu);
-      if (cg == 0 && my_row && my_sid < tstates && my_rin == 0)
-        for (int k = 0; k < p.self_dim; ++k) XS2[buf * MAX_STATES * 8 + my_sid * 8 + k] = xu[k];
+      if (cg == 0 && my_row && my_sid < tstates && my_rin == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)        // (constant indices: xu stays in registers)
+          if (k < p.self_dim) XS2[buf * MAX_STATES * 8 + my_sid * 8 + k] = xu[k];
+      }
       pipe.signal_a();
     };
     const bool early_x = P.early_x != 0;
@@ -624,6 +630,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long s0 = tile * ts;
       const int ns = (int)min((long long)ts, p.n_states - s0);
+      const bool was_early = staged;     // staged during the previous tile's tail: a crew_sync has passed since
       if (!staged) stage_x(cur, tile);
       staged = false;
       int *cnt = cnt2[cur];
@@ -650,7 +657,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
         EpiExtra ex;
         ex.one_col = P.st[ST_L2].bias_k;          // H1 is the A operand of mlp2.0 and attention.0
         if (P.with_global && n <= 32) {
-          crew_sync();   // cnt[] of this tile is visible
+          if (!was_early) crew_sync();   // cnt[] of this tile is visible
           ex.n = n; ex.row_cnt = cnt[st_of_row]; ex.g_out = G; ex.g_ld = g_ld; ex.g_states = ts;
           ex.g_sid = my_sid; ex.g_rin = my_rin; ex.g_seg = my_row ? my_sid : -1 - (row >> 5);
           epi_to_a<NSPLIT, true>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, b_in ? nullptr : P.bias[1], A, row, true, 0, ex);
@@ -716,9 +723,11 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
       // ---- attention.4 score, masked softmax, pooling (sarl.py:64-78) --------------------------------------
       {
         const TcStage &S = P.st[ST_L5];
-        SC[cg * TILE_M + row] = epi_dot(tmem_row, cg, S.acc_col, S.np, S.bias_k >= 0 ? nullptr : P.bias[5], P.w6);
+        SC[cg * TILE_M + row] = epi_dot(tmem_row, cg, S.acc_col, S.np, S.bias_k >= 0 ? nullptr : P.bias[5], P.w6c);
       }
+      pipe.stamp();
       crew_sync();
+      pipe.stamp();
       if (early_x && tile + gridDim.x < n_tiles) {
         // every read of the attention.2 accumulator is done and no MMA reads the operand images any more: hand
         // the next tile's input over now, its mlp1.0 (columns [0, 304)) runs under this tile's softmax / pooling
@@ -770,11 +779,11 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
           const float send = (lane & 1) ? w2[0] : w2[1], keep = (lane & 1) ? w2[1] : w2[0];
           const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 1);
           const int col = c + (lane & 15);
-          if (st_row < ns && col < h2d) p.joint[(size_t)(s0 + st_row) * p.jd + p.self_dim + col] = tot;
+          if (st_row < ns && col < h2d) p.joint[joint_index(s0 + st_row, p.self_dim + col, p.jch)] = tot;
         }
         if (tid < ns * p.self_dim) {
           const int s = tid / p.self_dim, k = tid % p.self_dim;
-          p.joint[(size_t)(s0 + s) * p.jd + k] = XS[s * 8 + k];
+          p.joint[joint_index(s0 + s, k, p.jch)] = XS[s * 8 + k];
         }
       } else {
         // any row count: a state's rows are a contiguous run of rows, i.e. at most one run of lanes per warp.
@@ -850,11 +859,13 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
             const int a_lo = n <= 32 ? s / spw : s * wps, a_hi = n <= 32 ? a_lo : a_lo + wps - 1;
             for (int qq = a_lo; qq <= a_hi; ++qq) v += PJ[((size_t)qq * ts + s) * S.np + col];
           }
-          p.joint[(size_t)(s0 + s) * p.jd + k] = v;
+          p.joint[joint_index(s0 + s, k, p.jch)] = v;
         }
       }
+      pipe.stamp();
       tc_fence_before();
       crew_sync();   // scratch (aliases A) / SC / XS / cnt are rewritten by the next tile
+      pipe.stamp();
       cur ^= 1;
     }
   }
@@ -868,7 +879,8 @@ struct TcMlp3Params {
   const float *joint;
   float *values;
   long long n_states;
-  int jd;
+  int jd, jch;
+  long long *trace;          // EBC_TC_TRACE=2: clock64 stamps of CTA 0's crew thread 0
 };
 
 template <int NSPLIT>
@@ -883,6 +895,7 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
   Pipe<NSPLIT> pipe;
   const long long n_tiles = (p.n_states + TILE_M - 1) / TILE_M;
   pipe_init<NSPLIT>(pipe, smem, L, P, (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  pipe.trace = p.trace;
   if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -902,18 +915,47 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
     const int cg = warp >> 2;
     const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const int jd = p.jd, kp = P.st[ST_L0A].ksteps * 16, one0 = P.st[ST_L0A].bias_k;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const long long s0 = tile * TILE_M;
-      const bool live = s0 + row < p.n_states;
-      // joint row -> A (K padded to a multiple of 16), k-chunks interleaved over the column groups
-      for (int k0 = 8 * cg; k0 < kp; k0 += 8 * NCG) {
-        float u[8];
+    // joint row -> A (K padded to a multiple of 16), k-chunks interleaved over the column groups.  The first XC
+    // chunks of a thread are fetched one tile ahead (their L2 / HBM latency hides behind the previous tile's last
+    // layer) and handed over as soon as that tile's output accumulator has been read.
+    constexpr int XC = 4;
+    float xu[XC][8];
+    const int jch = p.jch;
+    auto load_chunk = [&](long long t, int c, float (&u)[8]) {     // k-chunk c of this thread's row of tile t
+      const bool live = t * TILE_M + row < p.n_states && c < jch;
+      float4 lo = make_float4(0.0f, 0.0f, 0.0f, 0.0f), hi = lo;
+      if (live) {
+        const float4 *src = reinterpret_cast<const float4 *>(p.joint + joint_index(t * TILE_M + row, 8 * c, jch));
+        lo = __ldg(src); hi = __ldg(src + 1);
+      }
+      const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          u[j] = k0 + j == one0 ? 1.0f : ((live && k0 + j < jd) ? __ldg(p.joint + (size_t)(s0 + row) * jd + k0 + j) : 0.0f);
-        store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, row, k0, u);
+      for (int j = 0; j < 8; ++j) u[j] = 8 * c + j == one0 ? 1.0f : ((live && 8 * c + j < jd) ? v[j] : 0.0f);
+    };
+    auto load_x = [&](long long t) {
+#pragma unroll
+      for (int i = 0; i < XC; ++i) load_chunk(t, cg + NCG * i, xu[i]);
+    };
+    auto stage_x = [&](long long t) {
+#pragma unroll
+      for (int i = 0; i < XC; ++i) {
+        const int k0 = 8 * (cg + NCG * i);
+        if (k0 < kp) store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, row, k0, xu[i]);
+      }
+      for (int c = cg + NCG * XC; 8 * c < kp; c += NCG) {      // joint rows wider than 128 columns
+        float u[8];
+        load_chunk(t, c, u);
+        store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, row, 8 * c, u);
       }
       pipe.signal_a();
+    };
+    bool staged = false;
+    if (blockIdx.x < n_tiles) load_x(blockIdx.x);
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long s0 = tile * TILE_M;
+      const bool more = tile + gridDim.x < n_tiles;
+      if (!staged) stage_x(tile);
+      staged = false;
       pipe.wait_acc();
       for (int h = 0; h < P.n_wide; ++h) {
         const TcStage &W = P.st[ST_L0A + h];
@@ -932,12 +974,19 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
         ex.one_col = P.st[ST_L2].bias_k;
         epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, b_in ? nullptr : P.bias[1], A, row, true, 0, ex);
       }
+      pipe.stamp();
+      if (more) load_x(tile + gridDim.x);
       pipe.wait_acc();
       {
         const TcStage &S = P.st[ST_L2];
-        SC[cg * TILE_M + row] = epi_dot(tmem_row, cg, S.acc_col, S.np, S.bias_k >= 0 ? nullptr : P.bias[2], P.w6);
+        SC[cg * TILE_M + row] = epi_dot(tmem_row, cg, S.acc_col, S.np, S.bias_k >= 0 ? nullptr : P.bias[2], P.w6c);
       }
+      pipe.stamp();
       crew_sync();
+      if (more) {    // every MMA of this tile has completed and its output accumulator has been read
+        stage_x(tile + gridDim.x);
+        staged = true;
+      }
       if (tid < TILE_M && s0 + tid < p.n_states)
         p.values[s0 + tid] = ((SC[tid] + SC[TILE_M + tid]) + (SC[2 * TILE_M + tid] + SC[3 * TILE_M + tid])) + P.b6;
       tc_fence_before();
@@ -1036,15 +1085,17 @@ int launch_tc(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row
   while (n != 16 && ts > 1 && 512u + 16u * (uint32_t)ts * (uint32_t)p.prog.st[ST_L3].np > Cfg<NSPLIT>::A_IMAGE - 4u * A_CHUNK_BYTES) --ts;
   p.ts = ts;
   p.joint = s->d_joint; p.jd = s->net.self_dim + s->net.l[3].out; p.self_dim = s->net.self_dim;
+  p.jch = (p.jd + 7) / 8;
   p.trace = nullptr;
-  if (getenv("EBC_TC_TRACE")) {
+  TcMlp3Params q;
+  q.trace = nullptr;
+  if (const char *tr = getenv("EBC_TC_TRACE")) {      // 1: the entity kernel, 2: the mlp3 kernel
     if (!s->d_trace) { cudaMalloc(&s->d_trace, 4096 * sizeof(long long)); }
     cudaMemsetAsync(s->d_trace, 0, 4096 * sizeof(long long), stream);
-    p.trace = s->d_trace;
+    if (tr[0] == '2') q.trace = s->d_trace; else p.trace = s->d_trace;
   }
-  TcMlp3Params q;
   q.prog = s->tc[NSPLIT - 1].mlp3;
-  q.joint = s->d_joint; q.values = values; q.n_states = n_states; q.jd = p.jd;
+  q.joint = s->d_joint; q.values = values; q.n_states = n_states; q.jd = p.jd; q.jch = p.jch;
   cudaFuncSetAttribute(tc_entity_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
   cudaFuncSetAttribute(tc_mlp3_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
   const long long tiles_a = (n_states + ts - 1) / ts, tiles_b = (n_states + TILE_M - 1) / TILE_M;
@@ -1218,12 +1269,15 @@ int ebc_tc_prepare(ebc_sim *s, const ebc_weights *w, int mode_index, int nsplit)
   E.slab_off = reinterpret_cast<const uint32_t *>(d + o_eo); E.slab_bytes = reinterpret_cast<const uint32_t *>(d + o_eb);
   E.bias[0] = dfl + be0; E.bias[1] = dfl + be1; E.bias[2] = dfl + be2; E.bias[3] = dfl + be3;
   E.bias[4] = dfl + be4; E.bias[5] = dfl + be5; E.w6 = dfl + we6; E.b6 = a4->bias[0];
+  static_assert(sizeof(E.w6c) / sizeof(float) >= KMAX, "w6c holds the widest last-layer input");
+  for (int i = 0; i < KMAX; ++i) E.w6c[i] = i < a4->in_dim ? a4->weight[i] : 0.0f;
   E.with_global = w->with_global_state ? 1 : 0; E.h1d = h1; E.h2d = m22->out_dim;
   // the next tile's mlp1.0 may overwrite columns [0, wide) while this tile's pooling still reads the mlp2.2 accumulator
   E.early_x = (E.st[ST_L0A].np + (E.n_wide > 1 ? E.st[ST_L0B].np : 0)) <= c3 ? 1 : 0;
   M.wpack = d + o_pm; M.n_slabs = (int)n_m;
   M.slab_off = reinterpret_cast<const uint32_t *>(d + o_mo); M.slab_bytes = reinterpret_cast<const uint32_t *>(d + o_mb);
   M.bias[0] = dfl + bm0; M.bias[1] = dfl + bm1; M.bias[2] = dfl + bm2; M.w6 = dfl + wm6; M.b6 = p6->bias[0];
+  for (int i = 0; i < KMAX; ++i) M.w6c[i] = i < p6->in_dim ? p6->weight[i] : 0.0f;
   if (T.slab) cudaFree(T.slab);
   T.slab = d;
   T.entity = E;

@@ -20,12 +20,16 @@ torch.cuda.synchronize()
 buf=(ctypes.c_longlong*4096)()
 sim.be.lib.ebc_debug_trace(sim.h, buf, 4096)
 raw=np.array(buf[:], dtype=np.int64); t=raw[:2048]; t=t[t>0]; tm=raw[2048:]; tm=tm[tm>0]
+# Stamps of CTA 0's crew thread 0.  The first tile has 13 (X, acc1, W0a, W0b, acc2, H1, G, T2, acc3, U, acc4, score, sync);
+# every later one starts with the early hand-over of its input during the previous tile's tail and has 15.
+t=t[13:]
 d=np.diff(t)
-per=11
-names=["MMA mlp1.0 (X signalled -> acc)","epilogue wide half 0","epilogue wide half 1 (chases mlp1.2a)","wait mlp1.2 complete",
+per=15
+names=["tail of the previous tile (softmax, pooling, joint) under this tile's mlp1.0","crew sync",
+       "wait mlp1.0 complete","epilogue wide half 0","epilogue wide half 1 (chases mlp1.2a)","wait mlp1.2 complete",
        "epilogue H1 (+ state means)","G operand (chases attention.0 local)","epilogue T2 (chases attention.0 global)",
        "crew sync + wait attention.0 complete","epilogue U (chases mlp2.2)","wait attention.2 complete",
-       "tail (score, softmax, pooling, joint) + next X"]
+       "score epilogue","crew sync","next tile's X staged and handed over"]
 ntile=(len(t)-1)//per
 arr=d[:ntile*per].reshape(ntile,per).astype(float)
 mhz=1965.0
@@ -37,7 +41,7 @@ if len(tm) > 0:
     clk = tm >> 16; batch = tm & 0xffff
     for tile in (20,):
         base = t[tile*per]; end = t[(tile+1)*per]
-        print("tile %d, crew stamps (us): X, acc1, W0a, W0b, acc2, H1, G, T2, acc3, U, acc4, next X" % tile)
+        print("tile %d, crew stamps (us): X, tail, sync, acc1, W0a, W0b, acc2, H1, G, T2, acc3, U, acc4, score, sync, next X" % tile)
         print("  ", np.round((t[tile*per:(tile+1)*per+1] - base)/mhz, 2))
         sel = (clk >= base - 200) & (clk <= end)
         print("  MMA warp batches (us: k-steps):", " ".join("%.2f:%d" % ((c - base)/mhz, b) for c, b in zip(clk[sel], batch[sel])))
