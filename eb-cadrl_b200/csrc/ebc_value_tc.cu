@@ -229,7 +229,7 @@ struct Pipe {
           if (++idle > (1u << 26)) __trap();   // bounded: a protocol bug traps instead of hanging
         }
         tc_fence_after();
-        if (trace && leader && blockIdx.x == 0 && trace_pos < 2040)   // diagnostics: (clock, cleared k-steps)
+        if (trace && leader && blockIdx.x == 0 && trace_pos < 900)   // diagnostics: (clock, cleared k-steps)
           trace[2048 + trace_pos++] = (clock64() << 16) | (long long)((avail - (uint32_t)ks) & 0xFFFFu);
       }
       int nb = ((int)avail < ksteps ? (int)avail : ksteps) - ks;
@@ -638,15 +638,18 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
       // ---- mlp1.0 -> mlp1.2, K chunked by the wide halves; the second half overwrites the blocks of the first
       //      as mlp1.2's first K chunk releases them --------------------------------------------------------
       pipe.wait_acc();                                                             // #1
-      for (int h = 0; h < P.n_wide; ++h) {
-        const TcStage &W = P.st[ST_L0A + h];
-        const int n_free = h ? P.st[ST_L1A + h - 1].ksteps : 0;
-        EpiExtra ex;
-        ex.one_col = P.st[ST_L1A + h].bias_k;     // this half is K chunk h of mlp1.2
-        epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, W.acc_col, W.np, W.n_real, W.bias_k >= 0 ? nullptr : P.bias[0] + W.n_lo, A,
-                                row, true, n_free, ex);
-        if (h) pipe.f_phase ^= low_bits(n_free);
-        pipe.stamp();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {        // (unrolled: the stage fields become constant-bank operands, no LDC chain)
+        if (h < P.n_wide) {
+          const TcStage &W = P.st[ST_L0A + h];
+          const int n_free = h ? P.st[ST_L1A + (h ? h - 1 : 0)].ksteps : 0;
+          EpiExtra ex;
+          ex.one_col = P.st[ST_L1A + h].bias_k;     // this half is K chunk h of mlp1.2
+          epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, W.acc_col, W.np, W.n_real, W.bias_k >= 0 ? nullptr : P.bias[0] + W.n_lo,
+                                  A, row, true, n_free, ex);
+          if (h) pipe.f_phase ^= low_bits(n_free);
+          pipe.stamp();
+        }
       }
       // ---- H1 -> A; mlp2.0 and attention.0 (local half) share it -------------------------------------
       pipe.wait_acc();                                                             // #2
@@ -957,14 +960,17 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
       if (!staged) stage_x(tile);
       staged = false;
       pipe.wait_acc();
-      for (int h = 0; h < P.n_wide; ++h) {
-        const TcStage &W = P.st[ST_L0A + h];
-        const int n_free = h ? P.st[ST_L1A + h - 1].ksteps : 0;
-        EpiExtra ex;
-        ex.one_col = P.st[ST_L1A + h].bias_k;
-        epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, W.acc_col, W.np, W.n_real, W.bias_k >= 0 ? nullptr : P.bias[0] + W.n_lo, A,
-                                row, true, n_free, ex);
-        if (h) pipe.f_phase ^= low_bits(n_free);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (h < P.n_wide) {
+          const TcStage &W = P.st[ST_L0A + h];
+          const int n_free = h ? P.st[ST_L1A + (h ? h - 1 : 0)].ksteps : 0;
+          EpiExtra ex;
+          ex.one_col = P.st[ST_L1A + h].bias_k;
+          epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, W.acc_col, W.np, W.n_real, W.bias_k >= 0 ? nullptr : P.bias[0] + W.n_lo,
+                                  A, row, true, n_free, ex);
+          if (h) pipe.f_phase ^= low_bits(n_free);
+        }
       }
       pipe.wait_acc();
       {
