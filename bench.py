@@ -98,7 +98,9 @@ def flops_per_eval(sd, n):
 
 
 class ClockSampler(threading.Thread):
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / power / throttle reasons every 20 ms; `stop(t0, t1)` keeps the samples whose own timestamp
+    lies inside the timed region [t0, t1] (wall clock), so that idle samples before it do not dilute the median."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
@@ -110,23 +112,38 @@ class ClockSampler(threading.Thread):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([x.strip() for x in line.split(",")])
         except Exception:
             pass
 
-    def stop(self):
+    @staticmethod
+    def _epoch(stamp):
+        import datetime
+        try:
+            return datetime.datetime.strptime(stamp, "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
+    def stop(self, t0=None, t1=None):
         if self.proc is not None:
+            time.sleep(0.05)
             self.proc.terminate()
-        rows = [r for r in self.rows if len(r) == 7]
+            self.join(timeout=2.0)
+        rows = [r for r in self.rows if len(r) == 8]
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
+        if t0 is not None and t1 is not None:
+            inside = [r for r in rows if (self._epoch(r[0]) or 0.0) >= t0 and (self._epoch(r[0]) or 0.0) <= t1 + 0.02]
+            if inside:
+                rows = inside
+        sm = sorted(float(r[1]) for r in rows if r[1].replace(".", "").isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i] == "Active" for r in rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(rows[0][1]),
-                "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows), "reasons": reasons}
+        reasons = [n for i, n in enumerate(names) if any(r[4 + i] == "Active" for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": float(rows[0][2]), "power_w_max": max(float(r[3]) for r in rows), "samples": len(rows),
+                "reasons": reasons}
 
 
 def measured_peaks():
@@ -268,11 +285,13 @@ def main():
     marks = []
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    wall0 = time.time()
     t_begin.record()
     for _ in range(args.steps):
         one_step(marks)
     t_end.record()
     barrier()
+    wall1 = time.time()
     launches = sim.launch_count() - launches0
     elapsed_ms = t_begin.elapsed_time(t_end)
     phase_names = ["orca", "lookahead", "value", "select", "step", "reset"]
@@ -281,7 +300,7 @@ def main():
         m = marks[s * 7:(s + 1) * 7]
         for i, nm in enumerate(phase_names):
             phase_ms[nm] += m[i].elapsed_time(m[i + 1])
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
 
     # ---- side measurement: K4 in the other tensor-core mode on the same states + argmax agreement ------
     other = "tc_bf16" if args.value_mode != "tc_bf16" else "tc_fp16x2"
