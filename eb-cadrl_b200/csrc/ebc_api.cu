@@ -154,7 +154,8 @@ int ebc_lookahead(ebc_sim *s, float *vin, double *reward, uint8_t *done, uint8_t
 int ebc_value(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row_count, float *values, void *stream) {
   if (!s) return EBC_ERR_INVALID;
   if (!s->have_weights) return ebc_fail(s, EBC_ERR_UNBOUND, "ebc_value: weights not set");
-  if (!vin || !values || n_states < 0) return ebc_fail(s, EBC_ERR_INVALID, "ebc_value: bad argument");
+  if (n_states < 0 || (n_states > 0 && (!vin || !values))) return ebc_fail(s, EBC_ERR_INVALID, "ebc_value: bad argument");
+  if (n_states == 0) return EBC_OK;      // an empty batch is valid and launches nothing
   {
     // scratch for the pooled per-state features; grows monotonically, outside any timed steady state
     const int jd = s->net.self_dim + s->net.l[3].out;

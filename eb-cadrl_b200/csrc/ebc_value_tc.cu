@@ -1070,6 +1070,7 @@ struct Packer {
 
 template <int NSPLIT>
 int launch_tc(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row_count, float *values, cudaStream_t stream) {
+  if (n_states <= 0) return EBC_OK;     // an empty batch launches nothing (like the FFMA path)
   const Smem L = smem_layout<NSPLIT>();
   if ((int)L.total > s->max_smem_optin)
     return ebc_fail(s, EBC_ERR_INVALID, "tensor-core value path needs %u B of shared memory", L.total);

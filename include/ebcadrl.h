@@ -205,7 +205,8 @@ int ebc_lookahead(ebc_sim *sim, float *vin, double *reward, uint8_t *done, uint8
  * each; row_count[s] (<= n) rows are real, the rest are padding (excluded from the
  * mean and the softmax).  vin [n_states*n*D] -> values [n_states].
  * row_count may be NULL (all n rows real).  Used with n_states = N*A for the lookahead,
- * in which case pass row_count = NULL and the per-episode counts bound to the sim are used. */
+ * in which case pass row_count = NULL and the per-episode counts bound to the sim are used.
+ * n_states == 0 is valid and launches nothing (pointers may then be NULL). */
 int ebc_value(ebc_sim *sim, const float *vin, int64_t n_states, const int32_t *row_count,
               float *values, void *stream);
 

@@ -99,6 +99,26 @@ def test_tc_matches_golden_argmax(oracle):
     assert res["tc_bf16"][0] < 0.1
 
 
+@pytest.mark.parametrize("n_states", [0, 1, 127, 128, 129, 257])
+def test_tc_ragged_batch_sizes(n_states):
+    """Batch sizes around the 128-state tiles of the pooled-feature scratch (an empty batch launches nothing; partial last
+    tiles of both kernels; the state right after a tile boundary); every state's value must equal the value the same
+    state gets inside a large batch, bit for bit, in every mode."""
+    w = ob.load_weights("weights_ebcadrl.npz")
+    cfg = SimConfig()
+    cfg.with_agent_type = True
+    sim = BatchedSim(cfg, 1, 10, 6, 0, 81, device="cuda:0")
+    sim.set_weights(w)
+    x, cnt = make_inputs(300, 16, cfg.D, seed=5)
+    for mode in ("tc_fp16x2", "tc_fp32", "tc_bf16", "fp32"):
+        sim.set_value_mode(mode)
+        big = sim.value(x, cnt).clone()
+        small = sim.value(x[:n_states], cnt[:n_states]).clone()
+        torch.cuda.synchronize()
+        assert small.shape[0] == n_states
+        assert torch.equal(small, big[:n_states]), mode
+
+
 @pytest.mark.parametrize("n,with_global", [(16, False), (7, False), (8, True), (32, True)])
 def test_tc_random_networks(n, with_global):
     """Shapes the shipped checkpoints do not cover: no global state (sarl.py:28-32 with_global_state = False,
