@@ -131,18 +131,102 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
-// same with the descriptors given as (low word, shared high word): the low words carry the start address
+// same with the descriptors given as (low word, shared high word): the low words carry the start address.
+// COLL: use of the A-operand collector buffer -- consecutive MMAs with the same A tile (A_hi x B_lo, then A_hi x B_hi)
+// read it from shared memory once: 1 = fill (keep A after this MMA), 2 = use (take A from the buffer, keep it),
+// 3 = last use (take it from the buffer, then drop it), 0 = default.  SASS: UTCHMMA gdesc.A_KEEP / .A_REUSE.
+template <int COLL = 0>
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
                                          bool accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-      "mov.b64 da, {%1, %3};\n\t"
-      "mov.b64 db, {%2, %3};\n\t"
-      "setp.ne.b32 p, %5, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
-      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"((uint32_t)accumulate)
-      : "memory");
+#define EBC_UMMA(MOD)                                                                                          \
+  asm volatile(                                                                                                \
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"                                                          \
+      "mov.b64 da, {%1, %3};\n\t"                                                                              \
+      "mov.b64 db, {%2, %3};\n\t"                                                                              \
+      "setp.ne.b32 p, %5, 0;\n\t"                                                                              \
+      "tcgen05.mma.cta_group::1.kind::f16" MOD " [%0], da, db, %4, p;\n\t}"                                   \
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"((uint32_t)accumulate)                 \
+      : "memory")
+  if constexpr (COLL == 1) EBC_UMMA(".collector::a::fill");
+  else if constexpr (COLL == 2) EBC_UMMA(".collector::a::use");
+  else if constexpr (COLL == 3) EBC_UMMA(".collector::a::lastuse");
+  else EBC_UMMA("");
+#undef EBC_UMMA
 }
+// One k-step of the split product, issued by a CONVERGED warp: every lane executes the block, elect.sync picks the lane
+// whose tcgen05 instructions take effect.  Measured (tools/mma_issue.cu): issued this way a k-step of three N = 104 MMAs
+// and two commits takes 160 cycles (= the tensor pipe's N/2 per MMA); issued by one thread of a diverged warp, with the
+// descriptors moved register -> uniform register before every use, it takes 258 (the "88 cycles per MMA" floor of
+// tools/mma_rate.cu is that issue path, not the pipe).
+//   d: accumulator (TMEM address); a_lo / b_lo: low descriptor words of the leading parts; a_step / b_step: distance
+//   (descriptor units of 16 B) between the parts of A / B; acc: accumulate into d (false: the first MMA overwrites);
+//   bar_slot: mbarrier that frees the weight slab; bar_blk: mbarrier that frees the A block (used if commit_blk).
+//   The high descriptor word (SBO = 128 B, version 1) is the same for every operand: an immediate inside the block.
+constexpr uint32_t DESC_HI_CONST = (128u >> 4) | (1u << 14);
+template <int NSPLIT>
+__device__ __forceinline__ void umma_kstep(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t a_step, uint32_t b_step,
+                                           uint32_t idesc, bool acc, uint32_t bar_slot, uint32_t bar_blk, bool commit_blk) {
+#define EBC_MMA(MOD, A, B, P) "@q tcgen05.mma.cta_group::1.kind::f16" MOD " [%0], " A ", " B ", %4, " P ";\n\t"
+#define EBC_COMMITS                                                                                       \
+  "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t"                    \
+  "@pk tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
+#define EBC_HEAD                                                                                          \
+  "{\n\t.reg .pred q, pa, pt, pk;\n\t.reg .b64 a0, a1, a2, b0, b1, b2;\n\t.reg .b32 hi;\n\t"              \
+  "elect.sync _|q, 0xffffffff;\n\t"                                                                      \
+  "mov.b32 hi, %3;\n\t"                                                                                  \
+  "setp.ne.b32 pa, %7, 0;\n\t"                                                                           \
+  "setp.eq.b32 pt, 0, 0;\n\t"                                                                            \
+  "setp.ne.b32 pk, %8, 0;\n\t"                                                                           \
+  "and.pred pk, pk, q;\n\t"
+  if constexpr (NSPLIT == 1) {
+    asm volatile(EBC_HEAD
+                 "mov.b64 a0, {%1, hi};\n\t"
+                 "mov.b64 b0, {%2, hi};\n\t"
+                 EBC_MMA("", "a0", "b0", "pa")
+                 EBC_COMMITS "}"
+                 ::"r"(d), "r"(a_lo), "r"(b_lo), "n"(DESC_HI_CONST), "r"(idesc), "r"(bar_slot), "r"(bar_blk),
+                   "r"((uint32_t)acc), "r"((uint32_t)commit_blk)
+                 : "memory");
+  } else if constexpr (NSPLIT == 2) {
+    // terms, smallest first: A1 B0, A0 B1, A0 B0 (the two A0 terms share one read of A0 through the collector buffer)
+    asm volatile(EBC_HEAD
+                 "mov.b64 a0, {%1, hi};\n\t"
+                 "mov.b64 b0, {%2, hi};\n\t"
+                 "mov.b64 a1, {%9, hi};\n\t"
+                 "mov.b64 b1, {%10, hi};\n\t"
+                 EBC_MMA("", "a1", "b0", "pa")
+                 EBC_MMA(".collector::a::fill", "a0", "b1", "pt")
+                 EBC_MMA(".collector::a::lastuse", "a0", "b0", "pt")
+                 EBC_COMMITS "}"
+                 ::"r"(d), "r"(a_lo), "r"(b_lo), "n"(DESC_HI_CONST), "r"(idesc), "r"(bar_slot), "r"(bar_blk),
+                   "r"((uint32_t)acc), "r"((uint32_t)commit_blk), "r"(a_lo + a_step), "r"(b_lo + b_step)
+                 : "memory");
+  } else {
+    // A2 B0, A1 B1, A1 B0, A0 B2, A0 B1, A0 B0
+    asm volatile(EBC_HEAD
+                 "mov.b64 a0, {%1, hi};\n\t"
+                 "mov.b64 b0, {%2, hi};\n\t"
+                 "mov.b64 a1, {%9, hi};\n\t"
+                 "mov.b64 b1, {%10, hi};\n\t"
+                 "mov.b64 a2, {%11, hi};\n\t"
+                 "mov.b64 b2, {%12, hi};\n\t"
+                 EBC_MMA("", "a2", "b0", "pa")
+                 EBC_MMA(".collector::a::fill", "a1", "b1", "pt")
+                 EBC_MMA(".collector::a::lastuse", "a1", "b0", "pt")
+                 EBC_MMA(".collector::a::fill", "a0", "b2", "pt")
+                 EBC_MMA(".collector::a::use", "a0", "b1", "pt")
+                 EBC_MMA(".collector::a::lastuse", "a0", "b0", "pt")
+                 EBC_COMMITS "}"
+                 ::"r"(d), "r"(a_lo), "r"(b_lo), "n"(DESC_HI_CONST), "r"(idesc), "r"(bar_slot), "r"(bar_blk),
+                   "r"((uint32_t)acc), "r"((uint32_t)commit_blk), "r"(a_lo + a_step), "r"(b_lo + b_step),
+                   "r"(a_lo + 2 * a_step), "r"(b_lo + 2 * b_step)
+                 : "memory");
+  }
+#undef EBC_MMA
+#undef EBC_COMMITS
+#undef EBC_HEAD
+}
+
 // all previously issued MMAs of this thread done -> one arrival on `bar`
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -210,17 +294,26 @@ __device__ __forceinline__ void store_a8(uint8_t *a_base, uint32_t image_bytes, 
 }
 
 // (a part, b part) pairs accumulated per k-step, smallest magnitude first
+// Terms of the split product, smallest first; a(t) / b(t) = part index of A / B (0 = leading part), coll(t) = the
+// A-operand collector mode of term t (see umma_f16): consecutive terms with the same A part read it once.
 template <int NSPLIT> struct Terms;
-template <> struct Terms<1> { static constexpr int N = 1; __device__ static int a(int) { return 0; } __device__ static int b(int) { return 0; } };
+template <> struct Terms<1> {
+  static constexpr int N = 1;
+  __host__ __device__ static constexpr int a(int) { return 0; }
+  __host__ __device__ static constexpr int b(int) { return 0; }
+  __host__ __device__ static constexpr int coll(int) { return 0; }
+};
 template <> struct Terms<2> {
   static constexpr int N = 3;
-  __device__ static int a(int t) { const int v[3] = {1, 0, 0}; return v[t]; }
-  __device__ static int b(int t) { const int v[3] = {0, 1, 0}; return v[t]; }
+  __host__ __device__ static constexpr int a(int t) { constexpr int v[3] = {1, 0, 0}; return v[t]; }
+  __host__ __device__ static constexpr int b(int t) { constexpr int v[3] = {0, 1, 0}; return v[t]; }
+  __host__ __device__ static constexpr int coll(int t) { constexpr int v[3] = {0, 1, 3}; return v[t]; }
 };
 template <> struct Terms<3> {
   static constexpr int N = 6;
-  __device__ static int a(int t) { const int v[6] = {2, 0, 1, 1, 0, 0}; return v[t]; }
-  __device__ static int b(int t) { const int v[6] = {0, 2, 1, 0, 1, 0}; return v[t]; }
+  __host__ __device__ static constexpr int a(int t) { constexpr int v[6] = {2, 1, 1, 0, 0, 0}; return v[t]; }
+  __host__ __device__ static constexpr int b(int t) { constexpr int v[6] = {0, 1, 0, 2, 1, 0}; return v[t]; }
+  __host__ __device__ static constexpr int coll(int t) { constexpr int v[6] = {0, 1, 3, 1, 2, 3}; return v[t]; }
 };
 
 }  // namespace tc

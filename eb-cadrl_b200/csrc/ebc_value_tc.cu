@@ -201,6 +201,15 @@ struct Pipe {
     asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(r) : "r"(smem_u32(ready)) : "memory");
     return r;
   }
+  // the MMAs of one k-step: every term of the split product, A parts shared through the collector buffer
+  template <int T>
+  __device__ __forceinline__ void issue_terms(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t np, uint32_t desc_hi,
+                                              uint32_t idesc, bool accumulate) {
+    using TT = Terms<NSPLIT>;
+    umma_f16<TT::coll(T)>(d, a_lo + (uint32_t)(TT::a(T) * (int)(Cfg<NSPLIT>::A_IMAGE / 16)), b_lo + (uint32_t)TT::b(T) * np * 2,
+                          desc_hi, idesc, accumulate || T > 0);
+    if constexpr (T + 1 < TT::N) issue_terms<T + 1>(d, a_lo, b_lo, np, desc_hi, idesc, accumulate);
+  }
   // chase:    the crew is still writing the A operand; k-step ks is issued as soon as its two k-chunks (one
   //           16-column block of the previous stage's epilogue) have been stored and fenced by all 128 rows
   // commit_k: signal afree[ks] when the MMAs issued up to and including k-step ks have completed
@@ -210,57 +219,38 @@ struct Pipe {
     const uint32_t d = tmem_base + S.acc_col;
     const uint32_t np = (uint32_t)S.np;
     const int ksteps = S.ksteps;
-    const bool acc0 = S.accumulate != 0;
     // A descriptor = {start address >> 4 | LBO << 16, SBO | version}: only the low word changes (32-bit adds)
-    constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
-    const uint32_t a_lo0 = ((a_smem >> 4) & 0x3FFFu) | ((uint32_t)(A_CHUNK_BYTES >> 4) << 16);
-    const uint32_t b_lo0 = ((smem_u32(wbuf) >> 4) & 0x3FFFu) | (np << 16);
+    static_assert(DESC_HI_CONST == ((128u >> 4) | (1u << 14)), "SBO = 128 B, descriptor version 1");
+    // Everything the issue path needs is a running value that depends on kernel parameters and loop counters only
+    // (never on what the scout published): the compiler keeps such values in uniform registers, and a k-step is a
+    // dozen instructions next to its three MMAs and two commits.  That matters: this warp shares its scheduler with
+    // four crew warps, and every instruction it spends per k-step is time the tensor pipe's shallow queue can run dry.
+    uint32_t a_cur = ((a_smem >> 4) & 0x3FFFu) | ((uint32_t)(A_CHUNK_BYTES >> 4) << 16);
+    const uint32_t b_base = ((smem_u32(wbuf) >> 4) & 0x3FFFu) | (np << 16);
+    uint32_t slot = st;
+    const uint32_t empty0 = smem_u32(empty), afree0 = smem_u32(afree);
     const uint32_t base = issued;                 // schedule index of this stage's first k-step
-    uint32_t avail = seen - base;                 // cleared k-steps of this stage (the scout may be further ahead)
-    // Up to four cleared k-steps are issued per trip: their descriptor words are computed first (independent
-    // instruction chains), then the MMAs and commits go out back to back, so that this warp's own latency per
-    // k-step stays well below the 312 cycles the tensor pipe needs for it.
-    int ks = 0;
-    while (ks < ksteps) {
-      if ((int)avail <= ks) {
+    bool acc = S.accumulate != 0;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      if ((int)(seen - base) <= ks) {
         uint32_t idle = 0;
-        while ((int)(avail = (seen = ready_count()) - base) <= ks) {
+        while ((int)((seen = ready_count()) - base) <= ks) {
           // the scout sleeps on the barriers; this warp only watches its count (a shared-memory load per trip)
           if (++idle > (1u << 26)) __trap();   // bounded: a protocol bug traps instead of hanging
         }
         tc_fence_after();
         if (trace && leader && blockIdx.x == 0 && trace_pos < 900)   // diagnostics: (clock, cleared k-steps)
-          trace[2048 + trace_pos++] = (clock64() << 16) | (long long)((avail - (uint32_t)ks) & 0xFFFFu);
+          trace[2048 + trace_pos++] = (clock64() << 16) | (long long)((seen - base - (uint32_t)ks) & 0xFFFFu);
       }
-      int nb = ((int)avail < ksteps ? (int)avail : ksteps) - ks;
-      if (nb > 4) nb = 4;
-      uint32_t a_lo[4], b_lo[4], slot[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t sj = st + (uint32_t)j;
-        if (sj >= ST) sj -= ST;
-        slot[j] = sj;
-        a_lo[j] = a_lo0 + (uint32_t)(ks + j) * (2 * A_CHUNK_BYTES / 16);
-        b_lo[j] = b_lo0 + sj * (Cfg<NSPLIT>::STAGE_BYTES / 16);
-      }
-      if (leader) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (j < nb) {
-#pragma unroll
-            for (int t = 0; t < Terms<NSPLIT>::N; ++t)
-              umma_f16(d, a_lo[j] + (uint32_t)(Terms<NSPLIT>::a(t) * (Cfg<NSPLIT>::A_IMAGE / 16)),
-                       b_lo[j] + (uint32_t)(Terms<NSPLIT>::b(t)) * np * 2, DESC_HI, idesc, acc0 || ks + j > 0 || t > 0);
-            umma_commit(&empty[slot[j]]);   // frees the slab when these MMAs have read it
-            if (commit_k) umma_commit(&afree[ks + j]);
-          }
-        }
-      }
-      __syncwarp();
-      ks += nb;
-      st += (uint32_t)nb;
-      if (st >= ST) st -= ST;
+      const uint32_t b_cur = b_base + slot * (Cfg<NSPLIT>::STAGE_BYTES / 16);
+      __syncwarp();      // converged: every lane runs the issue block, one elected lane's instructions take effect
+      umma_kstep<NSPLIT>(d, a_cur, b_cur, Cfg<NSPLIT>::A_IMAGE / 16, np * 2, idesc, acc, empty0 + slot * 8,
+                         afree0 + (uint32_t)ks * 8, commit_k);
+      acc = true;
+      a_cur += 2 * A_CHUNK_BYTES / 16;
+      slot = slot + 1 == ST ? 0 : slot + 1;
     }
+    st = slot;
     issued = base + (uint32_t)ksteps;
   }
   // one tile of the program: every stage of the schedule, accumulator commits where the crew waits for them
