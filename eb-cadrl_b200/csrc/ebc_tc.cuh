@@ -232,6 +232,17 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// the same for a converged warp: every lane executes it, the lane elect.sync picks commits.  The accumulator commits of
+// the MMA warp use this form so that they are executed by the very lane whose MMAs they track (umma_kstep elects the
+// same way) -- tcgen05.commit only covers operations initiated by the executing thread.
+__device__ __forceinline__ void umma_commit_elect(uint64_t *bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar)) : "memory");
+}
+
 // one lane of a converged warp
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

@@ -260,8 +260,8 @@ struct Pipe {
     for (int i = 0; i < P.n_sched; ++i) {
       mma_stage(P.st[P.sched[i].stage], a_smem, tmem_base, P.sched[i].commit_k != 0);
       if (P.sched[i].commit_acc) {
-        if (leader) umma_commit(acc_bar);
         __syncwarp();
+        umma_commit_elect(acc_bar);
       }
     }
   }
