@@ -123,15 +123,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N, uint32_t fmt) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
-      : "memory");
-}
-// same with the descriptors given as (low word, shared high word): the low words carry the start address.
+// One MMA issued by the calling thread, descriptors given as (low word, shared high word): the low words carry the
+// start address.  Used by the microbenchmarks in tools/ (the kernels issue whole k-steps through umma_kstep below).
 // COLL: use of the A-operand collector buffer -- consecutive MMAs with the same A tile (A_hi x B_lo, then A_hi x B_hi)
 // read it from shared memory once: 1 = fill (keep A after this MMA), 2 = use (take A from the buffer, keep it),
 // 3 = last use (take it from the buffer, then drop it), 0 = default.  SASS: UTCHMMA gdesc.A_KEEP / .A_REUSE.
@@ -305,26 +298,4 @@ __device__ __forceinline__ void store_a8(uint8_t *a_base, uint32_t image_bytes, 
 }
 
 // (a part, b part) pairs accumulated per k-step, smallest magnitude first
-// Terms of the split product, smallest first; a(t) / b(t) = part index of A / B (0 = leading part), coll(t) = the
-// A-operand collector mode of term t (see umma_f16): consecutive terms with the same A part read it once.
-template <int NSPLIT> struct Terms;
-template <> struct Terms<1> {
-  static constexpr int N = 1;
-  __host__ __device__ static constexpr int a(int) { return 0; }
-  __host__ __device__ static constexpr int b(int) { return 0; }
-  __host__ __device__ static constexpr int coll(int) { return 0; }
-};
-template <> struct Terms<2> {
-  static constexpr int N = 3;
-  __host__ __device__ static constexpr int a(int t) { constexpr int v[3] = {1, 0, 0}; return v[t]; }
-  __host__ __device__ static constexpr int b(int t) { constexpr int v[3] = {0, 1, 0}; return v[t]; }
-  __host__ __device__ static constexpr int coll(int t) { constexpr int v[3] = {0, 1, 3}; return v[t]; }
-};
-template <> struct Terms<3> {
-  static constexpr int N = 6;
-  __host__ __device__ static constexpr int a(int t) { constexpr int v[6] = {2, 1, 1, 0, 0, 0}; return v[t]; }
-  __host__ __device__ static constexpr int b(int t) { constexpr int v[6] = {0, 1, 0, 2, 1, 0}; return v[t]; }
-  __host__ __device__ static constexpr int coll(int t) { constexpr int v[6] = {0, 1, 3, 1, 2, 3}; return v[t]; }
-};
-
 }  // namespace tc

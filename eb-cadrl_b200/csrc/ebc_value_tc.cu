@@ -201,15 +201,6 @@ struct Pipe {
     asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(r) : "r"(smem_u32(ready)) : "memory");
     return r;
   }
-  // the MMAs of one k-step: every term of the split product, A parts shared through the collector buffer
-  template <int T>
-  __device__ __forceinline__ void issue_terms(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t np, uint32_t desc_hi,
-                                              uint32_t idesc, bool accumulate) {
-    using TT = Terms<NSPLIT>;
-    umma_f16<TT::coll(T)>(d, a_lo + (uint32_t)(TT::a(T) * (int)(Cfg<NSPLIT>::A_IMAGE / 16)), b_lo + (uint32_t)TT::b(T) * np * 2,
-                          desc_hi, idesc, accumulate || T > 0);
-    if constexpr (T + 1 < TT::N) issue_terms<T + 1>(d, a_lo, b_lo, np, desc_hi, idesc, accumulate);
-  }
   // chase:    the crew is still writing the A operand; k-step ks is issued as soon as its two k-chunks (one
   //           16-column block of the previous stage's epilogue) have been stored and fenced by all 128 rows
   // commit_k: signal afree[ks] when the MMAs issued up to and including k-step ks have completed
