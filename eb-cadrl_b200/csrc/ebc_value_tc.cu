@@ -10,7 +10,7 @@
 //   warps 0-15 (512 threads)   epilogue crew: warp w reads TMEM lane quarter (w % 4) (row = lane) and the
 //                              16-column blocks b with b % 4 == w / 4, applies bias / ReLU, splits the fp32
 //                              value into 16-bit parts and stores the next stage's A operand
-//   warp 16 (converged)        issues the tcgen05.mma's from one elected lane, up to four k-steps per trip:
+//   warp 16 (converged)        issues the tcgen05.mma's, one converged block per k-step (elect.sync inside):
 //                              A = activations in shared memory (canonical K-major layout written by the
 //                              previous epilogue), B = weight slab, D = fp32 accumulator in TMEM
 //   warp 17 (converged)        scout: polls the hand-over barriers and publishes how many k-steps may issue
