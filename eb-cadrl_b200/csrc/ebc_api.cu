@@ -39,10 +39,11 @@ int ebc_create(const ebc_config *cfg, int device, ebc_sim **out) {
     return ebc_fail(nullptr, EBC_ERR_INVALID, "ebc_create: abi_version %d != %d", cfg->abi_version, EBC_ABI_VERSION);
   if (cfg->n_episodes < 1 || cfg->max_humans < 1 || cfg->max_humans > 64 || cfg->max_statics < 0 ||
       cfg->max_humans + cfg->max_statics > 64 || cfg->max_rects < 0 || cfg->n_actions < 1 || cfg->n_actions > 256 ||
-      cfg->orca_max_neighbors < 0 || cfg->orca_max_neighbors > 32 ||
+      cfg->orca_max_neighbors < 0 || cfg->orca_max_neighbors > 32 || cfg->max_obst < 0 || cfg->max_obst > 64 ||
+      (cfg->orca_obstacles && !(cfg->orca_time_horizon_obst > 0.0f)) ||
       cfg->max_humans + (cfg->robot_visible ? 1 : 0) > 64)
     return ebc_fail(nullptr, EBC_ERR_INVALID,
-                    "ebc_create: config out of range (1<=Hmax<=64, Hmax+Smax<=64, 1<=A<=256, max_neighbors<=32)");
+                    "ebc_create: config out of range (1<=Hmax<=64, Hmax+Smax<=64, 1<=A<=256, max_neighbors<=32, Omax<=64)");
   if (!(cfg->time_step > 0.0) || !(cfg->map_resolution > 0.0))
     return ebc_fail(nullptr, EBC_ERR_INVALID, "ebc_create: time_step and map_resolution must be positive");
   int count = 0;
@@ -81,8 +82,10 @@ int ebc_bind(ebc_sim *s, const ebc_state *st) {
   if (!s || !st) return EBC_ERR_INVALID;
   if (!st->hum_pv || !st->hum_gr || !st->hum_type || !st->hum_count || !st->hum_nv || !st->stat_count ||
       !st->rect_count || !st->rob_pv || !st->rob_gr || !st->rob_theta || !st->time ||
-      (s->cfg.max_statics > 0 && !st->stat) || (s->cfg.max_rects > 0 && !st->rect))
+      (s->cfg.max_statics > 0 && !st->stat) || (s->cfg.max_rects > 0 && !st->rect) ||
+      (s->cfg.orca_obstacles && (!st->obst || !st->obst_count || s->cfg.max_obst < 1)))
     return ebc_fail(s, EBC_ERR_INVALID, "ebc_bind: null state array");
+  if ((uintptr_t)st->obst & 15u) return ebc_fail(s, EBC_ERR_INVALID, "ebc_bind: obst must be 16-byte aligned");
   if (((uintptr_t)st->hum_pv | (uintptr_t)st->hum_gr | (uintptr_t)st->stat | (uintptr_t)st->rob_pv |
        (uintptr_t)st->rob_gr) & 15u)
     return ebc_fail(s, EBC_ERR_INVALID, "ebc_bind: float4 arrays must be 16-byte aligned");
@@ -90,6 +93,18 @@ int ebc_bind(ebc_sim *s, const ebc_state *st) {
     return ebc_fail(s, EBC_ERR_INVALID, "ebc_bind: hum_nv / rect / time must be 8-byte aligned");
   s->st = *st;
   s->bound = true;
+  return EBC_OK;
+}
+
+int ebc_bind_stats(ebc_sim *s, const ebc_stats *x) {
+  if (!s) return EBC_ERR_INVALID;
+  if (!x) { memset(&s->stats, 0, sizeof(s->stats)); return EBC_OK; }
+  if (!x->alive || !x->final_event || !x->steps || !x->too_close || !x->cum_reward || !x->discount || !x->min_dist_sum ||
+      !x->alive_count)
+    return ebc_fail(s, EBC_ERR_INVALID, "ebc_bind_stats: null statistics array");
+  if (((uintptr_t)x->cum_reward | (uintptr_t)x->discount | (uintptr_t)x->min_dist_sum) & 7u)
+    return ebc_fail(s, EBC_ERR_INVALID, "ebc_bind_stats: double arrays must be 8-byte aligned");
+  s->stats = *x;
   return EBC_OK;
 }
 
@@ -103,19 +118,57 @@ int ebc_set_actions(ebc_sim *s, const double *actions, int32_t n) {
   return EBC_OK;
 }
 
+// scratch for the pooled per-state features of K4: [ceil(n/128)*128][ceil(jd/8)*8] floats (the tensor-core kernels keep
+// it in 128-state tiles of 8-column chunks: both dimensions rounded up).  Grows monotonically; never called from ebc_value.
+static int reserve_states(ebc_sim *s, int64_t n_states) {
+  const int jd = s->net.self_dim + s->net.l[3].out;
+  const size_t need = (size_t)((n_states + 127) / 128 * 128) * (size_t)((jd + 7) / 8 * 8);
+  if (need > s->joint_floats) {
+    cudaSetDevice(s->device);
+    if (s->d_joint) cudaFree(s->d_joint);     // (synchronises: setup-time only)
+    s->d_joint = nullptr;
+    s->joint_floats = 0;
+    s->joint_cap = 0;
+    const cudaError_t err = cudaMalloc(&s->d_joint, need * sizeof(float));
+    if (err != cudaSuccess) return ebc_fail(s, EBC_ERR_NOMEM, "cudaMalloc joint scratch: %s", cudaGetErrorString(err));
+    s->joint_floats = need;
+  }
+  if (n_states > s->joint_cap) s->joint_cap = n_states;
+  return EBC_OK;
+}
+
 int ebc_set_weights(ebc_sim *s, const ebc_weights *w) {
   if (!s || !w) return EBC_ERR_INVALID;
   cudaSetDevice(s->device);
   int rc = ebc_value_prepare(s, w);
   if (rc) return rc;
-  // tensor-core programs: [0] bf16, [1] fp16x2 (default), [2] bf16x3.  A shape that does not fit keeps the FFMA path.
+  // the lookahead batch (N * A states) is reserved here, at setup time: ebc_value itself never allocates
+  const int64_t want = (int64_t)s->cfg.n_episodes * s->cfg.n_actions;
+  const int64_t keep = s->joint_cap > want ? s->joint_cap : want;   // (the row width may have changed with the network)
+  if ((rc = reserve_states(s, keep)) != 0) return rc;
+  // tensor-core programs: [0] bf16, [1] fp16x2 (default), [2] bf16x3
   const int r0 = ebc_tc_prepare(s, w, 0, 1), r1 = ebc_tc_prepare(s, w, 1, 2), r2 = ebc_tc_prepare(s, w, 2, 3);
   if (r0 < 0) return r0;
   if (r1 < 0) return r1;
   if (r2 < 0) return r2;
-  if (r0 || r1 || r2) { s->tc[0].ready = s->tc[1].ready = s->tc[2].ready = 0; s->value_mode = EBC_VALUE_FP32; }
-  else if (!s->value_mode_forced) s->value_mode = EBC_VALUE_TC_FP16X2;
+  if (r0 || r1 || r2) {
+    // the shape misses the tensor-core tiling: the weights are accepted, K4 runs on the FFMA kernels, and the caller
+    // is TOLD so (a positive status, never a silent downgrade)
+    s->tc[0].ready = s->tc[1].ready = s->tc[2].ready = 0;
+    s->value_mode = EBC_VALUE_FP32;
+    ebc_fail(s, EBC_WARN_VALUE_FFMA, "ebc_set_weights: this network's shape does not fit the tensor-core tiling "
+                                     "(layer widths <= 416 / 208, input <= 32, self state <= 8): value mode is EBC_VALUE_FP32");
+    return EBC_WARN_VALUE_FFMA;
+  }
+  if (!s->value_mode_forced) s->value_mode = EBC_VALUE_TC_FP16X2;
   return EBC_OK;
+}
+
+int ebc_reserve(ebc_sim *s, int64_t n_states) {
+  if (!s) return EBC_ERR_INVALID;
+  if (!s->have_weights) return ebc_fail(s, EBC_ERR_UNBOUND, "ebc_reserve: weights not set (the row width is the network's)");
+  if (n_states < 0) return ebc_fail(s, EBC_ERR_INVALID, "ebc_reserve: negative size");
+  return reserve_states(s, n_states);
 }
 
 int ebc_set_value_mode(ebc_sim *s, int32_t mode) {
@@ -156,20 +209,16 @@ int ebc_value(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row
   if (!s->have_weights) return ebc_fail(s, EBC_ERR_UNBOUND, "ebc_value: weights not set");
   if (n_states < 0 || (n_states > 0 && (!vin || !values))) return ebc_fail(s, EBC_ERR_INVALID, "ebc_value: bad argument");
   if (n_states == 0) return EBC_OK;      // an empty batch is valid and launches nothing
-  {
-    // scratch for the pooled per-state features; grows monotonically, outside any timed steady state
-    const int jd = s->net.self_dim + s->net.l[3].out;
-    if (n_states > s->joint_cap) {
-      if (s->d_joint) cudaFree(s->d_joint);
-      s->d_joint = nullptr;
-      // (the tensor-core kernels keep it in 128-state tiles of 8-column chunks: both dimensions rounded up)
-      const size_t cap_floats = (size_t)((n_states + 127) / 128 * 128) * (size_t)((jd + 7) / 8 * 8);
-      cudaError_t err = cudaMalloc(&s->d_joint, cap_floats * sizeof(float));
-      if (err != cudaSuccess) return ebc_fail(s, EBC_ERR_NOMEM, "cudaMalloc joint scratch: %s", cudaGetErrorString(err));
-      s->joint_cap = n_states;
-    }
+  if (n_states > s->joint_cap)
+    return ebc_fail(s, EBC_ERR_UNBOUND, "ebc_value: %lld states exceed the reserved %lld (call ebc_reserve at setup time; "
+                                        "ebc_value never allocates)", (long long)n_states, (long long)s->joint_cap);
+  if (!row_count) {
+    // NULL = the lookahead batch: state i belongs to episode i / A and takes that episode's bound entity counts
+    if (!s->bound) return ebc_fail(s, EBC_ERR_UNBOUND, "ebc_value: state not bound");
+    if (n_states != (int64_t)s->cfg.n_episodes * s->cfg.n_actions)
+      return ebc_fail(s, EBC_ERR_INVALID, "ebc_value: row_count == NULL needs n_states == n_episodes * n_actions (%lld), got %lld",
+                      (long long)s->cfg.n_episodes * s->cfg.n_actions, (long long)n_states);
   }
-  if (!row_count && !s->bound) return ebc_fail(s, EBC_ERR_UNBOUND, "ebc_value: state not bound");
   if (s->value_mode != EBC_VALUE_FP32 && s->tc[ebc_tc_index(s->value_mode)].ready)
     return ebc_launch_value_tc(s, s->value_mode, vin, n_states, row_count, values, (cudaStream_t)stream);
   return ebc_launch_value(s, vin, n_states, row_count, values, (cudaStream_t)stream);

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#define EBC_DIAGNOSTICS 1
 #include "../../include/ebcadrl.h"
 
 #define EBC_WARPS_PER_BLOCK 8
@@ -68,13 +69,15 @@ struct TcPrograms {
 struct ebc_sim {
   ebc_config cfg;
   ebc_state st;
+  ebc_stats stats;       // running episode statistics (ebc_bind_stats); all-null when unbound
   int device;
   bool bound, have_actions, have_weights;
   double *d_actions;     // [A*2]
   ValueNet net;
   float *d_weights;      // one slab
   float *d_joint;        // [cap_states * (self_dim + H2)] scratch for mlp3
-  int64_t joint_cap;
+  int64_t joint_cap;     // states ebc_value may be called with (ebc_reserve)
+  size_t joint_floats;   // allocated floats of d_joint
   TcPrograms tc[3];      // indexed by operand parts - 1: [0] bf16, [1] fp16x2, [2] bf16x3
   long long *d_trace;    // EBC_TC_TRACE=1: clock64 stamps of CTA 0 (diagnostics)
   int value_mode;        // EBC_VALUE_*

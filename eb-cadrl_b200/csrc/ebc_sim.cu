@@ -48,27 +48,53 @@ __device__ __forceinline__ double warp_min_d(double v) {
   return v;
 }
 
+// The warp's ORCA lines: line index = lane + 32 * chunk.  LPL (lines per lane) = 1 on the reference's live path
+// (at most max_neighbors <= 32 agent lines), 2 when obstacle half-planes are enabled (up to 64 lines, obstacle
+// lines first).  Every function below is the same arithmetic for both; LPL = 1 compiles to the single-line code.
+template <int LPL> struct Lines { Line l[LPL]; };
+
+template <int LPL>
+__device__ __forceinline__ void bcast_line(const Lines<LPL> &L, int i, float &px, float &py, float &dx, float &dy) {
+  const int il = i & 31;
+  if (LPL == 1 || i < 32) {
+    px = __shfl_sync(FULL, L.l[0].px, il); py = __shfl_sync(FULL, L.l[0].py, il);
+    dx = __shfl_sync(FULL, L.l[0].dx, il); dy = __shfl_sync(FULL, L.l[0].dy, il);
+  } else {
+    px = __shfl_sync(FULL, L.l[LPL - 1].px, il); py = __shfl_sync(FULL, L.l[LPL - 1].py, il);
+    dx = __shfl_sync(FULL, L.l[LPL - 1].dx, il); dy = __shfl_sync(FULL, L.l[LPL - 1].dy, il);
+  }
+}
+
 // RVO2 linearProgram1 with the scan over earlier lines done by the lanes that hold them.
 // tLeft only grows and tRight only shrinks along the sequential scan, so "fails at some
 // prefix" == "fails at the end", and the parallel-line failure is order-free (Appendix A.3).
-__device__ bool lp1_warp(const Line &L, int lane, int i, float radius, float ox, float oy, bool dir_opt,
+template <int LPL>
+__device__ bool lp1_warp(const Lines<LPL> &L, int lane, int i, float radius, float ox, float oy, bool dir_opt,
                          float &rx, float &ry) {
-  const float pix = __shfl_sync(FULL, L.px, i), piy = __shfl_sync(FULL, L.py, i);
-  const float dix = __shfl_sync(FULL, L.dx, i), diy = __shfl_sync(FULL, L.dy, i);
+  float pix, piy, dix, diy;
+  bcast_line<LPL>(L, i, pix, piy, dix, diy);
   const float dp = dot2(pix, piy, dix, diy);
   const float disc = dp * dp + radius * radius - dot2(pix, piy, pix, piy);
   if (disc < 0.0f) return false;
   const float s = sqrtf(disc);
   float tl = -dp - s;
   float tr = -dp + s;
-  const float den = det2(dix, diy, L.dx, L.dy);
-  const float num = det2(L.dx, L.dy, pix - L.px, piy - L.py);
-  const bool act = lane < i;
-  const bool par = fabsf(den) <= RVO_EPSILON;
-  const bool bad = act && par && (num < 0.0f);
-  const float t = num / den;
-  const float cr = warp_min_f((act && !par && den >= 0.0f) ? t : INFINITY);
-  const float cl = warp_max_f((act && !par && den < 0.0f) ? t : -INFINITY);
+  float cr = INFINITY, cl = -INFINITY;
+  bool bad = false;
+#pragma unroll
+  for (int c = 0; c < LPL; ++c) {
+    const Line &M = L.l[c];
+    const float den = det2(dix, diy, M.dx, M.dy);
+    const float num = det2(M.dx, M.dy, pix - M.px, piy - M.py);
+    const bool act = lane + 32 * c < i;
+    const bool par = fabsf(den) <= RVO_EPSILON;
+    bad = bad || (act && par && (num < 0.0f));
+    const float t = num / den;
+    cr = fminf(cr, (act && !par && den >= 0.0f) ? t : INFINITY);
+    cl = fmaxf(cl, (act && !par && den < 0.0f) ? t : -INFINITY);
+  }
+  cr = warp_min_f(cr);
+  cl = warp_max_f(cl);
   tr = fminf(tr, cr);
   tl = fmaxf(tl, cl);
   if (__any_sync(FULL, bad) || tl > tr) return false;
@@ -86,8 +112,9 @@ __device__ bool lp1_warp(const Line &L, int lane, int i, float radius, float ox,
 }
 
 // RVO2 linearProgram2: the result only changes inside lp1, so the sequential "first violated
-// line at or after i" is one ballot.
-__device__ int lp2_warp(const Line &L, int lane, int n, float radius, float ox, float oy, bool dir_opt,
+// line at or after i" is one ballot (per chunk).
+template <int LPL>
+__device__ int lp2_warp(const Lines<LPL> &L, int lane, int n, float radius, float ox, float oy, bool dir_opt,
                         float &rx, float &ry) {
   if (dir_opt) {
     rx = ox * radius;
@@ -102,12 +129,18 @@ __device__ int lp2_warp(const Line &L, int lane, int n, float radius, float ox, 
   }
   int i = 0;
   for (;;) {
-    const bool viol = lane >= i && lane < n && det2(L.dx, L.dy, L.px - rx, L.py - ry) > 0.0f;
-    const unsigned m = __ballot_sync(FULL, viol);
-    if (m == 0u) return n;
-    i = __ffs(m) - 1;
+    int first = -1;
+#pragma unroll
+    for (int c = 0; c < LPL; ++c) {
+      const int idx = lane + 32 * c;
+      const bool viol = idx >= i && idx < n && det2(L.l[c].dx, L.l[c].dy, L.l[c].px - rx, L.l[c].py - ry) > 0.0f;
+      const unsigned m = __ballot_sync(FULL, viol);
+      if (first < 0 && m != 0u) first = 32 * c + __ffs(m) - 1;
+    }
+    if (first < 0) return n;
+    i = first;
     const float tx = rx, ty = ry;
-    if (!lp1_warp(L, lane, i, radius, ox, oy, dir_opt, rx, ry)) {
+    if (!lp1_warp<LPL>(L, lane, i, radius, ox, oy, dir_opt, rx, ry)) {
       rx = tx;
       ry = ty;
       return i;
@@ -116,40 +149,71 @@ __device__ int lp2_warp(const Line &L, int lane, int n, float radius, float ox, 
   }
 }
 
-// RVO2 linearProgram3 (no obstacle lines on the reference's live path).
-__device__ void lp3_warp(const Line &L, int lane, int n, int begin, float radius, float &rx, float &ry) {
+// RVO2 linearProgram3.  The projected problem keeps the first num_obst (obstacle) lines verbatim and replaces
+// lines num_obst .. i-1 by their bisectors with line i (num_obst = 0 on the reference's live path).
+template <int LPL>
+__device__ void lp3_warp(const Lines<LPL> &L, int lane, int n, int num_obst, int begin, float radius, float &rx,
+                         float &ry) {
   float distance = 0.0f;
   for (int i = begin; i < n; ++i) {
-    const float pix = __shfl_sync(FULL, L.px, i), piy = __shfl_sync(FULL, L.py, i);
-    const float dix = __shfl_sync(FULL, L.dx, i), diy = __shfl_sync(FULL, L.dy, i);
+    float pix, piy, dix, diy;
+    bcast_line<LPL>(L, i, pix, piy, dix, diy);
     if (det2(dix, diy, pix - rx, piy - ry) > distance) {
-      Line P;
-      bool valid = lane < i;
-      const float d = det2(dix, diy, L.dx, L.dy);
-      if (fabsf(d) <= RVO_EPSILON) {
-        if (dot2(dix, diy, L.dx, L.dy) > 0.0f) valid = false;
-        P.px = 0.5f * (pix + L.px);
-        P.py = 0.5f * (piy + L.py);
-      } else {
-        const float t = det2(L.dx, L.dy, pix - L.px, piy - L.py) / d;
-        P.px = pix + t * dix;
-        P.py = piy + t * diy;
+      Lines<LPL> P;
+      unsigned vm[LPL];
+#pragma unroll
+      for (int c = 0; c < LPL; ++c) {
+        const Line &M = L.l[c];
+        const int idx = lane + 32 * c;
+        bool valid = idx < i;
+        const float d = det2(dix, diy, M.dx, M.dy);
+        if (fabsf(d) <= RVO_EPSILON) {
+          if (dot2(dix, diy, M.dx, M.dy) > 0.0f) valid = false;
+          P.l[c].px = 0.5f * (pix + M.px);
+          P.l[c].py = 0.5f * (piy + M.py);
+        } else {
+          const float t = det2(M.dx, M.dy, pix - M.px, piy - M.py) / d;
+          P.l[c].px = pix + t * dix;
+          P.l[c].py = piy + t * diy;
+        }
+        const float ddx = M.dx - dix, ddy = M.dy - diy;
+        const float inv = 1.0f / sqrtf(dot2(ddx, ddy, ddx, ddy));
+        P.l[c].dx = ddx * inv;
+        P.l[c].dy = ddy * inv;
+        if (LPL > 1 && idx < num_obst) {   // std::vector<Line> projLines(lines.begin(), lines.begin() + numObstLines)
+          P.l[c] = M;
+          valid = true;
+        }
+        vm[c] = __ballot_sync(FULL, valid);
       }
-      const float ddx = L.dx - dix, ddy = L.dy - diy;
-      const float inv = 1.0f / sqrtf(dot2(ddx, ddy, ddx, ddy));
-      P.dx = ddx * inv;
-      P.dy = ddy * inv;
-      const unsigned vm = __ballot_sync(FULL, valid);
-      const int m = __popc(vm);
-      int src = (int)__fns(vm, 0, lane + 1);   // lane k takes the k-th surviving line (order kept)
-      if (lane >= m) src = lane;
-      Line Q;
-      Q.px = __shfl_sync(FULL, P.px, src);
-      Q.py = __shfl_sync(FULL, P.py, src);
-      Q.dx = __shfl_sync(FULL, P.dx, src);
-      Q.dy = __shfl_sync(FULL, P.dy, src);
+      int m = 0;
+#pragma unroll
+      for (int c = 0; c < LPL; ++c) m += __popc(vm[c]);
+      Lines<LPL> Q;
+      if (LPL == 1) {
+        int src = (int)__fns(vm[0], 0, lane + 1);   // lane k takes the k-th surviving line (order kept)
+        if (lane >= m) src = lane;
+        Q.l[0].px = __shfl_sync(FULL, P.l[0].px, src);
+        Q.l[0].py = __shfl_sync(FULL, P.l[0].py, src);
+        Q.l[0].dx = __shfl_sync(FULL, P.l[0].dx, src);
+        Q.l[0].dy = __shfl_sync(FULL, P.l[0].dy, src);
+      } else {
+        const int m0 = __popc(vm[0]);
+#pragma unroll
+        for (int c = 0; c < LPL; ++c) {
+          const int t = lane + 32 * c;                   // target index: the t-th surviving line
+          int sc = 0, sl = lane;
+          if (t < m0) { sc = 0; sl = (int)__fns(vm[0], 0, t + 1); }
+          else if (t < m) { sc = 1; sl = (int)__fns(vm[LPL - 1], 0, t - m0 + 1); }
+          const float a0 = __shfl_sync(FULL, P.l[0].px, sl), a1 = __shfl_sync(FULL, P.l[LPL - 1].px, sl);
+          const float b0 = __shfl_sync(FULL, P.l[0].py, sl), b1 = __shfl_sync(FULL, P.l[LPL - 1].py, sl);
+          const float c0 = __shfl_sync(FULL, P.l[0].dx, sl), c1 = __shfl_sync(FULL, P.l[LPL - 1].dx, sl);
+          const float d0 = __shfl_sync(FULL, P.l[0].dy, sl), d1 = __shfl_sync(FULL, P.l[LPL - 1].dy, sl);
+          Q.l[c].px = sc ? a1 : a0; Q.l[c].py = sc ? b1 : b0; Q.l[c].dx = sc ? c1 : c0; Q.l[c].dy = sc ? d1 : d0;
+        }
+      }
       const float tx = rx, ty = ry;
-      if (lp2_warp(Q, lane, m, radius, -diy, dix, true, rx, ry) < m) {
+      if (lp2_warp<LPL>(Q, lane, m, radius, -diy, dix, true, rx, ry) < m) {
         rx = tx;
         ry = ty;
       }
@@ -158,13 +222,287 @@ __device__ void lp3_warp(const Line &L, int lane, int n, int begin, float radius
   }
 }
 
+// ---- ORCA obstacle half-planes: RVO2 Agent::computeNeighbors (obstacle part) + the obstacle
+//      section of Agent::computeNewVelocity, one warp per agent.  The episode's obstacle vertices are staged in
+//      shared memory by the block; every lane tests two of them, the visible ones in range are ranked by
+//      (distSq, RVO2's kd-tree visiting order), lane r builds the candidate line of neighbour r, and the
+//      sequential "already covered by an earlier obstacle line" rule is resolved with one ballot per neighbour.
+struct ObstV {                      // = ebc_obst_vertex, 48 bytes
+  float px, py, ux, uy;
+  short next, prev, convex, pad0;
+  unsigned long long anc, anc_left, pad1;
+};
+static_assert(sizeof(ObstV) == sizeof(ebc_obst_vertex), "obstacle record layout");
+constexpr int OBST_SCRATCH_FLOATS = 64 * 4 + 16;   // per warp: 64 lines (or 32 x 5 neighbour floats) + 64 sorted ids
+
+__device__ __forceinline__ float left_of(float ax, float ay, float bx, float by, float cx, float cy) {
+  return det2(ax - cx, ay - cy, bx - ax, by - ay);
+}
+__device__ __forceinline__ unsigned long long ballot64(bool p0, bool p1) {
+  return (unsigned long long)__ballot_sync(FULL, p0) | ((unsigned long long)__ballot_sync(FULL, p1) << 32);
+}
+__device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) {
+  const unsigned lo = __shfl_sync(FULL, (unsigned)v, src), hi = __shfl_sync(FULL, (unsigned)(v >> 32), src);
+  return (unsigned long long)lo | ((unsigned long long)hi << 32);
+}
+
+struct ObstCand {      // candidate line of one obstacle neighbour + what the cover test needs
+  Line ln;
+  float r1x, r1y, r2x, r2y;
+  bool creates;
+};
+
+// the body of the loop of Agent::computeNewVelocity for one obstacle neighbour (everything but "alreadyCovered")
+__device__ __forceinline__ void obstacle_candidate(const ObstV *so, int id, float px, float py, float vx, float vy,
+                                                   float radius, float inv_th, ObstCand &out) {
+  const ObstV &o1 = so[id];
+  const ObstV &o2 = so[o1.next];
+  const float r1x = o1.px - px, r1y = o1.py - py, r2x = o2.px - px, r2y = o2.py - py;
+  out.r1x = r1x; out.r1y = r1y; out.r2x = r2x; out.r2y = r2y;
+  out.creates = false;
+  out.ln.px = 0.0f; out.ln.py = 0.0f; out.ln.dx = 1.0f; out.ln.dy = 0.0f;
+  const float d1 = dot2(r1x, r1y, r1x, r1y), d2 = dot2(r2x, r2y, r2x, r2y);
+  const float rsq = radius * radius;
+  const float ovx = o2.px - o1.px, ovy = o2.py - o1.py;
+  const float s = dot2(-r1x, -r1y, ovx, ovy) / dot2(ovx, ovy, ovx, ovy);
+  const float qx = -r1x - s * ovx, qy = -r1y - s * ovy;
+  const float dline = dot2(qx, qy, qx, qy);
+  Line ln;
+  if (s < 0.0f && d1 <= rsq) {
+    if (o1.convex) {
+      const float inv = 1.0f / sqrtf(dot2(-r1y, r1x, -r1y, r1x));
+      ln.px = 0.0f; ln.py = 0.0f; ln.dx = -r1y * inv; ln.dy = r1x * inv;
+      out.ln = ln; out.creates = true;
+    }
+    return;
+  } else if (s > 1.0f && d2 <= rsq) {
+    if (o2.convex && det2(r2x, r2y, o2.ux, o2.uy) >= 0.0f) {
+      const float inv = 1.0f / sqrtf(dot2(-r2y, r2x, -r2y, r2x));
+      ln.px = 0.0f; ln.py = 0.0f; ln.dx = -r2y * inv; ln.dy = r2x * inv;
+      out.ln = ln; out.creates = true;
+    }
+    return;
+  } else if (s >= 0.0f && s < 1.0f && dline <= rsq) {
+    ln.px = 0.0f; ln.py = 0.0f; ln.dx = -o1.ux; ln.dy = -o1.uy;
+    out.ln = ln; out.creates = true;
+    return;
+  }
+  float llx, lly, rlx, rly;
+  int a1 = id, a2 = o1.next;     // obstacle1 / obstacle2 after the oblique-view reassignment
+  if (s < 0.0f && dline <= rsq) {
+    if (!o1.convex) return;
+    a2 = id;
+    const float leg1 = sqrtf(d1 - rsq);
+    const float inv = 1.0f / d1;
+    llx = (r1x * leg1 - r1y * radius) * inv; lly = (r1x * radius + r1y * leg1) * inv;
+    rlx = (r1x * leg1 + r1y * radius) * inv; rly = (-r1x * radius + r1y * leg1) * inv;
+  } else if (s > 1.0f && dline <= rsq) {
+    if (!o2.convex) return;
+    a1 = o1.next;
+    const float leg2 = sqrtf(d2 - rsq);
+    const float inv = 1.0f / d2;
+    llx = (r2x * leg2 - r2y * radius) * inv; lly = (r2x * radius + r2y * leg2) * inv;
+    rlx = (r2x * leg2 + r2y * radius) * inv; rly = (-r2x * radius + r2y * leg2) * inv;
+  } else {
+    if (o1.convex) {
+      const float leg1 = sqrtf(d1 - rsq);
+      const float inv = 1.0f / d1;
+      llx = (r1x * leg1 - r1y * radius) * inv; lly = (r1x * radius + r1y * leg1) * inv;
+    } else { llx = -o1.ux; lly = -o1.uy; }
+    if (o2.convex) {
+      const float leg2 = sqrtf(d2 - rsq);
+      const float inv = 1.0f / d2;
+      rlx = (r2x * leg2 + r2y * radius) * inv; rly = (-r2x * radius + r2y * leg2) * inv;
+    } else { rlx = o1.ux; rly = o1.uy; }
+  }
+  const ObstV &A1 = so[a1];
+  const ObstV &A2 = so[a2];
+  const ObstV &LN = so[A1.prev];
+  bool left_foreign = false, right_foreign = false;
+  if (A1.convex && det2(llx, lly, -LN.ux, -LN.uy) >= 0.0f) {
+    llx = -LN.ux; lly = -LN.uy;
+    left_foreign = true;
+  }
+  if (A2.convex && det2(rlx, rly, A2.ux, A2.uy) <= 0.0f) {
+    rlx = A2.ux; rly = A2.uy;
+    right_foreign = true;
+  }
+  const float lcx = inv_th * (A1.px - px), lcy = inv_th * (A1.py - py);
+  const float rcx = inv_th * (A2.px - px), rcy = inv_th * (A2.py - py);
+  const float cvx = rcx - lcx, cvy = rcy - lcy;
+  const bool same = a1 == a2;
+  const float t = same ? 0.5f : dot2(vx - lcx, vy - lcy, cvx, cvy) / dot2(cvx, cvy, cvx, cvy);
+  const float tl = dot2(vx - lcx, vy - lcy, llx, lly);
+  const float tr = dot2(vx - rcx, vy - rcy, rlx, rly);
+  if ((t < 0.0f && tl < 0.0f) || (same && tl < 0.0f && tr < 0.0f)) {
+    const float wx = vx - lcx, wy = vy - lcy;
+    const float inv = 1.0f / sqrtf(dot2(wx, wy, wx, wy));
+    const float ux = wx * inv, uy = wy * inv;
+    ln.dx = uy; ln.dy = -ux;
+    ln.px = lcx + radius * inv_th * ux; ln.py = lcy + radius * inv_th * uy;
+    out.ln = ln; out.creates = true;
+    return;
+  } else if (t > 1.0f && tr < 0.0f) {
+    const float wx = vx - rcx, wy = vy - rcy;
+    const float inv = 1.0f / sqrtf(dot2(wx, wy, wx, wy));
+    const float ux = wx * inv, uy = wy * inv;
+    ln.dx = uy; ln.dy = -ux;
+    ln.px = rcx + radius * inv_th * ux; ln.py = rcy + radius * inv_th * uy;
+    out.ln = ln; out.creates = true;
+    return;
+  }
+  float dcut, dleft, dright;
+  if (t < 0.0f || t > 1.0f || same) dcut = INFINITY;
+  else { const float ax = vx - (lcx + t * cvx), ay = vy - (lcy + t * cvy); dcut = dot2(ax, ay, ax, ay); }
+  if (tl < 0.0f) dleft = INFINITY;
+  else { const float ax = vx - (lcx + tl * llx), ay = vy - (lcy + tl * lly); dleft = dot2(ax, ay, ax, ay); }
+  if (tr < 0.0f) dright = INFINITY;
+  else { const float ax = vx - (rcx + tr * rlx), ay = vy - (rcy + tr * rly); dright = dot2(ax, ay, ax, ay); }
+  if (dcut <= dleft && dcut <= dright) {
+    ln.dx = -A1.ux; ln.dy = -A1.uy;
+    ln.px = lcx + radius * inv_th * -ln.dy; ln.py = lcy + radius * inv_th * ln.dx;
+    out.ln = ln; out.creates = true;
+  } else if (dleft <= dright) {
+    if (left_foreign) return;
+    ln.dx = llx; ln.dy = lly;
+    ln.px = lcx + radius * inv_th * -ln.dy; ln.py = lcy + radius * inv_th * ln.dx;
+    out.ln = ln; out.creates = true;
+  } else {
+    if (right_foreign) return;
+    ln.dx = -rlx; ln.dy = -rly;
+    ln.px = rcx + radius * inv_th * -ln.dy; ln.py = rcy + radius * inv_th * ln.dx;
+    out.ln = ln; out.creates = true;
+  }
+}
+
+// Obstacle lines of one agent into linebuf[0 .. n) (shared memory, this warp's); returns n = numObstLines.
+// `ids` = this warp's 64 bytes for the sorted neighbour list.
+__device__ int obstacle_lines_warp(const ObstV *so, int V, int lane, float px, float py, float vx, float vy, float radius,
+                                   float max_speed, float th_obst, Line *linebuf, unsigned char *ids) {
+  const float rr = th_obst * max_speed + radius;
+  const float range_sq = rr * rr;
+  float d[2];
+  bool vis[2], lok[2], nearl[2];
+  unsigned long long anc[2], ancl[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int v = lane + 32 * c;
+    d[c] = INFINITY; vis[c] = false; lok[c] = false; nearl[c] = false; anc[c] = 0ull; ancl[c] = 0ull;
+    if (v < V) {
+      const ObstV &o1 = so[v];
+      const ObstV &o2 = so[o1.next];
+      const float al = left_of(o1.px, o1.py, o2.px, o2.py, px, py);
+      const float ex = o2.px - o1.px, ey = o2.py - o1.py;
+      const float dsl = al * al / dot2(ex, ey, ex, ey);
+      nearl[c] = al >= 0.0f;                 // the kd-tree descends into the left child first
+      lok[c] = dsl < range_sq;               // queryObstacleTreeRecursive crosses this node's line
+      vis[c] = al < 0.0f;                    // agent on the right side: it can see the edge
+      anc[c] = o1.anc; ancl[c] = o1.anc_left;
+      // distSqPointLineSegment(o1, o2, p)
+      const float r = dot2(px - o1.px, py - o1.py, ex, ey) / dot2(ex, ey, ex, ey);
+      if (r < 0.0f) d[c] = dot2(px - o1.px, py - o1.py, px - o1.px, py - o1.py);
+      else if (r > 1.0f) d[c] = dot2(px - o2.px, py - o2.py, px - o2.px, py - o2.py);
+      else { const float qx = px - (o1.px + r * ex), qy = py - (o1.py + r * ey); d[c] = dot2(qx, qy, qx, qy); }
+    }
+  }
+  const unsigned long long side_l = ballot64(nearl[0], nearl[1]);
+  const unsigned long long line_ok = ballot64(lok[0], lok[1]);
+  bool sel[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    // reached by the traversal: every ancestor whose FAR subtree holds this node has its line within range
+    const unsigned long long far_anc = anc[c] & (ancl[c] ^ side_l);
+    sel[c] = vis[c] && lok[c] && ((far_anc & ~line_ok) == 0ull) && d[c] < range_sq;
+  }
+  const unsigned long long selm = ballot64(sel[0], sel[1]);
+  const int M = __popcll(selm);
+  if (M == 0) return 0;
+  // rank by (distSq, visiting order of the near-first in-order traversal)
+  int rank[2] = {0, 0};
+  unsigned long long m = selm;
+  while (m) {
+    const int k = __ffsll((long long)m) - 1;
+    m &= m - 1;
+    const int kl = k & 31;
+    const float dk = k < 32 ? __shfl_sync(FULL, d[0], kl) : __shfl_sync(FULL, d[1], kl);
+    const unsigned long long ak = k < 32 ? shfl64(anc[0], kl) : shfl64(anc[1], kl);
+    const unsigned long long alk = k < 32 ? shfl64(ancl[0], kl) : shfl64(ancl[1], kl);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int x = lane + 32 * c;
+      bool before;                            // k is visited before x
+      if (x == k) before = false;
+      else if ((anc[c] >> k) & 1ull) before = (((ancl[c] ^ side_l) >> k) & 1ull) != 0ull;      // k above x: x in k's far subtree
+      else if ((ak >> x) & 1ull) before = (((alk ^ side_l) >> x) & 1ull) == 0ull;             // x above k: k in x's near subtree
+      else {
+        const unsigned long long diff = (ancl[c] ^ alk) & anc[c] & ak;                        // the lowest common ancestor
+        before = ((alk ^ side_l) & diff) == 0ull;                                             // k on its near side
+      }
+      rank[c] += (dk < d[c] || (dk == d[c] && before)) ? 1 : 0;
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+    if (sel[c]) ids[rank[c]] = (unsigned char)(lane + 32 * c);
+  __syncwarp();
+  // candidate lines: lane r (and r + 32) takes neighbour r
+  const float inv_th = 1.0f / th_obst;
+  ObstCand cand[2];
+  bool accepted[2] = {false, false};
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int r = lane + 32 * c;
+    cand[c].creates = false;
+    cand[c].r1x = cand[c].r1y = cand[c].r2x = cand[c].r2y = 0.0f;
+    cand[c].ln.px = cand[c].ln.py = 0.0f; cand[c].ln.dx = 1.0f; cand[c].ln.dy = 0.0f;
+    if (r < M) obstacle_candidate(so, ids[r], px, py, vx, vy, radius, inv_th, cand[c]);
+  }
+  // "already covered by a previously constructed obstacle ORCA line": sequential over the neighbours
+  for (int i = 0; i < M; ++i) {
+    const int il = i & 31;
+    float r1x, r1y, r2x, r2y;
+    if (i < 32) {
+      r1x = __shfl_sync(FULL, cand[0].r1x, il); r1y = __shfl_sync(FULL, cand[0].r1y, il);
+      r2x = __shfl_sync(FULL, cand[0].r2x, il); r2y = __shfl_sync(FULL, cand[0].r2y, il);
+    } else {
+      r1x = __shfl_sync(FULL, cand[1].r1x, il); r1y = __shfl_sync(FULL, cand[1].r1y, il);
+      r2x = __shfl_sync(FULL, cand[1].r2x, il); r2y = __shfl_sync(FULL, cand[1].r2y, il);
+    }
+    bool cov = false;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const Line &J = cand[c].ln;
+      const bool hit = det2(inv_th * r1x - J.px, inv_th * r1y - J.py, J.dx, J.dy) - inv_th * radius >= -RVO_EPSILON &&
+                       det2(inv_th * r2x - J.px, inv_th * r2y - J.py, J.dx, J.dy) - inv_th * radius >= -RVO_EPSILON;
+      cov = cov || (accepted[c] && hit);     // accepted lines all belong to neighbours before i
+    }
+    const bool covered = __any_sync(FULL, cov);
+    if (!covered) {
+      if (i < 32) { if (lane == il && cand[0].creates) accepted[0] = true; }
+      else { if (lane == il && cand[1].creates) accepted[1] = true; }
+    }
+  }
+  // compact the accepted lines, in neighbour order, to linebuf[0 .. n)
+  const unsigned a0 = __ballot_sync(FULL, accepted[0]), a1 = __ballot_sync(FULL, accepted[1]);
+  const unsigned below = (1u << lane) - 1u;
+  if (accepted[0]) linebuf[__popc(a0 & below)] = cand[0].ln;
+  if (accepted[1]) linebuf[__popc(a0) + __popc(a1 & below)] = cand[1].ln;
+  __syncwarp();
+  return __popc(a0) + __popc(a1);
+}
+
 // One RVO2 agent step by one warp.  Candidates (the other agents, in the reference's list
-// order) sit two per lane: index lane and lane + 32.  `scratch` = 32*5 floats of this warp.
+// order) sit two per lane: index lane and lane + 32.  `scratch` = this warp's shared memory: 32*5 floats, or
+// OBST_SCRATCH_FLOATS with obstacle half-planes (so / V: the episode's obstacle vertices in shared memory).
+template <bool OBST>
 __device__ void orca_agent_warp(int lane, float px, float py, float vx, float vy, float radius, float max_speed,
                                 float prefx, float prefy, const float (&cpx)[2], const float (&cpy)[2],
                                 const float (&cvx)[2], const float (&cvy)[2], const float (&crad)[2],
                                 const bool (&cval)[2], int n_chunks, float neighbor_dist, int max_nb,
-                                float time_horizon, float time_step, float *scratch, float &outx, float &outy) {
+                                float time_horizon, float time_step, float *scratch, float &outx, float &outy,
+                                const ObstV *so = nullptr, int V = 0, float th_obst = 0.0f) {
+  constexpr int LPL = OBST ? 2 : 1;
   // Agent::insertAgentNeighbor == keep the max_nb smallest (distSq, arrival index) below range
   float d[2];
   unsigned vmask[2] = {0u, 0u};
@@ -194,7 +532,7 @@ __device__ void orca_agent_warp(int lane, float px, float py, float vx, float vy
     }
   }
   const int total = __popc(vmask[0]) + __popc(vmask[1]);
-  const int cnt = total < max_nb ? total : max_nb;
+  int cnt = total < max_nb ? total : max_nb;
   __syncwarp();
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
@@ -206,7 +544,7 @@ __device__ void orca_agent_warp(int lane, float px, float py, float vx, float vy
     }
   }
   __syncwarp();
-  Line L = {0.0f, 0.0f, 1.0f, 0.0f};
+  Line A = {0.0f, 0.0f, 1.0f, 0.0f};      // agent line `lane`
   if (lane < cnt) {
     const float *s = scratch + lane * 5;
     const float rpx = s[0] - px, rpy = s[1] - py;
@@ -224,8 +562,8 @@ __device__ void orca_agent_warp(int lane, float px, float py, float vx, float vy
         const float wlen = sqrtf(wlen_sq);
         const float inv = 1.0f / wlen;
         const float uwx = wx * inv, uwy = wy * inv;
-        L.dx = uwy;
-        L.dy = -uwx;
+        A.dx = uwy;
+        A.dy = -uwx;
         const float sc = R * inv_th - wlen;
         ux = sc * uwx;
         uy = sc * uwy;
@@ -233,15 +571,15 @@ __device__ void orca_agent_warp(int lane, float px, float py, float vx, float vy
         const float leg = sqrtf(dist_sq - R_sq);
         const float inv = 1.0f / dist_sq;
         if (det2(rpx, rpy, wx, wy) > 0.0f) {
-          L.dx = (rpx * leg - rpy * R) * inv;
-          L.dy = (rpx * R + rpy * leg) * inv;
+          A.dx = (rpx * leg - rpy * R) * inv;
+          A.dy = (rpx * R + rpy * leg) * inv;
         } else {
-          L.dx = (-(rpx * leg + rpy * R)) * inv;
-          L.dy = (-(-rpx * R + rpy * leg)) * inv;
+          A.dx = (-(rpx * leg + rpy * R)) * inv;
+          A.dy = (-(-rpx * R + rpy * leg)) * inv;
         }
-        const float dp2 = dot2(rvx, rvy, L.dx, L.dy);
-        ux = dp2 * L.dx - rvx;
-        uy = dp2 * L.dy - rvy;
+        const float dp2 = dot2(rvx, rvy, A.dx, A.dy);
+        ux = dp2 * A.dx - rvx;
+        uy = dp2 * A.dy - rvy;
       }
     } else {
       const float inv_ts = 1.0f / time_step;
@@ -249,19 +587,41 @@ __device__ void orca_agent_warp(int lane, float px, float py, float vx, float vy
       const float wlen = sqrtf(dot2(wx, wy, wx, wy));
       const float inv = 1.0f / wlen;
       const float uwx = wx * inv, uwy = wy * inv;
-      L.dx = uwy;
-      L.dy = -uwx;
+      A.dx = uwy;
+      A.dy = -uwx;
       const float sc = R * inv_ts - wlen;
       ux = sc * uwx;
       uy = sc * uwy;
     }
-    L.px = vx + 0.5f * ux;
-    L.py = vy + 0.5f * uy;
+    A.px = vx + 0.5f * ux;
+    A.py = vy + 0.5f * uy;
   }
   __syncwarp();
+  Lines<LPL> L;
+  int num_obst = 0;
+  if (OBST) {
+    // obstacle lines first (Agent::computeNewVelocity), then the agent lines; at most 64 lines in all (the farthest
+    // agent neighbours are dropped beyond that -- RVO2 itself has no such bound)
+    Line *linebuf = reinterpret_cast<Line *>(scratch);
+    unsigned char *ids = reinterpret_cast<unsigned char *>(scratch + 64 * 4);
+    num_obst = obstacle_lines_warp(so, V, lane, px, py, vx, vy, radius, max_speed, th_obst, linebuf, ids);
+    if (cnt > 64 - num_obst) cnt = 64 - num_obst;
+    if (lane < cnt) linebuf[num_obst + lane] = A;
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < LPL; ++c) {
+      const int idx = lane + 32 * c;
+      const Line Z = {0.0f, 0.0f, 1.0f, 0.0f};
+      L.l[c] = idx < num_obst + cnt ? linebuf[idx] : Z;
+    }
+    __syncwarp();
+  } else {
+    L.l[0] = A;
+  }
+  const int n_lines = num_obst + cnt;
   float rx, ry;
-  const int fail = lp2_warp(L, lane, cnt, max_speed, prefx, prefy, false, rx, ry);
-  if (fail < cnt) lp3_warp(L, lane, cnt, fail, max_speed, rx, ry);
+  const int fail = lp2_warp<LPL>(L, lane, n_lines, max_speed, prefx, prefy, false, rx, ry);
+  if (fail < n_lines) lp3_warp<LPL>(L, lane, n_lines, num_obst, fail, max_speed, rx, ry);
   outx = rx;
   outy = ry;
 }
@@ -281,9 +641,21 @@ __device__ __forceinline__ void orca_self_params(float px, float py, float gx, f
   }
 }
 
+// Stage the episode's obstacle vertices in shared memory (16-byte words; the whole block takes part).
+__device__ __forceinline__ int stage_obstacles(const ebc_config &c, const ebc_state &st, int e, ObstV *so, int tid,
+                                               int nthreads) {
+  int V = st.obst_count[e];
+  V = V < 0 ? 0 : (V > c.max_obst ? c.max_obst : V);
+  const uint4 *src = reinterpret_cast<const uint4 *>(st.obst + (size_t)e * c.max_obst);
+  uint4 *dst = reinterpret_cast<uint4 *>(so);
+  for (int i = tid; i < V * 3; i += nthreads) dst[i] = src[i];
+  return V;
+}
+
 // Policy of human h of episode e, computed by one warp (env.py:392-405).
+template <bool OBST>
 __device__ void human_policy_warp(const ebc_config &c, const ebc_state &st, int e, int h, int H, int lane,
-                                  float *scratch, float &nvx, float &nvy) {
+                                  float *scratch, float &nvx, float &nvy, const ObstV *so = nullptr, int V = 0) {
   const int Hm = c.max_humans;
   const float4 *pv = reinterpret_cast<const float4 *>(st.hum_pv) + (size_t)e * Hm;
   const float4 *gr = reinterpret_cast<const float4 *>(st.hum_gr) + (size_t)e * Hm;
@@ -319,9 +691,9 @@ __device__ void human_policy_warp(const ebc_config &c, const ebc_state &st, int 
   }
   float r_self, prefx, prefy;
   orca_self_params(me_pv.x, me_pv.y, me_gr.x, me_gr.y, me_gr.w, c.orca_safety_space, r_self, prefx, prefy);
-  orca_agent_warp(lane, me_pv.x, me_pv.y, me_pv.z, me_pv.w, r_self, me_gr.z, prefx, prefy, cpx, cpy, cvx, cvy,
-                  crad, cval, n_chunks, c.orca_neighbor_dist, c.orca_max_neighbors, c.orca_time_horizon,
-                  (float)c.time_step, scratch, nvx, nvy);
+  orca_agent_warp<OBST>(lane, me_pv.x, me_pv.y, me_pv.z, me_pv.w, r_self, me_gr.z, prefx, prefy, cpx, cpy, cvx, cvy,
+                        crad, cval, n_chunks, c.orca_neighbor_dist, c.orca_max_neighbors, c.orca_time_horizon,
+                        (float)c.time_step, scratch, nvx, nvy, so, V, c.orca_time_horizon_obst);
 }
 
 __global__ void __launch_bounds__(EBC_THREADS) orca_kernel(const ebc_config c, const ebc_state st) {
@@ -333,18 +705,26 @@ __global__ void __launch_bounds__(EBC_THREADS) orca_kernel(const ebc_config c, c
   const int H = st.hum_count[e];
   if (h >= H) return;
   float nvx, nvy;
-  human_policy_warp(c, st, e, h, H, lane, scratch[warp], nvx, nvy);
+  human_policy_warp<false>(c, st, e, h, H, lane, scratch[warp], nvx, nvy);
   if (lane == 0)
     reinterpret_cast<float2 *>(st.hum_nv)[(size_t)e * c.max_humans + h] = make_float2(nvx, nvy);
 }
 
-// Robot as ORCA agent 0 over humans + static discs (rl/train.py:99-143).
-__global__ void __launch_bounds__(EBC_THREADS) robot_orca_kernel(const ebc_config c, const ebc_state st,
-                                                                 double safety, double *out) {
-  __shared__ float scratch[EBC_WARPS_PER_BLOCK][32 * 5];
+// Robot as ORCA agent 0 over humans + static discs (rl/train.py:99-143).  WPB warps (= episodes) per block; with
+// obstacle half-planes one episode per block, its obstacle vertices staged in shared memory.
+template <bool OBST, int WPB>
+__global__ void __launch_bounds__(WPB * 32) robot_orca_kernel(const ebc_config c, const ebc_state st,
+                                                              double safety, double *out) {
+  __shared__ float scratch[WPB][OBST ? OBST_SCRATCH_FLOATS : 32 * 5];
+  __shared__ __align__(16) ObstV so[OBST ? 64 : 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int e = blockIdx.x * EBC_WARPS_PER_BLOCK + warp;
+  const int e = blockIdx.x * WPB + warp;
   if (e >= c.n_episodes) return;
+  int V = 0;
+  if (OBST) {
+    V = stage_obstacles(c, st, e, so, threadIdx.x, WPB * 32);
+    __syncthreads();
+  }
   const int Hm = c.max_humans, Sm = c.max_statics;
   const int H = st.hum_count[e], S = st.stat_count[e];
   const float4 *pv = reinterpret_cast<const float4 *>(st.hum_pv) + (size_t)e * Hm;
@@ -373,9 +753,9 @@ __global__ void __launch_bounds__(EBC_THREADS) robot_orca_kernel(const ebc_confi
   const float4 rg = reinterpret_cast<const float4 *>(st.rob_gr)[e];
   float r_self, prefx, prefy, vx, vy;
   orca_self_params(rp.x, rp.y, rg.x, rg.y, rg.w, safety, r_self, prefx, prefy);
-  orca_agent_warp(lane, rp.x, rp.y, rp.z, rp.w, r_self, rg.z, prefx, prefy, cpx, cpy, cvx, cvy, crad, cval,
-                  (H + S + 31) >> 5, c.orca_neighbor_dist, c.orca_max_neighbors, c.orca_time_horizon,
-                  (float)c.time_step, scratch[warp], vx, vy);
+  orca_agent_warp<OBST>(lane, rp.x, rp.y, rp.z, rp.w, r_self, rg.z, prefx, prefy, cpx, cpy, cvx, cvy, crad, cval,
+                        (H + S + 31) >> 5, c.orca_neighbor_dist, c.orca_max_neighbors, c.orca_time_horizon,
+                        (float)c.time_step, scratch[warp], vx, vy, so, V, c.orca_time_horizon_obst);
   if (lane == 0) {
     out[(size_t)e * 2] = (double)vx;
     out[(size_t)e * 2 + 1] = (double)vy;
@@ -396,6 +776,7 @@ __device__ __forceinline__ double point_to_segment_dist0(double x1, double y1, d
 struct Outcome {
   double dmin[3];
   double end_x, end_y, dist_to_goal, reward;
+  double min_dist; // Danger.min_dist (reward.py:138-166): the dmin of the type that triggered it
   double cs, sn;   // cos / sin of the robot's heading after the action (non-holonomic), computed once per action
   int done, event;
 };
@@ -435,6 +816,7 @@ __device__ __forceinline__ void classify_outcome(const ebc_config &c, const floa
   const double goal_reward = c.has_max_goal_distance ? 1.0 - dist / c.max_goal_distance : 0.0;
   double reward = c.new_reward ? goal_reward : 0.0;
   int done, ev;
+  o.min_dist = 0.0;
   if (gt >= c.time_limit) { done = 1; ev = EBC_EV_TIMEOUT; }
   else if (coll[EBC_CHILD]) { reward += c.collision_penalty_child; done = 1; ev = EBC_EV_COLLISION_CHILD; }
   else if (coll[EBC_BICYCLE]) { reward += c.collision_penalty_bicycle; done = 1; ev = EBC_EV_COLLISION_BICYCLE; }
@@ -453,12 +835,15 @@ __device__ __forceinline__ void classify_outcome(const ebc_config &c, const floa
     done = 1; ev = EBC_EV_REACH_GOAL;
   } else if (o.dmin[EBC_CHILD] < c.discomfort_dist_child) {
     reward = (o.dmin[EBC_CHILD] - c.discomfort_dist_child) * c.discomfort_penalty_factor_child * dt;
+    o.min_dist = o.dmin[EBC_CHILD];
     done = 0; ev = EBC_EV_DANGER;
   } else if (o.dmin[EBC_BICYCLE] < c.discomfort_dist_bicycle) {
     reward = (o.dmin[EBC_BICYCLE] - c.discomfort_dist_bicycle) * c.discomfort_penalty_factor_bicycle * dt;
+    o.min_dist = o.dmin[EBC_BICYCLE];
     done = 0; ev = EBC_EV_DANGER;
   } else if (o.dmin[EBC_ADULT] < c.discomfort_dist_adult) {
     reward = (o.dmin[EBC_ADULT] - c.discomfort_dist_adult) * c.discomfort_penalty_factor_adult * dt;
+    o.min_dist = o.dmin[EBC_ADULT];
     done = 0; ev = EBC_EV_DANGER;
   } else if (c.robot_kinematics != EBC_KIN_HOLONOMIC && fabs(a1) > 0.0 && c.rotation_penalty_factor != 0.0) {
     reward = fabs(a1) * c.rotation_penalty_factor;
@@ -863,7 +1248,8 @@ select_kernel(const ebc_config c, const ebc_state st, const double *__restrict__
 // Commit of one episode by one warp (env.py:340-386,424-466; agent.py:202-228).
 __device__ void commit_episode_warp(const ebc_config &c, const ebc_state &st, int e, int lane,
                                     const double *actions, const int32_t *action_idx, const double *action,
-                                    double *reward, uint8_t *done, uint8_t *event, double *dmin, double *dist_to_goal) {
+                                    double *reward, uint8_t *done, uint8_t *event, double *dmin, double *dist_to_goal,
+                                    const ebc_stats &sx) {
   const int Hm = c.max_humans;
   const int H = st.hum_count[e];
   double a0, a1;
@@ -921,6 +1307,21 @@ __device__ void commit_episode_warp(const ebc_config &c, const ebc_state &st, in
     }
     reinterpret_cast<float4 *>(st.rob_pv)[e] = np;
     st.time[e] = gt + dt;
+    if (sx.alive) {   // the explorer's running statistics (explorer.py:33-94,189-193), one writer per episode
+      const double disc = sx.discount[e];
+      sx.cum_reward[e] += disc * o.reward;
+      sx.discount[e] = disc * pow(c.gamma, dt * (double)rg.z);
+      sx.steps[e] += 1;
+      if (o.event == EBC_EV_DANGER) {
+        sx.too_close[e] += 1;
+        sx.min_dist_sum[e] += o.min_dist;
+      }
+      if (o.done) {
+        sx.final_event[e] = (uint8_t)o.event;
+        sx.alive[e] = 0;
+        atomicSub(sx.alive_count, 1);
+      }
+    }
   }
 }
 
@@ -928,34 +1329,44 @@ __device__ void commit_episode_warp(const ebc_config &c, const ebc_state &st, in
 __global__ void __launch_bounds__(EBC_THREADS)
 step_kernel(const ebc_config c, const ebc_state st, const double *__restrict__ actions, const int32_t *action_idx,
             const double *action, const uint8_t *active, double *reward, uint8_t *done, uint8_t *event,
-            double *dmin, double *dist_to_goal) {
+            double *dmin, double *dist_to_goal, const ebc_stats sx) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.x * EBC_WARPS_PER_BLOCK + warp;
   if (e >= c.n_episodes) return;
   if (active && !active[e]) return;
-  commit_episode_warp(c, st, e, lane, actions, action_idx, action, reward, done, event, dmin, dist_to_goal);
+  commit_episode_warp(c, st, e, lane, actions, action_idx, action, reward, done, event, dmin, dist_to_goal, sx);
 }
 
 // K1 + K2 fused, block per episode: every warp solves humans' LPs from the untouched state,
 // the block synchronises, then warp 0 commits.  One launch per env step on the policy-free path.
+// OBST: with ORCA obstacle half-planes (the episode's obstacle vertices staged in shared memory next to the
+// neighbour scratch); COMMIT = false is K1 alone in that block-per-episode shape (ebc_orca with obstacles).
+template <bool OBST, bool COMMIT>
 __global__ void __launch_bounds__(512)
 orca_step_kernel(const ebc_config c, const ebc_state st, const double *__restrict__ actions,
                  const int32_t *action_idx, const double *action, const uint8_t *active, double *reward,
-                 uint8_t *done, uint8_t *event, double *dmin, double *dist_to_goal) {
-  __shared__ float scratch[16][32 * 5];
+                 uint8_t *done, uint8_t *event, double *dmin, double *dist_to_goal, const ebc_stats sx) {
+  __shared__ float scratch[16][OBST ? OBST_SCRATCH_FLOATS : 32 * 5];
+  __shared__ __align__(16) ObstV so[OBST ? 64 : 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
   const int e = blockIdx.x;
   if (active && !active[e]) return;
   const int H = st.hum_count[e];
+  int V = 0;
+  if (OBST) {
+    V = stage_obstacles(c, st, e, so, threadIdx.x, blockDim.x);
+    __syncthreads();
+  }
   for (int h = warp; h < H; h += n_warps) {
     float nvx, nvy;
-    human_policy_warp(c, st, e, h, H, lane, scratch[warp], nvx, nvy);
+    human_policy_warp<OBST>(c, st, e, h, H, lane, scratch[warp], nvx, nvy, so, V);
     if (lane == 0)
       reinterpret_cast<float2 *>(st.hum_nv)[(size_t)e * c.max_humans + h] = make_float2(nvx, nvy);
   }
+  if (!COMMIT) return;
   __syncthreads();   // all reads of the old state are done; hum_nv is visible block-wide
   if (warp == 0)
-    commit_episode_warp(c, st, e, lane, actions, action_idx, action, reward, done, event, dmin, dist_to_goal);
+    commit_episode_warp(c, st, e, lane, actions, action_idx, action, reward, done, event, dmin, dist_to_goal, sx);
 }
 
 // env.reset from a device-resident scene pool; one warp per episode, lanes copy 16-byte words.
@@ -979,6 +1390,12 @@ reset_kernel(const ebc_config c, const ebc_state st, const ebc_state pool, int p
     reinterpret_cast<float4 *>(st.stat)[(size_t)e * Sm + k] = reinterpret_cast<const float4 *>(pool.stat)[(size_t)q * Sm + k];
   for (int j = lane; j < Rm; j += 32)
     reinterpret_cast<short4 *>(st.rect)[(size_t)e * Rm + j] = reinterpret_cast<const short4 *>(pool.rect)[(size_t)q * Rm + j];
+  if (c.max_obst > 0 && st.obst && pool.obst && st.obst_count && pool.obst_count) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(pool.obst + (size_t)q * c.max_obst);
+    uint4 *dst = reinterpret_cast<uint4 *>(st.obst + (size_t)e * c.max_obst);
+    for (int i = lane; i < c.max_obst * 3; i += 32) dst[i] = src[i];
+    if (lane == 0) st.obst_count[e] = pool.obst_count[q];
+  }
   if (lane == 0) {
     st.hum_count[e] = pool.hum_count[q];
     st.stat_count[e] = pool.stat_count[q];
@@ -1137,7 +1554,17 @@ int ebc_launch_reset(ebc_sim *s, const ebc_state *pool, int pool_size, const int
   return ebc_check_launch(s, "reset_kernel");
 }
 
+static int fused_warps(const ebc_sim *s) {
+  int warps = s->cfg.max_humans < 16 ? s->cfg.max_humans : 16;
+  return warps < 1 ? 1 : warps;
+}
+
 int ebc_launch_orca(ebc_sim *s, cudaStream_t stream) {
+  if (s->cfg.orca_obstacles) {   // block per episode: the obstacle vertices are staged once per block
+    orca_step_kernel<true, false><<<s->cfg.n_episodes, fused_warps(s) * 32, 0, stream>>>(
+        s->cfg, s->st, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ebc_stats{});
+    return ebc_check_launch(s, "orca_step_kernel<obstacles, no commit>");
+  }
   const long long warps = (long long)s->cfg.n_episodes * s->cfg.max_humans;
   const int blocks = (int)((warps + EBC_WARPS_PER_BLOCK - 1) / EBC_WARPS_PER_BLOCK);
   orca_kernel<<<blocks, EBC_THREADS, 0, stream>>>(s->cfg, s->st);
@@ -1145,8 +1572,12 @@ int ebc_launch_orca(ebc_sim *s, cudaStream_t stream) {
 }
 
 int ebc_launch_robot_orca(ebc_sim *s, double safety, double *out, cudaStream_t stream) {
+  if (s->cfg.orca_obstacles) {
+    robot_orca_kernel<true, 1><<<s->cfg.n_episodes, 32, 0, stream>>>(s->cfg, s->st, safety, out);
+    return ebc_check_launch(s, "robot_orca_kernel<obstacles>");
+  }
   const int blocks = (s->cfg.n_episodes + EBC_WARPS_PER_BLOCK - 1) / EBC_WARPS_PER_BLOCK;
-  robot_orca_kernel<<<blocks, EBC_THREADS, 0, stream>>>(s->cfg, s->st, safety, out);
+  robot_orca_kernel<false, EBC_WARPS_PER_BLOCK><<<blocks, EBC_THREADS, 0, stream>>>(s->cfg, s->st, safety, out);
   return ebc_check_launch(s, "robot_orca_kernel");
 }
 
@@ -1188,15 +1619,20 @@ int ebc_launch_select(ebc_sim *s, const double *reward, const float *values, dou
 int ebc_launch_step(ebc_sim *s, bool fused_orca, const int32_t *action_idx, const double *action,
                     const uint8_t *active, double *reward, uint8_t *done, uint8_t *event, double *dmin,
                     double *dist_to_goal, cudaStream_t stream) {
+  ebc_stats sx = s->stats;                      // all-null when unbound
+  if (!active && sx.alive) active = sx.alive;   // the bound alive[] is the mask (ebc_bind_stats)
   if (fused_orca) {
-    int warps = s->cfg.max_humans < 16 ? s->cfg.max_humans : 16;
-    if (warps < 1) warps = 1;
-    orca_step_kernel<<<s->cfg.n_episodes, warps * 32, 0, stream>>>(s->cfg, s->st, s->d_actions, action_idx, action,
-                                                                  active, reward, done, event, dmin, dist_to_goal);
+    const int threads = fused_warps(s) * 32;
+    if (s->cfg.orca_obstacles)
+      orca_step_kernel<true, true><<<s->cfg.n_episodes, threads, 0, stream>>>(s->cfg, s->st, s->d_actions, action_idx, action,
+                                                                             active, reward, done, event, dmin, dist_to_goal, sx);
+    else
+      orca_step_kernel<false, true><<<s->cfg.n_episodes, threads, 0, stream>>>(s->cfg, s->st, s->d_actions, action_idx, action,
+                                                                              active, reward, done, event, dmin, dist_to_goal, sx);
     return ebc_check_launch(s, "orca_step_kernel");
   }
   const int blocks = (s->cfg.n_episodes + EBC_WARPS_PER_BLOCK - 1) / EBC_WARPS_PER_BLOCK;
   step_kernel<<<blocks, EBC_THREADS, 0, stream>>>(s->cfg, s->st, s->d_actions, action_idx, action, active, reward,
-                                                  done, event, dmin, dist_to_goal);
+                                                  done, event, dmin, dist_to_goal, sx);
   return ebc_check_launch(s, "step_kernel");
 }

@@ -390,6 +390,7 @@ void ebc_value_release(ebc_sim *s) {
   s->d_weights = nullptr;
   s->d_joint = nullptr;
   s->joint_cap = 0;
+  s->joint_floats = 0;
 }
 
 int ebc_launch_value(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row_count, float *values,

@@ -7,7 +7,7 @@ package and reuses these struct definitions; nothing in this package loads it.)
 import ctypes
 import os
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EVENT_NAMES = ["Nothing", "Danger", "ReachGoal", "CollisionAdult", "CollisionBicycle",
                "CollisionChild", "CollisionObstacle", "Timeout"]
@@ -17,6 +17,8 @@ EV_NOTHING, EV_DANGER, EV_REACH_GOAL, EV_COLLISION_ADULT, EV_COLLISION_BICYCLE, 
 KIN_HOLONOMIC, KIN_UNICYCLE = 0, 1
 VALUE_FP32, VALUE_TC_FP32, VALUE_TC_BF16, VALUE_TC_FP16X2 = 0, 1, 2, 3
 POLICY_ORCA, POLICY_LINEAR = 0, 1
+ERR_INVALID, ERR_UNBOUND, ERR_CUDA, ERR_NOMEM = -1, -2, -3, -4
+WARN_VALUE_FFMA = 1      # ebc_set_weights: accepted, but K4 runs on the FFMA kernels
 
 c_i32, c_f64, c_f32 = ctypes.c_int32, ctypes.c_double, ctypes.c_float
 vp = ctypes.c_void_p
@@ -37,13 +39,29 @@ class EbcConfig(ctypes.Structure):
         ("discomfort_penalty_factor_child", c_f64), ("rotation_penalty_factor", c_f64),
         ("map_size_m", c_f64), ("map_resolution", c_f64), ("gamma", c_f64), ("orca_safety_space", c_f64),
         ("orca_neighbor_dist", c_f32), ("orca_time_horizon", c_f32),
+        ("orca_obstacles", c_i32), ("max_obst", c_i32), ("orca_time_horizon_obst", c_f32), ("reserved0", c_f32),
     ]
+
+
+class EbcObstVertex(ctypes.Structure):
+    _fields_ = [("px", c_f32), ("py", c_f32), ("ux", c_f32), ("uy", c_f32), ("next", ctypes.c_int16),
+                ("prev", ctypes.c_int16), ("convex", ctypes.c_int16), ("pad0", ctypes.c_int16),
+                ("anc", ctypes.c_uint64), ("anc_left", ctypes.c_uint64), ("pad1", ctypes.c_uint64)]
+
+
+OBST_DTYPE = [("px", "<f4"), ("py", "<f4"), ("ux", "<f4"), ("uy", "<f4"), ("next", "<i2"), ("prev", "<i2"),
+              ("convex", "<i2"), ("pad0", "<i2"), ("anc", "<u8"), ("anc_left", "<u8"), ("pad1", "<u8")]   # numpy view
 
 
 class EbcState(ctypes.Structure):
     _fields_ = [(n, vp) for n in (
         "hum_pv", "hum_gr", "hum_type", "hum_count", "hum_nv", "stat", "stat_count", "rect", "rect_count",
-        "rob_pv", "rob_gr", "rob_theta", "time")]
+        "rob_pv", "rob_gr", "rob_theta", "time", "obst", "obst_count")]
+
+
+class EbcStats(ctypes.Structure):
+    _fields_ = [(n, vp) for n in ("alive", "final_event", "steps", "too_close", "cum_reward", "discount",
+                                  "min_dist_sum", "alive_count")]
 
 
 class EbcLinear(ctypes.Structure):
@@ -73,8 +91,11 @@ PROTOTYPES = {
     "ebc_last_error": (ctypes.c_char_p, [SIM]),
     "ebc_abi_version": (c_i32, []),
     "ebc_bind": (c_i32, [SIM, ctypes.POINTER(EbcState)]),
+    "ebc_bind_stats": (c_i32, [SIM, ctypes.POINTER(EbcStats)]),
+    "ebc_pack_obstacles": (c_i32, [vp, vp, c_i32, vp, c_i32, vp]),
     "ebc_set_actions": (c_i32, [SIM, vp, c_i32]),
     "ebc_set_weights": (c_i32, [SIM, ctypes.POINTER(EbcWeights)]),
+    "ebc_reserve": (c_i32, [SIM, ctypes.c_int64]),
     "ebc_set_value_mode": (c_i32, [SIM, c_i32]),
     "ebc_get_value_mode": (c_i32, [SIM]),
     "ebc_orca": (c_i32, [SIM, vp]),

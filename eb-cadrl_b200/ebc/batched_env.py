@@ -86,6 +86,14 @@ class BatchedEnv(object):
             self.sim.set_actions(np.array([tuple(a)[:2] for a in policy.action_space], dtype=np.float64))
             self.sync_weights()
         self._weights_version = getattr(policy, "weights_version", 0)
+        # epsilon-greedy exploration stream: ONE generator for the life of the env, keyed by (seed, rank), so that
+        # neither successive run_episodes calls nor different ranks replay the same explore mask / random actions
+        # (the reference draws from numpy's global stream, reseeded per scene: multi_human_rl.py:31)
+        rank = int(__import__("os").environ.get("RANK", "0"))
+        self._explore_rng = np.random.default_rng(np.random.SeedSequence([20261018, rank]))
+
+    def seed_exploration(self, seed, rank=0):
+        self._explore_rng = np.random.default_rng(np.random.SeedSequence([int(seed), int(rank)]))
 
     def sync_weights(self):
         model = self.policy.get_model()
@@ -164,7 +172,7 @@ class BatchedEnv(object):
         steps = torch.zeros(N, dtype=torch.int64, device=dev)
         final_event = torch.zeros(N, dtype=torch.int64, device=dev)
         states, rewards, alive = [], [], []
-        gen = rng or np.random.default_rng(0)
+        gen = rng if rng is not None else self._explore_rng
         max_steps = int(self.time_limit / self.time_step) + 2
         dd = torch.tensor([self.cfg.discomfort_dist_adult, self.cfg.discomfort_dist_bicycle,
                            self.cfg.discomfort_dist_child], dtype=torch.float64, device=dev)

@@ -46,6 +46,9 @@ class SimConfig:
     orca_max_neighbors: int = 10
     orca_time_horizon: float = 5.0
     orca_safety_space: float = 0.0
+    # ORCA obstacle half-planes: off = the reference's live behaviour (humans ignore walls)
+    orca_obstacles: bool = False
+    orca_time_horizon_obst: float = 5.0
 
     @classmethod
     def from_ini(cls, env_config, policy_config=None):
@@ -85,7 +88,7 @@ class SimConfig:
     def D(self):
         return 17 if self.with_agent_type else 13
 
-    def to_abi(self, n_episodes, max_humans, max_statics, max_rects, n_actions):
+    def to_abi(self, n_episodes, max_humans, max_statics, max_rects, n_actions, max_obst=0):
         a = abi.EbcConfig()
         a.abi_version = abi.ABI_VERSION
         a.n_episodes, a.max_humans, a.max_statics = n_episodes, max_humans, max_statics
@@ -118,6 +121,9 @@ class SimConfig:
         a.orca_safety_space = self.orca_safety_space
         a.orca_neighbor_dist = self.orca_neighbor_dist
         a.orca_time_horizon = self.orca_time_horizon
+        a.orca_obstacles = int(self.orca_obstacles)
+        a.max_obst = int(max_obst)
+        a.orca_time_horizon_obst = self.orca_time_horizon_obst
         return a
 
 

@@ -44,12 +44,16 @@ class CudaBackend(object):
 
     def call(self, name, h, *args, stream=None):
         fn = getattr(self.lib, "ebc_" + name)
-        if name in ("bind", "set_actions", "set_weights"):
+        if name in ("bind", "bind_stats", "set_actions", "set_weights", "reserve"):
             rc = fn(h, *args)
         else:
             rc = fn(h, *args, stream)
-        if rc != 0:
+        if rc < 0:
             raise abi.EbcError("ebc_%s failed (%d): %s" % (name, rc, self.last_error(h)))
+        if rc > 0:          # accepted with a documented downgrade (EBC_WARN_*): tell the caller, loudly
+            import warnings
+            warnings.warn("ebc_%s: %s" % (name, self.last_error(h)), RuntimeWarning, stacklevel=3)
+        return rc
 
     def launch_count(self, h):
         return int(self.lib.ebc_launch_count(h))
@@ -61,9 +65,10 @@ def _ptr(t):
 
 class BatchedSim(object):
     def __init__(self, cfg, n_episodes, max_humans, max_statics=0, max_rects=0, n_actions=81,
-                 device="cuda:0", backend=None):
+                 device="cuda:0", backend=None, max_obst=0):
         self.cfg = cfg
         self.N, self.Hmax, self.Smax, self.Rmax, self.A = n_episodes, max_humans, max_statics, max_rects, n_actions
+        self.Omax = max_obst
         self.n = max_humans + max_statics
         self.D = cfg.D
         self.device = torch.device(device)
@@ -72,7 +77,7 @@ class BatchedSim(object):
                 raise abi.EbcError("BatchedSim needs a CUDA device: the hot path has no CPU fallback")
             backend = CudaBackend()
         self.be = backend
-        self._abi_cfg = cfg.to_abi(n_episodes, max_humans, max_statics, max_rects, n_actions)
+        self._abi_cfg = cfg.to_abi(n_episodes, max_humans, max_statics, max_rects, n_actions, max_obst)
         dev_index = self.device.index if self.device.type == "cuda" and self.device.index is not None else 0
         if self.device.type == "cuda":
             torch.cuda.set_device(self.device)
@@ -92,6 +97,9 @@ class BatchedSim(object):
         self.rob_gr = z(N, 4)
         self.rob_theta = z(N)
         self.time = z(N, dtype=torch.float64)
+        # ORCA obstacle vertices (ebc_obst_vertex records of 48 bytes, viewed as bytes)
+        self.obst = z(N, max(self.Omax, 1), 48, dtype=torch.uint8)
+        self.obst_count = z(N, dtype=torch.int32)
         # per-decision buffers
         self.vin = None
         self.la_reward = z(N, A, dtype=torch.float64)
@@ -110,10 +118,44 @@ class BatchedSim(object):
         self.actions = None
         st = abi.EbcState()
         for name in ("hum_pv", "hum_gr", "hum_type", "hum_count", "hum_nv", "stat", "stat_count", "rect",
-                     "rect_count", "rob_pv", "rob_gr", "rob_theta", "time"):
+                     "rect_count", "rob_pv", "rob_gr", "rob_theta", "time", "obst", "obst_count"):
             setattr(st, name, getattr(self, name).data_ptr())
         self._state = st
         self.be.call("bind", self.h, ctypes.byref(st))
+        self.stats = None
+
+    # ---- running episode statistics on the device (ebc_bind_stats) -----------------------------------------
+    def bind_stats(self, alive=None):
+        """Allocate (first call) and re-initialise the per-episode accumulators; every committed step updates them
+        for the episodes it steps, and `step(active=None)` then uses stats['alive'] as its mask."""
+        N = self.N
+        if self.stats is None:
+            z = lambda dtype: torch.zeros(N, dtype=dtype, device=self.device)  # noqa: E731
+            self.stats = {"alive": z(torch.uint8), "final_event": z(torch.uint8), "steps": z(torch.int32),
+                          "too_close": z(torch.int32), "cum_reward": z(torch.float64), "discount": z(torch.float64),
+                          "min_dist_sum": z(torch.float64),
+                          "alive_count": torch.zeros(1, dtype=torch.int32, device=self.device)}
+            sx = abi.EbcStats()
+            for k, t in self.stats.items():
+                setattr(sx, k, t.data_ptr())
+            self._stats_abi = sx
+            self.be.call("bind_stats", self.h, ctypes.byref(sx))
+        st = self.stats
+        for k in ("final_event", "steps", "too_close", "cum_reward", "min_dist_sum"):
+            st[k].zero_()
+        st["discount"].fill_(1.0)
+        if alive is None:
+            st["alive"].fill_(1)
+            st["alive_count"].fill_(N)
+        else:
+            st["alive"].copy_(alive)
+            st["alive_count"].copy_(alive.sum().to(torch.int32).reshape(1))
+        return st
+
+    def unbind_stats(self):
+        if self.stats is not None:
+            self.be.call("bind_stats", self.h, None)
+            self.stats = None
 
     def close(self):
         if getattr(self, "h", None) is not None:
@@ -159,6 +201,13 @@ class BatchedSim(object):
                 arr[i] = lin(k)
         self.be.call("set_weights", self.h, ctypes.byref(w))
         self._have_weights = True
+        self._reserved = max(getattr(self, "_reserved", 0), self.N * self.A)
+
+    def reserve(self, n_states):
+        """Setup-time: make room for value() batches of up to n_states states (ebc_value never allocates)."""
+        if n_states > getattr(self, "_reserved", 0):
+            self.be.call("reserve", self.h, ctypes.c_int64(int(n_states)))
+            self._reserved = int(n_states)
 
     def set_value_mode(self, mode):
         """K4 arithmetic: 'fp32' (FFMA), 'tc_fp16x2' (tcgen05, two fp16 parts per operand, 3 MMAs per product,
@@ -175,7 +224,8 @@ class BatchedSim(object):
 
     # ---- scene upload -------------------------------------------------------------
     def load_episodes(self, first, hum_pv, hum_gr, hum_type, hum_count, stat=None, stat_count=None,
-                      rect=None, rect_count=None, rob_pv=None, rob_gr=None, rob_theta=None, time=None):
+                      rect=None, rect_count=None, rob_pv=None, rob_gr=None, rob_theta=None, time=None,
+                      obst=None, obst_count=None):
         """Copy host arrays (numpy, already padded to Hmax/Smax/Rmax) into episodes [first, first+k)."""
         k = len(hum_count)
         sl = slice(first, first + k)
@@ -200,6 +250,9 @@ class BatchedSim(object):
         put(self.rob_gr, rob_gr, torch.float32)
         put(self.rob_theta, rob_theta, torch.float32)
         put(self.time, time, torch.float64)
+        if self.Omax and obst is not None:
+            put(self.obst, np.ascontiguousarray(obst).view(np.uint8).reshape(k, -1, 48), torch.uint8)
+            put(self.obst_count, obst_count, torch.int32)
 
     # ---- hot path -----------------------------------------------------------------
     def orca(self):
@@ -222,8 +275,11 @@ class BatchedSim(object):
             vin, out, n_states = self.vin, self.values, self.N * self.A
         else:
             n_states = vin.shape[0]
+            if row_count is None:      # an explicit batch never borrows the bound episodes' counts
+                row_count = torch.full((n_states,), self.n, dtype=torch.int32, device=self.device)
             if out is None:
                 out = torch.zeros(n_states, dtype=torch.float32, device=self.device)
+            self.reserve(n_states)
         self.be.call("value", self.h, _ptr(vin), ctypes.c_int64(n_states), _ptr(row_count), _ptr(out),
                      stream=self._stream())
         return out
@@ -280,19 +336,22 @@ class ScenePool(object):
     _FIELDS = (("hum_pv", torch.float32), ("hum_gr", torch.float32), ("hum_type", torch.uint8),
                ("hum_count", torch.int32), ("stat", torch.float32), ("stat_count", torch.int32),
                ("rect", torch.int16), ("rect_count", torch.int32), ("rob_pv", torch.float32),
-               ("rob_gr", torch.float32), ("rob_theta", torch.float32), ("time", torch.float64))
+               ("rob_gr", torch.float32), ("rob_theta", torch.float32), ("time", torch.float64),
+               ("obst", torch.uint8), ("obst_count", torch.int32))
 
     def __init__(self, sim, scenes):
         self.size = int(len(scenes["hum_count"]))
         self.tensors = {}
         shapes = {"hum_pv": (sim.Hmax, 4), "hum_gr": (sim.Hmax, 4), "hum_type": (sim.Hmax,),
-                  "stat": (max(sim.Smax, 1), 4), "rect": (max(sim.Rmax, 1), 4)}
+                  "stat": (max(sim.Smax, 1), 4), "rect": (max(sim.Rmax, 1), 4), "obst": (max(sim.Omax, 1), 48)}
         st = abi.EbcState()
         for name, dtype in self._FIELDS:
             src = scenes.get(name)
             if src is None:
                 t = torch.zeros((self.size,) + shapes.get(name, ()), dtype=dtype)
             else:
+                if name == "obst":
+                    src = np.ascontiguousarray(src).view(np.uint8).reshape(self.size, -1, 48)
                 t = torch.as_tensor(np.ascontiguousarray(src), dtype=dtype)
                 if name in shapes:
                     assert tuple(t.shape[1:]) == shapes[name], (name, tuple(t.shape), shapes[name])

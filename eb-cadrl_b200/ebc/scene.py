@@ -31,3 +31,33 @@ def rects_from_zero_cells(zero):
                 open_runs[run] = x
     rects.sort()
     return np.asarray(rects, dtype=np.int16).reshape(-1, 4)
+
+
+def wall_polygon(cx, cy, x_dim, y_dim, inflation=1.0):
+    """The 4 vertices the reference records for a wall (scene_generator.py:269-290): counter-clockwise from the
+    (+, +) corner, inflated by `inflation` (its inflation_rate_il)."""
+    hx, hy = inflation * x_dim / 2.0, inflation * y_dim / 2.0
+    return [(cx + hx, cy + hy), (cx - hx, cy + hy), (cx - hx, cy - hy), (cx + hx, cy - hy)]
+
+
+def pack_obstacles(polygons, cap=64):
+    """RVO2 addObstacle for every polygon + processObstacles (simulator/policy/orca_obstacles.py:102-107) through
+    the library's host entry point ebc_pack_obstacles -> structured array of ebc_obst_vertex records.  When the
+    kd-tree's edge splitting needs more than `cap` vertices, polygons are dropped from the END of the list until it
+    fits (returned as the second value: how many polygons were kept)."""
+    import ctypes
+    from . import abi
+    lib = abi.load()
+    polys = [list(p) for p in polygons]
+    while True:
+        out = np.zeros(max(cap, 1), dtype=abi.OBST_DTYPE)
+        n = ctypes.c_int32(0)
+        xy = np.asarray([c for p in polys for v in p for c in v[:2]], dtype=np.float32)
+        sizes = np.asarray([len(p) for p in polys], dtype=np.int32)
+        rc = lib.ebc_pack_obstacles(xy.ctypes.data_as(ctypes.c_void_p), sizes.ctypes.data_as(ctypes.c_void_p), len(polys),
+                                    out.ctypes.data_as(ctypes.c_void_p), cap, ctypes.byref(n))
+        if rc == 0:
+            return out[:n.value].copy(), len(polys)
+        if not polys:
+            raise abi.EbcError("ebc_pack_obstacles failed on an empty polygon list")
+        polys.pop()

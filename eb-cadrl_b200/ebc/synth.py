@@ -93,8 +93,9 @@ CFG1 = SceneShape("cfg1_h5_circle", [(0, 5, (0.6, 0.6), (0.2, 0.2))], rule="circ
                   circle_radius=3.0, robot_radius=0.2, robot_v_pref=0.7, num_walls=0)
 
 
-def generate(shape, episode_ids, seed=SEED_BASE, max_tries=64):
-    """-> dict of numpy arrays in the ebc_state layout for the given global episode ids."""
+def generate(shape, episode_ids, seed=SEED_BASE, max_tries=64, max_obst=0):
+    """-> dict of numpy arrays in the ebc_state layout for the given global episode ids.  max_obst > 0 adds the
+    walls as ORCA obstacle polygons (`obst`, `obst_count`: ebc_obst_vertex records)."""
     ids = np.asarray(episode_ids, dtype=np.uint64)
     N, H = len(ids), shape.H
     Smax, Rmax = max(shape.Smax, 1), shape.Rmax
@@ -161,6 +162,7 @@ def generate(shape, episode_ids, seed=SEED_BASE, max_tries=64):
     rect = np.zeros((N, Rmax, 4), np.int16)
     rect_count = np.zeros(N, np.int32)
     clear = shape.robot_radius + shape.discomfort_dist
+    walls = [[] for _ in range(N)]
     for w in range(shape.num_walls):
         todo = np.ones(N, bool)
         lx = np.zeros(N); ly = np.zeros(N); xd = np.ones(N); yd = np.ones(N)
@@ -195,6 +197,9 @@ def generate(shape, episode_ids, seed=SEED_BASE, max_tries=64):
         rect_count += 1
         # discs along the long axis, radius = half thickness * sqrt(2)
         xm, ym = lx * res, ly * res
+        if max_obst:
+            for e in range(N):
+                walls[e].append((xm[e], ym[e], xd[e], yd[e]))
         horiz = xd > yd
         half_t = np.where(horiz, yd, xd) / 2.0
         rr = half_t * np.sqrt(2.0)
@@ -211,7 +216,19 @@ def generate(shape, episode_ids, seed=SEED_BASE, max_tries=64):
             stat[np.nonzero(live)[0], k, 2] = rr[live]
             stat_count[live] += 1
             pos = pos + 2.0 * rr
+    extra = {}
+    if max_obst:
+        from . import abi
+        from .scene import pack_obstacles, wall_polygon
+        obst = np.zeros((N, max_obst), dtype=abi.OBST_DTYPE)
+        obst_count = np.zeros(N, np.int32)
+        for e in range(N):
+            rec, _ = pack_obstacles([wall_polygon(*w) for w in walls[e]], max_obst)
+            obst[e, :len(rec)] = rec
+            obst_count[e] = len(rec)
+        extra = {"obst": obst, "obst_count": obst_count}
     return {
+        **extra,
         "hum_pv": hum_pv, "hum_gr": hum_gr, "hum_type": hum_type, "hum_count": np.full(N, H, np.int32),
         "stat": stat, "stat_count": stat_count, "rect": rect, "rect_count": rect_count,
         "rob_pv": rob_pv, "rob_gr": rob_gr, "rob_theta": np.full(N, np.pi / 2, np.float32),
@@ -222,4 +239,5 @@ def generate(shape, episode_ids, seed=SEED_BASE, max_tries=64):
 def load(sim, scenes, first=0):
     sim.load_episodes(first, scenes["hum_pv"], scenes["hum_gr"], scenes["hum_type"], scenes["hum_count"],
                       scenes["stat"], scenes["stat_count"], scenes["rect"], scenes["rect_count"],
-                      scenes["rob_pv"], scenes["rob_gr"], scenes["rob_theta"], scenes["time"])
+                      scenes["rob_pv"], scenes["rob_gr"], scenes["rob_theta"], scenes["time"],
+                      obst=scenes.get("obst"), obst_count=scenes.get("obst_count"))

@@ -7,7 +7,7 @@ only success / collision episodes (explorer.py:82-92), the parallel one stores a
 (parallel_explorer.py:185-192) -> `store_all`; imitation learning uses discounted returns, RL uses the TD
 target r + gamma^(dt v_pref) V_target(s') with the terminal state's value = its reward (explorer.py:151-200).
 With torch.distributed initialised, every rank runs its slice of the seeds and the outcome counters are
-all-gathered before logging (the only collective of evaluation)."""
+exchanged with one fixed-size all_gather before logging (the only collective of evaluation)."""
 import copy
 import logging
 
@@ -37,27 +37,52 @@ class Explorer(object):
         self.target_model = copy.deepcopy(target_model)
 
     # ---- statistics (explorer.py:96-126, 214-340) ----------------------------------------------------------
-    def _gather(self, stats):
-        import torch.distributed as dist
-        arrays = {k: np.asarray(getattr(stats, k)) for k in ("event", "time", "steps", "cum_reward", "too_close",
-                                                             "min_dist_sum")}
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            out = [None] * dist.get_world_size()
-            dist.all_gather_object(out, arrays)
-            arrays = {k: np.concatenate([o[k] for o in out]) for k in arrays}
-        return arrays
+    # One fixed-size vector per rank: 8 event counts, sum of success times, sum of returns, danger steps,
+    # sum of min distances in danger, step count, episode count.  Ranks exchange it with ONE all_gather of 14 float64.
+    SUMMARY = 14
 
-    def log_results(self, arrays, phase, episode=None, seeds=None, print_failure=False):
-        ev, n = arrays["event"], len(arrays["event"])
-        rate = lambda code: float((ev == code).sum()) / n  # noqa: E731
-        success = ev == abi.EV_REACH_GOAL
+    @staticmethod
+    def summarise(arrays):
+        ev = np.asarray(arrays["event"])
+        v = np.zeros(Explorer.SUMMARY, np.float64)
+        for code in range(8):
+            v[code] = float((ev == code).sum())
+        v[8] = float(np.asarray(arrays["time"])[ev == abi.EV_REACH_GOAL].sum())
+        v[9] = float(np.asarray(arrays["cum_reward"]).sum())
+        v[10] = float(np.asarray(arrays["too_close"]).sum())
+        v[11] = float(np.asarray(arrays["min_dist_sum"]).sum())
+        v[12] = float(np.asarray(arrays["steps"]).sum())
+        v[13] = float(len(ev))
+        return v
+
+    def _gather(self, stats):
+        """Rank-local per-episode arrays -> the job-wide summary vector (sum over ranks of `summarise`)."""
+        import torch.distributed as dist
+        arrays = stats if isinstance(stats, dict) else {k: np.asarray(getattr(stats, k)) for k in (
+            "event", "time", "steps", "cum_reward", "too_close", "min_dist_sum")}
+        v = self.summarise(arrays)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dev = self.device if dist.get_backend() == "nccl" else "cpu"
+            mine = torch.as_tensor(v, dtype=torch.float64, device=dev)
+            out = torch.empty(dist.get_world_size(), self.SUMMARY, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(out, mine.reshape(1, -1))
+            v = out.sum(0).cpu().numpy()
+        return v
+
+    def log_results(self, summary, phase, episode=None, seeds=None, print_failure=False, events=None):
+        """`summary`: the vector of `_gather` (or a dict of per-episode arrays, summarised here without a collective)."""
+        if isinstance(summary, dict):
+            events = summary["event"] if events is None else events
+            summary = self.summarise(summary)
+        v, n = summary, max(float(summary[13]), 1.0)
+        rate = lambda code: float(v[code]) / n  # noqa: E731
         m = {
             "success_rate": rate(abi.EV_REACH_GOAL), "collision_rate": 0.0,
             "collision_rate_adult": rate(abi.EV_COLLISION_ADULT), "collision_rate_bicycle": rate(abi.EV_COLLISION_BICYCLE),
             "collision_rate_child": rate(abi.EV_COLLISION_CHILD), "collision_rate_obstacle": rate(abi.EV_COLLISION_OBSTACLE),
             "timeout_rate": rate(abi.EV_TIMEOUT),
-            "avg_nav_time": float(arrays["time"][success].mean()) if success.any() else float(self.env.time_limit),
-            "total_reward": float(arrays["cum_reward"].mean()) if n else 0.0,
+            "avg_nav_time": float(v[8] / v[abi.EV_REACH_GOAL]) if v[abi.EV_REACH_GOAL] else float(self.env.time_limit),
+            "total_reward": float(v[9] / n),
         }
         extra = "" if episode is None else "in episode {} ".format(episode)
         logging.info("{:<5} {}has success rate: {:.2f}, self.collision rate: {:.2f}, nav time: {:.2f}, total reward: {:.4f}".format(
@@ -67,17 +92,16 @@ class Explorer(object):
                          phase.upper(), extra, m["collision_rate_adult"], m["collision_rate_bicycle"],
                          m["collision_rate_child"], m["collision_rate_obstacle"]))
         if phase in self.PHASES:
-            num_step = int(arrays["steps"].sum())
-            close = int(arrays["too_close"].sum())
+            num_step, close = int(v[12]), int(v[10])
             m["danger_frequency"] = close / max(num_step, 1)
-            m["avg_min_dist"] = float(arrays["min_dist_sum"].sum() / close) if close else 0.0
+            m["avg_min_dist"] = float(v[11] / close) if close else 0.0
             logging.info("Frequency of being in danger: {:.2f} and average min separate distance in danger: {:.2f}".format(
                 m["danger_frequency"], m["avg_min_dist"]))
-        if print_failure and seeds is not None:
+        if print_failure and seeds is not None and events is not None:      # this rank's own cases
             for name, code in (("Collision adult", abi.EV_COLLISION_ADULT), ("Collision bicycle", abi.EV_COLLISION_BICYCLE),
                                ("Collision child", abi.EV_COLLISION_CHILD), ("Collision obstacle", abi.EV_COLLISION_OBSTACLE),
                                ("Timeout", abi.EV_TIMEOUT)):
-                cases = [int(s) for s, e in zip(seeds, ev) if e == code]
+                cases = [int(s) for s, e in zip(seeds, events) if e == code]
                 logging.info("%s cases: %s", name, " ".join(str(c) for c in cases))
         self.metrics = m
         return m
@@ -106,8 +130,8 @@ class Explorer(object):
             done_seeds += chunk
         merged = type("S", (), {k: np.concatenate([getattr(s, k) for s in all_stats]) for k in (
             "event", "time", "steps", "cum_reward", "too_close", "min_dist_sum")})()
-        arrays = self._gather(merged)
-        return self.log_results(arrays, phase, episode, done_seeds, print_failure)
+        summary = self._gather(merged)
+        return self.log_results(summary, phase, episode, done_seeds, print_failure, events=merged.event)
 
     @torch.no_grad()
     def update_memory(self, traj, stats, imitation_learning=False, store_all=False, keep=slice(None)):

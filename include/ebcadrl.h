@@ -29,8 +29,8 @@
  *   D      rotated row width: 13, or 17 with the 4-class entity-type one-hot
  *          (rl/policy/cadrl.py:236-337)
  * All calls are asynchronous on the given stream; no hidden synchronisation.
- * Return value: 0 on success, negative `ebc_status` otherwise; the message is in
- * `ebc_last_error`.
+ * Return value: 0 on success, negative `ebc_status` on failure, positive `EBC_WARN_*` when the
+ * call succeeded with a documented downgrade; the message is in `ebc_last_error`.
  */
 #ifndef EBCADRL_H
 #define EBCADRL_H
@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define EBC_ABI_VERSION 1
+#define EBC_ABI_VERSION 2
 
 /* simulator/utils/utils.py:9-14 (AgentType IntEnum) */
 enum { EBC_ADULT = 0, EBC_BICYCLE = 1, EBC_CHILD = 2, EBC_ADULT_STATIC = 3, EBC_ROBOT = 4 };
@@ -68,7 +68,10 @@ typedef enum ebc_status {
   EBC_ERR_INVALID = -1,   /* bad argument / config */
   EBC_ERR_UNBOUND = -2,   /* ebc_bind / ebc_set_actions / ebc_set_weights not called */
   EBC_ERR_CUDA = -3,      /* CUDA runtime error (message has the cudaError string) */
-  EBC_ERR_NOMEM = -4
+  EBC_ERR_NOMEM = -4,
+  /* positive = accepted, with a note in ebc_last_error */
+  EBC_WARN_VALUE_FFMA = 1 /* ebc_set_weights: the network's shape misses the tensor-core tiling; K4 runs on the
+                             fp32 FFMA kernels (ebc_get_value_mode() == EBC_VALUE_FP32) */
 } ebc_status;
 
 /* Per-simulator constants: the env INI ([env] [reward] [map] [robot]) and the
@@ -104,12 +107,34 @@ typedef struct ebc_config {
   double orca_safety_space;          /* orca.py:63 (0; IL robot uses 0.15, train.py:126-132) */
   float orca_neighbor_dist;          /* orca.py:64 (10) */
   float orca_time_horizon;           /* orca.py:66 (5) */
+  /* ORCA obstacle half-planes (spec: RVO2 computeNewVelocity obstacle section, caller
+   * simulator/policy/orca_obstacles.py:83-152).  OFF by default = the reference's live behaviour: humans never see
+   * walls (orca.py adds no obstacle to its rvo2 sims). */
+  int32_t orca_obstacles;            /* 1: humans (and the ORCA robot) avoid the episode's obstacle polygons */
+  int32_t max_obst;                  /* Omax: obstacle-vertex slots per episode (0..64) */
+  float orca_time_horizon_obst;      /* orca_obstacles.py:65 (5) */
+  float reserved0;
 } ebc_config;
 
 /* Structure-of-arrays episode state.  The library BORROWS these arrays (owned by
  * the caller, e.g. torch tensors); it never frees them.  fp32 state, float4-packed
  * per agent so that one warp lane loads one agent with one 16-byte load.
  * Layout follows simulator/utils/state.py:1-92 (FullState / ObservableState). */
+/* One RVO2 obstacle vertex (Obstacle.h: point_, unitDir_, nextObstacle_, prevObstacle_, isConvex_) plus this vertex's
+ * place in RVO2's obstacle kd-tree (KdTree::buildObstacleTreeRecursive: one node per vertex, edges that straddle a
+ * splitting line are split), from which every agent derives the tree's near-first visiting order for distance ties.
+ * Produced on the host by ebc_pack_obstacles. */
+typedef struct ebc_obst_vertex {
+  float px, py;         /* point_ */
+  float ux, uy;         /* unitDir_ = normalize(next.point_ - point_) */
+  int16_t next, prev;   /* vertex indices within the episode */
+  int16_t convex;       /* isConvex_ */
+  int16_t pad0;
+  uint64_t anc;         /* kd-tree ancestors of this node (bit j = vertex j) */
+  uint64_t anc_left;    /* the ancestors whose LEFT subtree holds this node */
+  uint64_t pad1;
+} ebc_obst_vertex;      /* 48 bytes */
+
 typedef struct ebc_state {
   float *hum_pv;        /* [N*Hmax*4]  px, py, vx, vy */
   float *hum_gr;        /* [N*Hmax*4]  gx, gy, v_pref, radius */
@@ -124,6 +149,8 @@ typedef struct ebc_state {
   float *rob_gr;        /* [N*4]       gx, gy, v_pref, radius */
   float *rob_theta;     /* [N] */
   double *time;         /* [N]         env.global_time */
+  ebc_obst_vertex *obst;/* [N*Omax]    obstacle vertices (may be NULL unless cfg.orca_obstacles) */
+  int32_t *obst_count;  /* [N] */
 } ebc_state;
 
 /* SARL / EB-CADRL value network (rl/policy/sarl.py:9-82).  HOST pointers to the
@@ -157,11 +184,45 @@ int ebc_abi_version(void);
 /* Borrow the caller's device arrays. */
 int ebc_bind(ebc_sim *sim, const ebc_state *state);
 
+/* Per-episode running statistics of the explorer's inner loop (rl/utils/explorer.py:33-94,189-193;
+ * rl/test_parallel.py:52-130), kept ON THE DEVICE: device arrays of N entries owned by the caller.  While bound,
+ * every committed step (ebc_step / ebc_orca_step) of an episode e that is stepped
+ *   cum_reward[e] += discount[e] * reward;  discount[e] *= gamma^(time_step * v_pref_robot);  steps[e] += 1;
+ *   event == Danger: too_close[e] += 1, min_dist_sum[e] += Danger.min_dist (reward.py:138-166);
+ *   done: final_event[e] = event, alive[e] = 0, alive_count[0] -= 1.
+ * With `active == NULL` in ebc_step the bound alive[] is the mask, so a whole batch runs to the end of every episode
+ * without a host round trip per step (the host reads alive_count[0] when it wants to). */
+typedef struct ebc_stats {
+  uint8_t *alive;        /* [N] in/out */
+  uint8_t *final_event;  /* [N] */
+  int32_t *steps;        /* [N] */
+  int32_t *too_close;    /* [N] */
+  double *cum_reward;    /* [N] */
+  double *discount;      /* [N] initialise to 1 */
+  double *min_dist_sum;  /* [N] */
+  int32_t *alive_count;  /* [1] initialise to the number of alive episodes */
+} ebc_stats;
+int ebc_bind_stats(ebc_sim *sim, const ebc_stats *stats);   /* NULL unbinds */
+
+/* RVO2 addObstacle (per polygon, counter-clockwise) + processObstacles for ONE episode, on the HOST: `xy` holds the
+ * polygons' vertices back to back (x, y pairs, float like the rvo2 boundary), poly_size[i] vertices each (>= 2).
+ * Writes at most `cap` (<= 64) records and their number; EBC_ERR_INVALID when the kd-tree's edge splitting needs more.
+ * No handle, no device: the result is plain data for state.obst (simulator/policy/orca_obstacles.py:102-107). */
+int ebc_pack_obstacles(const float *xy, const int32_t *poly_size, int32_t n_poly, ebc_obst_vertex *out, int32_t cap,
+                       int32_t *n_out);
+
 /* Action table, HOST pointer, A x 2 doubles: (vx, vy) for a holonomic robot, (v, r)
  * otherwise; built on the host exactly like rl/policy/cadrl.py:91-116. */
 int ebc_set_actions(ebc_sim *sim, const double *actions, int32_t n_actions);
 
+/* Copies and re-lays-out the weights (setup-time call: allocates and synchronises), and reserves K4's scratch
+ * for the lookahead batch of n_episodes * n_actions states.  Returns EBC_WARN_VALUE_FFMA (> 0) when the shape does
+ * not fit the tensor-core tiling -- the weights are in place, K4 then runs in EBC_VALUE_FP32. */
 int ebc_set_weights(ebc_sim *sim, const ebc_weights *w);
+
+/* Reserve K4's private scratch for ebc_value calls of up to n_states states (setup-time call: may allocate and
+ * synchronise).  ebc_value itself never allocates: a larger batch than reserved fails with EBC_ERR_UNBOUND. */
+int ebc_reserve(ebc_sim *sim, int64_t n_states);
 
 /* Arithmetic of K4 (the value network).  All four are this library's own kernels.
  *   EBC_VALUE_FP32      fp32 FFMA (CUDA cores): the first parity path, kept as a cross-check
@@ -204,8 +265,10 @@ int ebc_lookahead(ebc_sim *sim, float *vin, double *reward, uint8_t *done, uint8
 /* K4. Value network forward (rl/policy/sarl.py:38-82) over `n_states` states of n rows
  * each; row_count[s] (<= n) rows are real, the rest are padding (excluded from the
  * mean and the softmax).  vin [n_states*n*D] -> values [n_states].
- * row_count may be NULL (all n rows real).  Used with n_states = N*A for the lookahead,
- * in which case pass row_count = NULL and the per-episode counts bound to the sim are used.
+ * row_count == NULL selects the lookahead batch: n_states must then equal N*A, state i belongs to
+ * episode i / A and takes that episode's bound hum_count + stat_count (anything else is EBC_ERR_INVALID).
+ * For any other batch (replay samples, target-network evaluation) pass row_count explicitly.
+ * n_states must not exceed what ebc_set_weights / ebc_reserve reserved (this call never allocates).
  * n_states == 0 is valid and launches nothing (pointers may then be NULL). */
 int ebc_value(ebc_sim *sim, const float *vin, int64_t n_states, const int32_t *row_count,
               float *values, void *stream);
@@ -272,18 +335,24 @@ typedef struct ebc_scene_shape {
 int ebc_generate(ebc_sim *sim, const ebc_scene_shape *shape, uint64_t seed, const int64_t *episode_ids,
                  const uint8_t *mask, void *stream);
 
-/* Diagnostics: with EBC_TC_TRACE=1 in the environment the tensor-core K4 kernel records clock64()
- * stamps of CTA 0 (phase boundaries of its first tiles); this copies up to 4096 of them to the host. */
+/* ---- diagnostics (exported, but NOT part of the drop-in surface: nothing in the reference binds these;
+ *      declared only when the includer asks for them) ---------------------------------------------------------- */
+#ifdef EBC_DIAGNOSTICS
+/* With EBC_TC_TRACE=1 in the environment the tensor-core K4 kernel records clock64() stamps of CTA 0 (phase
+ * boundaries of its first tiles); this copies up to 4096 of them to the host (synchronises). */
 int ebc_debug_trace(ebc_sim *sim, long long *out, int32_t n);
-
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t ebc_launch_count(const ebc_sim *sim);
+#endif
 
 /* ---- CPU twins (oracle/libebc_oracle.so only; HOST pointers; test infrastructure) -- */
 int ebc_ref_create(const ebc_config *cfg, ebc_sim **out);
 void ebc_ref_destroy(ebc_sim *sim);
 const char *ebc_ref_last_error(const ebc_sim *sim);
 int ebc_ref_bind(ebc_sim *sim, const ebc_state *state);
+int ebc_ref_bind_stats(ebc_sim *sim, const ebc_stats *stats);
+int ebc_ref_pack_obstacles(const float *xy, const int32_t *poly_size, int32_t n_poly, ebc_obst_vertex *out, int32_t cap,
+                           int32_t *n_out);
 int ebc_ref_set_actions(ebc_sim *sim, const double *actions, int32_t n_actions);
 int ebc_ref_set_weights(ebc_sim *sim, const ebc_weights *w);
 int ebc_ref_orca(ebc_sim *sim);

@@ -37,7 +37,7 @@
 #endif
 
 #define RVO_EPSILON 0.00001f
-#define MAX_LINES 80 /* >= max neighbours considered (cap = orca_max_neighbors <= 64) */
+#define MAX_LINES 160 /* >= obstacle lines (<= 64) + agent neighbours (orca_max_neighbors <= 64) */
 
 typedef struct { float px, py, dx, dy; } line_t; /* RVO2 Line: point, direction */
 
@@ -145,6 +145,340 @@ static void lp3(const line_t *L, int n, int num_obst, int begin, float radius, f
   }
 }
 
+/* ------------------------------------------------------------------------------------
+ * RVO2 static obstacles: RVOSimulator::addObstacle, KdTree::buildObstacleTree /
+ * queryObstacleTreeRecursive, Agent::insertObstacleNeighbor and the obstacle section of
+ * Agent::computeNewVelocity, restated from the published RVO2 v2.0 sources [RVO2-from-memory].
+ * Reference caller: simulator/policy/orca_obstacles.py:102-107 (addObstacle per wall,
+ * processObstacles) -- dead code on the reference's live path, so this part is "parity
+ * unpinned" like the rest of rvo2; the CUDA kernel is held bit-exact against THIS.
+ * ---------------------------------------------------------------------------------- */
+#define OBST_MAX 64
+typedef struct {
+  float px, py, ux, uy;
+  int next, prev, convex;
+} obst_t;
+
+static inline float left_of(float ax, float ay, float bx, float by, float cx, float cy) {
+  return det2(ax - cx, ay - cy, bx - ax, by - ay); /* RVO2 leftOf(a, b, c) = det(a - c, b - a) */
+}
+
+typedef struct {
+  obst_t v[OBST_MAX];
+  int n, cap, overflow;
+  int left[OBST_MAX], right[OBST_MAX]; /* kd-tree children (vertex ids, -1 = none) */
+  int root;
+  uint64_t anc[OBST_MAX], anc_left[OBST_MAX];
+} obst_set;
+
+/* KdTree::buildObstacleTreeRecursive; returns the node (= vertex id) or -1 */
+static int build_obstacle_tree(obst_set *S, const int *list, int count, uint64_t anc, uint64_t anc_left) {
+  if (count == 0 || S->overflow) return -1;
+  int optimal = 0, min_left = count, min_right = count;
+  for (int i = 0; i < count; ++i) {
+    int ls = 0, rs = 0;
+    const obst_t *i1 = &S->v[list[i]], *i2 = &S->v[i1->next];
+    for (int j = 0; j < count; ++j) {
+      if (i == j) continue;
+      const obst_t *j1 = &S->v[list[j]], *j2 = &S->v[j1->next];
+      const float l1 = left_of(i1->px, i1->py, i2->px, i2->py, j1->px, j1->py);
+      const float l2 = left_of(i1->px, i1->py, i2->px, i2->py, j2->px, j2->py);
+      if (l1 >= -RVO_EPSILON && l2 >= -RVO_EPSILON) ++ls;
+      else if (l1 <= RVO_EPSILON && l2 <= RVO_EPSILON) ++rs;
+      else { ++ls; ++rs; }
+      /* std::make_pair(max, min) >= std::make_pair(max(minLeft, minRight), min(minLeft, minRight)) */
+      const int a = ls > rs ? ls : rs, b = ls > rs ? rs : ls;
+      const int c = min_left > min_right ? min_left : min_right, d = min_left > min_right ? min_right : min_left;
+      if (a > c || (a == c && b >= d)) break;
+    }
+    const int a = ls > rs ? ls : rs, b = ls > rs ? rs : ls;
+    const int c = min_left > min_right ? min_left : min_right, d = min_left > min_right ? min_right : min_left;
+    if (a < c || (a == c && b < d)) { min_left = ls; min_right = rs; optimal = i; }
+  }
+  int lefts[2 * OBST_MAX], rights[2 * OBST_MAX], nl = 0, nr = 0;
+  const int node = list[optimal];
+  for (int j = 0; j < count; ++j) {
+    if (j == optimal) continue;
+    const obst_t *i1 = &S->v[node], *i2 = &S->v[i1->next];
+    obst_t *j1 = &S->v[list[j]], *j2 = &S->v[j1->next];
+    const float l1 = left_of(i1->px, i1->py, i2->px, i2->py, j1->px, j1->py);
+    const float l2 = left_of(i1->px, i1->py, i2->px, i2->py, j2->px, j2->py);
+    if (l1 >= -RVO_EPSILON && l2 >= -RVO_EPSILON) lefts[nl++] = list[j];
+    else if (l1 <= RVO_EPSILON && l2 <= RVO_EPSILON) rights[nr++] = list[j];
+    else { /* split obstacle j at the line through i */
+      if (S->n >= S->cap) { S->overflow = 1; return -1; }
+      const float t = det2(i2->px - i1->px, i2->py - i1->py, j1->px - i1->px, j1->py - i1->py) /
+                      det2(i2->px - i1->px, i2->py - i1->py, j1->px - j2->px, j1->py - j2->py);
+      const int nid = S->n++;
+      obst_t *nw = &S->v[nid];
+      nw->px = j1->px + t * (j2->px - j1->px);
+      nw->py = j1->py + t * (j2->py - j1->py);
+      nw->prev = list[j];
+      nw->next = j1->next;
+      nw->convex = 1;
+      nw->ux = j1->ux;
+      nw->uy = j1->uy;
+      j2->prev = nid;
+      j1->next = nid;
+      if (l1 > 0.0f) { lefts[nl++] = list[j]; rights[nr++] = nid; }
+      else { rights[nr++] = list[j]; lefts[nl++] = nid; }
+    }
+  }
+  S->anc[node] = anc;
+  S->anc_left[node] = anc_left;
+  const uint64_t bit = (uint64_t)1 << node;
+  const int l = build_obstacle_tree(S, lefts, nl, anc | bit, anc_left | bit);
+  const int r = build_obstacle_tree(S, rights, nr, anc | bit, anc_left);
+  S->left[node] = l;
+  S->right[node] = r;
+  return node;
+}
+
+/* RVOSimulator::addObstacle for every polygon, then processObstacles (= buildObstacleTree). */
+static int pack_obstacles(const float *xy, const int32_t *poly_size, int32_t n_poly, int cap, obst_set *S) {
+  memset(S, 0, sizeof(*S));
+  S->cap = cap < OBST_MAX ? cap : OBST_MAX;
+  int off = 0;
+  for (int p = 0; p < n_poly; ++p) {
+    const int m = poly_size[p];
+    if (m < 2 || S->n + m > S->cap) return -1;
+    const float *q = xy + (size_t)off * 2;
+    const int base = S->n;
+    for (int i = 0; i < m; ++i) {
+      obst_t *o = &S->v[base + i];
+      const int nx = i == m - 1 ? 0 : i + 1, pr = i == 0 ? m - 1 : i - 1;
+      o->px = q[i * 2]; o->py = q[i * 2 + 1];
+      o->next = base + nx; o->prev = base + pr;
+      const float dx = q[nx * 2] - q[i * 2], dy = q[nx * 2 + 1] - q[i * 2 + 1];
+      const float inv = 1.0f / sqrtf(dot2(dx, dy, dx, dy)); /* normalize(v) = v / abs(v), v / s = v * (1 / s) */
+      o->ux = dx * inv; o->uy = dy * inv;
+      o->convex = m == 2 ? 1 : (left_of(q[pr * 2], q[pr * 2 + 1], q[i * 2], q[i * 2 + 1], q[nx * 2], q[nx * 2 + 1]) >= 0.0f);
+    }
+    S->n += m;
+    off += m;
+  }
+  int list[OBST_MAX];
+  for (int i = 0; i < S->n; ++i) list[i] = i;
+  const int n0 = S->n;
+  S->root = build_obstacle_tree(S, list, n0, 0, 0);
+  return S->overflow ? -1 : 0;
+}
+
+int ebc_ref_pack_obstacles(const float *xy, const int32_t *poly_size, int32_t n_poly, ebc_obst_vertex *out,
+                           int32_t cap, int32_t *n_out) {
+  if (!poly_size || !out || !n_out || n_poly < 0 || cap < 0 || (n_poly > 0 && !xy)) return EBC_ERR_INVALID;
+  obst_set S;
+  if (pack_obstacles(xy, poly_size, n_poly, cap, &S)) return EBC_ERR_INVALID;
+  for (int i = 0; i < S.n; ++i) {
+    memset(&out[i], 0, sizeof(out[i]));
+    out[i].px = S.v[i].px; out[i].py = S.v[i].py; out[i].ux = S.v[i].ux; out[i].uy = S.v[i].uy;
+    out[i].next = (int16_t)S.v[i].next; out[i].prev = (int16_t)S.v[i].prev;
+    out[i].convex = (int16_t)S.v[i].convex;
+    out[i].anc = S.anc[i]; out[i].anc_left = S.anc_left[i];
+  }
+  *n_out = S.n;
+  return EBC_OK;
+}
+
+/* Rebuild the tree's child links from the packed records (anc / anc_left). */
+static void unpack_obstacles(const ebc_obst_vertex *rec, int n, obst_set *S) {
+  memset(S, 0, sizeof(*S));
+  S->n = n;
+  S->root = -1;
+  for (int i = 0; i < n; ++i) {
+    S->v[i].px = rec[i].px; S->v[i].py = rec[i].py; S->v[i].ux = rec[i].ux; S->v[i].uy = rec[i].uy;
+    S->v[i].next = rec[i].next; S->v[i].prev = rec[i].prev; S->v[i].convex = rec[i].convex;
+    S->anc[i] = rec[i].anc; S->anc_left[i] = rec[i].anc_left;
+    S->left[i] = S->right[i] = -1;
+  }
+  for (int i = 0; i < n; ++i) {
+    if (S->anc[i] == 0) { S->root = i; continue; }
+    /* parent = the ancestor whose own ancestor set is anc[i] minus itself */
+    for (int z = 0; z < n; ++z) {
+      const uint64_t bit = (uint64_t)1 << z;
+      if ((S->anc[i] & bit) && S->anc[z] == (S->anc[i] & ~bit)) {
+        if (S->anc_left[i] & bit) S->left[z] = i; else S->right[z] = i;
+        break;
+      }
+    }
+  }
+}
+
+/* distSqPointLineSegment(a, b, c) */
+static inline float dist_sq_point_segment(float ax, float ay, float bx, float by, float cx, float cy) {
+  const float r = dot2(cx - ax, cy - ay, bx - ax, by - ay) / dot2(bx - ax, by - ay, bx - ax, by - ay);
+  if (r < 0.0f) return dot2(cx - ax, cy - ay, cx - ax, cy - ay);
+  if (r > 1.0f) return dot2(cx - bx, cy - by, cx - bx, cy - by);
+  const float qx = cx - (ax + r * (bx - ax)), qy = cy - (ay + r * (by - ay));
+  return dot2(qx, qy, qx, qy);
+}
+
+typedef struct { int id[OBST_MAX]; float d[OBST_MAX]; int n; } obst_nb;
+
+/* KdTree::queryObstacleTreeRecursive + Agent::insertObstacleNeighbor */
+static void query_obstacle_tree(const obst_set *S, int node, float px, float py, float range_sq, obst_nb *nb) {
+  if (node < 0) return;
+  const obst_t *o1 = &S->v[node], *o2 = &S->v[o1->next];
+  const float agent_left = left_of(o1->px, o1->py, o2->px, o2->py, px, py);
+  query_obstacle_tree(S, agent_left >= 0.0f ? S->left[node] : S->right[node], px, py, range_sq, nb);
+  const float ex = o2->px - o1->px, ey = o2->py - o1->py;
+  const float dist_sq_line = agent_left * agent_left / dot2(ex, ey, ex, ey);
+  if (dist_sq_line < range_sq) {
+    if (agent_left < 0.0f) { /* agent on the right side: it can see this edge */
+      const float d = dist_sq_point_segment(o1->px, o1->py, o2->px, o2->py, px, py);
+      if (d < range_sq) {
+        int i = nb->n++;
+        while (i != 0 && d < nb->d[i - 1]) { nb->d[i] = nb->d[i - 1]; nb->id[i] = nb->id[i - 1]; --i; }
+        nb->d[i] = d; nb->id[i] = node;
+      }
+    }
+    query_obstacle_tree(S, agent_left >= 0.0f ? S->right[node] : S->left[node], px, py, range_sq, nb);
+  }
+}
+
+/* Agent::computeNewVelocity, "Create obstacle ORCA lines".  Returns numObstLines. */
+static int obstacle_lines(const obst_set *S, float px, float py, float vx, float vy, float radius, float max_speed,
+                          float time_horizon_obst, line_t *L) {
+  obst_nb nb;
+  nb.n = 0;
+  const float rr = time_horizon_obst * max_speed + radius;
+  query_obstacle_tree(S, S->root, px, py, rr * rr, &nb); /* Agent::computeNeighbors */
+  const float inv_th = 1.0f / time_horizon_obst;
+  int n = 0;
+  for (int i = 0; i < nb.n; ++i) {
+    const obst_t *o1 = &S->v[nb.id[i]], *o2 = &S->v[o1->next];
+    const float r1x = o1->px - px, r1y = o1->py - py, r2x = o2->px - px, r2y = o2->py - py;
+    int covered = 0;
+    for (int j = 0; j < n; ++j) {
+      if (det2(inv_th * r1x - L[j].px, inv_th * r1y - L[j].py, L[j].dx, L[j].dy) - inv_th * radius >= -RVO_EPSILON &&
+          det2(inv_th * r2x - L[j].px, inv_th * r2y - L[j].py, L[j].dx, L[j].dy) - inv_th * radius >= -RVO_EPSILON) {
+        covered = 1;
+        break;
+      }
+    }
+    if (covered) continue;
+    const float d1 = dot2(r1x, r1y, r1x, r1y), d2 = dot2(r2x, r2y, r2x, r2y);
+    const float rsq = radius * radius;
+    const float ovx = o2->px - o1->px, ovy = o2->py - o1->py;
+    const float s = dot2(-r1x, -r1y, ovx, ovy) / dot2(ovx, ovy, ovx, ovy);
+    const float qx = -r1x - s * ovx, qy = -r1y - s * ovy;
+    const float dline = dot2(qx, qy, qx, qy);
+    line_t ln;
+    if (s < 0.0f && d1 <= rsq) { /* collision with the left vertex; ignore if non-convex */
+      if (o1->convex) {
+        ln.px = 0.0f; ln.py = 0.0f;
+        const float inv = 1.0f / sqrtf(dot2(-r1y, r1x, -r1y, r1x));
+        ln.dx = -r1y * inv; ln.dy = r1x * inv;
+        L[n++] = ln;
+      }
+      continue;
+    } else if (s > 1.0f && d2 <= rsq) { /* right vertex; ignore if non-convex or handled by the neighbouring edge */
+      if (o2->convex && det2(r2x, r2y, o2->ux, o2->uy) >= 0.0f) {
+        ln.px = 0.0f; ln.py = 0.0f;
+        const float inv = 1.0f / sqrtf(dot2(-r2y, r2x, -r2y, r2x));
+        ln.dx = -r2y * inv; ln.dy = r2x * inv;
+        L[n++] = ln;
+      }
+      continue;
+    } else if (s >= 0.0f && s < 1.0f && dline <= rsq) { /* collision with the segment */
+      ln.px = 0.0f; ln.py = 0.0f;
+      ln.dx = -o1->ux; ln.dy = -o1->uy;
+      L[n++] = ln;
+      continue;
+    }
+    /* no collision: legs */
+    float llx, lly, rlx, rly;
+    const obst_t *a1 = o1, *a2 = o2; /* obstacle1 / obstacle2 after the oblique-view reassignment */
+    if (s < 0.0f && dline <= rsq) {
+      if (!o1->convex) continue;
+      a2 = o1;
+      const float leg1 = sqrtf(d1 - rsq);
+      const float inv = 1.0f / d1;
+      llx = (r1x * leg1 - r1y * radius) * inv; lly = (r1x * radius + r1y * leg1) * inv;
+      rlx = (r1x * leg1 + r1y * radius) * inv; rly = (-r1x * radius + r1y * leg1) * inv;
+    } else if (s > 1.0f && dline <= rsq) {
+      if (!o2->convex) continue;
+      a1 = o2;
+      const float leg2 = sqrtf(d2 - rsq);
+      const float inv = 1.0f / d2;
+      llx = (r2x * leg2 - r2y * radius) * inv; lly = (r2x * radius + r2y * leg2) * inv;
+      rlx = (r2x * leg2 + r2y * radius) * inv; rly = (-r2x * radius + r2y * leg2) * inv;
+    } else {
+      if (o1->convex) {
+        const float leg1 = sqrtf(d1 - rsq);
+        const float inv = 1.0f / d1;
+        llx = (r1x * leg1 - r1y * radius) * inv; lly = (r1x * radius + r1y * leg1) * inv;
+      } else { llx = -o1->ux; lly = -o1->uy; }
+      if (o2->convex) {
+        const float leg2 = sqrtf(d2 - rsq);
+        const float inv = 1.0f / d2;
+        rlx = (r2x * leg2 + r2y * radius) * inv; rly = (-r2x * radius + r2y * leg2) * inv;
+      } else { rlx = o1->ux; rly = o1->uy; }
+    }
+    /* legs never point into the neighbouring edge of a convex vertex */
+    const obst_t *ln_left = &S->v[a1->prev];
+    int left_foreign = 0, right_foreign = 0;
+    if (a1->convex && det2(llx, lly, -ln_left->ux, -ln_left->uy) >= 0.0f) {
+      llx = -ln_left->ux; lly = -ln_left->uy;
+      left_foreign = 1;
+    }
+    if (a2->convex && det2(rlx, rly, a2->ux, a2->uy) <= 0.0f) {
+      rlx = a2->ux; rly = a2->uy;
+      right_foreign = 1;
+    }
+    const float lcx = inv_th * (a1->px - px), lcy = inv_th * (a1->py - py);
+    const float rcx = inv_th * (a2->px - px), rcy = inv_th * (a2->py - py);
+    const float cvx = rcx - lcx, cvy = rcy - lcy;
+    const int same = a1 == a2;
+    const float t = same ? 0.5f : dot2(vx - lcx, vy - lcy, cvx, cvy) / dot2(cvx, cvy, cvx, cvy);
+    const float tl = dot2(vx - lcx, vy - lcy, llx, lly);
+    const float tr = dot2(vx - rcx, vy - rcy, rlx, rly);
+    if ((t < 0.0f && tl < 0.0f) || (same && tl < 0.0f && tr < 0.0f)) { /* left cut-off circle */
+      const float wx = vx - lcx, wy = vy - lcy;
+      const float inv = 1.0f / sqrtf(dot2(wx, wy, wx, wy));
+      const float ux = wx * inv, uy = wy * inv;
+      ln.dx = uy; ln.dy = -ux;
+      ln.px = lcx + radius * inv_th * ux; ln.py = lcy + radius * inv_th * uy;
+      L[n++] = ln;
+      continue;
+    } else if (t > 1.0f && tr < 0.0f) { /* right cut-off circle */
+      const float wx = vx - rcx, wy = vy - rcy;
+      const float inv = 1.0f / sqrtf(dot2(wx, wy, wx, wy));
+      const float ux = wx * inv, uy = wy * inv;
+      ln.dx = uy; ln.dy = -ux;
+      ln.px = rcx + radius * inv_th * ux; ln.py = rcy + radius * inv_th * uy;
+      L[n++] = ln;
+      continue;
+    }
+    float dcut, dleft, dright;
+    if (t < 0.0f || t > 1.0f || same) dcut = INFINITY;
+    else { const float ax = vx - (lcx + t * cvx), ay = vy - (lcy + t * cvy); dcut = dot2(ax, ay, ax, ay); }
+    if (tl < 0.0f) dleft = INFINITY;
+    else { const float ax = vx - (lcx + tl * llx), ay = vy - (lcy + tl * lly); dleft = dot2(ax, ay, ax, ay); }
+    if (tr < 0.0f) dright = INFINITY;
+    else { const float ax = vx - (rcx + tr * rlx), ay = vy - (rcy + tr * rly); dright = dot2(ax, ay, ax, ay); }
+    if (dcut <= dleft && dcut <= dright) { /* cut-off line */
+      ln.dx = -a1->ux; ln.dy = -a1->uy;
+      ln.px = lcx + radius * inv_th * -ln.dy; ln.py = lcy + radius * inv_th * ln.dx;
+      L[n++] = ln;
+      continue;
+    } else if (dleft <= dright) { /* left leg */
+      if (left_foreign) continue;
+      ln.dx = llx; ln.dy = lly;
+      ln.px = lcx + radius * inv_th * -ln.dy; ln.py = lcy + radius * inv_th * ln.dx;
+      L[n++] = ln;
+      continue;
+    } else { /* right leg */
+      if (right_foreign) continue;
+      ln.dx = -rlx; ln.dy = -rly;
+      ln.px = rcx + radius * inv_th * -ln.dy; ln.py = rcy + radius * inv_th * ln.dx;
+      L[n++] = ln;
+      continue;
+    }
+  }
+  return n;
+}
+
 /* One agent's RVO2 step: computeNeighbors + computeNewVelocity (agent-agent part).
  * SURVEY Appendix A.1-A.4.  `others` are visited in index order (RVO2's kd-tree leaf
  * order for <= 10 agents; for more agents the order only matters for exact distance
@@ -153,7 +487,13 @@ void ebc_ref_orca_agent(float px, float py, float vx, float vy, float radius, fl
                         float pref_x, float pref_y, int n_other, const float *opx,
                         const float *opy, const float *ovx, const float *ovy, const float *orad,
                         float neighbor_dist, int max_neighbors, float time_horizon,
-                        float time_step, float *out_vx, float *out_vy) {
+                        float time_step, const void *obstacles, float time_horizon_obst, float *out_vx,
+                        float *out_vy) {
+  line_t L[MAX_LINES];
+  /* obstacle ORCA lines come first (Agent::computeNewVelocity); `obstacles` = an obst_set or NULL */
+  const int num_obst = obstacles ? obstacle_lines((const obst_set *)obstacles, px, py, vx, vy, radius, max_speed,
+                                                  time_horizon_obst, L)
+                                 : 0;
   int nb[MAX_LINES];
   float nbd[MAX_LINES];
   int cnt = 0;
@@ -177,8 +517,8 @@ void ebc_ref_orca_agent(float px, float py, float vx, float vy, float radius, fl
       }
     }
   }
-  line_t L[MAX_LINES];
   const float inv_th = 1.0f / time_horizon;
+  if (cnt > MAX_LINES - num_obst) cnt = MAX_LINES - num_obst;
   for (int k = 0; k < cnt; ++k) {
     const int j = nb[k];
     const float rpx = opx[j] - px, rpy = opy[j] - py;
@@ -229,11 +569,12 @@ void ebc_ref_orca_agent(float px, float py, float vx, float vy, float radius, fl
     }
     ln.px = vx + 0.5f * ux;
     ln.py = vy + 0.5f * uy;
-    L[k] = ln;
+    L[num_obst + k] = ln;
   }
   float rx, ry;
-  const int fail = lp2(L, cnt, max_speed, pref_x, pref_y, 0, &rx, &ry);
-  if (fail < cnt) lp3(L, cnt, 0, fail, max_speed, &rx, &ry);
+  const int total = num_obst + cnt;
+  const int fail = lp2(L, total, max_speed, pref_x, pref_y, 0, &rx, &ry);
+  if (fail < total) lp3(L, total, num_obst, fail, max_speed, &rx, &ry);
   *out_vx = rx;
   *out_vy = ry;
 }
@@ -246,8 +587,12 @@ void ebc_ref_orca_agent(float px, float py, float vx, float vy, float radius, fl
 typedef struct {
   float ts;
   int n, cap;
-  float *px, *py, *vx, *vy, *prx, *pry, *rad, *maxs, *nd, *th;
+  float *px, *py, *vx, *vy, *prx, *pry, *rad, *maxs, *nd, *th, *tho;
   int *maxn;
+  float oxy[2 * OBST_MAX]; /* addObstacle vertices, processed by processObstacles */
+  int32_t opoly[OBST_MAX];
+  int on, opolys, obst_ready;
+  obst_set obst;
 } rvo_sim;
 
 void *ebc_rvo_create(float time_step) {
@@ -259,7 +604,7 @@ void ebc_rvo_destroy(void *h) {
   rvo_sim *s = (rvo_sim *)h;
   if (!s) return;
   free(s->px); free(s->py); free(s->vx); free(s->vy); free(s->prx); free(s->pry);
-  free(s->rad); free(s->maxs); free(s->nd); free(s->th); free(s->maxn);
+  free(s->rad); free(s->maxs); free(s->nd); free(s->th); free(s->maxn); free(s->tho);
   free(s);
 }
 int ebc_rvo_add_agent(void *h, float px, float py, float nd, int maxn, float th, float rad,
@@ -270,13 +615,30 @@ int ebc_rvo_add_agent(void *h, float px, float py, float nd, int maxn, float th,
 #define GROW(p, T) s->p = (T *)realloc(s->p, sizeof(T) * (size_t)s->cap)
     GROW(px, float); GROW(py, float); GROW(vx, float); GROW(vy, float); GROW(prx, float);
     GROW(pry, float); GROW(rad, float); GROW(maxs, float); GROW(nd, float); GROW(th, float);
-    GROW(maxn, int);
+    GROW(tho, float); GROW(maxn, int);
 #undef GROW
   }
   const int i = s->n++;
   s->px[i] = px; s->py[i] = py; s->vx[i] = vx; s->vy[i] = vy; s->prx[i] = 0; s->pry[i] = 0;
   s->rad[i] = rad; s->maxs[i] = maxs; s->nd[i] = nd; s->th[i] = th; s->maxn[i] = maxn;
+  s->tho[i] = th; /* timeHorizonObst: set separately by ebc_rvo_set_time_horizon_obst (orca*.py pass 5 for both) */
   return i;
+}
+void ebc_rvo_set_time_horizon_obst(void *h, int i, float tho) { ((rvo_sim *)h)->tho[i] = tho; }
+/* RVOSimulator::addObstacle / processObstacles (orca_obstacles.py:105-107) */
+int ebc_rvo_add_obstacle(void *h, const float *xy, int n) {
+  rvo_sim *s = (rvo_sim *)h;
+  if (n < 2 || s->on + n > OBST_MAX || s->opolys >= OBST_MAX) return -1;
+  memcpy(s->oxy + 2 * s->on, xy, sizeof(float) * 2 * (size_t)n);
+  s->on += n;
+  s->opoly[s->opolys] = n;
+  return s->opolys++;
+}
+int ebc_rvo_process_obstacles(void *h) {
+  rvo_sim *s = (rvo_sim *)h;
+  if (pack_obstacles(s->oxy, s->opoly, s->opolys, OBST_MAX, &s->obst)) return -1;
+  s->obst_ready = 1;
+  return 0;
 }
 int ebc_rvo_num_agents(void *h) { return ((rvo_sim *)h)->n; }
 void ebc_rvo_set_pos(void *h, int i, float x, float y) { rvo_sim *s = h; s->px[i] = x; s->py[i] = y; }
@@ -301,7 +663,7 @@ void ebc_rvo_do_step(void *h) {
     }
     ebc_ref_orca_agent(s->px[i], s->py[i], s->vx[i], s->vy[i], s->rad[i], s->maxs[i], s->prx[i],
                        s->pry[i], m, ox, oy, ovx, ovy, orad, s->nd[i], s->maxn[i], s->th[i],
-                       s->ts, &nvx[i], &nvy[i]);
+                       s->ts, s->obst_ready ? &s->obst : NULL, s->tho[i], &nvx[i], &nvy[i]);
   }
   for (int i = 0; i < n; ++i) {
     s->vx[i] = nvx[i];
@@ -318,6 +680,7 @@ void ebc_rvo_do_step(void *h) {
 struct ebc_sim {
   ebc_config cfg;
   ebc_state st;
+  ebc_stats stats; /* all-null when unbound */
   int bound;
   double *actions; /* A*2 */
   int have_actions;
@@ -343,7 +706,8 @@ int ebc_ref_create(const ebc_config *cfg, ebc_sim **out) {
   if (cfg->abi_version != EBC_ABI_VERSION) return fail(NULL, EBC_ERR_INVALID, "abi_version mismatch");
   if (cfg->n_episodes < 1 || cfg->max_humans < 1 || cfg->max_humans > 64 || cfg->max_statics < 0 ||
       cfg->max_humans + cfg->max_statics > 64 || cfg->max_rects < 0 || cfg->n_actions < 1 ||
-      cfg->n_actions > 256 || cfg->orca_max_neighbors < 0 || cfg->orca_max_neighbors > 64)
+      cfg->n_actions > 256 || cfg->orca_max_neighbors < 0 || cfg->orca_max_neighbors > 64 ||
+      cfg->max_obst < 0 || cfg->max_obst > OBST_MAX || (cfg->orca_obstacles && !(cfg->orca_time_horizon_obst > 0.0f)))
     return fail(NULL, EBC_ERR_INVALID, "config out of range");
   ebc_sim *s = (ebc_sim *)calloc(1, sizeof(ebc_sim));
   if (!s) return fail(NULL, EBC_ERR_NOMEM, "calloc failed");
@@ -369,6 +733,18 @@ int ebc_ref_bind(ebc_sim *s, const ebc_state *st) {
     return fail(s, EBC_ERR_INVALID, "ebc_bind: null state array");
   s->st = *st;
   s->bound = 1;
+  return EBC_OK;
+}
+
+/* Running statistics of the explorer's inner loop: rl/utils/explorer.py:33-94 (too_close, min_dist, outcome of the
+ * last step), :189-193 (cumulative discounted reward), rl/test_parallel.py:52-130. */
+int ebc_ref_bind_stats(ebc_sim *s, const ebc_stats *x) {
+  if (!s) return EBC_ERR_INVALID;
+  if (!x) { memset(&s->stats, 0, sizeof(s->stats)); return EBC_OK; }
+  if (!x->alive || !x->final_event || !x->steps || !x->too_close || !x->cum_reward || !x->discount ||
+      !x->min_dist_sum || !x->alive_count)
+    return fail(s, EBC_ERR_INVALID, "ebc_bind_stats: null statistics array");
+  s->stats = *x;
   return EBC_OK;
 }
 
@@ -442,6 +818,9 @@ int ebc_ref_orca(ebc_sim *s) {
     const uint8_t *ty = s->st.hum_type + (size_t)e * Hm;
     float *nv = s->st.hum_nv + (size_t)e * Hm * 2;
     float ox[65], oy[65], ovx[65], ovy[65], orad[65];
+    obst_set obst;
+    const int use_obst = c->orca_obstacles && s->st.obst && s->st.obst_count;
+    if (use_obst) unpack_obstacles(s->st.obst + (size_t)e * c->max_obst, s->st.obst_count[e], &obst);
     for (int h = 0; h < H; ++h) {
       const float px = pv[h * 4], py = pv[h * 4 + 1], vx = pv[h * 4 + 2], vy = pv[h * 4 + 3];
       const float gx = gr[h * 4], gy = gr[h * 4 + 1], vpref = gr[h * 4 + 2], rad = gr[h * 4 + 3];
@@ -469,7 +848,8 @@ int ebc_ref_orca(ebc_sim *s) {
       orca_self_params(px, py, gx, gy, rad, c->orca_safety_space, &r_self, &prefx, &prefy);
       ebc_ref_orca_agent(px, py, vx, vy, r_self, vpref, prefx, prefy, m, ox, oy, ovx, ovy, orad,
                          c->orca_neighbor_dist, c->orca_max_neighbors, c->orca_time_horizon,
-                         (float)c->time_step, &nv[h * 2], &nv[h * 2 + 1]);
+                         (float)c->time_step, use_obst ? &obst : NULL, c->orca_time_horizon_obst,
+                         &nv[h * 2], &nv[h * 2 + 1]);
     }
   }
   return EBC_OK;
@@ -487,6 +867,9 @@ int ebc_ref_robot_orca(ebc_sim *s, double safety, double *out) {
     const float *pv = s->st.hum_pv + (size_t)e * Hm * 4;
     const float *gr = s->st.hum_gr + (size_t)e * Hm * 4;
     float ox[65], oy[65], ovx[65], ovy[65], orad[65];
+    obst_set obst;
+    const int use_obst = c->orca_obstacles && s->st.obst && s->st.obst_count;
+    if (use_obst) unpack_obstacles(s->st.obst + (size_t)e * c->max_obst, s->st.obst_count[e], &obst);
     int m = 0;
     for (int j = 0; j < H; ++j) {
       ox[m] = pv[j * 4]; oy[m] = pv[j * 4 + 1]; ovx[m] = pv[j * 4 + 2]; ovy[m] = pv[j * 4 + 3];
@@ -505,7 +888,7 @@ int ebc_ref_robot_orca(ebc_sim *s, double safety, double *out) {
     orca_self_params(rp[0], rp[1], rg[0], rg[1], rg[3], safety, &r_self, &prefx, &prefy);
     ebc_ref_orca_agent(rp[0], rp[1], rp[2], rp[3], r_self, rg[2], prefx, prefy, m, ox, oy, ovx, ovy,
                        orad, c->orca_neighbor_dist, c->orca_max_neighbors, c->orca_time_horizon,
-                       (float)c->time_step, &vx, &vy);
+                       (float)c->time_step, use_obst ? &obst : NULL, c->orca_time_horizon_obst, &vx, &vy);
     out[(size_t)e * 2] = (double)vx;
     out[(size_t)e * 2 + 1] = (double)vy;
   }
@@ -530,6 +913,7 @@ typedef struct {
   double end_x, end_y; /* robot next position (agent.py:164-188) */
   double dist_to_goal;
   double reward;
+  double min_dist; /* Danger.min_dist (reward.py:138-166) */
   int done, event;
 } outcome_t;
 
@@ -605,6 +989,7 @@ static void evaluate_action(const ebc_sim *s, int e, double a0, double a1, outco
   double reward = c->new_reward ? goal_reward : 0.0;
   const double gt = s->st.time[e];
   int done, ev;
+  o->min_dist = 0.0;
   if (gt >= c->time_limit) { done = 1; ev = EBC_EV_TIMEOUT; }
   else if (o->coll[EBC_CHILD]) { reward += c->collision_penalty_child; done = 1; ev = EBC_EV_COLLISION_CHILD; }
   else if (o->coll[EBC_BICYCLE]) { reward += c->collision_penalty_bicycle; done = 1; ev = EBC_EV_COLLISION_BICYCLE; }
@@ -623,12 +1008,15 @@ static void evaluate_action(const ebc_sim *s, int e, double a0, double a1, outco
     done = 1; ev = EBC_EV_REACH_GOAL;
   } else if (o->dmin[EBC_CHILD] < c->discomfort_dist_child) {
     reward = (o->dmin[EBC_CHILD] - c->discomfort_dist_child) * c->discomfort_penalty_factor_child * dt;
+    o->min_dist = o->dmin[EBC_CHILD];
     done = 0; ev = EBC_EV_DANGER;
   } else if (o->dmin[EBC_BICYCLE] < c->discomfort_dist_bicycle) {
     reward = (o->dmin[EBC_BICYCLE] - c->discomfort_dist_bicycle) * c->discomfort_penalty_factor_bicycle * dt;
+    o->min_dist = o->dmin[EBC_BICYCLE];
     done = 0; ev = EBC_EV_DANGER;
   } else if (o->dmin[EBC_ADULT] < c->discomfort_dist_adult) {
     reward = (o->dmin[EBC_ADULT] - c->discomfort_dist_adult) * c->discomfort_penalty_factor_adult * dt;
+    o->min_dist = o->dmin[EBC_ADULT];
     done = 0; ev = EBC_EV_DANGER;
   } else if (c->robot_kinematics != EBC_KIN_HOLONOMIC && fabs(a1) > 0.0 && c->rotation_penalty_factor != 0.0) {
     reward = fabs(a1) * c->rotation_penalty_factor;
@@ -891,7 +1279,10 @@ int ebc_ref_step(ebc_sim *s, const int32_t *action_idx, const double *action, co
   const ebc_config *c = &s->cfg;
   const int Hm = c->max_humans;
   const double dt = c->time_step;
-#pragma omp parallel for schedule(static) num_threads(g_threads)
+  const ebc_stats *sx = &s->stats;
+  if (!active && sx->alive) active = sx->alive;
+  int finished = 0;
+#pragma omp parallel for schedule(static) num_threads(g_threads) reduction(+ : finished)
   for (int e = 0; e < c->n_episodes; ++e) {
     if (active && !active[e]) continue;
     double a0, a1;
@@ -932,7 +1323,23 @@ int ebc_ref_step(ebc_sim *s, const int32_t *action_idx, const double *action, co
       pv[h * 4 + 3] = nv[h * 2 + 1];
     }
     s->st.time[e] += dt;
+    if (sx->alive) {
+      const double disc = sx->discount[e];
+      sx->cum_reward[e] += disc * o.reward; /* explorer.py:189-193 */
+      sx->discount[e] = disc * pow(c->gamma, dt * (double)s->st.rob_gr[(size_t)e * 4 + 2]);
+      sx->steps[e] += 1;
+      if (o.event == EBC_EV_DANGER) { /* explorer.py:47-49 */
+        sx->too_close[e] += 1;
+        sx->min_dist_sum[e] += o.min_dist;
+      }
+      if (o.done) {
+        sx->final_event[e] = (uint8_t)o.event;
+        sx->alive[e] = 0;
+        finished += 1;
+      }
+    }
   }
+  if (sx->alive) sx->alive_count[0] -= finished;
   return EBC_OK;
 }
 
@@ -960,6 +1367,11 @@ int ebc_ref_reset(ebc_sim *s, const ebc_state *pool, int32_t pool_size, const in
     memcpy(s->st.rob_gr + (size_t)e * 4, pool->rob_gr + (size_t)q * 4, sizeof(float) * 4);
     s->st.rob_theta[e] = pool->rob_theta[q];
     s->st.time[e] = pool->time[q];
+    if (c->max_obst && s->st.obst && pool->obst && s->st.obst_count && pool->obst_count) {
+      memcpy(s->st.obst + (size_t)e * c->max_obst, pool->obst + (size_t)q * c->max_obst,
+             sizeof(ebc_obst_vertex) * (size_t)c->max_obst);
+      s->st.obst_count[e] = pool->obst_count[q];
+    }
   }
   return EBC_OK;
 }

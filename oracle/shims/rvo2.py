@@ -21,6 +21,11 @@ for _n in ("ebc_rvo_set_pos", "ebc_rvo_set_vel", "ebc_rvo_set_pref"):
 for _n in ("ebc_rvo_get_vel", "ebc_rvo_get_pos"):
     getattr(_lib, _n).argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(_f), ctypes.POINTER(_f)]
 _lib.ebc_rvo_do_step.argtypes = [ctypes.c_void_p]
+_lib.ebc_rvo_set_time_horizon_obst.argtypes = [ctypes.c_void_p, ctypes.c_int, _f]
+_lib.ebc_rvo_add_obstacle.argtypes = [ctypes.c_void_p, ctypes.POINTER(_f), ctypes.c_int]
+_lib.ebc_rvo_add_obstacle.restype = ctypes.c_int
+_lib.ebc_rvo_process_obstacles.argtypes = [ctypes.c_void_p]
+_lib.ebc_rvo_process_obstacles.restype = ctypes.c_int
 
 
 class PyRVOSimulator(object):
@@ -42,8 +47,10 @@ class PyRVOSimulator(object):
         timeHorizon = d[2] if timeHorizon is None else timeHorizon
         radius = d[4] if radius is None else radius
         maxSpeed = d[5] if maxSpeed is None else maxSpeed
-        return _lib.ebc_rvo_add_agent(self._h, pos[0], pos[1], neighborDist, int(maxNeighbors),
-                                      timeHorizon, radius, maxSpeed, velocity[0], velocity[1])
+        i = _lib.ebc_rvo_add_agent(self._h, pos[0], pos[1], neighborDist, int(maxNeighbors),
+                                   timeHorizon, radius, maxSpeed, velocity[0], velocity[1])
+        _lib.ebc_rvo_set_time_horizon_obst(self._h, i, d[3] if timeHorizonObst is None else timeHorizonObst)
+        return i
 
     def getNumAgents(self):
         return _lib.ebc_rvo_num_agents(self._h)
@@ -71,7 +78,13 @@ class PyRVOSimulator(object):
         return (x.value, y.value)
 
     def addObstacle(self, vertices):
-        raise NotImplementedError("obstacle ORCA lines are not on the reference's live path (SURVEY §2 #8)")
+        """RVOSimulator::addObstacle (simulator/policy/orca_obstacles.py:105-106): counter-clockwise polygon."""
+        flat = (_f * (2 * len(vertices)))(*[c for v in vertices for c in v[:2]])
+        r = _lib.ebc_rvo_add_obstacle(self._h, flat, len(vertices))
+        if r < 0:
+            raise RuntimeError("addObstacle: more than 64 obstacle vertices")
+        return r
 
     def processObstacles(self):
-        raise NotImplementedError
+        if _lib.ebc_rvo_process_obstacles(self._h) != 0:
+            raise RuntimeError("processObstacles: the kd-tree needs more than 64 obstacle vertices")

@@ -107,6 +107,20 @@ def _rank_main(rank, world, port, tmp):
     tr = Trainer(model, mem, "cpu", 8, policy=pol)
     tr.set_optimizer(0.01)
     tr.optimize_batch(3)
+    # imitation-learning shape: per-rank shards whose sizes straddle the batch size (ceil(40/16) = 3 vs ceil(9/16) = 1
+    # steps per epoch if nobody agreed) and, in a second pass, one EMPTY shard -- every rank must still issue the
+    # same number of all-reduces or the job deadlocks
+    small = ReplayMemory(64, device="cpu")
+    if rank == 0:
+        small.push_batch(torch.randn(9, 5, 13, generator=g), torch.full((9,), 5), torch.randn(9, generator=g))
+    t2 = Trainer(model, mem if rank == 1 else small, "cpu", 16, policy=pol)
+    t2.set_optimizer(0.01)
+    t2.optimize_epoch(2)                                       # 40 vs 9 samples
+    empty = ReplayMemory(64, device="cpu")
+    t3 = Trainer(model, mem if rank == 0 else empty, "cpu", 16, policy=pol)
+    t3.set_optimizer(0.01)
+    t3.optimize_epoch(1)                                       # 40 vs 0 samples
+    t3.optimize_batch(2)
     flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
     out = [torch.zeros_like(flat) for _ in range(world)]
     dist.all_gather(out, flat)
@@ -116,9 +130,9 @@ def _rank_main(rank, world, port, tmp):
     stats = type("S", (), dict(event=np.array([2, 3]) if rank == 0 else np.array([2, 7]), time=np.array([5.0, 6.0]),
                                steps=np.array([20, 24]), cum_reward=np.array([0.5, -0.2]), too_close=np.array([1, 0]),
                                min_dist_sum=np.array([0.1, 0.0])))()
-    arrays = ex._gather(stats)
-    m = ex.log_results(arrays, "test")
-    torch.save({"same": same, "version": pol.weights_version, "n": len(arrays["event"]), "sr": m["success_rate"]},
+    summary = ex._gather(stats)
+    m = ex.log_results(summary, "test")
+    torch.save({"same": same, "version": pol.weights_version, "n": int(summary[13]), "sr": m["success_rate"]},
                os.path.join(tmp, "r%d.pt" % rank))
     dist.destroy_process_group()
 
@@ -133,7 +147,7 @@ def test_two_rank_gloo_training_and_stats(tmp_path):
     mp.spawn(_rank_main, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         d = torch.load(os.path.join(str(tmp_path), "r%d.pt" % r))
-        assert d["same"] and d["version"] == 3 and d["n"] == 4 and d["sr"] == 0.5
+        assert d["same"] and d["version"] == 3 + 2 * 3 + 3 + 2 and d["n"] == 4 and d["sr"] == 0.5
 
 
 def test_episode_sharding_is_independent_of_world_size():
