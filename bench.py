@@ -21,6 +21,11 @@ One "step" = what the reference does per env step with the policy in the loop
     e2e                   the same step through the host-facing API: pinned host state -> device,
                           decide + step, observation / reward / done / event -> pinned host
     cpu_baseline          the CPU oracle (port of the reference path) on this box's cores
+    sustained             the same step back to back for >= 2 s (the board reaches its power cap there): its own
+                          ms per step, clocks, K4 TFLOP/s -- `value` / `ms_per_step` are the driver's --steps region
+`value` is the POLICY-IN-THE-LOOP metric (every agent-step pays a full 81-action lookahead through the value
+network); `sim_only` is SURVEY 8d(i)'s committed-step path, the one north_star's 1e8 agent-steps/s target is
+stated on.  `--workload cfg5` times the training loop instead (rl/train.py semantics, see run_cfg5).
 """
 import argparse
 import json
@@ -207,6 +212,143 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_cfg5(args, rank, world, local_rank):
+    """BASELINE configs[4]: the EB-CADRL reinforcement-learning loop at N GPUs (one process per GPU).
+
+    One "step" = one training iteration of rl/train.py:212-273 with data/eb-cadrl/train_50k_8x.config semantics:
+    k = --episodes-per-iter episodes per GPU (the reference's PROCESSES_NUM = 8) run to their end with epsilon-greedy
+    exploration on the shipped 24-human + 3-wall scene (decisions on K1 + K3 + K4 + K5, statistics in the step kernel),
+    TD targets from the target network (K4, second handle), replay push, then `train_batches` SGD steps of batch 100
+    with ONE NCCL all-reduce of the flat 379,202-float gradient per optimizer step.  Weights start from the shipped
+    rl_model_val fixture (the imitation-learning warm-up is not part of the timed loop)."""
+    import configparser
+    import torch.distributed as dist
+    from ebc.batched_env import BatchedEnv
+    from rl.policy.policy_factory import policy_factory
+    from rl.utils.explorer import Explorer
+    from rl.utils.memory import ReplayMemory
+    from rl.utils.trainer import Trainer
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    cfgdir = os.path.join(ROOT, "tests", "golden", "configs")
+
+    def ini(name):
+        cp = configparser.RawConfigParser()
+        assert cp.read(os.path.join(cfgdir, name)), name
+        return cp
+
+    ec, pc, tc = ini("env_ebcadrl.config"), ini("policy_ebcadrl.config"), ini("train_50k_8x.config")
+    policy = policy_factory["sarl"]()
+    policy.configure(pc)
+    weights, wsrc = value_net_weights(fixture="weights_ebcadrl.npz")
+    policy.get_model().load_state_dict({k: torch.as_tensor(v) for k, v in weights.items()})
+    policy.set_device(dev)
+    policy.set_phase("train")
+    model = policy.get_model().to(dev)
+    k = args.episodes_per_iter
+    batch_size = tc.getint("trainer", "batch_size")
+    train_batches = args.train_batches or tc.getint("train", "train_batches")
+    env = BatchedEnv(ec, policy, k, dev)
+    memory = ReplayMemory(tc.getint("train", "capacity"), device=dev)
+    trainer = Trainer(model, memory, dev, batch_size, policy=policy)
+    trainer.set_optimizer(tc.getfloat("train", "rl_learning_rate"), tc.get("train", "optimizer_algorithm", fallback="sgd"))
+    explorer = Explorer(env, None, dev, memory, policy.gamma, target_policy=policy)
+    explorer.update_target_model(model)
+    env.seed_exploration(20261018, rank)
+    epsilon = tc.getfloat("train", "epsilon_start")
+    policy.set_epsilon(epsilon)
+    episode = [0]
+    acc = {"explore_s": 0.0, "sgd_s": 0.0, "steps": 0, "decisions": 0}
+
+    def iteration(timed):
+        seeds = [episode[0] + rank * k + i for i in range(k)]     # scene_number = episode (parallel_explorer.py:43-52)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        stats, traj = env.run_episodes("train", seeds, epsilon=epsilon, record=True)
+        explorer.update_memory(traj, stats, False, True)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        trainer.optimize_batch(train_batches)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        episode[0] += k * world
+        if timed:
+            acc["explore_s"] += t1 - t0
+            acc["sgd_s"] += t2 - t1
+            acc["steps"] += int(stats.steps.sum())
+            acc["decisions"] += int(stats.steps.sum())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 1)):
+        iteration(False)
+    launches0 = env.sim.launch_count()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    wall0 = time.time()
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin.record()
+    for _ in range(args.steps):
+        iteration(True)
+    t_end.record()
+    barrier()
+    wall1 = time.time()
+    elapsed_ms = t_begin.elapsed_time(t_end)
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+    launches = env.sim.launch_count() - launches0
+    # the collective alone: the flat gradient bucket, 200 all-reduces, CUDA events
+    n_params = sum(p.numel() for p in model.parameters())
+    ar_us = None
+    if world > 1:
+        flat = torch.zeros(n_params + 1, device=dev)
+        for _ in range(20):
+            dist.all_reduce(flat)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        for _ in range(200):
+            dist.all_reduce(flat)
+        b.record()
+        torch.cuda.synchronize()
+        ar_us = a.elapsed_time(b) / 200 * 1e3
+    t = torch.tensor([elapsed_ms, acc["explore_s"], acc["sgd_s"], ar_us or 0.0], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([acc["steps"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        sec = float(t[0]) / 1e3
+        H = env.sim.Hmax
+        line = {
+            "metric": "training_episodes_per_sec", "value": args.steps * k * world / sec, "unit": "episodes/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": sec / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg5_rl_training_loop", "env": "env_ebcadrl.config (24 humans, 3 walls, D = 17)",
+                       "episodes_per_iter_per_gpu": k, "train_batches": train_batches, "batch_size": batch_size,
+                       "global_batch": batch_size * world, "weights": wsrc, "epsilon": epsilon,
+                       "parallelism": "dp%d: episodes and replay shards per rank, one flat gradient all-reduce per optimizer step" % world},
+            "decisions_per_sec": float(cnt[0]) / sec, "agent_steps_per_sec": float(cnt[0]) * (H + 1) / sec,
+            "optimizer_steps_per_sec": args.steps * train_batches / sec,
+            "phase_s_per_iteration": {"explore_and_td_targets": float(t[1]) / args.steps, "sgd": float(t[2]) / args.steps},
+            "sgd_ms_per_optimizer_step": float(t[2]) / args.steps / train_batches * 1e3,
+            "allreduce": {"bytes": (n_params + 1) * 4, "us_per_call": float(t[3]) if world > 1 else None,
+                          "calls_per_iteration": train_batches},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -214,9 +356,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--episodes", type=int, default=None, help="episodes per GPU (default: the workload's)")
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
-                    help="cfg2 = BASELINE configs[1], the bench line; cfg3 / cfg4 are side measurements")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["cfg5"],
+                    help="cfg2 = BASELINE configs[1], the bench line; cfg3 / cfg4 are side measurements; cfg5 = the RL "
+                         "training loop (configs[4]), its own metric")
+    ap.add_argument("--episodes-per-iter", type=int, default=8, help="cfg5: episodes per iteration and GPU (reference: 8)")
+    ap.add_argument("--train-batches", type=int, default=None, help="cfg5: SGD steps per iteration (default: the config's 800)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0,
+                    help="length of the extra back-to-back region reported under `sustained` (0 = skip)")
     ap.add_argument("--value-mode", default="tc_fp16x2", choices=["fp32", "tc_fp32", "tc_fp16x2", "tc_bf16"],
                     help="K4 arithmetic; tc_fp16x2 (tcgen05, fp32-accurate operand splitting) is the parity mode")
     args = ap.parse_args()
@@ -225,6 +372,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "cfg5":
+        run_cfg5(args, rank, world, local_rank)
         return
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
     if args.warmup < 3:
@@ -238,20 +388,16 @@ def main():
     else:
         dist = None
 
-    from ebc import synth
     from ebc.actions import build_action_space
-    from ebc.engine import BatchedSim
+    from ebc.batched_env import BatchedEnv
     shape, cfg = workload(args.workload)
     weights, wsrc = value_net_weights(fixture=WORKLOADS[args.workload][3])
     N = args.episodes or WORKLOADS[args.workload][4]
-    ids = np.arange(rank * N, (rank + 1) * N)           # episodes shard trivially: no data-path collective
-    scenes = synth.generate(shape, ids)
-    sim = BatchedSim(cfg, N, shape.H, shape.Smax, shape.Rmax, N_ACTIONS, device=dev)
-    sim.set_actions(build_action_space(shape.robot_v_pref, cfg.robot_kinematics))
-    sim.set_weights(weights)
-    sim.set_value_mode(args.value_mode)
-    synth.load(sim, scenes)
-    pool = sim.make_pool(scenes)
+    # episodes shard trivially: rank r owns global episode ids [r N, (r + 1) N) and, as episodes finish, the ids
+    # r N + e + k N W (fresh scenes from the device generator, keyed by the global id): no data-path collective
+    env = BatchedEnv.synthetic(cfg, shape, N, dev, build_action_space(shape.robot_v_pref, cfg.robot_kinematics), weights,
+                               value_mode=args.value_mode, first_episode_id=rank * N, id_stride=N * world)
+    sim = env.sim
     n_rows = shape.H + shape.Smax
     H = shape.H
 
@@ -266,7 +412,7 @@ def main():
         mark(); sim.value()
         mark(); sim.select()
         mark(); sim.step(action_idx=sim.argmax)
-        mark(); sim.reset(pool, mask=sim.done)
+        mark(); env.reset_done()
         mark()
 
     def barrier():
@@ -302,6 +448,30 @@ def main():
             phase_ms[nm] += m[i].elapsed_time(m[i + 1])
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
 
+    # ---- sustained regime: the same step back to back for >= --sustained-seconds (power cap, settled clocks) ----
+    sustained = None
+    if args.sustained_seconds > 0:
+        est = max(elapsed_ms / 1e3 / args.steps, 1e-4)
+        s_steps = int(min(max(args.sustained_seconds / est, args.steps), 20000)) + 1
+        s_sampler = ClockSampler(local_rank)
+        if rank == 0:
+            s_sampler.start()
+            time.sleep(0.2)
+        s_marks = []
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        sw0 = time.time()
+        s0.record()
+        for i in range(s_steps):
+            one_step(s_marks if i % 8 == 0 else None)      # K4 phase events on every 8th step
+        s1.record()
+        barrier()
+        sw1 = time.time()
+        s_ms = s0.elapsed_time(s1)
+        k4 = [s_marks[j * 7 + 2].elapsed_time(s_marks[j * 7 + 3]) for j in range(len(s_marks) // 7)]
+        sustained = {"steps": s_steps, "ms_total": s_ms, "k4_ms": float(np.median(k4)),
+                     "clocks": s_sampler.stop(sw0, sw1) if rank == 0 else None}
+
     # ---- side measurement: K4 in the other tensor-core mode on the same states + argmax agreement ------
     other = "tc_bf16" if args.value_mode != "tc_bf16" else "tc_fp16x2"
     sim.orca(); sim.lookahead(); sim.value(); sim.select()
@@ -327,19 +497,24 @@ def main():
     h_pv.copy_(sim.hum_pv); h_rob.copy_(sim.rob_pv)
     torch.cuda.synchronize()
     h2d = h_pv.numel() * 4 + h_rob.numel() * 4
-    d2h = h2d + sum(t.numel() * t.element_size() for t in h_out.values())
+    d2h = 2 * h2d + sum(t.numel() * t.element_size() for t in h_out.values())
 
     def e2e_step():
+        """One step through the batched API a user calls (BatchedEnv.decide_batch / step_batch / reset_done), the
+        caller's observation arriving in pinned HOST buffers and the result going back to them, every step."""
         sim.hum_pv.copy_(h_pv, non_blocking=True)       # the caller's observation / robot state -> device
         sim.rob_pv.copy_(h_rob, non_blocking=True)
-        sim.decide()
-        sim.step(action_idx=sim.argmax)
+        idx = env.decide_batch()
+        env.step_batch(action_idx=idx)
         h_pv.copy_(sim.hum_pv, non_blocking=True)       # new observation, reward, done, info -> host
         h_rob.copy_(sim.rob_pv, non_blocking=True)
         for k, t in h_out.items():
             t.copy_(getattr(sim, k), non_blocking=True)
         torch.cuda.synchronize()                        # the host consumes the result every step
-        sim.reset(pool, mask=sim.done)
+        env.reset_done()
+        h_pv.copy_(sim.hum_pv, non_blocking=True)       # (the re-generated episodes' first observation)
+        h_rob.copy_(sim.rob_pv, non_blocking=True)
+        torch.cuda.synchronize()
 
     e2e_steps = max(3, min(args.steps, 10))
     e2e_step()
@@ -363,7 +538,7 @@ def main():
         torch.cuda.synchronize()
         if it >= 3:
             sim_ms += a.elapsed_time(b)
-        sim.reset(pool, mask=sim.done)
+        env.reset_done()
     del flush
 
     def allmax(x):
@@ -377,6 +552,9 @@ def main():
     e2e_s = allmax(e2e_s)
     sim_ms = allmax(sim_ms)
     value_ms = allmax(phase_ms["value"])
+    if sustained is not None:
+        sustained["ms_total"] = allmax(sustained["ms_total"])
+        sustained["k4_ms"] = allmax(sustained["k4_ms"])
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -389,11 +567,27 @@ def main():
     achieved_tf = fl / (value_ms / 1e3 / args.steps) / 1e12
     sim_step_s = sim_ms / 1e3 / sim_iters
     sim_bytes = N * (48 * H + 90)
+    sim_flops = N * H * 1000.0               # ~1.0 kFLOP per human-step (ORCA LP at 9 neighbours)
+    fp32_peak = 148 * 128 * 2 * 1.965e9      # 148 SMs x 128 lanes x 2 x 1.965 GHz = 74 TFLOP/s
+    if sustained is not None:
+        s_step = sustained["ms_total"] / 1e3 / sustained["steps"]
+        sustained = {"seconds": sustained["ms_total"] / 1e3, "steps": sustained["steps"], "ms_per_step": s_step * 1e3,
+                     "value": total_eps * (H + 1) / s_step, "unit": UNIT,
+                     "lookahead_evals_per_sec": total_eps * N_ACTIONS / s_step,
+                     "k4_ms": sustained["k4_ms"], "k4_tflops": fl / (sustained["k4_ms"] / 1e3) / 1e12,
+                     "k4_frac_of_peak": fl / (sustained["k4_ms"] / 1e3) / 1e12 / peaks["tensor_tflops"],
+                     "clocks": sustained["clocks"],
+                     "note": "back-to-back steps for >= %.1f s: the board reaches its power cap and the SM clock settles "
+                             "below the maximum; the headline value above is the driver's --steps region" % args.sustained_seconds}
     line = {
         "metric": METRIC, "value": total_eps * (H + 1) / step_s, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": shape.name, "episodes_per_gpu": N, "humans": H, "static_discs": shape.Smax,
+                   "what_is_measured": "value = POLICY-IN-THE-LOOP agent-steps/s: every step is a full decision (ORCA, "
+                                       "81-action lookahead, value network, argmax) + the committed env.step + fresh scenes "
+                                       "for finished episodes (device generator); sim_only = SURVEY 8d(i), the committed-step "
+                                       "path alone, which is what north_star's 1e8 agent-steps/s is stated on",
                    "rows_per_state": n_rows, "D": cfg.D, "actions": N_ACTIONS, "weights": wsrc,
                    "parallelism": "episodes sharded over %d GPU(s), no data-path collective" % world,
                    "l2": "per-step working set %.0f MB (value-net input) exceeds the 126 MB L2; "
@@ -424,7 +618,12 @@ def main():
                      "launches_per_step": 1,
                      "roofline": {"bound": "hbm", "achieved": sim_bytes / sim_step_s / 1e9, "peak": peaks["hbm_gbs"],
                                   "unit": "GB/s", "frac": sim_bytes / sim_step_s / 1e9 / peaks["hbm_gbs"],
-                                  "note": "48*H+90 algorithmic bytes per episode-step; latency/ALU-bound at this size"}},
+                                  "alu_achieved_tflops": sim_flops / sim_step_s / 1e12, "alu_peak_tflops": fp32_peak / 1e12,
+                                  "alu_frac": sim_flops / sim_step_s / fp32_peak,
+                                  "note": "SURVEY 8d asks for both roofs: 48*H+90 algorithmic bytes per episode-step against "
+                                          "the measured HBM copy bandwidth, and ~1.0 kFLOP per human-step (ORCA LP) against the "
+                                          "74 TFLOP/s FP32 roof; at this size the launch is latency / instruction-issue bound"}},
+        "sustained": sustained,
         "e2e": {"value": total_eps * (H + 1) / (e2e_s / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps},
     }

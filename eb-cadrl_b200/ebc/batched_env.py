@@ -34,6 +34,25 @@ class _RobotStub(object):
         self.px, self.py, self.gx, self.gy, self.vx, self.vy, self.theta = px, py, gx, gy, vx, vy, theta
 
 
+class TargetValue(object):
+    """The TARGET value network of the TD update (rl/utils/explorer.py:174-186) on the K4 kernels: a second library
+    handle that only ever runs ebc_value, with its own copy of the weights (the online network keeps changing)."""
+
+    def __init__(self, env):
+        sim = env.sim
+        self.sim = BatchedSim(env.cfg, 1, sim.Hmax, sim.Smax, 0, sim.A, device=sim.device)
+        self.value_mode = getattr(env.policy, "value_mode", None)
+
+    def set_model(self, model):
+        sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+        self.sim.set_weights(sd, with_global_state=model.with_global_state, self_state_dim=model.self_state_dim)
+        if self.value_mode:
+            self.sim.set_value_mode(self.value_mode)
+
+    def __call__(self, states, rows):
+        return self.sim.value(states.contiguous(), rows.to(torch.int32).contiguous())
+
+
 class EpisodeStats(object):
     """Per-episode outcome arrays (what rl/utils/explorer.py:33-94 accumulates one episode at a time)."""
 
@@ -89,11 +108,49 @@ class BatchedEnv(object):
         # epsilon-greedy exploration stream: ONE generator for the life of the env, keyed by (seed, rank), so that
         # neither successive run_episodes calls nor different ranks replay the same explore mask / random actions
         # (the reference draws from numpy's global stream, reseeded per scene: multi_human_rl.py:31)
+        self.target_value = TargetValue(self) if (policy is not None and self.device.type == "cuda") else None
         rank = int(__import__("os").environ.get("RANK", "0"))
-        self._explore_rng = np.random.default_rng(np.random.SeedSequence([20261018, rank]))
+        self._explore_gen = torch.Generator(device=self.device)
+        self.seed_exploration(20261018, rank)
 
     def seed_exploration(self, seed, rank=0):
-        self._explore_rng = np.random.default_rng(np.random.SeedSequence([int(seed), int(rank)]))
+        self._explore_gen.manual_seed(int(np.random.SeedSequence([int(seed), int(rank)]).generate_state(1, np.uint64)[0] >> 1))
+
+    @classmethod
+    def synthetic(cls, cfg, shape, n_episodes, device, actions, weights, value_mode=None, first_episode_id=0,
+                  id_stride=None, with_global_state=True, self_state_dim=6):
+        """The N-episode face over a SYNTHETIC workload (ebc.synth.SceneShape) instead of an INI file:
+        scenes come from the device generator (ebc_generate, counter-based in the global episode id), finished
+        episodes are re-generated with FRESH scenes (`reset_done`), weights / action table are given directly.
+        Same batched calls as the INI-driven env: lookahead_batch / decide_batch / step_batch."""
+        self = cls.__new__(cls)
+        self.config, self.policy, self.scene = None, None, None
+        self.cfg, self.shape = cfg, shape
+        self.time_step, self.time_limit = cfg.time_step, cfg.time_limit
+        self.robot = type("RobotStub", (), dict(radius=shape.robot_radius, v_pref=shape.robot_v_pref, visible=cfg.robot_visible))()
+        self.N = n_episodes
+        self.sim = BatchedSim(cfg, n_episodes, shape.H, shape.Smax, shape.Rmax, len(actions), device=device)
+        self.device = self.sim.device
+        self.sim.set_actions(np.asarray(actions, dtype=np.float64))
+        self.sim.set_weights(weights, with_global_state=with_global_state, self_state_dim=self_state_dim)
+        if value_mode:
+            self.sim.set_value_mode(value_mode)
+        self._weights_version = 0
+        self.target_value = None
+        self._explore_gen = torch.Generator(device=self.device)
+        self.seed_exploration(20261018, int(__import__("os").environ.get("RANK", "0")))
+        # global episode ids: this rank owns [first, first + N); a finished episode e continues with id + stride
+        self.episode_ids = torch.arange(first_episode_id, first_episode_id + n_episodes, dtype=torch.int64, device=self.device)
+        self.id_stride = int(id_stride if id_stride is not None else n_episodes)
+        self.sim.generate(shape, self.episode_ids)
+        return self
+
+    def reset_done(self, done=None):
+        """env.reset for the episodes that just ended (default: sim.done of the last step): a fresh scene from the
+        device generator, keyed by the next global id of that slot.  No host round trip."""
+        done = self.sim.done if done is None else done
+        self.episode_ids += done.to(torch.int64) * self.id_stride
+        self.sim.generate(self.shape, self.episode_ids, mask=done)
 
     def sync_weights(self):
         model = self.policy.get_model()
@@ -146,7 +203,7 @@ class BatchedEnv(object):
         return self.sim.la_reward, self.sim.la_done, self.sim.la_event
 
     def decide_batch(self):
-        if getattr(self.policy, "weights_version", 0) != self._weights_version:
+        if self.policy is not None and getattr(self.policy, "weights_version", 0) != self._weights_version:
             self.sync_weights()
         return self.sim.decide()
 
@@ -156,66 +213,68 @@ class BatchedEnv(object):
 
     # ---- the explorer's inner loop on the device (rl/utils/explorer.py:33-94) ------------------------------
     @torch.no_grad()
-    def run_episodes(self, phase, seeds, epsilon=None, record=False, imitation=False, safety_space=0.0, rng=None):
+    def run_episodes(self, phase, seeds, epsilon=None, record=False, imitation=False, safety_space=0.0, rng=None,
+                     poll_every=8, record_dmin=False):
         """Run every episode to its end.  Returns (EpisodeStats, trajectory or None); trajectory =
-        dict(states [T, N, n, D], rewards [T, N], alive [T, N], rows [N]) on the device."""
+        dict(states [T, N, n, D], rewards [T, N], alive [T, N], rows [N]) on the device.
+
+        The running statistics (discounted return, step / danger counts, min-distance sum, final event, alive mask)
+        are accumulated by the step kernel itself (ebc_bind_stats): the loop issues launches only and reads ONE int
+        (episodes still alive) every `poll_every` steps -- no per-step host synchronisation, no eager torch
+        arithmetic.  `rng`: a torch.Generator on this device for the epsilon-greedy draws (default: the env's own,
+        persistent across calls and keyed by the rank)."""
         sim = self.sim
         self.reset_batch(phase, seeds)
         N, dev = self.N, self.device
-        active = torch.ones(N, dtype=torch.uint8, device=dev)
-        st = EpisodeStats(N)
-        gamma_bar = self.cfg.gamma ** (self.time_step * self.robot.v_pref)
-        disc = torch.ones(N, dtype=torch.float64, device=dev)
-        cum = torch.zeros(N, dtype=torch.float64, device=dev)
-        too_close = torch.zeros(N, dtype=torch.int64, device=dev)
-        min_sum = torch.zeros(N, dtype=torch.float64, device=dev)
-        steps = torch.zeros(N, dtype=torch.int64, device=dev)
-        final_event = torch.zeros(N, dtype=torch.int64, device=dev)
+        sx = sim.bind_stats()
         states, rewards, alive = [], [], []
-        gen = rng if rng is not None else self._explore_rng
+        dmins = []
+        nan_seen = torch.zeros(N, dtype=torch.uint8, device=dev)
+        gen = rng if rng is not None else self._explore_gen
         max_steps = int(self.time_limit / self.time_step) + 2
-        dd = torch.tensor([self.cfg.discomfort_dist_adult, self.cfg.discomfort_dist_bicycle,
-                           self.cfg.discomfort_dist_child], dtype=torch.float64, device=dev)
-        for _ in range(max_steps):
-            if not bool(active.any()):
-                break
-            if record:
-                states.append(sim.transform().clone())
-            if imitation:
-                act = sim.robot_orca(safety_space)
-                sim.orca()
-                sim.step(action=act, active=active)
-            else:
-                idx = self.decide_batch()
-                if epsilon:
-                    explore = torch.as_tensor(gen.random(N) < epsilon, device=dev)
-                    rnd = torch.as_tensor(gen.integers(0, sim.A, N), dtype=torch.int32, device=dev)
-                    idx = torch.where(explore, rnd, idx)
-                sim.step(action_idx=idx.contiguous(), active=active)
-            a = active.bool()
-            r = torch.where(a, sim.reward, torch.zeros_like(sim.reward))
-            cum += disc * r
-            disc = torch.where(a, disc * gamma_bar, disc)
-            steps += a.long()
-            danger = a & (sim.event == abi.EV_DANGER)
-            too_close += danger.long()
-            # Danger.min_dist: the first type below its discomfort distance, child > bicycle > adult
-            dm = sim.dmin
-            md = torch.where(dm[:, 2] < dd[2], dm[:, 2], torch.where(dm[:, 1] < dd[1], dm[:, 1], dm[:, 0]))
-            min_sum += torch.where(danger, md, torch.zeros_like(md))
-            finished = a & sim.done.bool()
-            final_event = torch.where(finished, sim.event.long(), final_event)
-            if record:
-                rewards.append(r.clone())
-                alive.append(a.clone())
-            active = (a & ~finished).to(torch.uint8)
-        st.event = final_event.cpu().numpy()
+        try:
+            for t in range(max_steps):
+                if t % poll_every == 0 and t > 0:
+                    if int(sx["alive_count"].item()) == 0:
+                        break
+                    if bool(nan_seen.any()):
+                        raise ValueError("Value network is not well trained. ")      # multi_human_rl.py:81-82
+                if record or record_dmin:
+                    alive.append(sx["alive"].bool().clone())
+                if record:
+                    states.append(sim.transform().clone())
+                if imitation:
+                    act = sim.robot_orca(safety_space)
+                    sim.orca()
+                    sim.step(action=act)
+                else:
+                    idx = self.decide_batch()
+                    nan_seen |= sim.nan_flag & sx["alive"]
+                    if epsilon:
+                        explore = torch.rand(N, device=dev, generator=gen) < epsilon
+                        rnd = torch.randint(0, sim.A, (N,), device=dev, generator=gen, dtype=torch.int32)
+                        idx = torch.where(explore, rnd, idx).contiguous()
+                    sim.step(action_idx=idx)
+                if record:
+                    rewards.append(torch.where(alive[-1], sim.reward, torch.zeros_like(sim.reward)))
+                if record_dmin:
+                    dmins.append(sim.dmin.clone())
+            if bool(nan_seen.any()):
+                raise ValueError("Value network is not well trained. ")
+        finally:
+            sim.unbind_stats()
+        st = EpisodeStats(N)
+        st.event = sx["final_event"].cpu().numpy().astype(np.int64)
         st.time = sim.time.cpu().numpy().copy()
-        st.steps = steps.cpu().numpy()
-        st.cum_reward = cum.cpu().numpy()
-        st.too_close = too_close.cpu().numpy()
-        st.min_dist_sum = min_sum.cpu().numpy()
-        st.still_running = active.cpu().numpy().astype(bool)
+        st.steps = sx["steps"].cpu().numpy().astype(np.int64)
+        st.cum_reward = sx["cum_reward"].cpu().numpy().copy()
+        st.too_close = sx["too_close"].cpu().numpy().astype(np.int64)
+        st.min_dist_sum = sx["min_dist_sum"].cpu().numpy().copy()
+        st.still_running = sx["alive"].cpu().numpy().astype(bool)
+        st.dist_to_goal = sim.dist_to_goal.cpu().numpy().copy()
+        if record_dmin and dmins:
+            st.dmin_trace = torch.stack(dmins).cpu().numpy()          # [T, N, 3]
+            st.alive_trace = torch.stack(alive).cpu().numpy()         # [T, N]
         traj = None
         if record and states:
             traj = {"states": torch.stack(states), "rewards": torch.stack(rewards), "alive": torch.stack(alive),

@@ -126,8 +126,8 @@ class BatchedSim(object):
 
     # ---- running episode statistics on the device (ebc_bind_stats) -----------------------------------------
     def bind_stats(self, alive=None):
-        """Allocate (first call) and re-initialise the per-episode accumulators; every committed step updates them
-        for the episodes it steps, and `step(active=None)` then uses stats['alive'] as its mask."""
+        """Allocate (first call), re-initialise and bind the per-episode accumulators; every committed step then
+        updates them for the episodes it steps, and `step(active=None)` uses stats['alive'] as its mask."""
         N = self.N
         if self.stats is None:
             z = lambda dtype: torch.zeros(N, dtype=dtype, device=self.device)  # noqa: E731
@@ -139,7 +139,6 @@ class BatchedSim(object):
             for k, t in self.stats.items():
                 setattr(sx, k, t.data_ptr())
             self._stats_abi = sx
-            self.be.call("bind_stats", self.h, ctypes.byref(sx))
         st = self.stats
         for k in ("final_event", "steps", "too_close", "cum_reward", "min_dist_sum"):
             st[k].zero_()
@@ -150,12 +149,12 @@ class BatchedSim(object):
         else:
             st["alive"].copy_(alive)
             st["alive_count"].copy_(alive.sum().to(torch.int32).reshape(1))
+        self.be.call("bind_stats", self.h, ctypes.byref(self._stats_abi))
         return st
 
     def unbind_stats(self):
-        if self.stats is not None:
-            self.be.call("bind_stats", self.h, None)
-            self.stats = None
+        """Stop accumulating (the tensors stay readable); step(active=None) steps every episode again."""
+        self.be.call("bind_stats", self.h, None)
 
     def close(self):
         if getattr(self, "h", None) is not None:

@@ -22,6 +22,11 @@ def parse_arguments(argv=None):
     p.add_argument("--phase", type=str, default="test")
     p.add_argument("--test_case", type=int, default=None)
     p.add_argument("--csv", type=str, default=None)
+    p.add_argument("--model_name", type=str, default=None)
+    p.add_argument("--square", default=False, action="store_true")
+    p.add_argument("--circle", default=False, action="store_true")
+    p.add_argument("--processes", type=int, default=None, help="accepted for compatibility (the episodes are a "
+                   "device batch, not a process pool)")
     p.add_argument("--start", type=int, default=None)
     p.add_argument("--end", type=int, default=None)
     p.add_argument("--batch", type=int, default=256, help="episodes advanced at once per GPU")
@@ -78,11 +83,10 @@ def main(argv=None):
         for i, s in enumerate(chunk):
             rows.append({"episode": s, "info": EVENT_NAMES[int(stats.event[i])], "time": float(stats.time[i]),
                          "steps": int(stats.steps[i]), "cumulative_reward": float(stats.cum_reward[i]),
-                         "too_close": int(stats.too_close[i])})
+                         "too_close": int(stats.too_close[i]), "min_dist_sum": float(stats.min_dist_sum[i])})
     arrays = {k: np.array([r[v] for r in rows]) for k, v in (("time", "time"), ("steps", "steps"),
-              ("cum_reward", "cumulative_reward"), ("too_close", "too_close"))}
+              ("cum_reward", "cumulative_reward"), ("too_close", "too_close"), ("min_dist_sum", "min_dist_sum"))}
     arrays["event"] = np.array([EVENT_NAMES.index(r["info"]) for r in rows])
-    arrays["min_dist_sum"] = np.zeros(len(rows))
     metrics = explorer.log_results(arrays, args.phase, seeds=seeds, print_failure=True)
     if args.csv:
         import pandas as pd

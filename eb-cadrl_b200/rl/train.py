@@ -152,7 +152,8 @@ def run_train(args):
             vs = [VAL_EPISODE_START + rank + world * i for i in range(-(-val_size // world))]
             explorer.run_k_episodes(len(vs), "val", episode=episode, seeds=vs)
             policy.set_phase("train")
-        seeds = [2000 + episode + rank * k + i for i in range(k)]       # scene_number = episode (parallel_explorer.py:43-52)
+        # scene_number = episode, no phase offset (parallel_explorer.py:43-52 -> scene_generator.py:356-360)
+        seeds = [episode + rank * k + i for i in range(k)]
         explorer.run_k_episodes(k, "train", update_memory=True, episode=episode, seeds=seeds, epsilon=epsilon,
                                 store_all=True)
         trainer.optimize_batch(train_batches)

@@ -34,7 +34,20 @@ class Explorer(object):
         self.metrics = {}
 
     def update_target_model(self, target_model):
+        """explorer.py:29-30.  The copy is what TD targets are computed with; on a CUDA env its weights are also
+        handed to a second K4 handle (`env.target_value`), so the target network runs on the tensor-core kernels."""
         self.target_model = copy.deepcopy(target_model)
+        tv = getattr(self.env, "target_value", None)
+        if tv is not None:
+            tv.set_model(self.target_model)
+
+    def _target_values(self, states, rows):
+        """V_target(states) -> float64 [B]; states [B, n, D] fp32, rows [B] real row counts."""
+        tv = getattr(self.env, "target_value", None)
+        if tv is not None and states.is_cuda:
+            return tv(states, rows).double()
+        model = self.target_model.to(states.device)
+        return model(states, rows).reshape(-1).double()
 
     # ---- statistics (explorer.py:96-126, 214-340) ----------------------------------------------------------
     # One fixed-size vector per rank (SURVEY 8e): 8 event counts, sum of success times, sum of returns, danger steps,
@@ -156,14 +169,15 @@ class Explorer(object):
                 run = torch.where(alive[t], rewards[t] + gamma_bar * run, run)
                 values[t] = run
         else:
-            # value_i = r_i + gamma_bar V_target(s_{i+1}); terminal: r_i  (explorer.py:174-186)
-            model = self.target_model.to(states.device)
+            # value_i = r_i + gamma_bar V_target(s_{i+1}); terminal: r_i  (explorer.py:174-186,
+            # parallel_explorer.py:313-321).  Every next state of the batch in ONE target-network evaluation.
             values = rewards.clone()
-            for t in range(T - 1):
-                nxt = alive[t + 1]
+            if T > 1:
+                nxt = alive[1:]
                 if bool(nxt.any()):
-                    v = model(states[t + 1][nxt], rows[nxt]).reshape(-1).double()
-                    values[t, nxt] += gamma_bar * v
+                    t_idx, e_idx = nxt.nonzero(as_tuple=True)
+                    v = self._target_values(states[1:][t_idx, e_idx].contiguous(), rows[e_idx].contiguous())
+                    values[:-1][t_idx, e_idx] += gamma_bar * v
         sel = alive & use[None]
         t_idx, e_idx = sel.nonzero(as_tuple=True)
         if len(t_idx):

@@ -205,6 +205,9 @@ def trace(name, env, policy, robot, env_config, policy_config, reset_kwargs, n_s
             arrays["s%03d_%s" % (t, k)] = v
         action = robot.act(ob, local_map=None, env=env)
         step = {"t": t}
+        if sarl and policy.phase == "train" and torch.is_tensor(getattr(policy, "last_state", None)):
+            # multi_human_rl.py:84-85: the replay sample = transform(current joint state), n x D
+            arrays["s%03d_last_state" % t] = policy.last_state.detach().numpy().astype(np.float32)
         if sarl and len(look) > 0:
             A = len(policy.action_space)
             assert len(look) == A and len(vout) == A
@@ -358,10 +361,122 @@ def copy_configs(out):
     print("  scenes/: %d JSON scenes" % len(os.listdir(sdst)))
 
 
+def update_memory_golden(out):
+    """The reference's own Explorer.update_memory / ParallelExplorer.update_memory (rl/utils/explorer.py:151-200,
+    parallel_explorer.py:286-330) on trajectories it produced itself: (state, value) pairs of one RL episode (TD
+    target through a target network) and one imitation-learning episode (ORCA robot, discounted returns), plus
+    which episodes the sequential explorer lets into the memory (explorer.py:82-92)."""
+    from rl.utils.explorer import Explorer
+    from rl.utils.memory import ReplayMemory
+    from rl.utils.parallel_explorer import ParallelExplorer
+    POL = "configs/test_configs/test_policy_configs/policy.config"
+    ENVC = "configs/test_configs/test_env_configs/env_adults_5.config"
+    res = {}
+    # ---- RL episode: SARL robot, train phase, epsilon 0, target network = the same weights ----
+    env, policy, robot, ec, pc = make(ENVC, POL, "model_weights/sarl_model_baseline.pth", "sarl", phase="train")
+    policy.set_epsilon(0.0)
+    env.get_local_map_angular = lambda *a, **k: None
+    captured = {}
+    for tag, store_il in (("rl", False),):
+        mem = ReplayMemory(100000)
+        ex = Explorer(env, robot, "cpu", mem, policy.gamma, target_policy=policy)
+        ex.update_target_model(policy.get_model())
+        orig = ex.update_memory
+
+        def spy(states, actions, rewards, imitation_learning=False, _orig=orig):
+            captured["states"], captured["rewards"] = states, rewards
+            return _orig(states, actions, rewards, imitation_learning)
+
+        ex.update_memory = spy
+        np.random.seed(0)
+        env.scene.case_counter["train"] = 3
+        ex.run_k_episodes(1, "train", update_memory=True, imitation_learning=False)
+        states, rewards = captured["states"], captured["rewards"]
+        res["rl_states"] = torch.stack(states).numpy().astype(np.float32)
+        res["rl_rewards"] = np.array(rewards, dtype=np.float64)
+        res["rl_values"] = np.array([float(v) for _, v in mem.memory], dtype=np.float32)
+        res["rl_mem_states"] = torch.stack([s for s, _ in mem.memory]).numpy().astype(np.float32)
+        # the parallel explorer's twin must give the same pairs
+        mem2 = ReplayMemory(100000)
+        pex = ParallelExplorer(env, robot, "cpu", 1, mem2, policy.gamma, target_policy=policy)
+        pex.update_target_model(policy.get_model())
+        pex.update_memory(states, None, rewards, False)
+        assert np.array_equal(res["rl_values"], np.array([float(v) for _, v in mem2.memory], dtype=np.float32))
+        # and its IL branch on the same rewards (states pass through transform there; values depend on rewards only)
+        gamma, dt, vp = policy.gamma, robot.time_step, robot.v_pref
+        res["il_values_of_rl_rewards"] = np.array(
+            [sum(pow(gamma, max(t - i, 0) * dt * vp) * r * (1 if t >= i else 0) for t, r in enumerate(rewards))
+             for i in range(len(rewards))], dtype=np.float32)
+        res["gamma_dt_vpref"] = np.array([gamma, dt, vp], dtype=np.float64)
+        res["cumulative_reward"] = np.array([ex.calculate_cumulative_reward(rewards)], dtype=np.float64)
+    # ---- IL episode: ORCA robot (rl/train.py:99-143), memory values = discounted returns, states = transform ----
+    env2, orca, robot2, ec2, _ = make(ENVC, None, None, "orca", phase="train")
+    orca.safety_space = 0.15
+    orca.multiagent_training = policy.multiagent_training
+    robot2.set_policy(orca)
+    mem = ReplayMemory(100000)
+    ex = Explorer(env2, robot2, "cpu", mem, policy.gamma, target_policy=policy)
+    cap2 = {}
+    orig2 = ex.update_memory
+
+    def spy2(states, actions, rewards, imitation_learning=False):
+        cap2["rewards"] = rewards
+        return orig2(states, actions, rewards, imitation_learning)
+
+    ex.update_memory = spy2
+    tried = []
+    for case in range(5, 25):                     # until one episode is let into the memory (explorer.py:82-92)
+        env2.scene.case_counter["train"] = case
+        before = len(mem.memory)
+        ex.run_k_episodes(1, "train", update_memory=True, imitation_learning=True)
+        ended = "ReachGoal" if ex.success else ("Timeout" if ex.timeout else "Collision")
+        tried.append((case, ended, len(mem.memory) - before))
+        if len(mem.memory) > before:
+            break
+    res["il_tried_json"] = np.frombuffer(json.dumps(tried).encode(), dtype=np.uint8)
+    print("  IL episodes tried:", tried)
+    res["il_rewards"] = np.array(cap2.get("rewards", []), dtype=np.float64)
+    res["il_values"] = np.array([float(v) for _, v in mem.memory], dtype=np.float32)
+    res["il_states"] = (torch.stack([s for s, _ in mem.memory]).numpy().astype(np.float32) if len(mem.memory)
+                        else np.zeros((0, 5, 13), np.float32))
+    np.savez_compressed(os.path.join(out, "update_memory.npz"), **res)
+    print("  update_memory.npz: rl T=%d, il T=%d" % (len(res["rl_rewards"]), len(res["il_rewards"])))
+
+
+def round2(out):
+    """Fixtures added in round 2 (the earlier ones are left untouched)."""
+    POL = "configs/test_configs/test_policy_configs/policy.config"
+    BASE_W = "model_weights/sarl_model_baseline.pth"
+    EB_ENV = "data/eb-cadrl/adults_8_bikes_8_child_8_static_3_35_sec_new_reward_fix_static.config"
+    EB_POL = "data/eb-cadrl/policy_x2_agent_type.config"
+    EB_W = "data/eb-cadrl/rl_model_val.pth"
+    # humans driven by the `linear` policy (simulator/policy/linear.py:17-23): all of them, and mixed with ORCA
+    e = make("configs/test_configs/test_env_configs/env_adults_5.config", POL, BASE_W, "sarl",
+             env_overrides={("adults", "policy"): "linear"})
+    trace("trace_linear_adults5_seed1006", *e, {"test_case": 6}, 40, {0, 7}, out)
+    e = make("configs/test_configs/test_env_configs/env_adults_3_bikes_3_static_2.config", POL, BASE_W, "sarl",
+             env_overrides={("bicycles", "policy"): "linear"})
+    trace("trace_mixed_linear_bikes_seed1007", *e, {"test_case": 7}, 40, {0, 9}, out)
+    # train phase (epsilon 0): records policy.last_state = transform(current state) (multi_human_rl.py:84-85,128-149)
+    ov = {("sim", "adult_num"): 4, ("sim", "bicycle_num"): 3, ("sim", "children_num"): 3}
+    e = make(EB_ENV, EB_POL, EB_W, "sarl", phase="train", env_overrides=ov)
+    e[1].set_epsilon(0.0)
+    trace("trace_train_cfg2_h10_seed13", *e, {"scene_number": 13}, 24, {0}, out)
+    e = make("configs/test_configs/test_env_configs/env_adults_5.config", POL, BASE_W, "sarl", phase="train",
+             policy_overrides={("action_space", "kinematics"): "unicycle"},
+             env_overrides={("reward", "rotation_penalty_factor"): -0.01})
+    e[1].set_epsilon(0.0)
+    trace("trace_train_unicycle_adults5_seed1008", *e, {"test_case": 8}, 24, {0}, out)
+    update_memory_golden(out)
+
+
 def main():
     out = HERE
     if "--configs-only" in sys.argv:
         copy_configs(out)
+        return
+    if "--round2" in sys.argv:
+        round2(out)
         return
     POL = "configs/test_configs/test_policy_configs/policy.config"
     BASE_W = "model_weights/sarl_model_baseline.pth"
@@ -417,6 +532,7 @@ def main():
     trace("trace_orca_robot_h10_seed5", *e, {"scene_number": 5}, 60, set(), out)
     scenes(out)
     copy_configs(out)
+    round2(out)
 
 
 if __name__ == "__main__":

@@ -24,13 +24,23 @@ if os.environ.get("EBC_GOLDEN_CHILD") != "1":
 import multiprocessing as mp  # noqa: E402
 
 
+CONFIGS = {
+    # tag -> (env config, policy config, weights, first seed)
+    "cfg1": ("configs/test_configs/test_env_configs/env_adults_5.config",
+             "configs/test_configs/test_policy_configs/policy.config", "model_weights/sarl_model_baseline.pth", 1000),
+    # the shipped EB-CADRL experiment: 24 typed humans + 3 walls, entity-typed rows (the network the bench runs)
+    "ebcadrl": ("data/eb-cadrl/adults_8_bikes_8_child_8_static_3_35_sec_new_reward_fix_static.config",
+                "data/eb-cadrl/policy_x2_agent_type.config", "data/eb-cadrl/rl_model_val.pth", 1000),
+}
+TAG = "cfg1"
+
+
 def run(seed):
     import torch
     torch.set_num_threads(1)
     from simulator.utils.test_utils import configure_env_policy_robot
-    env, policy, robot = configure_env_policy_robot(
-        "configs/test_configs/test_env_configs/env_adults_5.config",
-        "configs/test_configs/test_policy_configs/policy.config", "model_weights/sarl_model_baseline.pth")
+    env_cfg, pol_cfg, weights, _ = CONFIGS[TAG]
+    env, policy, robot = configure_env_policy_robot(env_cfg, pol_cfg, weights)
     env.get_local_map_angular = lambda *a, **k: None
     ob, lm = env.reset("test", scene_number=seed)
     done, steps = False, 0
@@ -40,11 +50,18 @@ def run(seed):
     return {"seed": seed, "info": type(info).__name__, "time": env.global_time, "steps": steps}
 
 
+def _init(tag):
+    global TAG
+    TAG = tag
+
+
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-    with mp.Pool(os.cpu_count()) as pool:
-        rows = pool.map(run, range(1000, 1000 + n))
-    json.dump(rows, open(os.path.join(HERE, "outcomes_cfg1.json"), "w"), indent=0)
+    tag = sys.argv[2] if len(sys.argv) > 2 else "cfg1"
+    first = CONFIGS[tag][3]
+    with mp.Pool(os.cpu_count(), initializer=_init, initargs=(tag,)) as pool:
+        rows = pool.map(run, range(first, first + n), chunksize=1)
+    json.dump(rows, open(os.path.join(HERE, "outcomes_%s.json" % tag), "w"), indent=0)
     ok = sum(r["info"] == "ReachGoal" for r in rows)
     print("wrote %d outcomes: success %d, collisions %d, timeouts %d" % (
         len(rows), ok, sum(r["info"].startswith("Collision") for r in rows), sum(r["info"] == "Timeout" for r in rows)))

@@ -165,6 +165,11 @@ TRACE_WEIGHTS = {
     "trace_unicycle_adults5_seed1003": "weights_sarl_baseline.npz",
     "trace_nonholonomic_adults5_seed1003": "weights_sarl_baseline.npz",
     "trace_visible_adults5_seed1004": "weights_sarl_baseline.npz",
+    # round 2: `linear` humans (all / mixed with ORCA), train-phase traces that carry policy.last_state
+    "trace_linear_adults5_seed1006": "weights_sarl_baseline.npz",
+    "trace_mixed_linear_bikes_seed1007": "weights_sarl_baseline.npz",
+    "trace_train_cfg2_h10_seed13": "weights_ebcadrl.npz",
+    "trace_train_unicycle_adults5_seed1008": "weights_sarl_baseline.npz",
 }
 LINEAR_SCENES = ["scene_collision_with_adult", "scene_collision_with_bicycle", "scene_collision_with_static",
                  "scene_no_collisions", "scene_bikes_0_collision_with_adult_1",

@@ -159,3 +159,83 @@ def test_episode_sharding_is_independent_of_world_size():
         parts = [synth.generate(synth.CFG2, np.arange(r * per, (r + 1) * per)) for r in range(world)]
         for k in whole:
             assert np.array_equal(np.concatenate([p[k] for p in parts]), whole[k]), (world, k)
+
+
+def _explorer_with(gamma, dt, vp, target_model=None):
+    from rl.utils.explorer import Explorer
+    from rl.utils.memory import ReplayMemory
+    env = type("E", (), dict(time_limit=25, N=1, time_step=dt, robot=type("R", (), dict(v_pref=vp))()))()
+    ex = Explorer(env, robot=object(), device="cpu", memory=ReplayMemory(4096, device="cpu"), gamma=gamma)
+    if target_model is not None:
+        ex.update_target_model(target_model)
+    return ex
+
+
+def test_update_memory_matches_reference():
+    """a20: the (state, value) pairs our Explorer.update_memory pushes == the reference's own Explorer.update_memory /
+    ParallelExplorer.update_memory (rl/utils/explorer.py:151-200, parallel_explorer.py:286-330) on trajectories the
+    reference produced itself (tests/golden/update_memory.npz, written by make_golden.py: update_memory_golden).
+    TD target r_i + gamma^(dt v_pref) V_target(s_{i+1}) (terminal: r_i), IL discounted returns, to 1e-5; and the
+    sequential explorer's admission rule (only success / collision episodes, explorer.py:82-92)."""
+    from rl.policy.policy_factory import policy_factory
+    z = np.load(os.path.join(ob.GOLDEN, "update_memory.npz"))
+    gamma, dt, vp = [float(x) for x in z["gamma_dt_vpref"]]
+    pol = policy_factory["sarl"]()
+    pol.configure(read("policy.config"))
+    pol.get_model().load_state_dict({k: torch.as_tensor(v) for k, v in ob.load_weights("weights_sarl_baseline.npz").items()})
+    states = torch.as_tensor(z["rl_states"])                     # [T, n, D] = policy.last_state of every step
+    rewards = torch.as_tensor(z["rl_rewards"])
+    T, n, D = states.shape
+    assert T == 74 and np.array_equal(z["rl_mem_states"], z["rl_states"])
+    traj = {"states": states[:, None], "rewards": rewards[:, None], "alive": torch.ones(T, 1, dtype=torch.bool),
+            "rows": torch.tensor([n], dtype=torch.int32)}
+    stats = type("S", (), dict(event=np.array([ob.abi.EV_REACH_GOAL])))()
+    # ---- RL: TD targets through the target network ----
+    ex = _explorer_with(gamma, dt, vp, pol.get_model())
+    ex.update_memory(traj, stats, imitation_learning=False)
+    assert len(ex.memory) == T
+    assert torch.equal(ex.memory.states[:T], states)
+    got = ex.memory.values[:T, 0].numpy()
+    np.testing.assert_allclose(got, z["rl_values"], rtol=0, atol=1e-5)
+    assert got[-1] == np.float32(rewards[-1])                    # terminal state: value = reward
+    # ---- IL: discounted returns sum_{t >= i} gamma^((t - i) dt v_pref) r_t ----
+    ex = _explorer_with(gamma, dt, vp)
+    ex.update_memory(traj, stats, imitation_learning=True)
+    np.testing.assert_allclose(ex.memory.values[:T, 0].numpy(), z["il_values_of_rl_rewards"], rtol=0, atol=1e-5)
+    il_r = torch.as_tensor(z["il_rewards"])
+    Ti = len(il_r)
+    il_states = torch.as_tensor(z["il_states"])                  # transform(JointState) of the ORCA robot's episode
+    traj = {"states": il_states[:, None], "rewards": il_r[:, None], "alive": torch.ones(Ti, 1, dtype=torch.bool),
+            "rows": torch.tensor([il_states.shape[1]], dtype=torch.int32)}
+    ex = _explorer_with(gamma, dt, vp)
+    ex.update_memory(traj, stats, imitation_learning=True)
+    np.testing.assert_allclose(ex.memory.values[:Ti, 0].numpy(), z["il_values"], rtol=0, atol=1e-5)
+    assert torch.equal(ex.memory.states[:Ti], il_states)
+    # ---- admission: the reference tried scene 2005 (Timeout: nothing stored) then 2006 (ReachGoal: 41 pairs) ----
+    import json
+    tried = json.loads(bytes(z["il_tried_json"]).decode())
+    assert tried == [[5, "Timeout", 0], [6, "ReachGoal", Ti]]
+    for event, stored in ((ob.abi.EV_TIMEOUT, 0), (ob.abi.EV_REACH_GOAL, Ti), (ob.abi.EV_COLLISION_CHILD, Ti),
+                          (ob.abi.EV_COLLISION_OBSTACLE, Ti)):
+        ex = _explorer_with(gamma, dt, vp)
+        ex.update_memory(traj, type("S", (), dict(event=np.array([event])))(), imitation_learning=True, store_all=False)
+        assert len(ex.memory) == stored, (event, len(ex.memory))
+    ex = _explorer_with(gamma, dt, vp)                            # the parallel explorer stores every episode
+    ex.update_memory(traj, type("S", (), dict(event=np.array([ob.abi.EV_TIMEOUT])))(), imitation_learning=True, store_all=True)
+    assert len(ex.memory) == Ti
+    # ragged batch: two episodes of different length in one trajectory tensor (alive mask) give the same pairs
+    T2 = 30
+    st2 = torch.zeros(T, 2, n, D); st2[:, 0] = states; st2[:T2, 1] = states[:T2]
+    rw2 = torch.zeros(T, 2, dtype=torch.float64); rw2[:, 0] = rewards; rw2[:T2, 1] = rewards[:T2]
+    al2 = torch.zeros(T, 2, dtype=torch.bool); al2[:, 0] = True; al2[:T2, 1] = True
+    ex = _explorer_with(gamma, dt, vp, pol.get_model())
+    ex.update_memory({"states": st2, "rewards": rw2, "alive": al2, "rows": torch.tensor([n, n], dtype=torch.int32)},
+                     type("S", (), dict(event=np.array([2, 3])))(), imitation_learning=False)
+    assert len(ex.memory) == T + T2
+    vals = ex.memory.values[:T + T2, 0].numpy()
+    # time-major order: steps 0 .. T2-1 hold both episodes, then episode 0 alone
+    ep0 = np.concatenate([vals[0:2 * T2:2], vals[2 * T2:]])
+    ep1 = vals[1:2 * T2:2]
+    np.testing.assert_allclose(ep0, z["rl_values"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(ep1[:-1], z["rl_values"][:T2 - 1], rtol=0, atol=1e-5)
+    assert ep1[-1] == np.float32(rewards[T2 - 1])                # its last step is terminal: no bootstrap

@@ -72,13 +72,26 @@ def test_action_tables():
 def test_trace_single_steps(oracle, name):
     tr = ob.Trace(name)
     sim = make_sim(tr, oracle, weights=ob.TRACE_WEIGHTS[name])
-    n_flip, n_dec, worst_vin, worst_val = 0, 0, 0.0, 0.0
+    n_flip, n_dec, worst_vin, worst_val, n_last = 0, 0, 0.0, 0.0, 0
     for t in range(tr.n_steps):
         H, S = tr.load_into(sim, t)
         st = tr.steps[t]
+        if tr.has(t, "last_state"):
+            # multi_human_rl.py:84-85,128-149: the replay sample = transform(CURRENT joint state), pinned by the
+            # reference's own policy.last_state (train phase)
+            ref = tr.get(t, "last_state")
+            mine = sim.transform()[0].numpy()
+            assert ref.shape == (H + S, sim.D)
+            np.testing.assert_allclose(mine[:H + S], ref, rtol=0, atol=VIN_TOL)
+            assert not mine[H + S:].any()
+            n_last += 1
         sim.orca()
-        # humans' ORCA actions: fp32 inside rvo2 on both sides -> bit-exact
-        assert np.array_equal(sim.hum_nv[0, :H].numpy().astype(np.float64), tr.get(t, "orca")), (name, t)
+        # humans' ORCA actions: fp32 inside rvo2 on both sides -> bit-exact; `linear` humans (linear.py:17-23) are
+        # float64 in the reference and fp32 state here: equal after rounding to fp32
+        nv, ref_nv = sim.hum_nv[0, :H].numpy(), tr.get(t, "orca")
+        lin = np.array([tr.cfg_dict["human_policy"][int(ty)] == 1 for ty in tr.get(t, "hum_type")])
+        assert np.array_equal(nv[~lin].astype(np.float64), ref_nv[~lin]), (name, t)
+        assert np.array_equal(nv[lin], ref_nv[lin].astype(np.float32)), (name, t)
         if tr.has(t, "la_reward"):
             sim.lookahead()
             assert np.array_equal(sim.la_event[0].numpy(), tr.get(t, "la_event")), (name, t)
@@ -124,6 +137,10 @@ def test_trace_single_steps(oracle, name):
         assert float(sim.time[0]) == float(tr.get(t, "after_time"))
     print("%s: decisions=%d argmax flips=%d max|dvin|=%.2e max|dV|=%.2e" % (name, n_dec, n_flip, worst_vin, worst_val))
     assert n_flip <= max(1, n_dec // 50)
+    if "train" in name:
+        assert n_last >= 20        # every decision of a train-phase trace carries last_state
+    if "linear" in name:
+        assert 1 in tr.cfg_dict["human_policy"]
 
 
 @pytest.mark.parametrize("name", ob.LINEAR_SCENES)

@@ -8,10 +8,11 @@ import bench
 from ebc import synth
 from ebc.actions import build_action_space
 from ebc.engine import BatchedSim
-shape, cfg = bench.workload(); w, _ = bench.value_net_weights()
-N = 4096
+WL = os.environ.get("WORKLOAD", "cfg2")
+shape, cfg = bench.workload(WL); w, _ = bench.value_net_weights(fixture=bench.WORKLOADS[WL][3])
+N = int(os.environ.get("EPISODES", bench.WORKLOADS[WL][4]))
 sim = BatchedSim(cfg, N, shape.H, shape.Smax, shape.Rmax, 81, device="cuda:0")
-sim.set_actions(build_action_space(shape.robot_v_pref)); sim.set_weights(w)
+sim.set_actions(build_action_space(shape.robot_v_pref, cfg.robot_kinematics)); sim.set_weights(w)
 synth.load(sim, synth.generate(shape, np.arange(N)))
 sim.set_value_mode(sys.argv[1] if len(sys.argv) > 1 else "tc_fp16x2")
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 4
@@ -21,4 +22,4 @@ sim.value(); torch.cuda.synchronize()
 a.record()
 for _ in range(iters): sim.value()
 b.record(); torch.cuda.synchronize()
-print("K4 %s: %.3f ms per call" % (sim.value_mode(), a.elapsed_time(b) / iters))
+print("K4 %s %s N=%d: %.3f ms per call" % (WL, sim.value_mode(), N, a.elapsed_time(b) / iters))

@@ -15,11 +15,14 @@ sim.set_actions(build_action_space(shape.robot_v_pref, cfg.robot_kinematics)); s
 synth.load(sim, synth.generate(shape,np.arange(N)))
 mode = sys.argv[1] if len(sys.argv)>1 else "tc_fp32"
 sim.set_value_mode(mode)
+print("workload",WL,"episodes",N,"rows per state",shape.H+shape.Smax)
 for _ in range(2): sim.decide()
 torch.cuda.synchronize()
 buf=(ctypes.c_longlong*4096)()
 sim.be.lib.ebc_debug_trace(sim.h, buf, 4096)
-raw=np.array(buf[:], dtype=np.int64); t=raw[:2048]; t=t[t>0]; tm=raw[2048:]; tm=tm[tm>0]
+raw=np.array(buf[:], dtype=np.int64)
+os.makedirs(os.path.join(ROOT,"gpurun_out"),exist_ok=True); np.save(os.path.join(ROOT,"gpurun_out","trace_raw_%s_%s.npy"%(WL,mode)), raw)
+t=raw[:2048]; t=t[t>0]; tm=raw[2048:]; tm=tm[tm>0]
 # Stamps of CTA 0's crew thread 0.  The first tile has 13 (X, acc1, W0a, W0b, acc2, H1, G, T2, acc3, U, acc4, score, sync);
 # every later one starts with the early hand-over of its input during the previous tile's tail and has 15.
 t=t[13:]
