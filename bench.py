@@ -289,6 +289,14 @@ def run_cfg5(args, rank, world, local_rank):
 
     for _ in range(max(args.warmup, 1)):
         iteration(False)
+    if args.profile and rank == 0:      # where the host time of one iteration goes (cProfile, top of the cumulative list)
+        import cProfile
+        import pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        iteration(False)
+        pr.disable()
+        pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(45)
     launches0 = env.sim.launch_count()
     barrier()
     sampler = ClockSampler(local_rank)
@@ -361,6 +369,7 @@ def main():
                          "training loop (configs[4]), its own metric")
     ap.add_argument("--episodes-per-iter", type=int, default=8, help="cfg5: episodes per iteration and GPU (reference: 8)")
     ap.add_argument("--train-batches", type=int, default=None, help="cfg5: SGD steps per iteration (default: the config's 800)")
+    ap.add_argument("--profile", action="store_true", help="cfg5: cProfile of one untimed iteration to stderr")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sustained-seconds", type=float, default=2.0,
                     help="length of the extra back-to-back region reported under `sustained` (0 = skip)")

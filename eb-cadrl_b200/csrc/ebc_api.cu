@@ -271,7 +271,7 @@ int ebc_generate(ebc_sim *s, const ebc_scene_shape *shape, uint64_t seed, const 
                  void *stream) {
   REQUIRE_BOUND("ebc_generate");
   if (!shape || !episode_ids) return ebc_fail(s, EBC_ERR_INVALID, "ebc_generate: null shape or episode ids");
-  if (shape->n_types < 1 || shape->n_types > 4 || shape->max_tries < 1 || shape->rule < 0 || shape->rule > 2)
+  if (shape->n_types < 1 || shape->n_types > 4 || shape->max_tries < 1 || shape->rule < 0 || shape->rule > 3)
     return ebc_fail(s, EBC_ERR_INVALID, "ebc_generate: bad shape");
   int humans = 0;
   for (int t = 0; t < shape->n_types; ++t) {

@@ -32,47 +32,58 @@ struct Line { float px, py, dx, dy; };
 __device__ __forceinline__ float det2(float ax, float ay, float bx, float by) { return ax * by - ay * bx; }
 __device__ __forceinline__ float dot2(float ax, float ay, float bx, float by) { return ax * bx + ay * by; }
 
-__device__ __forceinline__ float warp_min_f(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL, v, o));
-  return v;
-}
-__device__ __forceinline__ float warp_max_f(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
-  return v;
-}
 __device__ __forceinline__ double warp_min_d(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
   return v;
 }
 
-// The warp's ORCA lines: line index = lane + 32 * chunk.  LPL (lines per lane) = 1 on the reference's live path
-// (at most max_neighbors <= 32 agent lines), 2 when obstacle half-planes are enabled (up to 64 lines, obstacle
-// lines first).  Every function below is the same arithmetic for both; LPL = 1 compiles to the single-line code.
+// The group's ORCA lines: line index = lane + GW * chunk.  A group = the GW lanes that solve one agent's LP: the whole
+// warp (GW = 32), or a half warp (GW = 16: two agents per warp, every shuffle / ballot / reduction confined to the
+// half through its member mask `m`; `lane` is then the lane index inside the half).  LPL (lines per lane) = 1 on the
+// reference's live path (at most max_neighbors agent lines), 2 when obstacle half-planes are enabled (up to 64
+// lines, obstacle lines first; GW = 32 only).  Every function below is the same arithmetic for all (GW, LPL).
 template <int LPL> struct Lines { Line l[LPL]; };
 
-template <int LPL>
-__device__ __forceinline__ void bcast_line(const Lines<LPL> &L, int i, float &px, float &py, float &dx, float &dy) {
-  const int il = i & 31;
-  if (LPL == 1 || i < 32) {
-    px = __shfl_sync(FULL, L.l[0].px, il); py = __shfl_sync(FULL, L.l[0].py, il);
-    dx = __shfl_sync(FULL, L.l[0].dx, il); dy = __shfl_sync(FULL, L.l[0].dy, il);
+template <int GW> __device__ __forceinline__ unsigned group_mask() {
+  return GW == 32 ? FULL : (0xFFFFu << ((threadIdx.x & 31) & 16));
+}
+template <int GW> __device__ __forceinline__ unsigned grp_ballot(unsigned m, bool p) {
+  const unsigned b = __ballot_sync(m, p);
+  return GW == 32 ? b : ((b >> ((threadIdx.x & 31) & 16)) & 0xFFFFu);
+}
+template <int GW> __device__ __forceinline__ float grp_min_f(unsigned m, float v) {
+#pragma unroll
+  for (int o = GW / 2; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(m, v, o, GW));
+  return v;
+}
+template <int GW> __device__ __forceinline__ float grp_max_f(unsigned m, float v) {
+#pragma unroll
+  for (int o = GW / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(m, v, o, GW));
+  return v;
+}
+
+template <int LPL, int GW>
+__device__ __forceinline__ void bcast_line(unsigned m, const Lines<LPL> &L, int i, float &px, float &py, float &dx,
+                                           float &dy) {
+  const int il = i & (GW - 1);
+  if (LPL == 1 || i < GW) {
+    px = __shfl_sync(m, L.l[0].px, il, GW); py = __shfl_sync(m, L.l[0].py, il, GW);
+    dx = __shfl_sync(m, L.l[0].dx, il, GW); dy = __shfl_sync(m, L.l[0].dy, il, GW);
   } else {
-    px = __shfl_sync(FULL, L.l[LPL - 1].px, il); py = __shfl_sync(FULL, L.l[LPL - 1].py, il);
-    dx = __shfl_sync(FULL, L.l[LPL - 1].dx, il); dy = __shfl_sync(FULL, L.l[LPL - 1].dy, il);
+    px = __shfl_sync(m, L.l[LPL - 1].px, il, GW); py = __shfl_sync(m, L.l[LPL - 1].py, il, GW);
+    dx = __shfl_sync(m, L.l[LPL - 1].dx, il, GW); dy = __shfl_sync(m, L.l[LPL - 1].dy, il, GW);
   }
 }
 
 // RVO2 linearProgram1 with the scan over earlier lines done by the lanes that hold them.
 // tLeft only grows and tRight only shrinks along the sequential scan, so "fails at some
 // prefix" == "fails at the end", and the parallel-line failure is order-free (Appendix A.3).
-template <int LPL>
-__device__ bool lp1_warp(const Lines<LPL> &L, int lane, int i, float radius, float ox, float oy, bool dir_opt,
-                         float &rx, float &ry) {
+template <int LPL, int GW>
+__device__ bool lp1_warp(unsigned m, const Lines<LPL> &L, int lane, int i, float radius, float ox, float oy,
+                         bool dir_opt, float &rx, float &ry) {
   float pix, piy, dix, diy;
-  bcast_line<LPL>(L, i, pix, piy, dix, diy);
+  bcast_line<LPL, GW>(m, L, i, pix, piy, dix, diy);
   const float dp = dot2(pix, piy, dix, diy);
   const float disc = dp * dp + radius * radius - dot2(pix, piy, pix, piy);
   if (disc < 0.0f) return false;
@@ -86,18 +97,18 @@ __device__ bool lp1_warp(const Lines<LPL> &L, int lane, int i, float radius, flo
     const Line &M = L.l[c];
     const float den = det2(dix, diy, M.dx, M.dy);
     const float num = det2(M.dx, M.dy, pix - M.px, piy - M.py);
-    const bool act = lane + 32 * c < i;
+    const bool act = lane + GW * c < i;
     const bool par = fabsf(den) <= RVO_EPSILON;
     bad = bad || (act && par && (num < 0.0f));
     const float t = num / den;
     cr = fminf(cr, (act && !par && den >= 0.0f) ? t : INFINITY);
     cl = fmaxf(cl, (act && !par && den < 0.0f) ? t : -INFINITY);
   }
-  cr = warp_min_f(cr);
-  cl = warp_max_f(cl);
+  cr = grp_min_f<GW>(m, cr);
+  cl = grp_max_f<GW>(m, cl);
   tr = fminf(tr, cr);
   tl = fmaxf(tl, cl);
-  if (__any_sync(FULL, bad) || tl > tr) return false;
+  if (__any_sync(m, bad) || tl > tr) return false;
   float tt;
   if (dir_opt) {
     tt = (dot2(ox, oy, dix, diy) > 0.0f) ? tr : tl;
@@ -113,9 +124,9 @@ __device__ bool lp1_warp(const Lines<LPL> &L, int lane, int i, float radius, flo
 
 // RVO2 linearProgram2: the result only changes inside lp1, so the sequential "first violated
 // line at or after i" is one ballot (per chunk).
-template <int LPL>
-__device__ int lp2_warp(const Lines<LPL> &L, int lane, int n, float radius, float ox, float oy, bool dir_opt,
-                        float &rx, float &ry) {
+template <int LPL, int GW>
+__device__ int lp2_warp(unsigned m, const Lines<LPL> &L, int lane, int n, float radius, float ox, float oy,
+                        bool dir_opt, float &rx, float &ry) {
   if (dir_opt) {
     rx = ox * radius;
     ry = oy * radius;
@@ -132,15 +143,15 @@ __device__ int lp2_warp(const Lines<LPL> &L, int lane, int n, float radius, floa
     int first = -1;
 #pragma unroll
     for (int c = 0; c < LPL; ++c) {
-      const int idx = lane + 32 * c;
+      const int idx = lane + GW * c;
       const bool viol = idx >= i && idx < n && det2(L.l[c].dx, L.l[c].dy, L.l[c].px - rx, L.l[c].py - ry) > 0.0f;
-      const unsigned m = __ballot_sync(FULL, viol);
-      if (first < 0 && m != 0u) first = 32 * c + __ffs(m) - 1;
+      const unsigned vm = grp_ballot<GW>(m, viol);
+      if (first < 0 && vm != 0u) first = GW * c + __ffs(vm) - 1;
     }
     if (first < 0) return n;
     i = first;
     const float tx = rx, ty = ry;
-    if (!lp1_warp<LPL>(L, lane, i, radius, ox, oy, dir_opt, rx, ry)) {
+    if (!lp1_warp<LPL, GW>(m, L, lane, i, radius, ox, oy, dir_opt, rx, ry)) {
       rx = tx;
       ry = ty;
       return i;
@@ -151,20 +162,20 @@ __device__ int lp2_warp(const Lines<LPL> &L, int lane, int n, float radius, floa
 
 // RVO2 linearProgram3.  The projected problem keeps the first num_obst (obstacle) lines verbatim and replaces
 // lines num_obst .. i-1 by their bisectors with line i (num_obst = 0 on the reference's live path).
-template <int LPL>
-__device__ void lp3_warp(const Lines<LPL> &L, int lane, int n, int num_obst, int begin, float radius, float &rx,
-                         float &ry) {
+template <int LPL, int GW>
+__device__ void lp3_warp(unsigned m, const Lines<LPL> &L, int lane, int n, int num_obst, int begin, float radius,
+                         float &rx, float &ry) {
   float distance = 0.0f;
   for (int i = begin; i < n; ++i) {
     float pix, piy, dix, diy;
-    bcast_line<LPL>(L, i, pix, piy, dix, diy);
+    bcast_line<LPL, GW>(m, L, i, pix, piy, dix, diy);
     if (det2(dix, diy, pix - rx, piy - ry) > distance) {
       Lines<LPL> P;
       unsigned vm[LPL];
 #pragma unroll
       for (int c = 0; c < LPL; ++c) {
         const Line &M = L.l[c];
-        const int idx = lane + 32 * c;
+        const int idx = lane + GW * c;
         bool valid = idx < i;
         const float d = det2(dix, diy, M.dx, M.dy);
         if (fabsf(d) <= RVO_EPSILON) {
@@ -184,36 +195,36 @@ __device__ void lp3_warp(const Lines<LPL> &L, int lane, int n, int num_obst, int
           P.l[c] = M;
           valid = true;
         }
-        vm[c] = __ballot_sync(FULL, valid);
+        vm[c] = grp_ballot<GW>(m, valid);
       }
-      int m = 0;
+      int cnt = 0;
 #pragma unroll
-      for (int c = 0; c < LPL; ++c) m += __popc(vm[c]);
+      for (int c = 0; c < LPL; ++c) cnt += __popc(vm[c]);
       Lines<LPL> Q;
       if (LPL == 1) {
         int src = (int)__fns(vm[0], 0, lane + 1);   // lane k takes the k-th surviving line (order kept)
-        if (lane >= m) src = lane;
-        Q.l[0].px = __shfl_sync(FULL, P.l[0].px, src);
-        Q.l[0].py = __shfl_sync(FULL, P.l[0].py, src);
-        Q.l[0].dx = __shfl_sync(FULL, P.l[0].dx, src);
-        Q.l[0].dy = __shfl_sync(FULL, P.l[0].dy, src);
+        if (lane >= cnt) src = lane;
+        Q.l[0].px = __shfl_sync(m, P.l[0].px, src, GW);
+        Q.l[0].py = __shfl_sync(m, P.l[0].py, src, GW);
+        Q.l[0].dx = __shfl_sync(m, P.l[0].dx, src, GW);
+        Q.l[0].dy = __shfl_sync(m, P.l[0].dy, src, GW);
       } else {
         const int m0 = __popc(vm[0]);
 #pragma unroll
         for (int c = 0; c < LPL; ++c) {
-          const int t = lane + 32 * c;                   // target index: the t-th surviving line
+          const int t = lane + GW * c;                   // target index: the t-th surviving line
           int sc = 0, sl = lane;
           if (t < m0) { sc = 0; sl = (int)__fns(vm[0], 0, t + 1); }
-          else if (t < m) { sc = 1; sl = (int)__fns(vm[LPL - 1], 0, t - m0 + 1); }
-          const float a0 = __shfl_sync(FULL, P.l[0].px, sl), a1 = __shfl_sync(FULL, P.l[LPL - 1].px, sl);
-          const float b0 = __shfl_sync(FULL, P.l[0].py, sl), b1 = __shfl_sync(FULL, P.l[LPL - 1].py, sl);
-          const float c0 = __shfl_sync(FULL, P.l[0].dx, sl), c1 = __shfl_sync(FULL, P.l[LPL - 1].dx, sl);
-          const float d0 = __shfl_sync(FULL, P.l[0].dy, sl), d1 = __shfl_sync(FULL, P.l[LPL - 1].dy, sl);
+          else if (t < cnt) { sc = 1; sl = (int)__fns(vm[LPL - 1], 0, t - m0 + 1); }
+          const float a0 = __shfl_sync(m, P.l[0].px, sl, GW), a1 = __shfl_sync(m, P.l[LPL - 1].px, sl, GW);
+          const float b0 = __shfl_sync(m, P.l[0].py, sl, GW), b1 = __shfl_sync(m, P.l[LPL - 1].py, sl, GW);
+          const float c0 = __shfl_sync(m, P.l[0].dx, sl, GW), c1 = __shfl_sync(m, P.l[LPL - 1].dx, sl, GW);
+          const float d0 = __shfl_sync(m, P.l[0].dy, sl, GW), d1 = __shfl_sync(m, P.l[LPL - 1].dy, sl, GW);
           Q.l[c].px = sc ? a1 : a0; Q.l[c].py = sc ? b1 : b0; Q.l[c].dx = sc ? c1 : c0; Q.l[c].dy = sc ? d1 : d0;
         }
       }
       const float tx = rx, ty = ry;
-      if (lp2_warp<LPL>(Q, lane, m, radius, -diy, dix, true, rx, ry) < m) {
+      if (lp2_warp<LPL, GW>(m, Q, lane, cnt, radius, -diy, dix, true, rx, ry) < cnt) {
         rx = tx;
         ry = ty;
       }
@@ -492,17 +503,18 @@ __device__ int obstacle_lines_warp(const ObstV *so, int V, int lane, float px, f
   return __popc(a0) + __popc(a1);
 }
 
-// One RVO2 agent step by one warp.  Candidates (the other agents, in the reference's list
-// order) sit two per lane: index lane and lane + 32.  `scratch` = this warp's shared memory: 32*5 floats, or
+// One RVO2 agent step by one group of GW lanes (m = its member mask, lane = the index inside it).  Candidates (the other
+// agents, in the reference's list order) sit two per lane: index lane and lane + GW.  `scratch` = this warp's shared memory: 32*5 floats, or
 // OBST_SCRATCH_FLOATS with obstacle half-planes (so / V: the episode's obstacle vertices in shared memory).
-template <bool OBST>
-__device__ void orca_agent_warp(int lane, float px, float py, float vx, float vy, float radius, float max_speed,
+template <bool OBST, int GW>
+__device__ void orca_agent_warp(unsigned m, int lane, float px, float py, float vx, float vy, float radius, float max_speed,
                                 float prefx, float prefy, const float (&cpx)[2], const float (&cpy)[2],
                                 const float (&cvx)[2], const float (&cvy)[2], const float (&crad)[2],
                                 const bool (&cval)[2], int n_chunks, float neighbor_dist, int max_nb,
                                 float time_horizon, float time_step, float *scratch, float &outx, float &outy,
                                 const ObstV *so = nullptr, int V = 0, float th_obst = 0.0f) {
   constexpr int LPL = OBST ? 2 : 1;
+  static_assert(!OBST || GW == 32, "obstacle half-planes use the whole warp");
   // Agent::insertAgentNeighbor == keep the max_nb smallest (distSq, arrival index) below range
   float d[2];
   unsigned vmask[2] = {0u, 0u};
@@ -512,7 +524,7 @@ __device__ void orca_agent_warp(int lane, float px, float py, float vx, float vy
     const float ddx = px - cpx[c], ddy = py - cpy[c];
     d[c] = dot2(ddx, ddy, ddx, ddy);
     const bool ok = (c < n_chunks) && cval[c] && (d[c] < range_sq);
-    vmask[c] = __ballot_sync(FULL, ok);
+    vmask[c] = grp_ballot<GW>(m, ok);
   }
   int rank[2] = {0, 0};
 #pragma unroll
@@ -522,18 +534,18 @@ __device__ void orca_agent_warp(int lane, float px, float py, float vx, float vy
     while (m) {
       const int l = __ffs(m) - 1;
       m &= m - 1;
-      const float dk = __shfl_sync(FULL, d[c2], l);
-      const int k = l + 32 * c2;
+      const float dk = __shfl_sync(m, d[c2], l, GW);
+      const int k = l + GW * c2;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        const int me = lane + 32 * c;
+        const int me = lane + GW * c;
         rank[c] += (dk < d[c] || (dk == d[c] && k < me)) ? 1 : 0;
       }
     }
   }
   const int total = __popc(vmask[0]) + __popc(vmask[1]);
   int cnt = total < max_nb ? total : max_nb;
-  __syncwarp();
+  __syncwarp(m);
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     if ((vmask[c] >> lane) & 1u) {
@@ -543,7 +555,7 @@ __device__ void orca_agent_warp(int lane, float px, float py, float vx, float vy
       }
     }
   }
-  __syncwarp();
+  __syncwarp(m);
   Line A = {0.0f, 0.0f, 1.0f, 0.0f};      // agent line `lane`
   if (lane < cnt) {
     const float *s = scratch + lane * 5;
@@ -596,7 +608,7 @@ __device__ void orca_agent_warp(int lane, float px, float py, float vx, float vy
     A.px = vx + 0.5f * ux;
     A.py = vy + 0.5f * uy;
   }
-  __syncwarp();
+  __syncwarp(m);
   Lines<LPL> L;
   int num_obst = 0;
   if (OBST) {
@@ -607,21 +619,21 @@ __device__ void orca_agent_warp(int lane, float px, float py, float vx, float vy
     num_obst = obstacle_lines_warp(so, V, lane, px, py, vx, vy, radius, max_speed, th_obst, linebuf, ids);
     if (cnt > 64 - num_obst) cnt = 64 - num_obst;
     if (lane < cnt) linebuf[num_obst + lane] = A;
-    __syncwarp();
+    __syncwarp(m);
 #pragma unroll
     for (int c = 0; c < LPL; ++c) {
       const int idx = lane + 32 * c;
       const Line Z = {0.0f, 0.0f, 1.0f, 0.0f};
       L.l[c] = idx < num_obst + cnt ? linebuf[idx] : Z;
     }
-    __syncwarp();
+    __syncwarp(m);
   } else {
     L.l[0] = A;
   }
   const int n_lines = num_obst + cnt;
   float rx, ry;
-  const int fail = lp2_warp<LPL>(L, lane, n_lines, max_speed, prefx, prefy, false, rx, ry);
-  if (fail < n_lines) lp3_warp<LPL>(L, lane, n_lines, num_obst, fail, max_speed, rx, ry);
+  const int fail = lp2_warp<LPL, GW>(m, L, lane, n_lines, max_speed, prefx, prefy, false, rx, ry);
+  if (fail < n_lines) lp3_warp<LPL, GW>(m, L, lane, n_lines, num_obst, fail, max_speed, rx, ry);
   outx = rx;
   outy = ry;
 }
@@ -653,8 +665,8 @@ __device__ __forceinline__ int stage_obstacles(const ebc_config &c, const ebc_st
 }
 
 // Policy of human h of episode e, computed by one warp (env.py:392-405).
-template <bool OBST>
-__device__ void human_policy_warp(const ebc_config &c, const ebc_state &st, int e, int h, int H, int lane,
+template <bool OBST, int GW>
+__device__ void human_policy_warp(unsigned m, const ebc_config &c, const ebc_state &st, int e, int h, int H, int lane,
                                   float *scratch, float &nvx, float &nvy, const ObstV *so = nullptr, int V = 0) {
   const int Hm = c.max_humans;
   const float4 *pv = reinterpret_cast<const float4 *>(st.hum_pv) + (size_t)e * Hm;
@@ -669,12 +681,12 @@ __device__ void human_policy_warp(const ebc_config &c, const ebc_state &st, int 
     return;
   }
   const int n_cand = H + (c.robot_visible ? 1 : 0);
-  const int n_chunks = (n_cand + 31) >> 5;
+  const int n_chunks = (n_cand + GW - 1) / GW;
   float cpx[2], cpy[2], cvx[2], cvy[2], crad[2];
   bool cval[2];
 #pragma unroll
   for (int ch = 0; ch < 2; ++ch) {
-    const int j = lane + 32 * ch;
+    const int j = lane + GW * ch;
     cval[ch] = false;
     cpx[ch] = cpy[ch] = cvx[ch] = cvy[ch] = crad[ch] = 0.0f;
     if (j < H && j != h) {
@@ -691,22 +703,26 @@ __device__ void human_policy_warp(const ebc_config &c, const ebc_state &st, int 
   }
   float r_self, prefx, prefy;
   orca_self_params(me_pv.x, me_pv.y, me_gr.x, me_gr.y, me_gr.w, c.orca_safety_space, r_self, prefx, prefy);
-  orca_agent_warp<OBST>(lane, me_pv.x, me_pv.y, me_pv.z, me_pv.w, r_self, me_gr.z, prefx, prefy, cpx, cpy, cvx, cvy,
-                        crad, cval, n_chunks, c.orca_neighbor_dist, c.orca_max_neighbors, c.orca_time_horizon,
-                        (float)c.time_step, scratch, nvx, nvy, so, V, c.orca_time_horizon_obst);
+  orca_agent_warp<OBST, GW>(m, lane, me_pv.x, me_pv.y, me_pv.z, me_pv.w, r_self, me_gr.z, prefx, prefy, cpx, cpy, cvx, cvy,
+                            crad, cval, n_chunks, c.orca_neighbor_dist, c.orca_max_neighbors, c.orca_time_horizon,
+                            (float)c.time_step, scratch, nvx, nvy, so, V, c.orca_time_horizon_obst);
 }
 
+// K1, one group of GW lanes per human: the whole warp, or a half warp (two humans per warp) when every human has at
+// most 32 candidates and 16 ORCA lines -- same arithmetic, bit-identical results, half the warp-instructions per human.
+template <int GW>
 __global__ void __launch_bounds__(EBC_THREADS) orca_kernel(const ebc_config c, const ebc_state st) {
-  __shared__ float scratch[EBC_WARPS_PER_BLOCK][32 * 5];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long w = (long long)blockIdx.x * EBC_WARPS_PER_BLOCK + warp;
+  constexpr int GPW = 32 / GW;
+  __shared__ float scratch[EBC_WARPS_PER_BLOCK * GPW][32 * 5];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane / GW, gl = lane % GW;
+  const long long w = ((long long)blockIdx.x * EBC_WARPS_PER_BLOCK + warp) * GPW + sub;
   const int e = (int)(w / c.max_humans), h = (int)(w % c.max_humans);
   if (e >= c.n_episodes) return;
   const int H = st.hum_count[e];
   if (h >= H) return;
   float nvx, nvy;
-  human_policy_warp<false>(c, st, e, h, H, lane, scratch[warp], nvx, nvy);
-  if (lane == 0)
+  human_policy_warp<false, GW>(group_mask<GW>(), c, st, e, h, H, gl, scratch[warp * GPW + sub], nvx, nvy);
+  if (gl == 0)
     reinterpret_cast<float2 *>(st.hum_nv)[(size_t)e * c.max_humans + h] = make_float2(nvx, nvy);
 }
 
@@ -753,9 +769,9 @@ __global__ void __launch_bounds__(WPB * 32) robot_orca_kernel(const ebc_config c
   const float4 rg = reinterpret_cast<const float4 *>(st.rob_gr)[e];
   float r_self, prefx, prefy, vx, vy;
   orca_self_params(rp.x, rp.y, rg.x, rg.y, rg.w, safety, r_self, prefx, prefy);
-  orca_agent_warp<OBST>(lane, rp.x, rp.y, rp.z, rp.w, r_self, rg.z, prefx, prefy, cpx, cpy, cvx, cvy, crad, cval,
-                        (H + S + 31) >> 5, c.orca_neighbor_dist, c.orca_max_neighbors, c.orca_time_horizon,
-                        (float)c.time_step, scratch[warp], vx, vy, so, V, c.orca_time_horizon_obst);
+  orca_agent_warp<OBST, 32>(FULL, lane, rp.x, rp.y, rp.z, rp.w, r_self, rg.z, prefx, prefy, cpx, cpy, cvx, cvy, crad, cval,
+                            (H + S + 31) >> 5, c.orca_neighbor_dist, c.orca_max_neighbors, c.orca_time_horizon,
+                            (float)c.time_step, scratch[warp], vx, vy, so, V, c.orca_time_horizon_obst);
   if (lane == 0) {
     out[(size_t)e * 2] = (double)vx;
     out[(size_t)e * 2 + 1] = (double)vy;
@@ -1341,14 +1357,16 @@ step_kernel(const ebc_config c, const ebc_state st, const double *__restrict__ a
 // the block synchronises, then warp 0 commits.  One launch per env step on the policy-free path.
 // OBST: with ORCA obstacle half-planes (the episode's obstacle vertices staged in shared memory next to the
 // neighbour scratch); COMMIT = false is K1 alone in that block-per-episode shape (ebc_orca with obstacles).
-template <bool OBST, bool COMMIT>
+template <bool OBST, bool COMMIT, int GW>
 __global__ void __launch_bounds__(512)
 orca_step_kernel(const ebc_config c, const ebc_state st, const double *__restrict__ actions,
                  const int32_t *action_idx, const double *action, const uint8_t *active, double *reward,
                  uint8_t *done, uint8_t *event, double *dmin, double *dist_to_goal, const ebc_stats sx) {
-  __shared__ float scratch[16][OBST ? OBST_SCRATCH_FLOATS : 32 * 5];
+  constexpr int GPW = 32 / GW;       // humans per warp
+  __shared__ float scratch[16 * GPW][OBST ? OBST_SCRATCH_FLOATS : 32 * 5];
   __shared__ __align__(16) ObstV so[OBST ? 64 : 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+  const int sub = lane / GW, gl = lane % GW;
   const int e = blockIdx.x;
   if (active && !active[e]) return;
   const int H = st.hum_count[e];
@@ -1357,10 +1375,11 @@ orca_step_kernel(const ebc_config c, const ebc_state st, const double *__restric
     V = stage_obstacles(c, st, e, so, threadIdx.x, blockDim.x);
     __syncthreads();
   }
-  for (int h = warp; h < H; h += n_warps) {
+  const unsigned m = group_mask<GW>();
+  for (int h = warp * GPW + sub; h < H; h += n_warps * GPW) {
     float nvx, nvy;
-    human_policy_warp<OBST>(c, st, e, h, H, lane, scratch[warp], nvx, nvy, so, V);
-    if (lane == 0)
+    human_policy_warp<OBST, GW>(m, c, st, e, h, H, gl, scratch[warp * GPW + sub], nvx, nvy, so, V);
+    if (gl == 0)
       reinterpret_cast<float2 *>(st.hum_nv)[(size_t)e * c.max_humans + h] = make_float2(nvx, nvy);
   }
   if (!COMMIT) return;
@@ -1432,9 +1451,12 @@ generate_kernel(const ebc_config c, const ebc_state st, const ebc_scene_shape sh
   const unsigned long long id = (unsigned long long)episode_ids[e];
   const int Hm = c.max_humans, Sm = c.max_statics, Rm = c.max_rects;
   const double R = sh.circle_radius, hw = sh.square_width / 2.0, dd = sh.discomfort_dist;
-  double px[64], py[64], rad[64];
+  double px[64], py[64], gx[64], gy[64], rad[64];
   int H = 0;
   for (int t = 0; t < sh.n_types; ++t) H += sh.type_count[t];
+  // rule 3 = mixed_20 (scene_generator.py:577-582): randint(20) static adults in a 6 x 8 box, the rest dynamic
+  const int n_static = sh.rule == 3 ? (int)floor(gen_uniform(seed, id, 4000, 0) * 20.0) : 0;
+  const int n_dynamic = H - n_static;
   // scene_generator.py:292-328: per-agent preferred speed and radius, group by group
   int h0 = 0;
   for (int t = 0; t < sh.n_types; ++t) {
@@ -1447,29 +1469,49 @@ generate_kernel(const ebc_config c, const ebc_state st, const ebc_scene_shape sh
       const int h = h0 + k;
       const double vpref = sh.v_pref_lo[t] + (sh.v_pref_hi[t] - sh.v_pref_lo[t]) * gen_uniform(seed, id, 1000 + h, 0);
       rad[h] = sh.radius_lo[t] + (sh.radius_hi[t] - sh.radius_lo[t]) * gen_uniform(seed, id, 1000 + h, 1);
-      const bool circle = sh.rule == 1 || (sh.rule == 2 && h < H / 2);
+      const int hd = h - n_static;              // index among the dynamic agents
+      const bool is_static = h < n_static;
+      const bool circle = !is_static && (sh.rule == 1 || ((sh.rule == 2 || sh.rule == 3) && hd < n_dynamic / 2));
+      const double md_robot = rad[h] + sh.robot_radius + dd;
       double x = 0, y = 0, tx = 0, ty = 0;
-      for (int attempt = 0; attempt < sh.max_tries; ++attempt) {
-        const unsigned long long d0 = (unsigned long long)attempt * 8ull;
-        if (circle) {           // :593-618: start on the circle, goal opposite
-          const double ang = gen_uniform(seed, id, 2000 + h, d0) * 2.0 * 3.141592653589793;
-          x = R * cos(ang); y = R * sin(ang);
-          tx = -x; ty = -y;
-        } else {                // :672-712: start on one side of the square, goal on the opposite side
-          const long long side = (long long)floor(gen_uniform(seed, id, 2000 + h, d0) * 4.0);
-          const double a = -hw + 2.0 * hw * gen_uniform(seed, id, 2000 + h, d0 + 1);
-          const double b = -hw + 2.0 * hw * gen_uniform(seed, id, 2000 + h, d0 + 2);
-          x = side == 0 ? a : (side == 1 ? a : (side == 2 ? -hw : hw));
-          y = side == 0 ? hw : (side == 1 ? -hw : a);
-          tx = side == 0 ? b : (side == 1 ? b : (side == 2 ? hw : -hw));
-          ty = side == 0 ? -hw : (side == 1 ? hw : b);
+      if (is_static && h == 0) {                // scene_generator.py:463-466: the first static adult is fixed
+        x = -0.5; y = -2.5; tx = x; ty = y;
+      } else {
+        // static adults (:467-487): one side of the y axis for all tries of this adult
+        const double sign = gen_uniform(seed, id, 2000 + h, 7) < 0.5 ? 1.0 : -1.0;
+        for (int attempt = 0; attempt < sh.max_tries; ++attempt) {
+          const unsigned long long d0 = (unsigned long long)attempt * 8ull;
+          bool ok;
+          if (is_static) {          // a 6 x 8 box; no start closer than the comfort distance to anybody, nor to the robot's goal
+            x = gen_uniform(seed, id, 2000 + h, d0) * 6.0 * 0.5 * sign;
+            y = (gen_uniform(seed, id, 2000 + h, d0 + 1) - 0.5) * 8.0;
+            tx = x; ty = y;
+            ok = hypot(x - 0.0, y + R) >= md_robot;
+            for (int j = first_of_type; j < h && ok; ++j) ok = hypot(x - px[j], y - py[j]) >= rad[h] + rad[j] + dd;
+            // (:480-483 takes the radius of the LAST agent of the list it has just walked)
+            ok = ok && hypot(x - 0.0, y - R) >= rad[h] + (h > first_of_type ? rad[h - 1] : sh.robot_radius) + dd;
+          } else if (circle) {      // :593-618: start on the circle, goal opposite; clear of everybody's start AND goal
+            const double ang = gen_uniform(seed, id, 2000 + h, d0) * 2.0 * 3.141592653589793;
+            x = R * cos(ang); y = R * sin(ang);
+            tx = -x; ty = -y;
+            ok = hypot(x - 0.0, y + R) >= md_robot && hypot(x - 0.0, y - R) >= md_robot;
+            for (int j = first_of_type; j < h && ok; ++j)
+              ok = hypot(x - px[j], y - py[j]) >= rad[h] + rad[j] + dd && hypot(x - gx[j], y - gy[j]) >= rad[h] + rad[j] + dd;
+          } else {                  // :672-712: start on one side of the square, goal on the opposite side; starts only
+            const long long side = (long long)floor(gen_uniform(seed, id, 2000 + h, d0) * 4.0);
+            const double a = -hw + 2.0 * hw * gen_uniform(seed, id, 2000 + h, d0 + 1);
+            const double b = -hw + 2.0 * hw * gen_uniform(seed, id, 2000 + h, d0 + 2);
+            x = side == 0 ? a : (side == 1 ? a : (side == 2 ? -hw : hw));
+            y = side == 0 ? hw : (side == 1 ? -hw : a);
+            tx = side == 0 ? b : (side == 1 ? b : (side == 2 ? hw : -hw));
+            ty = side == 0 ? -hw : (side == 1 ? hw : b);
+            ok = hypot(x - 0.0, y + R) >= md_robot;
+            for (int j = first_of_type; j < h && ok; ++j) ok = hypot(x - px[j], y - py[j]) >= rad[h] + rad[j] + dd;
+          }
+          if (ok || attempt == sh.max_tries - 1) break;
         }
-        // :683-693: reject starts too close to the robot or to agents of the same list placed earlier
-        bool ok = hypot(x - 0.0, y + R) >= rad[h] + sh.robot_radius + dd;
-        for (int j = first_of_type; j < h && ok; ++j) ok = hypot(x - px[j], y - py[j]) >= rad[h] + rad[j] + dd;
-        if (ok || attempt == sh.max_tries - 1) break;
       }
-      px[h] = x; py[h] = y;
+      px[h] = x; py[h] = y; gx[h] = tx; gy[h] = ty;
       reinterpret_cast<float4 *>(st.hum_pv)[(size_t)e * Hm + h] = make_float4((float)x, (float)y, 0.f, 0.f);
       reinterpret_cast<float4 *>(st.hum_gr)[(size_t)e * Hm + h] = make_float4((float)tx, (float)ty, (float)vpref, (float)rad[h]);
       st.hum_type[(size_t)e * Hm + h] = (uint8_t)sh.type_code[t];
@@ -1508,19 +1550,23 @@ generate_kernel(const ebc_config c, const ebc_state st, const ebc_scene_shape sh
     const double dimx = rint(xd / res), dimy = rint(yd / res);
     const double locx = rint(lx + G / 2.0), locy = rint(ly + G / 2.0);
     const double x0 = rint(locx - dimx / 2.0), y0 = rint(locy - dimy / 2.0);
+    // scene_generator.py:888-922: a wall strictly inside the map is the slice [start, start + dim); one that touches the
+    // border goes through the per-cell path, which only writes cells 0 < index < G: [max(start, 1), min(start + dim, G))
     short4 r;
-    r.x = (short)fmin(fmax(x0, 0.0), G); r.y = (short)fmin(fmax(y0, 0.0), G);
-    r.z = (short)fmin(fmax(x0 + dimx, 0.0), G); r.w = (short)fmin(fmax(y0 + dimy, 0.0), G);
+    r.x = (short)fmin(fmax(x0, 1.0), G); r.y = (short)fmin(fmax(y0, 1.0), G);
+    r.z = (short)fmin(fmax(x0 + dimx, 1.0), G); r.w = (short)fmin(fmax(y0 + dimy, 1.0), G);
     reinterpret_cast<short4 *>(st.rect)[(size_t)e * Rm + w] = r;
     const double xm = lx * res, ym = ly * res;
+    const bool square = xd == yd;               // :383-396: one disc at the centre
     const bool horiz = xd > yd;
     const double rr = (horiz ? yd : xd) / 2.0 * sqrt(2.0);
     const double hi = horiz ? xm + xd / 2.0 : ym + yd / 2.0;
     double pos = (horiz ? xm - xd / 2.0 : ym - yd / 2.0) + rr;
     for (int k = 0; k < sh.discs_per_wall; ++k) {
-      if (pos < hi && n_stat < Sm) {
+      const bool live = square ? k == 0 : pos < hi;
+      if (live && n_stat < Sm) {
         reinterpret_cast<float4 *>(st.stat)[(size_t)e * Sm + n_stat] =
-            make_float4((float)(horiz ? pos : xm), (float)(horiz ? ym : pos), (float)rr, 0.f);
+            make_float4((float)(square ? xm : (horiz ? pos : xm)), (float)(square ? ym : (horiz ? ym : pos)), (float)rr, 0.f);
         ++n_stat;
       }
       pos = pos + 2.0 * rr;
@@ -1554,20 +1600,33 @@ int ebc_launch_reset(ebc_sim *s, const ebc_state *pool, int pool_size, const int
   return ebc_check_launch(s, "reset_kernel");
 }
 
-static int fused_warps(const ebc_sim *s) {
-  int warps = s->cfg.max_humans < 16 ? s->cfg.max_humans : 16;
+// lanes per human in K1: a half warp when every human has at most 32 candidates and 16 ORCA lines (two humans per
+// warp, bit-identical to the whole-warp kernel; EBC_ORCA_GROUP=32 forces one human per warp)
+static int orca_group(const ebc_sim *s) {
+  const char *env = getenv("EBC_ORCA_GROUP");
+  if (env && atoi(env) == 32) return 32;
+  if (s->cfg.orca_obstacles) return 32;
+  return (s->cfg.max_humans + (s->cfg.robot_visible ? 1 : 0) <= 32 && s->cfg.orca_max_neighbors <= 16) ? 16 : 32;
+}
+static int fused_warps(const ebc_sim *s, int group) {
+  const int per_warp = 32 / group;
+  int warps = (s->cfg.max_humans + per_warp - 1) / per_warp;
+  warps = warps < 16 ? warps : 16;
   return warps < 1 ? 1 : warps;
 }
 
 int ebc_launch_orca(ebc_sim *s, cudaStream_t stream) {
   if (s->cfg.orca_obstacles) {   // block per episode: the obstacle vertices are staged once per block
-    orca_step_kernel<true, false><<<s->cfg.n_episodes, fused_warps(s) * 32, 0, stream>>>(
+    orca_step_kernel<true, false, 32><<<s->cfg.n_episodes, fused_warps(s, 32) * 32, 0, stream>>>(
         s->cfg, s->st, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ebc_stats{});
     return ebc_check_launch(s, "orca_step_kernel<obstacles, no commit>");
   }
-  const long long warps = (long long)s->cfg.n_episodes * s->cfg.max_humans;
+  const int group = orca_group(s);
+  const long long groups = (long long)s->cfg.n_episodes * s->cfg.max_humans;
+  const long long warps = (groups + (32 / group) - 1) / (32 / group);
   const int blocks = (int)((warps + EBC_WARPS_PER_BLOCK - 1) / EBC_WARPS_PER_BLOCK);
-  orca_kernel<<<blocks, EBC_THREADS, 0, stream>>>(s->cfg, s->st);
+  if (group == 16) orca_kernel<16><<<blocks, EBC_THREADS, 0, stream>>>(s->cfg, s->st);
+  else orca_kernel<32><<<blocks, EBC_THREADS, 0, stream>>>(s->cfg, s->st);
   return ebc_check_launch(s, "orca_kernel");
 }
 
@@ -1622,13 +1681,16 @@ int ebc_launch_step(ebc_sim *s, bool fused_orca, const int32_t *action_idx, cons
   ebc_stats sx = s->stats;                      // all-null when unbound
   if (!active && sx.alive) active = sx.alive;   // the bound alive[] is the mask (ebc_bind_stats)
   if (fused_orca) {
-    const int threads = fused_warps(s) * 32;
-    if (s->cfg.orca_obstacles)
-      orca_step_kernel<true, true><<<s->cfg.n_episodes, threads, 0, stream>>>(s->cfg, s->st, s->d_actions, action_idx, action,
-                                                                             active, reward, done, event, dmin, dist_to_goal, sx);
-    else
-      orca_step_kernel<false, true><<<s->cfg.n_episodes, threads, 0, stream>>>(s->cfg, s->st, s->d_actions, action_idx, action,
-                                                                              active, reward, done, event, dmin, dist_to_goal, sx);
+    const int group = orca_group(s);
+    const int threads = fused_warps(s, group) * 32;
+#define EBC_FUSED(OBST, GW)                                                                                         \
+  orca_step_kernel<OBST, true, GW><<<s->cfg.n_episodes, threads, 0, stream>>>(s->cfg, s->st, s->d_actions, action_idx, \
+                                                                              action, active, reward, done, event, dmin, \
+                                                                              dist_to_goal, sx)
+    if (s->cfg.orca_obstacles) EBC_FUSED(true, 32);
+    else if (group == 16) EBC_FUSED(false, 16);
+    else EBC_FUSED(false, 32);
+#undef EBC_FUSED
     return ebc_check_launch(s, "orca_step_kernel");
   }
   const int blocks = (s->cfg.n_episodes + EBC_WARPS_PER_BLOCK - 1) / EBC_WARPS_PER_BLOCK;

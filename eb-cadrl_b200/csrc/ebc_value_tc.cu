@@ -379,6 +379,7 @@ __device__ __forceinline__ void epi_to_a(Pipe<NSPLIT> &pipe, uint32_t tmem_row, 
         for (int i = 0; i < 16; ++i) x[i] = real ? v[i] : 0.0f;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
+          if (o >= n) break;          // a run holds at most min(n, 32) lanes: ceil(log2) steps reach its head (warp-uniform)
           const int s2 = __shfl_down_sync(0xffffffffu, g_seg, o);
           const bool take = lane + o < 32 && s2 == g_seg;
 #pragma unroll
@@ -640,10 +641,13 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
         const bool b_in = S.bias_k >= 0 || (P.n_wide > 1 && P.st[ST_L1B].bias_k >= 0);   // bias rode in one K chunk
         EpiExtra ex;
         ex.one_col = P.st[ST_L2].bias_k;          // H1 is the A operand of mlp2.0 and attention.0
-        if (P.with_global && n <= 32) {
+        if (P.with_global) {
           if (!was_early) crew_sync();   // cnt[] of this tile is visible
+          // the state mean of H1 is taken here, from the fp32 registers of the epilogue: a segmented shuffle reduction
+          // per warp; a state longer than a warp (n > 32) leaves one partial per warp, added in a fixed order below
           ex.n = n; ex.row_cnt = cnt[st_of_row]; ex.g_out = G; ex.g_ld = g_ld; ex.g_states = ts;
           ex.g_sid = my_sid; ex.g_rin = my_rin; ex.g_seg = my_row ? my_sid : -1 - (row >> 5);
+          ex.g_part = n <= 32 ? 0 : (row >> 5) % wps;
           epi_to_a<NSPLIT, true>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, b_in ? nullptr : P.bias[1], A, row, true, 0, ex);
         } else {
           epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, b_in ? nullptr : P.bias[1], A, row, true, 0, ex);
@@ -654,27 +658,11 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
       if (P.with_global) {
         if (n <= 32) {
           __syncwarp();    // G[., state] for this thread's blocks was written by this warp
+          gx_to_a<NSPLIT>(pipe, G, g_ld, st_of_row, cg, h1d, 16 * h1b, A, row, h1b, 1, 0);
         } else {
-          // states longer than a warp (few per tile): the mean is read back from the operand images, rows in order
-          crew_sync();     // every H1 block is in the A images
-          for (int i = tid; i < ts * h1d; i += NCREW) {
-            const int k = i % h1d, s = i / h1d;
-            const int c = cnt[s];
-            float acc = 0.0f;
-            for (int r = 0; r < c; ++r) {
-              const int trow = ((s * wps + (r >> 5)) << 5) + (r & 31);
-              const size_t off = (size_t)(k >> 3) * A_CHUNK_BYTES + (size_t)trow * 16 + (size_t)(k & 7) * 2;
-              float v = 0.0f;
-#pragma unroll
-              for (int sp = 0; sp < NSPLIT; ++sp)
-                v += Fmt<NSPLIT>::from16(*reinterpret_cast<const uint16_t *>(A + (size_t)sp * Cfg<NSPLIT>::A_IMAGE + off));
-              acc += v;
-            }
-            G[s * g_ld + k] = c > 0 ? acc / (float)c : 0.0f;
-          }
-          crew_sync();
+          crew_sync();     // the partial means of the state's other warps
+          gx_to_a<NSPLIT>(pipe, G, g_ld, st_of_row, cg, h1d, 16 * h1b, A, row, h1b, wps, ts * g_ld);
         }
-        gx_to_a<NSPLIT>(pipe, G, g_ld, st_of_row, cg, h1d, 16 * h1b, A, row, h1b, 1, 0);
         pipe.f_phase ^= low_bits(h1b);                  // attention.0 (local half) released every H1 block
         pipe.stamp();
       }
@@ -791,6 +779,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
           float es = e;
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) {
+            if (o >= n) break;
             const float y = __shfl_down_sync(0xffffffffu, es, o);
             const int s2 = __shfl_down_sync(0xffffffffu, sid, o);
             if (lane + o < 32 && s2 == sid) es += y;
@@ -818,6 +807,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
           for (int i = 0; i < 16; ++i) v[i] = (real && c + i < h2d) ? v[i] * wrow : 0.0f;
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) {
+            if (o >= n) break;
             const int s2 = __shfl_down_sync(0xffffffffu, sid, o);
             const bool take = lane + o < 32 && s2 == sid;
 #pragma unroll

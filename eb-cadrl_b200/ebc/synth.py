@@ -70,7 +70,7 @@ class SceneShape(object):
         for i, (code, count, (v0, v1), (r0, r1)) in enumerate(self.types):
             s.type_code[i], s.type_count[i] = code, count
             s.v_pref_lo[i], s.v_pref_hi[i], s.radius_lo[i], s.radius_hi[i] = v0, v1, r0, r1
-        s.rule = {"square_crossing": 0, "circle_crossing": 1, "mixed": 2}[self.rule]
+        s.rule = {"square_crossing": 0, "circle_crossing": 1, "mixed": 2, "mixed_20": 3}[self.rule]
         s.num_walls, s.wall_len_lo, s.wall_len_hi = self.num_walls, self.wall_len[0], self.wall_len[1]
         s.discs_per_wall, s.max_tries = self.discs_per_wall, max_tries
         s.square_width, s.circle_radius = self.square_width, self.circle_radius
@@ -88,9 +88,48 @@ CFG3 = SceneShape("cfg3_h5_circle_unicycle", [(0, 5, (1.0, 1.0), (0.3, 0.3))], r
 # configs[3]: dense crowd, 20 humans + 10 walls on a 14 m map
 CFG4 = SceneShape("cfg4_h20_10walls", [(0, 20, (1.0, 1.0), (0.3, 0.3))], rule="mixed", square_width=13.0,
                   circle_radius=6.0, robot_v_pref=1.0, num_walls=10, wall_len=(2, 4), map_size_m=14.0)
+# the reference's full `mixed_20` rule (scene_generator.py:577-582): randint(20) static adults + the dynamic mix
+MIXED20 = SceneShape("mixed_20_h20_5walls", [(0, 20, (0.5, 1.5), (0.2, 0.4))], rule="mixed_20", square_width=13.0,
+                     circle_radius=6.0, robot_v_pref=1.0, num_walls=5, wall_len=(2, 4), map_size_m=14.0)
 # configs[0] shape (the reference's CPU-runnable case): 5 adults on a circle of radius 3
 CFG1 = SceneShape("cfg1_h5_circle", [(0, 5, (0.6, 0.6), (0.2, 0.2))], rule="circle_crossing", square_width=9.0,
                   circle_radius=3.0, robot_radius=0.2, robot_v_pref=0.7, num_walls=0)
+
+
+def wall_geometry(lx, ly, xd, yd, G, res, discs_per_wall):
+    """What the reference derives from a wall (grid location lx, ly relative to the map centre; dimensions xd, yd in
+    metres), vectorised over episodes:
+      * its zero-cell rectangle in scene.map (scene_generator.py:255-268,888-922): dim = round(d / res) cells,
+        location = round(l + G / 2); a wall strictly inside the map is the slice [start, start + dim) with
+        start = round(location - dim / 2); one that touches the border goes through the per-cell path, which only
+        writes cells 0 < index < G -- so the rectangle is [max(start, 1), min(start + dim, G)) on both axes either way
+        (dim / 2 is a whole number of cells for whole-metre walls on a 0.1 m grid);
+      * its static discs (:380-422): radius = half thickness * sqrt(2), centres from (low edge + r) in steps of 2 r
+        while < high edge; a square wall is one disc at its centre.
+    -> (rect [N, 4] int16, list of (x, y, r, live) per disc slot)"""
+    dimx = np.rint(xd / res).astype(np.int64)
+    dimy = np.rint(yd / res).astype(np.int64)
+    locx = np.rint(lx + G / 2.0).astype(np.int64)
+    locy = np.rint(ly + G / 2.0).astype(np.int64)
+    x0 = np.rint(locx - dimx / 2.0).astype(np.int64)
+    y0 = np.rint(locy - dimy / 2.0).astype(np.int64)
+    r = np.stack([np.clip(x0, 1, G), np.clip(y0, 1, G), np.clip(x0 + dimx, 1, G), np.clip(y0 + dimy, 1, G)], 1).astype(np.int16)
+    xm, ym = lx * res, ly * res
+    square = xd == yd
+    horiz = xd > yd
+    half_t = np.where(horiz, yd, xd) / 2.0
+    rr = half_t * np.sqrt(2.0)
+    lo = np.where(horiz, xm - xd / 2.0, ym - yd / 2.0)
+    hi = np.where(horiz, xm + xd / 2.0, ym + yd / 2.0)
+    pos = lo + rr
+    discs = []
+    for k in range(discs_per_wall):
+        live = np.where(square, k == 0, pos < hi)
+        sx = np.where(square, xm, np.where(horiz, pos, xm))
+        sy = np.where(square, ym, np.where(horiz, ym, pos))
+        discs.append((sx, sy, rr, live))
+        pos = pos + 2.0 * rr
+    return r, discs
 
 
 def generate(shape, episode_ids, seed=SEED_BASE, max_tries=64, max_obst=0):
@@ -121,32 +160,55 @@ def generate(shape, episode_ids, seed=SEED_BASE, max_tries=64, max_obst=0):
             rad[:, h] = r0 + (r1 - r0) * uniform(seed, ids, 1000 + h, 1)
         h0 += c
     hw = shape.square_width / 2.0
+    # rule mixed_20 (scene_generator.py:577-582): randint(20) static adults in a 6 x 8 box, the rest dynamic
+    n_static = np.floor(uniform(seed, ids, 4000, 0) * 20.0).astype(np.int64) if shape.rule == "mixed_20" else np.zeros(N, np.int64)
+    n_dynamic = H - n_static
     for h in range(H):
-        todo = np.ones(N, bool)
         first_of_type = int(np.nonzero(types == types[h])[0][0])
+        is_static_all = h < n_static
+        hd = h - n_static
+        circle_all = ~is_static_all & ((shape.rule == "circle_crossing") | ((shape.rule in ("mixed", "mixed_20")) & (hd < n_dynamic // 2)))
+        fixed = is_static_all & (h == 0)                      # :463-466: the first static adult is fixed
+        px[fixed, h], py[fixed, h], gx[fixed, h], gy[fixed, h] = -0.5, -2.5, -0.5, -2.5
+        todo = ~fixed
+        sign_all = np.where(uniform(seed, ids, 2000 + h, 7) < 0.5, 1.0, -1.0)
+        md_robot_all = rad[:, h] + shape.robot_radius + shape.discomfort_dist
         for attempt in range(max_tries):
             if not todo.any():
                 break
             e = ids[todo]
             u = lambda d: uniform(seed, e, 2000 + h, attempt * 8 + d)  # noqa: E731
-            circle = shape.rule == "circle_crossing" or (shape.rule == "mixed" and h < H // 2)
-            if circle:
-                ang = u(0) * 2.0 * np.pi
-                x, y = R * np.cos(ang), R * np.sin(ang)
-                tx, ty = -x, -y
-            else:
-                side = np.floor(u(0) * 4.0).astype(np.int64)   # top, bottom, left, right
-                a = -hw + 2.0 * hw * u(1)
-                b = -hw + 2.0 * hw * u(2)
-                x = np.where(side == 0, a, np.where(side == 1, a, np.where(side == 2, -hw, hw)))
-                y = np.where(side == 0, hw, np.where(side == 1, -hw, a))
-                tx = np.where(side == 0, b, np.where(side == 1, b, np.where(side == 2, hw, -hw)))
-                ty = np.where(side == 0, -hw, np.where(side == 1, hw, b))
-            # reject starts too close to the robot or to same-type agents placed earlier
-            # (scene_generator.py:683-693 checks [robot] + other_agents of the same list)
-            ok = np.hypot(x - 0.0, y + R) >= rad[todo, h] + shape.robot_radius + shape.discomfort_dist
+            st_, ci_ = is_static_all[todo], circle_all[todo]
+            md_robot = md_robot_all[todo]
+            u0, u1, u2 = u(0), u(1), u(2)
+            # static adult (:467-487)
+            xs = u0 * 6.0 * 0.5 * sign_all[todo]
+            ys = (u1 - 0.5) * 8.0
+            # circle crossing (:593-618)
+            ang = u0 * 2.0 * np.pi
+            xc, yc = R * np.cos(ang), R * np.sin(ang)
+            # square crossing (:672-712): top, bottom, left, right
+            side = np.floor(u0 * 4.0).astype(np.int64)
+            a = -hw + 2.0 * hw * u1
+            b = -hw + 2.0 * hw * u2
+            xq = np.where(side == 0, a, np.where(side == 1, a, np.where(side == 2, -hw, hw)))
+            yq = np.where(side == 0, hw, np.where(side == 1, -hw, a))
+            txq = np.where(side == 0, b, np.where(side == 1, b, np.where(side == 2, hw, -hw)))
+            tyq = np.where(side == 0, -hw, np.where(side == 1, hw, b))
+            x = np.where(st_, xs, np.where(ci_, xc, xq))
+            y = np.where(st_, ys, np.where(ci_, yc, yq))
+            tx = np.where(st_, xs, np.where(ci_, -xc, txq))
+            ty = np.where(st_, ys, np.where(ci_, -yc, tyq))
+            # reject starts too close to the robot or to agents of the same list placed earlier (all rules); the circle
+            # rule also keeps clear of everybody's GOAL (:608-616), static adults of the robot's goal (:480-483)
+            ok = np.hypot(x - 0.0, y + R) >= md_robot
+            ok &= ~ci_ | (np.hypot(x - 0.0, y - R) >= md_robot)
             for j in range(first_of_type, h):
-                ok &= np.hypot(x - px[todo, j], y - py[todo, j]) >= rad[todo, h] + rad[todo, j] + shape.discomfort_dist
+                mdj = rad[todo, h] + rad[todo, j] + shape.discomfort_dist
+                ok &= np.hypot(x - px[todo, j], y - py[todo, j]) >= mdj
+                ok &= ~ci_ | (np.hypot(x - gx[todo, j], y - gy[todo, j]) >= mdj)
+            last_r = rad[todo, h - 1] if h > first_of_type else np.full(len(e), shape.robot_radius)
+            ok &= ~st_ | (np.hypot(x - 0.0, y - R) >= rad[todo, h] + last_r + shape.discomfort_dist)
             if attempt == max_tries - 1:
                 ok[:] = True
             idx = np.nonzero(todo)[0][ok]
@@ -186,36 +248,20 @@ def generate(shape, episode_ids, seed=SEED_BASE, max_tries=64, max_obst=0):
             idx = np.nonzero(todo)[0][ok]
             lx[idx], ly[idx], xd[idx], yd[idx] = cx[ok], cy[ok], xdim[ok], ydim[ok]
             todo[idx] = False
-        dimx = np.rint(xd / res).astype(np.int64)
-        dimy = np.rint(yd / res).astype(np.int64)
-        locx = np.rint(lx + G / 2.0).astype(np.int64)
-        locy = np.rint(ly + G / 2.0).astype(np.int64)
-        x0 = np.rint(locx - dimx / 2.0).astype(np.int64)
-        y0 = np.rint(locy - dimy / 2.0).astype(np.int64)
-        r = np.stack([np.clip(x0, 0, G), np.clip(y0, 0, G), np.clip(x0 + dimx, 0, G), np.clip(y0 + dimy, 0, G)], 1)
-        rect[:, w] = r.astype(np.int16)
+        r, discs = wall_geometry(lx, ly, xd, yd, G, res, shape.discs_per_wall)
+        rect[:, w] = r
         rect_count += 1
-        # discs along the long axis, radius = half thickness * sqrt(2)
         xm, ym = lx * res, ly * res
         if max_obst:
             for e in range(N):
                 walls[e].append((xm[e], ym[e], xd[e], yd[e]))
-        horiz = xd > yd
-        half_t = np.where(horiz, yd, xd) / 2.0
-        rr = half_t * np.sqrt(2.0)
-        lo = np.where(horiz, xm - xd / 2.0, ym - yd / 2.0)
-        hi = np.where(horiz, xm + xd / 2.0, ym + yd / 2.0)
-        pos = lo + rr
-        for _ in range(shape.discs_per_wall):
-            live = pos < hi
+        for sx, sy, rr, live in discs:
             k = stat_count[live]
-            sx = np.where(horiz, pos, xm)[live]
-            sy = np.where(horiz, ym, pos)[live]
-            stat[np.nonzero(live)[0], k, 0] = sx
-            stat[np.nonzero(live)[0], k, 1] = sy
-            stat[np.nonzero(live)[0], k, 2] = rr[live]
+            rows = np.nonzero(live)[0]
+            stat[rows, k, 0] = sx[live]
+            stat[rows, k, 1] = sy[live]
+            stat[rows, k, 2] = rr[live]
             stat_count[live] += 1
-            pos = pos + 2.0 * rr
     extra = {}
     if max_obst:
         from . import abi

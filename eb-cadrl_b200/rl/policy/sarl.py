@@ -24,7 +24,14 @@ class ValueNetwork(nn.Module):
         self.attention = mlp(mlp1_dims[-1] * (2 if with_global_state else 1), attention_dims)
         self.cell_size, self.cell_num = cell_size, cell_num
         self.mlp3 = mlp(mlp2_dims[-1] + self.self_state_dim, mlp3_dims)
-        self.attention_weights = None
+        self._attention = None
+
+    @property
+    def attention_weights(self):
+        """sarl.py:71 keeps `weights[0, :, 0].data.cpu().numpy()` on every forward; here the device -> host copy
+        happens when somebody reads it (a copy per forward would be a host sync per optimizer step, and is illegal
+        inside a CUDA-graph capture)."""
+        return None if self._attention is None else self._attention.cpu().numpy()
 
     def forward(self, state, row_count=None):
         """state: (batch, n, D); optional row_count (batch,) masks zero-padded entity rows."""
@@ -49,7 +56,7 @@ class ValueNetwork(nn.Module):
         if mask is not None:
             e = e * mask
         weights = (e / e.sum(dim=1, keepdim=True)).unsqueeze(2)
-        self.attention_weights = weights[0, :, 0].data.cpu().numpy()
+        self._attention = weights[0, :, 0].detach()
         pooled = (weights * h2.view(b, n, -1)).sum(dim=1)
         return self.mlp3(torch.cat([self_state, pooled], dim=1))
 

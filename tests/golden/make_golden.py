@@ -443,6 +443,55 @@ def update_memory_golden(out):
     print("  update_memory.npz: rl T=%d, il T=%d" % (len(res["rl_rewards"]), len(res["il_rewards"])))
 
 
+def static_decomposition(out):
+    """Walls -> occupancy grid (scene_generator.py:888-922, incl. the per-cell edge path) and -> static discs
+    (:380-422) by the REFERENCE's own code, for walls given as (grid location, dimensions) the way generate_wall
+    returns them (:194-243).  Pins the wall geometry of the synthetic / device scene generator."""
+    class WallCfg(object):      # what generate_static_map_input / generate_wall read from a scene config
+        def __init__(self, walls):
+            self.walls = walls
+
+        def getint(self, sec, key):
+            return {"num_circles": 0, "num_walls": len(self.walls)}[key]
+
+        def getfloat(self, sec, key):
+            w = self.walls[int(key)]
+            return {"x_locations_walls": w[0], "y_locations_walls": w[1], "x_dim": w[2], "y_dim": w[3]}[sec]
+
+    res = {}
+    rng = np.random.default_rng(20261018)
+    k = 0
+    for cfgp, size in (("configs/test_configs/test_env_configs/env_adults_3_bikes_3_static_2.config", None),
+                       ("data/eb-cadrl/adults_8_bikes_8_child_8_static_3_35_sec_new_reward_fix_static.config", None)):
+        env, policy, robot, ec, pc = make(cfgp, None, None, "linear")
+        sg = env.scene
+        robot.set(0, -sg.circle_radius, 0, sg.circle_radius, 0, 0, np.pi / 2)
+        G = int(round(sg.map_size_m / sg.map_resolution))
+        for scene in range(40):
+            walls = []
+            while len(walls) < 4:
+                lx, ly = int(rng.integers(-G // 2, G // 2)), int(rng.integers(-G // 2, G // 2))
+                length = int(rng.integers(1, 6))
+                xd, yd = (length, 1) if rng.random() > 0.5 else (1, length)
+                xm, ym = lx * sg.map_resolution, ly * sg.map_resolution
+                clear = robot.radius + sg.discomfort_dist
+                near = any(abs(xm - 0.0) < xd / 2.0 + clear and abs(ym - gy) < yd / 2.0 + clear
+                           for gy in (-sg.circle_radius, sg.circle_radius))
+                if not near:          # (generate_wall would spin on a fixed wall that touches the robot's start / goal)
+                    walls.append((lx, ly, xd, yd))
+            sg.generate_static_map_input(sg.map_size_m, "test", config=WallCfg(walls))
+            res["s%03d_walls" % k] = np.array(walls, dtype=np.int64)
+            res["s%03d_map" % k] = np.array([sg.map_size_m, sg.map_resolution])
+            res["s%03d_zero" % k] = np.packbits((sg.map == 0).astype(np.uint8), axis=None)
+            res["s%03d_discs" % k] = np.array([[s.px, s.py, s.radius] for s in sg.static_obstacles_as_pedestrians],
+                                              dtype=np.float64).reshape(-1, 3)
+            res["s%03d_vertices" % k] = np.array(sg.obstacle_vertices, dtype=np.float64).reshape(-1, 4, 2)
+            k += 1
+    res["n_scenes"] = np.array([k])
+    np.savez_compressed(os.path.join(out, "static_decomposition.npz"), **res)
+    print("  static_decomposition.npz: %d scenes x 4 walls" % k)
+
+
 def round2(out):
     """Fixtures added in round 2 (the earlier ones are left untouched)."""
     POL = "configs/test_configs/test_policy_configs/policy.config"
@@ -468,6 +517,7 @@ def round2(out):
     e[1].set_epsilon(0.0)
     trace("trace_train_unicycle_adults5_seed1008", *e, {"test_case": 8}, 24, {0}, out)
     update_memory_golden(out)
+    static_decomposition(out)
 
 
 def main():

@@ -240,3 +240,78 @@ def test_test_parallel_csv(tmp_path):
     row = df.iloc[0]
     assert len(row["dmin_adult"]) == round(row["time"] / 0.25) and len(row["min_dist"]) == row["too_close"]
     assert back.loc[0, "dmin_adult"].startswith("[")            # lists are written like pandas writes the reference's
+
+
+def test_graph_trainer_equals_eager_trainer():
+    """The CUDA-graph optimizer step (batch gather + forward + backward + SGD captured once, replayed per step) leaves
+    the same weights as the eager step on the same batches, and the replay really is one launch sequence."""
+    import copy
+    from rl.policy.policy_factory import policy_factory
+    from rl.utils.memory import ReplayMemory
+    from rl.utils.trainer import Trainer
+    pc = configparser.RawConfigParser(); pc.read(os.path.join(CFG, "policy_ebcadrl.config"))
+    torch.manual_seed(3)
+    pol = policy_factory["sarl"]()
+    pol.configure(pc)
+    model = pol.get_model().to("cuda:0")
+    twin = copy.deepcopy(model)
+    mem = ReplayMemory(4096, device="cuda:0")
+    g = torch.Generator(device="cuda:0").manual_seed(11)
+    mem.push_batch(torch.randn(3000, 30, 17, device="cuda:0", generator=g),
+                   torch.randint(1, 31, (3000,), device="cuda:0", generator=g),
+                   torch.randn(3000, device="cuda:0", generator=g) * 0.3)
+    a = Trainer(model, mem, torch.device("cuda:0"), 100, policy=pol, use_graphs=True)
+    b = Trainer(twin, mem, torch.device("cuda:0"), 100, use_graphs=False)
+    for t in (a, b):
+        t.set_optimizer(0.001)
+    idx = torch.randint(0, 3000, (12, 100), device="cuda:0", generator=g)
+    for i in range(12):
+        a._step(index=idx[i])
+        b._step(index=idx[i])
+    torch.cuda.synchronize()
+    assert a._graph is not None and a._graph[1] is None            # one GPU: a single graph holds the whole step
+    for (k, x), y in zip(model.state_dict().items(), twin.state_dict().values()):
+        assert torch.allclose(x, y, rtol=1e-5, atol=1e-7), (k, float((x - y).abs().max()))
+    la, lb = a._take_loss(), b._take_loss()
+    assert abs(la - lb) < 1e-5 * max(1.0, abs(lb))
+    # a partial batch (imitation-learning epochs end with one) takes the eager path on the same flat buffers
+    a._step(index=idx[0][:37]); b._step(index=idx[0][:37])
+    torch.cuda.synchronize()
+    for x, y in zip(model.state_dict().values(), twin.state_dict().values()):
+        assert torch.allclose(x, y, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("H,S,R,dense,visible", [(10, 6, 3, False, False), (24, 6, 3, True, True), (31, 0, 0, True, True)])
+def test_half_warp_orca_is_bit_identical(oracle, H, S, R, dense, visible):
+    """K1 with two humans per warp (16-lane groups, member-mask shuffles / ballots) == one human per warp == oracle,
+    bit for bit, in both launch shapes (orca_kernel, fused orca_step_kernel), incl. maxNeighbors truncation and LP3."""
+    N = 1024
+    cfg = random_cfg("holonomic", typed=True, visible=visible)
+    actions = build_action_space(0.8)
+    batch = random_batch(N, H, S, R, seed=300 + H, dense=dense)
+    idx = torch.as_tensor(np.random.default_rng(3).integers(0, 81, N), dtype=torch.int32)
+    out = {}
+    try:
+        for group in ("16", "32"):
+            os.environ["EBC_ORCA_GROUP"] = group
+            g = BatchedSim(cfg, N, H, S, R, 81, device="cuda:0")
+            g.set_actions(actions)
+            g.load_episodes(0, **batch)
+            g.orca()
+            nv = g.hum_nv.clone()
+            for _ in range(4):
+                g.step(action_idx=idx.cuda(), fused_orca=True)
+            torch.cuda.synchronize()
+            out[group] = (nv, g.hum_pv.clone(), g.hum_nv.clone())
+    finally:
+        os.environ.pop("EBC_ORCA_GROUP", None)
+    for a, b in zip(out["16"], out["32"]):
+        assert torch.equal(a, b)
+    r = BatchedSim(cfg, N, H, S, R, 81, device="cpu", backend=oracle)
+    r.set_actions(actions)
+    r.load_episodes(0, **batch)
+    r.orca()
+    assert np.array_equal(np_(out["16"][0]), r.hum_nv.numpy())
+    for _ in range(4):
+        r.step(action_idx=idx, fused_orca=True)
+    assert np.array_equal(np_(out["16"][1]), r.hum_pv.numpy())

@@ -239,3 +239,81 @@ def test_update_memory_matches_reference():
     np.testing.assert_allclose(ep0, z["rl_values"], rtol=0, atol=1e-5)
     np.testing.assert_allclose(ep1[:-1], z["rl_values"][:T2 - 1], rtol=0, atol=1e-5)
     assert ep1[-1] == np.float32(rewards[T2 - 1])                # its last step is terminal: no bootstrap
+
+
+def test_synth_wall_geometry_matches_reference():
+    """f-1: walls -> occupancy grid and -> static discs of the synthetic generator (ebc/synth.py: wall_geometry, which
+    the device generator ebc_generate is held equal to on the GPU) against the REFERENCE's own place_obstacles_on_map /
+    create_observation_from_static_obstacles (tests/golden/static_decomposition.npz: 80 scenes x 4 walls, lengths 1-5,
+    walls hanging over the map border included)."""
+    from ebc import synth
+    z = np.load(os.path.join(ob.GOLDEN, "static_decomposition.npz"))
+    n_clipped = n_square = 0
+    for k in range(int(z["n_scenes"][0])):
+        walls = z["s%03d_walls" % k]
+        size, res = z["s%03d_map" % k]
+        G = int(round(size / res))
+        zero = np.unpackbits(z["s%03d_zero" % k])[:G * G].reshape(G, G).astype(bool)
+        mine = np.zeros_like(zero)
+        discs = []
+        for lx, ly, xd, yd in walls:
+            r, dl = synth.wall_geometry(np.array([float(lx)]), np.array([float(ly)]), np.array([float(xd)]),
+                                        np.array([float(yd)]), G, res, 8)
+            x0, y0, x1, y1 = [int(v) for v in r[0]]
+            mine[x0:x1, y0:y1] = True
+            n_clipped += (x1 - x0) * (y1 - y0) != round(xd / res) * round(yd / res)
+            n_square += xd == yd
+            discs += [(sx[0], sy[0], rr[0]) for sx, sy, rr, live in dl if live[0]]
+        assert np.array_equal(mine, zero), k
+        ref = z["s%03d_discs" % k]
+        assert len(discs) == len(ref), (k, len(discs), len(ref))
+        np.testing.assert_allclose(np.array(discs).reshape(-1, 3), ref, rtol=0, atol=1e-12)
+    assert n_clipped >= 10 and n_square >= 10      # border-clipped and square walls were part of the fixture
+
+
+@pytest.mark.parametrize("shape_name", ["CFG1", "CFG2", "CFG3", "CFG4", "MIXED20"])
+def test_synth_scenes_obey_reference_placement_rules(shape_name):
+    """f-1: start / goal geometry, minimum separation, wall clearance, disc radii of scene_generator.py on the host
+    generator's output (tests/scene_rules.py restates each rule with its reference line)."""
+    from ebc import synth
+    from scene_rules import check_scene_rules
+    shape = getattr(synth, shape_name)
+    res = check_scene_rules(shape, synth.generate(shape, np.arange(5000, 5000 + 768)))
+    print(shape.name, res)
+
+
+def test_trainer_flat_sgd_equals_torch_sgd():
+    """The trainer's flat-buffer update == torch.optim.SGD(lr, momentum=0.9) of the reference (trainer.py:21-27,74-100)
+    on identical batches: same parameters after every step (to fp32 rounding of one fused multiply-add)."""
+    import copy
+    from rl.policy.policy_factory import policy_factory
+    from rl.utils.memory import ReplayMemory
+    from rl.utils.trainer import Trainer
+    torch.manual_seed(1)
+    pol = policy_factory["sarl"]()
+    pol.configure(read("policy.config"))
+    model = pol.get_model()
+    ref = copy.deepcopy(model)
+    mem = ReplayMemory(256, device="cpu")
+    g = torch.Generator().manual_seed(7)
+    mem.push_batch(torch.randn(200, 5, 13, generator=g), torch.randint(1, 6, (200,), generator=g), torch.randn(200, generator=g))
+    tr = Trainer(model, mem, "cpu", 32, policy=pol)
+    tr.set_optimizer(0.01)
+    opt = torch.optim.SGD(ref.parameters(), lr=0.01, momentum=0.9)
+    crit = torch.nn.MSELoss()
+    total = 0.0
+    for step in range(6):
+        idx = torch.randint(0, 200, (32,), generator=g)
+        tr._step(index=idx)
+        opt.zero_grad()
+        loss = crit(ref(mem.states[idx], mem.rows[idx]), mem.values[idx])
+        loss.backward()
+        opt.step()
+        total += loss.item()
+        for (k, a), b in zip(model.state_dict().items(), ref.state_dict().values()):
+            assert torch.allclose(a, b, rtol=1e-6, atol=1e-8), (step, k, (a - b).abs().max())
+    assert abs(tr._take_loss() - total) < 1e-6 and pol.weights_version == 6
+    # the module's tensors are views of the flat buffers (no gather / scatter around the all-reduce)
+    assert all(p.data.untyped_storage().data_ptr() == tr._flat.untyped_storage().data_ptr() for p in model.parameters())
+    sd = copy.deepcopy(model.state_dict())
+    model.load_state_dict(sd)                      # checkpoint I/O still works on the views
