@@ -530,10 +530,10 @@ __device__ void orca_agent_warp(unsigned m, int lane, float px, float py, float 
 #pragma unroll
   for (int c2 = 0; c2 < 2; ++c2) {
     if (c2 >= n_chunks) break;
-    unsigned m = vmask[c2];
-    while (m) {
-      const int l = __ffs(m) - 1;
-      m &= m - 1;
+    unsigned rest = vmask[c2];
+    while (rest) {
+      const int l = __ffs(rest) - 1;
+      rest &= rest - 1;
       const float dk = __shfl_sync(m, d[c2], l, GW);
       const int k = l + GW * c2;
 #pragma unroll

@@ -79,7 +79,7 @@ class Trainer(object):
         outputs = self.model(states, rows)
         loss = self.criterion(outputs, values)
         loss.backward()                      # accumulates into the views of self._grad
-        self._grad[-1] = 1.0
+        self._grad[-1:].fill_(1.0)           # (a kernel, not a host scalar copy: legal inside a graph capture)
         self._loss_acc += loss.detach().double()
 
     def _apply_update(self, averaged):

@@ -430,7 +430,7 @@ def test_error_codes():
     lib.ebc_destroy(h)
 
 
-@pytest.mark.parametrize("shape_name,N", [("CFG2", 4096), ("CFG3", 2048), ("CFG4", 2048), ("CFG1", 512)])
+@pytest.mark.parametrize("shape_name,N", [("CFG2", 4096), ("CFG3", 2048), ("CFG4", 2048), ("CFG1", 512), ("MIXED20", 2048)])
 def test_device_scene_generator_matches_host(shape_name, N):
     """the device generator (ebc_generate, thread per episode, counter-based draws) against the host
     generator of ebc/synth.py (numpy float64, same draws): humans with rejection sampling, walls with start / goal
@@ -454,6 +454,13 @@ def test_device_scene_generator_matches_host(shape_name, N):
         assert (a != b.reshape(a.shape)).mean() < 1e-4, k
     assert float(sim.hum_pv[5, 0, 0]) == 7.0 and float(sim.time[5]) == 3.0
     assert (np_(sim.hum_nv)[keep] == 0).all()
+    # and, directly on the DEVICE output, the reference's placement rules (tests/scene_rules.py cites each one:
+    # start / goal geometry, minimum separations, wall clearance, border-clipped grid rectangles, disc radii); the wall
+    # geometry itself is pinned to the reference by tests/golden/static_decomposition.npz through the host twin
+    from scene_rules import check_scene_rules
+    dev = {k: np_(getattr(sim, k))[keep] for k in ("hum_pv", "hum_gr", "hum_type", "hum_count", "stat", "stat_count", "rect",
+                                                   "rect_count", "rob_pv", "rob_gr", "rob_theta", "time")}
+    print(shape.name, check_scene_rules(shape, dev))
     # and the generated batch is a valid starting state: one full decision + step runs on it
     sim.set_actions(build_action_space(shape.robot_v_pref))
     sim.orca()
