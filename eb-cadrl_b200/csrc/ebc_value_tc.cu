@@ -280,6 +280,31 @@ struct Pipe {
   }
 };
 
+// Column sums over the 32 lanes of a warp: every lane passes 16 values (columns 0..15 of its row); lane l returns the
+// total of column (l >> 1) (both lanes of a pair hold it).  Transpose-reduce: 8 + 4 + 2 + 1 + 1 shuffles instead of
+// 16 x 5, additions in a fixed order.
+__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
+  float w8[8], w4[4], w2[2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = (lane & 16) ? v[i] : v[i + 8], keep = (lane & 16) ? v[i + 8] : v[i];
+    w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = (lane & 8) ? w8[i] : w8[i + 4], keep = (lane & 8) ? w8[i + 4] : w8[i];
+    w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = (lane & 4) ? w4[i] : w4[i + 2], keep = (lane & 4) ? w4[i + 2] : w4[i];
+    w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const float send = (lane & 2) ? w2[0] : w2[1], keep = (lane & 2) ? w2[1] : w2[0];
+  const float x = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  return x + __shfl_xor_sync(0xffffffffu, x, 1);
+}
+
 // accumulator columns [col0, col0 + ncols) of this thread's row, this thread's column group
 // -> relu(x + bias), columns >= n_real forced to 0 -> block (c / 16) of the A operand, published to the MMA warp.
 // n_free: blocks below this index wait for afree (the previous commit_k stage read them).
@@ -362,6 +387,15 @@ __device__ __forceinline__ void epi_to_a(Pipe<NSPLIT> &pipe, uint32_t tmem_row, 
         const float send = (lane & 1) ? w2[0] : w2[1], keep = (lane & 1) ? w2[1] : w2[0];
         const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 1);
         if (g_sid < g_states) g_out[g_sid * g_ld + c + (lane & 15)] = tot * inv;
+      } else if (n >= 32) {
+        // the warp's 32 rows belong to one state (a state longer than a warp leaves one partial per warp, g_part)
+        const int lane = threadIdx.x & 31;
+        float x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = real ? v[i] : 0.0f;
+        const float tot = warp_colsum16(x, lane);
+        if (!(lane & 1) && g_sid < g_states)
+          g_out[((size_t)g_part * g_states + g_sid) * g_ld + c + (lane >> 1)] = tot * inv;
       } else if (32 % n == 0) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -757,8 +791,65 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
           const int s = tid / p.self_dim, k = tid % p.self_dim;
           p.joint[joint_index(s0 + s, k, p.jch)] = XS[s * 8 + k];
         }
+      } else if (n <= 32) {
+        // a state = one run of n lanes of this warp (n does not divide 32: the warp's last lanes are padding rows).
+        // Softmax denominator and pooled features by segmented shuffle reductions whose order depends on n only;
+        // the run's first lane stores the pooled block straight to the joint row -- no scratch, no block barrier.
+        // (Same additions as the scratch path below, which adds its single per-warp partial to 0.)
+        const int lane = tid & 31;
+        const int sid = my_row ? my_sid : -1 - (row >> 5);         // padding rows: a run of their own
+        const bool in_tile = my_row && my_sid < ns;
+        const bool real = in_tile && my_rin < cnt[min(my_sid, MAX_STATES - 1)];
+        const int head_lane = my_row ? lane - my_rin : lane;
+        const bool head = lane == head_lane;
+        const TcStage &S = P.st[ST_L3];
+        const float sc = ((SC[row] + SC[TILE_M + row]) + (SC[2 * TILE_M + row] + SC[3 * TILE_M + row])) + P.b6;
+        const float e = (real && sc != 0.0f) ? expf(sc) : 0.0f;
+        float es = e;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          if (o >= n) break;
+          const float y = __shfl_down_sync(0xffffffffu, es, o);
+          const int s2 = __shfl_down_sync(0xffffffffu, sid, o);
+          if (lane + o < 32 && s2 == sid) es += y;
+        }
+        const float sum = __shfl_sync(0xffffffffu, es, head_lane);
+        const float wrow = e / sum;          // NaN like the reference when every score of the state is exactly 0
+        for (int c = 16 * cg; c < S.np; c += 16 * NCG) {
+          float v[16];
+          tmem_ld16(tmem_row + S.acc_col + c, v);
+          if (S.bias_k < 0) {
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+              const float4 bb = __ldg(reinterpret_cast<const float4 *>(P.bias[3] + c) + qd);
+              v[4 * qd] += bb.x; v[4 * qd + 1] += bb.y; v[4 * qd + 2] += bb.z; v[4 * qd + 3] += bb.w;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = (real && c + i < h2d) ? v[i] * wrow : 0.0f;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            if (o >= n) break;
+            const int s2 = __shfl_down_sync(0xffffffffu, sid, o);
+            const bool take = lane + o < 32 && s2 == sid;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float y = __shfl_down_sync(0xffffffffu, v[i], o);
+              if (take) v[i] += y;
+            }
+          }
+          if (head && in_tile) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c + i < h2d) p.joint[joint_index(s0 + my_sid, p.self_dim + c + i, p.jch)] = v[i];
+          }
+        }
+        if (tid < ns * p.self_dim) {
+          const int s = tid / p.self_dim, k = tid % p.self_dim;
+          p.joint[joint_index(s0 + s, k, p.jch)] = XS[s * 8 + k];
+        }
       } else {
-        // any row count: a state's rows are a contiguous run of rows, i.e. at most one run of lanes per warp.
+        // states longer than a warp: a state's rows are a contiguous run of rows, one run of lanes per warp.
         // Sums over a state = segmented shuffle reduction inside each warp, one partial per (lane quarter, state)
         // in shared memory, added in a fixed order (deterministic, no atomics).  Scratch aliases the A region,
         // which is free: every MMA that read it has completed.
@@ -805,22 +896,10 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = (real && c + i < h2d) ? v[i] * wrow : 0.0f;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            if (o >= n) break;
-            const int s2 = __shfl_down_sync(0xffffffffu, sid, o);
-            const bool take = lane + o < 32 && s2 == sid;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float y = __shfl_down_sync(0xffffffffu, v[i], o);
-              if (take) v[i] += y;
-            }
-          }
-          if (head && in_tile) {
-            float4 *dst = reinterpret_cast<float4 *>(PJ + ((size_t)q * ts + sid) * S.np + c);
-#pragma unroll
-            for (int qd = 0; qd < 4; ++qd) dst[qd] = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
-          }
+          // the warp's 32 rows belong to one state: one transpose-reduce, lane pair l holds the sum of column l >> 1
+          const float tot = warp_colsum16(v, lane);
+          const int sid_w = (row >> 5) / wps;
+          if (!(lane & 1) && sid_w < ns) PJ[((size_t)q * ts + sid_w) * S.np + c + (lane >> 1)] = tot;
         }
         crew_sync();
         for (int i = tid; i < ns * p.jd; i += NCREW) {
@@ -1058,9 +1137,9 @@ int launch_tc(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row
     const int g_cap = (int)(Cfg<NSPLIT>::G_BYTES / (4u * (uint32_t)p.prog.st[ST_L2].ksteps * 16u));
     if (ts > g_cap) ts = g_cap;
   }
-  // generic row counts pool through a scratch that aliases the operand images: [4][32] + [4][ts][np3] floats
+  // states longer than a warp pool through a scratch that aliases the operand images: [4][32] + [4][ts][np3] floats
   // (one image minus the four k-chunks that hold the next tile's input)
-  while (n != 16 && ts > 1 && 512u + 16u * (uint32_t)ts * (uint32_t)p.prog.st[ST_L3].np > Cfg<NSPLIT>::A_IMAGE - 4u * A_CHUNK_BYTES) --ts;
+  while (n > 32 && ts > 1 && 512u + 16u * (uint32_t)ts * (uint32_t)p.prog.st[ST_L3].np > Cfg<NSPLIT>::A_IMAGE - 4u * A_CHUNK_BYTES) --ts;
   p.ts = ts;
   p.joint = s->d_joint; p.jd = s->net.self_dim + s->net.l[3].out; p.self_dim = s->net.self_dim;
   p.jch = (p.jd + 7) / 8;

@@ -337,6 +337,27 @@ typedef struct ebc_scene_shape {
 int ebc_generate(ebc_sim *sim, const ebc_scene_shape *shape, uint64_t seed, const int64_t *episode_ids,
                  const uint8_t *mask, void *stream);
 
+/* Angular local map of simulator/env.py:468-628: for every episode the distance to the closest
+ * obstacle outline in each of `dim` angular sectors around the robot, in the robot's heading frame (angle 0 at
+ * the negative x axis as in the reference), clipped to max_range and optionally normalised by it.  What
+ * env.step / env.reset return as `local_map` when [map] use_grid_map = false.
+ * Obstacle outlines are the reference's scene.obstacle_vertices: quadrilaterals, 4 vertices each in the
+ * reference's order; the robot pose (px, py, radius, theta) comes from the bound state (fp32, promoted).
+ * All arithmetic is the reference's float64 sequence; sector minima are order-free, so the kernel spreads the
+ * (obstacle, robot corner) and (obstacle, vertex) passes of env.py:596-620 over the lanes of a warp. */
+typedef struct ebc_angular_map {
+  double max_range;      /* [map] angular_map_max_range */
+  double min_angle;      /* [map] angle_min * pi */
+  double max_angle;      /* [map] angle_max * pi */
+  int32_t dim;           /* [map] angular_map_dim (<= 256) */
+  int32_t normalize;     /* divide by max_range (env.py:622-623; the reference's default) */
+  int32_t max_polys;     /* Pmax: quadrilaterals per episode in poly_xy */
+  int32_t reserved;
+} ebc_angular_map;
+/* poly_xy [N*Pmax*4*2] f64 (device), poly_count [N] i32 (device), out [N*dim] f64 (device). */
+int ebc_local_map_angular(ebc_sim *sim, const ebc_angular_map *map, const double *poly_xy, const int32_t *poly_count,
+                          double *out, void *stream);
+
 /* ---- diagnostics (exported, but NOT part of the drop-in surface: nothing in the reference binds these;
  *      declared only when the includer asks for them) ---------------------------------------------------------- */
 #ifdef EBC_DIAGNOSTICS
@@ -370,6 +391,8 @@ int ebc_ref_step(ebc_sim *sim, const int32_t *action_idx, const double *action,
 int ebc_ref_transform(ebc_sim *sim, float *out);
 int ebc_ref_reset(ebc_sim *sim, const ebc_state *pool, int32_t pool_size, const int32_t *pool_index,
                   const uint8_t *mask);
+int ebc_ref_local_map_angular(ebc_sim *sim, const ebc_angular_map *map, const double *poly_xy, const int32_t *poly_count,
+                              double *out);
 void ebc_ref_set_threads(int n);   /* OpenMP threads over episodes (cpu_baseline leg) */
 
 #ifdef __cplusplus

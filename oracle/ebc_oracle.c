@@ -1344,6 +1344,102 @@ int ebc_ref_step(ebc_sim *s, const int32_t *action_idx, const double *action, co
 }
 
 /* env.reset from a scene pool: simulator/env.py:128-205 (state hand-over only). */
+/* ---- angular local map --------------------------------------------------------------------
+ * simulator/env.py:468-568 calculate_angular_map_distances: one vertex seen from one robot corner ("edge"), then
+ * the outline between this vertex and every earlier one of the same sweep, interpolated sector by sector. */
+typedef struct { double max_range, min_angle, max_angle, res; int dim; } amap_t;
+
+static void amap_calc(const amap_t *m, const double vertex[2], const double edge[2], double cs, double sn, double *vec,
+                      int *rad_indeces, double (*locations)[2], int *n_seen) {
+  double px = (vertex[0] - edge[0]) * cs + (vertex[1] - edge[1]) * sn;              /* env.py:474-479 */
+  double py = (vertex[1] - edge[1]) * cs - (vertex[0] - edge[0]) * sn;
+  const double phi = atan2(py, px);
+  const int rad_idx = (int)((phi - m->min_angle) / m->res);                         /* int(): truncation */
+  const double distance = sqrt(px * px + py * py);
+  if (rad_idx >= 0 && rad_idx < m->dim && distance < vec[rad_idx]) vec[rad_idx] = distance;
+  for (int k = 0; k < *n_seen; ++k) {                                                /* env.py:488-566 */
+    const int old = rad_indeces[k];
+    const double *loc = locations[k];
+    int wrapped, idx_diff;
+    if ((double)abs(rad_idx - old) > M_PI / m->res) {
+      wrapped = 1;
+      idx_diff = rad_idx > old ? m->dim - rad_idx + old : m->dim - old + rad_idx;
+    } else {
+      wrapped = 0;
+      idx_diff = abs(rad_idx - old);
+    }
+    for (int i = 0; i < idx_diff; ++i) {
+      const double t = (double)i / (double)idx_diff;
+      if ((rad_idx < old && !wrapped) || (rad_idx > old && wrapped)) {
+        if (rad_idx + i >= 0 && rad_idx + i < m->dim) {
+          const double qx = vertex[0] + t * (loc[0] - vertex[0]) - edge[0];
+          const double qy = vertex[1] + t * (loc[1] - vertex[1]) - edge[1];
+          px = qx * cs + qy * sn;
+          py = qy * cs - qx * sn;
+          const double d = sqrt(px * px + py * py);
+          if (d < vec[rad_idx + i]) vec[rad_idx + i] = d;
+        }
+      } else {
+        if (old + i >= 0 && old + i < m->dim) {
+          const double qx = loc[0] + t * (vertex[0] - loc[0]) - edge[0];
+          const double qy = loc[1] + t * (vertex[1] - loc[1]) - edge[1];
+          px = qx * cs + qy * sn;
+          py = qy * cs - qx * sn;
+          const double d = sqrt(px * px + py * py);
+          if (d < vec[old + i]) vec[old + i] = d;
+        }
+      }
+    }
+  }
+  rad_indeces[*n_seen] = rad_idx;
+  locations[*n_seen][0] = vertex[0];
+  locations[*n_seen][1] = vertex[1];
+  ++*n_seen;
+}
+
+/* simulator/env.py:570-628 get_local_map_angular for every episode of the bound state. */
+int ebc_ref_local_map_angular(ebc_sim *s, const ebc_angular_map *map, const double *poly_xy, const int32_t *poly_count,
+                              double *out) {
+  if (!s || !s->bound) return fail(s, EBC_ERR_UNBOUND, "ebc_local_map_angular: state not bound");
+  if (!map || !poly_count || !out || map->dim < 1 || map->dim > 256 || map->max_polys < 0 ||
+      (map->max_polys > 0 && !poly_xy))
+    return fail(s, EBC_ERR_INVALID, "ebc_local_map_angular: bad argument");
+  amap_t m;
+  m.max_range = map->max_range; m.min_angle = map->min_angle; m.max_angle = map->max_angle; m.dim = map->dim;
+  m.res = (map->max_angle - map->min_angle) / (double)map->dim;
+  static const double SGN[4][2] = {{-1, -1}, {1, -1}, {-1, 1}, {1, 1}};               /* env.py:592-594 */
+  for (int e = 0; e < s->cfg.n_episodes; ++e) {
+    double *vec = out + (size_t)e * m.dim;
+    for (int i = 0; i < m.dim; ++i) vec[i] = m.max_range;
+    const double rx = s->st.rob_pv[(size_t)e * 4], ry = s->st.rob_pv[(size_t)e * 4 + 1];
+    const double rad = s->st.rob_gr[(size_t)e * 4 + 3], theta = s->st.rob_theta[e];
+    const double cs = cos(theta), sn = sin(theta);
+    double edges[4][2];
+    for (int k = 0; k < 4; ++k) { edges[k][0] = rx + SGN[k][0] * rad; edges[k][1] = ry + SGN[k][1] * rad; }
+    int P = poly_count[e];
+    if (P > map->max_polys) P = map->max_polys;
+    int idx[4], n_seen;
+    double loc[4][2];
+    for (int o = 0; o < P; ++o) {                                                      /* env.py:596-609 */
+      const double *poly = poly_xy + ((size_t)e * map->max_polys + o) * 8;
+      for (int k = 0; k < 4; ++k) {
+        n_seen = 0;
+        for (int v = 0; v < 4; ++v) amap_calc(&m, poly + 2 * v, edges[k], cs, sn, vec, idx, loc, &n_seen);
+      }
+    }
+    for (int o = 0; o < P; ++o) {                                                      /* env.py:611-620 */
+      const double *poly = poly_xy + ((size_t)e * map->max_polys + o) * 8;
+      for (int v = 0; v < 4; ++v) {
+        n_seen = 0;
+        for (int k = 0; k < 4; ++k) amap_calc(&m, poly + 2 * v, edges[k], cs, sn, vec, idx, loc, &n_seen);
+      }
+    }
+    if (map->normalize)
+      for (int i = 0; i < m.dim; ++i) vec[i] /= m.max_range;                           /* env.py:622-623 */
+  }
+  return EBC_OK;
+}
+
 int ebc_ref_reset(ebc_sim *s, const ebc_state *pool, int32_t pool_size, const int32_t *pool_index,
                   const uint8_t *mask) {
   if (!s || !s->bound) return fail(s, EBC_ERR_UNBOUND, "ebc_reset: state not bound");
