@@ -286,6 +286,15 @@ int ebc_generate(ebc_sim *s, const ebc_scene_shape *shape, uint64_t seed, const 
   return ebc_launch_generate(s, shape, seed, episode_ids, mask, (cudaStream_t)stream);
 }
 
+int ebc_local_map_angular(ebc_sim *s, const ebc_angular_map *map, const double *poly_xy, const int32_t *poly_count,
+                          double *out, void *stream) {
+  REQUIRE_BOUND("ebc_local_map_angular");
+  if (!map || !poly_count || !out || map->dim < 1 || map->dim > 256 || map->max_polys < 0 ||
+      (map->max_polys > 0 && !poly_xy) || !(map->max_angle > map->min_angle) || !(map->max_range > 0.0))
+    return ebc_fail(s, EBC_ERR_INVALID, "ebc_local_map_angular: bad argument (1 <= dim <= 256, max_angle > min_angle, max_range > 0)");
+  return ebc_launch_angular_map(s, map, poly_xy, poly_count, out, (cudaStream_t)stream);
+}
+
 int ebc_debug_trace(ebc_sim *s, long long *out, int32_t n) {
   if (!s || !out || n < 1) return EBC_ERR_INVALID;
   if (!s->d_trace) return ebc_fail(s, EBC_ERR_UNBOUND, "ebc_debug_trace: run ebc_value with EBC_TC_TRACE=1 first");

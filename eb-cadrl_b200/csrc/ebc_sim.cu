@@ -1426,6 +1426,97 @@ reset_kernel(const ebc_config c, const ebc_state st, const ebc_state pool, int p
   }
 }
 
+// ---- angular local map (simulator/env.py:468-628) ------------------------------------------------
+// One vertex seen from one robot corner, then the outline towards every earlier vertex of the same sweep
+// (env.py:468-568).  Sector minima go to shared memory with a 64-bit atomicMin on the bit pattern of the
+// (non-negative) distance: the minimum does not depend on the order, so the reference's sequential sweeps can
+// run on different lanes.  fp64 in the reference's operation order (this unit has no FMA contraction).
+struct AngularMap { double max_range, min_angle, res; int dim; };
+
+__device__ __forceinline__ void amap_min(unsigned long long *vec, int i, double d) {
+  atomicMin(vec + i, (unsigned long long)__double_as_longlong(d));
+}
+
+__device__ void amap_calc(const AngularMap &m, double vx, double vy, double ex, double ey, double cs, double sn,
+                          unsigned long long *vec, int (&rad_indeces)[4], double (&lx)[4], double (&ly)[4], int &n_seen) {
+  double px = (vx - ex) * cs + (vy - ey) * sn;
+  double py = (vy - ey) * cs - (vx - ex) * sn;
+  const double phi = atan2(py, px);
+  const int rad_idx = (int)((phi - m.min_angle) / m.res);          // Python int(): truncation
+  if (rad_idx >= 0 && rad_idx < m.dim) amap_min(vec, rad_idx, sqrt(px * px + py * py));
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (k >= n_seen) break;
+    const int old = rad_indeces[k];
+    bool wrapped;
+    int idx_diff;
+    if ((double)abs(rad_idx - old) > 3.141592653589793 / m.res) {
+      wrapped = true;
+      idx_diff = rad_idx > old ? m.dim - rad_idx + old : m.dim - old + rad_idx;
+    } else {
+      wrapped = false;
+      idx_diff = abs(rad_idx - old);
+    }
+    const bool from_vertex = (rad_idx < old && !wrapped) || (rad_idx > old && wrapped);
+    const double ax = from_vertex ? vx : lx[k], ay = from_vertex ? vy : ly[k];      // start of the interpolation
+    const double bx = from_vertex ? lx[k] : vx, by = from_vertex ? ly[k] : vy;      // its end
+    const int first = from_vertex ? rad_idx : old;
+    for (int i = 0; i < idx_diff; ++i) {
+      if (first + i < 0 || first + i >= m.dim) continue;
+      const double t = (double)i / (double)idx_diff;
+      const double qx = ax + t * (bx - ax) - ex;
+      const double qy = ay + t * (by - ay) - ey;
+      px = qx * cs + qy * sn;
+      py = qy * cs - qx * sn;
+      amap_min(vec, first + i, sqrt(px * px + py * py));
+    }
+  }
+  rad_indeces[n_seen] = rad_idx; lx[n_seen] = vx; ly[n_seen] = vy;
+  ++n_seen;
+}
+
+// Warp per episode; lane g takes sweep g: sweeps [0, 4P) = (obstacle, robot corner) over the obstacle's four
+// vertices (env.py:596-609), sweeps [4P, 8P) = (obstacle, vertex) over the four robot corners (env.py:611-620).
+__global__ void __launch_bounds__(EBC_THREADS)
+angular_map_kernel(const ebc_config c, const ebc_state st, const ebc_angular_map mp, const double *__restrict__ poly_xy,
+                   const int32_t *__restrict__ poly_count, double *__restrict__ out) {
+  __shared__ unsigned long long vecs[EBC_WARPS_PER_BLOCK][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * EBC_WARPS_PER_BLOCK + warp;
+  if (e >= c.n_episodes) return;
+  unsigned long long *vec = vecs[warp];
+  AngularMap m;
+  m.max_range = mp.max_range; m.min_angle = mp.min_angle; m.dim = mp.dim;
+  m.res = (mp.max_angle - mp.min_angle) / (double)mp.dim;
+  for (int i = lane; i < m.dim; i += 32) vec[i] = (unsigned long long)__double_as_longlong(m.max_range);
+  __syncwarp();
+  const float4 rp = reinterpret_cast<const float4 *>(st.rob_pv)[e];
+  const double rx = (double)rp.x, ry = (double)rp.y, rad = (double)st.rob_gr[(size_t)e * 4 + 3];
+  const double theta = (double)st.rob_theta[e];
+  const double cs = cos(theta), sn = sin(theta);
+  int P = poly_count[e];
+  P = P < 0 ? 0 : (P > mp.max_polys ? mp.max_polys : P);
+  for (int g = lane; g < 8 * P; g += 32) {
+    const bool by_vertex = g >= 4 * P;
+    const int gg = by_vertex ? g - 4 * P : g;
+    const int o = gg >> 2, k = gg & 3;
+    const double *poly = poly_xy + ((size_t)e * mp.max_polys + o) * 8;
+    int idx[4], n_seen = 0;
+    double lx[4], ly[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int v = by_vertex ? k : j, corner = by_vertex ? j : k;      // (-1,-1), (1,-1), (-1,1), (1,1): env.py:592-594
+      const double ex = rx + ((corner & 1) ? 1.0 : -1.0) * rad, ey = ry + ((corner & 2) ? 1.0 : -1.0) * rad;
+      amap_calc(m, poly[2 * v], poly[2 * v + 1], ex, ey, cs, sn, vec, idx, lx, ly, n_seen);
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < m.dim; i += 32) {
+    const double d = __longlong_as_double((long long)vec[i]);
+    out[(size_t)e * m.dim + i] = mp.normalize ? d / m.max_range : d;
+  }
+}
+
 // ---- scene generator: thread per episode, counter-based draws, fp64 in the host generator's
 //      operation order (this unit is compiled without FMA contraction), narrowed to fp32 at the end ----------
 __device__ __forceinline__ unsigned long long gen_mix(unsigned long long x) {
@@ -1697,4 +1788,11 @@ int ebc_launch_step(ebc_sim *s, bool fused_orca, const int32_t *action_idx, cons
   step_kernel<<<blocks, EBC_THREADS, 0, stream>>>(s->cfg, s->st, s->d_actions, action_idx, action, active, reward,
                                                   done, event, dmin, dist_to_goal, sx);
   return ebc_check_launch(s, "step_kernel");
+}
+
+int ebc_launch_angular_map(ebc_sim *s, const ebc_angular_map *map, const double *poly_xy, const int32_t *poly_count,
+                           double *out, cudaStream_t stream) {
+  const int blocks = (s->cfg.n_episodes + EBC_WARPS_PER_BLOCK - 1) / EBC_WARPS_PER_BLOCK;
+  angular_map_kernel<<<blocks, EBC_THREADS, 0, stream>>>(s->cfg, s->st, *map, poly_xy, poly_count, out);
+  return ebc_check_launch(s, "angular_map_kernel");
 }

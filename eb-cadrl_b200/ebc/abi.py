@@ -84,6 +84,11 @@ class EbcSceneShape(ctypes.Structure):
                 ("map_size_m", c_f64), ("map_resolution", c_f64), ("discomfort_dist", c_f64)]
 
 
+class EbcAngularMap(ctypes.Structure):       # [map] section of the env config (simulator/env.py:79-87)
+    _fields_ = [("max_range", c_f64), ("min_angle", c_f64), ("max_angle", c_f64), ("dim", c_i32),
+                ("normalize", c_i32), ("max_polys", c_i32), ("reserved", c_i32)]
+
+
 SIM = vp
 PROTOTYPES = {
     "ebc_create": (c_i32, [ctypes.POINTER(EbcConfig), c_i32, ctypes.POINTER(SIM)]),
@@ -108,6 +113,7 @@ PROTOTYPES = {
     "ebc_transform": (c_i32, [SIM, vp, vp]),
     "ebc_reset": (c_i32, [SIM, ctypes.POINTER(EbcState), c_i32, vp, vp, vp]),
     "ebc_generate": (c_i32, [SIM, ctypes.POINTER(EbcSceneShape), ctypes.c_uint64, vp, vp, vp]),
+    "ebc_local_map_angular": (c_i32, [SIM, ctypes.POINTER(EbcAngularMap), vp, vp, vp, vp]),
     "ebc_debug_trace": (c_i32, [SIM, vp, c_i32]),
     "ebc_launch_count": (ctypes.c_int64, [SIM]),
 }

@@ -171,6 +171,7 @@ class BatchedEnv(object):
         sd = np.zeros((self.N, S, 4), np.float32); sc = np.zeros(self.N, np.int32)
         rc = np.zeros((self.N, R, 4), np.int16); rcc = np.zeros(self.N, np.int32)
         rad = sg.circle_radius
+        polys = []
         for e, seed in enumerate(seeds):
             self.robot.set(0, -rad, 0, rad, 0, 0, np.pi / 2)
             sg.generate_random_scene(self.COUNTER_OFFSET, phase, scene_number=int(seed))
@@ -191,6 +192,14 @@ class BatchedEnv(object):
                 raise abi.EbcError("scene %d needs %d grid rectangles (capacity %d)" % (seed, len(rects), sim.Rmax))
             rc[e, :len(rects)] = rects
             rcc[e] = len(rects)
+            polys.append(np.asarray(sg.obstacle_vertices, dtype=np.float64).reshape(-1, 4, 2))
+        # scene.obstacle_vertices of every episode, for the angular local map (local_map_batch)
+        P = max([len(v) for v in polys] + [1])
+        xy = np.zeros((self.N, P, 4, 2), np.float64)
+        for e, v in enumerate(polys):
+            xy[e, :len(v)] = v
+        self.poly_xy = torch.as_tensor(xy).to(self.device)
+        self.poly_count = torch.as_tensor(np.array([len(v) for v in polys], np.int32)).to(self.device)
         rob_pv = np.tile(np.array([0, -rad, 0, 0], np.float32), (self.N, 1))
         rob_gr = np.tile(np.array([0, rad, self.robot.v_pref, self.robot.radius], np.float32), (self.N, 1))
         sim.load_episodes(0, pv, gr, ty, hc, sd, sc, rc, rcc, rob_pv, rob_gr,
@@ -210,6 +219,14 @@ class BatchedEnv(object):
     def step_batch(self, action_idx=None, action=None, active=None):
         self.sim.step(action_idx=action_idx, action=action, active=active, fused_orca=action_idx is None)
         return self.sim.reward, self.sim.done, self.sim.event
+
+    def local_map_batch(self, normalize=True, out=None):
+        """`local_map` of env.reset / env.step for every episode (simulator/env.py:570-628, use_grid_map = false):
+        [N, angular_map_dim] float64 on the device, one launch (ebc_local_map_angular)."""
+        c = self.config
+        return self.sim.local_map_angular(self.poly_xy, self.poly_count, c.getfloat("map", "angular_map_max_range"),
+                                          c.getfloat("map", "angle_min") * np.pi, c.getfloat("map", "angle_max") * np.pi,
+                                          c.getint("map", "angular_map_dim"), normalize=normalize, out=out)
 
     # ---- the explorer's inner loop on the device (rl/utils/explorer.py:33-94) ------------------------------
     @torch.no_grad()

@@ -326,6 +326,18 @@ class BatchedSim(object):
         self.be.call("transform", self.h, _ptr(out), stream=self._stream())
         return out
 
+    def local_map_angular(self, poly_xy, poly_count, max_range, min_angle, max_angle, dim, normalize=True, out=None):
+        """Angular local map of every episode (simulator/env.py:570-628): `poly_xy` [N, Pmax, 4, 2]
+        float64 = scene.obstacle_vertices, `poly_count` [N] int32; returns [N, dim] float64 on the device."""
+        assert poly_xy.dtype == torch.float64 and poly_xy.dim() == 4 and tuple(poly_xy.shape[2:]) == (4, 2)
+        assert poly_xy.shape[0] == self.N and poly_count.dtype == torch.int32 and poly_count.shape[0] == self.N
+        if out is None:
+            out = torch.empty(self.N, dim, dtype=torch.float64, device=self.device)
+        m = abi.EbcAngularMap(max_range, min_angle, max_angle, dim, 1 if normalize else 0, poly_xy.shape[1], 0)
+        self.be.call("local_map_angular", self.h, ctypes.byref(m), _ptr(poly_xy.contiguous()), _ptr(poly_count),
+                     _ptr(out), stream=self._stream())
+        return out
+
     def launch_count(self):
         return self.be.launch_count(self.h)
 

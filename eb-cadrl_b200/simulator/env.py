@@ -8,8 +8,10 @@ libebcadrl.so (`self.native`, an ebc.engine.BatchedSim of one episode); the Agen
 the device state after every committed step.  N > 1 callers use ebc.batched_env.BatchedEnv, which drives the
 same BatchedSim with whole batches.
 
-Out of scope: the angular / grid local maps (`local_map` is returned as None — no shipped
-policy consumes it) and rendering.
+`local_map`: with [map] use_grid_map = false the angular map of env.py:570-628 is computed on the
+device (`ebc_local_map_angular`) for reset / step, like the reference does on every call; the lookahead skips it
+(the reference computes and drops it there).  The binary grid sub-map (use_grid_map = true, an OpenCV warpAffine of
+the occupancy grid) and rendering are out of scope: `local_map` is None in that mode.
 """
 import numpy as np
 import torch
@@ -48,6 +50,11 @@ class EntityBasedCollisionAvoidance(object):
         self.attention_weights = None
         self._policy_bound = None
         self._probe = None
+        self._map_probe = None
+        self._poly = None
+        self.local_maps = None
+        self.local_maps_angular = None
+        self.local_map_enabled = True       # False: reset / step return local_map = None without the extra launch
 
     # ---- set-up (env.py:58-92) ----------------------------------------------------------------------
     def configure(self, config):
@@ -58,6 +65,13 @@ class EntityBasedCollisionAvoidance(object):
         self.reward = Reward(config)
         self.case_capacity = {"train": np.iinfo(np.uint32).max - 2000, "val": 1000, "test": 1000}
         self.use_grid_map = config.getboolean("map", "use_grid_map")
+        if self.use_grid_map:
+            self.submap_size_m = config.getfloat("map", "submap_size_m")
+        else:
+            self.angular_map_max_range = config.getfloat("map", "angular_map_max_range")
+            self.angular_map_dim = config.getint("map", "angular_map_dim")
+            self.angular_map_min_angle = config.getfloat("map", "angle_min") * np.pi
+            self.angular_map_max_angle = config.getfloat("map", "angle_max") * np.pi
         self.sim_config = SimConfig.from_ini(config)
 
     def set_robot(self, robot):
@@ -138,6 +152,44 @@ class EntityBasedCollisionAvoidance(object):
         self.robot.theta = float(n.rob_theta[0].item())
         self.global_time = float(n.time[0].item())
 
+    # ---- angular local map (env.py:570-628) on the device ---------------------------------------------------
+    def _polygons(self):
+        """scene.obstacle_vertices as the device arrays of ebc_local_map_angular (rebuilt when the scene changes)."""
+        verts = np.asarray(self.scene.obstacle_vertices, dtype=np.float64).reshape(-1, 4, 2)
+        key = (verts.tobytes(), str(self.native.device))
+        if self._poly is None or self._poly[0] != key:
+            dev = self.native.device
+            P = len(verts)
+            xy = torch.zeros(1, max(P, 1), 4, 2, dtype=torch.float64)
+            if P:
+                xy[0, :P] = torch.as_tensor(verts)
+            self._poly = (key, xy.to(dev), torch.tensor([P], dtype=torch.int32, device=dev))
+        return self._poly[1], self._poly[2]
+
+    def get_local_map_angular(self, ob=None, normalize=True, append=True):
+        """Distance to the closest obstacle outline per angular sector around `ob` (a FullState; default: the
+        robot's current state on the device), simulator/env.py:570-628."""
+        n = self.native
+        xy, cnt = self._polygons()
+        sim = n
+        if ob is not None:
+            if self._map_probe is None or self._map_probe.device != n.device:
+                self._map_probe = BatchedSim(n.cfg, 1, 1, 0, 0, 1, device=n.device)
+            sim = self._map_probe
+            sim.rob_pv[0, 0], sim.rob_pv[0, 1] = float(ob.px), float(ob.py)
+            sim.rob_gr[0, 3] = float(ob.radius)
+            sim.rob_theta[0] = float(ob.theta)
+        vec = sim.local_map_angular(xy, cnt, self.angular_map_max_range, self.angular_map_min_angle,
+                                    self.angular_map_max_angle, self.angular_map_dim, normalize=normalize)[0].cpu().numpy()
+        if append and self.local_maps_angular is not None:
+            self.local_maps_angular.append(vec)
+        return vec
+
+    def _local_map(self, compute_local_map):
+        if not (compute_local_map and self.local_map_enabled) or self.use_grid_map:
+            return None
+        return self.get_local_map_angular()
+
     def _observation(self):
         ob = [h.get_observable_state() for h in self._humans()]
         if self.robot.policy.name != "SDOADRL":
@@ -169,6 +221,8 @@ class EntityBasedCollisionAvoidance(object):
         self.bicycle_times = [0] * len(self.scene.bicycles)
         self.children_times = [0] * len(self.scene.children)
         self.states = list()
+        self.local_maps = list()
+        self.local_maps_angular = list()
         if hasattr(self.robot.policy, "action_values"):
             self.action_values = list()
         if hasattr(self.robot.policy, "get_attention_weights"):
@@ -176,9 +230,10 @@ class EntityBasedCollisionAvoidance(object):
         self._build_native()
         self._sync_agents_from_device()      # the hot path's state is fp32: objects mirror it exactly
         ob = self._observation()
+        local_map = self._local_map(compute_local_map)
         if self.robot.policy.name == "ORCA":
-            return ob, self.scene.obstacle_vertices, None
-        return ob, None
+            return ob, self.scene.obstacle_vertices, local_map
+        return ob, local_map
 
     # ---- step (env.py:388-466) and lookahead (env.py:207-209) ----------------------------------------------
     def _action_pair(self, action):
@@ -214,7 +269,7 @@ class EntityBasedCollisionAvoidance(object):
             for i, agent in enumerate(group):      # first arrival times (env.py:365-378)
                 if times[i] == 0 and agent.reached_destination():
                     times[i] = self.global_time
-        return self._observation(), None, reward, done, info
+        return self._observation(), self._local_map(compute_local_map), reward, done, info
 
     def onestep_lookahead(self, action):
         """Simulate one step without committing it; returns (next entity states, reward, done, info)."""

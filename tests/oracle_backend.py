@@ -45,6 +45,7 @@ class OracleBackend(object):
         L.ebc_ref_step.argtypes = [vp] * 9
         L.ebc_ref_transform.argtypes = [vp, vp]
         L.ebc_ref_reset.argtypes = [vp, ctypes.POINTER(abi.EbcState), c_i32, vp, vp]
+        L.ebc_ref_local_map_angular.argtypes = [vp, ctypes.POINTER(abi.EbcAngularMap), vp, vp, vp]
         L.ebc_ref_set_threads.argtypes = [ctypes.c_int]
 
     def set_threads(self, n):
