@@ -624,7 +624,7 @@ def main():
         "other_value_mode": {"mode": other, "k4_ms": other_ms, "achieved_tflops": fl / (other_ms / 1e3) / 1e12,
                              "argmax_agreement_with_%s" % args.value_mode: other_agree},
         "sim_only": {"agent_steps_per_sec": total_eps * (H + 1) / sim_step_s, "ms_per_step": sim_step_s * 1e3,
-                     "launches_per_step": 1,
+                     "launches_per_step": 2,   # K1 (half a warp per human) then K2 (warp per episode), one ebc_orca_step call
                      "roofline": {"bound": "hbm", "achieved": sim_bytes / sim_step_s / 1e9, "peak": peaks["hbm_gbs"],
                                   "unit": "GB/s", "frac": sim_bytes / sim_step_s / 1e9 / peaks["hbm_gbs"],
                                   "alu_achieved_tflops": sim_flops / sim_step_s / 1e12, "alu_peak_tflops": fp32_peak / 1e12,

@@ -291,8 +291,10 @@ int ebc_step(ebc_sim *sim, const int32_t *action_idx, const double *action, cons
              double *reward, uint8_t *done, uint8_t *event, double *dmin, double *dist_to_goal,
              void *stream);
 
-/* Fused convenience for the policy-free path (robot action given, e.g. the `linear`
- * robot of tests/test_collisions_simulation.py): ebc_orca + ebc_step in one launch. */
+/* Convenience for the policy-free path (robot action given, e.g. the `linear` robot of
+ * tests/test_collisions_simulation.py): ebc_orca + ebc_step in one call -- K1 for the episodes the step will touch,
+ * then K2, on the same stream (with ORCA obstacle half-planes: one block-per-episode launch that stages the
+ * episode's obstacle vertices in shared memory once for both). */
 int ebc_orca_step(ebc_sim *sim, const int32_t *action_idx, const double *action,
                   const uint8_t *active, double *reward, uint8_t *done, uint8_t *event,
                   double *dmin, double *dist_to_goal, void *stream);

@@ -25,17 +25,27 @@ for wl, N in (("cfg2", 4096), ("cfg2", 65536), ("cfg4", 65536), ("cfg3", 65536))
     shape, cfg = bench.workload(wl)
     sim = BatchedSim(cfg, N, shape.H, shape.Smax, shape.Rmax, 81, device="cuda:0")
     sim.set_actions(build_action_space(shape.robot_v_pref, cfg.robot_kinematics))
-    synth.load(sim, synth.generate(shape, np.arange(min(N, 8192))))
-    if N > 8192:      # tile the first 8192 scenes over the batch
-        for k in ("hum_pv", "hum_gr", "hum_type", "hum_count", "stat", "stat_count", "rect", "rect_count", "rob_pv", "rob_gr", "rob_theta"):
-            t = getattr(sim, k)
-            t[8192:] = t[:8192].repeat((N // 8192 - 1,) + (1,) * (t.dim() - 1))
+    scenes = synth.generate(shape, np.arange(min(N, 8192)))
     zero = torch.zeros(N, dtype=torch.int32, device="cuda:0")
-    for _ in range(10):      # a few steps into the crossing: the LPs have real work
-        sim.step(action_idx=zero, fused_orca=True)
-    ms_f = timed(lambda: sim.step(action_idx=zero, fused_orca=True), 20)
-    ms_o = timed(sim.orca, 20)
+
+    def prep():
+        """The same state before every measurement: fresh scenes, ten steps into the crossing (the LPs have real work)."""
+        synth.load(sim, scenes)
+        if N > 8192:      # tile the first 8192 scenes over the batch
+            for k in ("hum_pv", "hum_gr", "hum_type", "hum_count", "stat", "stat_count", "rect", "rect_count", "rob_pv", "rob_gr", "rob_theta", "time"):
+                t = getattr(sim, k)
+                t[8192:] = t[:8192].repeat((N // 8192 - 1,) + (1,) * (t.dim() - 1))
+        for _ in range(10):
+            sim.step(action_idx=zero, fused_orca=True)
+        torch.cuda.synchronize()
+
     H = shape.H
-    print("%s N=%6d H=%2d: fused K1+K2 %.4f ms = %.3e agent-steps/s (%.1f GB/s algorithmic); K1 alone %.4f ms = %.3e human-steps/s" % (
-        wl, N, H, ms_f, N * (H + 1) / ms_f * 1e3, N * (48 * H + 90) / ms_f / 1e6, ms_o, N * H / ms_o * 1e3))
+    prep(); ms_f = timed(lambda: sim.step(action_idx=zero, fused_orca=True), 10)
+    prep(); ms_u = timed(lambda: (sim.orca(), sim.step(action_idx=zero)), 10)        # K1 then K2, two launches
+    prep(); ms_o = timed(sim.orca, 10)
+    prep(); sim.orca(); ms_s = timed(lambda: sim.step(action_idx=zero), 10)          # K2 alone (hum_nv from one K1)
+    print("%s N=%6d H=%2d: fused K1+K2 %.4f ms = %.3e agent-steps/s (%.1f GB/s algorithmic); two launches %.4f ms = %.3e agent-steps/s; "
+          "K1 alone %.4f ms = %.3e human-steps/s; K2 alone %.4f ms" % (
+              wl, N, H, ms_f, N * (H + 1) / ms_f * 1e3, N * (48 * H + 90) / ms_f / 1e6, ms_u, N * (H + 1) / ms_u * 1e3,
+              ms_o, N * H / ms_o * 1e3, ms_s))
     del sim
