@@ -43,9 +43,16 @@ struct TcSched {         // one entry of the MMA warp's per-tile schedule
   uint8_t commit_acc;    // then tell the crew that every MMA issued so far has completed
 };
 
+struct TcIssue {         // a schedule entry flattened for the MMA warp: everything it needs at constant parameter offsets
+  int np, ksteps, acc_col, accumulate, commit_k, commit_acc;
+  uint32_t idesc;        // tcgen05 instruction descriptor (M = 128, N = np, operand format of the splitting mode)
+  int pad;
+};
+
 struct TcProgram {
   TcStage st[ST_COUNT];
   TcSched sched[12];
+  TcIssue issue[12];     // issue[i] = the stage of sched[i] as the MMA warp sees it (filled by ebc_tc_prepare)
   int n_sched;
   int n_wide;                    // 1 or 2 halves of the wide first layer
   const uint8_t *wpack;          // packed bf16 weight slabs (device)

@@ -119,6 +119,7 @@ struct Pipe {
   uint32_t f_phase;          // crew: expected parity of every afree barrier, one bit each
   long long *trace;          // optional clock64() trace of CTA 0's crew thread 0 (EBC_TC_TRACE=1)
   int trace_pos;
+  bool fine;                 // EBC_TC_TRACE=3: the MMA warp stamps EVERY k-step it issues ((clock << 16) | schedule entry << 8 | k-step)
   __device__ __forceinline__ void stamp() {
     if (trace && threadIdx.x == 0 && blockIdx.x == 0 && trace_pos < 2048) trace[trace_pos++] = clock64();
   }
@@ -204,7 +205,7 @@ struct Pipe {
   // chase:    the crew is still writing the A operand; k-step ks is issued as soon as its two k-chunks (one
   //           16-column block of the previous stage's epilogue) have been stored and fenced by all 128 rows
   // commit_k: signal afree[ks] when the MMAs issued up to and including k-step ks have completed
-  __device__ void mma_stage(const TcStage &S, uint32_t a_smem, uint32_t tmem_base, bool commit_k) {
+  __device__ void mma_stage(const TcStage &S, uint32_t a_smem, uint32_t tmem_base, bool commit_k, int tag) {
     constexpr uint32_t ST = Cfg<NSPLIT>::STAGES;
     const uint32_t idesc = make_idesc_f16(TILE_M, S.np, Fmt<NSPLIT>::IDESC);
     const uint32_t d = tmem_base + S.acc_col;
@@ -230,13 +231,15 @@ struct Pipe {
           if (++idle > (1u << 26)) __trap();   // bounded: a protocol bug traps instead of hanging
         }
         tc_fence_after();
-        if (trace && leader && blockIdx.x == 0 && trace_pos < 900)   // diagnostics: (clock, cleared k-steps)
+        if (trace && !fine && leader && blockIdx.x == 0 && trace_pos < 900)   // diagnostics: (clock, cleared k-steps)
           trace[2048 + trace_pos++] = (clock64() << 16) | (long long)((seen - base - (uint32_t)ks) & 0xFFFFu);
       }
       const uint32_t b_cur = b_base + slot * (Cfg<NSPLIT>::STAGE_BYTES / 16);
       __syncwarp();      // converged: every lane runs the issue block, one elected lane's instructions take effect
       umma_kstep<NSPLIT>(d, a_cur, b_cur, Cfg<NSPLIT>::A_IMAGE / 16, np * 2, idesc, acc, empty0 + slot * 8,
                          afree0 + (uint32_t)ks * 8, commit_k);
+      if (fine && leader && blockIdx.x == 0 && trace_pos < 2040)
+        trace[2048 + trace_pos++] = (clock64() << 16) | (long long)((tag << 8) | ks);
       acc = true;
       a_cur += 2 * A_CHUNK_BYTES / 16;
       slot = slot + 1 == ST ? 0 : slot + 1;
@@ -249,7 +252,7 @@ struct Pipe {
     mbar_wait(a_bar, a_phase);          // sleep until the tile's input is staged (the scout clears it right after)
     a_phase ^= 1u;
     for (int i = 0; i < P.n_sched; ++i) {
-      mma_stage(P.st[P.sched[i].stage], a_smem, tmem_base, P.sched[i].commit_k != 0);
+      mma_stage(P.st[P.sched[i].stage], a_smem, tmem_base, P.sched[i].commit_k != 0, i);
       if (P.sched[i].commit_acc) {
         __syncwarp();
         umma_commit_elect(acc_bar);
@@ -509,7 +512,7 @@ __device__ __forceinline__ void pipe_init(Pipe<NSPLIT> &pipe, uint8_t *smem, con
   for (int i = threadIdx.x; i < P.n_slabs; i += blockDim.x) tab[i] = make_uint2(__ldg(P.slab_off + i), __ldg(P.slab_bytes + i));
   pipe.tab = tab;
   pipe.st = 0; pipe.leader = false; pipe.acc_phase = 0; pipe.a_phase = 0;
-  pipe.trace = nullptr; pipe.trace_pos = 0;
+  pipe.trace = nullptr; pipe.trace_pos = 0; pipe.fine = false;
   pipe.total = my_tiles * P.n_slabs;
   if (threadIdx.x == 0) {
     for (int i = 0; i < ST; ++i) { mbar_init(&pipe.full[i], 1); mbar_init(&pipe.empty[i], 1); }
@@ -518,6 +521,81 @@ __device__ __forceinline__ void pipe_init(Pipe<NSPLIT> &pipe, uint8_t *smem, con
     *pipe.ready = 0;
     for (int i = 0; i < NKB; ++i) { mbar_init(&pipe.kbar[i], TILE_M); mbar_init(&pipe.afree[i], 1); }
     fence_barrier_init();
+  }
+}
+
+// ---- the MMA warp ------------------------------------------------------------------------------------------
+// Everything this loop touches is WARP-UNIFORM BY CONSTRUCTION and visibly so to the compiler: shared-memory
+// addresses derived from the kernel's dynamic shared-memory symbol, stage fields read at constant offsets of the
+// kernel parameter block (the schedule loop is fully unrolled over P.issue[]), the TMEM base broadcast from lane 0.
+// ptxas then keeps the descriptors, the ring slot and the loop counters in UNIFORM registers and a k-step is ~35
+// uniform-datapath instructions around its three UTCHMMA and two UTCBAR.  The first version of this loop (Pipe::
+// mma_stage, values reached through generic pointers in a struct and dynamically indexed parameters) compiled to ~80
+// vector instructions per k-step, 21 of them R2UR moves -- and this warp shares its scheduler with four busy crew
+// warps, so the issue path, not the tensor pipe, set the floor: ~343 cycles per k-step whatever N (tools/trace_mma.py:
+// the N = 104 k-steps of mlp2.2 took as long as the N = 208 ones, whose three MMAs need 313 cycles of pipe).
+constexpr int MAX_SCHED = 12;
+template <int NSPLIT>
+__device__ __forceinline__ void mma_warp_main(const TcProgram &P, const uint8_t *smem, uint32_t tmem_base_lane,
+                                              long long my_tiles) {
+  constexpr uint32_t ST = Cfg<NSPLIT>::STAGES;
+  const Smem L = smem_layout<NSPLIT>();
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_lane, 0);
+  const uint32_t bars = sbase + L.bars;                       // same order as pipe_init
+  const uint32_t empty0 = bars + 8u * ST, acc_bar = bars + 16u * ST, a_bar = acc_bar + 8u;
+  const uint32_t afree0 = a_bar + 8u + 8u * NKB, ready = afree0 + 8u * NKB;
+  const uint32_t a_desc0 = (((sbase + L.a) >> 4) & 0x3FFFu) | ((uint32_t)(A_CHUNK_BYTES >> 4) << 16);
+  const uint32_t w_desc0 = ((sbase + L.w) >> 4) & 0x3FFFu;
+  uint32_t slot = 0, issued = 0, seen = 0, a_phase = 0;
+  for (long long t = 0; t < my_tiles; ++t) {
+    {   // sleep until the tile's input is staged (the scout clears it right after)
+      uint32_t spins = 0, ok = 0;
+      while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a_bar), "r"(a_phase) : "memory");
+        if (++spins > (1u << 22)) __trap();
+      }
+      a_phase ^= 1u;
+    }
+#pragma unroll
+    for (int i = 0; i < MAX_SCHED; ++i) {
+      if (i < P.n_sched) {
+        const TcIssue &E = P.issue[i];
+        const uint32_t d = tmem_base + (uint32_t)E.acc_col;
+        const uint32_t np = (uint32_t)E.np, idesc = E.idesc;
+        const uint32_t b_base = w_desc0 | (np << 16);
+        const bool commit_k = E.commit_k != 0;
+        const int ksteps = E.ksteps;
+        const uint32_t base = issued;             // schedule index of this entry's first k-step
+        uint32_t a_cur = a_desc0;
+        bool acc = E.accumulate != 0;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          if ((int)(seen - base) <= ks) {
+            // the scout sleeps on the barriers; this warp only watches its count (a shared-memory load per trip)
+            uint32_t idle = 0;
+            do {
+              asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(seen) : "r"(ready) : "memory");
+              if (++idle > (1u << 26)) __trap();   // bounded: a protocol bug traps instead of hanging
+            } while ((int)(seen - base) <= ks);
+            tc_fence_after();
+          }
+          umma_kstep<NSPLIT>(d, a_cur, b_base + slot * (Cfg<NSPLIT>::STAGE_BYTES / 16), Cfg<NSPLIT>::A_IMAGE / 16, np * 2, idesc,
+                             acc, empty0 + slot * 8u, afree0 + (uint32_t)ks * 8u, commit_k);
+          acc = true;
+          a_cur += 2 * A_CHUNK_BYTES / 16;
+          slot = slot + 1 == ST ? 0 : slot + 1;
+        }
+        issued = base + (uint32_t)ksteps;
+        if (E.commit_acc) {
+          asm volatile(
+              "{\n\t.reg .pred q;\n\t"
+              "elect.sync _|q, 0xffffffff;\n\t"
+              "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+              ::"r"(acc_bar) : "memory");
+        }
+      }
+    }
   }
 }
 
@@ -533,6 +611,7 @@ struct TcEntityParams {
   int jch;         // k-chunks of a joint row: (jd + 7) / 8
   int self_dim;
   long long *trace;
+  int trace_fine;
 };
 
 template <int NSPLIT>
@@ -548,9 +627,15 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
 
   Pipe<NSPLIT> pipe;
-  const long long n_tiles = (p.n_states + p.ts - 1) / p.ts;
-  pipe_init<NSPLIT>(pipe, smem, L, P, (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  // Tile counts in 32-bit unsigned arithmetic (launch_tc bounds n_states below 2^31).  Not a micro-optimisation: a
+  // 64-bit division by a run-time value compiles to a subroutine whose result ptxas no longer treats as warp-uniform,
+  // and with a "non-uniform" trip count every loop of the MMA warp fell back to vector registers + R2UR (see
+  // mma_warp_main).
+  const long long n_tiles = (long long)(((uint32_t)p.n_states + (uint32_t)p.ts - 1u) / (uint32_t)p.ts);
+  const long long my_tiles = (long long)(((uint32_t)n_tiles - blockIdx.x + gridDim.x - 1u) / gridDim.x);   // grid <= n_tiles
+  pipe_init<NSPLIT>(pipe, smem, L, P, my_tiles);
   pipe.trace = p.trace;
+  pipe.fine = p.trace != nullptr && p.trace_fine != 0;
   if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -563,10 +648,14 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
     // schedule (built on the host, P.sched): mlp1.0 halves | commit #1 | mlp1.2 K chunks chasing the wide-half
     // epilogues | commit #2 | mlp2.0 chasing the H1 epilogue, attention.0 local (H1 complete), attention.0 global
     // chasing the G operand | commit #3 | mlp2.2 chasing the T2 epilogue, attention.2 chasing the U epilogue | commit #4
-    pipe.leader = elect_one();
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) pipe.mma_tile(P, a_smem, tmem_base);
+    if (p.trace == nullptr) {
+      mma_warp_main<NSPLIT>(P, smem, tmem_slot, my_tiles);
+    } else {          // EBC_TC_TRACE: the instrumented (slower) form of the same loop
+      pipe.leader = elect_one();
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) pipe.mma_tile(P, a_smem, tmem_base);
+    }
   } else if (warp == NCREW / 32 + 1) {
-    pipe.scout_loop(P, (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    pipe.scout_loop(P, my_tiles);
   } else if (warp >= NCREW / 32 + 2) {
     if ((tid & 31) == 0) pipe.loader_loop(warp - (NCREW / 32 + 2));
   } else {
@@ -946,8 +1035,9 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
   const TcProgram &P = p.prog;
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   Pipe<NSPLIT> pipe;
-  const long long n_tiles = (p.n_states + TILE_M - 1) / TILE_M;
-  pipe_init<NSPLIT>(pipe, smem, L, P, (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  const long long n_tiles = (long long)(((uint32_t)p.n_states + (uint32_t)TILE_M - 1u) / (uint32_t)TILE_M);
+  const long long my_tiles = (long long)(((uint32_t)n_tiles - blockIdx.x + gridDim.x - 1u) / gridDim.x);   // grid <= n_tiles
+  pipe_init<NSPLIT>(pipe, smem, L, P, my_tiles);
   pipe.trace = p.trace;
   if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
   tc_fence_before();
@@ -957,10 +1047,14 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
   const uint32_t a_smem = smem_u32(A);
 
   if (warp == NCREW / 32) {
-    pipe.leader = elect_one();
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) pipe.mma_tile(P, a_smem, tmem_base);
+    if (p.trace == nullptr) {
+      mma_warp_main<NSPLIT>(P, smem, tmem_slot, my_tiles);
+    } else {          // EBC_TC_TRACE: the instrumented (slower) form of the same loop
+      pipe.leader = elect_one();
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) pipe.mma_tile(P, a_smem, tmem_base);
+    }
   } else if (warp == NCREW / 32 + 1) {
-    pipe.scout_loop(P, (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    pipe.scout_loop(P, my_tiles);
   } else if (warp >= NCREW / 32 + 2) {
     if ((tid & 31) == 0) pipe.loader_loop(warp - (NCREW / 32 + 2));
   } else {
@@ -1121,6 +1215,7 @@ struct Packer {
 template <int NSPLIT>
 int launch_tc(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row_count, float *values, cudaStream_t stream) {
   if (n_states <= 0) return EBC_OK;     // an empty batch launches nothing (like the FFMA path)
+  if (n_states >= (1ll << 31) - 256) return ebc_fail(s, EBC_ERR_INVALID, "tensor-core value path: at most 2^31 - 256 states per call");
   const Smem L = smem_layout<NSPLIT>();
   if ((int)L.total > s->max_smem_optin)
     return ebc_fail(s, EBC_ERR_INVALID, "tensor-core value path needs %u B of shared memory", L.total);
@@ -1143,13 +1238,14 @@ int launch_tc(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row
   p.ts = ts;
   p.joint = s->d_joint; p.jd = s->net.self_dim + s->net.l[3].out; p.self_dim = s->net.self_dim;
   p.jch = (p.jd + 7) / 8;
-  p.trace = nullptr;
+  p.trace = nullptr; p.trace_fine = 0;
   TcMlp3Params q;
   q.trace = nullptr;
   if (const char *tr = getenv("EBC_TC_TRACE")) {      // 1: the entity kernel, 2: the mlp3 kernel
     if (!s->d_trace) { cudaMalloc(&s->d_trace, 4096 * sizeof(long long)); }
     cudaMemsetAsync(s->d_trace, 0, 4096 * sizeof(long long), stream);
     if (tr[0] == '2') q.trace = s->d_trace; else p.trace = s->d_trace;
+    p.trace_fine = tr[0] == '3';
   }
   q.prog = s->tc[NSPLIT - 1].mlp3;
   q.joint = s->d_joint; q.values = values; q.n_states = n_states; q.jd = p.jd; q.jch = p.jch;
@@ -1301,6 +1397,17 @@ int ebc_tc_prepare(ebc_sim *s, const ebc_weights *w, int mode_index, int nsplit)
   const size_t bm2 = push_f(p4->bias, p4->out_dim, M.st[ST_L2].np);
   const size_t wm6 = push_f(p6->weight, p6->in_dim, M.st[ST_L2].np);
 
+  // the schedule as the MMA warp reads it: one flat record per entry, instruction descriptor precomputed
+  for (TcProgram *Q : {&E, &M})
+    for (int i = 0; i < Q->n_sched; ++i) {
+      const TcStage &S = Q->st[Q->sched[i].stage];
+      TcIssue &I = Q->issue[i];
+      I.np = S.np; I.ksteps = S.ksteps; I.acc_col = S.acc_col; I.accumulate = S.accumulate;
+      I.commit_k = Q->sched[i].commit_k; I.commit_acc = Q->sched[i].commit_acc;
+      const uint32_t fmt = nsplit == 2 ? 0u : 1u;           // fp16 parts in the two-part mode, bf16 otherwise
+      I.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(S.np >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+      I.pad = 0;
+    }
   // ---- upload ---------------------------------------------------------------------------------------
   const size_t n_e = pe.slab_off.size(), n_m = pm.slab_off.size();
   if (n_e > (size_t)MAX_SLABS || n_m > (size_t)MAX_SLABS) return 1;
