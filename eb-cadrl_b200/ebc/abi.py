@@ -118,7 +118,8 @@ PROTOTYPES = {
     "ebc_launch_count": (ctypes.c_int64, [SIM]),
 }
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib", "libebcadrl.so")
+LIB_PATH = os.environ.get("EBCADRL_LIB") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib",
+                                                        "libebcadrl.so")     # EBCADRL_LIB: another build of the same ABI
 
 
 class EbcError(RuntimeError):

@@ -19,6 +19,13 @@ for wl in cfg2 cfg3 cfg4; do
       -o $O/g_ncu_k4_$wl -f python tools/k4_only.py tc_fp16x2 3 > $O/g_ncu_k4_$wl.log 2>&1
 done
 timeout 300 python tools/sim_kernels.py > $O/g_sim_kernels.txt 2>&1 &&
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"orca_step|lookahead_group" -c 4 \
-      -o $O/g_ncu_sim -f python tools/sim_kernels.py > $O/g_ncu_sim.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"lookahead_group" -s 2 -c 1 \
+      -o $O/g_ncu_sim -f python tools/sim_kernels.py > $O/g_ncu_sim.log 2>&1 &&
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"orca_kernel|step_kernel" -s 4 -c 2 \
+      -o $O/g_ncu_k1k2 -f python tools/sim_kernels.py > $O/g_ncu_k1k2.log 2>&1
+timeout 600 python tools/sim_only.py > $O/g_sim_only.txt 2>&1
+for wl in cfg2 cfg3 cfg4; do
+  WORKLOAD=$wl timeout 300 python tools/trace_tc.py tc_fp16x2 > $O/g_trace_$wl.txt 2>&1
+  WORKLOAD=$wl timeout 300 python tools/trace_mma.py tc_fp16x2 > $O/g_trace_mma_$wl.txt 2>&1
+done
 ls -la $O > $O/g_ls.txt
