@@ -337,9 +337,6 @@ __device__ __forceinline__ void epi_to_a(Pipe<NSPLIT> &pipe, uint32_t tmem_row, 
     pipe.wait_free(cg < n_free ? cg : 0);
     tc_fence_after();
   }
-#ifdef EBC_STAGGER_NS
-  if (cg > 0) __nanosleep(EBC_STAGGER_NS * cg);     // experiment: block 0 first, the other column groups a little later
-#endif
   for (int c = 16 * cg; c < ncols; c += 16 * NCG) {
     float v[16];
     tmem_ld16(tmem_row + col0 + c, v);
