@@ -45,7 +45,7 @@ import torch  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the committed
 # `ncu --set full` capture (profiles/); None until a capture of that mode exists
-ROOFLINE_TRAFFIC = {"fp32": 492.2e6, "tc_fp32": 490.3e6, "tc_fp16x2": 499.7e6, "tc_bf16": None}
+ROOFLINE_TRAFFIC = {"fp32": 492.2e6, "tc_fp32": 490.3e6, "tc_fp16x2": 502.0e6, "tc_bf16": None}
 EPISODES_PER_GPU = 4096
 N_ACTIONS = 81
 METRIC = "agent_steps_per_sec"
