@@ -35,3 +35,18 @@ zero = torch.zeros(N, dtype=torch.int32, device="cuda:0")
 ms = timed(lambda: big.step(action_idx=zero, fused_orca=True), 10)
 print("K1+K2 fused ORCA + step, %d episodes: %.3f ms = %.3e agent-steps/s, %.1f GB/s algorithmic (48 H + 90 B per episode-step)" % (
     N, ms, N * (shape.H + 1) / ms * 1e3, N * (48 * shape.H + 90) / ms / 1e6))
+# angular local map: 3 wall quadrilaterals per episode, 48 sectors
+del big
+for N in (4096, 65536):
+    sim = make(N, False)
+    rng = np.random.default_rng(1)
+    c = rng.uniform(-3.5, 3.5, (N, 3, 2)); hw = np.stack([np.full((N, 3), 1.5), np.full((N, 3), 0.5)], -1)
+    xy = np.zeros((N, 3, 4, 2))
+    for k, (sx, sy) in enumerate(((1, 1), (-1, 1), (-1, -1), (1, -1))):
+        xy[:, :, k, 0] = c[..., 0] + sx * hw[..., 0]; xy[:, :, k, 1] = c[..., 1] + sy * hw[..., 1]
+    xy_d = torch.tensor(xy, device="cuda:0"); cnt = torch.full((N,), 3, dtype=torch.int32, device="cuda:0")
+    out = torch.empty(N, 48, dtype=torch.float64, device="cuda:0")
+    ms = timed(lambda: sim.local_map_angular(xy_d, cnt, 3.0, -np.pi, np.pi, 48, out=out), 10)
+    print("angular local map, %d episodes x 3 obstacles x 48 sectors: %.4f ms = %.3e maps/s (%.1f us per 1000 episodes)" % (
+        N, ms, N / ms * 1e3, ms * 1e3 / N * 1000))
+    del sim
