@@ -45,7 +45,8 @@ import torch  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the committed
 # `ncu --set full` capture (profiles/); None until a capture of that mode exists
-ROOFLINE_TRAFFIC = {"fp32": 492.2e6, "tc_fp32": 490.3e6, "tc_fp16x2": 502.0e6, "tc_bf16": None}
+ROOFLINE_TRAFFIC = {"fp32": 492.2e6, "tc_fp32": 490.3e6, "tc_fp16x2": 502.0e6, "tc_bf16": None}       # materialised input
+ROOFLINE_TRAFFIC_FUSED = {"tc_fp16x2": 115.8e6}                                                            # fused input path
 EPISODES_PER_GPU = 4096
 N_ACTIONS = 81
 METRIC = "agent_steps_per_sec"
@@ -371,6 +372,8 @@ def main():
     ap.add_argument("--train-batches", type=int, default=None, help="cfg5: SGD steps per iteration (default: the config's 800)")
     ap.add_argument("--profile", action="store_true", help="cfg5: cProfile of one untimed iteration to stderr")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--materialize-input", action="store_true",
+                    help="write the value-network input to HBM (K3) and read it back (K4) instead of the fused input path")
     ap.add_argument("--sustained-seconds", type=float, default=2.0,
                     help="length of the extra back-to-back region reported under `sustained` (0 = skip)")
     ap.add_argument("--value-mode", default="tc_fp16x2", choices=["fp32", "tc_fp32", "tc_fp16x2", "tc_bf16"],
@@ -409,6 +412,9 @@ def main():
     sim = env.sim
     n_rows = shape.H + shape.Smax
     H = shape.H
+    fused = sim.fused_input and not args.materialize_input
+    jd_pad = (6 + int(np.asarray(weights["mlp2.2.weight"]).shape[0]) + 7) // 8 * 8
+    joint_mb = (N * N_ACTIONS + 127) // 128 * 128 * jd_pad * 4 / 1e6
 
     def one_step(marks=None):
         def mark():
@@ -417,8 +423,12 @@ def main():
                 e.record()
                 marks.append(e)
         mark(); sim.orca()
-        mark(); sim.lookahead()
-        mark(); sim.value()
+        if fused:       # K3 leaves 48 B per (episode, action), K4 builds the rotated rows itself: no N*A*n*D buffer
+            mark(); sim.lookahead(build_inputs=False)
+            mark(); sim.value(fused=True)
+        else:
+            mark(); sim.lookahead()
+            mark(); sim.value()
         mark(); sim.select()
         mark(); sim.step(action_idx=sim.argmax)
         mark(); env.reset_done()
@@ -599,8 +609,13 @@ def main():
                                        "path alone, which is what north_star's 1e8 agent-steps/s is stated on",
                    "rows_per_state": n_rows, "D": cfg.D, "actions": N_ACTIONS, "weights": wsrc,
                    "parallelism": "episodes sharded over %d GPU(s), no data-path collective" % world,
-                   "l2": "per-step working set %.0f MB (value-net input) exceeds the 126 MB L2; "
-                         "sim_only flushes L2 between iterations" % (N * N_ACTIONS * n_rows * cfg.D * 4 / 1e6)},
+                   "input_path": ("fused: K3 leaves 48 B per (episode, action), K4's crew builds the rotated joint-state rows "
+                                  "from the state; the %.0f MB N*A*n*D input is never written" % (N * N_ACTIONS * n_rows * cfg.D * 4 / 1e6))
+                   if fused else "materialised: K3 writes N*A*n*D floats, K4 reads them",
+                   "l2": "per-step working set %.0f MB (%s) exceeds the 126 MB L2; sim_only flushes L2 between iterations" % (
+                       (joint_mb + 48e-6 * N * N_ACTIONS) if fused else N * N_ACTIONS * n_rows * cfg.D * 4 / 1e6 + joint_mb,
+                       "pooled per-state features written by the entity kernel and read by mlp3, + the lookahead records" if fused
+                       else "value-net input + pooled features")},
         "lookahead_evals_per_sec": total_eps * N_ACTIONS / step_s,
         "phase_ms_per_step": {k: v / args.steps for k, v in phase_ms.items()},
         "gpu_launches": launches,
@@ -613,7 +628,7 @@ def main():
                                 "tc_bf16": "K4 value network: tc_entity_kernel<1> + tc_mlp3_kernel<1> (tcgen05, bf16 operands)"
                                 }[args.value_mode],
                      "bound": "tensor", "achieved": achieved_tf, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
-                     "frac": achieved_tf / peaks["tensor_tflops"], "traffic": ROOFLINE_TRAFFIC.get(args.value_mode) if args.workload == "cfg2" and N == 4096 else None,
+                     "frac": achieved_tf / peaks["tensor_tflops"], "traffic": (ROOFLINE_TRAFFIC_FUSED if fused else ROOFLINE_TRAFFIC).get(args.value_mode) if args.workload == "cfg2" and N == 4096 else None,
                      "peak_source": peaks["source"],
                      "mma_issue_factor": {"fp32": 0, "tc_fp32": 6, "tc_fp16x2": 3, "tc_bf16": 1}[args.value_mode],
                      "note": "achieved = algorithmic FLOPs 2*(n*M_e+M_s) per (episode, action) / K4 time from CUDA events "

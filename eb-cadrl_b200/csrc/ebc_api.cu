@@ -73,6 +73,7 @@ void ebc_destroy(ebc_sim *s) {
   if (!s) return;
   cudaSetDevice(s->device);
   if (s->d_actions) cudaFree(s->d_actions);
+  if (s->d_la_rec) cudaFree(s->d_la_rec);
   ebc_value_release(s);
   ebc_tc_release(s);
   delete s;
@@ -146,6 +147,11 @@ int ebc_set_weights(ebc_sim *s, const ebc_weights *w) {
   const int64_t want = (int64_t)s->cfg.n_episodes * s->cfg.n_actions;
   const int64_t keep = s->joint_cap > want ? s->joint_cap : want;   // (the row width may have changed with the network)
   if ((rc = reserve_states(s, keep)) != 0) return rc;
+  if (!s->d_la_rec) {      // 48 bytes per (episode, action): the robot part of the rotated rows (fused input path)
+    const cudaError_t err = cudaMalloc(&s->d_la_rec, sizeof(float4) * 3 * (size_t)want);
+    if (err != cudaSuccess) return ebc_fail(s, EBC_ERR_NOMEM, "cudaMalloc lookahead records: %s", cudaGetErrorString(err));
+    s->la_rec_valid = 0;
+  }
   // tensor-core programs: [0] bf16, [1] fp16x2 (default), [2] bf16x3
   const int r0 = ebc_tc_prepare(s, w, 0, 1), r1 = ebc_tc_prepare(s, w, 1, 2), r2 = ebc_tc_prepare(s, w, 2, 3);
   if (r0 < 0) return r0;
@@ -207,8 +213,17 @@ int ebc_lookahead(ebc_sim *s, float *vin, double *reward, uint8_t *done, uint8_t
 int ebc_value(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row_count, float *values, void *stream) {
   if (!s) return EBC_ERR_INVALID;
   if (!s->have_weights) return ebc_fail(s, EBC_ERR_UNBOUND, "ebc_value: weights not set");
-  if (n_states < 0 || (n_states > 0 && (!vin || !values))) return ebc_fail(s, EBC_ERR_INVALID, "ebc_value: bad argument");
+  if (n_states < 0 || (n_states > 0 && !values)) return ebc_fail(s, EBC_ERR_INVALID, "ebc_value: bad argument");
   if (n_states == 0) return EBC_OK;      // an empty batch is valid and launches nothing
+  if (!vin) {
+    // fused input: K4 builds the rotated rows itself (bound state + the records of the last ebc_lookahead(vin = NULL))
+    if (row_count || !s->bound || n_states != (int64_t)s->cfg.n_episodes * s->cfg.n_actions)
+      return ebc_fail(s, EBC_ERR_INVALID, "ebc_value: vin == NULL is the lookahead batch (row_count NULL, n_states == n_episodes * n_actions)");
+    if (s->value_mode == EBC_VALUE_FP32 || !s->tc[ebc_tc_index(s->value_mode)].ready)
+      return ebc_fail(s, EBC_ERR_INVALID, "ebc_value: vin == NULL needs a tensor-core value mode (the FFMA cross-check reads vin)");
+    if (!s->d_la_rec || !s->la_rec_valid)
+      return ebc_fail(s, EBC_ERR_UNBOUND, "ebc_value: vin == NULL needs a preceding ebc_lookahead with vin == NULL on this state");
+  }
   if (n_states > s->joint_cap)
     return ebc_fail(s, EBC_ERR_UNBOUND, "ebc_value: %lld states exceed the reserved %lld (call ebc_reserve at setup time; "
                                         "ebc_value never allocates)", (long long)n_states, (long long)s->joint_cap);

@@ -82,6 +82,9 @@ struct ebc_sim {
   double *d_actions;     // [A*2]
   ValueNet net;
   float *d_weights;      // one slab
+  float4 *d_la_rec;      // [N * A * 3] robot part of the rotated rows per (episode, action), written by ebc_lookahead for
+                         // K4's fused input path (ebc_value with vin == NULL)
+  int la_rec_valid;      // the records belong to the current state (set by ebc_lookahead, consumed by ebc_value)
   float *d_joint;        // [cap_states * (self_dim + H2)] scratch for mlp3
   int64_t joint_cap;     // states ebc_value may be called with (ebc_reserve)
   size_t joint_floats;   // allocated floats of d_joint
@@ -126,5 +129,6 @@ int ebc_launch_value(ebc_sim *s, const float *vin, int64_t n_states, const int32
 // ebc_value_tc.cu
 int ebc_tc_prepare(ebc_sim *s, const ebc_weights *w, int mode_index, int nsplit);
 void ebc_tc_release(ebc_sim *s);
+// vin == NULL: the fused input path (rows built by the kernel from the bound state + s->d_la_rec)
 int ebc_launch_value_tc(ebc_sim *s, int mode, const float *vin, int64_t n_states, const int32_t *row_count,
                         float *values, cudaStream_t st);

@@ -1051,6 +1051,18 @@ __device__ __forceinline__ void rotate_row(const RobotRow &r, float px1, float p
   }
 }
 
+// The robot's part of rotate_row for one (episode, action), stored for K4's fused input path (ebc_value with vin ==
+// NULL builds the entity part of every row itself): {out0..3}, {out4, out5, px, py}, {cos, sin, 0, 0} -- the very
+// expressions of rotate_row above, so the fused rows equal the materialised ones bit for bit.
+__device__ __forceinline__ void store_robot_record(const RobotRow &r, int rotate_theta, float4 *rec) {
+  const float dx = r.gx - r.px, dy = r.gy - r.py;
+  const float rot = atan2f(r.gy - r.py, r.gx - r.px);
+  const float cr = cosf(rot), sr = sinf(rot);
+  rec[0] = make_float4(sqrtf(dx * dx + dy * dy), r.v_pref, rotate_theta ? r.theta - rot : 0.0f, r.radius);
+  rec[1] = make_float4(r.vx * cr + r.vy * sr, r.vy * cr - r.vx * sr, r.px, r.py);
+  rec[2] = make_float4(cr, sr, 0.0f, 0.0f);
+}
+
 // Build the n x D rows of one state into `tile` (this warp's shared-memory staging area), then
 // stream them out with coalesced stores.  next_state: humans advanced by their ORCA action
 // (agent.py:80-93) when true, current state (multi_human_rl.py:128-149) when false.
@@ -1089,7 +1101,7 @@ __device__ void build_rows_warp(const ebc_config &c, const ebc_state &st, int e,
 // K3
 __global__ void __launch_bounds__(EBC_THREADS)
 lookahead_kernel(const ebc_config c, const ebc_state st, const double *__restrict__ actions, float *vin,
-                 double *reward, uint8_t *done, uint8_t *event) {
+                 double *reward, uint8_t *done, uint8_t *event, float4 *rec) {
   extern __shared__ float tiles[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int A = c.n_actions;
@@ -1112,7 +1124,7 @@ lookahead_kernel(const ebc_config c, const ebc_state st, const double *__restric
     if (done) done[ea] = (uint8_t)o.done;
     if (event) event[ea] = (uint8_t)o.event;
   }
-  if (!vin) return;
+  if (!vin && !rec) return;
   // rl/policy/cadrl.py:118-165 propagate(robot) in fp64, narrowed like torch.Tensor([...])
   RobotRow rr;
   const double dt = c.time_step;
@@ -1132,7 +1144,8 @@ lookahead_kernel(const ebc_config c, const ebc_state st, const double *__restric
     rr.theta = (float)nth;
   }
   rr.radius = rg.w; rr.gx = rg.x; rr.gy = rg.y; rr.v_pref = rg.z;
-  build_rows_warp(c, st, e, lane, H, S, rr, true, tiles + (size_t)warp * n * D, vin + ea * (size_t)n * D);
+  if (rec && lane == 0) store_robot_record(rr, c.rotate_theta, rec + ea * 3);
+  if (vin) build_rows_warp(c, st, e, lane, H, S, rr, true, tiles + (size_t)warp * n * D, vin + ea * (size_t)n * D);
 }
 
 // K3 for episodes with at most G rows per state (G = 8 or 16): 32 / G (episode, action) pairs per warp, lane l of
@@ -1140,7 +1153,7 @@ lookahead_kernel(const ebc_config c, const ebc_state st, const double *__restric
 template <int G>
 __global__ void __launch_bounds__(EBC_THREADS)
 lookahead_group_kernel(const ebc_config c, const ebc_state st, const double *__restrict__ actions, float *vin,
-                       double *reward, uint8_t *done, uint8_t *event) {
+                       double *reward, uint8_t *done, uint8_t *event, float4 *rec) {
   extern __shared__ float tiles[];
   constexpr int GPW = 32 / G;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane / G, l = lane % G;
@@ -1166,7 +1179,7 @@ lookahead_group_kernel(const ebc_config c, const ebc_state st, const double *__r
     if (done) done[ea] = (uint8_t)o.done;
     if (event) event[ea] = (uint8_t)o.event;
   }
-  if (!vin) return;
+  if (!vin && !rec) return;
   RobotRow rr;
   const double dt = c.time_step;
   if (c.robot_kinematics == EBC_KIN_HOLONOMIC) {
@@ -1185,6 +1198,8 @@ lookahead_group_kernel(const ebc_config c, const ebc_state st, const double *__r
     rr.theta = (float)nth;
   }
   rr.radius = rg.w; rr.gx = rg.x; rr.gy = rg.y; rr.v_pref = rg.z;
+  if (rec && live && l == 0) store_robot_record(rr, c.rotate_theta, rec + ea * 3);
+  if (!vin) return;               // (warp-uniform: a kernel argument)
   // rows (n <= G): lane l builds row l in the group's tile, then the group copies it out contiguously
   float *tile = tiles + (size_t)(warp * GPW + sub) * n * D;
   if (l < n) {
@@ -1680,6 +1695,7 @@ generate_kernel(const ebc_config c, const ebc_state st, const ebc_scene_shape sh
 
 int ebc_launch_generate(ebc_sim *s, const ebc_scene_shape *shape, uint64_t seed, const int64_t *episode_ids,
                         const uint8_t *mask, cudaStream_t stream) {
+  s->la_rec_valid = 0;      // the state moves on: the lookahead records no longer describe it
   const int blocks = (s->cfg.n_episodes + 127) / 128;
   generate_kernel<<<blocks, 128, 0, stream>>>(s->cfg, s->st, *shape, (unsigned long long)seed,
                                               reinterpret_cast<const long long *>(episode_ids), mask);
@@ -1688,6 +1704,7 @@ int ebc_launch_generate(ebc_sim *s, const ebc_scene_shape *shape, uint64_t seed,
 
 int ebc_launch_reset(ebc_sim *s, const ebc_state *pool, int pool_size, const int32_t *pool_index,
                      const uint8_t *mask, cudaStream_t stream) {
+  s->la_rec_valid = 0;      // the state moves on: the lookahead records no longer describe it
   const int blocks = (s->cfg.n_episodes + EBC_WARPS_PER_BLOCK - 1) / EBC_WARPS_PER_BLOCK;
   reset_kernel<<<blocks, EBC_THREADS, 0, stream>>>(s->cfg, s->st, *pool, pool_size, pool_index, mask);
   return ebc_check_launch(s, "reset_kernel");
@@ -1748,12 +1765,16 @@ int ebc_launch_lookahead(ebc_sim *s, float *vin, double *reward, uint8_t *done, 
   const long long warps = (pairs + gpw - 1) / gpw;
   const int blocks = (int)((warps + EBC_WARPS_PER_BLOCK - 1) / EBC_WARPS_PER_BLOCK);
   const size_t smem = (size_t)EBC_WARPS_PER_BLOCK * gpw * n * D * sizeof(float);
+  // without a destination for the rows the kernel leaves the robot part of every (episode, action) in s->d_la_rec:
+  // K4's fused input path builds the rows from it (ebc_value with vin == NULL)
+  float4 *rec = vin ? nullptr : s->d_la_rec;
   if (group == 8 && n <= 8)
-    lookahead_group_kernel<8><<<blocks, EBC_THREADS, smem, stream>>>(s->cfg, s->st, s->d_actions, vin, reward, done, event);
+    lookahead_group_kernel<8><<<blocks, EBC_THREADS, smem, stream>>>(s->cfg, s->st, s->d_actions, vin, reward, done, event, rec);
   else if (group == 16 && n <= 16)
-    lookahead_group_kernel<16><<<blocks, EBC_THREADS, smem, stream>>>(s->cfg, s->st, s->d_actions, vin, reward, done, event);
+    lookahead_group_kernel<16><<<blocks, EBC_THREADS, smem, stream>>>(s->cfg, s->st, s->d_actions, vin, reward, done, event, rec);
   else
-    lookahead_kernel<<<blocks, EBC_THREADS, smem, stream>>>(s->cfg, s->st, s->d_actions, vin, reward, done, event);
+    lookahead_kernel<<<blocks, EBC_THREADS, smem, stream>>>(s->cfg, s->st, s->d_actions, vin, reward, done, event, rec);
+  s->la_rec_valid = rec != nullptr;
   return ebc_check_launch(s, "lookahead_kernel");
 }
 
@@ -1775,6 +1796,7 @@ int ebc_launch_select(ebc_sim *s, const double *reward, const float *values, dou
 int ebc_launch_step(ebc_sim *s, bool fused_orca, const int32_t *action_idx, const double *action,
                     const uint8_t *active, double *reward, uint8_t *done, uint8_t *event, double *dmin,
                     double *dist_to_goal, cudaStream_t stream) {
+  s->la_rec_valid = 0;      // the state moves on: the lookahead records no longer describe it
   ebc_stats sx = s->stats;                      // all-null when unbound
   if (!active && sx.alive) active = sx.alive;   // the bound alive[] is the mask (ebc_bind_stats)
   if (fused_orca && s->cfg.orca_obstacles) {

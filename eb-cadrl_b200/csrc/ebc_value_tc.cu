@@ -601,7 +601,15 @@ __device__ __forceinline__ void mma_warp_main(const TcProgram &P, const uint8_t 
 
 struct TcEntityParams {
   TcProgram prog;
-  const float *vin;
+  const float *vin;          // materialised rows, or NULL: the fused input path below
+  // fused input: the crew builds its k-chunk of every rotated row (rl/policy/cadrl.py:236-337) from the
+  // bound state and the robot record ebc_lookahead left per (episode, action); the n x D input never touches HBM
+  const float4 *rec;         // [n_states * 3]: {out0..3}, {out4, out5, robot px, py}, {cos, sin, -, -}
+  const float4 *hum_pv, *hum_gr, *stat;
+  const float2 *hum_nv;
+  const uint8_t *hum_type;
+  int Hmax, Smax;
+  double dt;
   const int32_t *row_count, *hum_count, *stat_count;
   int n_actions;
   long long n_states;
@@ -694,18 +702,73 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
     auto load_x = [&](long long t) {
       const long long t0 = t * ts;
       const int tstates = (int)min((long long)ts, p.n_states - t0);
-      const float *src = p.vin + ((size_t)(t0 + my_sid) * n + my_rin) * D;
+      if (p.vin) {
+        const float *src = p.vin + ((size_t)(t0 + my_sid) * n + my_rin) * D;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int k = 8 * cg + j;
-        xu[j] = k == one0 ? 1.0f : ((my_row && my_sid < tstates && k < D) ? __ldg(src + k) : 0.0f);
+        for (int j = 0; j < 8; ++j) {
+          const int k = 8 * cg + j;
+          xu[j] = k == one0 ? 1.0f : ((my_row && my_sid < tstates && k < D) ? __ldg(src + k) : 0.0f);
+        }
+      } else {
+        // Fused input: this thread's k-chunk of its rotated row, computed exactly like K3's rotate_row (separate
+        // roundings: the _rn intrinsics are never contracted), so that the values equal the materialised ones bit for bit.
+        float (&o)[8] = xu;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = 0.0f;
+        if (my_row && my_sid < tstates && cg < 3) {
+          const long long gs = t0 + my_sid;
+          const int e = (int)((uint32_t)gs / (uint32_t)p.n_actions);      // (n_states < 2^31: launch_tc)
+          // every load that does not depend on the entity counts is issued first, the human slot speculatively (always
+          // in bounds): one L2 round trip for a human row, two for a static disc, instead of three dependent ones
+          const int H = __ldg(p.hum_count + e), S = __ldg(p.stat_count + e);
+          const float4 *rc = p.rec + (size_t)gs * 3;
+          const float4 ra = __ldg(rc), rb = __ldg(rc + 1), rcs = __ldg(rc + 2);
+          const size_t h = (size_t)e * p.Hmax + min(my_rin, p.Hmax - 1);
+          const float4 pv = __ldg(p.hum_pv + h);
+          const float2 nv = __ldg(p.hum_nv + h);
+          const float hr = __ldg(p.hum_gr + h).w;
+          const int hty = __ldg(p.hum_type + h);
+          if (my_rin < H + S) {
+            float px1, py1, vx1 = 0.0f, vy1 = 0.0f, r1;
+            int ty = 3;                                    // EBC_ADULT_STATIC (env.py:457-458)
+            if (my_rin < H) {                              // the human advanced by its ORCA action (agent.py:80-93)
+              px1 = (float)__dadd_rn((double)pv.x, __dmul_rn((double)nv.x, p.dt));
+              py1 = (float)__dadd_rn((double)pv.y, __dmul_rn((double)nv.y, p.dt));
+              vx1 = nv.x; vy1 = nv.y;
+              r1 = hr;
+              ty = hty;
+            } else {
+              const float4 sd = __ldg(p.stat + (size_t)e * p.Smax + (my_rin - H));
+              px1 = sd.x; py1 = sd.y; r1 = sd.z;
+            }
+            if (cg == 0) {
+              const float ddx = __fsub_rn(px1, rb.z), ddy = __fsub_rn(py1, rb.w);
+              o[0] = ra.x; o[1] = ra.y; o[2] = ra.z; o[3] = ra.w; o[4] = rb.x; o[5] = rb.y;
+              o[6] = __fadd_rn(__fmul_rn(ddx, rcs.x), __fmul_rn(ddy, rcs.y));
+              o[7] = __fsub_rn(__fmul_rn(ddy, rcs.x), __fmul_rn(ddx, rcs.y));
+            } else if (cg == 1) {
+              const float ax = __fsub_rn(rb.z, px1), ay = __fsub_rn(rb.w, py1);
+              o[0] = __fadd_rn(__fmul_rn(vx1, rcs.x), __fmul_rn(vy1, rcs.y));
+              o[1] = __fsub_rn(__fmul_rn(vy1, rcs.x), __fmul_rn(vx1, rcs.y));
+              o[2] = r1;
+              o[3] = __fsqrt_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)));
+              o[4] = __fadd_rn(ra.w, r1);
+              if (D == 17) { o[5] = ty == 0 ? 1.0f : 0.0f; o[6] = ty == 1 ? 1.0f : 0.0f; o[7] = ty == 2 ? 1.0f : 0.0f; }
+            } else if (D == 17) {
+              o[0] = ty == 3 ? 1.0f : 0.0f;
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (8 * cg + j == one0) xu[j] = 1.0f;
       }
       if (tid < MAX_STATES) {
         int c = 0;
         if (tid < tstates) {
           if (p.row_count) c = __ldg(p.row_count + t0 + tid);
           else {
-            const long long e = (t0 + tid) / p.n_actions;
+            const int e = (int)((uint32_t)(t0 + tid) / (uint32_t)p.n_actions);
             c = __ldg(p.hum_count + e) + __ldg(p.stat_count + e);
           }
           c = min(max(c, 0), n);
@@ -1223,6 +1286,10 @@ int launch_tc(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row
   TcEntityParams p;
   p.prog = s->tc[NSPLIT - 1].entity;
   p.vin = vin; p.row_count = row_count; p.hum_count = s->st.hum_count; p.stat_count = s->st.stat_count;
+  p.rec = s->d_la_rec;
+  p.hum_pv = reinterpret_cast<const float4 *>(s->st.hum_pv); p.hum_gr = reinterpret_cast<const float4 *>(s->st.hum_gr);
+  p.stat = reinterpret_cast<const float4 *>(s->st.stat); p.hum_nv = reinterpret_cast<const float2 *>(s->st.hum_nv);
+  p.hum_type = s->st.hum_type; p.Hmax = s->cfg.max_humans; p.Smax = s->cfg.max_statics; p.dt = s->cfg.time_step;
   p.n_actions = s->cfg.n_actions; p.n_states = n_states; p.n = n; p.D = s->net.D;
   // states per 128-row tile: whole states per warp (n <= 32) or whole warps per state (see the kernel)
   int ts = n <= 32 ? 4 * (32 / n) : 4 / ((n + 31) / 32);

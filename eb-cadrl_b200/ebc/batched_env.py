@@ -135,6 +135,7 @@ class BatchedEnv(object):
         self.sim.set_weights(weights, with_global_state=with_global_state, self_state_dim=self_state_dim)
         if value_mode:
             self.sim.set_value_mode(value_mode)
+        self.sim.fused_input = self.sim.value_mode().startswith("tc")      # K4 builds its own input: no N*A*n*D buffer
         self._weights_version = 0
         self.target_value = None
         self._explore_gen = torch.Generator(device=self.device)
@@ -158,6 +159,7 @@ class BatchedEnv(object):
         self.sim.set_weights(sd, with_global_state=model.with_global_state, self_state_dim=model.self_state_dim)
         if getattr(self.policy, "value_mode", None):
             self.sim.set_value_mode(self.policy.value_mode)
+        self.sim.fused_input = self.sim.value_mode().startswith("tc")      # K4 builds its own input: no N*A*n*D buffer
         self._weights_version = getattr(self.policy, "weights_version", 0)
 
     # ---- env.reset x N ---------------------------------------------------------------------------------

@@ -102,6 +102,7 @@ class BatchedSim(object):
         self.obst_count = z(N, dtype=torch.int32)
         # per-decision buffers
         self.vin = None
+        self.fused_input = False      # decide(): K4 builds its own input (set by BatchedEnv when K4 runs on the tensor cores)
         self.la_reward = z(N, A, dtype=torch.float64)
         self.la_done = z(N, A, dtype=torch.uint8)
         self.la_event = z(N, A, dtype=torch.uint8)
@@ -269,7 +270,13 @@ class BatchedSim(object):
         self.be.call("lookahead", self.h, _ptr(self.vin if build_inputs else None), _ptr(self.la_reward),
                      _ptr(self.la_done), _ptr(self.la_event), stream=self._stream())
 
-    def value(self, vin=None, row_count=None, out=None):
+    def value(self, vin=None, row_count=None, out=None, fused=False):
+        """K4.  Default: the lookahead batch from `self.vin`.  `fused=True`: no materialised input at all -- the kernel
+        builds the rotated rows itself from the bound state and the robot records the preceding
+        `lookahead(build_inputs=False)` left (tensor-core modes).  `vin=...`: any batch of states."""
+        if fused:
+            self.be.call("value", self.h, None, ctypes.c_int64(self.N * self.A), None, _ptr(self.values), stream=self._stream())
+            return self.values
         if vin is None:
             vin, out, n_states = self.vin, self.values, self.N * self.A
         else:
@@ -288,11 +295,18 @@ class BatchedSim(object):
                      _ptr(self.argmax), _ptr(self.nan_flag), stream=self._stream())
         return self.argmax
 
-    def decide(self):
-        """One robot decision for every episode (rl/policy/multi_human_rl.py:12-87, test phase)."""
+    def decide(self, fused=None):
+        """One robot decision for every episode (rl/policy/multi_human_rl.py:12-87, test phase).  With `fused` (default:
+        `self.fused_input`) the value-network input is never written to memory: K3 leaves 48 bytes per (episode, action)
+        and K4 builds its rows from the state (bit-identical values; `self.vin` is then not updated)."""
+        fused = self.fused_input if fused is None else fused
         self.orca()
-        self.lookahead()
-        self.value()
+        if fused:
+            self.lookahead(build_inputs=False)
+            self.value(fused=True)
+        else:
+            self.lookahead()
+            self.value()
         return self.select()
 
     def step(self, action_idx=None, action=None, active=None, fused_orca=False):

@@ -257,7 +257,9 @@ int ebc_robot_orca(ebc_sim *sim, double safety_space, double *out_action, void *
  * done / event (utils/reward.py:80-181), next human states (agent.py:80-93), robot
  * propagate (rl/policy/cadrl.py:118-165) and the rotated joint state
  * (rl/policy/multi_human_rl.py:52-61 + cadrl.py:236-337).  Requires ebc_orca first.
- *   vin    [N*A*n*D] fp32 value-network input (NULL: skip the joint-state build)
+ *   vin    [N*A*n*D] fp32 value-network input, or NULL: the rows are not materialised -- the kernel leaves the robot
+ *          part of every (episode, action)'s rows (48 bytes) in the handle's scratch, from which ebc_value(vin = NULL)
+ *          builds them itself (the n x D input never touches HBM)
  *   reward [N*A] f64, done [N*A] u8, event [N*A] u8  (any may be NULL) */
 int ebc_lookahead(ebc_sim *sim, float *vin, double *reward, uint8_t *done, uint8_t *event,
                   void *stream);
@@ -269,7 +271,11 @@ int ebc_lookahead(ebc_sim *sim, float *vin, double *reward, uint8_t *done, uint8
  * episode i / A and takes that episode's bound hum_count + stat_count (anything else is EBC_ERR_INVALID).
  * For any other batch (replay samples, target-network evaluation) pass row_count explicitly.
  * n_states must not exceed what ebc_set_weights / ebc_reserve reserved (this call never allocates).
- * n_states == 0 is valid and launches nothing (pointers may then be NULL). */
+ * n_states == 0 is valid and launches nothing (pointers may then be NULL).
+ * vin == NULL (with row_count == NULL, n_states == N*A, a tensor-core value mode) is the FUSED input path: the kernel
+ * computes every rotated joint-state row (cadrl.py:236-337) from the bound state and the records of the preceding
+ * ebc_lookahead(vin = NULL) on the same state -- bit-identical values, no N*A*n*D buffer.  EBC_ERR_UNBOUND if no such
+ * lookahead preceded (or the state has been stepped / reset since), EBC_ERR_INVALID in the FFMA mode. */
 int ebc_value(ebc_sim *sim, const float *vin, int64_t n_states, const int32_t *row_count,
               float *values, void *stream);
 

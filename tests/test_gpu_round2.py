@@ -319,3 +319,47 @@ def test_half_warp_orca_is_bit_identical(oracle, H, S, R, dense, visible):
     for _ in range(4):
         r.step(action_idx=idx, fused_orca=True)
     assert np.array_equal(np_(out["16"][1]), r.hum_pv.numpy())
+
+
+@pytest.mark.parametrize("shape_name,N,kin,wname,typed", [
+    ("CFG2", 1024, "holonomic", "weights_ebcadrl.npz", True),        # 16 rows per state: the transpose-reduce path
+    ("CFG3", 2048, "unicycle", "weights_sarl_baseline.npz", False),  # 5 rows per state, D = 13, theta in the row
+    ("CFG4", 256, "holonomic", "weights_ebcadrl.npz", True),         # 50 rows per state: two warps per state
+])
+def test_fused_input_equals_materialised(shape_name, N, kin, wname, typed):
+    """with vin == NULL K4 builds the rotated joint-state rows itself (the crew computes its k-chunk
+    of every row from the state and the 48-byte robot record K3 leaves per (episode, action)).  Same arithmetic, same
+    roundings as K3's rotate_row: values, action values and argmax are BIT-IDENTICAL to the materialised path, on
+    ragged episodes (humans removed at random), a few steps into the crossing, in every tensor-core mode."""
+    shape = getattr(synth, shape_name)
+    cfg = random_cfg(kin, typed=typed)
+    cfg.map_size_m, cfg.map_resolution = shape.map_size_m, shape.map_resolution
+    sim = BatchedSim(cfg, N, shape.H, shape.Smax, shape.Rmax, 81, device="cuda:0")
+    sim.set_actions(build_action_space(shape.robot_v_pref, kin))
+    sim.set_weights(ob.load_weights(wname))
+    synth.load(sim, synth.generate(shape, np.arange(N)))
+    rng = np.random.default_rng(3)
+    sim.hum_count.copy_(torch.as_tensor(rng.integers(1, shape.H + 1, N).astype(np.int32)))       # ragged
+    if shape.Smax:
+        sim.stat_count.copy_(torch.as_tensor(rng.integers(0, shape.Smax + 1, N).astype(np.int32)))
+    zero = torch.zeros(N, dtype=torch.int32, device="cuda:0")
+    for _ in range(6):
+        sim.step(action_idx=zero, fused_orca=True)
+    for mode in ("tc_fp16x2", "tc_fp32", "tc_bf16"):
+        sim.set_value_mode(mode)
+        a = sim.decide(fused=False).clone()
+        v, av, ev = sim.values.clone(), sim.action_values.clone(), sim.la_event.clone()
+        sim.values.zero_()
+        b = sim.decide(fused=True).clone()
+        torch.cuda.synchronize()
+        assert torch.equal(sim.la_event, ev)
+        assert np.array_equal(np_(sim.values).view(np.uint32), np_(v).view(np.uint32)), mode
+        assert torch.equal(sim.action_values, av) and torch.equal(a, b), mode
+    # the fused call is refused where it cannot be honoured
+    sim.set_value_mode("fp32")
+    with pytest.raises(Exception):
+        sim.value(fused=True)
+    sim.set_value_mode("tc_fp16x2")
+    sim.step(action_idx=zero, fused_orca=True)          # the state moved on: the records are stale
+    with pytest.raises(Exception):
+        sim.value(fused=True)

@@ -16,10 +16,12 @@ sim.set_actions(build_action_space(shape.robot_v_pref, cfg.robot_kinematics)); s
 synth.load(sim, synth.generate(shape, np.arange(N)))
 sim.set_value_mode(sys.argv[1] if len(sys.argv) > 1 else "tc_fp16x2")
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 4
-sim.orca(); sim.lookahead()
+FUSED = os.environ.get("FUSED", "1") != "0"        # FUSED=0: the materialised input (K3 writes N*A*n*D floats, K4 reads them)
+sim.orca(); sim.lookahead(build_inputs=not FUSED)
+run = (lambda: sim.value(fused=True)) if FUSED else sim.value
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-sim.value(); torch.cuda.synchronize()
+run(); torch.cuda.synchronize()
 a.record()
-for _ in range(iters): sim.value()
+for _ in range(iters): run()
 b.record(); torch.cuda.synchronize()
-print("K4 %s %s N=%d: %.3f ms per call" % (WL, sim.value_mode(), N, a.elapsed_time(b) / iters))
+print("K4 %s %s N=%d %s input: %.3f ms per call" % (WL, sim.value_mode(), N, "fused" if FUSED else "materialised", a.elapsed_time(b) / iters))
