@@ -12,7 +12,9 @@
 //                              value into 16-bit parts and stores the next stage's A operand
 //   warp 16 (converged)        issues the tcgen05.mma's, one converged block per k-step (elect.sync inside):
 //                              A = activations in shared memory (canonical K-major layout written by the
-//                              previous epilogue), B = weight slab, D = fp32 accumulator in TMEM
+//                              previous epilogue), B = weight slab, D = fp32 accumulator in TMEM.  Its loop
+//                              (mma_warp_main) is written so that ptxas keeps it on the UNIFORM datapath
+//                              (~45 uniform instructions per k-step, no R2UR): see the comment there
 //   warp 17 (converged)        scout: polls the hand-over barriers and publishes how many k-steps may issue
 //   warps 18-19, one lane each stream the pre-packed weight slabs L2 -> shared memory with cp.async.bulk
 //                              (mbarrier full/empty ring), every other slab each
@@ -23,6 +25,8 @@
 // so the tensor pipe and the epilogue crew work on the same tile at the same time.  The global state of
 // sarl.py:51-60 is an extra K chunk of attention.0: the crew writes the per-state mean of H1 (replicated
 // over the state's rows) as an A operand and the tensor core multiplies it with the global half of the weights.
+// The input X is either read from the materialised value-network input (vin) or, with vin == NULL, computed by the
+// crew itself from the bound state and the 48-byte robot record K3 leaves per (episode, action) (fused input path).
 // See ebc_tc.cuh for the operand layout and the fp32-accurate operand splitting.
 #include <cuda_fp16.h>
 #include <stdio.h>
