@@ -310,6 +310,15 @@ int ebc_local_map_angular(ebc_sim *s, const ebc_angular_map *map, const double *
   return ebc_launch_angular_map(s, map, poly_xy, poly_count, out, (cudaStream_t)stream);
 }
 
+int ebc_local_map_grid(ebc_sim *s, const ebc_grid_map *map, uint8_t *out, void *stream) {
+  REQUIRE_BOUND("ebc_local_map_grid");
+  const int G = (int)rint(s->cfg.map_size_m / s->cfg.map_resolution);           // scene_generator.py:310-311
+  if (!map || !out || map->size < 1 || map->size > 192 || map->size > G ||
+      map->size != (int)rint(map->submap_size_m / s->cfg.map_resolution))
+    return ebc_fail(s, EBC_ERR_INVALID, "ebc_local_map_grid: bad argument (size = round(submap_size_m / map_resolution), 1..192, <= map cells)");
+  return ebc_launch_grid_map(s, map, out, (cudaStream_t)stream);
+}
+
 int ebc_debug_trace(ebc_sim *s, long long *out, int32_t n) {
   if (!s || !out || n < 1) return EBC_ERR_INVALID;
   if (!s->d_trace) return ebc_fail(s, EBC_ERR_UNBOUND, "ebc_debug_trace: run ebc_value with EBC_TC_TRACE=1 first");

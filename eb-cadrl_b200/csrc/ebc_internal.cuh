@@ -117,6 +117,7 @@ int ebc_launch_reset(ebc_sim *s, const ebc_state *pool, int pool_size, const int
 
 int ebc_launch_angular_map(ebc_sim *s, const ebc_angular_map *map, const double *poly_xy, const int32_t *poly_count,
                            double *out, cudaStream_t st);
+int ebc_launch_grid_map(ebc_sim *s, const ebc_grid_map *map, uint8_t *out, cudaStream_t st);
 int ebc_launch_generate(ebc_sim *s, const ebc_scene_shape *shape, uint64_t seed, const int64_t *episode_ids,
                         const uint8_t *mask, cudaStream_t st);
 

@@ -1534,6 +1534,108 @@ angular_map_kernel(const ebc_config c, const ebc_state st, const ebc_angular_map
   }
 }
 
+// ---- binary grid sub-map (simulator/env.py:630-708, [map] use_grid_map = true) ----------------------
+// Block per episode.  (1) thread 0: the reference's window / clip index arithmetic and the inverse rotation matrix of
+// cv2.getRotationMatrix2D + cv2.warpAffine in float64; (2) the first `size` threads: the per-column and per-row
+// fixed-point terms (OpenCV's adelta / bdelta / X0 / Y0, 1/1024 units, cvRound = rint); (3) the window of scene.map is
+// rasterised from the episode's zero-cell rectangles into shared memory, one byte per cell; (4) every thread takes
+// four consecutive output cells: sample position to 1/32 pixel, four taps from shared memory (constant border 1),
+// OpenCV's float weight table, threshold, one 32-bit store.  HBM traffic = the size x size bytes written per episode
+// + the rectangle list; everything else stays in shared memory.
+struct GridMapShared {
+  double m[6];
+  int sgx, sgy, egx, egy, six, siy, degenerate, pad;
+};
+
+__global__ void __launch_bounds__(256)
+grid_map_kernel(const ebc_config c, const ebc_state st, const int S, uint8_t *__restrict__ out) {
+  extern __shared__ __align__(16) uint8_t gm_smem[];
+  __shared__ GridMapShared sh;
+  const int e = blockIdx.x, tid = threadIdx.x;
+  const int cells = S * S;
+  uint8_t *grid = gm_smem;                                             // [S][S]
+  int *adelta = reinterpret_cast<int *>(gm_smem + ((cells + 15) & ~15));   // [S] each
+  int *bdelta = adelta + S, *x0s = bdelta + S, *y0s = x0s + S;
+  if (tid == 0) {
+    const float4 rp = reinterpret_cast<const float4 *>(st.rob_pv)[e];
+    const double px = (double)rp.x, py = (double)rp.y, theta = (double)st.rob_theta[e];
+    const int G = (int)rint(c.map_size_m / c.map_resolution);
+    const int cx = (int)rint((px + c.map_size_m / 2.0) / c.map_resolution);       // env.py:637-642
+    const int cy = (int)rint((py + c.map_size_m / 2.0) / c.map_resolution);
+    int six = (int)rint((double)cx - floor((double)S / 2.0));                       // env.py:645-648
+    int siy = (int)rint((double)cy - floor((double)S / 2.0));
+    int eix = six + S - 1, eiy = siy + S - 1;
+    const int max_idx = G - 1;
+    int sgx = 0, sgy = 0, egx = S - 1, egy = S - 1;
+    if (six < 0) { sgx = -six; six = 0; }                                            // env.py:660-672
+    else if (eix > max_idx) { egx = egx - (eix - max_idx); eix = max_idx; }
+    if (siy < 0) { sgy = -siy; siy = 0; }
+    else if (eiy > max_idx) { egy = egy - (eiy - max_idx); eiy = max_idx; }
+    sh.degenerate = (sgy > egy || siy > eiy || six > eix || sgx > egx) ? 1 : 0;      // env.py:674-680
+    sh.sgx = sgx; sh.sgy = sgy; sh.egx = egx; sh.egy = egy; sh.six = six; sh.siy = siy;
+    const double angle = (-theta + 3.141592653589793 / 2) * 180 / 3.141592653589793;   // env.py:686
+    const double a = angle * (3.141592653589793 / 180), alpha = cos(a), beta = sin(a), ctr = (double)S / 2.0;
+    double M[6] = {alpha, beta, (1 - alpha) * ctr - beta * ctr, -beta, alpha, beta * ctr + (1 - alpha) * ctr};
+    double D = M[0] * M[4] - M[1] * M[3];
+    D = D != 0 ? 1. / D : 0;
+    const double A11 = M[4] * D, A22 = M[0] * D;
+    M[0] = A11; M[1] *= -D; M[3] *= -D; M[4] = A22;
+    const double b1 = -M[0] * M[2] - M[1] * M[5], b2 = -M[3] * M[2] - M[4] * M[5];
+    M[2] = b1; M[5] = b2;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) sh.m[k] = M[k];
+  }
+  for (int i = tid; i < (cells + 3) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(grid)[i] = 0x01010101u;
+  __syncthreads();
+  if (sh.degenerate) {
+    for (int i = tid; i < cells; i += blockDim.x) out[(size_t)e * cells + i] = 1;
+    return;
+  }
+  for (int i = tid; i < S; i += blockDim.x) {
+    adelta[i] = (int)rint(sh.m[0] * i * 1024);
+    bdelta[i] = (int)rint(sh.m[3] * i * 1024);
+    x0s[i] = (int)rint((sh.m[1] * i + sh.m[2]) * 1024) + 16;
+    y0s[i] = (int)rint((sh.m[4] * i + sh.m[5]) * 1024) + 16;
+  }
+  {   // grid[sgx:egx, sgy:egy] = map[six:eix, siy:eiy]: the zero cells are the rectangles' cells (env.py:682-684)
+    const int R = c.max_rects ? min(st.rect_count[e], c.max_rects) : 0;
+    const short4 *rc = reinterpret_cast<const short4 *>(st.rect) + (size_t)e * c.max_rects;
+    for (int j = 0; j < R; ++j) {
+      const short4 r = rc[j];
+      const int i0 = max(sh.sgx, (int)r.x - sh.six + sh.sgx), i1 = min(sh.egx, (int)r.z - sh.six + sh.sgx);
+      const int j0 = max(sh.sgy, (int)r.y - sh.siy + sh.sgy), j1 = min(sh.egy, (int)r.w - sh.siy + sh.sgy);
+      const int w = j1 - j0, n = (i1 - i0) * w;
+      if (i1 <= i0 || w <= 0) continue;
+      for (int k = tid; k < n; k += blockDim.x) grid[(i0 + k / w) * S + j0 + k % w] = 0;
+    }
+  }
+  __syncthreads();
+  const bool packed = (cells & 3) == 0;
+  for (int q = tid; 4 * q < cells; q += blockDim.x) {
+    uint32_t word = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int idx = 4 * q + k;
+      if (idx >= cells) break;
+      const int y = idx / S, x = idx - y * S;
+      const int X = (x0s[y] + adelta[x]) >> 5, Y = (y0s[y] + bdelta[x]) >> 5;
+      const int sx = X >> 5, sy = Y >> 5, fx = X & 31, fy = Y & 31;
+      // initInterTab1D(INTER_LINEAR): {1 - f / 32, f / 32} in float; the 2-D table holds their float products
+      const float ax1 = (float)fx * (1.0f / 32), ay1 = (float)fy * (1.0f / 32), ax0 = 1.0f - ax1, ay0 = 1.0f - ay1;
+      const float w0 = ay0 * ax0, w1 = ay0 * ax1, w2 = ay1 * ax0, w3 = ay1 * ax1;
+      const bool r0 = sy >= 0 && sy < S, r1 = sy + 1 >= 0 && sy + 1 < S;
+      const bool c0 = sx >= 0 && sx < S, c1 = sx + 1 >= 0 && sx + 1 < S;
+      const double s0 = (r0 && c0) ? (double)grid[sy * S + sx] : 1.0, s1 = (r0 && c1) ? (double)grid[sy * S + sx + 1] : 1.0;
+      const double s2 = (r1 && c0) ? (double)grid[(sy + 1) * S + sx] : 1.0, s3 = (r1 && c1) ? (double)grid[(sy + 1) * S + sx + 1] : 1.0;
+      const double v = s0 * w0 + s1 * w1 + s2 * w2 + s3 * w3;
+      const uint32_t bit = v > 0.9 ? 1u : 0u;                                    // env.py:687-689
+      if (packed) word |= bit << (8 * k);
+      else out[(size_t)e * cells + idx] = (uint8_t)bit;
+    }
+    if (packed) reinterpret_cast<uint32_t *>(out + (size_t)e * cells)[q] = word;
+  }
+}
+
 // ---- scene generator: thread per episode, counter-based draws, fp64 in the host generator's
 //      operation order (this unit is compiled without FMA contraction), narrowed to fp32 at the end ----------
 __device__ __forceinline__ unsigned long long gen_mix(unsigned long long x) {
@@ -1819,6 +1921,13 @@ int ebc_launch_step(ebc_sim *s, bool fused_orca, const int32_t *action_idx, cons
   step_kernel<<<blocks, EBC_THREADS, 0, stream>>>(s->cfg, s->st, s->d_actions, action_idx, action, active, reward,
                                                   done, event, dmin, dist_to_goal, sx);
   return ebc_check_launch(s, "step_kernel");
+}
+
+int ebc_launch_grid_map(ebc_sim *s, const ebc_grid_map *map, uint8_t *out, cudaStream_t stream) {
+  const int S = map->size;
+  const size_t smem = (size_t)((S * S + 15) & ~15) + 4 * sizeof(int) * (size_t)S;
+  grid_map_kernel<<<s->cfg.n_episodes, 256, smem, stream>>>(s->cfg, s->st, S, out);
+  return ebc_check_launch(s, "grid_map_kernel");
 }
 
 int ebc_launch_angular_map(ebc_sim *s, const ebc_angular_map *map, const double *poly_xy, const int32_t *poly_count,

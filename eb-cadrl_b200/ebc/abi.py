@@ -89,6 +89,10 @@ class EbcAngularMap(ctypes.Structure):       # [map] section of the env config (
                 ("normalize", c_i32), ("max_polys", c_i32), ("reserved", c_i32)]
 
 
+class EbcGridMap(ctypes.Structure):          # [map] submap_size_m (simulator/env.py:81-82, :630-692)
+    _fields_ = [("submap_size_m", c_f64), ("size", c_i32), ("reserved", c_i32)]
+
+
 SIM = vp
 PROTOTYPES = {
     "ebc_create": (c_i32, [ctypes.POINTER(EbcConfig), c_i32, ctypes.POINTER(SIM)]),
@@ -114,6 +118,7 @@ PROTOTYPES = {
     "ebc_reset": (c_i32, [SIM, ctypes.POINTER(EbcState), c_i32, vp, vp, vp]),
     "ebc_generate": (c_i32, [SIM, ctypes.POINTER(EbcSceneShape), ctypes.c_uint64, vp, vp, vp]),
     "ebc_local_map_angular": (c_i32, [SIM, ctypes.POINTER(EbcAngularMap), vp, vp, vp, vp]),
+    "ebc_local_map_grid": (c_i32, [SIM, ctypes.POINTER(EbcGridMap), vp, vp]),
     "ebc_debug_trace": (c_i32, [SIM, vp, c_i32]),
     "ebc_launch_count": (ctypes.c_int64, [SIM]),
 }

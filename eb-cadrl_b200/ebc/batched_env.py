@@ -223,9 +223,12 @@ class BatchedEnv(object):
         return self.sim.reward, self.sim.done, self.sim.event
 
     def local_map_batch(self, normalize=True, out=None):
-        """`local_map` of env.reset / env.step for every episode (simulator/env.py:570-628, use_grid_map = false):
-        [N, angular_map_dim] float64 on the device, one launch (ebc_local_map_angular)."""
+        """`local_map` of env.reset / env.step for every episode, one launch: with [map] use_grid_map = false the
+        angular map (simulator/env.py:570-628, ebc_local_map_angular), [N, angular_map_dim] float64 on the device;
+        with use_grid_map = true the binary grid sub-map (env.py:630-708, ebc_local_map_grid), [N, size, size] uint8."""
         c = self.config
+        if c.getboolean("map", "use_grid_map"):
+            return self.sim.local_map_grid(c.getfloat("map", "submap_size_m"), out=out)
         return self.sim.local_map_angular(self.poly_xy, self.poly_count, c.getfloat("map", "angular_map_max_range"),
                                           c.getfloat("map", "angle_min") * np.pi, c.getfloat("map", "angle_max") * np.pi,
                                           c.getint("map", "angular_map_dim"), normalize=normalize, out=out)

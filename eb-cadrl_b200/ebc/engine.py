@@ -352,6 +352,18 @@ class BatchedSim(object):
                      _ptr(out), stream=self._stream())
         return out
 
+    def local_map_grid(self, submap_size_m, out=None):
+        """Binary grid sub-map of every episode (simulator/env.py:630-708, SURVEY 8f-3, [map] use_grid_map = true):
+        the window of scene.map (the bound zero-cell rectangles) around the robot, rotated into its heading like
+        cv2.warpAffine does and thresholded; returns [N, size, size] uint8 on the device."""
+        size = int(round(submap_size_m / self.cfg.map_resolution))
+        if out is None:
+            out = torch.empty(self.N, size, size, dtype=torch.uint8, device=self.device)
+        assert out.dtype == torch.uint8 and tuple(out.shape) == (self.N, size, size) and out.is_contiguous()
+        m = abi.EbcGridMap(submap_size_m, size, 0)
+        self.be.call("local_map_grid", self.h, ctypes.byref(m), _ptr(out), stream=self._stream())
+        return out
+
     def launch_count(self):
         return self.be.launch_count(self.h)
 

@@ -10,8 +10,9 @@ same BatchedSim with whole batches.
 
 `local_map`: with [map] use_grid_map = false the angular map of env.py:570-628 is computed on the
 device (`ebc_local_map_angular`) for reset / step, like the reference does on every call; the lookahead skips it
-(the reference computes and drops it there).  The binary grid sub-map (use_grid_map = true, an OpenCV warpAffine of
-the occupancy grid) and rendering are out of scope: `local_map` is None in that mode.
+(the reference computes and drops it there).  With use_grid_map = true it is the binary grid sub-map of env.py:630-708
+(`ebc_local_map_grid`: the window of scene.map around the robot, rotated like cv2.warpAffine does, thresholded).
+Rendering is out of scope.
 """
 import numpy as np
 import torch
@@ -51,6 +52,7 @@ class EntityBasedCollisionAvoidance(object):
         self._policy_bound = None
         self._probe = None
         self._map_probe = None
+        self._grid_probe = None
         self._poly = None
         self.local_maps = None
         self.local_maps_angular = None
@@ -185,10 +187,29 @@ class EntityBasedCollisionAvoidance(object):
             self.local_maps_angular.append(vec)
         return vec
 
+    def get_local_map(self, ob=None, append=True):
+        """Binary sub-map of scene.map around `ob` (a FullState; default: the robot's current state on the device)
+        rotated into the robot's heading, simulator/env.py:630-692: float64 [size, size] of zeros and ones."""
+        n = self.native
+        sim = n
+        if ob is not None:
+            # a one-episode probe that shares the scene's rectangle list
+            if self._grid_probe is None or self._grid_probe.device != n.device or self._grid_probe.Rmax != n.Rmax:
+                self._grid_probe = BatchedSim(n.cfg, 1, 1, 0, n.Rmax, 1, device=n.device)
+            sim = self._grid_probe
+            sim.rect.copy_(n.rect[:1])
+            sim.rect_count.copy_(n.rect_count[:1])
+            sim.rob_pv[0, 0], sim.rob_pv[0, 1] = float(ob.px), float(ob.py)
+            sim.rob_theta[0] = float(ob.theta)
+        grid = sim.local_map_grid(self.submap_size_m)[0].cpu().numpy().astype(np.float64)
+        if append and self.local_maps is not None:
+            self.local_maps.append(grid)
+        return grid
+
     def _local_map(self, compute_local_map):
-        if not (compute_local_map and self.local_map_enabled) or self.use_grid_map:
+        if not (compute_local_map and self.local_map_enabled):
             return None
-        return self.get_local_map_angular()
+        return self.get_local_map() if self.use_grid_map else self.get_local_map_angular()
 
     def _observation(self):
         ob = [h.get_observable_state() for h in self._humans()]

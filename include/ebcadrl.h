@@ -366,6 +366,24 @@ typedef struct ebc_angular_map {
 int ebc_local_map_angular(ebc_sim *sim, const ebc_angular_map *map, const double *poly_xy, const int32_t *poly_count,
                           double *out, void *stream);
 
+/* Binary grid sub-map of simulator/env.py:630-708: what env.step / env.reset return as `local_map`
+ * when [map] use_grid_map = true.  For every episode a size x size window of the occupancy grid (scene.map, given by
+ * the bound state's zero-cell rectangles) centred on the robot's cell -- clipped at the map border with the
+ * reference's index arithmetic (env.py:637-672; the window's last row and column keep the fill value 1, as there),
+ * all ones when the window misses the map (env.py:674-680) -- rotated by (-theta + pi/2) about (size/2, size/2) and
+ * thresholded at 0.9 (env.py:685-689).  The rotation is OpenCV's cv2.getRotationMatrix2D + cv2.warpAffine(grid, M,
+ * (size, size), borderValue=1) for a float64 image (third-party, opencv-python, not under /root/reference, no
+ * pinned version; restated from OpenCV 4.x imgwarp.cpp WarpAffineInvoker + remapBilinear and pinned to cv2 4.13):
+ * inverse map in 1/1024 fixed point (AB_BITS 10, cvRound), sample position to 1/32 pixel (INTER_BITS 5), bilinear
+ * weights from the float table, constant border 1.  out[e][i][j] in {0, 1}, i = first (x) index of the rotated grid. */
+typedef struct ebc_grid_map {
+  double submap_size_m;  /* [map] submap_size_m */
+  int32_t size;          /* int(round(submap_size_m / map_resolution)), 1..192; must not exceed the map's cells */
+  int32_t reserved;
+} ebc_grid_map;
+/* out [N*size*size] u8 (device). */
+int ebc_local_map_grid(ebc_sim *sim, const ebc_grid_map *map, uint8_t *out, void *stream);
+
 /* ---- diagnostics (exported, but NOT part of the drop-in surface: nothing in the reference binds these;
  *      declared only when the includer asks for them) ---------------------------------------------------------- */
 #ifdef EBC_DIAGNOSTICS
@@ -401,7 +419,8 @@ int ebc_ref_reset(ebc_sim *sim, const ebc_state *pool, int32_t pool_size, const 
                   const uint8_t *mask);
 int ebc_ref_local_map_angular(ebc_sim *sim, const ebc_angular_map *map, const double *poly_xy, const int32_t *poly_count,
                               double *out);
-void ebc_ref_set_threads(int n);   /* OpenMP threads over episodes (cpu_baseline leg) */
+int ebc_ref_local_map_grid(ebc_sim *sim, const ebc_grid_map *map, uint8_t *out);
+void ebc_ref_set_threads(int n);  /* OpenMP threads over episodes (cpu_baseline leg) */
 
 #ifdef __cplusplus
 }

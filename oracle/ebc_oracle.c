@@ -1440,6 +1440,88 @@ int ebc_ref_local_map_angular(ebc_sim *s, const ebc_angular_map *map, const doub
   return EBC_OK;
 }
 
+/* ---- binary grid sub-map ([map] use_grid_map = true) ---------------------------------------------
+ * simulator/env.py:630-692 get_local_map + :694-708 rotate_grid_around_center.  The rotation is OpenCV's
+ * (opencv-python, third party, not under /root/reference, no pinned version): cv2.getRotationMatrix2D and
+ * cv2.warpAffine(INTER_LINEAR, BORDER_CONSTANT, borderValue 1) on a float64 image, restated from OpenCV 4.x
+ * modules/imgproc/src/imgwarp.cpp (getRotationMatrix2D, invertAffineTransform part of warpAffine, WarpAffineInvoker,
+ * remapBilinear<Cast<double,double>, RemapNoVec, float>, initInterTab2D) and pinned to cv2 4.13 by
+ * tests/golden/make_local_map_golden.py (bit-equal on every cell of the goldens, before thresholding). */
+static int scene_map_is_free(const ebc_sim *s, int e, int ix, int iy) {          /* scene.map[ix][iy] (1 free, 0 wall) */
+  const int16_t *rc = s->st.rect + (size_t)e * s->cfg.max_rects * 4;
+  const int R = s->cfg.max_rects ? s->st.rect_count[e] : 0;
+  for (int j = 0; j < R && j < s->cfg.max_rects; ++j)
+    if (ix >= rc[4 * j] && ix < rc[4 * j + 2] && iy >= rc[4 * j + 1] && iy < rc[4 * j + 3]) return 0;
+  return 1;
+}
+
+int ebc_ref_local_map_grid(ebc_sim *s, const ebc_grid_map *map, uint8_t *out) {
+  if (!s || !s->bound) return fail(s, EBC_ERR_UNBOUND, "ebc_local_map_grid: state not bound");
+  const ebc_config *c = &s->cfg;
+  const int G = (int)rint(c->map_size_m / c->map_resolution);                      /* scene_generator.py:310-311 */
+  if (!map || !out || map->size < 1 || map->size > 192 || map->size > G ||
+      map->size != (int)rint(map->submap_size_m / c->map_resolution))
+    return fail(s, EBC_ERR_INVALID, "ebc_local_map_grid: bad argument (size = round(submap_size_m / map_resolution), 1..192, <= map cells)");
+  const int S = map->size;                                                          /* env.py:643 */
+  float tab[32][2];                                                                 /* initInterTab1D, INTER_LINEAR */
+  for (int i = 0; i < 32; ++i) {
+    const float x = (float)i * (1.0f / 32);
+    tab[i][0] = 1.0f - x;
+    tab[i][1] = x;
+  }
+  for (int e = 0; e < c->n_episodes; ++e) {
+    uint8_t *o = out + (size_t)e * S * S;
+    const double px = s->st.rob_pv[(size_t)e * 4], py = s->st.rob_pv[(size_t)e * 4 + 1], theta = s->st.rob_theta[e];
+    const int cx = (int)rint((px + c->map_size_m / 2.0) / c->map_resolution);       /* env.py:637-642 (round half even) */
+    const int cy = (int)rint((py + c->map_size_m / 2.0) / c->map_resolution);
+    int six = (int)rint((double)cx - floor((double)S / 2.0));                        /* env.py:645-648 */
+    int siy = (int)rint((double)cy - floor((double)S / 2.0));
+    int eix = six + S - 1, eiy = siy + S - 1;
+    const int max_idx = G - 1;                                                      /* env.py:652-653 (square map) */
+    int sgx = 0, sgy = 0, egx = S - 1, egy = S - 1;                                  /* env.py:655-658 */
+    if (six < 0) { sgx = -six; six = 0; }                                            /* env.py:660-672 */
+    else if (eix > max_idx) { egx = egx - (eix - max_idx); eix = max_idx; }
+    if (siy < 0) { sgy = -siy; siy = 0; }
+    else if (eiy > max_idx) { egy = egy - (eiy - max_idx); eiy = max_idx; }
+    if (sgy > egy || siy > eiy || six > eix || sgx > egx) {                          /* env.py:674-680: all ones */
+      memset(o, 1, (size_t)S * S);
+      continue;
+    }
+    /* grid[sgx:egx, sgy:egy] = map[six:eix, siy:eiy] (env.py:682-684; the slices exclude their end index) */
+#define GRID_AT(i, j)                                                                                         \
+  (((i) < 0 || (i) >= S || (j) < 0 || (j) >= S) ? 1.0 /* borderValue */                                       \
+   : ((i) >= sgx && (i) < egx && (j) >= sgy && (j) < egy) ? (double)scene_map_is_free(s, e, six + (i)-sgx, siy + (j)-sgy) \
+                                                           : 1.0)
+    const double angle = (-theta + M_PI / 2) * 180 / M_PI;                           /* env.py:686 */
+    /* cv2.getRotationMatrix2D(center = (rows / 2, cols / 2), angle, 1) */
+    const double a = angle * (M_PI / 180), alpha = cos(a), beta = sin(a), ctr = (double)S / 2.0;
+    double M[6] = {alpha, beta, (1 - alpha) * ctr - beta * ctr, -beta, alpha, beta * ctr + (1 - alpha) * ctr};
+    /* warpAffine without WARP_INVERSE_MAP: invert */
+    double D = M[0] * M[4] - M[1] * M[3];
+    D = D != 0 ? 1. / D : 0;
+    const double A11 = M[4] * D, A22 = M[0] * D;
+    M[0] = A11; M[1] *= -D; M[3] *= -D; M[4] = A22;
+    const double b1 = -M[0] * M[2] - M[1] * M[5], b2 = -M[3] * M[2] - M[4] * M[5];
+    M[2] = b1; M[5] = b2;
+    const int AB_SCALE = 1 << 10, round_delta = AB_SCALE / 32 / 2;
+    for (int y = 0; y < S; ++y) {                                                   /* dst row = first index */
+      const int X0 = (int)lrint((M[1] * y + M[2]) * AB_SCALE) + round_delta;
+      const int Y0 = (int)lrint((M[4] * y + M[5]) * AB_SCALE) + round_delta;
+      for (int x = 0; x < S; ++x) {
+        const int X = (X0 + (int)lrint(M[0] * x * AB_SCALE)) >> 5, Y = (Y0 + (int)lrint(M[3] * x * AB_SCALE)) >> 5;
+        const int sx = X >> 5, sy = Y >> 5, fx = X & 31, fy = Y & 31;
+        const float w0 = tab[fy][0] * tab[fx][0], w1 = tab[fy][0] * tab[fx][1];
+        const float w2 = tab[fy][1] * tab[fx][0], w3 = tab[fy][1] * tab[fx][1];
+        const double v = GRID_AT(sy, sx) * w0 + GRID_AT(sy, sx + 1) * w1 + GRID_AT(sy + 1, sx) * w2 +
+                         GRID_AT(sy + 1, sx + 1) * w3;
+        o[(size_t)y * S + x] = v > 0.9 ? 1 : 0;                                      /* env.py:687-689 */
+      }
+    }
+#undef GRID_AT
+  }
+  return EBC_OK;
+}
+
 int ebc_ref_reset(ebc_sim *s, const ebc_state *pool, int32_t pool_size, const int32_t *pool_index,
                   const uint8_t *mask) {
   if (!s || !s->bound) return fail(s, EBC_ERR_UNBOUND, "ebc_reset: state not bound");

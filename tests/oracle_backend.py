@@ -46,6 +46,7 @@ class OracleBackend(object):
         L.ebc_ref_transform.argtypes = [vp, vp]
         L.ebc_ref_reset.argtypes = [vp, ctypes.POINTER(abi.EbcState), c_i32, vp, vp]
         L.ebc_ref_local_map_angular.argtypes = [vp, ctypes.POINTER(abi.EbcAngularMap), vp, vp, vp]
+        L.ebc_ref_local_map_grid.argtypes = [vp, ctypes.POINTER(abi.EbcGridMap), vp]
         L.ebc_ref_set_threads.argtypes = [ctypes.c_int]
 
     def set_threads(self, n):

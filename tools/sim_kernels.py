@@ -49,4 +49,25 @@ for N in (4096, 65536):
     ms = timed(lambda: sim.local_map_angular(xy_d, cnt, 3.0, -np.pi, np.pi, 48, out=out), 10)
     print("angular local map, %d episodes x 3 obstacles x 48 sectors: %.4f ms = %.3e maps/s (%.1f us per 1000 episodes)" % (
         N, ms, N / ms * 1e3, ms * 1e3 / N * 1000))
+    # binary grid sub-map (use_grid_map = true): 5 m window of the 0.1 m grid = 50 x 50 cells per episode,
+    # the scene's 3 wall rectangles, random headings; algorithmic bytes = the size x size bytes written + the rectangles read
+    sim.rob_theta.copy_(torch.tensor(rng.uniform(-np.pi, np.pi, N), dtype=torch.float32))
+    sim.rob_pv[:, :2] = torch.tensor(rng.uniform(-4.0, 4.0, (N, 2)), dtype=torch.float32)
+    for sub in (5.0, 6.0):
+        S = int(round(sub / 0.1))
+        g = torch.empty(N, S, S, dtype=torch.uint8, device="cuda:0")
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
+        sim.local_map_grid(sub, out=g); torch.cuda.synchronize()
+        evs = []
+        for _ in range(10):     # L2 flushed before every timed launch (a 25-236 MB output would otherwise partly stay in L2)
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); sim.local_map_grid(sub, out=g); b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+        byt = N * (S * S + 8 * shape.Rmax + 20)
+        print("grid local map, %d episodes x %d x %d cells: %.4f ms = %.3e maps/s, %.1f GB/s algorithmic (%.0f MB), zero cells %.1f %%" % (
+            N, S, S, ms, N / ms * 1e3, byt / ms / 1e6, byt / 1e6, 100.0 * float((g == 0).float().mean())))
+        del g, flush
     del sim
