@@ -1538,10 +1538,13 @@ angular_map_kernel(const ebc_config c, const ebc_state st, const ebc_angular_map
 // Block per episode.  (1) thread 0: the reference's window / clip index arithmetic and the inverse rotation matrix of
 // cv2.getRotationMatrix2D + cv2.warpAffine in float64; (2) the first `size` threads: the per-column and per-row
 // fixed-point terms (OpenCV's adelta / bdelta / X0 / Y0, 1/1024 units, cvRound = rint); (3) the window of scene.map is
-// rasterised from the episode's zero-cell rectangles into shared memory, one byte per cell; (4) every thread takes
-// four consecutive output cells: sample position to 1/32 pixel, four taps from shared memory (constant border 1),
-// OpenCV's float weight table, threshold, one 32-bit store.  HBM traffic = the size x size bytes written per episode
-// + the rectangle list; everything else stays in shared memory.
+// rasterised from the episode's zero-cell rectangles into shared memory, one byte per cell, inside a one-cell frame
+// of ones (the constant border: a tap outside the window reads 1 without a bounds test); (4) every thread takes four
+// consecutive output cells: sample position to 1/32 pixel, four taps from shared memory, threshold, one 32-bit store.
+// The bilinear sum is taken in integers: OpenCV's float weights are (32 - fy)(32 - fx) / 1024 etc. (exact in
+// float), the taps are 0 or 1, so its float64 sum equals (integer sum) / 1024 exactly and "> 0.9" is "integer sum >=
+// 922" (0.9 * 1024 = 921.6) -- the oracle keeps OpenCV's float / double sequence, the tests demand equal cells.
+// HBM traffic = the size x size bytes written per episode + the rectangle list; the rest stays in shared memory.
 struct GridMapShared {
   double m[6];
   int sgx, sgy, egx, egy, six, siy, degenerate, pad;
@@ -1552,9 +1555,9 @@ grid_map_kernel(const ebc_config c, const ebc_state st, const int S, uint8_t *__
   extern __shared__ __align__(16) uint8_t gm_smem[];
   __shared__ GridMapShared sh;
   const int e = blockIdx.x, tid = threadIdx.x;
-  const int cells = S * S;
-  uint8_t *grid = gm_smem;                                             // [S][S]
-  int *adelta = reinterpret_cast<int *>(gm_smem + ((cells + 15) & ~15));   // [S] each
+  const int cells = S * S, P = S + 2, framed = P * P;                  // framed grid: [S + 2][S + 2], window at (1, 1)
+  uint8_t *grid = gm_smem;
+  int *adelta = reinterpret_cast<int *>(gm_smem + ((framed + 15) & ~15));   // [S] each
   int *bdelta = adelta + S, *x0s = bdelta + S, *y0s = x0s + S;
   if (tid == 0) {
     const float4 rp = reinterpret_cast<const float4 *>(st.rob_pv)[e];
@@ -1585,7 +1588,7 @@ grid_map_kernel(const ebc_config c, const ebc_state st, const int S, uint8_t *__
 #pragma unroll
     for (int k = 0; k < 6; ++k) sh.m[k] = M[k];
   }
-  for (int i = tid; i < (cells + 3) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(grid)[i] = 0x01010101u;
+  for (int i = tid; i < (framed + 3) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(grid)[i] = 0x01010101u;
   __syncthreads();
   if (sh.degenerate) {
     for (int i = tid; i < cells; i += blockDim.x) out[(size_t)e * cells + i] = 1;
@@ -1606,31 +1609,29 @@ grid_map_kernel(const ebc_config c, const ebc_state st, const int S, uint8_t *__
       const int j0 = max(sh.sgy, (int)r.y - sh.siy + sh.sgy), j1 = min(sh.egy, (int)r.w - sh.siy + sh.sgy);
       const int w = j1 - j0, n = (i1 - i0) * w;
       if (i1 <= i0 || w <= 0) continue;
-      for (int k = tid; k < n; k += blockDim.x) grid[(i0 + k / w) * S + j0 + k % w] = 0;
+      for (int k = tid; k < n; k += blockDim.x) grid[(i0 + 1 + k / w) * P + j0 + 1 + k % w] = 0;
     }
   }
   __syncthreads();
   const bool packed = (cells & 3) == 0;
   for (int q = tid; 4 * q < cells; q += blockDim.x) {
     uint32_t word = 0;
+    int y = (4 * q) / S, x = 4 * q - y * S;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int idx = 4 * q + k;
-      if (idx >= cells) break;
-      const int y = idx / S, x = idx - y * S;
+      if (4 * q + k >= cells) break;
       const int X = (x0s[y] + adelta[x]) >> 5, Y = (y0s[y] + bdelta[x]) >> 5;
       const int sx = X >> 5, sy = Y >> 5, fx = X & 31, fy = Y & 31;
-      // initInterTab1D(INTER_LINEAR): {1 - f / 32, f / 32} in float; the 2-D table holds their float products
-      const float ax1 = (float)fx * (1.0f / 32), ay1 = (float)fy * (1.0f / 32), ax0 = 1.0f - ax1, ay0 = 1.0f - ay1;
-      const float w0 = ay0 * ax0, w1 = ay0 * ax1, w2 = ay1 * ax0, w3 = ay1 * ax1;
-      const bool r0 = sy >= 0 && sy < S, r1 = sy + 1 >= 0 && sy + 1 < S;
-      const bool c0 = sx >= 0 && sx < S, c1 = sx + 1 >= 0 && sx + 1 < S;
-      const double s0 = (r0 && c0) ? (double)grid[sy * S + sx] : 1.0, s1 = (r0 && c1) ? (double)grid[sy * S + sx + 1] : 1.0;
-      const double s2 = (r1 && c0) ? (double)grid[(sy + 1) * S + sx] : 1.0, s3 = (r1 && c1) ? (double)grid[(sy + 1) * S + sx + 1] : 1.0;
-      const double v = s0 * w0 + s1 * w1 + s2 * w2 + s3 * w3;
-      const uint32_t bit = v > 0.9 ? 1u : 0u;                                    // env.py:687-689
+      uint32_t bit = 1u;                           // all four taps outside the window: the border value
+      if ((unsigned)(sx + 1) <= (unsigned)S && (unsigned)(sy + 1) <= (unsigned)S) {     // sx, sy in [-1, S - 1]
+        const uint8_t *g = grid + (sy + 1) * P + sx + 1;
+        const int sum = (int)g[0] * (32 - fy) * (32 - fx) + (int)g[1] * (32 - fy) * fx + (int)g[P] * fy * (32 - fx) +
+                        (int)g[P + 1] * fy * fx;
+        bit = sum >= 922 ? 1u : 0u;                // env.py:687-689: > 0.9
+      }
       if (packed) word |= bit << (8 * k);
-      else out[(size_t)e * cells + idx] = (uint8_t)bit;
+      else out[(size_t)e * cells + 4 * q + k] = (uint8_t)bit;
+      if (++x == S) { x = 0; ++y; }
     }
     if (packed) reinterpret_cast<uint32_t *>(out + (size_t)e * cells)[q] = word;
   }
@@ -1925,7 +1926,7 @@ int ebc_launch_step(ebc_sim *s, bool fused_orca, const int32_t *action_idx, cons
 
 int ebc_launch_grid_map(ebc_sim *s, const ebc_grid_map *map, uint8_t *out, cudaStream_t stream) {
   const int S = map->size;
-  const size_t smem = (size_t)((S * S + 15) & ~15) + 4 * sizeof(int) * (size_t)S;
+  const size_t smem = (size_t)(((S + 2) * (S + 2) + 15) & ~15) + 4 * sizeof(int) * (size_t)S;
   grid_map_kernel<<<s->cfg.n_episodes, 256, smem, stream>>>(s->cfg, s->st, S, out);
   return ebc_check_launch(s, "grid_map_kernel");
 }

@@ -6,5 +6,5 @@ O=gpurun_out; mkdir -p $O
 ( time timeout 600 python -m pytest tests/test_local_map_grid.py -m gpu -q -x ) > $O/m_pytest_grid.log 2>&1; echo "pytest rc=$?" >> $O/m_pytest_grid.log
 timeout 600 python tools/sim_kernels.py > $O/m_sim_kernels.txt 2>&1; echo "rc=$?" >> $O/m_sim_kernels.txt
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:grid_map_kernel -c 2 -o $O/m_grid_map python tools/sim_kernels.py > $O/m_ncu.log 2>&1
-( time timeout 1200 python -m pytest tests -m gpu -q -x ) > $O/m_pytest_all.log 2>&1; echo "pytest rc=$?" >> $O/m_pytest_all.log
+( time timeout 900 python -m pytest tests/test_gpu_mirror.py tests/test_local_map.py -m gpu -q -x ) > $O/m_pytest_all.log 2>&1; echo "pytest rc=$?" >> $O/m_pytest_all.log
 tail -3 $O/m_pytest_grid.log $O/m_pytest_all.log; cat $O/m_sim_kernels.txt
