@@ -286,13 +286,16 @@ int ebc_generate(ebc_sim *s, const ebc_scene_shape *shape, uint64_t seed, const 
                  void *stream) {
   REQUIRE_BOUND("ebc_generate");
   if (!shape || !episode_ids) return ebc_fail(s, EBC_ERR_INVALID, "ebc_generate: null shape or episode ids");
-  if (shape->n_types < 1 || shape->n_types > 4 || shape->max_tries < 1 || shape->rule < 0 || shape->rule > 3)
+  if (shape->n_types < 1 || shape->n_types > 4 || shape->max_tries < 1 || shape->rule < 0 || shape->rule > 4)
     return ebc_fail(s, EBC_ERR_INVALID, "ebc_generate: bad shape");
   int humans = 0;
   for (int t = 0; t < shape->n_types; ++t) {
     if (shape->type_count[t] < 0) return ebc_fail(s, EBC_ERR_INVALID, "ebc_generate: negative group size");
     humans += shape->type_count[t];
   }
+  if (shape->rule == 4 && (humans != 2 || shape->n_types != 1))     // scene_generator.py:583-589 ignores adult_num
+    return ebc_fail(s, EBC_ERR_INVALID, "ebc_generate: the one_static rule places exactly two agents of one type (got %d in %d groups)",
+                    humans, shape->n_types);
   if (humans > s->cfg.max_humans || humans > 64)
     return ebc_fail(s, EBC_ERR_INVALID, "ebc_generate: %d humans do not fit (Hmax %d, generator limit 64)", humans, s->cfg.max_humans);
   if (shape->num_walls > s->cfg.max_rects || shape->num_walls * shape->discs_per_wall > s->cfg.max_statics)

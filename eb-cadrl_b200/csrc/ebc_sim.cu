@@ -1685,7 +1685,9 @@ generate_kernel(const ebc_config c, const ebc_state st, const ebc_scene_shape sh
       const bool circle = !is_static && (sh.rule == 1 || ((sh.rule == 2 || sh.rule == 3) && hd < n_dynamic / 2));
       const double md_robot = rad[h] + sh.robot_radius + dd;
       double x = 0, y = 0, tx = 0, ty = 0;
-      if (is_static && h == 0) {                // scene_generator.py:463-466: the first static adult is fixed
+      if (sh.rule == 4) {                       // one_static (scene_generator.py:583-589): two adults standing at (-2, -8), (-3, -8)
+        x = -2.0 - (double)h; y = -8.0; tx = x; ty = y;
+      } else if (is_static && h == 0) {         // scene_generator.py:463-466: the first static adult is fixed
         x = -0.5; y = -2.5; tx = x; ty = y;
       } else {
         // static adults (:467-487): one side of the y axis for all tries of this adult

@@ -70,7 +70,7 @@ class SceneShape(object):
         for i, (code, count, (v0, v1), (r0, r1)) in enumerate(self.types):
             s.type_code[i], s.type_count[i] = code, count
             s.v_pref_lo[i], s.v_pref_hi[i], s.radius_lo[i], s.radius_hi[i] = v0, v1, r0, r1
-        s.rule = {"square_crossing": 0, "circle_crossing": 1, "mixed": 2, "mixed_20": 3}[self.rule]
+        s.rule = {"square_crossing": 0, "circle_crossing": 1, "mixed": 2, "mixed_20": 3, "one_static": 4}[self.rule]
         s.num_walls, s.wall_len_lo, s.wall_len_hi = self.num_walls, self.wall_len[0], self.wall_len[1]
         s.discs_per_wall, s.max_tries = self.discs_per_wall, max_tries
         s.square_width, s.circle_radius = self.square_width, self.circle_radius
@@ -91,6 +91,9 @@ CFG4 = SceneShape("cfg4_h20_10walls", [(0, 20, (1.0, 1.0), (0.3, 0.3))], rule="m
 # the reference's full `mixed_20` rule (scene_generator.py:577-582): randint(20) static adults + the dynamic mix
 MIXED20 = SceneShape("mixed_20_h20_5walls", [(0, 20, (0.5, 1.5), (0.2, 0.4))], rule="mixed_20", square_width=13.0,
                      circle_radius=6.0, robot_v_pref=1.0, num_walls=5, wall_len=(2, 4), map_size_m=14.0)
+# configs/env_configs/env_one_static_human.config: the `one_static` rule (scene_generator.py:583-589), no obstacles
+ONE_STATIC = SceneShape("one_static_h2", [(0, 2, (1.0, 1.0), (0.3, 0.3))], rule="one_static", square_width=10.0,
+                        circle_radius=4.0, robot_v_pref=1.0, num_walls=0, discomfort_dist=0.2)
 # configs[0] shape (the reference's CPU-runnable case): 5 adults on a circle of radius 3
 CFG1 = SceneShape("cfg1_h5_circle", [(0, 5, (0.6, 0.6), (0.2, 0.2))], rule="circle_crossing", square_width=9.0,
                   circle_radius=3.0, robot_radius=0.2, robot_v_pref=0.7, num_walls=0)
@@ -170,6 +173,10 @@ def generate(shape, episode_ids, seed=SEED_BASE, max_tries=64, max_obst=0):
         circle_all = ~is_static_all & ((shape.rule == "circle_crossing") | ((shape.rule in ("mixed", "mixed_20")) & (hd < n_dynamic // 2)))
         fixed = is_static_all & (h == 0)                      # :463-466: the first static adult is fixed
         px[fixed, h], py[fixed, h], gx[fixed, h], gy[fixed, h] = -0.5, -2.5, -0.5, -2.5
+        if shape.rule == "one_static":                        # :583-589: two adults standing at (-2, -8) and (-3, -8)
+            assert H == 2 and len(shape.types) == 1
+            fixed = np.ones(N, bool)
+            px[:, h], py[:, h], gx[:, h], gy[:, h] = -2.0 - h, -8.0, -2.0 - h, -8.0
         todo = ~fixed
         sign_all = np.where(uniform(seed, ids, 2000 + h, 7) < 0.5, 1.0, -1.0)
         md_robot_all = rad[:, h] + shape.robot_radius + shape.discomfort_dist

@@ -329,7 +329,8 @@ typedef struct ebc_scene_shape {
   double v_pref_lo[4], v_pref_hi[4], radius_lo[4], radius_hi[4];
   int32_t rule;               /* 0 square_crossing, 1 circle_crossing, 2 mixed (first half circle: the dynamic part of
                                  mixed_20), 3 mixed_20 (scene_generator.py:577-582: randint(20) static adults in a
-                                 6 x 8 box, the first at (-0.5, -2.5), then the dynamic mix) */
+                                 6 x 8 box, the first at (-0.5, -2.5), then the dynamic mix), 4 one_static
+                                 (scene_generator.py:583-589: exactly two agents standing at (-2, -8) and (-3, -8)) */
   int32_t num_walls;
   int32_t wall_len_lo, wall_len_hi;   /* metres, inclusive */
   int32_t discs_per_wall;     /* static discs a wall of wall_len_hi decomposes into */

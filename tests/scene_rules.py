@@ -41,6 +41,9 @@ def check_scene_rules(shape, sc, max_fallback_frac=2e-3):
         assert is_square.all()
     elif shape.rule == "mixed":                                       # :492-501: first half circle, second half square
         assert is_circle[:, :H // 2].all() and is_square[:, H // 2:].all()
+    elif shape.rule == "one_static":                                  # :583-589: two adults standing still, fixed places
+        assert H == 2 and static.all()
+        assert (p[:, 0] == np.array([-2.0, -8.0])).all() and (p[:, 1] == np.array([-3.0, -8.0])).all()
     elif shape.rule == "mixed_20":                                    # :577-582
         n_static = static.sum(1)
         assert ((n_static >= 0) & (n_static <= 19)).all() and len(np.unique(n_static)) > 10      # randint(20)
@@ -61,7 +64,7 @@ def check_scene_rules(shape, sc, max_fallback_frac=2e-3):
         md_r = rad[:, h] + shape.robot_radius + dd
         bad = np.hypot(*(p[:, h] - robot).T) < md_r - 1e-6
         bad |= is_circle[:, h] & (np.hypot(*(p[:, h] - goal).T) < md_r - 1e-6)
-        fixed = static[:, h] & (h == 0)
+        fixed = static[:, h] & ((h == 0) | (shape.rule == "one_static"))      # placed without sampling
         for j in range(h):
             if types[j] != types[h]:
                 continue

@@ -430,7 +430,7 @@ def test_error_codes():
     lib.ebc_destroy(h)
 
 
-@pytest.mark.parametrize("shape_name,N", [("CFG2", 4096), ("CFG3", 2048), ("CFG4", 2048), ("CFG1", 512), ("MIXED20", 2048)])
+@pytest.mark.parametrize("shape_name,N", [("CFG2", 4096), ("CFG3", 2048), ("CFG4", 2048), ("CFG1", 512), ("MIXED20", 2048), ("ONE_STATIC", 256)])
 def test_device_scene_generator_matches_host(shape_name, N):
     """the device generator (ebc_generate, thread per episode, counter-based draws) against the host
     generator of ebc/synth.py (numpy float64, same draws): humans with rejection sampling, walls with start / goal

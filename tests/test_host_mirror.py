@@ -271,7 +271,7 @@ def test_synth_wall_geometry_matches_reference():
     assert n_clipped >= 10 and n_square >= 10      # border-clipped and square walls were part of the fixture
 
 
-@pytest.mark.parametrize("shape_name", ["CFG1", "CFG2", "CFG3", "CFG4", "MIXED20"])
+@pytest.mark.parametrize("shape_name", ["CFG1", "CFG2", "CFG3", "CFG4", "MIXED20", "ONE_STATIC"])
 def test_synth_scenes_obey_reference_placement_rules(shape_name):
     """f-1: start / goal geometry, minimum separation, wall clearance, disc radii of scene_generator.py on the host
     generator's output (tests/scene_rules.py restates each rule with its reference line)."""
