@@ -210,6 +210,12 @@ int ebc_lookahead(ebc_sim *s, float *vin, double *reward, uint8_t *done, uint8_t
   return ebc_launch_lookahead(s, vin, reward, done, event, (cudaStream_t)stream);
 }
 
+int ebc_set_attention_output(ebc_sim *s, float *attn) {
+  if (!s) return EBC_ERR_INVALID;
+  s->attn_out = attn;
+  return EBC_OK;
+}
+
 int ebc_value(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row_count, float *values, void *stream) {
   if (!s) return EBC_ERR_INVALID;
   if (!s->have_weights) return ebc_fail(s, EBC_ERR_UNBOUND, "ebc_value: weights not set");

@@ -85,6 +85,7 @@ struct ebc_sim {
   float4 *d_la_rec;      // [N * A * 3] robot part of the rotated rows per (episode, action), written by ebc_lookahead for
                          // K4's fused input path (ebc_value with vin == NULL)
   int la_rec_valid;      // the records belong to the current state (set by ebc_lookahead, consumed by ebc_value)
+  float *attn_out;       // caller's array for the softmax attention weights (ebc_set_attention_output), or null
   float *d_joint;        // [cap_states * (self_dim + H2)] scratch for mlp3
   int64_t joint_cap;     // states ebc_value may be called with (ebc_reserve)
   size_t joint_floats;   // allocated floats of d_joint

@@ -158,6 +158,7 @@ struct EntityParams {
   int n;                     // rows per state slot
   int ts;                    // states per tile
   float *joint;              // [n_states][self_dim + H2]
+  float *attn;               // [n_states][n] softmax attention weights (ebc_set_attention_output), or null
   // shared-memory offsets (floats)
   int off_x, off_t, off_h1, off_h2, off_w, off_g, off_gv, off_sc;
 };
@@ -251,6 +252,8 @@ __global__ void __launch_bounds__(256, 1) value_entity_kernel(const EntityParams
         sum += e;
       }
       for (int r = 0; r < c; ++r) SC[tid * n + r] = SC[tid * n + r] / sum;
+      if (p.attn && tid < ns)
+        for (int r = 0; r < n; ++r) p.attn[(size_t)(s0 + tid) * n + r] = r < c ? SC[tid * n + r] : 0.0f;
     }
     __syncthreads();
     // joint = [self_state, sum_r w_r * mlp2_r]
@@ -410,6 +413,7 @@ int ebc_launch_value(ebc_sim *s, const float *vin, int64_t n_states, const int32
   if (ts > MAX_TS) ts = MAX_TS;
   p.ts = ts;
   p.joint = s->d_joint;
+  p.attn = s->attn_out;
   const int h1d = net.l[1].out, h2d = net.l[3].out, a1d = net.l[4].out;
   int tmax = net.l[0].out;
   if (net.l[2].out > tmax) tmax = net.l[2].out;

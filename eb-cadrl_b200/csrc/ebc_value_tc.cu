@@ -619,6 +619,7 @@ struct TcEntityParams {
   long long n_states;
   int n, ts, D;
   float *joint;
+  float *attn;     // [n_states][n] softmax attention weights (ebc_set_attention_output), or null
   int jd;          // self_dim + H2
   int jch;         // k-chunks of a joint row: (jd + 7) / 8
   int self_dim;
@@ -909,6 +910,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
 #pragma unroll
         for (int o = 1; o < 16; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         const float wrow = e / sum;          // NaN like the reference when every score is exactly 0
+        if (p.attn && cg == 0 && st_row < ns) p.attn[(size_t)(s0 + st_row) * 16 + (row & 15)] = real ? wrow : 0.0f;
         const TcStage &S = P.st[ST_L3];
         for (int c = 16 * cg; c < S.np; c += 16 * NCG) {
           float v[16];
@@ -971,6 +973,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
         }
         const float sum = __shfl_sync(0xffffffffu, es, head_lane);
         const float wrow = e / sum;          // NaN like the reference when every score of the state is exactly 0
+        if (p.attn && cg == 0 && in_tile) p.attn[(size_t)(s0 + my_sid) * n + my_rin] = real ? wrow : 0.0f;
         for (int c = 16 * cg; c < S.np; c += 16 * NCG) {
           float v[16];
           tmem_ld16(tmem_row + S.acc_col + c, v);
@@ -1040,6 +1043,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
         if (in_tile)
           for (int qq = q_lo; qq <= q_hi; ++qq) sum += PSUM[qq * MAX_STATES + sid];
         const float wrow = e / sum;          // NaN like the reference when every score of the state is exactly 0
+        if (p.attn && cg == 0 && in_tile) p.attn[(size_t)(s0 + my_sid) * n + r_in] = real ? wrow : 0.0f;
         for (int c = 16 * cg; c < S.np; c += 16 * NCG) {
           float v[16];
           tmem_ld16(tmem_row + S.acc_col + c, v);
@@ -1308,6 +1312,7 @@ int launch_tc(ebc_sim *s, const float *vin, int64_t n_states, const int32_t *row
   while (n > 32 && ts > 1 && 512u + 16u * (uint32_t)ts * (uint32_t)p.prog.st[ST_L3].np > Cfg<NSPLIT>::A_IMAGE - 4u * A_CHUNK_BYTES) --ts;
   p.ts = ts;
   p.joint = s->d_joint; p.jd = s->net.self_dim + s->net.l[3].out; p.self_dim = s->net.self_dim;
+  p.attn = s->attn_out;
   p.jch = (p.jd + 7) / 8;
   p.trace = nullptr; p.trace_fine = 0;
   TcMlp3Params q;

@@ -111,6 +111,7 @@ PROTOTYPES = {
     "ebc_robot_orca": (c_i32, [SIM, c_f64, vp, vp]),
     "ebc_lookahead": (c_i32, [SIM, vp, vp, vp, vp, vp]),
     "ebc_value": (c_i32, [SIM, vp, ctypes.c_int64, vp, vp, vp]),
+    "ebc_set_attention_output": (c_i32, [SIM, vp]),
     "ebc_select": (c_i32, [SIM, vp, vp, vp, vp, vp, vp]),
     "ebc_step": (c_i32, [SIM, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "ebc_orca_step": (c_i32, [SIM, vp, vp, vp, vp, vp, vp, vp, vp, vp]),

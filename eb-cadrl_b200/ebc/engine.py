@@ -44,7 +44,7 @@ class CudaBackend(object):
 
     def call(self, name, h, *args, stream=None):
         fn = getattr(self.lib, "ebc_" + name)
-        if name in ("bind", "bind_stats", "set_actions", "set_weights", "reserve"):
+        if name in ("bind", "bind_stats", "set_actions", "set_weights", "reserve", "set_attention_output"):
             rc = fn(h, *args)
         else:
             rc = fn(h, *args, stream)
@@ -91,6 +91,7 @@ class BatchedSim(object):
         self.hum_nv = z(N, H, 2)
         self.stat = z(N, S, 4)
         self.stat_count = z(N, dtype=torch.int32)
+        self.attention = None      # enable_attention()
         self.rect = z(N, R, 4, dtype=torch.int16)
         self.rect_count = z(N, dtype=torch.int32)
         self.rob_pv = z(N, 4)
@@ -286,9 +287,21 @@ class BatchedSim(object):
             if out is None:
                 out = torch.zeros(n_states, dtype=torch.float32, device=self.device)
             self.reserve(n_states)
+            if self.attention is not None:
+                self.enable_attention(n_states)       # grow the borrowed array with the batch
         self.be.call("value", self.h, _ptr(vin), ctypes.c_int64(n_states), _ptr(row_count), _ptr(out),
                      stream=self._stream())
         return out
+
+    def enable_attention(self, n_states=None):
+        """Also keep the softmax attention weights of every state K4 evaluates (sarl.py:69-71,
+        ValueNetwork.attention_weights): `self.attention` [n_states, n] float32 on the device, row i = state i of the
+        last value() call (the lookahead batch: state e * A + a).  Off by default (one more n-float store per state)."""
+        rows = int(n_states or self.N * self.A)
+        if self.attention is None or self.attention.shape[0] < rows:
+            self.attention = torch.zeros(rows, self.n, dtype=torch.float32, device=self.device)
+            self.be.call("set_attention_output", self.h, _ptr(self.attention))
+        return self.attention
 
     def select(self):
         self.be.call("select", self.h, _ptr(self.la_reward), _ptr(self.values), _ptr(self.action_values),

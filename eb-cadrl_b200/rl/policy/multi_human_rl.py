@@ -36,10 +36,17 @@ class MultiHumanRL(CADRL):
         if self.phase == "train" and probability < self.epsilon:
             max_action = self.action_space[np.random.choice(len(self.action_space))]
         else:
+            keeps_attention = hasattr(self, "get_attention_weights") and hasattr(self.model, "_attention")
+            if keeps_attention and sim.attention is None:
+                sim.enable_attention()
             sim.decide()
             if int(sim.nan_flag[0].item()):
                 raise ValueError("Value network is not well trained. ")
             self.action_values = sim.action_values[0].cpu().tolist()
+            if keeps_attention:
+                # the reference keeps the weights of its LAST forward (sarl.py:71) = the last action of the loop
+                rows = int(sim.hum_count[0].item()) + int(sim.stat_count[0].item())
+                self.model._attention = sim.attention[sim.A - 1, :rows].clone()
             max_action = self.action_space[int(sim.argmax[0].item())]
         if self.phase == "train":
             self.last_state = self.transform(state, env)

@@ -280,6 +280,8 @@ class EntityBasedCollisionAvoidance(object):
                             [c.get_full_state() for c in self.scene.children]])
         if hasattr(self.robot.policy, "action_values"):
             self.action_values.append(self.robot.policy.action_values)
+        if hasattr(self.robot.policy, "get_attention_weights"):            # env.py:355-356
+            self.attention_weights.append(self.robot.policy.get_attention_weights())
         act = torch.tensor([self._action_pair(action)], dtype=torch.float64, device=n.device)
         n.step(action=act, fused_orca=True)          # humans' policies + collisions + reward + commit, one launch
         reward, done = float(n.reward[0].item()), bool(n.done[0].item())

@@ -279,6 +279,14 @@ int ebc_lookahead(ebc_sim *sim, float *vin, double *reward, uint8_t *done, uint8
 int ebc_value(ebc_sim *sim, const float *vin, int64_t n_states, const int32_t *row_count,
               float *values, void *stream);
 
+/* ValueNetwork.attention_weights / SARL.get_attention_weights (rl/policy/sarl.py:36,69-71,130-131): the softmax
+ * weights the network pools the entities with.  With a device array set here, every later ebc_value call also stores
+ * attn[i * n + r] = the weight of entity row r of state i (0 for rows past the state's row count; NaN like the
+ * reference when every score of the state is exactly 0).  The reference keeps the weights of its LAST forward, which
+ * in the lookahead is the last action's state: row (e * A + A - 1) of the batch.  NULL (the default) turns the
+ * output off.  The pointer is borrowed; it must hold n floats for every state of the largest ebc_value call. */
+int ebc_set_attention_output(ebc_sim *sim, float *attn);
+
 /* K5. Action selection (rl/policy/multi_human_rl.py:25-26,72-80):
  * action_values[e,a] = reward[e,a] + gamma^(time_step*v_pref) * values[e,a] (float64),
  * argmax[e] = first maximum (strict '>'), or 0 (the stop action) when the robot is
@@ -410,6 +418,7 @@ int ebc_ref_robot_orca(ebc_sim *sim, double safety_space, double *out_action);
 int ebc_ref_lookahead(ebc_sim *sim, float *vin, double *reward, uint8_t *done, uint8_t *event);
 int ebc_ref_value(ebc_sim *sim, const float *vin, int64_t n_states, const int32_t *row_count,
                   float *values);
+int ebc_ref_set_attention_output(ebc_sim *sim, float *attn);
 int ebc_ref_select(ebc_sim *sim, const double *reward, const float *values, double *action_values,
                    int32_t *argmax, uint8_t *nan_flag);
 int ebc_ref_step(ebc_sim *sim, const int32_t *action_idx, const double *action,

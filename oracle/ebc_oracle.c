@@ -686,6 +686,7 @@ struct ebc_sim {
   int have_actions;
   /* value net (copied) */
   int have_weights;
+  float *attn_out; /* ebc_set_attention_output */
   int D, self_dim, with_global;
   struct { float *w, *b; int in, out; } lin[11]; /* mlp1[2] mlp2[2] att[3] mlp3[4] */
   char err[256];
@@ -1166,7 +1167,7 @@ static void linear_f(const float *w, const float *b, int in, int out, const floa
 }
 
 /* rl/policy/sarl.py:38-82, one state of `rows` real rows. */
-static float value_forward(const ebc_sim *s, const float *x, int rows, int stride) {
+static float value_forward(const ebc_sim *s, const float *x, int rows, int stride, float *attn) {
   const int D = s->D;
   const int d1a = s->lin[0].out, h1d = s->lin[1].out, d2a = s->lin[2].out, h2d = s->lin[3].out;
   const int a1d = s->lin[4].out, a2d = s->lin[5].out;
@@ -1204,6 +1205,8 @@ static float value_forward(const ebc_sim *s, const float *x, int rows, int strid
     sum += (double)e;
   }
   const float fsum = (float)sum;
+  if (attn)                          /* sarl.py:71 attention_weights = weights[0, :, 0] */
+    for (int r = 0; r < rows; ++r) attn[r] = sc[r] / fsum;
   float *joint = tmp; /* [self_dim + h2d] */
   for (int k = 0; k < s->self_dim; ++k) joint[k] = x[k];
   for (int k = 0; k < h2d; ++k) {
@@ -1219,6 +1222,12 @@ static float value_forward(const ebc_sim *s, const float *x, int rows, int strid
   linear_f(s->lin[10].w, s->lin[10].b, s->lin[10].in, 1, m3, &v, 0);
   free(h1);
   return v;
+}
+
+int ebc_ref_set_attention_output(ebc_sim *s, float *attn) {
+  if (!s) return EBC_ERR_INVALID;
+  s->attn_out = attn;
+  return EBC_OK;
 }
 
 /* K4 */
@@ -1238,7 +1247,9 @@ int ebc_ref_value(ebc_sim *s, const float *vin, int64_t n_states, const int32_t 
       const int64_t e = i / A;
       rows = s->st.hum_count[e] + s->st.stat_count[e];
     }
-    values[i] = value_forward(s, vin + (size_t)i * n * D, rows, D);
+    float *attn = s->attn_out ? s->attn_out + (size_t)i * n : NULL;
+    if (attn) memset(attn, 0, sizeof(float) * (size_t)n);
+    values[i] = value_forward(s, vin + (size_t)i * n * D, rows, D, attn);
   }
   return EBC_OK;
 }

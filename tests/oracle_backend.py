@@ -42,6 +42,7 @@ class OracleBackend(object):
         L.ebc_ref_lookahead.argtypes = [vp] * 5
         L.ebc_ref_value.argtypes = [vp, vp, ctypes.c_int64, vp, vp]
         L.ebc_ref_select.argtypes = [vp] * 6
+        L.ebc_ref_set_attention_output.argtypes = [vp, vp]
         L.ebc_ref_step.argtypes = [vp] * 9
         L.ebc_ref_transform.argtypes = [vp, vp]
         L.ebc_ref_reset.argtypes = [vp, ctypes.POINTER(abi.EbcState), c_i32, vp, vp]
