@@ -1637,6 +1637,118 @@ grid_map_kernel(const ebc_config c, const ebc_state st, const int S, uint8_t *__
   }
 }
 
+// The same map for windows of at most 62 cells (the reference's 5 m and 6 m sub-maps on the 0.1 m grid): a framed row
+// of the window is ONE 64-bit word (bit = 1: free cell or border), so rasterising is a thread per row that clears
+// the bit range of every rectangle crossing it, the four taps of a sample are two 8-byte loads and two shifts
+// (code = t00 | t01 << 1 | t10 << 2 | t11 << 3), and the thresholded bilinear sum is a table lookup: bit fx of
+// lut[code * 32 + fy] says whether the integer sum (see above) reaches 922 -- the table is built at compile time.
+struct GridLut { uint32_t w[512]; };
+constexpr GridLut make_grid_lut() {
+  GridLut t{};
+  for (int code = 0; code < 16; ++code)
+    for (int fy = 0; fy < 32; ++fy) {
+      uint32_t bits = 0;
+      for (int fx = 0; fx < 32; ++fx) {
+        const int sum = ((code & 1) * (32 - fx) + ((code >> 1) & 1) * fx) * (32 - fy) +
+                        (((code >> 2) & 1) * (32 - fx) + ((code >> 3) & 1) * fx) * fy;
+        if (sum >= 922) bits |= 1u << fx;
+      }
+      t.w[code * 32 + fy] = bits;
+    }
+  return t;
+}
+__device__ const GridLut grid_lut = make_grid_lut();
+
+__global__ void __launch_bounds__(256)
+grid_map_bits_kernel(const ebc_config c, const ebc_state st, const int S, const uint32_t magic, uint8_t *__restrict__ out) {
+  __shared__ GridMapShared sh;
+  __shared__ unsigned long long rows[64];           // framed rows 0 .. S + 1, window cell (i, j) = bit j + 1 of rows[i + 1]
+  __shared__ int2 ab[64];                           // {adelta, bdelta} of column x
+  __shared__ int2 xy0[64];                          // {X0, Y0} of row y
+  __shared__ uint32_t lut[512];
+  const int e = blockIdx.x, tid = threadIdx.x;
+  const int cells = S * S;
+  if (tid == 0) {
+    const float4 rp = reinterpret_cast<const float4 *>(st.rob_pv)[e];
+    const double px = (double)rp.x, py = (double)rp.y, theta = (double)st.rob_theta[e];
+    const int G = (int)rint(c.map_size_m / c.map_resolution);
+    const int cx = (int)rint((px + c.map_size_m / 2.0) / c.map_resolution);       // env.py:637-642
+    const int cy = (int)rint((py + c.map_size_m / 2.0) / c.map_resolution);
+    int six = (int)rint((double)cx - floor((double)S / 2.0));                       // env.py:645-648
+    int siy = (int)rint((double)cy - floor((double)S / 2.0));
+    int eix = six + S - 1, eiy = siy + S - 1;
+    const int max_idx = G - 1;
+    int sgx = 0, sgy = 0, egx = S - 1, egy = S - 1;
+    if (six < 0) { sgx = -six; six = 0; }                                            // env.py:660-672
+    else if (eix > max_idx) { egx = egx - (eix - max_idx); eix = max_idx; }
+    if (siy < 0) { sgy = -siy; siy = 0; }
+    else if (eiy > max_idx) { egy = egy - (eiy - max_idx); eiy = max_idx; }
+    sh.degenerate = (sgy > egy || siy > eiy || six > eix || sgx > egx) ? 1 : 0;      // env.py:674-680
+    sh.sgx = sgx; sh.sgy = sgy; sh.egx = egx; sh.egy = egy; sh.six = six; sh.siy = siy;
+    const double angle = (-theta + 3.141592653589793 / 2) * 180 / 3.141592653589793;   // env.py:686
+    const double a = angle * (3.141592653589793 / 180), alpha = cos(a), beta = sin(a), ctr = (double)S / 2.0;
+    double M[6] = {alpha, beta, (1 - alpha) * ctr - beta * ctr, -beta, alpha, beta * ctr + (1 - alpha) * ctr};
+    double D = M[0] * M[4] - M[1] * M[3];
+    D = D != 0 ? 1. / D : 0;
+    const double A11 = M[4] * D, A22 = M[0] * D;
+    M[0] = A11; M[1] *= -D; M[3] *= -D; M[4] = A22;
+    const double b1 = -M[0] * M[2] - M[1] * M[5], b2 = -M[3] * M[2] - M[4] * M[5];
+    M[2] = b1; M[5] = b2;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) sh.m[k] = M[k];
+  }
+  for (int i = tid; i < 512; i += blockDim.x) lut[i] = grid_lut.w[i];
+  __syncthreads();
+  if (sh.degenerate) {
+    for (int i = tid; i < cells; i += blockDim.x) out[(size_t)e * cells + i] = 1;
+    return;
+  }
+  if (tid < S) {
+    ab[tid] = make_int2((int)rint(sh.m[0] * tid * 1024), (int)rint(sh.m[3] * tid * 1024));
+    xy0[tid] = make_int2((int)rint((sh.m[1] * tid + sh.m[2]) * 1024) + 16, (int)rint((sh.m[4] * tid + sh.m[5]) * 1024) + 16);
+  } else if (tid >= 64 && tid < 64 + S + 2) {
+    // framed row fr of the window (window row gi = fr - 1): grid[sgx:egx, sgy:egy] = map[six:eix, siy:eiy] (env.py:682-684)
+    const int fr = tid - 64, gi = fr - 1;
+    unsigned long long bits = ~0ull;
+    if (gi >= sh.sgx && gi < sh.egx) {
+      const int mx = sh.six + gi - sh.sgx;                          // scene.map row of this window row
+      const int R = c.max_rects ? min(st.rect_count[e], c.max_rects) : 0;
+      const short4 *rc = reinterpret_cast<const short4 *>(st.rect) + (size_t)e * c.max_rects;
+      for (int j = 0; j < R; ++j) {
+        const short4 r = rc[j];
+        if (mx < (int)r.x || mx >= (int)r.z) continue;
+        const int j0 = max(sh.sgy, (int)r.y - sh.siy + sh.sgy), j1 = min(sh.egy, (int)r.w - sh.siy + sh.sgy);
+        if (j1 > j0) bits &= ~((((1ull << (j1 - j0)) - 1ull)) << (j0 + 1));     // j1 - j0 <= 61
+      }
+    }
+    rows[fr] = bits;
+  }
+  __syncthreads();
+  // 32-bit shared-memory addresses taken once (a generic pointer to static shared memory costs an S2R + LEA per use);
+  // no branch per cell: out-of-window samples read a clamped, valid word and are overridden by a select.
+  // Consecutive lanes take consecutive cells: the {adelta, bdelta} loads of a warp are one contiguous 256 bytes, most
+  // lanes of a warp sample the same one or two source rows (broadcast), and a warp stores 32 consecutive bytes.  (Four
+  // consecutive cells per thread and one 32-bit store cost 6 shared-memory wavefronts per {adelta, bdelta} load -- a
+  // stride of 32 bytes between lanes -- and the kernel ran at 88-95 % of the shared-memory pipe.)
+  const uint32_t rows_s = (uint32_t)__cvta_generic_to_shared(rows), ab_s = (uint32_t)__cvta_generic_to_shared(ab);
+  const uint32_t xy0_s = (uint32_t)__cvta_generic_to_shared(xy0), lut_s = (uint32_t)__cvta_generic_to_shared(lut);
+  auto lds64 = [](uint32_t a) { unsigned long long v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return v; };
+  auto lds32x2 = [](uint32_t a) { int2 v; asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; };
+  auto lds32 = [](uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; };
+  uint8_t *dst = out + (size_t)e * cells;
+  for (int idx = tid; idx < cells; idx += blockDim.x) {     // idx / S = umulhi(idx, magic), magic = ceil(2^32 / S) (host)
+    const int y = (int)__umulhi((uint32_t)idx, magic), x = idx - y * S;
+    const int2 o = lds32x2(xy0_s + 8u * (uint32_t)y), d = lds32x2(ab_s + 8u * (uint32_t)x);
+    const int Xf = o.x + d.x, Yf = o.y + d.y;               // 1/1024 pixel
+    const uint32_t cx = (uint32_t)((Xf >> 10) + 1), cy = (uint32_t)((Yf >> 10) + 1);   // framed column / row of tap (0, 0)
+    const bool inside = cx <= (uint32_t)S && cy <= (uint32_t)S;                     // sx, sy in [-1, S - 1]
+    const uint32_t ccx = min(cx, (uint32_t)S), ccy = min(cy, (uint32_t)S);
+    const uint32_t p0 = (uint32_t)(lds64(rows_s + 8u * ccy) >> ccx) & 3u, p1 = (uint32_t)(lds64(rows_s + 8u * ccy + 8u) >> ccx) & 3u;
+    const uint32_t lw = lds32(lut_s + (((p0 | (p1 << 2)) << 5) | (((uint32_t)Yf >> 5) & 31u)) * 4u);
+    dst[idx] = inside ? (uint8_t)((lw >> (((uint32_t)Xf >> 5) & 31u)) & 1u) : (uint8_t)1;     // env.py:687-689: > 0.9; outside: the border
+  }
+}
+
 // ---- scene generator: thread per episode, counter-based draws, fp64 in the host generator's
 //      operation order (this unit is compiled without FMA contraction), narrowed to fp32 at the end ----------
 __device__ __forceinline__ unsigned long long gen_mix(unsigned long long x) {
@@ -1929,6 +2041,11 @@ int ebc_launch_step(ebc_sim *s, bool fused_orca, const int32_t *action_idx, cons
 int ebc_launch_grid_map(ebc_sim *s, const ebc_grid_map *map, uint8_t *out, cudaStream_t stream) {
   const int S = map->size;
   const size_t smem = (size_t)(((S + 2) * (S + 2) + 15) & ~15) + 4 * sizeof(int) * (size_t)S;
+  if (S <= 62 && !getenv("EBC_GRID_MAP_BYTES")) {      // a framed row fits one 64-bit word (EBC_GRID_MAP_BYTES=1: the general kernel)
+    const uint32_t magic = (uint32_t)((0x100000000ull + (unsigned)S - 1u) / (unsigned)S);   // idx / S = umulhi(idx, magic): exact for idx * S < 2^32
+    grid_map_bits_kernel<<<s->cfg.n_episodes, 256, 0, stream>>>(s->cfg, s->st, S, magic, out);
+    return ebc_check_launch(s, "grid_map_bits_kernel");
+  }
   grid_map_kernel<<<s->cfg.n_episodes, 256, smem, stream>>>(s->cfg, s->st, S, out);
   return ebc_check_launch(s, "grid_map_kernel");
 }

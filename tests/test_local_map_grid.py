@@ -145,7 +145,7 @@ def test_gpu_grid_map_matches_reference_and_oracle(case):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("submap", [5.0, 6.0, 3.1])
+@pytest.mark.parametrize("submap", [5.0, 6.0, 3.1, 7.0])      # 7 m = 70 cells: the general (byte-grid) kernel; the others fit 64-bit rows
 def test_gpu_grid_map_large_batch(submap):
     """4096 episodes with 0..6 rectangles each and random poses (a third of them with the window off the map's
     edge): kernel against the oracle, and an episode's map does not depend on its neighbours (permutation)."""
@@ -157,6 +157,12 @@ def test_gpu_grid_map_large_batch(submap):
     perm = np.random.default_rng(1).permutation(4096)
     got_p = _run_batch([rects[i] for i in perm], poses[perm], submap, "cuda:0", None)
     assert np.array_equal(got_p, got[perm])
+    # both kernels (64-bit rows + lookup table for windows of <= 62 cells, byte grid + integer taps otherwise) agree
+    os.environ["EBC_GRID_MAP_BYTES"] = "1"
+    try:
+        assert np.array_equal(_run_batch(rects, poses, submap, "cuda:0", None), got)
+    finally:
+        del os.environ["EBC_GRID_MAP_BYTES"]
 
 
 @pytest.mark.gpu
