@@ -61,6 +61,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     if (++spins > (1u << 22)) __trap();
   }
 }
+// the same on a 32-bit shared-memory address (no generic pointer to re-form: a generic pointer to shared memory
+// costs an S2UR SR_CgaCtaId + LEA wherever the compiler re-materialises it)
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0, ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_arrive_s(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // ---- async (bulk) copy global -> shared, completion on an mbarrier (UBLKCP) -----------------------
@@ -273,10 +291,10 @@ template <> struct Fmt<2> {
 };
 
 // Store 8 consecutive k-elements (k0 % 8 == 0) of row `row` into the NSPLIT A images.
-// a_base: shared memory, image s at a_base + s * image_bytes.  Parts are peeled two values at a time:
+// a_base: 32-bit shared-memory address, image s at a_base + s * image_bytes.  Parts are peeled two values at a time:
 // p = round16(v), v -= float(p) (exact), repeat.
 template <int NSPLIT>
-__device__ __forceinline__ void store_a8(uint8_t *a_base, uint32_t image_bytes, int row, int k0, const float (&v)[8]) {
+__device__ __forceinline__ void store_a8(uint32_t a_base, uint32_t image_bytes, int row, int k0, const float (&v)[8]) {
   float r[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) r[i] = v[i];
@@ -293,7 +311,10 @@ __device__ __forceinline__ void store_a8(uint8_t *a_base, uint32_t image_bytes, 
         r[2 * i + 1] -= Fmt<NSPLIT>::hi(pk);
       }
     }
-    *reinterpret_cast<uint4 *>(a_base + (size_t)s * image_bytes + (size_t)(k0 >> 3) * A_CHUNK_BYTES + (size_t)row * 16) = w;
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_base + (uint32_t)s * image_bytes + (uint32_t)(k0 >> 3) * A_CHUNK_BYTES +
+                                                                     (uint32_t)row * 16u),
+                 "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w)
+                 : "memory");
   }
 }
 

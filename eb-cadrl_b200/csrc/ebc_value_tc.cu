@@ -110,6 +110,7 @@ __device__ __forceinline__ float relu_nan(float x) {
 template <int NSPLIT>
 struct Pipe {
   uint64_t *full, *empty, *acc_bar, *a_bar, *kbar, *afree;
+  uint32_t acc_s, abar_s, kbar_s, afree_s;   // the crew's barriers as 32-bit shared-memory addresses
   uint8_t *wbuf;
   const uint8_t *wpack;      // packed weights (global)
   int n_stage_slabs;         // slabs per tile
@@ -266,7 +267,7 @@ struct Pipe {
 
   // ---- crew -------------------------------------------------------------------------------------------
   __device__ void wait_acc() {
-    mbar_wait(acc_bar, acc_phase);     // (a busy test_wait spin instead of the suspended try_wait: 0.5 % slower, measured)
+    mbar_wait_s(acc_s, acc_phase);     // (a busy test_wait spin instead of the suspended try_wait: 0.5 % slower, measured)
     acc_phase ^= 1u;
     tc_fence_after();
     stamp();
@@ -275,15 +276,15 @@ struct Pipe {
     stamp();         // after this thread's A-operand stores / TMEM reads
     fence_proxy_async();               // generic-proxy smem writes -> async proxy (UMMA)
     tc_fence_before();                 // this thread's tcgen05.ld's are ordered before the arrive
-    mbar_arrive(a_bar);
+    mbar_arrive_s(abar_s);
   }
   // block b of the A operand may be overwritten: the MMAs of the last commit_k stage that read it are done
-  __device__ __forceinline__ void wait_free(int b) { mbar_wait(&afree[b], (f_phase >> b) & 1u); }
+  __device__ __forceinline__ void wait_free(int b) { mbar_wait_s(afree_s + 8u * (uint32_t)b, (f_phase >> b) & 1u); }
   // hand block b of the A operand (this thread's row) to the MMA warp
   __device__ __forceinline__ void publish(int b) {
     fence_proxy_async();
     tc_fence_before();
-    mbar_arrive(&kbar[b]);
+    mbar_arrive_s(kbar_s + 8u * (uint32_t)b);
   }
 };
 
@@ -331,7 +332,7 @@ struct EpiExtra {
 
 template <int NSPLIT, bool GSUM>
 __device__ __forceinline__ void epi_to_a(Pipe<NSPLIT> &pipe, uint32_t tmem_row, int cg, int col0, int ncols, int n_real,
-                                         const float *__restrict__ bias, uint8_t *a_base, int row, bool chase,
+                                         const float *__restrict__ bias, uint32_t a_base, int row, bool chase,
                                          int n_free, const EpiExtra &x = EpiExtra()) {
   const int n = x.n, row_cnt = x.row_cnt, g_ld = x.g_ld, g_states = x.g_states, g_sid = x.g_sid, g_rin = x.g_rin;
   const int g_seg = x.g_seg, g_part = x.g_part, one_col = x.one_col;
@@ -445,7 +446,7 @@ __device__ __forceinline__ void epi_to_a(Pipe<NSPLIT> &pipe, uint32_t tmem_row, 
 // mean of its own state, so [H1 | G] . [W_local | W_global]^T accumulates in one TMEM accumulator (sarl.py:51-63).
 template <int NSPLIT>
 __device__ __forceinline__ void gx_to_a(Pipe<NSPLIT> &pipe, const float *G, int g_ld, int state, int cg, int h1d, int h1p,
-                                        uint8_t *a_base, int row, int n_free, int n_parts, int part_stride) {
+                                        uint32_t a_base, int row, int n_free, int n_parts, int part_stride) {
   for (int c = 16 * cg; c < h1p; c += 16 * NCG) {
     float v[16];
     const float4 *g4 = reinterpret_cast<const float4 *>(G + state * g_ld + c);   // one address per state: broadcast
@@ -507,6 +508,8 @@ __device__ __forceinline__ void pipe_init(Pipe<NSPLIT> &pipe, uint8_t *smem, con
   pipe.full = bars; pipe.empty = bars + ST; pipe.acc_bar = bars + 2 * ST; pipe.a_bar = bars + 2 * ST + 1;
   pipe.kbar = bars + 2 * ST + 2; pipe.afree = pipe.kbar + NKB;
   pipe.ready = reinterpret_cast<uint32_t *>(pipe.afree + NKB);
+  pipe.acc_s = smem_u32(pipe.acc_bar); pipe.abar_s = smem_u32(pipe.a_bar);
+  pipe.kbar_s = smem_u32(pipe.kbar); pipe.afree_s = smem_u32(pipe.afree);
   pipe.issued = 0; pipe.seen = 0;
   static_assert((2 * ST + 3 + 2 * NKB) * 8 <= 512, "barrier region");
   pipe.f_phase = 0;
@@ -788,7 +791,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
     auto stage_x = [&](int buf, long long t) {
       const int tstates = (int)min((long long)ts, p.n_states - t * ts);
       if (tid < MAX_STATES) cnt2[buf][tid] = cnt_next;
-      store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, row, 8 * cg, xu);
+      store_a8<NSPLIT>(a_smem, Cfg<NSPLIT>::A_IMAGE, row, 8 * cg, xu);
       if (cg == 0 && my_row && my_sid < tstates && my_rin == 0) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)        // (constant indices: xu stays in registers)
@@ -819,7 +822,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
           EpiExtra ex;
           ex.one_col = P.st[ST_L1A + h].bias_k;     // this half is K chunk h of mlp1.2
           epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, W.acc_col, W.np, W.n_real, W.bias_k >= 0 ? nullptr : P.bias[0] + W.n_lo,
-                                  A, row, true, n_free, ex);
+                                  a_smem, row, true, n_free, ex);
           if (h) pipe.f_phase ^= low_bits(n_free);
           pipe.stamp();
         }
@@ -839,9 +842,9 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
           ex.n = n; ex.row_cnt = cnt[st_of_row]; ex.g_out = G; ex.g_ld = g_ld; ex.g_states = ts;
           ex.g_sid = my_sid; ex.g_rin = my_rin; ex.g_seg = my_row ? my_sid : -1 - (row >> 5);
           ex.g_part = n <= 32 ? 0 : (row >> 5) % wps;
-          epi_to_a<NSPLIT, true>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, b_in ? nullptr : P.bias[1], A, row, true, 0, ex);
+          epi_to_a<NSPLIT, true>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, b_in ? nullptr : P.bias[1], a_smem, row, true, 0, ex);
         } else {
-          epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, b_in ? nullptr : P.bias[1], A, row, true, 0, ex);
+          epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, b_in ? nullptr : P.bias[1], a_smem, row, true, 0, ex);
         }
       }
       pipe.stamp();
@@ -849,10 +852,10 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
       if (P.with_global) {
         if (n <= 32) {
           __syncwarp();    // G[., state] for this thread's blocks was written by this warp
-          gx_to_a<NSPLIT>(pipe, G, g_ld, st_of_row, cg, h1d, 16 * h1b, A, row, h1b, 1, 0);
+          gx_to_a<NSPLIT>(pipe, G, g_ld, st_of_row, cg, h1d, 16 * h1b, a_smem, row, h1b, 1, 0);
         } else {
           crew_sync();     // the partial means of the state's other warps
-          gx_to_a<NSPLIT>(pipe, G, g_ld, st_of_row, cg, h1d, 16 * h1b, A, row, h1b, wps, ts * g_ld);
+          gx_to_a<NSPLIT>(pipe, G, g_ld, st_of_row, cg, h1d, 16 * h1b, a_smem, row, h1b, wps, ts * g_ld);
         }
         pipe.f_phase ^= low_bits(h1b);                  // attention.0 (local half) released every H1 block
         pipe.stamp();
@@ -863,7 +866,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
         EpiExtra ex;
         ex.one_col = P.st[ST_L3].bias_k;
         ex.wait_first = true;
-        epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, S.bias_k >= 0 ? nullptr : P.bias[2], A, row, true,
+        epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, S.bias_k >= 0 ? nullptr : P.bias[2], a_smem, row, true,
                                 h1b, ex);
         pipe.f_phase ^= low_bits(h1b);                  // attention.0's last K chunk released its blocks
       }
@@ -876,7 +879,7 @@ __global__ void __launch_bounds__(NT, 1) tc_entity_kernel(const TcEntityParams p
         const int n_free = P.st[ST_L3].ksteps;
         EpiExtra ex;
         ex.one_col = P.st[ST_L5].bias_k;
-        epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, S.bias_k >= 0 ? nullptr : P.bias[4], A, row, true,
+        epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, S.bias_k >= 0 ? nullptr : P.bias[4], a_smem, row, true,
                                 n_free, ex);
         pipe.f_phase ^= low_bits(n_free);
       }
@@ -1158,12 +1161,12 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
 #pragma unroll
       for (int i = 0; i < XC; ++i) {
         const int k0 = 8 * (cg + NCG * i);
-        if (k0 < kp) store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, row, k0, xu[i]);
+        if (k0 < kp) store_a8<NSPLIT>(a_smem, Cfg<NSPLIT>::A_IMAGE, row, k0, xu[i]);
       }
       for (int c = cg + NCG * XC; 8 * c < kp; c += NCG) {      // joint rows wider than 128 columns
         float u[8];
         load_chunk(t, c, u);
-        store_a8<NSPLIT>(A, Cfg<NSPLIT>::A_IMAGE, row, 8 * c, u);
+        store_a8<NSPLIT>(a_smem, Cfg<NSPLIT>::A_IMAGE, row, 8 * c, u);
       }
       pipe.signal_a();
     };
@@ -1183,7 +1186,7 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
           EpiExtra ex;
           ex.one_col = P.st[ST_L1A + h].bias_k;
           epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, W.acc_col, W.np, W.n_real, W.bias_k >= 0 ? nullptr : P.bias[0] + W.n_lo,
-                                  A, row, true, n_free, ex);
+                                  a_smem, row, true, n_free, ex);
           if (h) pipe.f_phase ^= low_bits(n_free);
         }
       }
@@ -1193,7 +1196,7 @@ __global__ void __launch_bounds__(NT, 1) tc_mlp3_kernel(const TcMlp3Params p) {
         const bool b_in = S.bias_k >= 0 || (P.n_wide > 1 && P.st[ST_L1B].bias_k >= 0);
         EpiExtra ex;
         ex.one_col = P.st[ST_L2].bias_k;
-        epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, b_in ? nullptr : P.bias[1], A, row, true, 0, ex);
+        epi_to_a<NSPLIT, false>(pipe, tmem_row, cg, S.acc_col, S.np, S.n_real, b_in ? nullptr : P.bias[1], a_smem, row, true, 0, ex);
       }
       pipe.stamp();
       if (more) load_x(tile + gridDim.x);
