@@ -89,6 +89,57 @@ def test_info_and_state_layout():
     assert info.from_code(0, 0.0, (1, 2, 3)).dist_to_goal is None
 
 
+def _kin_agent(kinematics, dt):
+    from simulator.agents.agent import Agent
+    cfg = configparser.RawConfigParser()
+    cfg.add_section("a")
+    for k, v in (("visible", "true"), ("v_pref", "1"), ("radius", "0.3"), ("policy", "none"), ("sensor", "coordinates")):
+        cfg.set("a", k, v)
+    agent = Agent(cfg, "a")
+    agent.set_policy(type("P", (), {"kinematics": kinematics})())
+    agent.time_step = dt
+    return agent
+
+
+def test_agent_kinematics_match_reference():
+    """Host-side kinematics of the plugin classes against the unmodified reference's Agent on 256 random
+    poses x 3 action kinds (tests/golden/agent_kinematics.npz, written by make_agent_golden.py from
+    /root/reference/simulator/agents/agent.py:80-93,164-234).  Bit-exact: same float64 operations in the same order."""
+    from simulator.utils.action import ActionRot, ActionXY, ActionXYRot
+    from simulator.utils.utils import AgentType
+    g = np.load(os.path.join(ob.GOLDEN, "agent_kinematics.npz"))
+    pose, act, dt = g["pose"], g["act"], float(g["dt"])
+    for kind in ("xy", "rot", "xyrot"):
+        agent = _kin_agent("holonomic" if kind == "xy" else "unicycle", dt)
+        for i in range(len(pose)):
+            a = {"xy": ActionXY(act[i, 0], act[i, 1]), "rot": ActionRot(act[i, 0], act[i, 2]),
+                 "xyrot": ActionXYRot(act[i, 0], act[i, 1], act[i, 2])}[kind]
+            agent.set(*pose[i, 0:7], radius=pose[i, 7], v_pref=pose[i, 8], agent_type=AgentType.ADULT)
+            assert bool(agent.reached_destination()) == bool(g[kind + "_reach"][i])
+            assert tuple(agent.compute_position(a, dt)) == tuple(g[kind + "_pos"][i])
+            if kind != "xy":
+                assert tuple(agent.compute_velocity(a)) == tuple(g[kind + "_vel"][i])
+            if kind != "xyrot":
+                o = agent.get_next_observable_state(a)
+                assert (o.px, o.py, o.vx, o.vy, o.radius) == tuple(g[kind + "_next"][i]) and o.obj_type == AgentType.ADULT
+            agent.step(a)
+            if kind != "xyrot":
+                assert (agent.px, agent.py, agent.vx, agent.vy, agent.theta) == tuple(g[kind + "_step"][i])
+            else:   # the reference's step() raises on ActionXYRot (reads action.v); here it follows compute_velocity
+                th = (pose[i, 6] + act[i, 2]) % (2 * np.pi)
+                assert agent.theta == th and (agent.px, agent.py) == tuple(g["xyrot_pos"][i])
+                assert agent.vx == act[i, 0] * np.cos(th) - act[i, 1] * np.sin(th)
+    holo = _kin_agent("holonomic", dt)
+    holo.set(0, 0, 1, 1, 0, 0, 0)
+    with pytest.raises(AssertionError):                      # agent.py:158-162
+        holo.compute_position(ActionRot(1.0, 0.1), dt)
+    d = holo.get_state_dict()
+    other = _kin_agent("holonomic", dt)
+    other.set_from_state_dict(d)
+    assert other.get_full_state()._tuple() == holo.get_full_state()._tuple()
+    assert other.get_observable_state()._tuple() == holo.get_observable_state()._tuple()
+
+
 def _rank_main(rank, world, port, tmp):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
