@@ -161,8 +161,9 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "tensor_tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
-def cpu_oracle_rate(shape, cfg, weights, episodes, steps, threads, full_loop=True, kin="holonomic"):
-    """agent-steps/s of the CPU oracle on `episodes` episodes of the same workload."""
+def cpu_oracle_rate(shape, cfg, weights, episodes, steps, threads, full_loop=True, kin="holonomic", min_seconds=None):
+    """agent-steps/s of the CPU oracle on `episodes` episodes of the same workload; with `min_seconds`, `steps` is the
+    upper bound and the loop ends after the first step that passes that much wall time.  Returns (rate, seconds, steps)."""
     import oracle_backend as ob
     from ebc import synth
     from ebc.actions import build_action_space
@@ -174,14 +175,18 @@ def cpu_oracle_rate(shape, cfg, weights, episodes, steps, threads, full_loop=Tru
     sim.set_weights(weights)
     synth.load(sim, synth.generate(shape, np.arange(episodes)))
     t0 = time.perf_counter()
+    done = 0
     for _ in range(steps):
         if full_loop:
             sim.decide()
             sim.step(action_idx=sim.argmax)
         else:
             sim.step(action_idx=torch.zeros(episodes, dtype=torch.int32), fused_orca=True)
+        done += 1
+        if min_seconds is not None and time.perf_counter() - t0 >= min_seconds:
+            break
     dt = time.perf_counter() - t0
-    return episodes * (shape.H + 1) * steps / dt, dt
+    return episodes * (shape.H + 1) * done / dt, dt, done
 
 
 def run_reference(args, rank, world):
@@ -198,7 +203,7 @@ def run_reference(args, rank, world):
     steps = max(1, args.steps)
     for _ in range(min(args.warmup, 1)):
         cpu_oracle_rate(shape, cfg, weights, sample, 1, threads)
-    rate, dt = cpu_oracle_rate(shape, cfg, weights, sample, steps, threads)
+    rate, dt, _ = cpu_oracle_rate(shape, cfg, weights, sample, steps, threads)
     desc = "%d episodes x %d full steps (decision over 81 actions + env.step) of %s" % (sample, steps, shape.name)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
@@ -654,9 +659,11 @@ def main():
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         sample = max(4 * threads, 32)
-        rate, dt = cpu_oracle_rate(shape, cfg, weights, sample, 2, threads, kin=cfg.robot_kinematics)
+        # a bounded sample of the same loop: whole steps until >= 10 s of wall time (<= 64 steps), every host thread busy
+        rate, dt, n_cpu = cpu_oracle_rate(shape, cfg, weights, sample, 64, threads, kin=cfg.robot_kinematics, min_seconds=10.0)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "%d episodes x 2 full steps of %s, %.1f s" % (sample, shape.name, dt)}
+                                "sample": "%d episodes x %d full steps (decision over %d actions + env.step) of %s, %.1f s on %d threads"
+                                          % (sample, n_cpu, N_ACTIONS, shape.name, dt, threads)}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
