@@ -656,7 +656,7 @@ def main():
         "e2e": {"value": total_eps * (H + 1) / (e2e_s / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps},
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:           # rank 0 at N = 1 only
         threads = os.cpu_count() or 1
         sample = max(4 * threads, 32)
         # a bounded sample of the same loop: whole steps until >= 10 s of wall time (<= 64 steps), every host thread busy
