@@ -30,6 +30,10 @@ def parse_arguments(argv=None):
     p.add_argument("--start", type=int, default=None)
     p.add_argument("--end", type=int, default=None)
     p.add_argument("--batch", type=int, default=256, help="episodes advanced at once per GPU")
+    # rendering flags of the reference (rl/test.py:32,36-37): parsed so that its command lines keep working
+    p.add_argument("--visualize", default=False, action="store_true")
+    p.add_argument("--video_file", type=str, default=None)
+    p.add_argument("--traj", default=False, action="store_true")
     return p.parse_args(argv)
 
 
@@ -74,6 +78,13 @@ def main(argv=None):
         seeds = [BatchedEnv.COUNTER_OFFSET[args.phase] + args.test_case]
     else:
         seeds = [BatchedEnv.COUNTER_OFFSET[args.phase] + i for i in range(ec.getint("env", "test_size"))]
+    if args.visualize:
+        raise NotImplementedError("--visualize: rendering (simulator/utils/render.py) is outside the hot path (SURVEY §2 #18); "
+                                  "run without it for the per-episode statistics, --csv for one row per episode")
+    if args.square:                                      # rl/test.py:100-103
+        ec.set("sim", "test_sim_adult", "square_crossing")
+    if args.circle:
+        ec.set("sim", "test_sim_adult", "circle_crossing")
     env = BatchedEnv(ec, policy, min(args.batch, len(seeds)), device)
     explorer = Explorer(env, None, device, gamma=policy.gamma)
     rows = []
