@@ -157,7 +157,7 @@ def measured_peaks():
     if os.path.exists(path):
         d = json.load(open(path))
         return {"hbm_gbs": d["hbm_gbs"], "tensor_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
-                "tensor_tflops_burst": d["bf16_tflops"],
+                "tensor_tflops_burst": d.get("bf16_tflops"),
                 "source": "MEASURED_PEAKS.json (bf16 sustained, copy bandwidth)"}
     return {"hbm_gbs": 6650.0, "tensor_tflops": 1400.0, "tensor_tflops_burst": None, "source": "fallback (B200_PROFILING.md)"}
 
